@@ -1,0 +1,202 @@
+/*
+ * pnb200.h -- C ABI of libpnb200.so: a B200 (sm_100a) native fixed-radius neighbourhood search
+ * that is a drop-in for the hot path of trixi-framework/PointNeighbors.jl v0.6.7.
+ *
+ * The reference has no FFI (it is pure Julia, dispatching on the coordinate array type,
+ * src/util.jl:81-83, src/gpu.jl:10-35).  Each entry point below names the reference interface
+ * it replaces (file:line relative to the reference checkout); INTEGRATION.md shows the Julia
+ * `ccall` glue and the Python `ctypes` binding that sit on top.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw device pointers, sizes; no torch / CUDA C++ types.
+ *   - coordinates: NDIMS x N column-major (Julia) == N x NDIMS row-major (C): xyzxyz...
+ *     (src/neighborhood_search.jl:25-26), NDIMS in {1,2,3}, element type float32.
+ *   - every function returns a pnb_status; pnb_last_error() returns the message, which is the
+ *     reference's own error text where the reference raises one.
+ *   - `index_base` (0 or 1) selects the numbering of point ids in everything that is exported
+ *     or imported (Julia passes 1, C/Python pass 0).  Internally ids are 0-based int32.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     synchronous with respect to the host unless the name ends in _async: the reference
+ *     blocks in KernelAbstractions.synchronize after every launch (src/util.jl:166-170).
+ *   - device pointers must belong to the CUDA device that was current when the handle was
+ *     created.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ *     PNB_ERR_CUDA.
+ */
+#ifndef PNB200_H
+#define PNB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB200_VERSION 100 /* 0.1.0 */
+
+typedef enum pnb_status {
+    PNB_OK = 0,
+    PNB_ERR_DOMAIN = 1,    /* "particle coordinates are NaN or outside the domain bounds of the cell list" (src/cell_lists/full_grid.jl:211) */
+    PNB_ERR_ARG = 2,       /* ArgumentError of a constructor (src/nhs_grid.jl:81-124, src/cell_lists/full_grid.jl:52-59) */
+    PNB_ERR_LIST_FULL = 3, /* "cell list is full. Use a larger `max_points_per_cell`." (src/vector_of_vectors.jl:119) */
+    PNB_ERR_BOUNDS = 4,    /* BoundsError of the safe sweep: a query point's 3^d stencil leaves the grid (src/nhs_grid.jl:530-532) */
+    PNB_ERR_CUDA = 5,      /* CUDA runtime failure / no device */
+    PNB_ERR_STATE = 6      /* call order violated (e.g. sweep before initialize!) */
+} pnb_status;
+
+typedef struct pnb_grid pnb_grid;   /* GridNeighborhoodSearch{NDIMS} + FullGridCellList (+ PeriodicBox) */
+typedef struct pnb_nlist pnb_nlist; /* PrecomputedNeighborhoodSearch neighbour lists */
+
+int pnb_version(void);
+/* thread-local; valid until the next failing call on this thread */
+const char *pnb_last_error(void);
+/* number of CUDA devices visible; 0 when there is none (then nothing else works) */
+int pnb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side grid arithmetic (pure function, no device needed)
+ *   replaces: FullGridCellList(; min_corner, max_corner, search_radius)   src/cell_lists/full_grid.jl:48-82
+ *             GridNeighborhoodSearch{NDIMS}(; search_radius, periodic_box, cell_list)  src/nhs_grid.jl:77-129
+ *             PeriodicBox(; min_corner, max_corner)                      src/neighborhood_search.jl:129-143
+ * box_min/box_max == NULL: no periodic box.  Outputs (any may be NULL):
+ *   padded_min/padded_max[ndims] : cell_list.min_corner / max_corner after the 1.001*r padding
+ *   grid_size[ndims]             : n_cells_per_dimension of the allocated (padded) grid
+ *   n_cells[ndims]               : nhs.n_cells (-1 when not periodic)
+ *   cell_size[ndims]             : nhs.cell_size
+ * Errors: PNB_ERR_ARG with the reference's ArgumentError text.
+ * ------------------------------------------------------------------------------------------- */
+pnb_status pnb_grid_params_f32(int ndims, float search_radius, const float *min_corner,
+                               const float *max_corner, const float *box_min, const float *box_max,
+                               float *padded_min, float *padded_max, int64_t *grid_size,
+                               int64_t *n_cells, float *cell_size);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid handle
+ *   replaces: the GridNeighborhoodSearch / FullGridCellList objects after Adapt.adapt(backend, nhs)
+ *             (src/gpu.jl:10-12) and copy_neighborhood_search (src/nhs_grid.jl:640-649).
+ * min_corner/max_corner are the USER corners (unpadded).  search_radius < eps() gives the legal
+ * "template / unused" search whose build only empties the cell list (src/nhs_grid.jl:263-267).
+ * ------------------------------------------------------------------------------------------- */
+pnb_status pnb_grid_create_f32(int ndims, float search_radius, const float *min_corner,
+                               const float *max_corner, const float *box_min, const float *box_max,
+                               pnb_grid **out);
+void pnb_grid_destroy(pnb_grid *g);
+int64_t pnb_grid_total_cells(const pnb_grid *g);
+int64_t pnb_grid_n_points(const pnb_grid *g); /* points in the cell list after the last build */
+
+/* initialize!(nhs, x, y; eachindex_y) / update!(nhs, x, y; points_moving = (_, true), eachindex_y)
+ *   src/nhs_grid.jl:220-225, 255-292, 470-477; src/cell_lists/full_grid.jl:96-139
+ * Device counting sort: cell index + histogram, decoupled-lookback scan, scatter, per-cell id
+ * sort (deterministic: ids ascending inside a cell) fused with the cell-order copy of the
+ * coordinates.  y: device, n x ndims.  eachindex_y: device int32 ids (index_base) or NULL = all.
+ * Returns PNB_ERR_DOMAIN if any listed point is NaN / outside the padded grid. */
+pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n, const int32_t *eachindex_y,
+                              int64_t n_idx, int index_base, void *stream);
+
+/* cell_coords + cell_index of arbitrary points (src/nhs_grid.jl:622-628, full_grid.jl:84-94,157-161):
+ * out[i] = 0-based linear cell index, or -1 when the cell is outside 2:(size-1). */
+pnb_status pnb_point_cells_f32(const pnb_grid *g, const float *x, int64_t n, int32_t *out_linear,
+                               void *stream);
+
+/* The cell list in CSR form: cell_start[C+1] (int32 offsets), cell_points[n_points] (ids + index_base).
+ * This replaces cell_list.cells (DynamicVectorOfVectors, src/vector_of_vectors.jl:3-31). */
+pnb_status pnb_grid_export_csr(const pnb_grid *g, int32_t *cell_start, int32_t *cell_points,
+                               int index_base, void *stream);
+/* The cell list in the reference's own layout: backend[max_points_per_cell x C] column-major int32,
+ * lengths[C] int32.  PNB_ERR_LIST_FULL if a cell holds more than max_points_per_cell points. */
+pnb_status pnb_grid_export_dvov(const pnb_grid *g, int32_t *backend, int32_t *lengths,
+                                int32_t max_points_per_cell, int index_base, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused sweeps = foreach_point_neighbor(f, x, y, nhs; points)  (src/neighborhood_search.jl:183-201,
+ * src/nhs_grid.jl:519-575) with f one of the benchmarked closures.
+ * x: device nx x ndims (points looped over), y: device n x ndims (the array the grid was built
+ * from).  points: device int32 ids (index_base) or NULL = all of x.
+ * When x == y (same pointer and size) and points == NULL the cell-ordered fast path runs; it
+ * uses the coordinates snapshotted by the last pnb_grid_build (call update! after moving y, as
+ * the reference requires, src/neighborhood_search.jl:161-164).
+ * Returns PNB_ERR_BOUNDS if a query point's stencil leaves the grid.
+ * ------------------------------------------------------------------------------------------- */
+
+/* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */
+pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
+                                   int64_t n, const int32_t *points, int64_t n_points,
+                                   int index_base, int64_t *out, void *stream);
+
+/* benchmarks/n_body.jl:29-51: dv (nx x ndims) zeroed, then for every pair with
+ * distance >= sqrt(eps): dv[:, i] += -G * mass[j] * pos_diff / distance^3 */
+pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, const float *y, int64_t n,
+                         const int32_t *points, int64_t n_points, int index_base,
+                         const float *mass, float G, float *dv, void *stream);
+
+/* WCSPH continuity + momentum pair interaction, TrixiParticles.interact! as configured by
+ * benchmarks/smoothed_particle_hydrodynamics.jl:45-102 (WendlandC2, ContinuityDensity,
+ * ArtificialViscosityMonaghan, DensityDiffusionMolteniColagrossi, StateEquationCole exponent 1).
+ * v: (ndims+1) per point = velocity, density; dv: same shape, zeroed then accumulated. */
+typedef struct pnb_wcsph_params {
+    float smoothing_length;  /* h = search_radius / 2 */
+    float sound_speed;       /* c */
+    float alpha, beta, epsilon; /* Monaghan viscosity, epsilon = 0.01 */
+    float delta;             /* Molteni-Colagrossi */
+    float kernel_norm;       /* sigma_d / h^d (WendlandC2: 21/(16 pi h^3) in 3D, 7/(4 pi h^2) in 2D) */
+} pnb_wcsph_params;
+pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
+                                  int64_t n, const int32_t *points, int64_t n_points,
+                                  int index_base, const float *v_x, const float *v_y,
+                                  const float *mass_x, const float *mass_y,
+                                  const float *pressure_x, const float *pressure_y,
+                                  const pnb_wcsph_params *params, float *dv, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Neighbour lists = PrecomputedNeighborhoodSearch (src/nhs_precomputed.jl:67-277)
+ * ------------------------------------------------------------------------------------------- */
+/* initialize_neighbor_lists! (src/nhs_precomputed.jl:187-206): count pass, scan, fill pass and a
+ * per-list sort (sort != 0 -> ascending ids, the deterministic result of sorteach!,
+ * src/vector_of_vectors.jl:177-212).  The lists are a device CSR owned by the handle. */
+pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t nx, const float *y, int64_t n,
+                               int sort, pnb_nlist **out, void *stream);
+void pnb_nlist_destroy(pnb_nlist *l);
+int64_t pnb_nlist_n_points(const pnb_nlist *l);
+int64_t pnb_nlist_n_pairs(const pnb_nlist *l);
+/* offsets[nx+1] int64, ids[n_pairs] int32 (+ index_base) */
+pnb_status pnb_nlist_export_csr(const pnb_nlist *l, int64_t *offsets, int32_t *ids, int index_base,
+                                void *stream);
+/* reference layout (src/vector_of_vectors.jl:3-31): lengths[nx]; backend max_neighbors x nx
+ * column-major, or its transpose nx x max_neighbors (transpose_backend = true, :18-23).
+ * Unused slots are set to typemax(Int32) like the GPU sorteach! (:200-204).
+ * PNB_ERR_LIST_FULL if a list is longer than max_neighbors. */
+pnb_status pnb_nlist_export_dvov(const pnb_nlist *l, int32_t *backend, int32_t *lengths,
+                                 int32_t max_neighbors, int transposed, int index_base,
+                                 void *stream);
+/* sweep without radius test (src/nhs_precomputed.jl:210-247): what the closure receives, in
+ * list order: pos_diff[n_pairs x ndims], distance[n_pairs] (either may be NULL). */
+pnb_status pnb_nlist_pairs_f32(const pnb_nlist *l, const pnb_grid *g, const float *x,
+                               const float *y, float *pos_diff, float *distance, void *stream);
+/* TLSPH deformation gradient over the lists (TrixiParticles.calc_deformation_grad!, called at
+ * benchmarks/smoothed_particle_hydrodynamics.jl:142): neighbours and kernel gradient on the
+ * initial coordinates X0, current coordinates xcur; L = kernel correction matrix (ndims x ndims
+ * column-major per point); F same layout. */
+pnb_status pnb_tlsph_deformation_grad_f32(const pnb_nlist *l, const pnb_grid *g, const float *X0,
+                                          const float *xcur, const float *mass, const float *rho0,
+                                          const float *L, float smoothing_length,
+                                          float kernel_norm, float *F, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device memory helpers for hosts without a CUDA binding (the Julia glue's B200Array;
+ * replaces Adapt.adapt(backend, array), src/gpu.jl, benchmarks/run_benchmarks.jl:97-99)
+ * ------------------------------------------------------------------------------------------- */
+pnb_status pnb_malloc(void **dev_ptr, int64_t bytes);
+pnb_status pnb_free(void *dev_ptr);
+pnb_status pnb_malloc_host(void **host_ptr, int64_t bytes); /* pinned */
+pnb_status pnb_free_host(void *host_ptr);
+pnb_status pnb_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+pnb_status pnb_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
+pnb_status pnb_memset(void *dev_ptr, int value, int64_t bytes, void *stream);
+pnb_status pnb_stream_synchronize(void *stream);
+
+/* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
+int64_t pnb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNB200_H */

@@ -1,0 +1,159 @@
+// common.cuh -- shared device/host definitions of libpnb200 (sm_100a only).
+//
+// Arithmetic contract: everything that decides a cell or a neighbour set
+// is written with explicit round-to-nearest intrinsics (__fsub_rn, __fmul_rn, __fadd_rn,
+// __fdiv_rn, __fsqrt_rn).  These are never contracted into FMAs and never replaced by
+// approximate sequences, whatever flags the translation unit is compiled with.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pnb200.h"
+
+namespace pnb {
+
+// Plain-old-data copy of GridNeighborhoodSearch + FullGridCellList (+ PeriodicBox) scalars,
+// passed to kernels by value.  (reference: src/nhs_grid.jl:67-75, src/cell_lists/full_grid.jl:30-35)
+struct GridP {
+    int ndims;
+    int periodic;
+    float r;           // search_radius
+    float r2;          // r * r, rounded once (src/nhs_grid.jl:555)
+    float minc[3];     // padded min corner
+    float cs[3];       // cell_size
+    int gs[3];         // allocated grid size (1 for unused dims)
+    int nc[3];         // periodic cells per dim (-1 if not periodic)
+    float bsize[3];    // periodic box size
+    float wrap_d2;     // d2 below this can never be changed by the periodic fix (see periodic_fix)
+    int total_cells;
+};
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+pnb_status cuda_fail(cudaError_t e, const char *what);
+extern int64_t g_launch_count;
+
+#define PNB_CUDA(expr)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (expr);                                        \
+        if (e__ != cudaSuccess) return ::pnb::cuda_fail(e__, #expr);     \
+    } while (0)
+
+#define PNB_LAUNCHED()                                                   \
+    do {                                                                 \
+        ::pnb::g_launch_count++;                                         \
+        cudaError_t e__ = cudaGetLastError();                            \
+        if (e__ != cudaSuccess) return ::pnb::cuda_fail(e__, "kernel launch"); \
+    } while (0)
+
+static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// device arithmetic
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Julia mod(a, n), n > 0
+__device__ __forceinline__ int floormod_i(int a, int n)
+{
+    int m = a % n;
+    return m < 0 ? m + n : m;
+}
+
+// Slow path of floor_to_int (src/util.jl:19-34) + `.+ 1` + periodic wrap with Julia's wrapping
+// Int64 arithmetic, for |floor| >= 2^30 or NaN.  Non-periodic: such a cell is always outside
+// the grid, any out-of-range marker will do.
+static __device__ __noinline__ int cell_coord_slow(float f, int periodic, int nc)
+{
+    if (!periodic) return f < 0.f ? -1 : 0x7fffffff;  // NaN lands here too -> out of bounds (high)
+    long long c;
+    if (isnan(f) || f >= 9223372036854775808.0f) c = 0x7fffffffffffffffLL;
+    else if (f <= -9223372036854775808.0f) c = (long long)0x8000000000000000ULL;
+    else c = (long long)f;
+    unsigned long long u = (unsigned long long)c + 1ULL;   // .+ 1 (wraps)
+    u = u - 2ULL;                                          // cell .- 2 (wraps)
+    long long a = (long long)u;
+    long long m = a % (long long)nc;
+    if (m < 0) m += nc;
+    return (int)m + 2;
+}
+
+// cell_coords (src/nhs_grid.jl:622-628) for one dimension:
+//   floor_to_int((x - min_corner) / cell_size) + 1   (src/cell_lists/full_grid.jl:93)
+//   periodic: mod(c - 2, n_cells) + 2                (src/nhs_grid.jl:619)
+__device__ __forceinline__ int cell_coord(float x, float minc, float cs, int periodic, int nc)
+{
+    float q = __fdiv_rn(__fsub_rn(x, minc), cs);
+    float f = floorf(q);
+    if (!(fabsf(f) < 1073741824.0f)) return cell_coord_slow(f, periodic, nc);
+    int c = (int)f + 1;
+    if (periodic) c = floormod_i(c - 2, nc) + 2;
+    return c;
+}
+
+// Linear 0-based cell index (src/cell_lists/full_grid.jl:157-161), or -1 when the cell is not
+// in 2:(size-1) in some dimension (check_cell_bounds, :205-213).
+template <int ND>
+__device__ __forceinline__ int point_cell(const GridP &g, const float *p, int *cc)
+{
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+        cc[d] = cell_coord(p[d], g.minc[d], g.cs[d], g.periodic, g.nc[d]);
+        ok = ok && (cc[d] >= 2) && (cc[d] <= g.gs[d] - 1);
+    }
+#pragma unroll
+    for (int d = ND; d < 3; d++) cc[d] = 1;
+    if (!ok) return -1;
+    return (cc[0] - 1) + (cc[1] - 1) * g.gs[0] + (cc[2] - 1) * g.gs[0] * g.gs[1];
+}
+
+__device__ __forceinline__ int linear_cell(const GridP &g, int c0, int c1, int c2)
+{
+    return (c0 - 1) + (c1 - 1) * g.gs[0] + (c2 - 1) * g.gs[0] * g.gs[1];
+}
+
+// pos_diff = x_i - y_j ; d2 = dot(pos_diff, pos_diff) left to right (src/nhs_grid.jl:547-549)
+template <int ND>
+__device__ __forceinline__ float dist2(float px, float py, float pz)
+{
+    float d2 = __fmul_rn(px, px);
+    if (ND > 1) d2 = __fadd_rn(d2, __fmul_rn(py, py));
+    if (ND > 2) d2 = __fadd_rn(d2, __fmul_rn(pz, pz));
+    return d2;
+}
+
+// compute_periodic_distance (src/neighborhood_search.jl:428-435), applied by the caller only
+// when d2 > r2:   pos_diff -= size .* round.(pos_diff ./ size);  d2 = dot(pos_diff, pos_diff)
+// Julia's round is ties-to-even == rintf.
+template <int ND>
+__device__ __noinline__ float periodic_fix(const GridP &g, float &px, float &py, float &pz)
+{
+    px = __fsub_rn(px, __fmul_rn(g.bsize[0], rintf(__fdiv_rn(px, g.bsize[0]))));
+    if (ND > 1) py = __fsub_rn(py, __fmul_rn(g.bsize[1], rintf(__fdiv_rn(py, g.bsize[1]))));
+    if (ND > 2) pz = __fsub_rn(pz, __fmul_rn(g.bsize[2], rintf(__fdiv_rn(pz, g.bsize[2]))));
+    return dist2<ND>(px, py, pz);
+}
+
+// The fix is the identity whenever every |pos_diff[d]| / size[d] rounds to 0, which is certain
+// when d2 < (0.49 * min size)^2 =: wrap_d2 (and wrap_d2 > r2 because every periodic box has at
+// least 3 cells of size >= r).  So `d2 >= wrap_d2` selects exactly the candidates that need the
+// exact slow path; for all others the reference's recomputation reproduces the same bits.
+template <int ND, bool PER>
+__device__ __forceinline__ float maybe_periodic_fix(const GridP &g, float d2, float &px, float &py,
+                                                    float &pz)
+{
+    if (PER && d2 >= g.wrap_d2) {
+        if (d2 > g.r2) d2 = periodic_fix<ND>(g, px, py, pz);
+    }
+    return d2;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+#endif  // __CUDACC__
+
+}  // namespace pnb

@@ -1,0 +1,55 @@
+// grid.cuh -- the grid handle (host side) shared by the translation units of libpnb200.
+#pragma once
+
+#include "common.cuh"
+
+struct pnb_grid {
+    pnb::GridP p;
+    // host copies of the constructor results (reference field names in comments)
+    float padded_min[3], padded_max[3];  // cell_list.min_corner / max_corner
+    int64_t grid_size[3];                // size(cell_list.linear_indices)
+    int64_t n_cells[3];                  // nhs.n_cells
+    float cell_size[3];                  // nhs.cell_size
+    float box_min[3], box_max[3];
+    bool template_search;                // search_radius < eps(): build only empties the list
+
+    int device;
+
+    // cell list in CSR form, device
+    uint32_t *cell_start;   // [C+1]
+    uint32_t *cell_count;   // [C]   histogram (scratch of the build)
+    int32_t *cell_points;   // [cap] ids, 0-based, ascending inside a cell
+    int32_t *ids_tmp;       // [cap] scatter output before the per-cell sort
+    int2 *cell_rank;        // [cap] (cell, rank) of the k-th listed point
+    float4 *sorted;         // [cap] (x, y, z, id bits) in cell order
+    int64_t cap_points;
+
+    // scan workspace
+    unsigned long long *scan_status;
+    int64_t scan_tiles_cap;
+    unsigned int *scan_ticket;  // [1]
+
+    // device + pinned error words: bit0 domain, bit1 bounds, bit2 list full
+    int *d_err;
+    int *h_err;
+
+    // state of the last build
+    int64_t n_built;        // number of points in the list
+    const void *y_built;    // pointer identity of the coordinates
+    int64_t n_y_built;      // columns of y at build time
+    bool built;
+    bool full_build;        // eachindex_y == all
+
+    // per-sweep scratch (payload gathered into cell order), grown on demand
+    void *scratch;
+    int64_t scratch_bytes;
+};
+
+namespace pnb {
+pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
+pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate d_err
+pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
+                              cudaStream_t s);
+pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *out, int64_t n,
+                                     cudaStream_t s);
+}  // namespace pnb

@@ -1,0 +1,174 @@
+// sweep.cu -- C-ABI entry points of the fused sweeps (count, n-body, WCSPH).
+// reference: foreach_point_neighbor (src/neighborhood_search.jl:183-201) with the closures of
+// benchmarks/count_neighbors.jl, benchmarks/n_body.jl, benchmarks/smoothed_particle_hydrodynamics.jl.
+#include "closures.cuh"
+#include "sweep.cuh"
+
+namespace pnb {
+
+// payload of the neighbour points gathered into cell order (one coalesced pass), so that the
+// staging loops of k_sweep_cells read contiguous memory.
+__global__ void k_gather_f32(int64_t n, const int32_t *__restrict__ ids,
+                             const float *__restrict__ src, float *__restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __ldg(src + ids[i]);
+}
+
+__global__ void k_gather_wcsph(int64_t n, int nd, const int32_t *__restrict__ ids,
+                               const float *__restrict__ v, const float *__restrict__ mass,
+                               const float *__restrict__ pressure, float4 *__restrict__ vrho,
+                               float2 *__restrict__ mp)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t id = ids[i];
+    const int ns = nd + 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.x = __ldg(v + id * ns);
+    if (nd > 1) a.y = __ldg(v + id * ns + 1);
+    if (nd > 2) a.z = __ldg(v + id * ns + 2);
+    a.w = __ldg(v + id * ns + nd);
+    vrho[i] = a;
+    mp[i] = make_float2(__ldg(mass + id), __ldg(pressure + id));
+}
+
+static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
+                                 int64_t *n_loop)
+{
+    if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    if (!g->built) {
+        set_error("the neighborhood search has not been initialized (call initialize! first)");
+        return PNB_ERR_STATE;
+    }
+    if (nx > 0 && !x) { set_error("x is NULL"); return PNB_ERR_ARG; }
+    *n_loop = points ? *n_loop : nx;
+    return PNB_OK;
+}
+
+static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points)
+{
+    return points == nullptr && g->full_build && x == g->y_built && nx == g->n_y_built;
+}
+
+template <int ND, bool PER, class CL>
+static pnb_status launch_nd(pnb_grid *g, bool fast, const float *x, int64_t n_loop,
+                            const int32_t *points, int base, const CL &cl, cudaStream_t s)
+{
+    if (fast) {
+        const int nxc = g->p.gs[0] - 2;
+        const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
+        const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
+        if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
+        const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
+        const size_t smem = (size_t)kCap * (sizeof(float4) + CL::kPayBytes);
+        k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem, s>>>(
+            g->p, g->cell_start, g->sorted, cl);
+        PNB_LAUNCHED();
+    } else if (n_loop > 0) {
+        k_sweep_points<ND, PER, CL><<<(unsigned)div_up(n_loop, 128), 128, 0, s>>>(
+            g->p, g->cell_start, g->sorted, x, n_loop, points, base, cl, g->d_err);
+        PNB_LAUNCHED();
+    }
+    return PNB_OK;
+}
+
+template <class CL>
+static pnb_status launch_sweep(pnb_grid *g, bool fast, const float *x, int64_t n_loop,
+                               const int32_t *points, int base, const CL &cl, cudaStream_t s)
+{
+    if (g->template_search || g->n_built == 0) return PNB_OK;  // every neighbourhood is empty
+    const bool per = g->p.periodic != 0;
+    switch (g->p.ndims) {
+        case 1:
+            return per ? launch_nd<1, true>(g, fast, x, n_loop, points, base, cl, s)
+                       : launch_nd<1, false>(g, fast, x, n_loop, points, base, cl, s);
+        case 2:
+            return per ? launch_nd<2, true>(g, fast, x, n_loop, points, base, cl, s)
+                       : launch_nd<2, false>(g, fast, x, n_loop, points, base, cl, s);
+        default:
+            return per ? launch_nd<3, true>(g, fast, x, n_loop, points, base, cl, s)
+                       : launch_nd<3, false>(g, fast, x, n_loop, points, base, cl, s);
+    }
+}
+
+}  // namespace pnb
+
+using namespace pnb;
+
+extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx,
+                                              const float *y, int64_t n, const int32_t *points,
+                                              int64_t n_points, int index_base, int64_t *out,
+                                              void *stream)
+{
+    (void)y; (void)n;
+    int64_t n_loop = n_points;
+    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop);
+    if (st != PNB_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    // count_neighbors.jl:22  n_neighbors .= 0
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)nx, s));
+    CountCl cl{out};
+    st = launch_sweep(g, is_fast_path(g, x, nx, points), x, n_loop, points, index_base, cl, s);
+    if (st != PNB_OK) return st;
+    return check_err_word(g, s);
+}
+
+extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
+                                    int64_t n, const int32_t *points, int64_t n_points,
+                                    int index_base, const float *mass, float G, float *dv,
+                                    void *stream)
+{
+    (void)y; (void)n;
+    int64_t n_loop = n_points;
+    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop);
+    if (st != PNB_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nd = g->p.ndims;
+    // n_body.jl:36  dv .= 0
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * nd, s));
+    if (g->template_search || g->n_built == 0) return check_err_word(g, s);
+    st = ensure_scratch(g, sizeof(float) * (size_t)g->n_built);
+    if (st != PNB_OK) return st;
+    float *mass_sorted = reinterpret_cast<float *>(g->scratch);
+    k_gather_f32<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(g->n_built, g->cell_points,
+                                                                   mass, mass_sorted);
+    PNB_LAUNCHED();
+    NBodyCl cl{mass_sorted, -G, dv, nd};
+    st = launch_sweep(g, is_fast_path(g, x, nx, points), x, n_loop, points, index_base, cl, s);
+    if (st != PNB_OK) return st;
+    return check_err_word(g, s);
+}
+
+extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_t nx,
+                                             const float *y, int64_t n, const int32_t *points,
+                                             int64_t n_points, int index_base, const float *v_x,
+                                             const float *v_y, const float *mass_x,
+                                             const float *mass_y, const float *pressure_x,
+                                             const float *pressure_y,
+                                             const pnb_wcsph_params *params, float *dv,
+                                             void *stream)
+{
+    (void)y; (void)n; (void)mass_x;
+    int64_t n_loop = n_points;
+    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop);
+    if (st != PNB_OK) return st;
+    if (!params) { set_error("params is NULL"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nd = g->p.ndims;
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * (nd + 1), s));
+    if (g->template_search || g->n_built == 0) return check_err_word(g, s);
+    const int64_t nb = g->n_built;
+    const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
+    st = ensure_scratch(g, off_mp + (int64_t)sizeof(float2) * nb);
+    if (st != PNB_OK) return st;
+    float4 *vrho = reinterpret_cast<float4 *>(g->scratch);
+    float2 *mp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
+    k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, g->cell_points, v_y, mass_y,
+                                                             pressure_y, vrho, mp);
+    PNB_LAUNCHED();
+    WcsphCl cl{vrho, mp, v_x, pressure_x, *params, dv, nd};
+    st = launch_sweep(g, is_fast_path(g, x, nx, points), x, n_loop, points, index_base, cl, s);
+    if (st != PNB_OK) return st;
+    return check_err_word(g, s);
+}

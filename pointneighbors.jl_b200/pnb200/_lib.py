@@ -1,0 +1,126 @@
+"""ctypes binding of libpnb200.so (include/pnb200.h).  One Python function per C entry point.
+
+The library is the product: if it cannot be loaded, or there is no CUDA device, every compute
+call raises -- there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+PNB_OK, PNB_ERR_DOMAIN, PNB_ERR_ARG, PNB_ERR_LIST_FULL, PNB_ERR_BOUNDS, PNB_ERR_CUDA, \
+    PNB_ERR_STATE = range(7)
+
+
+class ArgumentError(ValueError):
+    """Julia's ArgumentError (constructor validation)."""
+
+
+class PointNeighborsError(RuntimeError):
+    """Julia's ErrorException raised by `error(...)` in the reference."""
+
+
+class BoundsError(IndexError):
+    """Julia's BoundsError (safe sweep leaving the grid)."""
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+class WcsphParams(C.Structure):
+    _fields_ = [("smoothing_length", C.c_float), ("sound_speed", C.c_float),
+                ("alpha", C.c_float), ("beta", C.c_float), ("epsilon", C.c_float),
+                ("delta", C.c_float), ("kernel_norm", C.c_float)]
+
+
+_lib = None
+
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+_pf = C.POINTER(C.c_float)
+_pi64 = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); must list every symbol declared in include/pnb200.h
+SIGNATURES = {
+    "pnb_version": (C.c_int, []),
+    "pnb_last_error": (C.c_char_p, []),
+    "pnb_device_count": (C.c_int, []),
+    "pnb_grid_params_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, _pf, _pf, _pi64, _pi64, _pf]),
+    "pnb_grid_create_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, C.POINTER(_vp)]),
+    "pnb_grid_destroy": (None, [_vp]),
+    "pnb_grid_total_cells": (_i64, [_vp]),
+    "pnb_grid_n_points": (_i64, [_vp]),
+    "pnb_grid_build_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
+    "pnb_point_cells_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "pnb_grid_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "pnb_grid_export_dvov": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, _vp]),
+    "pnb_count_neighbors_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
+    "pnb_nbody_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _f32, _vp, _vp]),
+    "pnb_wcsph_interact_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp,
+                                         _vp, _vp, _vp, _vp, C.POINTER(WcsphParams), _vp, _vp]),
+    "pnb_nlist_build_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), _vp]),
+    "pnb_nlist_destroy": (None, [_vp]),
+    "pnb_nlist_n_points": (_i64, [_vp]),
+    "pnb_nlist_n_pairs": (_i64, [_vp]),
+    "pnb_nlist_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "pnb_nlist_export_dvov": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, C.c_int, _vp]),
+    "pnb_nlist_pairs_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnb_tlsph_deformation_grad_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
+                                                 _vp, _vp]),
+    "pnb_malloc": (C.c_int, [C.POINTER(_vp), _i64]),
+    "pnb_free": (C.c_int, [_vp]),
+    "pnb_malloc_host": (C.c_int, [C.POINTER(_vp), _i64]),
+    "pnb_free_host": (C.c_int, [_vp]),
+    "pnb_memcpy_h2d": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pnb_memcpy_d2h": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pnb_memset": (C.c_int, [_vp, C.c_int, _i64, _vp]),
+    "pnb_stream_synchronize": (C.c_int, [_vp]),
+    "pnb_launch_count": (_i64, []),
+}
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def lib() -> C.CDLL:
+    """Load libpnb200.so (building it first if the sources are newer and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        # fail loudly: no silent fallback
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover - depends on toolchain
+            raise ImportError(
+                f"libpnb200.so is missing and could not be built ({exc}); the CUDA library is "
+                "required, pnb200 has no CPU fallback") from exc
+    handle = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().pnb_last_error().decode("utf-8", "replace")
+
+
+def check(status: int) -> None:
+    """Translate a pnb_status into the exception the reference would raise."""
+    if status == PNB_OK:
+        return
+    msg = last_error()
+    if status == PNB_ERR_ARG:
+        raise ArgumentError(msg)
+    if status in (PNB_ERR_DOMAIN, PNB_ERR_LIST_FULL, PNB_ERR_STATE):
+        raise PointNeighborsError(msg)
+    if status == PNB_ERR_BOUNDS:
+        raise BoundsError(msg)
+    raise CudaError(msg)

@@ -1,0 +1,745 @@
+"""Host-side mirror of the PointNeighbors.jl interface for the hot path, on top of the C ABI.
+
+The reference is Julia and there is no Julia toolchain in this image, so the host side is this
+Python module; julia/PNB200.jl carries the same calls as `ccall`s.  Names,
+keyword arguments, defaults, return values and error texts follow the reference:
+
+    GridNeighborhoodSearch{NDIMS}(; ...)        ->  GridNeighborhoodSearch[NDIMS](...)      src/nhs_grid.jl:77-129
+    FullGridCellList(; ...)                      ->  FullGridCellList(...)                   src/cell_lists/full_grid.jl:48-82
+    PeriodicBox(; min_corner, max_corner)        ->  PeriodicBox(...)                        src/neighborhood_search.jl:129-143
+    PrecomputedNeighborhoodSearch{NDIMS}(; ...)  ->  PrecomputedNeighborhoodSearch[NDIMS](...)  src/nhs_precomputed.jl:89-111
+    initialize!(nhs, x, y; eachindex_y)          ->  initialize_(nhs, x, y, eachindex_y=)    src/nhs_grid.jl:220-225
+    update!(nhs, x, y; points_moving, ...)       ->  update_(nhs, x, y, points_moving=)      src/nhs_grid.jl:283-292
+    foreach_point_neighbor(f, x, y, nhs; points) ->  same                                    src/neighborhood_search.jl:183-201
+    copy_neighborhood_search / freeze_neighborhood_search / requires_update / search_radius / ndims
+
+Coordinates are torch CUDA tensors of shape (N, NDIMS), float32, contiguous: byte for byte the
+memory of Julia's NDIMS x N column-major matrix.  Point indices are 0-based on this side (the
+Julia glue passes index_base = 1).  torch is only the owner of device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import ArgumentError, BoundsError, PointNeighborsError, WcsphParams, check
+
+__all__ = [
+    "ArgumentError", "PointNeighborsError", "BoundsError",
+    "ParallelUpdate", "SerialUpdate", "ParallelIncrementalUpdate", "SemiParallelUpdate",
+    "SerialIncrementalUpdate", "DynamicVectorOfVectors",
+    "PeriodicBox", "FullGridCellList", "GridNeighborhoodSearch", "PrecomputedNeighborhoodSearch",
+    "initialize_", "update_", "initialize", "update", "foreach_point_neighbor",
+    "copy_neighborhood_search", "freeze_neighborhood_search", "requires_update",
+    "search_radius", "ndims", "CountNeighbors", "NBodyGravity", "WCSPHInteract",
+    "TLSPHDeformationGradient", "wendland_c2_norm",
+]
+
+_EPS64 = 2.220446049250313e-16
+
+
+def _torch():
+    import torch
+    return torch
+
+
+# ---------------------------------------------------------------------------------------------
+# update strategies (src/nhs_grid.jl:135-192).  The device build is a full counting-sort rebuild,
+# i.e. ParallelUpdate semantics; SerialUpdate is the same rebuild in the reference
+# (nhs_grid.jl:470-477).  The incremental strategies are CPU algorithms and not offered.
+# ---------------------------------------------------------------------------------------------
+class _Strategy:
+    def __eq__(self, other):
+        return type(self) is type(other)
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+    def __repr__(self):
+        return f"{type(self).__name__}()"
+
+
+class ParallelUpdate(_Strategy):
+    pass
+
+
+class SerialUpdate(_Strategy):
+    pass
+
+
+class ParallelIncrementalUpdate(_Strategy):
+    pass
+
+
+class SemiParallelUpdate(_Strategy):
+    pass
+
+
+class SerialIncrementalUpdate(_Strategy):
+    pass
+
+
+class DynamicVectorOfVectors:
+    """Type tag of the reference's list storage (src/vector_of_vectors.jl:3-31); `backend=` keyword."""
+
+    def __init__(self, eltype=np.int32):
+        self.eltype = eltype
+
+    def __class_getitem__(cls, eltype):
+        return cls(eltype)
+
+
+def _as_real_vector(v, what):
+    a = np.asarray(v)
+    if a.ndim != 1:
+        a = a.reshape(-1)
+    return a
+
+
+def _is_integer_scalar(v) -> bool:
+    return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
+
+
+def _eltype_of(v):
+    if isinstance(v, np.floating):
+        return np.dtype(type(v))
+    if isinstance(v, float):
+        return np.dtype(np.float64)
+    a = np.asarray(v)
+    return a.dtype
+
+
+class PeriodicBox:
+    """PeriodicBox(; min_corner, max_corner)  (src/neighborhood_search.jl:129-143)."""
+
+    def __init__(self, *, min_corner, max_corner):
+        mn = np.asarray(min_corner)
+        mx = np.asarray(max_corner)
+        dt = np.result_type(mn, mx)
+        if not np.issubdtype(dt, np.floating):
+            dt = np.dtype(np.float64)
+        self.min_corner = mn.astype(dt)
+        self.max_corner = mx.astype(dt)
+        self.size = self.max_corner - self.min_corner   # evaluated in the element type
+        self.eltype = np.dtype(dt)
+
+    def __len__(self):
+        return self.min_corner.size
+
+
+class FullGridCellList:
+    """FullGridCellList(; min_corner, max_corner, search_radius, backend, max_points_per_cell)
+    (src/cell_lists/full_grid.jl:48-82).  Stores the PADDED corners like the reference."""
+
+    def __init__(self, *, min_corner, max_corner, search_radius=None,
+                 backend=DynamicVectorOfVectors[np.int32], max_points_per_cell: int = 100):
+        mn = _as_real_vector(min_corner, "min_corner")
+        mx = _as_real_vector(max_corner, "max_corner")
+        if mn.size != mx.size:
+            raise ArgumentError("min_corner and max_corner must have the same length")
+        if mn.size > 100:
+            raise ArgumentError("FullGridCellList only supports up to 100 dimensions, "
+                                "check your `min_corner` and `max_corner`")
+        if search_radius is None:
+            dt = mn.dtype if np.issubdtype(mn.dtype, np.floating) else np.dtype(np.float64)
+            search_radius = dt.type(0)
+        if not isinstance(backend, DynamicVectorOfVectors):
+            raise ArgumentError("only the DynamicVectorOfVectors backend is GPU-compatible "
+                                "(src/cell_lists/full_grid.jl:21-25)")
+        self.backend = backend
+        self.max_points_per_cell = int(max_points_per_cell)
+        self.search_radius = search_radius
+        self._ndims = int(mn.size)
+        r = np.float32(search_radius)
+        # padding and grid size through the library's host arithmetic (bit-identical to Julia)
+        pmin = (C.c_float * 3)()
+        pmax = (C.c_float * 3)()
+        gsz = (C.c_int64 * 3)()
+        mn32 = np.ascontiguousarray(mn, dtype=np.float32)
+        mx32 = np.ascontiguousarray(mx, dtype=np.float32)
+        if self._ndims > 3:
+            raise ArgumentError("`NDIMS` must be 1, 2, or 3")
+        check(_lib.lib().pnb_grid_params_f32(
+            self._ndims, r, mn32.ctypes.data_as(_lib._pf), mx32.ctypes.data_as(_lib._pf), None,
+            None, pmin, pmax, gsz, None, None))
+        self.min_corner = np.array(pmin[:self._ndims], dtype=np.float32)
+        self.max_corner = np.array(pmax[:self._ndims], dtype=np.float32)
+        self.n_cells_per_dimension = tuple(int(v) for v in gsz[:self._ndims])
+        # what was passed in, needed to re-create the device grid
+        self._user_min = mn32
+        self._user_max = mx32
+
+    def ndims(self):
+        return self._ndims
+
+    @property
+    def is_template(self):
+        return float(self.search_radius) < _EPS64
+
+
+def supported_update_strategies(cell_list):
+    # src/cell_lists/full_grid.jl:39-42 lists five strategies for the CPU; on the device the two
+    # full-rebuild strategies exist.
+    return (ParallelUpdate, SerialUpdate)
+
+
+def copy_cell_list(cell_list: FullGridCellList, search_radius, periodic_box):
+    """src/cell_lists/full_grid.jl:179-185 -- re-pads from the STORED corners."""
+    return FullGridCellList(min_corner=cell_list.min_corner, max_corner=cell_list.max_corner,
+                            search_radius=search_radius, backend=cell_list.backend,
+                            max_points_per_cell=cell_list.max_points_per_cell)
+
+
+class _Parametric(type):
+    """`GridNeighborhoodSearch[3](...)` stands for Julia's `GridNeighborhoodSearch{3}(; ...)`."""
+
+    def __getitem__(cls, ndims_):
+        def ctor(**kwargs):
+            return cls(int(ndims_), **kwargs)
+        ctor.__name__ = f"{cls.__name__}[{ndims_}]"
+        return ctor
+
+
+class GridNeighborhoodSearch(metaclass=_Parametric):
+    """GridNeighborhoodSearch{NDIMS}(; search_radius, n_points, periodic_box, cell_list,
+    update_strategy)  (src/nhs_grid.jl:67-129) backed by a device CSR cell list."""
+
+    def __init__(self, ndims_: int, *, search_radius=0.0, n_points: int = 0, periodic_box=None,
+                 cell_list: Optional[FullGridCellList] = None, update_strategy=None):
+        self._ndims = int(ndims_)
+        if cell_list is None:
+            raise ArgumentError("the default DictionaryCellList is not GPU-compatible "
+                                "(src/cell_lists/dictionary.jl:8-10); pass a FullGridCellList")
+        if cell_list.ndims() != self._ndims:
+            raise ArgumentError(f"a {self._ndims}D cell list is required for "
+                                f"a GridNeighborhoodSearch{{{self._ndims}}}")
+        if update_strategy is None:
+            update_strategy = supported_update_strategies(cell_list)[0]()
+        elif type(update_strategy) not in supported_update_strategies(cell_list):
+            names = ", ".join(s.__name__ for s in supported_update_strategies(cell_list))
+            raise ArgumentError(f"{update_strategy} is not a valid update strategy for "
+                                f"this cell list. Available options are ({names})")
+        if _is_integer_scalar(search_radius):
+            raise ArgumentError("`search_radius` cannot be an integer type, since computed "
+                                "distances will be converted to this type")
+        self.cell_list = cell_list
+        self.search_radius = search_radius
+        self.periodic_box = periodic_box
+        self.update_strategy = update_strategy
+        self.update_buffer = None          # nhs_grid.jl:195-197
+        self.n_points = int(n_points)
+        is_template = float(search_radius) < _EPS64
+        if is_template or periodic_box is None:
+            self.n_cells = tuple(-1 for _ in range(self._ndims))
+            self.cell_size = tuple(search_radius for _ in range(self._ndims))
+        else:
+            if _eltype_of(search_radius) != periodic_box.eltype:
+                raise ArgumentError("the `search_radius` and the `PeriodicBox` must have "
+                                    "the same element type")
+            if _eltype_of(search_radius) != np.dtype(np.float32):
+                raise ArgumentError("the B200 path computes in Float32: pass a Float32 "
+                                    "`search_radius` and `PeriodicBox`")
+            nc = (C.c_int64 * 3)()
+            cs = (C.c_float * 3)()
+            bmn = np.ascontiguousarray(periodic_box.min_corner, dtype=np.float32)
+            bmx = np.ascontiguousarray(periodic_box.max_corner, dtype=np.float32)
+            check(_lib.lib().pnb_grid_params_f32(
+                self._ndims, np.float32(search_radius),
+                cell_list._user_min.ctypes.data_as(_lib._pf),
+                cell_list._user_max.ctypes.data_as(_lib._pf),
+                bmn.ctypes.data_as(_lib._pf), bmx.ctypes.data_as(_lib._pf),
+                None, None, None, nc, cs))
+            self.n_cells = tuple(int(v) for v in nc[:self._ndims])
+            self.cell_size = tuple(np.float32(v) for v in cs[:self._ndims])
+        self._handle = None
+        self._cell_list_radius = cell_list.search_radius
+
+    # -- device handle -----------------------------------------------------------------------
+    def _grid(self):
+        if self._handle is None:
+            if float(self.search_radius) >= _EPS64 and \
+                    _eltype_of(self.search_radius) != np.dtype(np.float32):
+                raise ArgumentError("the B200 path computes in Float32: pass a Float32 "
+                                    "`search_radius` (src/nhs_grid.jl:60-65)")
+            cl = self.cell_list
+            h = C.c_void_p()
+            bmn = bmx = None
+            if self.periodic_box is not None:
+                bmn_a = np.ascontiguousarray(self.periodic_box.min_corner, dtype=np.float32)
+                bmx_a = np.ascontiguousarray(self.periodic_box.max_corner, dtype=np.float32)
+                bmn, bmx = bmn_a.ctypes.data_as(_lib._pf), bmx_a.ctypes.data_as(_lib._pf)
+            # The cell list was padded with ITS search radius (normally the same as the search's).
+            check(_lib.lib().pnb_grid_create_f32(
+                self._ndims, np.float32(self.search_radius),
+                cl._user_min.ctypes.data_as(_lib._pf), cl._user_max.ctypes.data_as(_lib._pf),
+                bmn, bmx, C.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _lib.lib().pnb_grid_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # -- inspection (tests, exports) ------------------------------------------------------------
+    def total_cells(self) -> int:
+        return int(_lib.lib().pnb_grid_total_cells(self._grid()))
+
+    def export_csr(self):
+        """(cell_start[C+1], cell_points[n]) int32 CUDA tensors, 0-based ids."""
+        torch = _torch()
+        g = self._grid()
+        Cn = self.total_cells()
+        n = int(_lib.lib().pnb_grid_n_points(g))
+        cs = torch.empty(Cn + 1, dtype=torch.int32, device="cuda")
+        cp = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+        check(_lib.lib().pnb_grid_export_csr(g, cs.data_ptr(), cp.data_ptr(), 0, _stream()))
+        return cs, cp[:n]
+
+    def export_dvov(self, max_points_per_cell=None, index_base=1):
+        """The reference's cell storage: backend (C, max_points_per_cell) == Julia's
+        max_points_per_cell x C column-major matrix, lengths (C,)."""
+        torch = _torch()
+        m = int(max_points_per_cell or self.cell_list.max_points_per_cell)
+        Cn = self.total_cells()
+        backend = torch.zeros((Cn, m), dtype=torch.int32, device="cuda")
+        lengths = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+        check(_lib.lib().pnb_grid_export_dvov(self._grid(), backend.data_ptr(), lengths.data_ptr(),
+                                              m, index_base, _stream()))
+        return backend, lengths
+
+    def point_cells(self, x):
+        """0-based linear cell index of every point of x, -1 outside (cell_coords + cell_index)."""
+        torch = _torch()
+        x = _coords(x, self._ndims)
+        out = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
+        check(_lib.lib().pnb_point_cells_f32(self._grid(), x.data_ptr(), x.shape[0],
+                                             out.data_ptr(), _stream()))
+        return out
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _coords(x, nd):
+    torch = _torch()
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("coordinates must be a torch CUDA tensor of shape (N, NDIMS)")
+    if not x.is_cuda:
+        raise TypeError("coordinates must live on the GPU: pnb200 has no CPU path "
+                        "(use adapt(...) / tensor.cuda())")
+    if x.dtype != torch.float32:
+        raise TypeError("coordinates must be float32")
+    if x.ndim != 2 or x.shape[1] != nd:
+        raise ArgumentError(f"coordinates must have shape (N, {nd}) "
+                            "(the memory of Julia's NDIMS x N matrix)")
+    if not x.is_contiguous():
+        raise TypeError("coordinates must be contiguous")
+    return x
+
+
+def _index_tensor(idx, n, what):
+    """points / eachindex_y: None, range, sequence or int tensor -> (int32 CUDA tensor | None)."""
+    torch = _torch()
+    if idx is None:
+        return None
+    if isinstance(idx, range):
+        if idx.step == 1 and idx.start == 0 and idx.stop == n:
+            return None
+        idx = list(idx)
+    if isinstance(idx, torch.Tensor):
+        t = idx.to(device="cuda", dtype=torch.int32).contiguous()
+    else:
+        t = torch.as_tensor(np.asarray(idx, dtype=np.int32), device="cuda")
+    if t.numel() > 0:
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= n:   # @boundscheck checkbounds (neighborhood_search.jl:192, nhs_grid.jl:269)
+            raise BoundsError(f"attempt to access {n} points at {what} index [{lo}, {hi}]")
+    return t
+
+
+def ndims(nhs) -> int:
+    return nhs._ndims
+
+
+def search_radius(nhs):
+    return nhs.search_radius
+
+
+def requires_update(nhs):
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        return (True, True)      # nhs_precomputed.jl:128
+    return (False, True)         # nhs_grid.jl:133
+
+
+# ---------------------------------------------------------------------------------------------
+# initialize! / update!
+# ---------------------------------------------------------------------------------------------
+def initialize_(nhs, x, y, *, parallelization_backend=None, eachindex_y=None):
+    """initialize!(nhs, x, y; eachindex_y)  (src/nhs_grid.jl:220-225, nhs_precomputed.jl:130-147)."""
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        return nhs._initialize(x, y, eachindex_y)
+    y = _coords(y, nhs._ndims)
+    idx = _index_tensor(eachindex_y, y.shape[0], "eachindex_y")
+    check(_lib.lib().pnb_grid_build_f32(
+        nhs._grid(), y.data_ptr(), y.shape[0], None if idx is None else idx.data_ptr(),
+        0 if idx is None else idx.numel(), 0, _stream()))
+    nhs._y_ref = y   # keep the coordinates alive: the fast path is keyed on their address
+    return nhs
+
+
+def update_(nhs, x, y, *, points_moving=(True, True), parallelization_backend=None,
+            eachindex_y=None):
+    """update!(nhs, x, y; points_moving, eachindex_y)  (src/nhs_grid.jl:283-292)."""
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        return nhs._update(x, y, points_moving, eachindex_y)
+    # "Only update when the second set is moving." (nhs_grid.jl:289)
+    if not points_moving[1]:
+        return nhs
+    return initialize_(nhs, x, y, eachindex_y=eachindex_y)
+
+
+initialize = initialize_
+update = update_
+
+
+# ---------------------------------------------------------------------------------------------
+# closures that have a fused kernel
+# ---------------------------------------------------------------------------------------------
+class CountNeighbors:
+    """`n_neighbors[i] += 1` (benchmarks/count_neighbors.jl:24-27); n_neighbors: int64 CUDA tensor.
+    Like the benchmark, the array is zeroed first (`n_neighbors .= 0`, :22)."""
+
+    def __init__(self, n_neighbors):
+        self.n_neighbors = n_neighbors
+
+
+class NBodyGravity:
+    """benchmarks/n_body.jl:38-48: dv zeroed, then dv[:, i] += -G * mass[j] * pos_diff / distance^3."""
+
+    def __init__(self, dv, mass, G):
+        self.dv, self.mass, self.G = dv, mass, G
+
+
+def wendland_c2_norm(ndims_: int, h) -> np.float32:
+    """sigma_d / h^d of the Wendland C2 kernel (TrixiParticles kernel_normalization), in Float32."""
+    h = np.float32(h)
+    if ndims_ == 3:
+        sigma = np.float32(21.0 / (16.0 * np.pi))
+        return np.float32(sigma / (h * h * h))
+    if ndims_ == 2:
+        sigma = np.float32(7.0 / (4.0 * np.pi))
+        return np.float32(sigma / (h * h))
+    raise ArgumentError("WendlandC2Kernel is defined for 2 and 3 dimensions")
+
+
+class WCSPHInteract:
+    """TrixiParticles.interact!(dv, v, u, v, u, system, system, semi) as configured by
+    benchmarks/smoothed_particle_hydrodynamics.jl:45-102.  v, dv: (N, NDIMS+1) = velocity, density."""
+
+    def __init__(self, dv, v_x, v_y, mass_x, mass_y, pressure_x, pressure_y, *, smoothing_length,
+                 sound_speed, alpha=0.02, beta=0.0, epsilon=0.01, delta=0.1, kernel_norm=None,
+                 ndims_=3):
+        self.dv = dv
+        self.v_x, self.v_y = v_x, v_y
+        self.mass_x, self.mass_y = mass_x, mass_y
+        self.pressure_x, self.pressure_y = pressure_x, pressure_y
+        if kernel_norm is None:
+            kernel_norm = wendland_c2_norm(ndims_, smoothing_length)
+        self.params = WcsphParams(np.float32(smoothing_length), np.float32(sound_speed),
+                                  np.float32(alpha), np.float32(beta), np.float32(epsilon),
+                                  np.float32(delta), np.float32(kernel_norm))
+
+    def params_array(self):
+        p = self.params
+        return np.array([p.smoothing_length, p.sound_speed, p.alpha, p.beta, p.epsilon, p.delta,
+                         p.kernel_norm], dtype=np.float32)
+
+
+class TLSPHDeformationGradient:
+    """TrixiParticles.calc_deformation_grad! over a PrecomputedNeighborhoodSearch
+    (benchmarks/smoothed_particle_hydrodynamics.jl:136-189)."""
+
+    def __init__(self, F, current_coordinates, mass, material_density, correction_matrix, *,
+                 smoothing_length, kernel_norm=None, ndims_=3):
+        self.F = F
+        self.current_coordinates = current_coordinates
+        self.mass = mass
+        self.material_density = material_density
+        self.correction_matrix = correction_matrix
+        self.smoothing_length = np.float32(smoothing_length)
+        self.kernel_norm = np.float32(kernel_norm if kernel_norm is not None
+                                      else wendland_c2_norm(ndims_, smoothing_length))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_search, *,
+                           parallelization_backend=None, points=None):
+    """foreach_point_neighbor(f, x, y, nhs; points)  (src/neighborhood_search.jl:183-201).
+
+    f is one of the fused closures (CountNeighbors, NBodyGravity, WCSPHInteract,
+    TLSPHDeformationGradient) or any Python callable f(i, j, pos_diff, distance); a callable is
+    served from a device-built neighbour list (the pairs are computed on the GPU, the callable is
+    host code and runs on the host).  Returns None like the reference."""
+    nhs = neighborhood_search
+    nd = nhs._ndims
+    x = _coords(system_coords, nd)
+    y = _coords(neighbor_coords, nd)
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        return nhs._foreach(f, x, y, points)
+    L = _lib.lib()
+    pts = _index_tensor(points, x.shape[0], "points")
+    npts = 0 if pts is None else pts.numel()
+    g = nhs._grid()
+    if isinstance(f, CountNeighbors):
+        check(L.pnb_count_neighbors_f32(g, x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
+                                        _ptr(pts), npts, 0, f.n_neighbors.data_ptr(), _stream()))
+    elif isinstance(f, NBodyGravity):
+        check(L.pnb_nbody_f32(g, x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], _ptr(pts),
+                              npts, 0, f.mass.data_ptr(), np.float32(f.G), f.dv.data_ptr(),
+                              _stream()))
+    elif isinstance(f, WCSPHInteract):
+        check(L.pnb_wcsph_interact_f32(g, x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
+                                       _ptr(pts), npts, 0, f.v_x.data_ptr(), f.v_y.data_ptr(),
+                                       f.mass_x.data_ptr(), f.mass_y.data_ptr(),
+                                       f.pressure_x.data_ptr(), f.pressure_y.data_ptr(),
+                                       C.byref(f.params), f.dv.data_ptr(), _stream()))
+    elif callable(f):
+        lists = _NeighborLists.build(nhs, x, y, sort=False)
+        lists.call_host(f, x, y, nhs, points, radius_test=True)
+    else:
+        raise TypeError("f must be a fused closure object or a callable f(i, j, pos_diff, d)")
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+# neighbour lists
+# ---------------------------------------------------------------------------------------------
+class _NeighborLists:
+    """Owner of a pnb_nlist handle (device CSR)."""
+
+    def __init__(self, handle, nd):
+        self._handle = handle
+        self._nd = nd
+
+    @classmethod
+    def build(cls, grid_nhs, x, y, sort=True):
+        h = C.c_void_p()
+        check(_lib.lib().pnb_nlist_build_f32(grid_nhs._grid(), x.data_ptr(), x.shape[0],
+                                             y.data_ptr(), y.shape[0], int(bool(sort)),
+                                             C.byref(h), _stream()))
+        return cls(h, grid_nhs._ndims)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _lib.lib().pnb_nlist_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    @property
+    def n_points(self):
+        return int(_lib.lib().pnb_nlist_n_points(self._handle))
+
+    @property
+    def n_pairs(self):
+        return int(_lib.lib().pnb_nlist_n_pairs(self._handle))
+
+    def export_csr(self, index_base=0):
+        torch = _torch()
+        off = torch.empty(self.n_points + 1, dtype=torch.int64, device="cuda")
+        ids = torch.empty(max(self.n_pairs, 1), dtype=torch.int32, device="cuda")
+        check(_lib.lib().pnb_nlist_export_csr(self._handle, off.data_ptr(), ids.data_ptr(),
+                                              index_base, _stream()))
+        return off, ids[:self.n_pairs]
+
+    def export_dvov(self, max_neighbors, transposed=False, index_base=1):
+        """(backend, lengths).  backend has the PARENT memory layout of the reference:
+        regular: (n_points, max_neighbors) row-major == Julia max_neighbors x n_points;
+        transposed: (max_neighbors, n_points) row-major == Julia parent n_points x max_neighbors
+        (src/vector_of_vectors.jl:18-26)."""
+        torch = _torch()
+        n = self.n_points
+        shape = (max_neighbors, n) if transposed else (n, max_neighbors)
+        backend = torch.empty(shape, dtype=torch.int32, device="cuda")
+        lengths = torch.empty(n, dtype=torch.int32, device="cuda")
+        check(_lib.lib().pnb_nlist_export_dvov(self._handle, backend.data_ptr(), lengths.data_ptr(),
+                                               int(max_neighbors), int(bool(transposed)),
+                                               index_base, _stream()))
+        return backend, lengths
+
+    def pairs(self, grid_nhs, x, y):
+        """pos_diff (P, nd) and distance (P,) of every listed pair, in list order."""
+        torch = _torch()
+        P = self.n_pairs
+        pd = torch.empty((max(P, 1), self._nd), dtype=torch.float32, device="cuda")
+        dist = torch.empty(max(P, 1), dtype=torch.float32, device="cuda")
+        check(_lib.lib().pnb_nlist_pairs_f32(self._handle, grid_nhs._grid(), x.data_ptr(),
+                                             y.data_ptr(), pd.data_ptr(), dist.data_ptr(),
+                                             _stream()))
+        return pd[:P], dist[:P]
+
+    def call_host(self, f: Callable, x, y, grid_nhs, points, radius_test: bool):
+        off, ids = self.export_csr(0)
+        pd, dist = self.pairs(grid_nhs, x, y)
+        off = off.cpu().numpy()
+        ids = ids.cpu().numpy()
+        pd = pd.cpu().numpy()
+        dist = dist.cpu().numpy()
+        loop = range(x.shape[0]) if points is None else [int(p) for p in points]
+        for i in loop:
+            for k in range(off[i], off[i + 1]):
+                f(i, int(ids[k]), pd[k], dist[k])
+
+
+class PrecomputedNeighborhoodSearch(metaclass=_Parametric):
+    """PrecomputedNeighborhoodSearch{NDIMS}(; search_radius, n_points, periodic_box,
+    update_strategy, update_neighborhood_search, backend, transpose_backend, max_neighbors,
+    sort_neighbor_lists)  (src/nhs_precomputed.jl:67-124).
+
+    The lists live on the device as CSR; `neighbor_lists()` exports them in the reference's
+    DynamicVectorOfVectors layout (regular or transposed) with `max_neighbors` rows."""
+
+    @staticmethod
+    def default_max_neighbors(nd):
+        # nhs_precomputed.jl:114-124
+        if nd == 1:
+            return 32
+        if nd == 2:
+            return 64
+        if nd == 3:
+            return 320
+        raise ArgumentError("`NDIMS` must be 1, 2, or 3")
+
+    def __init__(self, ndims_: int, *, search_radius=0.0, n_points: int = 0, periodic_box=None,
+                 update_strategy=None, update_neighborhood_search=None,
+                 backend=DynamicVectorOfVectors[np.int32], transpose_backend: bool = False,
+                 max_neighbors: Optional[int] = None, sort_neighbor_lists: bool = True):
+        self._ndims = int(ndims_)
+        if _is_integer_scalar(search_radius):
+            raise ArgumentError("`search_radius` cannot be an integer type, since computed "
+                                "distances will be converted to this type")
+        if update_neighborhood_search is None:
+            raise ArgumentError("the default update_neighborhood_search uses a DictionaryCellList, "
+                                "which is not GPU-compatible; pass a GridNeighborhoodSearch with a "
+                                "FullGridCellList (src/nhs_precomputed.jl:37-42)")
+        self.search_radius = search_radius
+        self.periodic_box = periodic_box
+        self.neighborhood_search = update_neighborhood_search
+        self.backend = backend
+        self.transpose_backend = bool(transpose_backend)
+        self.max_neighbors = int(max_neighbors if max_neighbors is not None
+                                 else self.default_max_neighbors(self._ndims))
+        self.sort_neighbor_lists = bool(sort_neighbor_lists)
+        self.n_points = int(n_points)
+        self._lists: Optional[_NeighborLists] = None
+        self._grid_for_pairs = update_neighborhood_search
+
+    # initialize! (nhs_precomputed.jl:130-147)
+    def _initialize(self, x, y, eachindex_y):
+        nd = self._ndims
+        x = _coords(x, nd)
+        y = _coords(y, nd)
+        if _index_tensor(eachindex_y, y.shape[0], "eachindex_y") is not None:
+            raise PointNeighborsError("this neighborhood search does not support inactive points")
+        if self.neighborhood_search is None:
+            raise PointNeighborsError("this neighborhood search has been frozen and cannot be "
+                                      "initialized or updated")
+        initialize_(self.neighborhood_search, x, y)
+        self._build_lists(x, y)
+        return self
+
+    # update! (nhs_precomputed.jl:149-169)
+    def _update(self, x, y, points_moving, eachindex_y):
+        nd = self._ndims
+        x = _coords(x, nd)
+        y = _coords(y, nd)
+        if _index_tensor(eachindex_y, y.shape[0], "eachindex_y") is not None:
+            raise PointNeighborsError("this neighborhood search does not support inactive points")
+        if self.neighborhood_search is None:
+            raise PointNeighborsError("this neighborhood search has been frozen and cannot be "
+                                      "initialized or updated")
+        update_(self.neighborhood_search, x, y, points_moving=points_moving)
+        if any(points_moving):
+            self._build_lists(x, y)
+        return self
+
+    def _build_lists(self, x, y):
+        self._lists = _NeighborLists.build(self.neighborhood_search, x, y,
+                                           sort=self.sort_neighbor_lists)
+        # the reference errors when a list overflows `max_neighbors` (vector_of_vectors.jl:114-121)
+        torch = _torch()
+        off, _ = self._lists.export_csr(0)
+        if off.numel() > 1:
+            longest = int((off[1:] - off[:-1]).max())
+            if longest > self.max_neighbors:
+                raise PointNeighborsError("cell list is full. Use a larger `max_points_per_cell`.")
+
+    def neighbor_lists(self, index_base=1):
+        """(backend, lengths) in the reference layout, see _NeighborLists.export_dvov."""
+        return self._lists.export_dvov(self.max_neighbors, self.transpose_backend, index_base)
+
+    def export_csr(self, index_base=0):
+        return self._lists.export_csr(index_base)
+
+    def _foreach(self, f, x, y, points):
+        if self._lists is None:
+            raise PointNeighborsError("the neighborhood search has not been initialized")
+        if isinstance(f, TLSPHDeformationGradient):
+            if points is not None:
+                raise ArgumentError("the fused TLSPH sweep loops over all points")
+            check(_lib.lib().pnb_tlsph_deformation_grad_f32(
+                self._lists._handle, self._grid_for_pairs._grid(), x.data_ptr(),
+                f.current_coordinates.data_ptr(), f.mass.data_ptr(),
+                f.material_density.data_ptr(), f.correction_matrix.data_ptr(),
+                f.smoothing_length, f.kernel_norm, f.F.data_ptr(), _stream()))
+            return None
+        if callable(f):
+            self._lists.call_host(f, x, y, self._grid_for_pairs, points, radius_test=False)
+            return None
+        raise TypeError("f must be TLSPHDeformationGradient or a callable f(i, j, pos_diff, d)")
+
+
+# ---------------------------------------------------------------------------------------------
+# copy / freeze
+# ---------------------------------------------------------------------------------------------
+def copy_neighborhood_search(nhs, search_radius_, n_points, *, eachpoint=None):
+    """copy_neighborhood_search(nhs, search_radius, n_points)  (src/nhs_grid.jl:640-649,
+    src/nhs_precomputed.jl:249-266): a new, uninitialized search with the same options."""
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        inner = copy_neighborhood_search(nhs.neighborhood_search, search_radius_, n_points)
+        return PrecomputedNeighborhoodSearch(
+            nhs._ndims, search_radius=search_radius_, n_points=n_points,
+            periodic_box=nhs.periodic_box, update_neighborhood_search=inner, backend=nhs.backend,
+            transpose_backend=nhs.transpose_backend, max_neighbors=nhs.max_neighbors,
+            sort_neighbor_lists=nhs.sort_neighbor_lists)
+    cell_list = copy_cell_list(nhs.cell_list, search_radius_, nhs.periodic_box)
+    return GridNeighborhoodSearch(nhs._ndims, search_radius=search_radius_, n_points=n_points,
+                                  periodic_box=nhs.periodic_box, cell_list=cell_list,
+                                  update_strategy=nhs.update_strategy)
+
+
+def freeze_neighborhood_search(nhs):
+    """src/neighborhood_search.jl:112-118, src/nhs_precomputed.jl:268-277.  The lists keep working;
+    the inner grid search is no longer available for updates.  (The scalars needed by the list
+    sweep -- periodic box, radius -- stay with the frozen object.)"""
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        frozen = PrecomputedNeighborhoodSearch.__new__(PrecomputedNeighborhoodSearch)
+        frozen.__dict__.update(nhs.__dict__)
+        frozen.neighborhood_search = None
+        return frozen
+    return nhs
