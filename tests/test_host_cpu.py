@@ -1,0 +1,227 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host-side
+constructor arithmetic equals the oracle's (and hence the reference's KATs), the host mirror
+raises the reference's errors, and the product refuses to compute without a CUDA device.
+No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pn():
+    import pnb200
+    pnb200.build()
+    return pnb200
+
+
+def test_library_exports_every_declared_symbol(pn):
+    header = open(os.path.join(REPO, "include", "pnb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pnb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    lib = C.CDLL(pn.library_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pnb200.h but not exported"
+    # and the ctypes binding covers all of them
+    assert declared == set(pn._lib.SIGNATURES)
+    assert pn._lib.lib().pnb_version() == 100
+
+
+def test_library_is_sm100a_cuda(pn):
+    """The .so carries sm_100a SASS (no PTX-only / other-arch fallback)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", pn.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def _params(pn, nd, r, mn, mx, box=None):
+    L = pn._lib.lib()
+    pf = pn._lib._pf
+    mn = np.ascontiguousarray(mn, np.float32)
+    mx = np.ascontiguousarray(mx, np.float32)
+    pmin, pmax = (C.c_float * 3)(), (C.c_float * 3)()
+    gs, nc = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+    cs = (C.c_float * 3)()
+    bmn = bmx = None
+    if box is not None:
+        b0 = np.ascontiguousarray(box[0], np.float32)
+        b1 = np.ascontiguousarray(box[1], np.float32)
+        bmn, bmx = b0.ctypes.data_as(pf), b1.ctypes.data_as(pf)
+    st = L.pnb_grid_params_f32(nd, np.float32(r), mn.ctypes.data_as(pf), mx.ctypes.data_as(pf),
+                               bmn, bmx, pmin, pmax, gs, nc, cs)
+    return st, (np.array(pmin[:nd], np.float32), np.array(pmax[:nd], np.float32),
+                tuple(gs[:nd]), tuple(nc[:nd]), np.array(cs[:nd], np.float32))
+
+
+def test_grid_params_match_oracle(pn, oracle):
+    """pnb_grid_params_f32 is a pure host function: compare bit for bit with the oracle on the
+    benchmark configurations and on random boxes."""
+    expect = {64: 24, 101: 37, 254: 88, 504: 171}
+    for n, cells in expect.items():
+        r = np.float32(3.0) / np.float32(n + 1)
+        st, (pmin, pmax, gs, nc, cs) = _params(pn, 3, r, np.zeros(3), np.ones(3))
+        assert st == 0 and gs == (cells,) * 3 and nc == (-1,) * 3
+        og = oracle.Grid(3, r, np.zeros(3), np.ones(3))
+        assert og.grid_size == gs
+        assert np.array_equal(og.min_corner, pmin) and np.array_equal(og.max_corner, pmax)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        nd = int(rng.integers(1, 4))
+        mn = rng.normal(0, 3, nd).astype(np.float32)
+        mx = (mn + rng.uniform(0.5, 4, nd)).astype(np.float32)
+        r = np.float32(rng.uniform(0.02, 0.15))
+        periodic = bool(rng.integers(0, 2))
+        box = (mn, mx) if periodic else None
+        st, (pmin, pmax, gs, nc, cs) = _params(pn, nd, r, mn, mx, box)
+        og = oracle.Grid(nd, r, mn, mx, periodic_box=box)
+        assert st == 0
+        assert og.grid_size == gs and og.n_cells == nc
+        assert np.array_equal(og.min_corner, pmin) and np.array_equal(og.max_corner, pmax)
+        assert np.array_equal(og.cell_size, cs)
+
+
+def test_grid_params_periodic_c4(pn, oracle):
+    """200^3 lattice with a box of exactly 200 spacings -> 66 periodic cells in
+    a 69^3 allocated grid; Float32 box 1 with r = 0.1f0 -> 9 cells (App. A.3)."""
+    T = np.float32
+    n = 200
+    s = T(1) / T(n + 1)
+    r = T(3) / T(n + 1)
+    bmn = np.full(3, s / T(2), T)
+    bmx = np.full(3, (T(n) + T(0.5)) * s, T)
+    st, (_, _, gs, nc, cs) = _params(pn, 3, r, bmn, bmx, (bmn, bmx))
+    assert st == 0 and nc == (66, 66, 66) and gs == (69, 69, 69)
+    st, (_, _, gs, nc, cs) = _params(pn, 2, T(0.1), np.zeros(2), np.ones(2), (np.zeros(2), np.ones(2)))
+    assert nc == (9, 9)
+    # fewer than 3 periodic cells -> ArgumentError text of nhs_grid.jl:120-124
+    st, _ = _params(pn, 2, T(0.4), np.zeros(2), np.ones(2), (np.zeros(2), np.ones(2)))
+    assert st == pn._lib.PNB_ERR_ARG
+    assert "needs at least 3 cells in each dimension" in pn._lib.last_error()
+
+
+def test_constructor_errors(pn, kats):
+    """test/nhs_grid.jl:2-19, test/cell_lists/full_grid.jl:3-16."""
+    e = kats["error_texts"]
+    with pytest.raises(pn.ArgumentError, match="FullGridCellList only supports up to 100 dimensions"):
+        pn.FullGridCellList(min_corner=np.zeros(101), max_corner=np.ones(101))
+    with pytest.raises(pn.ArgumentError, match=e["corner_length"]):
+        pn.FullGridCellList(min_corner=np.zeros(3), max_corner=np.ones(2))
+    cl3 = pn.FullGridCellList(min_corner=np.zeros(3), max_corner=np.ones(3))
+    with pytest.raises(pn.ArgumentError, match="a 2D cell list is required for a GridNeighborhoodSearch\\{2\\}"):
+        pn.GridNeighborhoodSearch[2](cell_list=cl3)
+    cl2 = pn.FullGridCellList(min_corner=np.zeros(2), max_corner=np.ones(2))
+    with pytest.raises(pn.ArgumentError, match="is not a valid update strategy"):
+        pn.GridNeighborhoodSearch[2](cell_list=cl2, update_strategy="test")
+    with pytest.raises(pn.ArgumentError, match="is not a valid update strategy"):
+        pn.GridNeighborhoodSearch[2](cell_list=cl2, update_strategy=pn.SemiParallelUpdate())
+    with pytest.raises(pn.ArgumentError, match="`search_radius` cannot be an integer type"):
+        pn.GridNeighborhoodSearch[2](cell_list=cl2, search_radius=1)
+    with pytest.raises(pn.ArgumentError, match="must have the same element type"):
+        pn.GridNeighborhoodSearch[2](
+            cell_list=pn.FullGridCellList(min_corner=np.zeros(2), max_corner=np.ones(2),
+                                          search_radius=np.float32(0.1)),
+            search_radius=np.float32(0.1),
+            periodic_box=pn.PeriodicBox(min_corner=np.zeros(2), max_corner=np.ones(2)))
+    with pytest.raises(pn.ArgumentError, match="`search_radius` cannot be an integer type"):
+        pn.PrecomputedNeighborhoodSearch[2](search_radius=1)
+    assert pn.PrecomputedNeighborhoodSearch.default_max_neighbors(3) == 320
+    assert pn.PrecomputedNeighborhoodSearch.default_max_neighbors(2) == 64
+
+
+def test_copy_neighborhood_search(pn):
+    """test/nhs_grid.jl:21-60: strategy and max_points_per_cell survive; default is ParallelUpdate."""
+    mn, mx = np.zeros(2, np.float32), np.ones(2, np.float32)
+    nhs = pn.GridNeighborhoodSearch[2](cell_list=pn.FullGridCellList(min_corner=mn, max_corner=mx))
+    assert nhs.update_strategy == pn.ParallelUpdate()
+    assert nhs.n_cells == (-1, -1)
+    assert pn.requires_update(nhs) == (False, True)
+    cp = pn.copy_neighborhood_search(nhs, np.float32(1.0), 10)
+    assert pn.ndims(cp) == 2 and pn.search_radius(cp) == np.float32(1.0)
+    assert isinstance(cp.cell_list, pn.FullGridCellList)
+    assert cp.update_strategy == pn.ParallelUpdate()
+    # template corners are unpadded, the copy is padded by 1.001 r (full_grid.jl:66-67,179-185)
+    assert np.array_equal(nhs.cell_list.min_corner, mn)
+    assert np.array_equal(cp.cell_list.min_corner, mn - np.float32(1001.0 / 1000.0 * 1.0))
+    nhs = pn.GridNeighborhoodSearch[2](
+        cell_list=pn.FullGridCellList(min_corner=mn, max_corner=mx, max_points_per_cell=101),
+        update_strategy=pn.SerialUpdate())
+    cp = pn.copy_neighborhood_search(nhs, np.float32(1.0), 10)
+    assert cp.update_strategy == pn.SerialUpdate()
+    assert cp.cell_list.max_points_per_cell == 101
+    pre = pn.PrecomputedNeighborhoodSearch[2](update_neighborhood_search=nhs, max_neighbors=77,
+                                              transpose_backend=True, sort_neighbor_lists=False)
+    assert pn.requires_update(pre) == (True, True)
+    cp = pn.copy_neighborhood_search(pre, np.float32(0.5), 27)
+    assert cp.max_neighbors == 77 and cp.transpose_backend and not cp.sort_neighbor_lists
+    assert pn.search_radius(cp.neighborhood_search) == np.float32(0.5)
+    assert pn.freeze_neighborhood_search(cp).neighborhood_search is None
+    assert pn.freeze_neighborhood_search(nhs) is nhs
+
+
+def test_padded_corners_kat(pn):
+    """test/cell_lists/full_grid.jl:28-29 in Float32: min = 0 - 1.001f0*1, max = 10 + 1.001f0*1."""
+    cl = pn.FullGridCellList(min_corner=np.zeros(3, np.float32), max_corner=np.full(3, 10, np.float32),
+                             search_radius=np.float32(1.0))
+    f = np.float32(1001) / np.float32(1000)
+    assert np.array_equal(cl.min_corner, np.full(3, np.float32(0) - f, np.float32))
+    assert np.array_equal(cl.max_corner, np.full(3, np.float32(10) + f, np.float32))
+    assert cl.n_cells_per_dimension == (13, 13, 13)
+
+
+def test_no_cpu_fallback(pn):
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = pn._lib.lib()
+    assert L.pnb_device_count() == 0
+    nhs = pn.GridNeighborhoodSearch[3](
+        search_radius=np.float32(0.1),
+        cell_list=pn.FullGridCellList(min_corner=np.zeros(3, np.float32),
+                                      max_corner=np.ones(3, np.float32),
+                                      search_radius=np.float32(0.1)))
+    with pytest.raises(pn._lib.CudaError, match="no CUDA device"):
+        nhs._grid()
+    y = torch.zeros((4, 3), dtype=torch.float32)
+    with pytest.raises(TypeError, match="no CPU path"):
+        pn.initialize_(nhs, y, y)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under pointneighbors.jl_b200/ may reference it."""
+    root = os.path.join(REPO, "pointneighbors.jl_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for line in text.splitlines():
+                    s = line.strip()
+                    if s.startswith(("import ", "from ", "#include", "using ", "include(")):
+                        assert "oracle" not in s, f"{f}: {s}"
+                assert "libpn_oracle" not in text and "pn_oracle" not in text.replace(
+                    "oracle/pn_oracle_impl.h", "").replace("oracle pno_", ""), f
+
+
+def test_point_cloud_generator(pn):
+    """test/point_cloud.jl:4-58: size, lattice + two perturbations, cell-sorted, dim 1 major."""
+    c = pn.point_cloud((9, 10, 7), 2.5, seed=1)
+    assert c.shape == (630, 3) and c.dtype == np.float64
+    assert np.all(c.min(0) > 0.5) and np.all(c.max(0) < np.array([9.5, 10.5, 7.5]))
+    assert not np.array_equal(c, pn.point_cloud((9, 10, 7), 2.5, seed=2))
+    assert np.array_equal(c, pn.point_cloud((9, 10, 7), 2.5, seed=1))
+    cells = np.floor(c / 2.5).astype(int)
+    key = cells[:, 0] * 10000 + cells[:, 1] * 100 + cells[:, 2]
+    # sorted by the once-perturbed cell; the second perturbation moves ~few % across cells
+    assert np.mean(np.diff(key) < 0) < 0.25
+    coords, r, mn, mx = pn.benchmark_cloud((8, 6, 4))
+    assert coords.dtype == np.float32 and r == np.float32(3.0) / np.float32(9)
+    assert np.array_equal(mx, np.array([1.0, 0.75, 0.5], np.float32))
