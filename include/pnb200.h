@@ -117,6 +117,14 @@ pnb_status pnb_grid_export_dvov(const pnb_grid *g, int32_t *backend, int32_t *le
  * Returns PNB_ERR_BOUNDS if a query point's stencil leaves the grid.
  * ------------------------------------------------------------------------------------------- */
 
+/* Arithmetic of the per-pair TERMS of the fused n-body / WCSPH closures (never of the neighbour
+ * test, which is always the reference's exact operation sequence):
+ *   0 (default) fast: MUFU rsqrt/rcp + FMA, per-term relative error ~1e-6, sums within the 1e-5 bar;
+ *   1 exact: the Julia operation sequence with IEEE sqrt/div and no FMA -- sums bit-identical to
+ *     the CPU oracle (candidates are visited in the reference's order). */
+void pnb_set_exact_arithmetic(int on);
+int pnb_get_exact_arithmetic(void);
+
 /* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */
 pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
                                    int64_t n, const int32_t *points, int64_t n_points,
@@ -195,6 +203,15 @@ pnb_status pnb_stream_synchronize(void *stream);
 
 /* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
 int64_t pnb_launch_count(void);
+
+/* Optional per-kernel timing (CUDA events recorded on the launching stream around every kernel
+ * of a phase).  Off by default.  pnb_profile_get synchronizes the recorded events and returns
+ * the accumulated device time and launch count of one phase since the last reset. */
+void pnb_profile_enable(int on);
+void pnb_profile_reset(void);
+int pnb_profile_phases(void);
+const char *pnb_profile_name(int phase);
+pnb_status pnb_profile_get(int phase, double *total_ms, int64_t *launches);
 
 #ifdef __cplusplus
 }

@@ -39,10 +39,28 @@ struct CountCl {
     __device__ __forceinline__ void finish(State &s, int, int i_id) const { out[i_id] = (int64_t)s.cnt; }
 };
 
+// MUFU-based approximations used by the fast (default) interaction arithmetic.  They only ever
+// touch the per-pair TERMS; which pairs are delivered is decided by exact arithmetic.
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // benchmarks/n_body.jl:38-48
 //   distance < sqrt(eps(ELTYPE)) && return
 //   dv_ = -G * mass[j] * pos_diff / distance^3 ;  dv[dim, i] += dv_[dim]
-struct NBodyCl {
+// EXACT: the Julia operation sequence with IEEE sqrt/div (bit-identical terms and sums).
+// fast (default): one MUFU.RSQ, FMAs; per-term relative error ~3e-7, far inside the 1e-5 bar.
+template <bool EXACT>
+struct NBodyClT {
     static constexpr bool kCountOnly = false;
     static constexpr int kPayBytes = 4;
     const float *mass_sorted;  // mass of the neighbour points in cell order
@@ -59,13 +77,22 @@ struct NBodyCl {
     template <int ND>
     __device__ __forceinline__ void term(State &s, float px, float py, float pz, float d2, float m) const
     {
-        const float d = __fsqrt_rn(d2);
-        if (d < PNB_SQRT_EPS_F32) return;
-        const float t = __fmul_rn(negG, m);
-        const float d3 = __fmul_rn(__fmul_rn(d, d), d);
-        s.a[0] = __fadd_rn(s.a[0], __fdiv_rn(__fmul_rn(t, px), d3));
-        if (ND > 1) s.a[1] = __fadd_rn(s.a[1], __fdiv_rn(__fmul_rn(t, py), d3));
-        if (ND > 2) s.a[2] = __fadd_rn(s.a[2], __fdiv_rn(__fmul_rn(t, pz), d3));
+        if (EXACT) {
+            const float d = __fsqrt_rn(d2);
+            if (d < PNB_SQRT_EPS_F32) return;
+            const float t = __fmul_rn(negG, m);
+            const float d3 = __fmul_rn(__fmul_rn(d, d), d);
+            s.a[0] = __fadd_rn(s.a[0], __fdiv_rn(__fmul_rn(t, px), d3));
+            if (ND > 1) s.a[1] = __fadd_rn(s.a[1], __fdiv_rn(__fmul_rn(t, py), d3));
+            if (ND > 2) s.a[2] = __fadd_rn(s.a[2], __fdiv_rn(__fmul_rn(t, pz), d3));
+        } else {
+            if (d2 < PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32) return;
+            const float inv_d = fast_rsqrt(d2);
+            const float c = (negG * m) * (inv_d * inv_d * inv_d);
+            s.a[0] = fmaf(c, px, s.a[0]);
+            if (ND > 1) s.a[1] = fmaf(c, py, s.a[1]);
+            if (ND > 2) s.a[2] = fmaf(c, pz, s.a[2]);
+        }
     }
     template <int ND>
     __device__ __forceinline__ void pair(State &s, float px, float py, float pz, float d2, int,
@@ -87,45 +114,89 @@ struct NBodyCl {
 
 // WCSPH continuity + momentum (TrixiParticles.interact!, benchmarks/smoothed_particle_hydrodynamics.jl:45-102).
 // Formulas: oracle/pn_oracle_impl.h pno_cl_wcsph (parity with TrixiParticles itself is unpinned).
-struct WcsphCl {
+// EXACT: the oracle's operation sequence (IEEE div/sqrt, no FMA) -> sums identical to the oracle.
+// fast (default): algebraically the same terms with one MUFU.RSQ per pair (two MUFU.RCP more for
+// approaching pairs), FMAs, and 1/rho_b, m_b/rho_b precomputed once per neighbour:
+//   grad_k = s p_k,  s = (sigma/h) w(q) / d
+//   dv_k  += (pf + visc) s p_k
+//   drho  += (m_b/rho_b) s [ rho_a (v_ab . p) + 2 delta h c (rho_a - rho_b) ]     (psi.grad = 2 (rho_a - rho_b) s)
+template <bool EXACT>
+struct WcsphClT {
     static constexpr bool kCountOnly = false;
-    static constexpr int kPayBytes = 16 + 8;
+    static constexpr int kPayBytes = 16 + 16;
+    static constexpr int kPlane1 = 16 * 512;   // byte offset of plane 1 = sizeof(float4) * kCap
     const float4 *vrho_sorted;  // (vx, vy, vz, rho) of the neighbour points, cell order
-    const float2 *mp_sorted;    // (mass, pressure) of the neighbour points, cell order
+    const float4 *mp_sorted;    // (mass, pressure, 1/rho, mass/rho) of the neighbour points
     const float *v_x;           // general path: state of the points looped over, (nd+1) per point
     const float *p_x;
     pnb_wcsph_params prm;
     float *dv;
     int nd;
-    struct State { float v[3]; float rho, p; float acc[4]; };
+    struct State { float v[3]; float rho, p, inv_rho; float acc[4]; };
 
     __device__ __forceinline__ void init(State &s, bool active, int i_sorted, int i_id) const
     {
         s.acc[0] = s.acc[1] = s.acc[2] = s.acc[3] = 0.f;
-        s.v[0] = s.v[1] = s.v[2] = 0.f; s.rho = 1.f; s.p = 0.f;
+        s.v[0] = s.v[1] = s.v[2] = 0.f; s.rho = 1.f; s.p = 0.f; s.inv_rho = 1.f;
         if (!active) return;
         if (i_sorted >= 0) {
             const float4 a = vrho_sorted[i_sorted];
+            const float4 b = mp_sorted[i_sorted];
             s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.rho = a.w;
-            s.p = mp_sorted[i_sorted].y;
+            s.p = b.y; s.inv_rho = b.z;
         } else {
             const int ns = nd + 1;
             for (int k = 0; k < nd; k++) s.v[k] = v_x[(int64_t)i_id * ns + k];
             s.rho = v_x[(int64_t)i_id * ns + nd];
             s.p = p_x[i_id];
+            s.inv_rho = __fdiv_rn(1.f, s.rho);
         }
     }
     __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi) const
     {
         reinterpret_cast<float4 *>(pay)[slot] = vrho_sorted[gi];
-        reinterpret_cast<float2 *>(pay + 16 * 512)[slot] = mp_sorted[gi];  // plane 1 after kCap float4
+        reinterpret_cast<float4 *>(pay + kPlane1)[slot] = mp_sorted[gi];
     }
     __device__ __forceinline__ void count(State &, int) const {}
 
     template <int ND>
-    __device__ __forceinline__ void term(State &s, float px, float py, float pz, float d2,
-                                         float4 vb, float2 mpb) const
+    __device__ __forceinline__ void term_fast(State &s, float px, float py, float pz, float d2,
+                                              float4 vb, float4 mpb) const
     {
+        // pairs closer than sqrt(eps) (the self pair) contribute exactly zero in the reference
+        if (d2 < PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32) return;
+        const float h = prm.smoothing_length;
+        const float inv_d = fast_rsqrt(d2);
+        const float d = d2 * inv_d;
+        const float q = d * prm_inv_h;
+        const float t = fmaf(-0.5f, q, 1.f);
+        const float w = (-5.f * q) * (t * t * t);       // q <= 2 inside the search radius
+        const float sg = (prm_kh * w) * inv_d;
+        const float rho_a = s.rho, rho_b = vb.w;
+        const float m_b = mpb.x, p_b = mpb.y, inv_rho_b = mpb.z, vol_b = mpb.w;
+        float coef = (-m_b * (s.p + p_b)) * (s.inv_rho * inv_rho_b);
+        const float vdx = s.v[0] - vb.x, vdy = s.v[1] - vb.y, vdz = s.v[2] - vb.z;
+        float vr = vdx * px;
+        if (ND > 1) vr = fmaf(vdy, py, vr);
+        if (ND > 2) vr = fmaf(vdz, pz, vr);
+        if (vr < 0.f) {
+            const float mu = (h * vr) * fast_rcp(fmaf(prm.epsilon, h * h, d2));
+            const float pi_ab = (prm_ac * mu - prm.beta * (mu * mu)) * fast_rcp(0.5f * (rho_a + rho_b));
+            coef = fmaf(m_b, pi_ab, coef);
+        }
+        coef *= sg;
+        s.acc[0] = fmaf(coef, px, s.acc[0]);
+        if (ND > 1) s.acc[1] = fmaf(coef, py, s.acc[1]);
+        if (ND > 2) s.acc[2] = fmaf(coef, pz, s.acc[2]);
+        s.acc[3] = fmaf(vol_b * sg, fmaf(rho_a, vr, prm_dhc2 * (rho_a - rho_b)), s.acc[3]);
+    }
+
+    template <int ND>
+    __device__ __forceinline__ void term(State &s, float px, float py, float pz, float d2,
+                                         float4 vb, float4 mpb4) const
+    {
+        if (!EXACT) { term_fast<ND>(s, px, py, pz, d2, vb, mpb4); return; }
+        const float2 mpb = make_float2(mpb4.x, mpb4.y);
         const float d = __fsqrt_rn(d2);
         const float rho_a = s.rho, rho_b = vb.w;
         const float m_b = mpb.x, p_b = mpb.y;
@@ -191,7 +262,7 @@ struct WcsphCl {
                                          const unsigned char *pay, int slot, int) const
     {
         const float4 vb = reinterpret_cast<const float4 *>(pay)[slot];
-        const float2 mpb = reinterpret_cast<const float2 *>(pay + 16 * 512)[slot];
+        const float4 mpb = reinterpret_cast<const float4 *>(pay + kPlane1)[slot];
         term<ND>(s, px, py, pz, d2, vb, mpb);
     }
     template <int ND>
@@ -206,6 +277,11 @@ struct WcsphCl {
         for (int k = 0; k < nd; k++) dv[(int64_t)i_id * ns + k] = s.acc[k];
         dv[(int64_t)i_id * ns + nd] = s.acc[3];
     }
+    // derived constants of the fast path, filled by the host
+    float prm_inv_h;   // 1 / h
+    float prm_kh;      // kernel_norm / h
+    float prm_ac;      // alpha * c
+    float prm_dhc2;    // 2 * delta * h * c
 };
 
 }  // namespace pnb

@@ -52,6 +52,31 @@ extern int64_t g_launch_count;
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
+// optional per-kernel timing with CUDA events on the launching stream (pnb_profile_*), used by
+// bench.py for the roofline numbers.  Off by default: no events are recorded then.
+// ---------------------------------------------------------------------------------------------
+enum Phase {
+    PH_BUILD_CELL_COUNT = 0,  // k_cell_count
+    PH_BUILD_SCAN,            // k_scan_lookback (+ its two tiny memsets)
+    PH_BUILD_SCATTER,         // k_scatter
+    PH_BUILD_FINALIZE,        // k_finalize_cells
+    PH_GATHER,                // k_gather_* (payload into cell order)
+    PH_SWEEP_CELLS,           // k_sweep_cells
+    PH_SWEEP_POINTS,          // k_sweep_points
+    PH_NLIST_SORT,            // k_sort_lists
+    PH_NLIST_SWEEP,           // k_tlsph_defgrad / k_nlist_pairs
+    PH_EXPORT,                // export kernels
+    PH_COUNT_
+};
+struct ProfScope {
+    int phase;
+    cudaStream_t stream;
+    void *slot;
+    ProfScope(int phase, cudaStream_t s);
+    ~ProfScope();
+};
+
+// ---------------------------------------------------------------------------------------------
 // device arithmetic
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

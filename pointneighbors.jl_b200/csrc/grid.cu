@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "grid.cuh"
 
@@ -32,6 +33,57 @@ pnb_status cuda_fail(cudaError_t e, const char *what)
     set_error("CUDA error: %s (%s)", cudaGetErrorString(e), what);
     return PNB_ERR_CUDA;
 }
+
+// ---- profiling ----------------------------------------------------------------------------
+struct ProfRec { int phase; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[PH_COUNT_];
+static int64_t g_prof_n[PH_COUNT_];
+
+static cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(int phase_, cudaStream_t s) : phase(phase_), stream(s), slot(nullptr)
+{
+    if (!g_prof_on) return;
+    ProfRec *r = new ProfRec{phase, prof_event(), prof_event()};
+    cudaEventRecord(r->a, stream);
+    slot = r;
+}
+ProfScope::~ProfScope()
+{
+    if (!slot) return;
+    ProfRec *r = static_cast<ProfRec *>(slot);
+    cudaEventRecord(r->b, stream);
+    g_prof_recs.push_back(*r);
+    delete r;
+}
+
+static void prof_collect()
+{
+    for (ProfRec &r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_prof_ms[r.phase] += ms;
+            g_prof_n[r.phase] += 1;
+        }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    cudaGetLastError();
+}
+
+static const char *kPhaseNames[PH_COUNT_] = {
+    "k_cell_count", "k_scan_lookback", "k_scatter", "k_finalize_cells", "k_gather",
+    "k_sweep_cells", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export"};
 
 static const char *kDomainMsg =
     "particle coordinates are NaN or outside the domain bounds of the cell list";
@@ -130,6 +182,26 @@ using namespace pnb;
 extern "C" int pnb_version(void) { return PNB200_VERSION; }
 extern "C" const char *pnb_last_error(void) { return t_err; }
 extern "C" int64_t pnb_launch_count(void) { return g_launch_count; }
+
+extern "C" void pnb_profile_enable(int on) { g_prof_on = on != 0; }
+extern "C" void pnb_profile_reset(void)
+{
+    prof_collect();
+    for (int i = 0; i < PH_COUNT_; i++) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+}
+extern "C" int pnb_profile_phases(void) { return PH_COUNT_; }
+extern "C" const char *pnb_profile_name(int phase)
+{
+    return (phase >= 0 && phase < PH_COUNT_) ? kPhaseNames[phase] : "";
+}
+extern "C" pnb_status pnb_profile_get(int phase, double *total_ms, int64_t *launches)
+{
+    if (phase < 0 || phase >= PH_COUNT_) { set_error("no such phase"); return PNB_ERR_ARG; }
+    prof_collect();
+    if (total_ms) *total_ms = g_prof_ms[phase];
+    if (launches) *launches = g_prof_n[phase];
+    return PNB_OK;
+}
 
 extern "C" int pnb_device_count(void)
 {
@@ -492,6 +564,7 @@ static pnb_status scan_impl(pnb_grid *g, const uint32_t *in, OutT *out, int64_t 
         PNB_CUDA(cudaMalloc(&g->scan_status, sizeof(unsigned long long) * (size_t)tiles));
         g->scan_tiles_cap = tiles;
     }
+    ProfScope ps(PH_BUILD_SCAN, s);
     PNB_CUDA(cudaMemsetAsync(g->scan_status, 0, sizeof(unsigned long long) * (size_t)tiles, s));
     PNB_CUDA(cudaMemsetAsync(g->scan_ticket, 0, sizeof(unsigned int), s));
     k_scan_lookback<OutT><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, n, g->scan_status,
@@ -537,6 +610,7 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
     PNB_CUDA(cudaMemsetAsync(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 1), s));
     if (n_idx > 0) {
         unsigned blocks = (unsigned)div_up(n_idx, kBuildThreads);
+        ProfScope ps(PH_BUILD_CELL_COUNT, s);
         k_cell_count<ND><<<blocks, kBuildThreads, 0, s>>>(g->p, y, n_idx, idx, base, g->cell_rank,
                                                           g->cell_count, g->d_err);
         PNB_LAUNCHED();
@@ -545,10 +619,14 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
     if (st != PNB_OK) return st;
     if (n_idx > 0) {
         unsigned blocks = (unsigned)div_up(n_idx, kBuildThreads);
-        k_scatter<<<blocks, kBuildThreads, 0, s>>>(n_idx, idx, base, g->cell_rank, g->cell_start,
-                                                   g->ids_tmp);
-        PNB_LAUNCHED();
+        {
+            ProfScope ps(PH_BUILD_SCATTER, s);
+            k_scatter<<<blocks, kBuildThreads, 0, s>>>(n_idx, idx, base, g->cell_rank,
+                                                       g->cell_start, g->ids_tmp);
+            PNB_LAUNCHED();
+        }
         unsigned fblocks = (unsigned)div_up(C * 32, 256);
+        ProfScope ps(PH_BUILD_FINALIZE, s);
         k_finalize_cells<ND><<<fblocks, 256, 0, s>>>((int)C, g->cell_start, g->ids_tmp, y,
                                                      g->cell_points, g->sorted);
         PNB_LAUNCHED();

@@ -80,11 +80,13 @@ static pnb_status launch_list_nd(pnb_grid *g, bool fast, const float *x, int64_t
         const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
         if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
         const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
-        const size_t smem = (size_t)kCap * (sizeof(float4) + CL::kPayBytes);
+        const size_t smem = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
+        ProfScope ps(PH_SWEEP_CELLS, s);
         k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem, s>>>(
             g->p, g->cell_start, g->sorted, cl);
         PNB_LAUNCHED();
     } else if (nx > 0) {
+        ProfScope ps(PH_SWEEP_POINTS, s);
         k_sweep_points<ND, PER, CL><<<(unsigned)div_up(nx, 128), 128, 0, s>>>(
             g->p, g->cell_start, g->sorted, x, nx, nullptr, 0, cl, g->d_err);
         PNB_LAUNCHED();
@@ -357,6 +359,7 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     st = launch_list(g, fast, x, nx, ListFillCl{l->offsets, l->ids}, s);
     if (st != PNB_OK) return fail(st);
     if (sort && nx > 0 && total > 0) {
+        ProfScope ps(PH_NLIST_SORT, s);
         k_sort_lists<<<(unsigned)div_up(nx, kSortWarps), kSortWarps * 32, 0, s>>>(nx, l->offsets,
                                                                                   l->ids);
         cudaError_t e = cudaGetLastError();
@@ -408,6 +411,7 @@ extern "C" pnb_status pnb_nlist_pairs_f32(const pnb_nlist *l, const pnb_grid *g,
     if (l->nx > 0) {
         const unsigned blocks = (unsigned)div_up(l->nx * 32, 256);
         const bool per = g->p.periodic != 0;
+        ProfScope ps(PH_NLIST_SWEEP, s);
 #define PAIRS(ND)                                                                                  \
     if (per) k_nlist_pairs<ND, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, x, y, pos_diff, distance); \
     else k_nlist_pairs<ND, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, x, y, pos_diff, distance)
@@ -434,6 +438,7 @@ extern "C" pnb_status pnb_tlsph_deformation_grad_f32(const pnb_nlist *l, const p
     if (l->nx > 0) {
         const unsigned blocks = (unsigned)div_up(l->nx * 32, 256);
         const bool per = g->p.periodic != 0;
+        ProfScope ps(PH_NLIST_SWEEP, s);
 #define DEFGRAD(ND)                                                                                 \
     if (per) k_tlsph_defgrad<ND, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, X0, xcur, mass, rho0, L, smoothing_length, kernel_norm, F); \
     else k_tlsph_defgrad<ND, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, X0, xcur, mass, rho0, L, smoothing_length, kernel_norm, F)

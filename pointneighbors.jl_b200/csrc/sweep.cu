@@ -18,7 +18,7 @@ __global__ void k_gather_f32(int64_t n, const int32_t *__restrict__ ids,
 __global__ void k_gather_wcsph(int64_t n, int nd, const int32_t *__restrict__ ids,
                                const float *__restrict__ v, const float *__restrict__ mass,
                                const float *__restrict__ pressure, float4 *__restrict__ vrho,
-                               float2 *__restrict__ mp)
+                               float4 *__restrict__ mp)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -30,8 +30,14 @@ __global__ void k_gather_wcsph(int64_t n, int nd, const int32_t *__restrict__ id
     if (nd > 2) a.z = __ldg(v + id * ns + 2);
     a.w = __ldg(v + id * ns + nd);
     vrho[i] = a;
-    mp[i] = make_float2(__ldg(mass + id), __ldg(pressure + id));
+    const float m = __ldg(mass + id);
+    // 1/rho_b and m_b/rho_b once per neighbour instead of once per pair (fast path)
+    mp[i] = make_float4(m, __ldg(pressure + id), __fdiv_rn(1.f, a.w), __fdiv_rn(m, a.w));
 }
+
+// pnb_set_exact_arithmetic: 0 (default) = fast per-pair terms (MUFU + FMA, |error| << 1e-5),
+// 1 = the oracle's IEEE operation sequence (sums bit-identical to the oracle).
+static int g_exact_arithmetic = 0;
 
 static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
                                  int64_t *n_loop)
@@ -61,11 +67,13 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, const float *x, int64_t n_lo
         const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
         if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
         const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
-        const size_t smem = (size_t)kCap * (sizeof(float4) + CL::kPayBytes);
+        const size_t smem = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
+        ProfScope ps(PH_SWEEP_CELLS, s);
         k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem, s>>>(
             g->p, g->cell_start, g->sorted, cl);
         PNB_LAUNCHED();
     } else if (n_loop > 0) {
+        ProfScope ps(PH_SWEEP_POINTS, s);
         k_sweep_points<ND, PER, CL><<<(unsigned)div_up(n_loop, 128), 128, 0, s>>>(
             g->p, g->cell_start, g->sorted, x, n_loop, points, base, cl, g->d_err);
         PNB_LAUNCHED();
@@ -95,6 +103,9 @@ static pnb_status launch_sweep(pnb_grid *g, bool fast, const float *x, int64_t n
 }  // namespace pnb
 
 using namespace pnb;
+
+extern "C" void pnb_set_exact_arithmetic(int on) { g_exact_arithmetic = on != 0; }
+extern "C" int pnb_get_exact_arithmetic(void) { return g_exact_arithmetic; }
 
 extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx,
                                               const float *y, int64_t n, const int32_t *points,
@@ -131,11 +142,17 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
     st = ensure_scratch(g, sizeof(float) * (size_t)g->n_built);
     if (st != PNB_OK) return st;
     float *mass_sorted = reinterpret_cast<float *>(g->scratch);
-    k_gather_f32<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(g->n_built, g->cell_points,
+    {
+        ProfScope ps(PH_GATHER, s);
+        k_gather_f32<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(g->n_built, g->cell_points,
                                                                    mass, mass_sorted);
-    PNB_LAUNCHED();
-    NBodyCl cl{mass_sorted, -G, dv, nd};
-    st = launch_sweep(g, is_fast_path(g, x, nx, points), x, n_loop, points, index_base, cl, s);
+        PNB_LAUNCHED();
+    }
+    const bool fastp = is_fast_path(g, x, nx, points);
+    if (g_exact_arithmetic)
+        st = launch_sweep(g, fastp, x, n_loop, points, index_base, NBodyClT<true>{mass_sorted, -G, dv, nd}, s);
+    else
+        st = launch_sweep(g, fastp, x, n_loop, points, index_base, NBodyClT<false>{mass_sorted, -G, dv, nd}, s);
     if (st != PNB_OK) return st;
     return check_err_word(g, s);
 }
@@ -160,15 +177,27 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
     if (g->template_search || g->n_built == 0) return check_err_word(g, s);
     const int64_t nb = g->n_built;
     const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
-    st = ensure_scratch(g, off_mp + (int64_t)sizeof(float2) * nb);
+    st = ensure_scratch(g, off_mp + (int64_t)sizeof(float4) * nb);
     if (st != PNB_OK) return st;
     float4 *vrho = reinterpret_cast<float4 *>(g->scratch);
-    float2 *mp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
-    k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, g->cell_points, v_y, mass_y,
-                                                             pressure_y, vrho, mp);
-    PNB_LAUNCHED();
-    WcsphCl cl{vrho, mp, v_x, pressure_x, *params, dv, nd};
-    st = launch_sweep(g, is_fast_path(g, x, nx, points), x, n_loop, points, index_base, cl, s);
+    float4 *mp = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
+    {
+        ProfScope ps(PH_GATHER, s);
+        k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, g->cell_points, v_y,
+                                                                 mass_y, pressure_y, vrho, mp);
+        PNB_LAUNCHED();
+    }
+    const bool fastp = is_fast_path(g, x, nx, points);
+    const float h = params->smoothing_length;
+    const float inv_h = 1.0f / h, kh = params->kernel_norm / h;
+    const float ac = params->alpha * params->sound_speed;
+    const float dhc2 = 2.0f * params->delta * h * params->sound_speed;
+    if (g_exact_arithmetic)
+        st = launch_sweep(g, fastp, x, n_loop, points, index_base,
+                          WcsphClT<true>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2}, s);
+    else
+        st = launch_sweep(g, fastp, x, n_loop, points, index_base,
+                          WcsphClT<false>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2}, s);
     if (st != PNB_OK) return st;
     return check_err_word(g, s);
 }

@@ -29,7 +29,29 @@ namespace pnb {
 constexpr int kTX = 8;            // cells (= warps) per CTA in k_sweep_cells
 constexpr int kCellThreads = kTX * 32;
 constexpr int kCap = 512;         // staged candidates per chunk
+constexpr int kCapPad = kCap + 32; // position buffer is read up to 31 slots past the chunk (masked)
 constexpr int kSlots = kTX + 2;   // x-neighbour cells of a tile in one row
+
+// One block of 32 staged candidates against the lane's own point: bit k of the result is set
+// iff candidate k is within the search radius (same operations, same order as
+// src/nhs_grid.jl:547-555).  All lanes read the same address: broadcast LDS.128.
+template <int ND, bool PER>
+__device__ __forceinline__ unsigned test_block(const GridP &g, const float4 *__restrict__ cp,
+                                               float xi, float yi, float zi)
+{
+    unsigned hits = 0u;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const float4 pj = cp[k];
+        float px = __fsub_rn(xi, pj.x);
+        float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
+        float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
+        float d2 = dist2<ND>(px, py, pz);
+        d2 = maybe_periodic_fix<ND, PER>(g, d2, px, py, pz);
+        if (d2 <= g.r2) hits |= 1u << k;
+    }
+    return hits;
+}
 
 // Candidate views handed to the closures --------------------------------------------------------
 // Shared-memory view: payload planes are arrays of kCap elements.
@@ -42,7 +64,7 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_pos = reinterpret_cast<float4 *>(smem_raw);
-    unsigned char *s_pay = smem_raw + sizeof(float4) * kCap;
+    unsigned char *s_pay = smem_raw + sizeof(float4) * kCapPad;
     __shared__ uint32_t s_begin[kSlots];   // global begin of each slot's cell
     __shared__ uint32_t s_prefix[kSlots + 1];
 
@@ -149,52 +171,45 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                     }
                     __syncthreads();
                     // ---- test + interact -------------------------------------------------
+                    // Super-blocks of 128 candidates: four 32-bit hit masks per lane are filled by
+                    // fully unrolled test blocks (candidates past the warp's range are masked off,
+                    // so there is no remainder loop), then drained bit by bit.
                     if (warp_active) {
                         const uint32_t a0 = max(w_q0, q0), a1 = min(w_q1, q1);
-                        for (uint32_t blk = a0; blk < a1; blk += 32) {
-                            const int nb = (int)min(32u, a1 - blk);
-                            const float4 *cp = s_pos + (blk - q0);
-                            unsigned hits = 0;
-                            if (nb == 32) {
-#pragma unroll 8
-                                for (int k = 0; k < 32; k++) {
-                                    const float4 pj = cp[k];
-                                    float px = __fsub_rn(xi, pj.x);
-                                    float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
-                                    float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
-                                    float d2 = dist2<ND>(px, py, pz);
-                                    d2 = maybe_periodic_fix<ND, PER>(g, d2, px, py, pz);
-                                    hits |= (d2 <= g.r2 ? 1u : 0u) << k;
-                                }
-                            } else {
-                                for (int k = 0; k < nb; k++) {
-                                    const float4 pj = cp[k];
-                                    float px = __fsub_rn(xi, pj.x);
-                                    float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
-                                    float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
-                                    float d2 = dist2<ND>(px, py, pz);
-                                    d2 = maybe_periodic_fix<ND, PER>(g, d2, px, py, pz);
-                                    hits |= (d2 <= g.r2 ? 1u : 0u) << k;
+                        for (uint32_t sb = a0; sb < a1; sb += 128) {
+                            unsigned m[4];
+#pragma unroll
+                            for (int bb = 0; bb < 4; bb++) {
+                                const uint32_t blk = sb + 32u * bb;
+                                m[bb] = 0u;
+                                if (blk < a1) {   // warp-uniform
+                                    unsigned hh = test_block<ND, PER>(g, s_pos + (blk - q0), xi, yi, zi);
+                                    const uint32_t nv = a1 - blk;
+                                    if (nv < 32u) hh &= (1u << nv) - 1u;
+                                    m[bb] = active ? hh : 0u;
                                 }
                             }
-                            if (!active) hits = 0;
                             if (CL::kCountOnly) {
-                                cl.count(st, __popc(hits));
+                                cl.count(st, __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
                             } else {
-                                // deferred interaction: one set bit per round and lane
-                                while (__any_sync(0xffffffffu, hits != 0)) {
-                                    if (hits) {
-                                        const int k = __ffs(hits) - 1;
-                                        hits &= hits - 1;
-                                        const float4 pj = cp[k];
+                                unsigned any = m[0] | m[1] | m[2] | m[3];
+                                while (__any_sync(0xffffffffu, any != 0u)) {
+                                    if (any) {
+                                        int k;
+                                        if (m[0]) { k = __ffs(m[0]) - 1; m[0] &= m[0] - 1u; }
+                                        else if (m[1]) { k = 31 + __ffs(m[1]); m[1] &= m[1] - 1u; }
+                                        else if (m[2]) { k = 63 + __ffs(m[2]); m[2] &= m[2] - 1u; }
+                                        else { k = 95 + __ffs(m[3]); m[3] &= m[3] - 1u; }
+                                        const int slot = (int)(sb - q0) + k;
+                                        const float4 pj = s_pos[slot];
                                         float px = __fsub_rn(xi, pj.x);
                                         float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
                                         float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
                                         float d2 = dist2<ND>(px, py, pz);
                                         d2 = maybe_periodic_fix<ND, PER>(g, d2, px, py, pz);
                                         cl.template pair<ND>(st, px, py, pz, d2,
-                                                             __float_as_int(pj.w), s_pay,
-                                                             (int)(blk - q0) + k, kCap);
+                                                             __float_as_int(pj.w), s_pay, slot, kCap);
+                                        any = m[0] | m[1] | m[2] | m[3];
                                     }
                                 }
                             }

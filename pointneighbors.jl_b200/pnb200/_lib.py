@@ -78,6 +78,13 @@ SIGNATURES = {
     "pnb_memset": (C.c_int, [_vp, C.c_int, _i64, _vp]),
     "pnb_stream_synchronize": (C.c_int, [_vp]),
     "pnb_launch_count": (_i64, []),
+    "pnb_set_exact_arithmetic": (None, [C.c_int]),
+    "pnb_get_exact_arithmetic": (C.c_int, []),
+    "pnb_profile_enable": (None, [C.c_int]),
+    "pnb_profile_reset": (None, []),
+    "pnb_profile_phases": (C.c_int, []),
+    "pnb_profile_name": (C.c_char_p, [C.c_int]),
+    "pnb_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), _pi64]),
 }
 
 
@@ -124,3 +131,18 @@ def check(status: int) -> None:
     if status == PNB_ERR_BOUNDS:
         raise BoundsError(msg)
     raise CudaError(msg)
+
+
+def profile(enable=None, reset=False):
+    """Per-kernel device times {name: (total_ms, launches)} accumulated since the last reset."""
+    L = lib()
+    if enable is not None:
+        L.pnb_profile_enable(int(bool(enable)))
+    out = {}
+    for ph in range(L.pnb_profile_phases()):
+        ms, n = C.c_double(), C.c_int64()
+        check(L.pnb_profile_get(ph, C.byref(ms), C.byref(n)))
+        out[L.pnb_profile_name(ph).decode()] = (ms.value, n.value)
+    if reset:
+        L.pnb_profile_reset()
+    return out

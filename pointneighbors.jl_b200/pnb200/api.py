@@ -35,7 +35,7 @@ __all__ = [
     "initialize_", "update_", "initialize", "update", "foreach_point_neighbor",
     "copy_neighborhood_search", "freeze_neighborhood_search", "requires_update",
     "search_radius", "ndims", "CountNeighbors", "NBodyGravity", "WCSPHInteract",
-    "TLSPHDeformationGradient", "wendland_c2_norm",
+    "TLSPHDeformationGradient", "wendland_c2_norm", "set_exact_arithmetic",
 ]
 
 _EPS64 = 2.220446049250313e-16
@@ -483,6 +483,13 @@ class TLSPHDeformationGradient:
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def set_exact_arithmetic(on: bool) -> None:
+    """Per-pair terms of the fused n-body / WCSPH closures: False (default) = MUFU + FMA fast
+    arithmetic (within the 1e-5 bar), True = the reference's IEEE operation sequence (sums
+    bit-identical to the CPU oracle).  The neighbour test itself is always exact."""
+    _lib.lib().pnb_set_exact_arithmetic(int(bool(on)))
 
 
 def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_search, *,
