@@ -5,7 +5,9 @@
 //   State                 per-point accumulators, live in registers of the lane that owns point i
 //   init(st, active, i_sorted, i_id)   i_sorted >= 0: cell-ordered index (x === y fast path)
 //                                      i_sorted <  0: general path, i_id indexes the x arrays
-//   stage(pay, slot, gi)  copy the payload of cell-ordered candidate gi into shared slot `slot`
+//   stage(pay, slot, gi, cap)  copy the payload of cell-ordered candidate gi into shared slot
+//                         `slot`; payload planes are arrays of `cap` elements
+//   merge(st, other)      add the partial accumulators of another warp (sweep_tiles.cuh)
 //   pair<ND>(st, px, py, pz, d2, j_id, pay, slot, cap)   one accepted pair, payload in shared memory
 //   pair_global<ND>(st, px, py, pz, d2, j_id, gi)        same, payload read from global memory
 //   finish(st, i_sorted, i_id)         write the result of point i (original numbering)
@@ -28,8 +30,9 @@ struct CountCl {
     int64_t *out;
     struct State { int cnt; };
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
-    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t) const {}
+    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
     __device__ __forceinline__ void count(State &s, int c) const { s.cnt += c; }
+    __device__ __forceinline__ void merge(State &s, const State &o) const { s.cnt += o.cnt; }
     template <int ND>
     __device__ __forceinline__ void pair(State &, float, float, float, float, int,
                                          const unsigned char *, int, int) const {}
@@ -69,11 +72,15 @@ struct NBodyClT {
     int nd;
     struct State { float a[3]; };
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.a[0] = s.a[1] = s.a[2] = 0.f; }
-    __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi) const
+    __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi, int) const
     {
         reinterpret_cast<float *>(pay)[slot] = mass_sorted[gi];
     }
     __device__ __forceinline__ void count(State &, int) const {}
+    __device__ __forceinline__ void merge(State &s, const State &o) const
+    {
+        s.a[0] += o.a[0]; s.a[1] += o.a[1]; s.a[2] += o.a[2];
+    }
     template <int ND>
     __device__ __forceinline__ void term(State &s, float px, float py, float pz, float d2, float m) const
     {
@@ -124,7 +131,6 @@ template <bool EXACT>
 struct WcsphClT {
     static constexpr bool kCountOnly = false;
     static constexpr int kPayBytes = 16 + 16;
-    static constexpr int kPlane1 = 16 * 512;   // byte offset of plane 1 = sizeof(float4) * kCap
     const float4 *vrho_sorted;  // (vx, vy, vz, rho) of the neighbour points, cell order
     const float4 *mp_sorted;    // (mass, pressure, 1/rho, mass/rho) of the neighbour points
     const float *v_x;           // general path: state of the points looped over, (nd+1) per point
@@ -152,12 +158,16 @@ struct WcsphClT {
             s.inv_rho = __fdiv_rn(1.f, s.rho);
         }
     }
-    __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi) const
+    __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi, int cap) const
     {
         reinterpret_cast<float4 *>(pay)[slot] = vrho_sorted[gi];
-        reinterpret_cast<float4 *>(pay + kPlane1)[slot] = mp_sorted[gi];
+        reinterpret_cast<float4 *>(pay + 16 * cap)[slot] = mp_sorted[gi];   // plane 1
     }
     __device__ __forceinline__ void count(State &, int) const {}
+    __device__ __forceinline__ void merge(State &s, const State &o) const
+    {
+        s.acc[0] += o.acc[0]; s.acc[1] += o.acc[1]; s.acc[2] += o.acc[2]; s.acc[3] += o.acc[3];
+    }
 
     template <int ND>
     __device__ __forceinline__ void term_fast(State &s, float px, float py, float pz, float d2,
@@ -259,10 +269,10 @@ struct WcsphClT {
     }
     template <int ND>
     __device__ __forceinline__ void pair(State &s, float px, float py, float pz, float d2, int,
-                                         const unsigned char *pay, int slot, int) const
+                                         const unsigned char *pay, int slot, int cap) const
     {
         const float4 vb = reinterpret_cast<const float4 *>(pay)[slot];
-        const float4 mpb = reinterpret_cast<const float4 *>(pay + kPlane1)[slot];
+        const float4 mpb = reinterpret_cast<const float4 *>(pay + 16 * cap)[slot];
         term<ND>(s, px, py, pz, d2, vb, mpb);
     }
     template <int ND>

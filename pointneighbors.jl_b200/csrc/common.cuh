@@ -61,7 +61,8 @@ enum Phase {
     PH_BUILD_SCATTER,         // k_scatter
     PH_BUILD_FINALIZE,        // k_finalize_cells
     PH_GATHER,                // k_gather_* (payload into cell order)
-    PH_SWEEP_CELLS,           // k_sweep_cells
+    PH_SWEEP_CELLS,           // k_sweep_cells / k_sweep_tiles
+    PH_SWEEP_OVERFLOW,        // k_sweep_overflow
     PH_SWEEP_POINTS,          // k_sweep_points
     PH_NLIST_SORT,            // k_sort_lists
     PH_NLIST_SWEEP,           // k_tlsph_defgrad / k_nlist_pairs
@@ -151,15 +152,31 @@ __device__ __forceinline__ float dist2(float px, float py, float pz)
     return d2;
 }
 
+// The scalars the distance test needs, kept in registers (passing GridP by reference into a
+// non-inlined function would force the kernel parameters through local memory).
+struct PerP {
+    float r2;        // search_radius^2
+    float wrap_d2;   // see maybe_periodic_fix
+    float bs[3];     // periodic box size
+};
+__device__ __forceinline__ PerP make_perp(const GridP &g)
+{
+    PerP q;
+    q.r2 = g.r2; q.wrap_d2 = g.wrap_d2;
+    q.bs[0] = g.bsize[0]; q.bs[1] = g.bsize[1]; q.bs[2] = g.bsize[2];
+    return q;
+}
+
 // compute_periodic_distance (src/neighborhood_search.jl:428-435), applied by the caller only
 // when d2 > r2:   pos_diff -= size .* round.(pos_diff ./ size);  d2 = dot(pos_diff, pos_diff)
 // Julia's round is ties-to-even == rintf.
 template <int ND>
-__device__ __noinline__ float periodic_fix(const GridP &g, float &px, float &py, float &pz)
+__device__ __noinline__ float periodic_fix(float bx, float by, float bz, float &px, float &py,
+                                           float &pz)
 {
-    px = __fsub_rn(px, __fmul_rn(g.bsize[0], rintf(__fdiv_rn(px, g.bsize[0]))));
-    if (ND > 1) py = __fsub_rn(py, __fmul_rn(g.bsize[1], rintf(__fdiv_rn(py, g.bsize[1]))));
-    if (ND > 2) pz = __fsub_rn(pz, __fmul_rn(g.bsize[2], rintf(__fdiv_rn(pz, g.bsize[2]))));
+    px = __fsub_rn(px, __fmul_rn(bx, rintf(__fdiv_rn(px, bx))));
+    if (ND > 1) py = __fsub_rn(py, __fmul_rn(by, rintf(__fdiv_rn(py, by))));
+    if (ND > 2) pz = __fsub_rn(pz, __fmul_rn(bz, rintf(__fdiv_rn(pz, bz))));
     return dist2<ND>(px, py, pz);
 }
 
@@ -168,11 +185,11 @@ __device__ __noinline__ float periodic_fix(const GridP &g, float &px, float &py,
 // least 3 cells of size >= r).  So `d2 >= wrap_d2` selects exactly the candidates that need the
 // exact slow path; for all others the reference's recomputation reproduces the same bits.
 template <int ND, bool PER>
-__device__ __forceinline__ float maybe_periodic_fix(const GridP &g, float d2, float &px, float &py,
+__device__ __forceinline__ float maybe_periodic_fix(const PerP &q, float d2, float &px, float &py,
                                                     float &pz)
 {
-    if (PER && d2 >= g.wrap_d2) {
-        if (d2 > g.r2) d2 = periodic_fix<ND>(g, px, py, pz);
+    if (PER && d2 >= q.wrap_d2) {
+        if (d2 > q.r2) d2 = periodic_fix<ND>(q.bs[0], q.bs[1], q.bs[2], px, py, pz);
     }
     return d2;
 }

@@ -83,7 +83,7 @@ static void prof_collect()
 
 static const char *kPhaseNames[PH_COUNT_] = {
     "k_cell_count", "k_scan_lookback", "k_scatter", "k_finalize_cells", "k_gather",
-    "k_sweep_cells", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export"};
+    "k_sweep_cells", "k_sweep_overflow", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export"};
 
 static const char *kDomainMsg =
     "particle coordinates are NaN or outside the domain bounds of the cell list";
@@ -315,6 +315,8 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->d_err);
     if (g->h_err) cudaFreeHost(g->h_err);
     cudaFree(g->scratch);
+    cudaFree(g->ovf_tiles);
+    cudaFree(g->ovf_count);
     cudaGetLastError();
     delete g;
 }

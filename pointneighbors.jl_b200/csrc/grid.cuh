@@ -43,6 +43,11 @@ struct pnb_grid {
     // per-sweep scratch (payload gathered into cell order), grown on demand
     void *scratch;
     int64_t scratch_bytes;
+
+    // tiles of k_sweep_tiles that did not fit its staging buffer (handled by k_sweep_overflow)
+    int *ovf_tiles;
+    int64_t ovf_cap;
+    int *ovf_count;
 };
 
 namespace pnb {

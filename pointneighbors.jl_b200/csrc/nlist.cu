@@ -31,8 +31,9 @@ struct ListCountCl {
     uint32_t *out;
     struct State { int cnt; };
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
-    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t) const {}
+    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
     __device__ __forceinline__ void count(State &s, int c) const { s.cnt += c; }
+    __device__ __forceinline__ void merge(State &s, const State &o) const { s.cnt += o.cnt; }
     template <int ND>
     __device__ __forceinline__ void pair(State &, float, float, float, float, int,
                                          const unsigned char *, int, int) const {}
@@ -53,7 +54,7 @@ struct ListFillCl {
     {
         s.pos = active ? offsets[i_id] : 0;
     }
-    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t) const {}
+    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
     __device__ __forceinline__ void count(State &, int) const {}
     template <int ND>
     __device__ __forceinline__ void pair(State &s, float, float, float, float, int j_id,
@@ -202,7 +203,7 @@ __global__ void k_nlist_pairs(GridP g, int64_t nx, const int64_t *__restrict__ o
 #pragma unroll
         for (int d = 0; d < ND; d++) p[d] = __fsub_rn(xi[d], __ldg(y + j * ND + d));
         float d2 = dist2<ND>(p[0], p[1], p[2]);
-        d2 = maybe_periodic_fix<ND, PER>(g, d2, p[0], p[1], p[2]);
+        d2 = maybe_periodic_fix<ND, PER>(make_perp(g), d2, p[0], p[1], p[2]);
         if (pos_diff) {
 #pragma unroll
             for (int d = 0; d < ND; d++) pos_diff[k * ND + d] = p[d];
@@ -241,7 +242,7 @@ k_tlsph_defgrad(GridP g, int64_t n, const int64_t *__restrict__ offsets,
 #pragma unroll
         for (int d = 0; d < ND; d++) p[d] = __fsub_rn(Xi[d], __ldg(X0 + j * ND + d));
         float d2 = dist2<ND>(p[0], p[1], p[2]);
-        d2 = maybe_periodic_fix<ND, PER>(g, d2, p[0], p[1], p[2]);
+        d2 = maybe_periodic_fix<ND, PER>(make_perp(g), d2, p[0], p[1], p[2]);
         const float dist = __fsqrt_rn(d2);
         if (dist < PNB_SQRT_EPS_F32) continue;
         const float q = __fdiv_rn(dist, h);

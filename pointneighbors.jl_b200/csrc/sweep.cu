@@ -3,6 +3,7 @@
 // benchmarks/count_neighbors.jl, benchmarks/n_body.jl, benchmarks/smoothed_particle_hydrodynamics.jl.
 #include "closures.cuh"
 #include "sweep.cuh"
+#include "sweep_tiles.cuh"
 
 namespace pnb {
 
@@ -57,8 +58,18 @@ static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int
     return points == nullptr && g->full_build && x == g->y_built && nx == g->n_y_built;
 }
 
+template <class K>
+static pnb_status allow_smem(K kernel, size_t smem)
+{
+    // static + dynamic shared memory above 48 KB needs the opt-in; the kernels carry up to
+    // ~17 KB of static shared memory, so opt in whenever the dynamic part alone exceeds 28 KB
+    if (smem > 28 * 1024)
+        PNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return PNB_OK;
+}
+
 template <int ND, bool PER, class CL>
-static pnb_status launch_nd(pnb_grid *g, bool fast, const float *x, int64_t n_loop,
+static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
                             const int32_t *points, int base, const CL &cl, cudaStream_t s)
 {
     if (fast) {
@@ -66,12 +77,43 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, const float *x, int64_t n_lo
         const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
         const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
         if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
-        const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
-        const size_t smem = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
-        ProfScope ps(PH_SWEEP_CELLS, s);
-        k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem, s>>>(
-            g->p, g->cell_start, g->sorted, cl);
-        PNB_LAUNCHED();
+        const size_t smem_rows = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
+        if (!tiles) {
+            const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
+            ProfScope ps(PH_SWEEP_CELLS, s);
+            k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem_rows, s>>>(
+                g->p, g->cell_start, g->sorted, cl);
+            PNB_LAUNCHED();
+            return PNB_OK;
+        }
+        const int64_t blocks = (int64_t)div_up(nxc, kFTX) * nyc * nzc;
+        if (blocks > g->ovf_cap) {
+            cudaFree(g->ovf_tiles);
+            g->ovf_tiles = nullptr;
+            g->ovf_cap = 0;
+            PNB_CUDA(cudaMalloc(&g->ovf_tiles, sizeof(int) * (size_t)blocks));
+            g->ovf_cap = blocks;
+        }
+        if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, sizeof(int)));
+        PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, sizeof(int), s));
+        size_t pay = (size_t)kFCap * CL::kPayBytes;
+        const size_t red = sizeof(typename CL::State) * kFTX * (kWPC - 1) * 32;
+        if (red > pay) pay = red;
+        const size_t smem = sizeof(float4) * kFCapPad + pay;
+        pnb_status st = allow_smem(k_sweep_tiles<ND, PER, CL>, smem);
+        if (st != PNB_OK) return st;
+        {
+            ProfScope ps(PH_SWEEP_CELLS, s);
+            k_sweep_tiles<ND, PER, CL><<<(unsigned)blocks, kFThreads, smem, s>>>(
+                g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);
+            PNB_LAUNCHED();
+        }
+        {
+            ProfScope ps(PH_SWEEP_OVERFLOW, s);
+            k_sweep_overflow<ND, PER, CL><<<148 * 2, kFTX * 32, smem_rows, s>>>(
+                g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);
+            PNB_LAUNCHED();
+        }
     } else if (n_loop > 0) {
         ProfScope ps(PH_SWEEP_POINTS, s);
         k_sweep_points<ND, PER, CL><<<(unsigned)div_up(n_loop, 128), 128, 0, s>>>(
@@ -81,22 +123,24 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, const float *x, int64_t n_lo
     return PNB_OK;
 }
 
+// tiles = true: the throughput kernel (any visiting order); false: the ordered kernel whose
+// candidate order is the reference's (needed for bit-identical sums in exact mode).
 template <class CL>
-static pnb_status launch_sweep(pnb_grid *g, bool fast, const float *x, int64_t n_loop,
+static pnb_status launch_sweep(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
                                const int32_t *points, int base, const CL &cl, cudaStream_t s)
 {
     if (g->template_search || g->n_built == 0) return PNB_OK;  // every neighbourhood is empty
     const bool per = g->p.periodic != 0;
     switch (g->p.ndims) {
         case 1:
-            return per ? launch_nd<1, true>(g, fast, x, n_loop, points, base, cl, s)
-                       : launch_nd<1, false>(g, fast, x, n_loop, points, base, cl, s);
+            return per ? launch_nd<1, true>(g, fast, tiles, x, n_loop, points, base, cl, s)
+                       : launch_nd<1, false>(g, fast, tiles, x, n_loop, points, base, cl, s);
         case 2:
-            return per ? launch_nd<2, true>(g, fast, x, n_loop, points, base, cl, s)
-                       : launch_nd<2, false>(g, fast, x, n_loop, points, base, cl, s);
+            return per ? launch_nd<2, true>(g, fast, tiles, x, n_loop, points, base, cl, s)
+                       : launch_nd<2, false>(g, fast, tiles, x, n_loop, points, base, cl, s);
         default:
-            return per ? launch_nd<3, true>(g, fast, x, n_loop, points, base, cl, s)
-                       : launch_nd<3, false>(g, fast, x, n_loop, points, base, cl, s);
+            return per ? launch_nd<3, true>(g, fast, tiles, x, n_loop, points, base, cl, s)
+                       : launch_nd<3, false>(g, fast, tiles, x, n_loop, points, base, cl, s);
     }
 }
 
@@ -120,7 +164,7 @@ extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64
     // count_neighbors.jl:22  n_neighbors .= 0
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)nx, s));
     CountCl cl{out};
-    st = launch_sweep(g, is_fast_path(g, x, nx, points), x, n_loop, points, index_base, cl, s);
+    st = launch_sweep(g, is_fast_path(g, x, nx, points), true, x, n_loop, points, index_base, cl, s);
     if (st != PNB_OK) return st;
     return check_err_word(g, s);
 }
@@ -150,9 +194,9 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
     }
     const bool fastp = is_fast_path(g, x, nx, points);
     if (g_exact_arithmetic)
-        st = launch_sweep(g, fastp, x, n_loop, points, index_base, NBodyClT<true>{mass_sorted, -G, dv, nd}, s);
+        st = launch_sweep(g, fastp, false, x, n_loop, points, index_base, NBodyClT<true>{mass_sorted, -G, dv, nd}, s);
     else
-        st = launch_sweep(g, fastp, x, n_loop, points, index_base, NBodyClT<false>{mass_sorted, -G, dv, nd}, s);
+        st = launch_sweep(g, fastp, true, x, n_loop, points, index_base, NBodyClT<false>{mass_sorted, -G, dv, nd}, s);
     if (st != PNB_OK) return st;
     return check_err_word(g, s);
 }
@@ -193,10 +237,10 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
     const float ac = params->alpha * params->sound_speed;
     const float dhc2 = 2.0f * params->delta * h * params->sound_speed;
     if (g_exact_arithmetic)
-        st = launch_sweep(g, fastp, x, n_loop, points, index_base,
+        st = launch_sweep(g, fastp, false, x, n_loop, points, index_base,
                           WcsphClT<true>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2}, s);
     else
-        st = launch_sweep(g, fastp, x, n_loop, points, index_base,
+        st = launch_sweep(g, fastp, true, x, n_loop, points, index_base,
                           WcsphClT<false>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2}, s);
     if (st != PNB_OK) return st;
     return check_err_word(g, s);

@@ -36,7 +36,7 @@ constexpr int kSlots = kTX + 2;   // x-neighbour cells of a tile in one row
 // iff candidate k is within the search radius (same operations, same order as
 // src/nhs_grid.jl:547-555).  All lanes read the same address: broadcast LDS.128.
 template <int ND, bool PER>
-__device__ __forceinline__ unsigned test_block(const GridP &g, const float4 *__restrict__ cp,
+__device__ __forceinline__ unsigned test_block(const PerP &g, const float4 *__restrict__ cp,
                                                float xi, float yi, float zi)
 {
     unsigned hits = 0u;
@@ -57,32 +57,34 @@ __device__ __forceinline__ unsigned test_block(const GridP &g, const float4 *__r
 // Shared-memory view: payload planes are arrays of kCap elements.
 // Global view: payload planes are the cell-ordered arrays themselves.
 
-template <int ND, bool PER, class CL>
-__global__ void __launch_bounds__(kCellThreads)
-k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
-              CL cl)
+template <int ND, bool PER, class CL, int TX>
+__device__ __forceinline__ void
+sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
+                const float4 *__restrict__ sorted, const CL &cl, int64_t tile)
 {
+    constexpr int kSlotsT = TX + 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_pos = reinterpret_cast<float4 *>(smem_raw);
     unsigned char *s_pay = smem_raw + sizeof(float4) * kCapPad;
-    __shared__ uint32_t s_begin[kSlots];   // global begin of each slot's cell
-    __shared__ uint32_t s_prefix[kSlots + 1];
+    __shared__ uint32_t s_begin[kSlotsT];   // global begin of each slot's cell
+    __shared__ uint32_t s_prefix[kSlotsT + 1];
 
     // ---- which tile ---------------------------------------------------------------------
     // valid (non-padding) cells are 2 .. gs-1 in every used dimension
     const int nx = g.gs[0] - 2;
     const int ny = ND > 1 ? g.gs[1] - 2 : 1;
-    const int ntx = (nx + kTX - 1) / kTX;
-    int64_t b = blockIdx.x;
+    const int ntx = (nx + TX - 1) / TX;
+    int64_t b = tile;
     const int tx = (int)(b % ntx); b /= ntx;
     const int iy = (int)(b % ny);  b /= ny;
     const int iz = (int)b;
-    const int cx0 = 2 + tx * kTX;
-    const int cx1 = min(cx0 + kTX - 1, g.gs[0] - 1);
+    const int cx0 = 2 + tx * TX;
+    const int cx1 = min(cx0 + TX - 1, g.gs[0] - 1);
     const int cy = ND > 1 ? 2 + iy : 1;
     const int cz = ND > 2 ? 2 + iz : 1;
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
+    const PerP pp = make_perp(g);
 
     // points of this tile are one contiguous range of the cell-ordered array
     const uint32_t tile_p0 = cell_start[linear_cell(g, cx0, cy, cz)];
@@ -101,12 +103,12 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     int max_passes = my_passes;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) max_passes = max(max_passes, __shfl_xor_sync(0xffffffffu, max_passes, o));
-    __shared__ int s_maxpass[kTX];
+    __shared__ int s_maxpass[TX];
     if (lane == 0) s_maxpass[warp] = max_passes;
     __syncthreads();
     int n_batches = 0;
 #pragma unroll
-    for (int w = 0; w < kTX; w++) n_batches = max(n_batches, s_maxpass[w]);
+    for (int w = 0; w < TX; w++) n_batches = max(n_batches, s_maxpass[w]);
 
     for (int batch = 0; batch < n_batches; batch++) {
         const uint32_t i_sorted = c_p0 + (uint32_t)batch * 32u + (uint32_t)lane;
@@ -132,7 +134,7 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                 }
                 __syncthreads();   // previous row fully consumed; s_begin/s_prefix reusable
                 // slot s <-> cell x = cx0 - 1 + s (wrapped when periodic)
-                if (threadIdx.x < kSlots) {
+                if (threadIdx.x < kSlotsT) {
                     int sx = cx0 - 1 + (int)threadIdx.x;
                     uint32_t b0 = 0, cnt = 0;
                     if (sx <= cx1 + 1) {
@@ -146,28 +148,28 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                     uint32_t incl = cnt;
 #pragma unroll
                     for (int o = 1; o < 16; o <<= 1) {
-                        uint32_t t = __shfl_up_sync((1u << kSlots) - 1u, incl, o);
+                        uint32_t t = __shfl_up_sync((1u << kSlotsT) - 1u, incl, o);
                         if ((int)threadIdx.x >= o) incl += t;
                     }
                     s_prefix[threadIdx.x + 1] = incl;
                     if (threadIdx.x == 0) s_prefix[0] = 0;
                 }
                 __syncthreads();
-                const uint32_t total = s_prefix[kSlots];
+                const uint32_t total = s_prefix[kSlotsT];
                 // this warp's candidates in the row: slots warp .. warp+2 (cells cx-1 .. cx+1)
-                const uint32_t w_q0 = s_prefix[warp], w_q1 = s_prefix[min(warp + 3, kSlots)];
+                const uint32_t w_q0 = s_prefix[warp], w_q1 = s_prefix[min(warp + 3, kSlotsT)];
 
                 for (uint32_t q0 = 0; q0 < total; q0 += kCap) {
                     const uint32_t q1 = min(q0 + (uint32_t)kCap, total);
                     if (q0 > 0) __syncthreads();
                     // ---- stage chunk [q0, q1) -------------------------------------------
-                    for (uint32_t q = q0 + threadIdx.x; q < q1; q += kCellThreads) {
+                    for (uint32_t q = q0 + threadIdx.x; q < q1; q += TX * 32) {
                         int s = 0;
 #pragma unroll
-                        for (int t = 1; t < kSlots; t++) s += (q >= s_prefix[t]) ? 1 : 0;
+                        for (int t = 1; t < kSlotsT; t++) s += (q >= s_prefix[t]) ? 1 : 0;
                         const uint32_t gi = s_begin[s] + (q - s_prefix[s]);
                         s_pos[q - q0] = sorted[gi];
-                        cl.stage(s_pay, (int)(q - q0), gi);
+                        cl.stage(s_pay, (int)(q - q0), gi, kCap);
                     }
                     __syncthreads();
                     // ---- test + interact -------------------------------------------------
@@ -183,7 +185,7 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                                 const uint32_t blk = sb + 32u * bb;
                                 m[bb] = 0u;
                                 if (blk < a1) {   // warp-uniform
-                                    unsigned hh = test_block<ND, PER>(g, s_pos + (blk - q0), xi, yi, zi);
+                                    unsigned hh = test_block<ND, PER>(pp, s_pos + (blk - q0), xi, yi, zi);
                                     const uint32_t nv = a1 - blk;
                                     if (nv < 32u) hh &= (1u << nv) - 1u;
                                     m[bb] = active ? hh : 0u;
@@ -206,7 +208,7 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                                         float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
                                         float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
                                         float d2 = dist2<ND>(px, py, pz);
-                                        d2 = maybe_periodic_fix<ND, PER>(g, d2, px, py, pz);
+                                        d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
                                         cl.template pair<ND>(st, px, py, pz, d2,
                                                              __float_as_int(pj.w), s_pay, slot, kCap);
                                         any = m[0] | m[1] | m[2] | m[3];
@@ -221,6 +223,16 @@ k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
         if (active) cl.finish(st, (int)i_sorted, i_id);
         __syncthreads();
     }
+}
+
+
+// x === y fast path, ordered variant: one CTA per tile of kTX cells.
+template <int ND, bool PER, class CL>
+__global__ void __launch_bounds__(kCellThreads)
+k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
+              CL cl)
+{
+    sweep_tile_rows<ND, PER, CL, kTX>(g, cell_start, sorted, cl, (int64_t)blockIdx.x);
 }
 
 // General path: one thread per query point ------------------------------------------------------
@@ -243,6 +255,7 @@ k_sweep_points(GridP g, const uint32_t *__restrict__ cell_start, const float4 *_
     for (int d = ND; d < 3; d++) cc[d] = 1;
     typename CL::State st;
     cl.init(st, true, -1, i_id);
+    const PerP pp = make_perp(g);
     bool oob = false;
     for (int oz = (ND > 2 ? -1 : 0); oz <= (ND > 2 ? 1 : 0); oz++)
         for (int oy = (ND > 1 ? -1 : 0); oy <= (ND > 1 ? 1 : 0); oy++)
@@ -266,7 +279,7 @@ k_sweep_points(GridP g, const uint32_t *__restrict__ cell_start, const float4 *_
                     float py = ND > 1 ? __fsub_rn(p[1], pj.y) : 0.f;
                     float pz = ND > 2 ? __fsub_rn(p[2], pj.z) : 0.f;
                     float d2 = dist2<ND>(px, py, pz);
-                    d2 = maybe_periodic_fix<ND, PER>(g, d2, px, py, pz);
+                    d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
                     if (d2 <= g.r2) {
                         if (CL::kCountOnly) cl.count(st, 1);
                         else cl.template pair_global<ND>(st, px, py, pz, d2, __float_as_int(pj.w), gi);
