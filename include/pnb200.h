@@ -79,6 +79,15 @@ pnb_status pnb_grid_params_f32(int ndims, float search_radius, const float *min_
 pnb_status pnb_grid_create_f32(int ndims, float search_radius, const float *min_corner,
                                const float *max_corner, const float *box_min, const float *box_max,
                                pnb_grid **out);
+/* A window of the same global grid (multi-GPU slab decomposition): cells
+ * win_lo[d]..win_hi[d] (global 1-based cell coordinates, inclusive; the outermost layer on each
+ * side acts as the empty padding layer) with the GLOBAL cell arithmetic, so cell assignments and
+ * neighbour sets are bit-identical to the undecomposed search.  NULL windows = the full grid.
+ * There is no reference counterpart (the reference is single-device). */
+pnb_status pnb_grid_create_window_f32(int ndims, float search_radius, const float *min_corner,
+                                      const float *max_corner, const float *box_min,
+                                      const float *box_max, const int64_t *win_lo,
+                                      const int64_t *win_hi, pnb_grid **out);
 void pnb_grid_destroy(pnb_grid *g);
 int64_t pnb_grid_total_cells(const pnb_grid *g);
 int64_t pnb_grid_n_points(const pnb_grid *g); /* points in the cell list after the last build */

@@ -24,6 +24,7 @@ struct GridP {
     float cs[3];       // cell_size
     int gs[3];         // allocated grid size (1 for unused dims)
     int nc[3];         // periodic cells per dim (-1 if not periodic)
+    int off[3];        // window offset: local cell = global cell - off (0 for a full grid)
     float bsize[3];    // periodic box size
     float wrap_d2;     // d2 below this can never be changed by the periodic fix (see periodic_fix)
     int total_cells;
@@ -110,14 +111,15 @@ static __device__ __noinline__ int cell_coord_slow(float f, int periodic, int nc
 // cell_coords (src/nhs_grid.jl:622-628) for one dimension:
 //   floor_to_int((x - min_corner) / cell_size) + 1   (src/cell_lists/full_grid.jl:93)
 //   periodic: mod(c - 2, n_cells) + 2                (src/nhs_grid.jl:619)
-__device__ __forceinline__ int cell_coord(float x, float minc, float cs, int periodic, int nc)
+__device__ __forceinline__ int cell_coord(float x, float minc, float cs, int periodic, int nc,
+                                          int off = 0)
 {
     float q = __fdiv_rn(__fsub_rn(x, minc), cs);
     float f = floorf(q);
     if (!(fabsf(f) < 1073741824.0f)) return cell_coord_slow(f, periodic, nc);
     int c = (int)f + 1;
     if (periodic) c = floormod_i(c - 2, nc) + 2;
-    return c;
+    return c - off;   // windowed grids (slabs) count cells from their own first layer
 }
 
 // Linear 0-based cell index (src/cell_lists/full_grid.jl:157-161), or -1 when the cell is not
@@ -128,7 +130,7 @@ __device__ __forceinline__ int point_cell(const GridP &g, const float *p, int *c
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
-        cc[d] = cell_coord(p[d], g.minc[d], g.cs[d], g.periodic, g.nc[d]);
+        cc[d] = cell_coord(p[d], g.minc[d], g.cs[d], g.periodic, g.nc[d], g.off[d]);
         ok = ok && (cc[d] >= 2) && (cc[d] <= g.gs[d] - 1);
     }
 #pragma unroll

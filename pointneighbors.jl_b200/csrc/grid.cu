@@ -230,6 +230,15 @@ extern "C" pnb_status pnb_grid_create_f32(int ndims, float r, const float *min_c
                                           const float *max_corner, const float *box_min,
                                           const float *box_max, pnb_grid **out)
 {
+    return pnb_grid_create_window_f32(ndims, r, min_corner, max_corner, box_min, box_max, nullptr,
+                                      nullptr, out);
+}
+
+extern "C" pnb_status pnb_grid_create_window_f32(int ndims, float r, const float *min_corner,
+                                                 const float *max_corner, const float *box_min,
+                                                 const float *box_max, const int64_t *win_lo,
+                                                 const int64_t *win_hi, pnb_grid **out)
+{
     if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
     *out = nullptr;
     if (pnb_device_count() <= 0) {
@@ -255,6 +264,24 @@ extern "C" pnb_status pnb_grid_create_f32(int ndims, float r, const float *min_c
         p.cs[d] = d < ndims ? g->cell_size[d] : 1.f;
         int64_t gs = d < ndims ? g->grid_size[d] : 1;
         if (g->template_search) gs = d < ndims ? 0 : 1;
+        p.off[d] = 0;
+        if (win_lo && win_hi && d < ndims && !g->template_search) {
+            // window of the global grid (slab decomposition): global cells win_lo..win_hi
+            // (1-based, inclusive, outermost layer = padding) become local cells 1..(hi-lo+1)
+            if (box_min && box_max) {
+                set_error("a windowed grid cannot be combined with a PeriodicBox");
+                delete g;
+                return PNB_ERR_ARG;
+            }
+            if (win_lo[d] < 1 || win_hi[d] > gs || win_hi[d] - win_lo[d] + 1 < 3) {
+                set_error("grid window [%lld, %lld] is not inside 1..%lld with at least 3 cells",
+                          (long long)win_lo[d], (long long)win_hi[d], (long long)gs);
+                delete g;
+                return PNB_ERR_ARG;
+            }
+            p.off[d] = (int)(win_lo[d] - 1);
+            gs = win_hi[d] - win_lo[d] + 1;
+        }
         if (gs > 0x7fffffff) gs = 0x7fffffff;
         p.gs[d] = (int)gs;
         p.nc[d] = d < ndims ? (int)g->n_cells[d] : -1;

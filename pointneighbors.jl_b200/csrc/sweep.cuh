@@ -250,7 +250,7 @@ k_sweep_points(GridP g, const uint32_t *__restrict__ cell_start, const float4 *_
     for (int d = 0; d < ND; d++) p[d] = __ldg(x + (int64_t)i_id * ND + d);
     int cc[3];
 #pragma unroll
-    for (int d = 0; d < ND; d++) cc[d] = cell_coord(p[d], g.minc[d], g.cs[d], g.periodic, g.nc[d]);
+    for (int d = 0; d < ND; d++) cc[d] = cell_coord(p[d], g.minc[d], g.cs[d], g.periodic, g.nc[d], g.off[d]);
 #pragma unroll
     for (int d = ND; d < 3; d++) cc[d] = 1;
     typename CL::State st;

@@ -49,6 +49,8 @@ SIGNATURES = {
     "pnb_device_count": (C.c_int, []),
     "pnb_grid_params_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, _pf, _pf, _pi64, _pi64, _pf]),
     "pnb_grid_create_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, C.POINTER(_vp)]),
+    "pnb_grid_create_window_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, _pi64, _pi64,
+                                             C.POINTER(_vp)]),
     "pnb_grid_destroy": (None, [_vp]),
     "pnb_grid_total_cells": (_i64, [_vp]),
     "pnb_grid_n_points": (_i64, [_vp]),

@@ -255,6 +255,7 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
             self.n_cells = tuple(int(v) for v in nc[:self._ndims])
             self.cell_size = tuple(np.float32(v) for v in cs[:self._ndims])
         self._handle = None
+        self._window = None    # (lo, hi) global cell window for slab decomposition (slabs.py)
         self._cell_list_radius = cell_list.search_radius
 
     # -- device handle -----------------------------------------------------------------------
@@ -272,10 +273,14 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
                 bmx_a = np.ascontiguousarray(self.periodic_box.max_corner, dtype=np.float32)
                 bmn, bmx = bmn_a.ctypes.data_as(_lib._pf), bmx_a.ctypes.data_as(_lib._pf)
             # The cell list was padded with ITS search radius (normally the same as the search's).
-            check(_lib.lib().pnb_grid_create_f32(
+            wlo = whi = None
+            if self._window is not None:
+                wlo = (C.c_int64 * 3)(*[int(v) for v in self._window[0]] + [1] * (3 - self._ndims))
+                whi = (C.c_int64 * 3)(*[int(v) for v in self._window[1]] + [1] * (3 - self._ndims))
+            check(_lib.lib().pnb_grid_create_window_f32(
                 self._ndims, np.float32(self.search_radius),
                 cl._user_min.ctypes.data_as(_lib._pf), cl._user_max.ctypes.data_as(_lib._pf),
-                bmn, bmx, C.byref(h)))
+                bmn, bmx, wlo, whi, C.byref(h)))
             self._handle = h
         return self._handle
 

@@ -1,0 +1,311 @@
+"""Multi-GPU slab decomposition of the grid search: one process per GPU, one ghost cell layer
+exchanged per step over torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+There is no counterpart in the reference (single device).  Design:
+
+  * the GLOBAL FullGridCellList is cut along its slowest cell dimension (the last one): linear
+    cell index = c1 + (c2-1) n1 + (c3-1) n1 n2 (src/cell_lists/full_grid.jl:157-161), so a slab
+    of cell layers is a contiguous range of cells;
+  * rank g owns the cell layers [z_lo, z_hi]; because cell_size >= search_radius a point only
+    interacts with the 3^d stencil (src/nhs_grid.jl:577-583), so the rank needs exactly the
+    points of the layers z_lo - 1 and z_hi + 1 of its neighbours (ghosts);
+  * every rank builds a WINDOW of the global grid (pnb_grid_create_window_f32) with the global
+    cell arithmetic, so cell assignments and neighbour sets are bit-identical to the
+    undecomposed search; results are taken for the owned points only;
+  * one exchange round per step and direction carries both the migrants (points whose cell left
+    the slab) and the boundary layer (ghosts): a rank sends upwards every owned point with
+    cz >= z_hi, the receiver keeps cz >= its z_lo as its own and cz == z_lo - 1 as ghosts, the
+    sender keeps what it sent with cz == z_hi + 1 as its own ghosts (symmetrically downwards).
+
+The exchange logic is plain torch + torch.distributed and runs on CPU tensors with gloo
+(tests/test_slabs_gloo.py); the compute (build + sweep) is the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ArgumentError, check
+
+
+def global_grid(ndims: int, search_radius, min_corner, max_corner):
+    """(padded_min, grid_size) of the global FullGridCellList, from the library's host arithmetic."""
+    mn = np.ascontiguousarray(min_corner, dtype=np.float32)
+    mx = np.ascontiguousarray(max_corner, dtype=np.float32)
+    pmin = (C.c_float * 3)()
+    gs = (C.c_int64 * 3)()
+    check(_lib.lib().pnb_grid_params_f32(ndims, np.float32(search_radius),
+                                         mn.ctypes.data_as(_lib._pf), mx.ctypes.data_as(_lib._pf),
+                                         None, None, pmin, None, gs, None, None))
+    return np.array(pmin[:ndims], dtype=np.float32), tuple(int(v) for v in gs[:ndims])
+
+
+def split_layers(n_layers_total: int, world: int) -> List[Tuple[int, int]]:
+    """Owned layer ranges [z_lo, z_hi] (global 1-based cell coordinates) of every rank: the valid
+    layers 2 .. n-1 in `world` contiguous, nearly equal parts."""
+    valid = n_layers_total - 2
+    if valid < 3 * world:
+        raise ArgumentError(f"{valid} cell layers cannot be split into {world} slabs of >= 3 layers")
+    base, extra = divmod(valid, world)
+    out, z = [], 2
+    for g in range(world):
+        n = base + (1 if g < extra else 0)
+        out.append((z, z + n - 1))
+        z += n
+    return out
+
+
+class SlabExchange:
+    """Ownership, migration and ghost exchange for one rank.  Device-agnostic (CPU/gloo or CUDA/NCCL)."""
+
+    def __init__(self, ndims: int, search_radius, min_corner, max_corner, rank: int, world: int,
+                 group=None):
+        self.ndims = int(ndims)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.search_radius = np.float32(search_radius)
+        self.padded_min, self.grid_size = global_grid(ndims, search_radius, min_corner, max_corner)
+        self.layers = split_layers(self.grid_size[-1], world)
+        self.z_lo, self.z_hi = self.layers[rank]
+        # window of the global grid held by this rank: owned layers, one ghost layer and one
+        # (empty) padding layer on each side, clipped to the global grid
+        lo = [1] * ndims
+        hi = list(self.grid_size)
+        lo[-1] = max(1, self.z_lo - 2)
+        hi[-1] = min(self.grid_size[-1], self.z_hi + 2)
+        self.window = (tuple(lo), tuple(hi))
+        self.last_stats = {}
+
+    # cell layer of every point: floor((z - min_corner) / cell_size) + 1 in Float32
+    # (src/cell_lists/full_grid.jl:93), the same IEEE operations as the library's cell kernel
+    def cell_layer(self, coords):
+        import torch
+        z = coords[:, self.ndims - 1]
+        # tensor / tensor: torch turns `tensor / python_scalar` into a multiplication by the
+        # reciprocal on CUDA, which would not be the reference's true division
+        pmin = torch.tensor(float(self.padded_min[-1]), dtype=torch.float32, device=coords.device)
+        cs = torch.tensor(float(self.search_radius), dtype=torch.float32, device=coords.device)
+        q = (z - pmin) / cs
+        return torch.floor(q).to(torch.int64) + 1
+
+    def owned_mask(self, coords):
+        cz = self.cell_layer(coords)
+        return (cz >= self.z_lo) & (cz <= self.z_hi)
+
+    def _sendrecv(self, send_up, send_down):
+        """Exchange variable-length row blocks with rank+1 (up) and rank-1 (down)."""
+        import torch
+        import torch.distributed as dist
+        dev = send_up.device
+        ncol = send_up.shape[1]
+        up, down = self.rank + 1, self.rank - 1
+        has_up, has_down = up < self.world, down >= 0
+        n_send = torch.tensor([send_up.shape[0], send_down.shape[0]], dtype=torch.int64, device=dev)
+        n_recv = torch.zeros(2, dtype=torch.int64, device=dev)   # [from up, from down]
+        ops = []
+        if has_up:
+            ops += [dist.P2POp(dist.isend, n_send[0:1], up, self.group),
+                    dist.P2POp(dist.irecv, n_recv[0:1], up, self.group)]
+        if has_down:
+            ops += [dist.P2POp(dist.isend, n_send[1:2], down, self.group),
+                    dist.P2POp(dist.irecv, n_recv[1:2], down, self.group)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        n_up, n_down = (int(v) for v in n_recv.tolist())
+        recv_up = torch.empty((n_up, ncol), dtype=send_up.dtype, device=dev)
+        recv_down = torch.empty((n_down, ncol), dtype=send_up.dtype, device=dev)
+        ops = []
+        if has_up:
+            if send_up.shape[0]:
+                ops.append(dist.P2POp(dist.isend, send_up, up, self.group))
+            if n_up:
+                ops.append(dist.P2POp(dist.irecv, recv_up, up, self.group))
+        if has_down:
+            if send_down.shape[0]:
+                ops.append(dist.P2POp(dist.isend, send_down, down, self.group))
+            if n_down:
+                ops.append(dist.P2POp(dist.irecv, recv_down, down, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return recv_up, recv_down
+
+    def exchange(self, rows):
+        """rows: (n, ndims + k) float32, the first ndims columns are the coordinates of the points
+        this rank currently holds as its own.  Returns (local_rows, n_own): the new owned points
+        first, then the ghosts of the layer below, then the ghosts of the layer above."""
+        import torch
+        cz = self.cell_layer(rows)
+        up_mask = cz >= self.z_hi if self.rank + 1 < self.world else torch.zeros_like(cz, dtype=torch.bool)
+        down_mask = cz <= self.z_lo if self.rank > 0 else torch.zeros_like(cz, dtype=torch.bool)
+        send_up = rows[up_mask].contiguous()
+        send_down = rows[down_mask].contiguous()
+        recv_up, recv_down = self._sendrecv(send_up, send_down)
+        stay = rows[(cz >= self.z_lo) & (cz <= self.z_hi)]
+        # received rows: own if inside my layers, ghost if in the adjacent layer
+        cz_u = self.cell_layer(recv_up)
+        cz_d = self.cell_layer(recv_down)
+        own_new = torch.cat([stay, recv_up[cz_u <= self.z_hi], recv_down[cz_d >= self.z_lo]])
+        ghost_up = torch.cat([recv_up[cz_u == self.z_hi + 1], rows[cz == self.z_hi + 1]]) \
+            if self.rank + 1 < self.world else rows[:0]
+        ghost_down = torch.cat([recv_down[cz_d == self.z_lo - 1], rows[cz == self.z_lo - 1]]) \
+            if self.rank > 0 else rows[:0]
+        n_own = own_new.shape[0]
+        self.last_stats = {"sent_up": int(send_up.shape[0]), "sent_down": int(send_down.shape[0]),
+                           "ghosts": int(ghost_up.shape[0] + ghost_down.shape[0]),
+                           "migrated_in": int(n_own - stay.shape[0]),
+                           "bytes_sent": int((send_up.numel() + send_down.numel()) * 4)}
+        return torch.cat([own_new, ghost_down, ghost_up]).contiguous(), n_own
+
+
+class SlabNeighborhoodSearch:
+    """A GridNeighborhoodSearch over one slab (window of the global grid) + its exchange."""
+
+    def __init__(self, ndims: int, search_radius, min_corner, max_corner, rank: int, world: int,
+                 group=None):
+        from .api import FullGridCellList, GridNeighborhoodSearch
+        self.exchange = SlabExchange(ndims, search_radius, min_corner, max_corner, rank, world, group)
+        r = np.float32(search_radius)
+        cl = FullGridCellList(min_corner=min_corner, max_corner=max_corner, search_radius=r)
+        self.nhs = GridNeighborhoodSearch(ndims, search_radius=r, cell_list=cl)
+        self.nhs._window = self.exchange.window
+        self.ndims = int(ndims)
+
+    def step_inputs(self, rows):
+        """Exchange, then split the local rows into contiguous coordinates and the other columns."""
+        local, n_own = self.exchange.exchange(rows)
+        coords = local[:, :self.ndims].contiguous()
+        return local, coords, n_own
+
+    def update_(self, coords):
+        from .api import update_
+        return update_(self.nhs, coords, coords, points_moving=(True, True))
+
+
+# ---------------------------------------------------------------------------------------------
+# benchmark at N > 1 (called by bench.py): weak scaling, 254 lattice layers per GPU
+# ---------------------------------------------------------------------------------------------
+def lattice_planes(n, k_lo, k_hi, domain_n, seed, device):
+    """Perturbed lattice planes k_lo..k_hi (1-based, last dimension) of an n x n x (.) lattice.
+    The perturbation of a plane depends only on (seed, plane), so every rank generates identical
+    coordinates for the planes it shares with a neighbour.  Float32, normalised by domain_n + 1."""
+    import torch
+    out = []
+    gen = torch.Generator(device=device)
+    kk = torch.arange(n * n, device=device, dtype=torch.int64)
+    ix = (kk % n).to(torch.float64) + 1.0
+    iy = (kk // n).to(torch.float64) + 1.0
+    for k in range(k_lo, k_hi + 1):
+        gen.manual_seed(seed * 1000003 + k)
+        c = torch.stack([ix, iy, torch.full_like(ix, float(k))], dim=1)
+        c += 0.05 * torch.randn(n * n, 3, device=device, dtype=torch.float64, generator=gen)
+        c += 0.05 * torch.randn(n * n, 3, device=device, dtype=torch.float64, generator=gen)
+        out.append((c.to(torch.float32) / np.float32(domain_n + 1)))
+    return torch.cat(out).contiguous()
+
+
+def bench_multi_gpu(args, rank, world, dev, metric, unit):
+    import json
+    import torch
+    import torch.distributed as dist
+    from . import api as pn
+
+    T = np.float32
+    n = args.lattice
+    nz = n * world
+    r = T(3.0) / T(nz + 1)
+    mn = np.zeros(3, T)
+    mx = (np.array([n, n, nz], dtype=np.float64) / nz).astype(T)
+    slab = SlabNeighborhoodSearch(3, r, mn, mx, rank, world)
+    ex = slab.exchange
+    # lattice planes that can fall into my layers (3 planes per layer, one plane of margin)
+    k_lo = max(1, 3 * (ex.z_lo - 2) - 1)
+    k_hi = min(nz, 3 * (ex.z_hi - 2) + 3)
+    cand = lattice_planes(n, k_lo, k_hi, nz, 1, dev)
+    A = cand[ex.owned_mask(cand)].contiguous()
+    # cell-sorted order like the single-GPU cloud (dimension 1 most significant)
+    cellk = torch.floor(A.to(torch.float64) * (nz + 1) / 3.0).to(torch.int64)
+    key = (cellk[:, 0] * (n + 8) + cellk[:, 1]) * (nz + 8) + cellk[:, 2]
+    A = A[torch.sort(key, stable=True).indices].contiguous()
+    N = A.shape[0]
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    B = (A + (T(4e-4) * r) * torch.randn(N, 3, device=dev, generator=gen)).contiguous()
+    gen2 = torch.Generator(device=dev).manual_seed(2000 + rank)
+    rho = 1000.0 + torch.rand(N, device=dev, generator=gen2, dtype=torch.float32)
+    vel = torch.zeros((N, 3), device=dev, dtype=torch.float32)
+    mass = torch.full((N,), float(T(0.1) * (r / T(3))), device=dev, dtype=torch.float32)
+    pressure = T(100.0) * (rho - T(1000.0))
+    state = torch.cat([vel, rho[:, None], mass[:, None], pressure[:, None]], dim=1)   # 6 columns
+    rowsA = torch.cat([A, state], dim=1).contiguous()
+    rowsB = torch.cat([B, state], dim=1).contiguous()
+    rows = [rowsA, rowsB]
+    h = T(r / T(2))
+
+    def step(s, count_only=False):
+        local, coords, n_own = slab.step_inputs(rows[(s + 1) % 2])
+        slab.update_(coords)
+        nl = local.shape[0]
+        if count_only:
+            cnt = torch.zeros(nl, dtype=torch.int64, device=dev)
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), coords, coords, slab.nhs)
+            return int(cnt[:n_own].sum()), n_own
+        v = local[:, 3:7].contiguous()
+        m = local[:, 7].contiguous()
+        p = local[:, 8].contiguous()
+        dv = torch.empty((nl, 4), device=dev, dtype=torch.float32)
+        f = pn.WCSPHInteract(dv, v, v, m, m, p, p, smoothing_length=h, sound_speed=T(10.0))
+        pn.foreach_point_neighbor(f, coords, coords, slab.nhs)
+        return dv[:n_own], n_own
+
+    pairs = [0, 0]
+    pairs[1], _ = step(0, count_only=True)   # step 0 uses rows[1] = B
+    pairs[0], _ = step(1, count_only=True)
+    for s in range(max(args.warmup, 3)):
+        step(s)
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches0 = int(_lib.lib().pnb_launch_count())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    my_pairs = 0
+    for s in range(args.steps):
+        step(s)
+        my_pairs += pairs[(s + 1) % 2]
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms, float(my_pairs), float(N), float(ex.last_stats.get("bytes_sent", 0)),
+                      float(ex.last_stats.get("ghosts", 0))], device=dev, dtype=torch.float64)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    launches = int(_lib.lib().pnb_launch_count()) - launches0
+    if rank == 0:
+        ms_max = float(tmax[0])
+        total_pairs = float(tsum[1])
+        line = {
+            "metric": metric, "value": total_pairs / (ms_max * 1e-3), "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"WCSPH step 3D, slab-decomposed: {n}x{n}x{nz} = {int(tsum[2])} particles "
+                                   f"over {world} GPUs ({n} lattice layers per GPU, ~BASELINE config 5 at 8), "
+                                   "per step: migrant+ghost exchange (NCCL send/recv), update!, interact!",
+                       "particles_total": int(tsum[2]), "search_radius": float(r),
+                       "ghost_points_per_rank_max": int(tmax[4]),
+                       "exchange_bytes_per_rank_max": int(tmax[3]),
+                       "l2": "per-GPU inputs larger than the 126 MB L2"},
+            "gpu_launches": launches,
+            "e2e": None,
+            "note": "device-resident multi-GPU step; the host-buffer e2e number is measured at N = 1",
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
