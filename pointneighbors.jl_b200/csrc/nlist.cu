@@ -108,11 +108,58 @@ static pnb_status launch_list(pnb_grid *g, bool fast, const float *x, int64_t nx
     }
 }
 
-// sorteach! (vector_of_vectors.jl:177-183): every list ascending.  One warp per list; the list is
-// staged in shared memory and each element's rank is the number of smaller elements (ids in a
-// list are distinct).  Lists longer than kSortCap rank against global memory instead.
+// sorteach! (vector_of_vectors.jl:177-183): every list ascending.  One warp per list.
+//   <= 128 neighbours (the normal case, ~108 at r = 3 spacings): bitonic network in registers,
+//      element e = r * 32 + lane lives in register r of lane `lane`; partners at distance < 32
+//      are exchanged with __shfl_xor_sync, larger distances are register swaps.
+//   <= kSortCap: rank by counting in shared memory.   larger: odd-even transposition in global.
 constexpr int kSortCap = 512;
 constexpr int kSortWarps = 4;
+
+template <int NR>
+__device__ __forceinline__ void bitonic_sort_regs(int32_t (&v)[NR], int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32 * NR; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    if ((r & jr) == 0) {
+                        const int r2 = r | jr;
+                        const bool asc = (((r << 5) | lane) & k) == 0;
+                        const int32_t a = v[r], c = v[r2];
+                        const bool sw = (a > c) == asc;
+                        v[r] = sw ? c : a;
+                        v[r2] = sw ? a : c;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    const int32_t other = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool asc = (((r << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    v[r] = (lower == asc) ? min(v[r], other) : max(v[r], other);
+                }
+            }
+        }
+    }
+}
+
+template <int NR>
+__device__ __forceinline__ void sort_list_regs(int32_t *lst, int len, int lane)
+{
+    int32_t v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) v[r] = (r * 32 + lane < len) ? lst[r * 32 + lane] : 0x7fffffff;
+    bitonic_sort_regs<NR>(v, lane);
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+        if (r * 32 + lane < len) lst[r * 32 + lane] = v[r];
+}
 
 __global__ void __launch_bounds__(kSortWarps * 32)
 k_sort_lists(int64_t nx, const int64_t *__restrict__ offsets, int32_t *__restrict__ ids)
@@ -125,7 +172,13 @@ k_sort_lists(int64_t nx, const int64_t *__restrict__ offsets, int32_t *__restric
     const int len = (int)(offsets[i + 1] - o0);
     if (len <= 1) return;
     int32_t *lst = ids + o0;
-    if (len <= kSortCap) {
+    if (len <= 32) {
+        sort_list_regs<1>(lst, len, lane);
+    } else if (len <= 64) {
+        sort_list_regs<2>(lst, len, lane);
+    } else if (len <= 128) {
+        sort_list_regs<4>(lst, len, lane);
+    } else if (len <= kSortCap) {
         int32_t *buf = s_buf[warp];
         for (int e = lane; e < len; e += 32) buf[e] = lst[e];
         __syncwarp();

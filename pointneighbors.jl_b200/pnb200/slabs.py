@@ -136,29 +136,85 @@ class SlabExchange:
     def exchange(self, rows):
         """rows: (n, ndims + k) float32, the first ndims columns are the coordinates of the points
         this rank currently holds as its own.  Returns (local_rows, n_own): the new owned points
-        first, then the ghosts of the layer below, then the ghosts of the layer above."""
+        first, then the ghosts.  Convenience form (copies everything); step loops use
+        exchange_inplace."""
         import torch
-        cz = self.cell_layer(rows)
-        up_mask = cz >= self.z_hi if self.rank + 1 < self.world else torch.zeros_like(cz, dtype=torch.bool)
-        down_mask = cz <= self.z_lo if self.rank > 0 else torch.zeros_like(cz, dtype=torch.bool)
-        send_up = rows[up_mask].contiguous()
-        send_down = rows[down_mask].contiguous()
+        n = rows.shape[0]
+        nd = self.ndims
+        cap = n + n // 8 + 1024
+        coords = torch.empty((cap, nd), dtype=rows.dtype, device=rows.device)
+        state = torch.empty((cap, rows.shape[1] - nd), dtype=rows.dtype, device=rows.device)
+        coords[:n] = rows[:, :nd]
+        state[:n] = rows[:, nd:]
+        (coords, state), n_own, n_local = self.exchange_inplace([coords, state], n)
+        return torch.cat([coords[:n_local], state[:n_local]], dim=1).contiguous(), n_own
+
+    def exchange_inplace(self, arrays, n):
+        """Structure-of-arrays form used every step.  arrays: list of float32 tensors with a
+        common leading capacity dimension, arrays[0] = coordinates (cap, ndims), the others (cap,)
+        or (cap, k) per-point state; the first n rows are the points this rank owns.  Migrants and
+        ghosts are exchanged with the two neighbours in one round; on return rows [0, n_own) are
+        the owned points (holes left by emigrants are filled from the tail, so the order of owned
+        points may change), rows [n_own, n_local) the ghosts.  Only boundary rows are ever copied.
+        Returns (arrays, n_own, n_local); buffers are re-allocated if too small."""
+        import torch
+        nd = self.ndims
+        coords = arrays[0]
+        dev = coords.device
+        has_up, has_down = self.rank + 1 < self.world, self.rank > 0
+        widths = [1 if a.ndim == 1 else a.shape[1] for a in arrays]
+        cz = self.cell_layer(coords[:n])
+        empty = torch.zeros(0, dtype=torch.int64, device=dev)
+        up_idx = torch.nonzero(cz >= self.z_hi).flatten() if has_up else empty
+        down_idx = torch.nonzero(cz <= self.z_lo).flatten() if has_down else empty
+
+        def pack(idx):
+            return torch.cat([a[idx].reshape(idx.numel(), w) for a, w in zip(arrays, widths)],
+                             dim=1).contiguous()
+
+        send_up, send_down = pack(up_idx), pack(down_idx)
         recv_up, recv_down = self._sendrecv(send_up, send_down)
-        stay = rows[(cz >= self.z_lo) & (cz <= self.z_hi)]
-        # received rows: own if inside my layers, ghost if in the adjacent layer
-        cz_u = self.cell_layer(recv_up)
-        cz_d = self.cell_layer(recv_down)
-        own_new = torch.cat([stay, recv_up[cz_u <= self.z_hi], recv_down[cz_d >= self.z_lo]])
-        ghost_up = torch.cat([recv_up[cz_u == self.z_hi + 1], rows[cz == self.z_hi + 1]]) \
-            if self.rank + 1 < self.world else rows[:0]
-        ghost_down = torch.cat([recv_down[cz_d == self.z_lo - 1], rows[cz == self.z_lo - 1]]) \
-            if self.rank > 0 else rows[:0]
-        n_own = own_new.shape[0]
+        cz_u = self.cell_layer(recv_up[:, :nd])
+        cz_d = self.cell_layer(recv_down[:, :nd])
+        # what I sent and is now one layer outside my slab stays with me as a ghost
+        my_ghost_up = send_up[cz[up_idx] == self.z_hi + 1] if has_up else send_up[:0]
+        my_ghost_down = send_down[cz[down_idx] == self.z_lo - 1] if has_down else send_down[:0]
+        mig_in = torch.cat([recv_up[cz_u <= self.z_hi], recv_down[cz_d >= self.z_lo]])
+        ghosts = torch.cat([recv_down[cz_d == self.z_lo - 1], my_ghost_down,
+                            recv_up[cz_u == self.z_hi + 1], my_ghost_up])
+        # emigrants: fill their holes from the tail (swap-with-last, like deleteatat!,
+        # src/vector_of_vectors.jl:123-139)
+        leave_idx = torch.nonzero((cz < self.z_lo) | (cz > self.z_hi)).flatten()
+        n_leave = int(leave_idx.numel())
+        n_stay = n - n_leave
+        if n_leave:
+            tail = torch.arange(n_stay, n, device=dev)
+            leaving_tail = torch.zeros(n - n_stay, dtype=torch.bool, device=dev)
+            leaving_tail[leave_idx[leave_idx >= n_stay] - n_stay] = True
+            fillers = tail[~leaving_tail]
+            holes = leave_idx[leave_idx < n_stay]
+            for a in arrays:
+                a[holes] = a[fillers]
+        n_own = n_stay + mig_in.shape[0]
+        n_local = n_own + ghosts.shape[0]
+        if n_local > coords.shape[0]:
+            cap = n_local + n_local // 8 + 1024
+            grown = []
+            for a in arrays:
+                g = torch.empty((cap,) + tuple(a.shape[1:]), dtype=a.dtype, device=dev)
+                g[:n_stay] = a[:n_stay]
+                grown.append(g)
+            arrays = grown
+        col = 0
+        for a, w in zip(arrays, widths):
+            a[n_stay:n_own] = mig_in[:, col:col + w].reshape((mig_in.shape[0],) + tuple(a.shape[1:]))
+            a[n_own:n_local] = ghosts[:, col:col + w].reshape((ghosts.shape[0],) + tuple(a.shape[1:]))
+            col += w
         self.last_stats = {"sent_up": int(send_up.shape[0]), "sent_down": int(send_down.shape[0]),
-                           "ghosts": int(ghost_up.shape[0] + ghost_down.shape[0]),
-                           "migrated_in": int(n_own - stay.shape[0]),
+                           "ghosts": int(ghosts.shape[0]), "migrated_in": int(mig_in.shape[0]),
+                           "migrated_out": n_leave,
                            "bytes_sent": int((send_up.numel() + send_down.numel()) * 4)}
-        return torch.cat([own_new, ghost_down, ghost_up]).contiguous(), n_own
+        return arrays, n_own, n_local
 
 
 class SlabNeighborhoodSearch:
@@ -175,7 +231,8 @@ class SlabNeighborhoodSearch:
         self.ndims = int(ndims)
 
     def step_inputs(self, rows):
-        """Exchange, then split the local rows into contiguous coordinates and the other columns."""
+        """Exchange, then split the local rows into contiguous coordinates and the other columns
+        (convenience form for tests; step loops call exchange.exchange_inplace)."""
         local, n_own = self.exchange.exchange(rows)
         coords = local[:, :self.ndims].contiguous()
         return local, coords, n_own
@@ -238,23 +295,32 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     vel = torch.zeros((N, 3), device=dev, dtype=torch.float32)
     mass = torch.full((N,), float(T(0.1) * (r / T(3))), device=dev, dtype=torch.float32)
     pressure = T(100.0) * (rho - T(1000.0))
-    state = torch.cat([vel, rho[:, None], mass[:, None], pressure[:, None]], dim=1)   # 6 columns
-    rowsA = torch.cat([A, state], dim=1).contiguous()
-    rowsB = torch.cat([B, state], dim=1).contiguous()
-    rows = [rowsA, rowsB]
+    vfull = torch.cat([vel, rho[:, None]], dim=1)      # v = vcat(velocity, density'), (N, 4)
+    cap = N + N // 16 + 4096
+
+    def with_cap(t):
+        out = torch.empty((cap,) + tuple(t.shape[1:]), device=dev, dtype=torch.float32)
+        out[:N] = t
+        return out
+
+    # two independent particle buffers (positions A / B of the same cloud), each [coords, v, m, p]
+    bufs = [[with_cap(X), with_cap(vfull), with_cap(mass), with_cap(pressure)] for X in (A, B)]
+    n_cur = [N, N]
+    del A, B, vfull, cand, vel, rho, mass, pressure
     h = T(r / T(2))
 
     def step(s, count_only=False):
-        local, coords, n_own = slab.step_inputs(rows[(s + 1) % 2])
+        k = (s + 1) % 2
+        bufs[k], n_own, nl = ex.exchange_inplace(bufs[k], n_cur[k])
+        n_cur[k] = n_own
+        cbuf, vbuf, mbuf, pbuf = bufs[k]
+        coords = cbuf[:nl]
         slab.update_(coords)
-        nl = local.shape[0]
         if count_only:
             cnt = torch.zeros(nl, dtype=torch.int64, device=dev)
             pn.foreach_point_neighbor(pn.CountNeighbors(cnt), coords, coords, slab.nhs)
             return int(cnt[:n_own].sum()), n_own
-        v = local[:, 3:7].contiguous()
-        m = local[:, 7].contiguous()
-        p = local[:, 8].contiguous()
+        v, m, p = vbuf[:nl], mbuf[:nl], pbuf[:nl]
         dv = torch.empty((nl, 4), device=dev, dtype=torch.float32)
         f = pn.WCSPHInteract(dv, v, v, m, m, p, p, smoothing_length=h, sound_speed=T(10.0))
         pn.foreach_point_neighbor(f, coords, coords, slab.nhs)

@@ -468,7 +468,23 @@ def test_edge_cases(pn, oracle):
     pn.foreach_point_neighbor(pn.NBodyGravity(dvd, dev(mass2), T(6.6743e-11)), td2, td2, nhs)
     _, r64, rabs = og2.nbody(dense2, dense2, mass2, T(6.6743e-11), wide=True)
     assert np.all(np.abs(dvd.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30)
+    # long neighbour lists: > 512 neighbours (global odd-even sort) and 128..512 (shared memory
+    # rank sort) must come out ascending and equal to the oracle's
+    pre_big = pn.PrecomputedNeighborhoodSearch[3](search_radius=T(0.1), n_points=len(dense2),
+                                                  update_neighborhood_search=nhs, max_neighbors=4000)
+    pn.initialize_(pre_big, td2, td2)
+    off_b, ids_b = pre_big.export_csr()
+    off_o2, ids_o2 = og2.neighbor_lists(dense2, dense2, sort=True)
+    assert (off_b.cpu().numpy() == off_o2).all() and (ids_b.cpu().numpy() == ids_o2).all()
+    assert int(np.diff(off_o2).max()) > 512
     pn.initialize_(nhs, td, td)
+    pre_mid = pn.PrecomputedNeighborhoodSearch[3](search_radius=T(0.1), n_points=300,
+                                                  update_neighborhood_search=nhs, max_neighbors=400)
+    pn.initialize_(pre_mid, td, td)
+    off_m, ids_m = pre_mid.export_csr()
+    off_o1, ids_o1 = og.neighbor_lists(dense, dense, sort=True)
+    assert (off_m.cpu().numpy() == off_o1).all() and (ids_m.cpu().numpy() == ids_o1).all()
+    assert 128 < int(np.diff(off_o1).max()) <= 512
     # determinism: two builds give identical structures
     pn.update_(nhs, td, td)
     cs_a, cp_a = nhs.export_csr()
