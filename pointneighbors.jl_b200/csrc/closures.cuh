@@ -27,6 +27,7 @@ namespace pnb {
 struct CountCl {
     static constexpr bool kCountOnly = true;
     static constexpr int kPayBytes = 0;
+    static constexpr int kWarpsPerCell = 2;
     int64_t *out;
     struct State { int cnt; };
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
@@ -66,6 +67,7 @@ template <bool EXACT>
 struct NBodyClT {
     static constexpr bool kCountOnly = false;
     static constexpr int kPayBytes = 4;
+    static constexpr int kWarpsPerCell = 2;
     const float *mass_sorted;  // mass of the neighbour points in cell order
     float negG;
     float *dv;
@@ -131,6 +133,7 @@ template <bool EXACT>
 struct WcsphClT {
     static constexpr bool kCountOnly = false;
     static constexpr int kPayBytes = 16 + 16;
+    static constexpr int kWarpsPerCell = 4;
     const float4 *vrho_sorted;  // (vx, vy, vz, rho) of the neighbour points, cell order
     const float4 *mp_sorted;    // (mass, pressure, 1/rho, mass/rho) of the neighbour points
     const float *v_x;           // general path: state of the points looped over, (nd+1) per point

@@ -28,6 +28,7 @@ namespace pnb {
 struct ListCountCl {
     static constexpr bool kCountOnly = true;
     static constexpr int kPayBytes = 0;
+    static constexpr int kWarpsPerCell = 2;
     uint32_t *out;
     struct State { int cnt; };
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
@@ -47,6 +48,7 @@ struct ListCountCl {
 struct ListFillCl {
     static constexpr bool kCountOnly = false;
     static constexpr int kPayBytes = 0;
+    static constexpr int kWarpsPerCell = 2;
     const int64_t *offsets;
     int32_t *ids;
     struct State { int64_t pos; };

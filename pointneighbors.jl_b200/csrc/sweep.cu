@@ -97,14 +97,14 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, sizeof(int)));
         PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, sizeof(int), s));
         size_t pay = (size_t)kFCap * CL::kPayBytes;
-        const size_t red = sizeof(typename CL::State) * kFTX * (kWPC - 1) * 32;
+        const size_t red = sizeof(typename CL::State) * kFTX * (CL::kWarpsPerCell - 1) * 32;
         if (red > pay) pay = red;
         const size_t smem = sizeof(float4) * kFCapPad + pay;
         pnb_status st = allow_smem(k_sweep_tiles<ND, PER, CL>, smem);
         if (st != PNB_OK) return st;
         {
             ProfScope ps(PH_SWEEP_CELLS, s);
-            k_sweep_tiles<ND, PER, CL><<<(unsigned)blocks, kFThreads, smem, s>>>(
+            k_sweep_tiles<ND, PER, CL><<<(unsigned)blocks, kFTX * CL::kWarpsPerCell * 32, smem, s>>>(
                 g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);
             PNB_LAUNCHED();
         }

@@ -8,7 +8,7 @@
 //   * stages the candidates of all rows of a tile at once (slot-major: for every x-column of
 //     the tile's (TX+2) columns the cells of all rows are contiguous, so the 3^d neighbour cells
 //     of a tile cell are ONE contiguous range of shared memory),
-//   * splits that range between kWPC warps per cell in an interleaved fashion (warp p takes the
+//   * splits that range between kWPC (2 or 4) warps per cell in an interleaved fashion (warp p takes the
 //     32-candidate blocks b = p, p + kWPC, ...), so every warp sees a uniform sample of all rows,
 //   * tests up to 8 blocks (256 candidates) into 8 hit masks per lane before draining them,
 //   * adds the kWPC partial accumulators of a point through shared memory at the end.
@@ -22,22 +22,27 @@
 namespace pnb {
 
 constexpr int kFTX = 4;                    // cells per tile
-constexpr int kWPC = 4;                    // warps per cell
-constexpr int kFThreads = kFTX * kWPC * 32;
 constexpr int kFSlots = kFTX + 2;
 constexpr int kFCap = 1920;                // staged candidates per tile (typical: 6*9*27 = 1458)
 constexpr int kFCapPad = kFCap + 32;
-constexpr int kFMasks = 8;
 
 __host__ __device__ constexpr int rows_of(int nd) { return nd == 3 ? 9 : (nd == 2 ? 3 : 1); }
 
+// kWPC (warps per cell) is a property of the closure: cheap closures run best with 2 (less
+// merge/synchronisation overhead, better balance: measured count 7.8 -> 6.6 ms, n-body
+// 14.5 -> 12.9 ms), the latency-heavy WCSPH interaction needs the occupancy of 4
+// (18.9 ms vs 22.8 ms with 2).
 template <int ND, bool PER, class CL>
-__global__ void __launch_bounds__(kFThreads, 2)
+__global__ void __launch_bounds__(kFTX * CL::kWarpsPerCell * 32, 1024 / (kFTX * CL::kWarpsPerCell * 32))
 k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
               CL cl, int *__restrict__ overflow_tiles, int *__restrict__ overflow_count)
 {
     constexpr int NR = rows_of(ND);
     constexpr int NE = kFSlots * NR;          // staged cells per tile
+    constexpr int kWPC = CL::kWarpsPerCell;
+    constexpr int kFThreads = kFTX * kWPC * 32;
+    // hit-mask words per lane: one drain per batch covers a whole part (729 / kWPC candidates)
+    constexpr int kFMasks = kWPC == 2 ? 12 : 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_pos = reinterpret_cast<float4 *>(smem_raw);
     unsigned char *s_pay = smem_raw + sizeof(float4) * kFCapPad;
