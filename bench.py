@@ -345,8 +345,8 @@ def gpu_arm(args):
     sweep_avg = sweep_ms / max(sweep_n, 1)
     bytes_sweep = 56 * N + 4 * (C_cells + 1)          # WCSPH interact
     ach = bytes_sweep / (sweep_avg * 1e-3) / 1e9
-    build_names = ["k_cell_count", "k_scan_lookback", "k_scatter", "k_finalize_cells"]
-    build_ms = sum(prof[k][0] for k in build_names) / max(prof["k_cell_count"][1], 1)
+    build_names = ["k_cell_hist", "k_scan_lookback", "k_scatter_points"]
+    build_ms = sum(prof[k][0] for k in build_names) / max(prof["k_cell_hist"][1], 1)
     bytes_update = 28 * N + 4 * (C_cells + 1)          # 16N + 4(C+1) + 12N (cell-ordered coordinates)
     ach_u = bytes_update / (build_ms * 1e-3) / 1e9
     P_avg = float(np.mean(pairs))
@@ -372,7 +372,7 @@ def gpu_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_cells<3,false,WcsphCl>", "achieved": ach,
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_tiles<3,false,WcsphClT<false>,4,true>", "achieved": ach,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                      "peak_source": peak_src, "launch_ms": sweep_avg,
                      "algorithmic_bytes": bytes_sweep,

@@ -134,6 +134,11 @@ pnb_status pnb_grid_export_dvov(const pnb_grid *g, int32_t *backend, int32_t *le
 void pnb_set_exact_arithmetic(int on);
 int pnb_get_exact_arithmetic(void);
 
+/* Measurement overrides of the tile sweep (3-D, non-periodic): warps per cell (2 or 4, 0 = the
+ * closure's default) and the fp16 pre-filter of the distance test (0 = off: exact Float32 test,
+ * -1 = default on).  Results are identical for every setting; only the speed changes. */
+void pnb_set_tuning(int warps_per_cell, int half_prefilter);
+
 /* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */
 pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
                                    int64_t n, const int32_t *points, int64_t n_points,

@@ -28,8 +28,11 @@ struct CountCl {
     static constexpr bool kCountOnly = true;
     static constexpr int kPayBytes = 0;
     static constexpr int kWarpsPerCell = 2;
+    static constexpr int kAccWords = 1;
     int64_t *out;
     struct State { int cnt; };
+    __device__ __forceinline__ void save_acc(const State &, float *) const {}
+    __device__ __forceinline__ void add_acc(State &, const float *) const {}
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
     __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
     __device__ __forceinline__ void count(State &s, int c) const { s.cnt += c; }
@@ -73,6 +76,16 @@ struct NBodyClT {
     float *dv;
     int nd;
     struct State { float a[3]; };
+    static constexpr int kAccWords = 3;
+    // partial accumulators of one warp, word w of lane l at p[w * 32] (p already points at lane l)
+    __device__ __forceinline__ void save_acc(const State &s, float *p) const
+    {
+        p[0] = s.a[0]; p[32] = s.a[1]; p[64] = s.a[2];
+    }
+    __device__ __forceinline__ void add_acc(State &s, const float *p) const
+    {
+        s.a[0] += p[0]; s.a[1] += p[32]; s.a[2] += p[64];
+    }
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.a[0] = s.a[1] = s.a[2] = 0.f; }
     __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi, int) const
     {
@@ -142,6 +155,15 @@ struct WcsphClT {
     float *dv;
     int nd;
     struct State { float v[3]; float rho, p, inv_rho; float acc[4]; };
+    static constexpr int kAccWords = 4;
+    __device__ __forceinline__ void save_acc(const State &s, float *p) const
+    {
+        p[0] = s.acc[0]; p[32] = s.acc[1]; p[64] = s.acc[2]; p[96] = s.acc[3];
+    }
+    __device__ __forceinline__ void add_acc(State &s, const float *p) const
+    {
+        s.acc[0] += p[0]; s.acc[1] += p[32]; s.acc[2] += p[64]; s.acc[3] += p[96];
+    }
 
     __device__ __forceinline__ void init(State &s, bool active, int i_sorted, int i_id) const
     {

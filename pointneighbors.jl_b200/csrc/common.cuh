@@ -57,10 +57,10 @@ static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // bench.py for the roofline numbers.  Off by default: no events are recorded then.
 // ---------------------------------------------------------------------------------------------
 enum Phase {
-    PH_BUILD_CELL_COUNT = 0,  // k_cell_count
-    PH_BUILD_SCAN,            // k_scan_lookback (+ its two tiny memsets)
-    PH_BUILD_SCATTER,         // k_scatter
-    PH_BUILD_FINALIZE,        // k_finalize_cells
+    PH_BUILD_CELL_COUNT = 0,  // k_cell_hist
+    PH_BUILD_SCAN,            // k_scan_lookback
+    PH_BUILD_SCATTER,         // k_scatter_points
+    PH_BUILD_FINALIZE,        // k_canonicalize (on demand, not part of update!)
     PH_GATHER,                // k_gather_* (payload into cell order)
     PH_SWEEP_CELLS,           // k_sweep_cells / k_sweep_tiles
     PH_SWEEP_OVERFLOW,        // k_sweep_overflow

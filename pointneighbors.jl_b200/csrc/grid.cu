@@ -82,7 +82,7 @@ static void prof_collect()
 }
 
 static const char *kPhaseNames[PH_COUNT_] = {
-    "k_cell_count", "k_scan_lookback", "k_scatter", "k_finalize_cells", "k_gather",
+    "k_cell_hist", "k_scan_lookback", "k_scatter_points", "k_canonicalize", "k_gather",
     "k_sweep_cells", "k_sweep_overflow", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export"};
 
 static const char *kDomainMsg =
@@ -93,11 +93,12 @@ static const char *kBoundsMsg =
 
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
 {
-    PNB_CUDA(cudaMemcpyAsync(g->h_err, g->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // the error word lives in mapped pinned host memory (kernels OR their bits into it through
+    // d_err): one stream synchronisation, no copy
     PNB_CUDA(cudaStreamSynchronize(s));
-    int e = *g->h_err;
+    int e = *(volatile int *)g->h_err;
     if (e == 0) return PNB_OK;
-    PNB_CUDA(cudaMemsetAsync(g->d_err, 0, sizeof(int), s));
+    *(volatile int *)g->h_err = 0;
     if (e & 1) { set_error("%s", kDomainMsg); return PNB_ERR_DOMAIN; }
     if (e & 4) { set_error("%s", kListFullMsg); return PNB_ERR_LIST_FULL; }
     set_error("%s", kBoundsMsg);
@@ -312,18 +313,26 @@ extern "C" pnb_status pnb_grid_create_window_f32(int ndims, float r, const float
         return s;
     };
     int64_t C = total;
-    if ((e = cudaMalloc(&g->cell_start, sizeof(uint32_t) * (size_t)(C + 1))) != cudaSuccess)
+    // cell_start = alloc + 3 so that cell_start + 1 (the scan output / scatter cursor) is 16-byte
+    // aligned; cell_start[0] = 0 is written here once and never again
+    if ((e = cudaMalloc(&g->cell_start_alloc, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
         return fail(e, "cudaMalloc cell_start");
-    if ((e = cudaMalloc(&g->cell_count, sizeof(uint32_t) * (size_t)(C + 1))) != cudaSuccess)
+    g->cell_start = g->cell_start_alloc + 3;
+    if ((e = cudaMalloc(&g->cell_count, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
         return fail(e, "cudaMalloc cell_count");
-    if ((e = cudaMemset(g->cell_start, 0, sizeof(uint32_t) * (size_t)(C + 1))) != cudaSuccess)
+    if ((e = cudaMemset(g->cell_start_alloc, 0, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
         return fail(e, "cudaMemset");
-    if ((e = cudaMalloc(&g->d_err, sizeof(int))) != cudaSuccess) return fail(e, "cudaMalloc err");
-    if ((e = cudaMemset(g->d_err, 0, sizeof(int))) != cudaSuccess) return fail(e, "cudaMemset");
-    if ((e = cudaMallocHost(&g->h_err, sizeof(int))) != cudaSuccess)
-        return fail(e, "cudaMallocHost");
+    if ((e = cudaMemset(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
+        return fail(e, "cudaMemset");
+    if ((e = cudaHostAlloc(&g->h_err, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
+        return fail(e, "cudaHostAlloc");
+    *g->h_err = 0;
+    if ((e = cudaHostGetDevicePointer(&g->d_err, g->h_err, 0)) != cudaSuccess)
+        return fail(e, "cudaHostGetDevicePointer");
     if ((e = cudaMalloc(&g->scan_ticket, sizeof(unsigned int))) != cudaSuccess)
         return fail(e, "cudaMalloc ticket");
+    if ((e = cudaMemset(g->scan_ticket, 0, sizeof(unsigned int))) != cudaSuccess)
+        return fail(e, "cudaMemset");
     *out = g;
     return PNB_OK;
 }
@@ -331,15 +340,13 @@ extern "C" pnb_status pnb_grid_create_window_f32(int ndims, float r, const float
 extern "C" void pnb_grid_destroy(pnb_grid *g)
 {
     if (!g) return;
-    cudaFree(g->cell_start);
+    cudaFree(g->cell_start_alloc);
     cudaFree(g->cell_count);
     cudaFree(g->cell_points);
-    cudaFree(g->ids_tmp);
-    cudaFree(g->cell_rank);
     cudaFree(g->sorted);
+    cudaFree(g->sorted_alt);
     cudaFree(g->scan_status);
     cudaFree(g->scan_ticket);
-    cudaFree(g->d_err);
     if (g->h_err) cudaFreeHost(g->h_err);
     cudaFree(g->scratch);
     cudaFree(g->ovf_tiles);
@@ -353,86 +360,193 @@ extern "C" int64_t pnb_grid_n_points(const pnb_grid *g) { return g ? g->n_built 
 
 // ---------------------------------------------------------------------------------------------
 // kernels of the counting sort
+//
+//   update! = k_cell_hist (read 12 N) -> k_scan_lookback (8 C) -> k_scatter_points (read 12 N,
+//   write 16 N): 40 N + 8 C bytes, two passes over the coordinates and nothing else.  The cell
+//   index is recomputed in the second pass instead of being written and re-read, and the
+//   slot of a point is taken from an atomic cursor (= cell_start itself, see below), so the
+//   order of the points inside a cell is arrival order -- exactly what the reference has
+//   (pushat_atomic!, src/vector_of_vectors.jl:99-109).  Consumers that need a reproducible
+//   order (exports, exact arithmetic mode, neighbour-list fills) call ensure_canonical(), which
+//   sorts every cell by point id once (k_canonicalize) and is skipped by the fast sweeps.
 // ---------------------------------------------------------------------------------------------
 namespace pnb {
 
 constexpr int kBuildThreads = 256;
+constexpr int kBuildPPT = 4;                                // points per thread
+constexpr int kBuildTile = kBuildThreads * kBuildPPT;       // points per block
 
-// K_a: cell index + domain check + histogram with warp-aggregated atomics.
-//   reference: the first half of initialize_grid! (src/nhs_grid.jl:271-278): cell_coords,
-//   check_cell_bounds, and the `lengths[cell] += 1` of pushat_atomic!
-//   (src/vector_of_vectors.jl:102).  The returned old value is the point's provisional rank.
-// HBM: reads 12 B/point (coordinates, staged through shared memory so the three component
-// loads of a warp are three fully coalesced 128 B requests), writes 8 B/point.
-template <int ND>
-__global__ void __launch_bounds__(kBuildThreads)
-k_cell_count(GridP g, const float *__restrict__ y, int64_t n_idx, const int32_t *__restrict__ idx,
-             int base, int2 *__restrict__ cell_rank, uint32_t *__restrict__ cell_count,
-             int *__restrict__ err)
+struct BuildP {
+    float rcs[3];   // fl(1 / cell_size): fast quotient, verified against the exact division
+};
+
+// cell_coords for one dimension (src/nhs_grid.jl:622-628, src/cell_lists/full_grid.jl:93) with
+// the division replaced by a multiplication whenever that provably gives the same floor:
+//   q' = fl(t * fl(1/cs)) differs from the IEEE quotient fl(t / cs) by less than |q| 2^-22, so
+//   if q' is farther than |q| 2^-21 from both neighbouring integers the two floors agree.
+// Otherwise (about 1e-4 of the points) the exact path of common.cuh decides.
+template <bool PER>
+__device__ __forceinline__ int cell_coord_fast(float x, float minc, float cs, float rcs, int nc,
+                                               int off)
 {
-    __shared__ float s_xyz[kBuildThreads * ND];
-    const int64_t block0 = (int64_t)blockIdx.x * kBuildThreads;
-    const int64_t k = block0 + threadIdx.x;
-    float p[3] = {0.f, 0.f, 0.f};
-    if (idx == nullptr) {
-        // coalesced tile load of kBuildThreads * ND consecutive floats
-        const int64_t f0 = block0 * ND;
-        const int64_t fend = n_idx * ND;
+    const float t = __fsub_rn(x, minc);
+    const float q = __fmul_rn(t, rcs);
+    const float f = floorf(q);
+    const float fr = __fsub_rn(q, f);                      // exact
+    const float delta = __fmul_rn(fabsf(q), 4.76837158203125e-7f);   // |q| 2^-21
+    if (!(fr > delta && fr < __fsub_rn(1.0f, delta) && fabsf(f) < 4194304.0f))
+        return cell_coord(x, minc, cs, PER ? 1 : 0, nc, off);
+    int c = (int)f + 1;
+    if (PER) {
+        c -= 2;
+        if (c < 0) c += nc; else if (c >= nc) c -= nc;
+        if (c < 0 || c >= nc) c = floormod_i(c, nc);
+        c += 2;
+    }
+    return c - off;
+}
+
+template <int ND, bool PER>
+__device__ __forceinline__ int point_cell_fast(const GridP &g, const BuildP &bp, const float *p)
+{
+    int cc[3] = {1, 1, 1};
+    bool ok = true;
 #pragma unroll
-        for (int t = 0; t < ND; t++) {
-            int64_t f = f0 + threadIdx.x + (int64_t)t * kBuildThreads;
-            if (f < fend) s_xyz[threadIdx.x + t * kBuildThreads] = __ldg(y + f);
+    for (int d = 0; d < ND; d++) {
+        cc[d] = cell_coord_fast<PER>(p[d], g.minc[d], g.cs[d], bp.rcs[d], g.nc[d], g.off[d]);
+        ok = ok && (cc[d] >= 2) && (cc[d] <= g.gs[d] - 1);
+    }
+    if (!ok) return -1;
+    return (cc[0] - 1) + (cc[1] - 1) * g.gs[0] + (cc[2] - 1) * g.gs[0] * g.gs[1];
+}
+
+// Coalesced load of one tile of coordinates into shared memory (float4 when the tile is full and
+// the array is 16-byte aligned), then kBuildPPT strided points per thread.
+template <int ND>
+__device__ __forceinline__ void load_tile(const float *__restrict__ y, int64_t block0, int64_t n,
+                                          float *s_xyz)
+{
+    const int64_t f0 = block0 * ND;
+    const int64_t fend = n * ND;
+    constexpr int kFloats = kBuildTile * ND;
+    if (f0 + kFloats <= fend && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+        const float4 *src = reinterpret_cast<const float4 *>(y + f0);
+        float4 *dst = reinterpret_cast<float4 *>(s_xyz);
+#pragma unroll
+        for (int t = 0; t < (kFloats / 4 + kBuildThreads - 1) / kBuildThreads; t++) {
+            const int q = (int)threadIdx.x + t * kBuildThreads;
+            if (q < kFloats / 4) dst[q] = __ldg(src + q);
         }
-        __syncthreads();
-#pragma unroll
-        for (int d = 0; d < ND; d++) p[d] = s_xyz[threadIdx.x * ND + d];
-    } else if (k < n_idx) {
-        const int64_t pt = (int64_t)idx[k] - base;
-#pragma unroll
-        for (int d = 0; d < ND; d++) p[d] = __ldg(y + pt * ND + d);
+    } else {
+        for (int q = threadIdx.x; q < kFloats; q += kBuildThreads)
+            if (f0 + q < fend) s_xyz[q] = __ldg(y + f0 + q);
     }
-    bool in_range = k < n_idx;
-    int cc[3];
-    int lin = in_range ? point_cell<ND>(g, p, cc) : -1;
-    bool valid = in_range && lin >= 0;
-    if (in_range && lin < 0) atomicOr(err, 1);
-    unsigned act = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-        unsigned m = __match_any_sync(act, lin);
-        int leader = __ffs(m) - 1;
-        int pos = __popc(m & ((1u << lane_id()) - 1u));
-        unsigned basev = 0;
-        if (lane_id() == leader) basev = atomicAdd(cell_count + lin, (unsigned)__popc(m));
-        basev = __shfl_sync(m, basev, leader);
-        cell_rank[k] = make_int2(lin, (int)(basev + pos));
-    } else if (in_range) {
-        cell_rank[k] = make_int2(-1, 0);
-    }
+    __syncthreads();
 }
 
-// K_c: scatter ids to cell_start[cell] + rank   (the `backend[new_length, i] = value` of
-// pushat_atomic!, src/vector_of_vectors.jl:109, into a CSR instead of a 100-row matrix).
-__global__ void __launch_bounds__(kBuildThreads)
-k_scatter(int64_t n_idx, const int32_t *__restrict__ idx, int base,
-          const int2 *__restrict__ cell_rank, const uint32_t *__restrict__ cell_start,
-          int32_t *__restrict__ ids_tmp)
+// Runs of equal cells among consecutive lanes (points of a cell-sorted cloud arrive in runs):
+// the first lane of a run issues one atomic for the whole run.
+//   returns the run head lane; *run_len is valid on the head lane.
+__device__ __forceinline__ int run_head(int lin, bool valid, int *run_len)
 {
-    int64_t k = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x;
-    if (k >= n_idx) return;
-    int2 cr = cell_rank[k];
-    if (cr.x < 0) return;
-    int32_t id = idx ? idx[k] - base : (int32_t)k;
-    ids_tmp[cell_start[cr.x] + (uint32_t)cr.y] = id;
+    const int lane = lane_id();
+    const int prev = __shfl_up_sync(0xffffffffu, lin, 1);
+    const bool head = valid && (lane == 0 || prev != lin);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    const unsigned below = (2u << lane) - 1u;                 // lanes 0..lane (lane 31: all ones)
+    const int h = 31 - __clz(heads & below);
+    const unsigned ends = (heads | ~act) & ~below;            // next run start or invalid lane
+    const int e = ends ? (__ffs(ends) - 1) : 32;
+    *run_len = e - lane;                                      // meaningful on the head lane
+    return h;
 }
 
-// K_d: one warp per cell: order the cell's ids ascending (rank by counting), write them to
-// cell_points and gather the coordinates into the cell-ordered float4 array (x, y, z, id).
-// Cells with <= 32 points (the normal case) stay in registers.
-template <int ND>
+// K_a: histogram.  reference: the `lengths[cell] += 1` half of pushat_atomic!
+// (src/vector_of_vectors.jl:102) for every point of initialize_grid! (src/nhs_grid.jl:271-278),
+// including check_cell_bounds (full_grid.jl:205-213) -> error word.
+template <int ND, bool PER>
+__global__ void __launch_bounds__(kBuildThreads)
+k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
+            const int32_t *__restrict__ idx, int base, uint32_t *__restrict__ cell_count,
+            int *__restrict__ err)
+{
+    __shared__ __align__(16) float s_xyz[kBuildTile * ND];
+    const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
+    if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < kBuildPPT; j++) {
+        const int loc = j * kBuildThreads + (int)threadIdx.x;
+        const int64_t k = block0 + loc;
+        const bool in_range = k < n_idx;
+        float p[3] = {0.f, 0.f, 0.f};
+        if (idx == nullptr) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) p[d] = s_xyz[loc * ND + d];
+        } else if (in_range) {
+            const int64_t pt = (int64_t)idx[k] - base;
+#pragma unroll
+            for (int d = 0; d < ND; d++) p[d] = __ldg(y + pt * ND + d);
+        }
+        const int lin = in_range ? point_cell_fast<ND, PER>(g, bp, p) : -1;
+        const bool valid = lin >= 0;
+        bad = bad || (in_range && !valid);
+        int run_len;
+        const int h = run_head(lin, valid, &run_len);
+        if (valid && h == lane_id()) atomicAdd(cell_count + lin, (unsigned)run_len);
+    }
+    if (bad) atomicOr(err, 1);
+}
+
+// K_c: scatter.  `cursor` is cell_start + 1 holding the exclusive prefix E[c] at cursor[c]; the
+// atomic hands out the slots of cell c and leaves E[c] + count[c] = E[c + 1] behind, i.e. after
+// this kernel cell_start[0 .. C] is the finished CSR offset array with no copy.
+// (the `backend[new_length, i] = value` of pushat_atomic!, src/vector_of_vectors.jl:109, into a
+// CSR of (x, y, z, id) records instead of a 100-row id matrix.)
+template <int ND, bool PER>
+__global__ void __launch_bounds__(kBuildThreads)
+k_scatter_points(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
+                 const int32_t *__restrict__ idx, int base, uint32_t *__restrict__ cursor,
+                 float4 *__restrict__ sorted)
+{
+    __shared__ __align__(16) float s_xyz[kBuildTile * ND];
+    const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
+    if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
+#pragma unroll
+    for (int j = 0; j < kBuildPPT; j++) {
+        const int loc = j * kBuildThreads + (int)threadIdx.x;
+        const int64_t k = block0 + loc;
+        const bool in_range = k < n_idx;
+        float p[3] = {0.f, 0.f, 0.f};
+        int32_t id = (int32_t)k;
+        if (idx == nullptr) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) p[d] = s_xyz[loc * ND + d];
+        } else if (in_range) {
+            id = idx[k] - base;
+#pragma unroll
+            for (int d = 0; d < ND; d++) p[d] = __ldg(y + (int64_t)id * ND + d);
+        }
+        const int lin = in_range ? point_cell_fast<ND, PER>(g, bp, p) : -1;
+        const bool valid = lin >= 0;
+        int run_len;
+        const int h = run_head(lin, valid, &run_len);
+        unsigned basev = 0;
+        if (valid && h == lane_id()) basev = atomicAdd(cursor + lin, (unsigned)run_len);
+        basev = __shfl_sync(0xffffffffu, basev, h & 31);
+        if (valid)
+            sorted[basev + (unsigned)(lane_id() - h)] = make_float4(p[0], p[1], p[2], __int_as_float(id));
+    }
+}
+
+// Canonical order: one warp per cell sorts the cell's records by point id (rank by counting) and
+// writes them to `out` plus the id list `cell_points`.  Cells with <= 32 points (the normal
+// case) stay in registers.
 __global__ void __launch_bounds__(256)
-k_finalize_cells(int total_cells, const uint32_t *__restrict__ cell_start,
-                 const int32_t *__restrict__ ids_tmp, const float *__restrict__ y,
-                 int32_t *__restrict__ cell_points, float4 *__restrict__ sorted)
+k_canonicalize(int total_cells, const uint32_t *__restrict__ cell_start,
+               const float4 *__restrict__ in, float4 *__restrict__ out,
+               int32_t *__restrict__ cell_points)
 {
     int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= total_cells) return;
@@ -441,40 +555,40 @@ k_finalize_cells(int total_cells, const uint32_t *__restrict__ cell_start,
     const int cnt = (int)(s1 - s0);
     if (cnt == 0) return;
     if (cnt <= 32) {
-        int v = lane < cnt ? ids_tmp[s0 + lane] : 0x7fffffff;
+        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+        int v = 0x7fffffff;
+        if (lane < cnt) { rec = in[s0 + lane]; v = __float_as_int(rec.w); }
         int r = 0;
         for (int k = 0; k < cnt; k++) r += (__shfl_sync(0xffffffffu, v, k) < v) ? 1 : 0;
         if (lane < cnt) {
-            float px = __ldg(y + (int64_t)v * ND);
-            float py = ND > 1 ? __ldg(y + (int64_t)v * ND + 1) : 0.f;
-            float pz = ND > 2 ? __ldg(y + (int64_t)v * ND + 2) : 0.f;
             cell_points[s0 + r] = v;
-            sorted[s0 + r] = make_float4(px, py, pz, __int_as_float(v));
+            out[s0 + r] = rec;
         }
     } else {
         for (int e = lane; e < cnt; e += 32) {
-            int v = ids_tmp[s0 + e];
+            const float4 rec = in[s0 + e];
+            const int v = __float_as_int(rec.w);
             int r = 0;
-            for (int k = 0; k < cnt; k++) r += (ids_tmp[s0 + k] < v) ? 1 : 0;
-            float px = __ldg(y + (int64_t)v * ND);
-            float py = ND > 1 ? __ldg(y + (int64_t)v * ND + 1) : 0.f;
-            float pz = ND > 2 ? __ldg(y + (int64_t)v * ND + 2) : 0.f;
+            for (int k = 0; k < cnt; k++) r += (__float_as_int(in[s0 + k].w) < v) ? 1 : 0;
             cell_points[s0 + r] = v;
-            sorted[s0 + r] = make_float4(px, py, pz, __int_as_float(v));
+            out[s0 + r] = rec;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// single-pass exclusive scan with decoupled look-back (Merrill & Garland), uint32
-//   tile = 256 threads x 8 items; status word = (flag << 62) | value, flag 1 = aggregate,
-//   2 = inclusive prefix.  Tiles are taken from an atomic ticket so a tile never waits on a
-//   tile that has not started.
+// single-pass exclusive scan with decoupled look-back (Merrill & Garland), uint32 input
+//   tile = 512 threads x 16 items; status word = flag(2) | epoch(14) | value(48), flag 1 = tile
+//   aggregate, 2 = inclusive prefix.  A word counts only if its epoch is the current launch's,
+//   so the status array is never cleared between launches; tiles are taken from an atomic
+//   ticket (reset by the last tile) so a tile never waits on a tile that has not started.
+//   ZERO_IN: the input is cleared after it has been read (the histogram is ready for the next
+//   build without a memset).
 // Replaces nothing in the reference (its 100-row cell matrix needs no offsets): this is what
-// turns the histogram into CSR offsets.  HBM: reads 4 B/cell, writes 4 B/cell.
+// turns the histogram into CSR offsets.  HBM: reads 4 B/cell, writes 4 (+4) B/cell.
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
@@ -488,13 +602,20 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// status word: (flag << 62) | value, flag 1 = tile aggregate, 2 = inclusive prefix
-constexpr unsigned long long kScanValMask = (1ULL << 62) - 1ULL;
+constexpr unsigned long long kScanValMask = (1ULL << 48) - 1ULL;
+constexpr int kScanEpochs = 1 << 14;
 
-template <typename OutT>
+// flag of a status word as seen by a launch with epoch `ep` (0 = not published yet)
+__device__ __forceinline__ unsigned scan_flag(unsigned long long sv, unsigned ep)
+{
+    return (((unsigned)(sv >> 48)) & (kScanEpochs - 1)) == ep ? (unsigned)(sv >> 62) : 0u;
+}
+
+template <typename OutT, bool ZERO_IN, bool WRITE_TOTAL>
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_lookback(const uint32_t *__restrict__ in, OutT *__restrict__ out, int64_t n,
-                unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket)
+k_scan_lookback(uint32_t *__restrict__ in, OutT *__restrict__ out, int64_t n,
+                unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
+                unsigned epoch)
 {
     __shared__ unsigned int s_tile;
     __shared__ uint32_t s_warp[kScanThreads / 32];
@@ -503,18 +624,25 @@ k_scan_lookback(const uint32_t *__restrict__ in, OutT *__restrict__ out, int64_t
     __syncthreads();
     const unsigned int tile = s_tile;
     const int64_t base = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    const unsigned long long ep_bits = (unsigned long long)epoch << 48;
 
     uint32_t v[kScanItems];
     if (base + kScanItems <= n && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(in + base));
-        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(in + base) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        uint4 *src = reinterpret_cast<uint4 *>(in + base);
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; q++) {
+            const uint4 a = src[q];
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+            if (ZERO_IN) src[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < kScanItems; k++) v[k] = (base + k < n) ? __ldg(in + base + k) : 0u;
+        for (int k = 0; k < kScanItems; k++) {
+            v[k] = (base + k < n) ? in[base + k] : 0u;
+            if (ZERO_IN && base + k < n) in[base + k] = 0u;
+        }
     }
-    // a tile holds 2048 items; callers guarantee the sum of one tile fits 32 bits
+    // a tile holds 8192 items; callers guarantee the sum of one tile fits 32 bits
     uint32_t tsum = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) tsum += v[k];
@@ -542,47 +670,63 @@ k_scan_lookback(const uint32_t *__restrict__ in, OutT *__restrict__ out, int64_t
     if (warp == 0) {
         unsigned long long excl = 0;
         if (tile == 0) {
-            if (lane == 0) st_status(status, (2ULL << 62) | block_agg);
+            if (lane == 0) st_status(status, (2ULL << 62) | ep_bits | block_agg);
         } else {
-            if (lane == 0) st_status(status + tile, (1ULL << 62) | block_agg);
+            if (lane == 0) st_status(status + tile, (1ULL << 62) | ep_bits | block_agg);
             int64_t look = (int64_t)tile - 1;
             while (true) {
                 const int64_t t = look - lane;
                 const bool have = t >= 0;
-                unsigned long long sv;
+                unsigned long long sv = 0;
+                unsigned fl;
                 do {
-                    sv = have ? ld_status(status + t) : (2ULL << 62);
-                } while (__any_sync(0xffffffffu, (sv >> 62) == 0));
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                    if (have) { sv = ld_status(status + t); fl = scan_flag(sv, epoch); }
+                    else fl = 2u;
+                } while (__any_sync(0xffffffffu, fl == 0u));
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, fl == 2u);
                 const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-                unsigned long long contrib = (lane <= first) ? (sv & kScanValMask) : 0ULL;
+                unsigned long long contrib = (have && lane <= first) ? (sv & kScanValMask) : 0ULL;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
                 excl += contrib;
                 if (incl_mask) break;
                 look -= 32;
             }
-            if (lane == 0) st_status(status + tile, (2ULL << 62) | ((excl + block_agg) & kScanValMask));
+            if (lane == 0)
+                st_status(status + tile, (2ULL << 62) | ep_bits | ((excl + block_agg) & kScanValMask));
         }
         if (lane == 0) s_prefix = excl;
     }
     __syncthreads();
     unsigned long long run = s_prefix + thread_excl;
     const bool owns_last = base < n && base + kScanItems >= n;
+    if (base + kScanItems <= n && sizeof(OutT) == 4 &&
+        ((reinterpret_cast<uintptr_t>(out + base) & 15) == 0)) {
+        uint32_t o32[kScanItems];
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        if (base + k < n) out[base + k] = (OutT)run;
-        run += (base + k < n) ? v[k] : 0u;
+        for (int k = 0; k < kScanItems; k++) { o32[k] = (uint32_t)run; run += v[k]; }
+        uint4 *dst = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; q++)
+            dst[q] = make_uint4(o32[4 * q], o32[4 * q + 1], o32[4 * q + 2], o32[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if (base + k < n) out[base + k] = (OutT)run;
+            run += (base + k < n) ? v[k] : 0u;
+        }
     }
     // the thread that owns the last element also writes the total at out[n]
-    if (owns_last) out[n] = (OutT)run;
+    if (WRITE_TOTAL && owns_last) out[n] = (OutT)run;
+    // every ticket of this launch has been handed out once the last one is seen
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) *ticket = 0u;
 }
 
-template <typename OutT>
-static pnb_status scan_impl(pnb_grid *g, const uint32_t *in, OutT *out, int64_t n, cudaStream_t s)
+template <typename OutT, bool ZERO_IN, bool WRITE_TOTAL>
+static pnb_status scan_impl(pnb_grid *g, uint32_t *in, OutT *out, int64_t n, cudaStream_t s)
 {
     if (n <= 0) {
-        PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(OutT), s));
+        if (WRITE_TOTAL) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(OutT), s));
         return PNB_OK;
     }
     int64_t tiles = div_up(n, kScanTile);
@@ -592,12 +736,19 @@ static pnb_status scan_impl(pnb_grid *g, const uint32_t *in, OutT *out, int64_t 
         g->scan_tiles_cap = 0;
         PNB_CUDA(cudaMalloc(&g->scan_status, sizeof(unsigned long long) * (size_t)tiles));
         g->scan_tiles_cap = tiles;
+        g->scan_epoch = 0;
     }
     ProfScope ps(PH_BUILD_SCAN, s);
-    PNB_CUDA(cudaMemsetAsync(g->scan_status, 0, sizeof(unsigned long long) * (size_t)tiles, s));
-    PNB_CUDA(cudaMemsetAsync(g->scan_ticket, 0, sizeof(unsigned int), s));
-    k_scan_lookback<OutT><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, n, g->scan_status,
-                                                                    g->scan_ticket);
+    if (g->scan_epoch == 0 || g->scan_epoch + 1 >= kScanEpochs) {
+        // first use or epoch wrap: clear every status word once (epoch 0 is never current)
+        PNB_CUDA(cudaMemsetAsync(g->scan_status, 0,
+                                 sizeof(unsigned long long) * (size_t)g->scan_tiles_cap, s));
+        PNB_CUDA(cudaMemsetAsync(g->scan_ticket, 0, sizeof(unsigned int), s));
+        g->scan_epoch = 0;
+    }
+    g->scan_epoch++;
+    k_scan_lookback<OutT, ZERO_IN, WRITE_TOTAL><<<(unsigned)tiles, kScanThreads, 0, s>>>(
+        in, out, n, g->scan_status, g->scan_ticket, (unsigned)g->scan_epoch);
     PNB_LAUNCHED();
     return PNB_OK;
 }
@@ -605,59 +756,70 @@ static pnb_status scan_impl(pnb_grid *g, const uint32_t *in, OutT *out, int64_t 
 pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
                               cudaStream_t s)
 {
-    return scan_impl<uint32_t>(g, in, out, n, s);
+    return scan_impl<uint32_t, false, true>(g, const_cast<uint32_t *>(in), out, n, s);
 }
 
 pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *out, int64_t n,
                                      cudaStream_t s)
 {
-    return scan_impl<int64_t>(g, in, out, n, s);
+    return scan_impl<int64_t, false, true>(g, const_cast<uint32_t *>(in), out, n, s);
 }
 
 static pnb_status ensure_point_capacity(pnb_grid *g, int64_t n)
 {
     if (n <= g->cap_points) return PNB_OK;
     cudaFree(g->cell_points); g->cell_points = nullptr;
-    cudaFree(g->ids_tmp); g->ids_tmp = nullptr;
-    cudaFree(g->cell_rank); g->cell_rank = nullptr;
     cudaFree(g->sorted); g->sorted = nullptr;
+    cudaFree(g->sorted_alt); g->sorted_alt = nullptr;
     g->cap_points = 0;
     int64_t cap = n + n / 16 + 32;
-    PNB_CUDA(cudaMalloc(&g->cell_points, sizeof(int32_t) * (size_t)cap));
-    PNB_CUDA(cudaMalloc(&g->ids_tmp, sizeof(int32_t) * (size_t)cap));
-    PNB_CUDA(cudaMalloc(&g->cell_rank, sizeof(int2) * (size_t)cap));
     PNB_CUDA(cudaMalloc(&g->sorted, sizeof(float4) * (size_t)cap));
     g->cap_points = cap;
     return PNB_OK;
 }
 
-template <int ND>
+// Sort every cell by point id (once per build, on demand): the CSR id list `cell_points` and
+// the cell-ordered records become reproducible (ids ascending inside a cell), which is what the
+// exports, the exact arithmetic mode and the neighbour-list fills are specified against.
+pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s)
+{
+    if (g->canonical || !g->built || g->template_search || g->n_built == 0) return PNB_OK;
+    if (!g->sorted_alt) PNB_CUDA(cudaMalloc(&g->sorted_alt, sizeof(float4) * (size_t)g->cap_points));
+    if (!g->cell_points) PNB_CUDA(cudaMalloc(&g->cell_points, sizeof(int32_t) * (size_t)g->cap_points));
+    const int64_t C = g->p.total_cells;
+    {
+        ProfScope ps(PH_BUILD_FINALIZE, s);
+        k_canonicalize<<<(unsigned)div_up(C * 32, 256), 256, 0, s>>>((int)C, g->cell_start, g->sorted,
+                                                                   g->sorted_alt, g->cell_points);
+        PNB_LAUNCHED();
+    }
+    float4 *t = g->sorted; g->sorted = g->sorted_alt; g->sorted_alt = t;
+    g->canonical = true;
+    return PNB_OK;
+}
+
+template <int ND, bool PER>
 static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t *idx,
                            int64_t n_idx, int base, cudaStream_t s)
 {
     const int64_t C = g->p.total_cells;
-    PNB_CUDA(cudaMemsetAsync(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 1), s));
+    BuildP bp;
+    for (int d = 0; d < 3; d++) { volatile float rc = 1.0f / g->p.cs[d]; bp.rcs[d] = rc; }
+    const unsigned blocks = (unsigned)div_up(n_idx, kBuildTile);
+    // cell_count is all zero here: cleared at creation and by every scan (ZERO_IN)
     if (n_idx > 0) {
-        unsigned blocks = (unsigned)div_up(n_idx, kBuildThreads);
         ProfScope ps(PH_BUILD_CELL_COUNT, s);
-        k_cell_count<ND><<<blocks, kBuildThreads, 0, s>>>(g->p, y, n_idx, idx, base, g->cell_rank,
-                                                          g->cell_count, g->d_err);
+        k_cell_hist<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, idx, base,
+                                                              g->cell_count, g->d_err);
         PNB_LAUNCHED();
     }
-    pnb_status st = exclusive_scan_u32(g, g->cell_count, g->cell_start, C, s);
+    // exclusive prefix E[c] -> cell_start[c + 1]; cell_start[0] stays 0 (set at creation)
+    pnb_status st = scan_impl<uint32_t, true, false>(g, g->cell_count, g->cell_start + 1, C, s);
     if (st != PNB_OK) return st;
     if (n_idx > 0) {
-        unsigned blocks = (unsigned)div_up(n_idx, kBuildThreads);
-        {
-            ProfScope ps(PH_BUILD_SCATTER, s);
-            k_scatter<<<blocks, kBuildThreads, 0, s>>>(n_idx, idx, base, g->cell_rank,
-                                                       g->cell_start, g->ids_tmp);
-            PNB_LAUNCHED();
-        }
-        unsigned fblocks = (unsigned)div_up(C * 32, 256);
-        ProfScope ps(PH_BUILD_FINALIZE, s);
-        k_finalize_cells<ND><<<fblocks, 256, 0, s>>>((int)C, g->cell_start, g->ids_tmp, y,
-                                                     g->cell_points, g->sorted);
+        ProfScope ps(PH_BUILD_SCATTER, s);
+        k_scatter_points<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, idx, base,
+                                                                   g->cell_start + 1, g->sorted);
         PNB_LAUNCHED();
     }
     (void)n;
@@ -675,6 +837,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
     const int64_t C = g->p.total_cells;
     if (eachindex_y == nullptr) n_idx = n;
     g->built = false;
+    g->canonical = false;
     // empty!(cell_list)  (src/cell_lists/full_grid.jl:96-105)
     if (g->template_search) {
         // nhs_grid.jl:263-267: zero search radius -> emptied cell list, nothing else
@@ -695,9 +858,12 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
     pnb_status st = ensure_point_capacity(g, n_idx);
     if (st != PNB_OK) return st;
     switch (g->p.ndims) {
-        case 1: st = build_nd<1>(g, y, n, eachindex_y, n_idx, index_base, s); break;
-        case 2: st = build_nd<2>(g, y, n, eachindex_y, n_idx, index_base, s); break;
-        default: st = build_nd<3>(g, y, n, eachindex_y, n_idx, index_base, s); break;
+        case 1: st = g->p.periodic ? build_nd<1, true>(g, y, n, eachindex_y, n_idx, index_base, s)
+                                   : build_nd<1, false>(g, y, n, eachindex_y, n_idx, index_base, s); break;
+        case 2: st = g->p.periodic ? build_nd<2, true>(g, y, n, eachindex_y, n_idx, index_base, s)
+                                   : build_nd<2, false>(g, y, n, eachindex_y, n_idx, index_base, s); break;
+        default: st = g->p.periodic ? build_nd<3, true>(g, y, n, eachindex_y, n_idx, index_base, s)
+                                    : build_nd<3, false>(g, y, n, eachindex_y, n_idx, index_base, s); break;
     }
     if (st != PNB_OK) return st;
     st = check_err_word(g, s);  // also synchronizes: initialize!/update! are blocking calls
@@ -787,11 +953,16 @@ __global__ void k_export_dvov(int total_cells, const uint32_t *__restrict__ cs,
 }
 }  // namespace pnb
 
-extern "C" pnb_status pnb_grid_export_csr(const pnb_grid *g, int32_t *cell_start,
+extern "C" pnb_status pnb_grid_export_csr(const pnb_grid *g_, int32_t *cell_start,
                                           int32_t *cell_points, int index_base, void *stream)
 {
+    pnb_grid *g = const_cast<pnb_grid *>(g_);
     if (!g || !g->built) { set_error("the neighborhood search has not been initialized"); return PNB_ERR_STATE; }
     cudaStream_t s = (cudaStream_t)stream;
+    if (cell_points) {
+        pnb_status stc = ensure_canonical(g, s);
+        if (stc != PNB_OK) return stc;
+    }
     int64_t C1 = (int64_t)g->p.total_cells + 1;
     int64_t m = C1 > g->n_built ? C1 : g->n_built;
     k_export_csr<<<(unsigned)div_up(m, 256), 256, 0, s>>>(C1, g->n_built, g->cell_start,
@@ -810,6 +981,10 @@ extern "C" pnb_status pnb_grid_export_dvov(const pnb_grid *g_, int32_t *backend,
     if (!g || !g->built) { set_error("the neighborhood search has not been initialized"); return PNB_ERR_STATE; }
     cudaStream_t s = (cudaStream_t)stream;
     int64_t C = g->p.total_cells;
+    {
+        pnb_status stc = ensure_canonical(g, s);
+        if (stc != PNB_OK) return stc;
+    }
     if (C > 0) {
         k_export_dvov<<<(unsigned)div_up(C * 32, 256), 256, 0, s>>>(
             (int)C, g->cell_start, g->cell_points, backend, lengths, max_points_per_cell,

@@ -16,20 +16,23 @@ struct pnb_grid {
     int device;
 
     // cell list in CSR form, device
-    uint32_t *cell_start;   // [C+1]
-    uint32_t *cell_count;   // [C]   histogram (scratch of the build)
-    int32_t *cell_points;   // [cap] ids, 0-based, ascending inside a cell
-    int32_t *ids_tmp;       // [cap] scatter output before the per-cell sort
-    int2 *cell_rank;        // [cap] (cell, rank) of the k-th listed point
-    float4 *sorted;         // [cap] (x, y, z, id bits) in cell order
+    uint32_t *cell_start_alloc;  // allocation behind cell_start (offset so cell_start + 1 is 16 B aligned)
+    uint32_t *cell_start;   // [C+1] CSR offsets; during a build cell_start + 1 is the scatter cursor
+    uint32_t *cell_count;   // [C]   histogram (scratch of the build; zero between builds)
+    float4 *sorted;         // [cap] (x, y, z, id bits) in cell order -- the list every sweep reads
+    float4 *sorted_alt;     // [cap] second buffer of ensure_canonical (allocated on first use)
+    int32_t *cell_points;   // [cap] ids, 0-based, ascending inside a cell (valid when canonical)
     int64_t cap_points;
+    bool canonical;         // records inside every cell are ordered by point id (ensure_canonical)
 
     // scan workspace
     unsigned long long *scan_status;
     int64_t scan_tiles_cap;
     unsigned int *scan_ticket;  // [1]
+    int scan_epoch;             // status words of older launches are ignored (no memset per scan)
 
-    // device + pinned error words: bit0 domain, bit1 bounds, bit2 list full
+    // error word in mapped pinned host memory (d_err = its device address):
+    // bit0 domain, bit1 bounds, bit2 list full
     int *d_err;
     int *h_err;
 
@@ -52,7 +55,8 @@ struct pnb_grid {
 
 namespace pnb {
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
-pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate d_err
+pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
+pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s); // ids ascending inside every cell + cell_points
 pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
                               cudaStream_t s);
 pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *out, int64_t n,

@@ -403,7 +403,14 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     NL_CUDA(cudaMallocHost(&l->h_err, sizeof(int)));
     NL_CUDA(cudaMemsetAsync(l->counts, 0, sizeof(uint32_t) * (size_t)(nx + 8), s));
     const bool fast = g->full_build && x == g->y_built && nx == g->n_y_built;
-    pnb_status st = launch_list(g, fast, x, nx, ListCountCl{l->counts}, s);
+    pnb_status st = PNB_OK;
+    if (!sort) {
+        // unsorted lists keep the visiting order: make it the reproducible one (ids ascending
+        // inside every cell); sorted lists do not depend on it
+        st = ensure_canonical(g, s);
+        if (st != PNB_OK) return fail(st);
+    }
+    st = launch_list(g, fast, x, nx, ListCountCl{l->counts}, s);
     if (st != PNB_OK) return fail(st);
     st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
     if (st != PNB_OK) return fail(st);

@@ -9,27 +9,32 @@ namespace pnb {
 
 // payload of the neighbour points gathered into cell order (one coalesced pass), so that the
 // staging loops of k_sweep_cells read contiguous memory.
-__global__ void k_gather_f32(int64_t n, const int32_t *__restrict__ ids,
+// ids are the .w field of the cell-ordered records (no separate id list on this path)
+__global__ void k_gather_f32(int64_t n, const float4 *__restrict__ sorted,
                              const float *__restrict__ src, float *__restrict__ dst)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __ldg(src + ids[i]);
+    if (i < n) dst[i] = __ldg(src + __float_as_int(__ldg(&sorted[i].w)));
 }
 
-__global__ void k_gather_wcsph(int64_t n, int nd, const int32_t *__restrict__ ids,
+__global__ void k_gather_wcsph(int64_t n, int nd, const float4 *__restrict__ sorted,
                                const float *__restrict__ v, const float *__restrict__ mass,
                                const float *__restrict__ pressure, float4 *__restrict__ vrho,
                                float4 *__restrict__ mp)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int64_t id = ids[i];
+    const int64_t id = __float_as_int(__ldg(&sorted[i].w));
     const int ns = nd + 1;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    a.x = __ldg(v + id * ns);
-    if (nd > 1) a.y = __ldg(v + id * ns + 1);
-    if (nd > 2) a.z = __ldg(v + id * ns + 2);
-    a.w = __ldg(v + id * ns + nd);
+    if (nd == 3 && ((reinterpret_cast<uintptr_t>(v) & 15) == 0)) {
+        a = __ldg(reinterpret_cast<const float4 *>(v) + id);   // (vx, vy, vz, rho) is one 16 B record
+    } else {
+        a.x = __ldg(v + id * ns);
+        if (nd > 1) a.y = __ldg(v + id * ns + 1);
+        if (nd > 2) a.z = __ldg(v + id * ns + 2);
+        a.w = __ldg(v + id * ns + nd);
+    }
     vrho[i] = a;
     const float m = __ldg(mass + id);
     // 1/rho_b and m_b/rho_b once per neighbour instead of once per pair (fast path)
@@ -39,6 +44,9 @@ __global__ void k_gather_wcsph(int64_t n, int nd, const int32_t *__restrict__ id
 // pnb_set_exact_arithmetic: 0 (default) = fast per-pair terms (MUFU + FMA, |error| << 1e-5),
 // 1 = the oracle's IEEE operation sequence (sums bit-identical to the oracle).
 static int g_exact_arithmetic = 0;
+// measurement overrides of the tile sweep (0 = closure default): warps per cell, fp16 pre-filter
+static int g_tune_wpc = 0;
+static int g_tune_half = -1;
 
 static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
                                  int64_t *n_loop)
@@ -96,18 +104,35 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         }
         if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, sizeof(int)));
         PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, sizeof(int), s));
-        size_t pay = (size_t)kFCap * CL::kPayBytes;
-        const size_t red = sizeof(typename CL::State) * kFTX * (CL::kWarpsPerCell - 1) * 32;
-        if (red > pay) pay = red;
-        const size_t smem = sizeof(float4) * kFCapPad + pay;
-        pnb_status st = allow_smem(k_sweep_tiles<ND, PER, CL>, smem);
-        if (st != PNB_OK) return st;
-        {
-            ProfScope ps(PH_SWEEP_CELLS, s);
-            k_sweep_tiles<ND, PER, CL><<<(unsigned)blocks, kFTX * CL::kWarpsPerCell * 32, smem, s>>>(
-                g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);
-            PNB_LAUNCHED();
+        // variant: warps per cell and the fp16 pre-filter (non-periodic grids only); the tuning
+        // overrides (pnb_set_tuning) exist for A/B measurements of the 3-D non-periodic kernels
+        constexpr bool kHalfOk = !PER;
+        int wpc = CL::kWarpsPerCell;
+        bool half = kHalfOk;
+        if (ND == 3 && !PER) {
+            if (g_tune_wpc == 2 || g_tune_wpc == 4) wpc = g_tune_wpc;
+            if (g_tune_half == 0) half = false;
         }
+        pnb_status st = PNB_OK;
+#define PNB_TILES(WPC, HALF)                                                                      \
+    do {                                                                                          \
+        constexpr size_t smem = tiles_smem_bytes<ND, CL, HALF>();                                 \
+        st = allow_smem(k_sweep_tiles<ND, PER, CL, WPC, HALF>, smem);                             \
+        if (st != PNB_OK) return st;                                                              \
+        ProfScope ps(PH_SWEEP_CELLS, s);                                                          \
+        k_sweep_tiles<ND, PER, CL, WPC, HALF><<<(unsigned)blocks, kFTX * WPC * 32, smem, s>>>(    \
+            g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);                      \
+        PNB_LAUNCHED();                                                                           \
+    } while (0)
+        if constexpr (ND == 3 && !PER) {
+            if (wpc == 2 && half) PNB_TILES(2, true);
+            else if (wpc == 2) PNB_TILES(2, false);
+            else if (half) PNB_TILES(4, true);
+            else PNB_TILES(4, false);
+        } else {
+            PNB_TILES(CL::kWarpsPerCell, kHalfOk);
+        }
+#undef PNB_TILES
         {
             ProfScope ps(PH_SWEEP_OVERFLOW, s);
             k_sweep_overflow<ND, PER, CL><<<148 * 2, kFTX * 32, smem_rows, s>>>(
@@ -150,6 +175,11 @@ using namespace pnb;
 
 extern "C" void pnb_set_exact_arithmetic(int on) { g_exact_arithmetic = on != 0; }
 extern "C" int pnb_get_exact_arithmetic(void) { return g_exact_arithmetic; }
+extern "C" void pnb_set_tuning(int warps_per_cell, int half_prefilter)
+{
+    g_tune_wpc = warps_per_cell;
+    g_tune_half = half_prefilter;
+}
 
 extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx,
                                               const float *y, int64_t n, const int32_t *points,
@@ -185,10 +215,12 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
     if (g->template_search || g->n_built == 0) return check_err_word(g, s);
     st = ensure_scratch(g, sizeof(float) * (size_t)g->n_built);
     if (st != PNB_OK) return st;
+    // bit-identical sums need the reference's visiting order with ids ascending in a cell
+    if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
     float *mass_sorted = reinterpret_cast<float *>(g->scratch);
     {
         ProfScope ps(PH_GATHER, s);
-        k_gather_f32<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(g->n_built, g->cell_points,
+        k_gather_f32<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(g->n_built, g->sorted,
                                                                    mass, mass_sorted);
         PNB_LAUNCHED();
     }
@@ -223,11 +255,12 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
     const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
     st = ensure_scratch(g, off_mp + (int64_t)sizeof(float4) * nb);
     if (st != PNB_OK) return st;
+    if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
     float4 *vrho = reinterpret_cast<float4 *>(g->scratch);
     float4 *mp = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
     {
         ProfScope ps(PH_GATHER, s);
-        k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, g->cell_points, v_y,
+        k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, g->sorted, v_y,
                                                                  mass_y, pressure_y, vrho, mp);
         PNB_LAUNCHED();
     }

@@ -1,21 +1,37 @@
 // sweep_tiles.cuh -- the throughput variant of the x === y sweep (default, "fast" arithmetic mode).
 //
-// Why a second kernel: ncu on the row-by-row kernel (profiles/r1_wcsph_sweep_v2_*) showed the
-// deferred interaction loop running with 10 of 32 lanes active.  A lane's hits inside ONE
-// neighbour row depend strongly on where its point sits in the cell (near the +y face -> many
-// hits in the dy = +1 rows, few in dy = -1), while its hits summed over ALL 3^(d-1) rows are
-// nearly the same for every lane.  So this kernel
-//   * stages the candidates of all rows of a tile at once (slot-major: for every x-column of
-//     the tile's (TX+2) columns the cells of all rows are contiguous, so the 3^d neighbour cells
-//     of a tile cell are ONE contiguous range of shared memory),
-//   * splits that range between kWPC (2 or 4) warps per cell in an interleaved fashion (warp p takes the
-//     32-candidate blocks b = p, p + kWPC, ...), so every warp sees a uniform sample of all rows,
-//   * tests up to 8 blocks (256 candidates) into 8 hit masks per lane before draining them,
-//   * adds the kWPC partial accumulators of a point through shared memory at the end.
-// The visiting order is no longer the reference's, which only matters for the bit-identical
-// "exact" mode; that mode (and any tile whose candidates exceed the staging capacity) runs the
-// ordered row-by-row kernel of sweep.cuh instead.
+// What ncu said about the previous version (profiles/r1_wcsph_sweep_v3_ncu_summary.txt): the
+// kernel is issue bound (72 % issue-active, 15.7 G warp instructions for 16.4 M points); 35 % of
+// the instructions are the FP32 distance test (12 per candidate and warp) and 53 % the deferred
+// interaction loop, which ran with 17 of 32 lanes because every warp drained only the hits of
+// its own interleaved quarter of the candidates.  This version removes both:
+//
+//   * TEST in packed half precision (non-periodic grids).  Every staged candidate also gets a
+//     (x, y, z) copy relative to the tile centre in units of the search radius, rounded to
+//     fp16 and packed two candidates per register (candidate k and k + 16 of a 32-block).  One
+//     HADD2 x3 + HMUL2 + HFMA2 x2 + HSET2 + LOP3 tests two candidates: 4 instructions per
+//     candidate instead of 12.  The fp16 test is a conservative PRE-FILTER, never the decision:
+//     all rounding errors together are below 0.007 r^2 (derivation in DESIGN.md 5.2), the
+//     threshold is 1.0098 r^2, so no true neighbour can be missed, and every hit is re-tested
+//     in the drain loop with the reference's exact Float32 operation sequence (the drain
+//     computes pos_diff and d2 exactly anyway) -- the delivered neighbour SET is bit-identical.
+//     About 3 % of the pre-filter hits are rejected there.  Periodic grids keep the exact
+//     Float32 test (the wrap-around needs it).
+//   * BALANCED DRAIN.  The kWPC warps of a cell first publish their hit masks (one word per
+//     lane and 32-block) in shared memory; after a cell-local named barrier every lane knows
+//     the total hit count H of its point and takes the hits of rank [part * H / kWPC,
+//     (part + 1) * H / kWPC): the warps of a cell run the same number of rounds (+-1) and the
+//     per-point totals vary by only a few percent, so ~26 of the 27 occupied lanes stay busy.
+//
+// Layout of the staged candidates: slot-major (for every x-column of the tile's (TX+2) columns
+// the cells of all 3^(d-1) rows are contiguous), every slot padded to a multiple of 32, so
+// the 3^d neighbour cells of a tile cell are ONE run of whole 32-blocks.
+// The visiting order is not the reference's, which only matters for the bit-identical "exact"
+// mode; that mode (and any tile whose candidates exceed the staging capacity) runs the ordered
+// row-by-row kernel of sweep.cuh instead.
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "sweep.cuh"
 
@@ -23,33 +39,100 @@ namespace pnb {
 
 constexpr int kFTX = 4;                    // cells per tile
 constexpr int kFSlots = kFTX + 2;
-constexpr int kFCap = 1920;                // staged candidates per tile (typical: 6*9*27 = 1458)
-constexpr int kFCapPad = kFCap + 32;
+constexpr int kFCap = 1728;                // staged candidates per tile incl. padding (typical 6 * 256)
+constexpr int kFBlocks = kFCap / 32;
+constexpr int kFNBlkMax = 28;              // 32-blocks per cell (3 slots): up to 896 candidates
+constexpr float kHalfSentinel = 64.0f;     // padding candidates: farther than any real one
+constexpr float kHalfThreshold = 1.009765625f;   // 1 + 10 * 2^-10, exactly representable in fp16
+constexpr float kHalfSure = 0.990234375f;        // 1 - 20 * 2^-11: below this the exact test must pass
 
 __host__ __device__ constexpr int rows_of(int nd) { return nd == 3 ? 9 : (nd == 2 ? 3 : 1); }
 
-// kWPC (warps per cell) is a property of the closure: cheap closures run best with 2 (less
-// merge/synchronisation overhead, better balance: measured count 7.8 -> 6.6 ms, n-body
-// 14.5 -> 12.9 ms), the latency-heavy WCSPH interaction needs the occupancy of 4
-// (18.9 ms vs 22.8 ms with 2).
-template <int ND, bool PER, class CL>
-__global__ void __launch_bounds__(kFTX * CL::kWarpsPerCell * 32, 1024 / (kFTX * CL::kWarpsPerCell * 32))
+// dynamic shared memory of k_sweep_tiles
+template <int ND, class CL, bool HALF>
+__host__ __device__ constexpr size_t tiles_smem_bytes()
+{
+    return sizeof(float4) * kFCap                               // exact positions + id
+           + (HALF ? (size_t)kFBlocks * ND * 16 * 4 : 0)        // packed fp16 coordinates
+           + (size_t)kFCap * CL::kPayBytes                      // closure payload planes
+           + ((CL::kCountOnly && !HALF) ? 0 : (size_t)kFTX * kFNBlkMax * 32 * 4);   // hit masks
+}
+
+__device__ __forceinline__ void cell_barrier(int cell, int nthreads)
+{
+    // immediate barrier ids so that ptxas reserves kFTX + 1 barriers, not all 16
+    switch (cell) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+    }
+    static_assert(kFTX == 4, "one named barrier per tile cell");
+}
+
+// One 32-block in packed fp16: bit k of the result <=> candidate k passes the pre-filter
+// (d2 <= thr_hi).  TWO: *sure gets the candidates with d2 <= thr_lo, which are neighbours
+// whatever the rounding did (count-only closures re-test only the band in between).
+template <int ND, bool TWO>
+__device__ __forceinline__ unsigned test_block_half(const uint32_t *__restrict__ hb, __half2 xi,
+                                                    __half2 yi, __half2 zi, __half2 thr_hi,
+                                                    __half2 thr_lo, unsigned *sure)
+{
+    unsigned hits = 0u, in = 0u;
+    const uint4 *hp = reinterpret_cast<const uint4 *>(hb);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint4 X = hp[q];
+        uint4 Y = make_uint4(0u, 0u, 0u, 0u), Z = make_uint4(0u, 0u, 0u, 0u);
+        if (ND > 1) Y = hp[4 + q];
+        if (ND > 2) Z = hp[8 + q];
+        const uint32_t xw[4] = {X.x, X.y, X.z, X.w};
+        const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w};
+        const uint32_t zw[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const int k = q * 4 + w;
+            const __half2 ex = __hsub2(xi, *reinterpret_cast<const __half2 *>(&xw[w]));
+            __half2 d2 = __hmul2(ex, ex);
+            if (ND > 1) {
+                const __half2 ey = __hsub2(yi, *reinterpret_cast<const __half2 *>(&yw[w]));
+                d2 = __hfma2(ey, ey, d2);
+            }
+            if (ND > 2) {
+                const __half2 ez = __hsub2(zi, *reinterpret_cast<const __half2 *>(&zw[w]));
+                d2 = __hfma2(ez, ez, d2);
+            }
+            const unsigned sel = (1u << k) | (1u << (k + 16));
+            hits |= __hle2_mask(d2, thr_hi) & sel;             // 0xffff per passing half
+            if (TWO) in |= __hle2_mask(d2, thr_lo) & sel;
+        }
+    }
+    if (TWO) *sure = in;
+    return hits;
+}
+
+template <int ND, bool PER, class CL, int kWPC, bool HALF>
+__global__ void __launch_bounds__(kFTX * kWPC * 32, 1024 / (kFTX * kWPC * 32))
 k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
               CL cl, int *__restrict__ overflow_tiles, int *__restrict__ overflow_count)
 {
+    static_assert(!(HALF && PER), "the fp16 pre-filter is for non-periodic grids");
     constexpr int NR = rows_of(ND);
     constexpr int NE = kFSlots * NR;          // staged cells per tile
-    constexpr int kWPC = CL::kWarpsPerCell;
     constexpr int kFThreads = kFTX * kWPC * 32;
-    // hit-mask words per lane: one drain per batch covers a whole part (729 / kWPC candidates)
-    constexpr int kFMasks = kWPC == 2 ? 12 : 8;
+    constexpr int kCellThreads_ = kWPC * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_pos = reinterpret_cast<float4 *>(smem_raw);
-    unsigned char *s_pay = smem_raw + sizeof(float4) * kFCapPad;
-    __shared__ uint32_t s_cbeg[NE];
-    __shared__ uint32_t s_cpre[NE + 1];
+    uint32_t *s_half = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * kFCap);
+    unsigned char *s_pay = smem_raw + sizeof(float4) * kFCap + (HALF ? (size_t)kFBlocks * ND * 64 : 0);
+    unsigned *s_mask = reinterpret_cast<unsigned *>(s_pay + (size_t)kFCap * CL::kPayBytes);
+    __shared__ uint32_t s_cbeg[NE];           // global begin of every staged cell
+    __shared__ uint32_t s_ccnt[NE];           // its point count
+    __shared__ uint32_t s_cpre[NE];           // its first staged (padded) index
+    __shared__ uint32_t s_slot0[kFSlots + 1]; // first staged index of every slot (multiples of 32)
+    __shared__ uint32_t s_spop[kFSlots];      // candidates in the slot (without padding)
+    __shared__ int s_cnt[kFTX][kWPC][32];     // hits per lane and part
     __shared__ int s_maxpass[kFTX];
-    __shared__ unsigned s_mask[kFMasks][kFThreads];   // hit masks of the current super-block
 
     const int nx = g.gs[0] - 2;
     const int ny = ND > 1 ? g.gs[1] - 2 : 1;
@@ -71,43 +154,41 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
 
     // ---- table of staged cells, entry e = slot * NR + row (rows in CartesianIndices order) ----
     if (warp == 0) {
-        uint32_t cnt[2] = {0u, 0u};
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int e = (int)threadIdx.x * 2 + h;      // thread t owns entries 2t, 2t+1
-            if (e < NE) {
-                const int slot = e / NR, row = e % NR;
-                int sx = cx0 - 1 + slot;
-                int ry = cy + (ND > 1 ? (row % 3) - 1 : 0);
-                int rz = cz + (ND > 2 ? (row / 3) - 1 : 0);
-                uint32_t b0 = 0;
-                if (sx <= cx1 + 1) {
-                    if (PER) {
-                        sx = floormod_i(sx - 2, g.nc[0]) + 2;
-                        if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
-                        if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
-                    }
-                    const int lin = linear_cell(g, sx, ry, rz);
-                    b0 = cell_start[lin];
-                    cnt[h] = cell_start[lin + 1] - b0;
+        for (int e = lane; e < NE; e += 32) {
+            const int slot = e / NR, row = e % NR;
+            int sx = cx0 - 1 + slot;
+            int ry = cy + (ND > 1 ? (row % 3) - 1 : 0);
+            int rz = cz + (ND > 2 ? (row / 3) - 1 : 0);
+            uint32_t b0 = 0, cnt = 0;
+            if (sx <= cx1 + 1) {
+                if (PER) {
+                    sx = floormod_i(sx - 2, g.nc[0]) + 2;
+                    if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
+                    if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
                 }
-                s_cbeg[e] = b0;
+                const int lin = linear_cell(g, sx, ry, rz);
+                b0 = cell_start[lin];
+                cnt = cell_start[lin + 1] - b0;
             }
+            s_cbeg[e] = b0;
+            s_ccnt[e] = cnt;
         }
-        // exclusive prefix over the (<= 64) entries by the first warp
-        uint32_t pair_sum = cnt[0] + cnt[1];
-        uint32_t incl = pair_sum;
+        __syncwarp();
+        if (lane < kFSlots) {
+            uint32_t run = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            for (int r = 0; r < NR; r++) { s_cpre[lane * NR + r] = run; run += s_ccnt[lane * NR + r]; }
+            s_spop[lane] = run;
         }
-        static_assert(NE <= 64, "cell table is scanned by one warp");
-        const uint32_t excl = incl - pair_sum;
-        const int e0 = lane * 2;
-        if (e0 < NE) s_cpre[e0] = excl;
-        if (e0 + 1 < NE) s_cpre[e0 + 1] = excl + cnt[0];
-        if (e0 + 2 == NE || e0 + 1 == NE) s_cpre[NE] = excl + cnt[0] + (e0 + 1 < NE ? cnt[1] : 0u);
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int sl = 0; sl < kFSlots; sl++) { s_slot0[sl] = run; run += (s_spop[sl] + 31u) & ~31u; }
+            s_slot0[kFSlots] = run;
+        }
+        __syncwarp();
+        for (int e = lane; e < NE; e += 32) s_cpre[e] += s_slot0[e / NR];
     }
     // passes per cell (cells with more than 32 points are swept in several batches)
     const int my_cell = warp / kWPC, part = warp % kWPC;
@@ -120,9 +201,12 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     }
     if (part == 0 && lane == 0) s_maxpass[my_cell] = (int)((c_p1 - c_p0 + 31) / 32);
     __syncthreads();
-    const uint32_t total = s_cpre[NE];
-    if (total > (uint32_t)kFCap) {
-        // too dense for the staging buffer: hand the tile to the ordered kernel
+    // too dense for the staging buffer or the mask table: hand the tile to the ordered kernel
+    bool too_big = s_slot0[kFSlots] > (uint32_t)kFCap;
+#pragma unroll
+    for (int w = 0; w < kFTX; w++)
+        too_big = too_big || (s_slot0[w + 3] - s_slot0[w]) > (uint32_t)(kFNBlkMax * 32);
+    if (too_big) {
         if (threadIdx.x == 0) overflow_tiles[atomicAdd(overflow_count, 1)] = (int)blockIdx.x;
         return;
     }
@@ -130,99 +214,193 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
 #pragma unroll
     for (int w = 0; w < kFTX; w++) n_batches = max(n_batches, s_maxpass[w]);
 
-    // ---- stage every cell of the table: positions + closure payload ---------------------------
+    // ---- stage every cell of the table: exact positions, fp16 copies, closure payload ---------
+    // tile centre (local cell c covers [minc + (c + off - 1) cs, minc + (c + off) cs))
+    float org[3] = {0.f, 0.f, 0.f};
+    float inv_r = 0.f;
+    if (HALF) {
+        org[0] = fmaf((float)(cx0 + g.off[0] + 1), g.cs[0], g.minc[0]);
+        if (ND > 1) org[1] = fmaf((float)(cy + g.off[1]) - 0.5f, g.cs[1], g.minc[1]);
+        if (ND > 2) org[2] = fmaf((float)(cz + g.off[2]) - 0.5f, g.cs[2], g.minc[2]);
+        inv_r = __frcp_rn(g.r);
+    }
+    __half *s_half16 = reinterpret_cast<__half *>(s_half);
     for (int e = warp; e < NE; e += kFTX * kWPC) {
-        const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_cpre[e + 1] - d0;
+        const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
         for (uint32_t k = lane; k < n; k += 32) {
-            s_pos[d0 + k] = sorted[b0 + k];
-            cl.stage(s_pay, (int)(d0 + k), b0 + k, kFCap);
+            const float4 pj = sorted[b0 + k];
+            const uint32_t q = d0 + k;
+            s_pos[q] = pj;
+            if (HALF) {
+                const uint32_t hb = (q >> 5) * (ND * 32) + (q & 15u) * 2u + ((q >> 4) & 1u);
+                s_half16[hb] = __float2half_rn((pj.x - org[0]) * inv_r);
+                if (ND > 1) s_half16[hb + 32] = __float2half_rn((pj.y - org[1]) * inv_r);
+                if (ND > 2) s_half16[hb + 64] = __float2half_rn((pj.z - org[2]) * inv_r);
+            }
+            cl.stage(s_pay, (int)q, b0 + k, kFCap);
+        }
+    }
+    // padding between a slot's last candidate and the next multiple of 32
+    for (int sl = warp; sl < kFSlots; sl += kFTX * kWPC) {
+        const uint32_t q = s_slot0[sl] + s_spop[sl] + (uint32_t)lane;
+        if (q < s_slot0[sl + 1]) {
+            if (HALF) {
+                const uint32_t hb = (q >> 5) * (ND * 32) + (q & 15u) * 2u + ((q >> 4) & 1u);
+                const __half far = __float2half_rn(kHalfSentinel);
+                s_half16[hb] = far;
+                if (ND > 1) s_half16[hb + 32] = far;
+                if (ND > 2) s_half16[hb + 64] = far;
+            }
+            s_pos[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     __syncthreads();
 
-    // candidates of my cell: slots my_cell .. my_cell + 2, all rows
-    const uint32_t R0 = s_cpre[my_cell * NR], R1 = s_cpre[(my_cell + 3) * NR];
-    const int nblk = (int)((R1 - R0 + 31u) / 32u);
+    // candidates of my cell: slots my_cell .. my_cell + 2 = whole blocks B0 .. B0 + nblk - 1
+    const int B0 = (int)(s_slot0[my_cell] >> 5);
+    const int nblk = (int)((s_slot0[my_cell + 3] - s_slot0[my_cell]) >> 5);
+    unsigned *my_mask = s_mask + (size_t)my_cell * kFNBlkMax * 32 + lane;   // word of block b: my_mask[b * 32]
+    const uint32_t q_self0 = s_cpre[(my_cell + 1) * NR + NR / 2];
+    const __half2 thr = __float2half2_rn(kHalfThreshold);
+    const __half2 thr_lo = __float2half2_rn(kHalfSure);
 
     for (int batch = 0; batch < n_batches; batch++) {
         const uint32_t i_sorted = c_p0 + (uint32_t)batch * 32u + (uint32_t)lane;
         const bool active = i_sorted < c_p1;
         float xi = 0.f, yi = 0.f, zi = 0.f;
         int i_id = 0;
+        __half2 hx = __float2half2_rn(0.f), hy = hx, hz = hx;
         typename CL::State st;
         if (active) {
-            const float4 pi = sorted[i_sorted];
+            const uint32_t q = q_self0 + (uint32_t)batch * 32u + (uint32_t)lane;
+            const float4 pi = s_pos[q];
             xi = pi.x; yi = pi.y; zi = pi.z;
             i_id = __float_as_int(pi.w);
+            if (HALF) {
+                const uint32_t hb = (q >> 5) * (ND * 32) + (q & 15u) * 2u + ((q >> 4) & 1u);
+                hx = __half2half2(s_half16[hb]);
+                if (ND > 1) hy = __half2half2(s_half16[hb + 32]);
+                if (ND > 2) hz = __half2half2(s_half16[hb + 64]);
+            }
         }
         cl.init(st, active, (int)i_sorted, i_id);
-        if (__any_sync(0xffffffffu, active)) {
-            for (int b0 = part; b0 < nblk; b0 += kWPC * kFMasks) {
-                // ---- test: up to kFMasks blocks of 32 candidates, hit masks parked in shared
-                //      memory (each thread only ever touches its own words: no barrier needed)
-                int rem = 0;
-#pragma unroll 1
-                for (int u = 0; u < kFMasks; u++) {
-                    const int bb = b0 + u * kWPC;
-                    unsigned hh = 0u;
-                    if (bb < nblk) {   // warp-uniform
-                        const uint32_t blk = R0 + 32u * (uint32_t)bb;
-                        hh = test_block<ND, PER>(pp, s_pos + blk, xi, yi, zi);
-                        const uint32_t nv = R1 - blk;
-                        if (nv < 32u) hh &= (1u << nv) - 1u;
-                        if (!active) hh = 0u;
-                    }
-                    s_mask[u][threadIdx.x] = hh;
-                    rem += __popc(hh);
-                }
-                if (CL::kCountOnly) {
-                    cl.count(st, rem);
-                } else {
-                    // ---- drain: every lane walks its own masks with a cursor, one hit per round
-                    int u = -1;
-                    unsigned mm = 0u;
-                    while (__any_sync(0xffffffffu, rem > 0)) {
-                        if (rem > 0) {
-                            while (mm == 0u) mm = s_mask[++u][threadIdx.x];
-                            const int k = __ffs(mm) - 1;
-                            mm &= mm - 1u;
-                            rem--;
-                            const int slot = (int)R0 + 32 * (b0 + u * kWPC) + k;
-                            const float4 pj = s_pos[slot];
-                            float px = __fsub_rn(xi, pj.x);
-                            float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
-                            float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
-                            float d2 = dist2<ND>(px, py, pz);
-                            d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
-                            cl.template pair<ND>(st, px, py, pz, d2, __float_as_int(pj.w), s_pay,
-                                                 slot, kFCap);
-                        }
-                    }
+
+        // ---- phase 1: test the blocks b = part, part + kWPC, ...; masks to shared memory -----
+        int cnt = 0, n_maybe = 0;
+        for (int bb = part; bb < nblk; bb += kWPC) {
+            unsigned hh;
+            if (HALF && CL::kCountOnly) {
+                // count only: certain neighbours are counted here, the band between the two
+                // thresholds is parked and decided by the exact test below
+                unsigned sure;
+                hh = test_block_half<ND, true>(s_half + (size_t)(B0 + bb) * (ND * 16), hx, hy, hz,
+                                               thr, thr_lo, &sure);
+                if (!active) { hh = 0u; sure = 0u; }
+                my_mask[bb * 32] = hh & ~sure;
+                n_maybe += __popc(hh & ~sure);
+                hh = sure;
+            } else if (HALF) {
+                hh = test_block_half<ND, false>(s_half + (size_t)(B0 + bb) * (ND * 16), hx, hy, hz,
+                                                thr, thr_lo, nullptr);
+            } else {
+                hh = test_block<ND, PER>(pp, s_pos + 32 * (B0 + bb), xi, yi, zi);
+                // padding slots are not candidates
+                const int q0 = 32 * (B0 + bb);
+                int sl = my_cell;
+                if (q0 >= (int)s_slot0[my_cell + 1]) sl = my_cell + 1;
+                if (q0 >= (int)s_slot0[my_cell + 2]) sl = my_cell + 2;
+                const int nv = (int)(s_slot0[sl] + s_spop[sl]) - q0;
+                if (nv < 32) hh &= (1u << max(nv, 0)) - 1u;
+            }
+            if (!active) hh = 0u;
+            if (!CL::kCountOnly) my_mask[bb * 32] = hh;
+            cnt += __popc(hh);
+        }
+        if (HALF && CL::kCountOnly) {
+            // exact test (the reference's operation sequence) of the undecided candidates of my
+            // own blocks
+            const int rounds = __reduce_max_sync(0xffffffffu, n_maybe);
+            int bb = part - kWPC;
+            unsigned mm = 0u;
+            for (int t = 0; t < rounds; t++) {
+                if (t < n_maybe) {
+                    while (mm == 0u) { bb += kWPC; mm = my_mask[bb * 32]; }
+                    const int k = __ffs(mm) - 1;
+                    mm &= mm - 1u;
+                    const float4 pj = s_pos[32 * (B0 + bb) + k];
+                    const float px = __fsub_rn(xi, pj.x);
+                    const float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
+                    const float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
+                    cnt += (dist2<ND>(px, py, pz) <= pp.r2) ? 1 : 0;
                 }
             }
         }
-        // ---- add the kWPC partial states of every point: parts 1.. publish, part 0 merges ------
-        // (the payload region is free once every warp has finished its drain)
-        __syncthreads();
-        typename CL::State *s_red = reinterpret_cast<typename CL::State *>(s_pay);
-        if (part > 0) s_red[((my_cell * (kWPC - 1)) + (part - 1)) * 32 + lane] = st;
-        __syncthreads();
-        if (part == 0 && active) {
+        if (CL::kCountOnly) {
+            // the parts' counts are added through s_cnt
+            s_cnt[my_cell][part][lane] = cnt;
+            cell_barrier(my_cell, kCellThreads_);
+            if (part == 0) {
+                int tot = 0;
 #pragma unroll
-            for (int q = 0; q < kWPC - 1; q++)
-                cl.merge(st, s_red[((my_cell * (kWPC - 1)) + q) * 32 + lane]);
-            cl.finish(st, (int)i_sorted, i_id);
-        }
-        if (batch + 1 < n_batches) {
-            // the payload was overwritten by the partial states: stage it again for the next batch
-            __syncthreads();
-            for (int e = warp; e < NE; e += kFTX * kWPC) {
-                const uint32_t bb0 = s_cbeg[e], d0 = s_cpre[e], n = s_cpre[e + 1] - d0;
-                for (uint32_t k = lane; k < n; k += 32) cl.stage(s_pay, (int)(d0 + k), bb0 + k, kFCap);
+                for (int p = 0; p < kWPC; p++) tot += s_cnt[my_cell][p][lane];
+                cl.count(st, tot);
             }
-            __syncthreads();
+            if (batch + 1 < n_batches) cell_barrier(my_cell, kCellThreads_);
+        } else {
+            s_cnt[my_cell][part][lane] = cnt;
+            cell_barrier(my_cell, kCellThreads_);
+
+            // ---- phase 2: my share of the point's hits: ranks [part * Q, part * Q + n_mine) ----
+            int H = 0;
+#pragma unroll
+            for (int p = 0; p < kWPC; p++) H += s_cnt[my_cell][p][lane];
+            const int Q = (H + kWPC - 1) / kWPC;
+            int skip = part * Q;
+            const int n_mine = max(0, min(Q, H - skip));
+            int bb = 0;
+            unsigned mm = 0u;
+            if (n_mine > 0) {
+                mm = my_mask[0];
+                int c = __popc(mm);
+                while (skip >= c) { skip -= c; bb++; mm = my_mask[bb * 32]; c = __popc(mm); }
+                for (; skip > 0; skip--) mm &= mm - 1u;
+            }
+            const int rounds = __reduce_max_sync(0xffffffffu, n_mine);
+
+            // ---- phase 3: drain, one hit per lane and round ------------------------------------
+            for (int t = 0; t < rounds; t++) {
+                if (t < n_mine) {
+                    while (mm == 0u) { bb++; mm = my_mask[bb * 32]; }
+                    const int k = __ffs(mm) - 1;
+                    mm &= mm - 1u;
+                    const int slot = 32 * (B0 + bb) + k;
+                    const float4 pj = s_pos[slot];
+                    float px = __fsub_rn(xi, pj.x);
+                    float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
+                    float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
+                    float d2 = dist2<ND>(px, py, pz);
+                    d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
+                    // the decision: the reference's exact test (the fp16 pass only pre-selects)
+                    if (!HALF || d2 <= pp.r2)
+                        cl.template pair<ND>(st, px, py, pz, d2, __float_as_int(pj.w), s_pay, slot, kFCap);
+                }
+            }
+            // ---- phase 4: add the kWPC partial accumulators of every point ---------------------
+            // (the cell's mask words are free once all its warps have finished their drain)
+            cell_barrier(my_cell, kCellThreads_);
+            float *s_red = reinterpret_cast<float *>(s_mask + (size_t)my_cell * kFNBlkMax * 32);
+            static_assert((kWPC - 1) * CL::kAccWords <= kFNBlkMax, "partials fit the mask words");
+            if (part > 0) cl.save_acc(st, s_red + ((part - 1) * CL::kAccWords) * 32 + lane);
+            cell_barrier(my_cell, kCellThreads_);
+            if (part == 0) {
+#pragma unroll
+                for (int p = 0; p < kWPC - 1; p++) cl.add_acc(st, s_red + (p * CL::kAccWords) * 32 + lane);
+            }
+            if (batch + 1 < n_batches) cell_barrier(my_cell, kCellThreads_);
         }
+        if (part == 0 && active) cl.finish(st, (int)i_sorted, i_id);
     }
+    (void)kFThreads;
 }
 
 // Tiles that did not fit the staging buffer of k_sweep_tiles: ordered row-by-row sweep with the
