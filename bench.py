@@ -309,35 +309,87 @@ def gpu_arm(args):
     value = total_pairs / (ms_total * 1e-3)
 
     # ---- e2e: same step through the public API with HOST (pinned) buffers ---------------------
+    # Every step copies its inputs (coordinates, state, pressure) from pinned host memory and
+    # copies its result (dv) back.  Two measurements:
+    #   serial    : H2D -> update! -> interact! -> D2H on one stream (latency of one step)
+    #   pipelined : three streams, double-buffered device arrays: the H2D of step s+1 and the
+    #               D2H of step s-1 overlap the kernels of step s (throughput; this is `value`)
     hA, hB = A.cpu().pin_memory(), B.cpu().pin_memory()
     hv, hp = v.cpu().pin_memory(), pressure.cpu().pin_memory()
-    hdv = torch.empty((N, 4), dtype=torch.float32).pin_memory()
-    dy = torch.empty_like(A)
+    hdv = [torch.empty((N, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    dy = [torch.empty_like(A) for _ in range(2)]
+    dvv = [v, torch.empty_like(v)]
+    dpp = [pressure, torch.empty_like(pressure)]
+    dvo = [dv, torch.empty_like(dv)]
+    cls = [closure, pn.WCSPHInteract(dvo[1], dvv[1], dvv[1], mass, mass, dpp[1], dpp[1],
+                                     smoothing_length=h, sound_speed=T(10.0), alpha=T(0.02),
+                                     beta=T(0.0), delta=T(0.1))]
     hcoords = [hA, hB]
 
-    def e2e_step(s):
-        dy.copy_(hcoords[(s + 1) % 2], non_blocking=True)
-        v.copy_(hv, non_blocking=True)
-        pressure.copy_(hp, non_blocking=True)
-        pn.update_(nhs, dy, dy, points_moving=(True, True))
-        pn.foreach_point_neighbor(closure, dy, dy, nhs)
-        hdv.copy_(dv, non_blocking=True)
+    def e2e_serial_step(s):
+        dy[0].copy_(hcoords[(s + 1) % 2], non_blocking=True)
+        dvv[0].copy_(hv, non_blocking=True)
+        dpp[0].copy_(hp, non_blocking=True)
+        pn.update_(nhs, dy[0], dy[0], points_moving=(True, True))
+        pn.foreach_point_neighbor(cls[0], dy[0], dy[0], nhs)
+        hdv[0].copy_(dvo[0], non_blocking=True)
 
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 10))
     for s in range(2):
-        e2e_step(s)
+        e2e_serial_step(s)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_pairs = 0
     for s in range(e2e_steps):
-        e2e_step(s)
-        e2e_pairs += pairs[(s + 1) % 2]
+        e2e_serial_step(s)
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_serial_ms = e0.elapsed_time(e1) / e2e_steps
+
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_h2d(s):
+        bb = s % 2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_cmp[bb])           # the kernels of step s-2 are done with these buffers
+            dy[bb].copy_(hcoords[(s + 1) % 2], non_blocking=True)
+            dvv[bb].copy_(hv, non_blocking=True)
+            dpp[bb].copy_(hp, non_blocking=True)
+            ev_in[bb].record(s_in)
+
+    def run_pipelined(n_steps):
+        pairs_done = 0
+        issue_h2d(0)
+        for s in range(n_steps):
+            bb = s % 2
+            if s + 1 < n_steps:
+                issue_h2d(s + 1)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[bb])
+                s_cmp.wait_event(ev_out[bb])      # dv buffer of step s-2 has reached the host
+                pn.update_(nhs, dy[bb], dy[bb], points_moving=(True, True))
+                pn.foreach_point_neighbor(cls[bb], dy[bb], dy[bb], nhs)
+                ev_cmp[bb].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[bb])
+                hdv[bb].copy_(dvo[bb], non_blocking=True)
+                ev_out[bb].record(s_out)
+            pairs_done += pairs[(s + 1) % 2]
+        return pairs_done
+
+    torch.cuda.synchronize()
+    run_pipelined(2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_pairs = run_pipelined(e2e_steps)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)      # wall clock across the three streams
     h2d = int(hA.numel() * 4 + hv.numel() * 4 + hp.numel() * 4)
-    d2h = int(hdv.numel() * 4)
+    d2h = int(hdv[0].numel() * 4)
 
     # ---- roofline -----------------------------------------------------------------------------
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
@@ -371,7 +423,11 @@ def gpu_arm(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "e2e": {"value": e2e_pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                "mode": "pipelined: 3 streams, double-buffered device arrays, every step copies "
+                        "its inputs from pinned host memory and its dv back (wall clock)",
+                "serial_ms_per_step": e2e_serial_ms,
+                "serial_value": float(np.mean(pairs)) / (e2e_serial_ms * 1e-3)},
         "roofline": {"bound": "hbm", "kernel": "k_sweep_tiles<3,false,WcsphClT<false>,4,true>", "achieved": ach,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                      "peak_source": peak_src, "launch_ms": sweep_avg,

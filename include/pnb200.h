@@ -138,6 +138,10 @@ int pnb_get_exact_arithmetic(void);
  * closure's default) and the fp16 pre-filter of the distance test (0 = off: exact Float32 test,
  * -1 = default on).  Results are identical for every setting; only the speed changes. */
 void pnb_set_tuning(int warps_per_cell, int half_prefilter);
+/* Measurement variants of the counting-sort kernels (bit 0: histogram reads global memory
+ * directly, bit 1: scatter uses the strided lane mapping, bit 2: histogram uses it too).
+ * Results are identical for every setting. */
+void pnb_set_build_tuning(int variant);
 
 /* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */
 pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,

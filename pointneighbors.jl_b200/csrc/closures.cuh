@@ -41,6 +41,9 @@ struct CountCl {
     __device__ __forceinline__ void pair(State &, float, float, float, float, int,
                                          const unsigned char *, int, int) const {}
     template <int ND>
+    __device__ __forceinline__ void pair_s(State &, float, float, float, float, int, uint32_t, int,
+                                           int) const {}
+    template <int ND>
     __device__ __forceinline__ void pair_global(State &, float, float, float, float, int,
                                                 uint32_t) const {}
     __device__ __forceinline__ void finish(State &s, int, int i_id) const { out[i_id] = (int64_t)s.cnt; }
@@ -122,6 +125,15 @@ struct NBodyClT {
     {
         term<ND>(s, px, py, pz, d2, reinterpret_cast<const float *>(pay)[slot]);
     }
+    // payload addressed by its 32-bit shared-window address (k_sweep_tiles)
+    template <int ND>
+    __device__ __forceinline__ void pair_s(State &s, float px, float py, float pz, float d2, int,
+                                           uint32_t pay_sa, int slot, int) const
+    {
+        float m;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(pay_sa + 4u * (uint32_t)slot));
+        term<ND>(s, px, py, pz, d2, m);
+    }
     template <int ND>
     __device__ __forceinline__ void pair_global(State &s, float px, float py, float pz, float d2,
                                                 int, uint32_t gi) const
@@ -154,7 +166,7 @@ struct WcsphClT {
     pnb_wcsph_params prm;
     float *dv;
     int nd;
-    struct State { float v[3]; float rho, p, inv_rho; float acc[4]; };
+    struct State { float v[3]; float rho, p, inv_rho, neg_inv_rho; float acc[4]; };
     static constexpr int kAccWords = 4;
     __device__ __forceinline__ void save_acc(const State &s, float *p) const
     {
@@ -168,7 +180,7 @@ struct WcsphClT {
     __device__ __forceinline__ void init(State &s, bool active, int i_sorted, int i_id) const
     {
         s.acc[0] = s.acc[1] = s.acc[2] = s.acc[3] = 0.f;
-        s.v[0] = s.v[1] = s.v[2] = 0.f; s.rho = 1.f; s.p = 0.f; s.inv_rho = 1.f;
+        s.v[0] = s.v[1] = s.v[2] = 0.f; s.rho = 1.f; s.p = 0.f; s.inv_rho = 1.f; s.neg_inv_rho = -1.f;
         if (!active) return;
         if (i_sorted >= 0) {
             const float4 a = vrho_sorted[i_sorted];
@@ -182,6 +194,7 @@ struct WcsphClT {
             s.p = p_x[i_id];
             s.inv_rho = __fdiv_rn(1.f, s.rho);
         }
+        s.neg_inv_rho = -s.inv_rho;
     }
     __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi, int cap) const
     {
@@ -201,15 +214,15 @@ struct WcsphClT {
         // pairs closer than sqrt(eps) (the self pair) contribute exactly zero in the reference
         if (d2 < PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32) return;
         const float h = prm.smoothing_length;
+        // grad W / d = (sigma/h) w(q)/d with w = -5 q (1 - q/2)^3 and q = d/h: the d cancels,
+        //   sg = (-5 sigma / h^2) t^3,  t = 1 - d / (2 h)
         const float inv_d = fast_rsqrt(d2);
         const float d = d2 * inv_d;
-        const float q = d * prm_inv_h;
-        const float t = fmaf(-0.5f, q, 1.f);
-        const float w = (-5.f * q) * (t * t * t);       // q <= 2 inside the search radius
-        const float sg = (prm_kh * w) * inv_d;
+        const float t = fmaxf(fmaf(prm_nhalf_inv_h, d, 1.f), 0.f);   // w = 0 beyond the support q >= 2
+        const float sg = (prm_k5 * t) * (t * t);
         const float rho_a = s.rho, rho_b = vb.w;
-        const float m_b = mpb.x, p_b = mpb.y, inv_rho_b = mpb.z, vol_b = mpb.w;
-        float coef = (-m_b * (s.p + p_b)) * (s.inv_rho * inv_rho_b);
+        const float m_b = mpb.x, p_b = mpb.y, vol_b = mpb.w;
+        float coef = (vol_b * (s.p + p_b)) * s.neg_inv_rho;       // -m_b (p_a + p_b) / (rho_a rho_b)
         const float vdx = s.v[0] - vb.x, vdy = s.v[1] - vb.y, vdz = s.v[2] - vb.z;
         float vr = vdx * px;
         if (ND > 1) vr = fmaf(vdy, py, vr);
@@ -301,6 +314,18 @@ struct WcsphClT {
         term<ND>(s, px, py, pz, d2, vb, mpb);
     }
     template <int ND>
+    __device__ __forceinline__ void pair_s(State &s, float px, float py, float pz, float d2, int,
+                                           uint32_t pay_sa, int slot, int cap) const
+    {
+        float4 vb, mpb;
+        const uint32_t a = pay_sa + 16u * (uint32_t)slot;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(vb.x), "=f"(vb.y), "=f"(vb.z), "=f"(vb.w) : "r"(a));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(mpb.x), "=f"(mpb.y), "=f"(mpb.z), "=f"(mpb.w) : "r"(a + 16u * (uint32_t)cap));
+        term<ND>(s, px, py, pz, d2, vb, mpb);
+    }
+    template <int ND>
     __device__ __forceinline__ void pair_global(State &s, float px, float py, float pz, float d2,
                                                 int, uint32_t gi) const
     {
@@ -313,8 +338,8 @@ struct WcsphClT {
         dv[(int64_t)i_id * ns + nd] = s.acc[3];
     }
     // derived constants of the fast path, filled by the host
-    float prm_inv_h;   // 1 / h
-    float prm_kh;      // kernel_norm / h
+    float prm_nhalf_inv_h;   // -1 / (2 h)
+    float prm_k5;            // -5 kernel_norm / h^2
     float prm_ac;      // alpha * c
     float prm_dhc2;    // 2 * delta * h * c
 };

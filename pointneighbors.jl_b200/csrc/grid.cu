@@ -372,6 +372,7 @@ extern "C" int64_t pnb_grid_n_points(const pnb_grid *g) { return g ? g->n_built 
 // ---------------------------------------------------------------------------------------------
 namespace pnb {
 
+int g_tune_build = 3;   // measurement variants of the build kernels (pnb_set_build_tuning)
 constexpr int kBuildThreads = 256;
 constexpr int kBuildPPT = 4;                                // points per thread
 constexpr int kBuildTile = kBuildThreads * kBuildPPT;       // points per block
@@ -469,12 +470,74 @@ template <int ND, bool PER>
 __global__ void __launch_bounds__(kBuildThreads)
 k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
             const int32_t *__restrict__ idx, int base, uint32_t *__restrict__ cell_count,
-            int *__restrict__ err)
+            int *__restrict__ err, int variant)
 {
     __shared__ __align__(16) float s_xyz[kBuildTile * ND];
     const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
-    if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
     bool bad = false;
+    if ((variant & 1) && idx == nullptr && block0 + kBuildTile <= n_idx &&
+        ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+        // full tile, no staging: every thread reads its kBuildPPT consecutive points straight
+        // from global memory (ND 16-byte loads), no barrier
+        float v[kBuildPPT * ND];
+        const float4 *gp = reinterpret_cast<const float4 *>(y + block0 * ND) + (int)threadIdx.x * ND;
+#pragma unroll
+        for (int q = 0; q < ND; q++) {
+            const float4 a = __ldg(gp + q);
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
+        int lin[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            lin[j] = point_cell_fast<ND, PER>(g, bp, &v[j * ND]);
+            bad = bad || lin[j] < 0;
+        }
+        int cur = lin[0], n = 1;
+#pragma unroll
+        for (int j = 1; j < kBuildPPT; j++) {
+            if (lin[j] == cur) n++;
+            else {
+                if (cur >= 0) atomicAdd(cell_count + cur, (unsigned)n);
+                cur = lin[j];
+                n = 1;
+            }
+        }
+        if (cur >= 0) atomicAdd(cell_count + cur, (unsigned)n);
+        if (bad) atomicOr(err, 1);
+        return;
+    }
+    if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
+    if (!(variant & 4) && idx == nullptr && block0 + kBuildTile <= n_idx) {
+        // full tile: kBuildPPT CONSECUTIVE points per thread (ND conflict-free LDS.128), runs of
+        // equal cells are merged inside the thread: no shuffles, no votes, one RED per run
+        float v[kBuildPPT * ND];
+        const float4 *sp = reinterpret_cast<const float4 *>(s_xyz) + (int)threadIdx.x * ND;
+#pragma unroll
+        for (int q = 0; q < ND; q++) {
+            const float4 a = sp[q];
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
+        int lin[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            lin[j] = point_cell_fast<ND, PER>(g, bp, &v[j * ND]);
+            bad = bad || lin[j] < 0;
+        }
+        int cur = lin[0], n = 1;
+#pragma unroll
+        for (int j = 1; j < kBuildPPT; j++) {
+            if (lin[j] == cur) n++;
+            else {
+                if (cur >= 0) atomicAdd(cell_count + cur, (unsigned)n);
+                cur = lin[j];
+                n = 1;
+            }
+        }
+        if (cur >= 0) atomicAdd(cell_count + cur, (unsigned)n);
+        if (bad) atomicOr(err, 1);
+        return;
+    }
+    // generic path (last tile, `eachindex_y` subsets): strided points, runs merged across lanes
 #pragma unroll
     for (int j = 0; j < kBuildPPT; j++) {
         const int loc = j * kBuildThreads + (int)threadIdx.x;
@@ -508,11 +571,47 @@ template <int ND, bool PER>
 __global__ void __launch_bounds__(kBuildThreads)
 k_scatter_points(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
                  const int32_t *__restrict__ idx, int base, uint32_t *__restrict__ cursor,
-                 float4 *__restrict__ sorted)
+                 float4 *__restrict__ sorted, int variant)
 {
     __shared__ __align__(16) float s_xyz[kBuildTile * ND];
     const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
     if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
+    if (!(variant & 2) && idx == nullptr && block0 + kBuildTile <= n_idx) {
+        // full tile: consecutive points per thread, thread-local runs (see k_cell_hist); the
+        // atomics of all runs are issued before any record is stored
+        float v[kBuildPPT * ND];
+        const float4 *sp = reinterpret_cast<const float4 *>(s_xyz) + (int)threadIdx.x * ND;
+#pragma unroll
+        for (int q = 0; q < ND; q++) {
+            const float4 a = sp[q];
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
+        int lin[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) lin[j] = point_cell_fast<ND, PER>(g, bp, &v[j * ND]);
+        // run lengths (a run = consecutive points of one cell), heads take the cursor once
+        int rl[kBuildPPT];
+        rl[kBuildPPT - 1] = 1;
+#pragma unroll
+        for (int j = kBuildPPT - 2; j >= 0; j--) rl[j] = (lin[j] == lin[j + 1]) ? rl[j + 1] + 1 : 1;
+        unsigned slot[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const bool is_head = (j == 0) || (lin[j] != lin[j - 1]);
+            slot[j] = (is_head && lin[j] >= 0) ? atomicAdd(cursor + lin[j], (unsigned)rl[j]) : 0u;
+        }
+#pragma unroll
+        for (int j = 1; j < kBuildPPT; j++)
+            if (lin[j] == lin[j - 1]) slot[j] = slot[j - 1] + 1u;
+        const int32_t id0 = (int32_t)(block0 + (int64_t)threadIdx.x * kBuildPPT);
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            if (lin[j] >= 0)
+                sorted[slot[j]] = make_float4(v[j * ND], ND > 1 ? v[j * ND + 1] : 0.f,
+                                              ND > 2 ? v[j * ND + 2] : 0.f, __int_as_float(id0 + j));
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < kBuildPPT; j++) {
         const int loc = j * kBuildThreads + (int)threadIdx.x;
@@ -810,7 +909,7 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
     if (n_idx > 0) {
         ProfScope ps(PH_BUILD_CELL_COUNT, s);
         k_cell_hist<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, idx, base,
-                                                              g->cell_count, g->d_err);
+                                                              g->cell_count, g->d_err, g_tune_build);
         PNB_LAUNCHED();
     }
     // exclusive prefix E[c] -> cell_start[c + 1]; cell_start[0] stays 0 (set at creation)
@@ -819,7 +918,7 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
     if (n_idx > 0) {
         ProfScope ps(PH_BUILD_SCATTER, s);
         k_scatter_points<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, idx, base,
-                                                                   g->cell_start + 1, g->sorted);
+                                                                   g->cell_start + 1, g->sorted, g_tune_build);
         PNB_LAUNCHED();
     }
     (void)n;
@@ -827,6 +926,8 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
 }
 
 }  // namespace pnb
+
+extern "C" void pnb_set_build_tuning(int variant) { pnb::g_tune_build = variant; }
 
 extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                                          const int32_t *eachindex_y, int64_t n_idx, int index_base,

@@ -266,7 +266,7 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
     }
     const bool fastp = is_fast_path(g, x, nx, points);
     const float h = params->smoothing_length;
-    const float inv_h = 1.0f / h, kh = params->kernel_norm / h;
+    const float inv_h = -0.5f / h, kh = -5.0f * params->kernel_norm / (h * h);
     const float ac = params->alpha * params->sound_speed;
     const float dhc2 = 2.0f * params->delta * h * params->sound_speed;
     if (g_exact_arithmetic)

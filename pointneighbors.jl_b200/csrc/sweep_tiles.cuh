@@ -58,6 +58,20 @@ __host__ __device__ constexpr size_t tiles_smem_bytes()
            + ((CL::kCountOnly && !HALF) ? 0 : (size_t)kFTX * kFNBlkMax * 32 * 4);   // hit masks
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t sa)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t sa)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
+    return v;
+}
+
 __device__ __forceinline__ void cell_barrier(int cell, int nthreads)
 {
     // immediate barrier ids so that ptxas reserves kFTX + 1 barriers, not all 16
@@ -260,6 +274,13 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     const int B0 = (int)(s_slot0[my_cell] >> 5);
     const int nblk = (int)((s_slot0[my_cell + 3] - s_slot0[my_cell]) >> 5);
     unsigned *my_mask = s_mask + (size_t)my_cell * kFNBlkMax * 32 + lane;   // word of block b: my_mask[b * 32]
+    // 32-bit shared-window addresses, computed once (the compiler otherwise rebuilds the window
+    // base of the dynamic shared memory in every round of the drain loop)
+    uint32_t pos_sa = (uint32_t)__cvta_generic_to_shared(s_pos);
+    asm volatile("mov.u32 %0, %0;" : "+r"(pos_sa));    // opaque: keep it in a register, do not rematerialise
+    const uint32_t pay_sa = pos_sa + (uint32_t)(sizeof(float4) * kFCap + (HALF ? (size_t)kFBlocks * ND * 64 : 0));
+    const int nb4 = (nblk + kWPC - 1) / kWPC;                // blocks per share
+    const int blk_lo = min(part * nb4, nblk), blk_hi = min(blk_lo + nb4, nblk);
     const uint32_t q_self0 = s_cpre[(my_cell + 1) * NR + NR / 2];
     const __half2 thr = __float2half2_rn(kHalfThreshold);
     const __half2 thr_lo = __float2half2_rn(kHalfSure);
@@ -285,9 +306,9 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
         }
         cl.init(st, active, (int)i_sorted, i_id);
 
-        // ---- phase 1: test the blocks b = part, part + kWPC, ...; masks to shared memory -----
+        // ---- phase 1: test my contiguous share of the cell's blocks; masks to shared memory --
         int cnt = 0, n_maybe = 0;
-        for (int bb = part; bb < nblk; bb += kWPC) {
+        for (int bb = blk_lo; bb < blk_hi; bb++) {
             unsigned hh;
             if (HALF && CL::kCountOnly) {
                 // count only: certain neighbours are counted here, the band between the two
@@ -320,11 +341,11 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
             // exact test (the reference's operation sequence) of the undecided candidates of my
             // own blocks
             const int rounds = __reduce_max_sync(0xffffffffu, n_maybe);
-            int bb = part - kWPC;
+            int bb = blk_lo - 1;
             unsigned mm = 0u;
             for (int t = 0; t < rounds; t++) {
                 if (t < n_maybe) {
-                    while (mm == 0u) { bb += kWPC; mm = my_mask[bb * 32]; }
+                    while (mm == 0u) { bb++; mm = my_mask[bb * 32]; }
                     const int k = __ffs(mm) - 1;
                     mm &= mm - 1u;
                     const float4 pj = s_pos[32 * (B0 + bb) + k];
@@ -351,16 +372,22 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
             cell_barrier(my_cell, kCellThreads_);
 
             // ---- phase 2: my share of the point's hits: ranks [part * Q, part * Q + n_mine) ----
+            int pc[kWPC];
             int H = 0;
 #pragma unroll
-            for (int p = 0; p < kWPC; p++) H += s_cnt[my_cell][p][lane];
+            for (int p = 0; p < kWPC; p++) { pc[p] = s_cnt[my_cell][p][lane]; H += pc[p]; }
             const int Q = (H + kWPC - 1) / kWPC;
             int skip = part * Q;
             const int n_mine = max(0, min(Q, H - skip));
             int bb = 0;
             unsigned mm = 0u;
             if (n_mine > 0) {
-                mm = my_mask[0];
+                // the share that holds my first hit (hits of share p live in blocks p * nb4 ...),
+                // then the word inside it
+#pragma unroll
+                for (int p = 0; p < kWPC - 1; p++)
+                    if (bb == p * nb4 && skip >= pc[p]) { skip -= pc[p]; bb = (p + 1) * nb4; }
+                mm = my_mask[bb * 32];
                 int c = __popc(mm);
                 while (skip >= c) { skip -= c; bb++; mm = my_mask[bb * 32]; c = __popc(mm); }
                 for (; skip > 0; skip--) mm &= mm - 1u;
@@ -374,7 +401,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                     const int k = __ffs(mm) - 1;
                     mm &= mm - 1u;
                     const int slot = 32 * (B0 + bb) + k;
-                    const float4 pj = s_pos[slot];
+                    const float4 pj = lds128(pos_sa + 16u * (uint32_t)slot);
                     float px = __fsub_rn(xi, pj.x);
                     float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
                     float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
@@ -382,7 +409,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                     d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
                     // the decision: the reference's exact test (the fp16 pass only pre-selects)
                     if (!HALF || d2 <= pp.r2)
-                        cl.template pair<ND>(st, px, py, pz, d2, __float_as_int(pj.w), s_pay, slot, kFCap);
+                        cl.template pair_s<ND>(st, px, py, pz, d2, __float_as_int(pj.w), pay_sa, slot, kFCap);
                 }
             }
             // ---- phase 4: add the kWPC partial accumulators of every point ---------------------

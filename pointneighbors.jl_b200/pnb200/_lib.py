@@ -83,6 +83,7 @@ SIGNATURES = {
     "pnb_set_exact_arithmetic": (None, [C.c_int]),
     "pnb_get_exact_arithmetic": (C.c_int, []),
     "pnb_set_tuning": (None, [C.c_int, C.c_int]),
+    "pnb_set_build_tuning": (None, [C.c_int]),
     "pnb_profile_enable": (None, [C.c_int]),
     "pnb_profile_reset": (None, []),
     "pnb_profile_phases": (C.c_int, []),
