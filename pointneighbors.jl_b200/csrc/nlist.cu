@@ -10,6 +10,7 @@
 
 #include "closures.cuh"
 #include "sweep.cuh"
+#include "sweep_launch.cuh"
 
 struct pnb_nlist {
     int64_t nx;        // number of lists (points of x)
@@ -20,17 +21,60 @@ struct pnb_nlist {
     int ndims;
     int *d_err;
     int *h_err;
+    float4 *pack;      // [2 nx] per-point records of the TLSPH sweep (allocated on first use)
+    size_t bytes_offsets, bytes_ids, bytes_counts, bytes_pack;
 };
 
 namespace pnb {
+
+// One spare device buffer per kind survives pnb_nlist_destroy, so that rebuilding the lists every
+// step (update! of a PrecomputedNeighborhoodSearch) does not pay cudaMalloc / cudaFree of
+// gigabytes each time.  Keyed by the device the buffer lives on.
+struct SpareBuf { void *p; size_t bytes; int device; };
+static SpareBuf g_spare[4] = {{nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}};
+
+static cudaError_t cached_malloc(int kind, void **out, size_t bytes, size_t *got)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SpareBuf &sp = g_spare[kind];
+    if (sp.p && sp.device == dev && sp.bytes >= bytes && sp.bytes <= 2 * bytes + (1u << 20)) {
+        *out = sp.p; *got = sp.bytes;
+        sp.p = nullptr; sp.bytes = 0;
+        return cudaSuccess;
+    }
+    *got = bytes;
+    return cudaMalloc(out, bytes);
+}
+
+static void cached_free(int kind, void *p, size_t bytes)
+{
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SpareBuf &sp = g_spare[kind];
+    if (sp.p == nullptr || sp.bytes < bytes) {
+        if (sp.p) cudaFree(sp.p);
+        sp.p = p; sp.bytes = bytes; sp.device = dev;
+    } else {
+        cudaFree(p);
+    }
+}
 
 // count pass: lengths of the lists (the `lengths[i] += 1` half of pushat!, vector_of_vectors.jl:83)
 struct ListCountCl {
     static constexpr bool kCountOnly = true;
     static constexpr int kPayBytes = 0;
     static constexpr int kWarpsPerCell = 2;
+    static constexpr int kAccWords = 1;
     uint32_t *out;
     struct State { int cnt; };
+    __device__ __forceinline__ void save_acc(const State &, float *) const {}
+    __device__ __forceinline__ void add_acc(State &, const float *) const {}
+    __device__ __forceinline__ void seek(State &, int) const {}
+    template <int ND>
+    __device__ __forceinline__ void pair_s(State &, float, float, float, float, int, uint32_t, int,
+                                           int) const {}
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
     __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
     __device__ __forceinline__ void count(State &s, int c) const { s.cnt += c; }
@@ -48,10 +92,23 @@ struct ListCountCl {
 struct ListFillCl {
     static constexpr bool kCountOnly = false;
     static constexpr int kPayBytes = 0;
-    static constexpr int kWarpsPerCell = 2;
+    static constexpr int kWarpsPerCell = 4;
+    static constexpr int kAccWords = 1;
+    // the position of a hit in its list is its rank among the point's hits: the tile kernel
+    // must hand over exact hit masks (no fp16 pre-filter)
+    static constexpr bool kExactMasks = true;
     const int64_t *offsets;
     int32_t *ids;
     struct State { int64_t pos; };
+    __device__ __forceinline__ void save_acc(const State &, float *) const {}
+    __device__ __forceinline__ void add_acc(State &, const float *) const {}
+    __device__ __forceinline__ void seek(State &s, int first_rank) const { s.pos += first_rank; }
+    template <int ND>
+    __device__ __forceinline__ void pair_s(State &s, float, float, float, float, int j_id, uint32_t,
+                                           int, int) const
+    {
+        ids[s.pos++] = j_id;
+    }
     __device__ __forceinline__ void init(State &s, bool active, int, int i_id) const
     {
         s.pos = active ? offsets[i_id] : 0;
@@ -72,43 +129,6 @@ struct ListFillCl {
     }
     __device__ __forceinline__ void finish(State &, int, int) const {}
 };
-
-template <int ND, bool PER, class CL>
-static pnb_status launch_list_nd(pnb_grid *g, bool fast, const float *x, int64_t nx, const CL &cl,
-                                 cudaStream_t s)
-{
-    if (fast) {
-        const int nxc = g->p.gs[0] - 2;
-        const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
-        const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
-        if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
-        const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
-        const size_t smem = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
-        ProfScope ps(PH_SWEEP_CELLS, s);
-        k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem, s>>>(
-            g->p, g->cell_start, g->sorted, cl);
-        PNB_LAUNCHED();
-    } else if (nx > 0) {
-        ProfScope ps(PH_SWEEP_POINTS, s);
-        k_sweep_points<ND, PER, CL><<<(unsigned)div_up(nx, 128), 128, 0, s>>>(
-            g->p, g->cell_start, g->sorted, x, nx, nullptr, 0, cl, g->d_err);
-        PNB_LAUNCHED();
-    }
-    return PNB_OK;
-}
-
-template <class CL>
-static pnb_status launch_list(pnb_grid *g, bool fast, const float *x, int64_t nx, const CL &cl,
-                              cudaStream_t s)
-{
-    if (g->template_search || g->n_built == 0) return PNB_OK;
-    const bool per = g->p.periodic != 0;
-    switch (g->p.ndims) {
-        case 1: return per ? launch_list_nd<1, true>(g, fast, x, nx, cl, s) : launch_list_nd<1, false>(g, fast, x, nx, cl, s);
-        case 2: return per ? launch_list_nd<2, true>(g, fast, x, nx, cl, s) : launch_list_nd<2, false>(g, fast, x, nx, cl, s);
-        default: return per ? launch_list_nd<3, true>(g, fast, x, nx, cl, s) : launch_list_nd<3, false>(g, fast, x, nx, cl, s);
-    }
-}
 
 // sorteach! (vector_of_vectors.jl:177-183): every list ascending.  One warp per list.
 //   <= 128 neighbours (the normal case, ~108 at r = 3 spacings): bitonic network in registers,
@@ -268,72 +288,148 @@ __global__ void k_nlist_pairs(GridP g, int64_t nx, const int64_t *__restrict__ o
 }
 
 // TLSPH deformation gradient (formulas: oracle pno_tlsph_deformation_grad; unpinned).
-// One warp per point: lanes stride over the point's list (coalesced id reads), gather X0_j, x_j,
-// m_j, rho0_j, accumulate the ND x ND outer products privately, then a shuffle tree adds the 32
-// partial matrices.  HBM: 4 B per pair + 108 B per point.
-template <int ND, bool PER>
+// Per-point records of the TLSPH sweep: rec[2 j] = (X0_j, -m_j / rho0_j), rec[2 j + 1] = (x_j, 0):
+// what a pair needs from its neighbour is ONE aligned 32-byte sector instead of eight 4-byte
+// gathers from four arrays.
+template <int ND>
+__global__ void k_pack_tlsph(int64_t n, const float *__restrict__ X0, const float *__restrict__ xcur,
+                             const float *__restrict__ mass, const float *__restrict__ rho0,
+                             float4 *__restrict__ rec)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.x = __ldg(X0 + j * ND); b.x = __ldg(xcur + j * ND);
+    if (ND > 1) { a.y = __ldg(X0 + j * ND + 1); b.y = __ldg(xcur + j * ND + 1); }
+    if (ND > 2) { a.z = __ldg(X0 + j * ND + 2); b.z = __ldg(xcur + j * ND + 2); }
+    a.w = -__fdiv_rn(__ldg(mass + j), __ldg(rho0 + j));
+    rec[2 * j] = a;
+    rec[2 * j + 1] = b;
+}
+
+// one 256-bit load (LDG.E.256, sm_100): the two halves of a 32-byte record in ONE L1 wavefront
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
+// One warp per point: lanes stride over the point's list (coalesced id reads), gather the
+// neighbour's 32-byte record, accumulate the ND x ND outer products privately, then a shuffle
+// tree adds the 32 partial matrices.  HBM: 4 B per pair + 108 B per point; the
+// binding resource is L2 -> SM gather bandwidth (one sector per pair).
+// EXACT: the oracle's IEEE operation sequence per term; fast (default): one MUFU.RSQ + FMAs,
+// grad W / d = (-5 sigma / h^2) t^3 with t = 1 - d / (2 h) (the d of w(q)/d cancels).
+template <int ND, bool PER, bool EXACT>
 __global__ void __launch_bounds__(256)
 k_tlsph_defgrad(GridP g, int64_t n, const int64_t *__restrict__ offsets,
-                const int32_t *__restrict__ ids, const float *__restrict__ X0,
-                const float *__restrict__ xcur, const float *__restrict__ mass,
-                const float *__restrict__ rho0, const float *__restrict__ L, float h,
-                float kernel_norm, float *__restrict__ F)
+                const int32_t *__restrict__ ids, const float4 *__restrict__ rec,
+                const float *__restrict__ L, float h, float kernel_norm, float *__restrict__ F)
 {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n) return;
+    // kG lanes per point (4 points per warp): the per-point work (loads of L, the reduction tree,
+    // the store of F) is shared by 4 points per warp instruction, and a list of ~108 neighbours
+    // fills 14 rounds of 8 lanes to 96 % (one warp per point: 4 rounds of 32 lanes, 84 %).
+    constexpr int kG = 8;
+    constexpr int kU = 2;      // pairs per lane in flight: ids first, then records, then arithmetic
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kG;
+    const int sub = (int)(threadIdx.x % kG);
+    const bool have = i < n;
+    const int64_t ii = have ? i : 0;
     constexpr int NN = ND * ND;
-    float Xi[3] = {0.f, 0.f, 0.f}, xi[3] = {0.f, 0.f, 0.f}, Li[NN];
+    float Li[NN];
+    float4 ra, rb;
+    ldg256(rec + 2 * ii, ra, rb);
+    const float Xi[3] = {ra.x, ra.y, ra.z}, xi[3] = {rb.x, rb.y, rb.z};
 #pragma unroll
-    for (int d = 0; d < ND; d++) { Xi[d] = __ldg(X0 + i * ND + d); xi[d] = __ldg(xcur + i * ND + d); }
-#pragma unroll
-    for (int e = 0; e < NN; e++) Li[e] = __ldg(L + i * NN + e);
+    for (int e = 0; e < NN; e++) Li[e] = __ldg(L + ii * NN + e);
     float acc[NN];
 #pragma unroll
     for (int e = 0; e < NN; e++) acc[e] = 0.f;
     const float nh = __fdiv_rn(kernel_norm, h);
-    for (int64_t k = offsets[i] + lane_id(); k < offsets[i + 1]; k += 32) {
-        const int64_t j = ids[k];
-        float p[3] = {0.f, 0.f, 0.f};
+    const float k5 = -5.0f * kernel_norm / (h * h), nhalf_inv_h = -0.5f / h;
+    const PerP pp = make_perp(g);
+    const int64_t k_beg = have ? offsets[ii] : 0;
+    const int len = have ? (int)(offsets[ii + 1] - k_beg) : 0;
+    const int32_t *my_ids = ids + k_beg;
+    int max_len = len;
 #pragma unroll
-        for (int d = 0; d < ND; d++) p[d] = __fsub_rn(Xi[d], __ldg(X0 + j * ND + d));
-        float d2 = dist2<ND>(p[0], p[1], p[2]);
-        d2 = maybe_periodic_fix<ND, PER>(make_perp(g), d2, p[0], p[1], p[2]);
-        const float dist = __fsqrt_rn(d2);
-        if (dist < PNB_SQRT_EPS_F32) continue;
-        const float q = __fdiv_rn(dist, h);
-        float w = 0.f;
-        if (q < 2.f) {
-            const float t = __fsub_rn(1.f, __fmul_rn(q, 0.5f));
-            w = __fmul_rn(__fmul_rn(-5.f, q), __fmul_rn(__fmul_rn(t, t), t));
+    for (int o = 16; o >= kG; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    for (int k0 = sub; k0 < max_len; k0 += kG * kU) {
+        int jj[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) jj[u] = (k0 + kG * u < len) ? __ldg(my_ids + k0 + kG * u) : -1;
+        float4 ra4[kU], rb4[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const int64_t j = jj[u] >= 0 ? jj[u] : ii;
+            ldg256(rec + 2 * j, ra4[u], rb4[u]);
         }
-        const float sg = __fdiv_rn(__fmul_rn(nh, w), dist);
-        float grad[3] = {0.f, 0.f, 0.f}, lg[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int d = 0; d < ND; d++) grad[d] = __fmul_rn(sg, p[d]);
+        for (int u = 0; u < kU; u++) {
+            if (jj[u] < 0) continue;
+            const float4 a = ra4[u], b = rb4[u];
+            const float Xj[3] = {a.x, a.y, a.z}, xj[3] = {b.x, b.y, b.z};
+            const float nvol = a.w;
+            float p[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int a = 0; a < ND; a++) {
-            float t = __fmul_rn(Li[a], grad[0]);
-#pragma unroll
-            for (int b = 1; b < ND; b++) t = __fadd_rn(t, __fmul_rn(Li[b * ND + a], grad[b]));
-            lg[a] = t;
-        }
-        const float nvol = -__fdiv_rn(__ldg(mass + j), __ldg(rho0 + j));
-#pragma unroll
-        for (int b = 0; b < ND; b++)
-#pragma unroll
-            for (int a = 0; a < ND; a++) {
-                const float cd = __fsub_rn(xi[a], __ldg(xcur + j * ND + a));
-                acc[b * ND + a] = __fadd_rn(acc[b * ND + a], __fmul_rn(__fmul_rn(nvol, cd), lg[b]));
+            for (int d = 0; d < ND; d++) p[d] = __fsub_rn(Xi[d], Xj[d]);
+            float d2 = dist2<ND>(p[0], p[1], p[2]);
+            d2 = maybe_periodic_fix<ND, PER>(pp, d2, p[0], p[1], p[2]);
+            float sg;
+            if (EXACT) {
+                const float dist = __fsqrt_rn(d2);
+                if (dist < PNB_SQRT_EPS_F32) continue;
+                const float q = __fdiv_rn(dist, h);
+                float w = 0.f;
+                if (q < 2.f) {
+                    const float t = __fsub_rn(1.f, __fmul_rn(q, 0.5f));
+                    w = __fmul_rn(__fmul_rn(-5.f, q), __fmul_rn(__fmul_rn(t, t), t));
+                }
+                sg = __fdiv_rn(__fmul_rn(nh, w), dist);
+            } else {
+                if (d2 < PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32) continue;
+                const float dist = d2 * fast_rsqrt(d2);
+                const float t = fmaxf(fmaf(nhalf_inv_h, dist, 1.f), 0.f);
+                sg = (k5 * t) * (t * t);
             }
+            float grad[3] = {0.f, 0.f, 0.f}, lg[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int d = 0; d < ND; d++) grad[d] = __fmul_rn(sg, p[d]);
+#pragma unroll
+            for (int a2 = 0; a2 < ND; a2++) {
+                if (EXACT) {
+                    float t = __fmul_rn(Li[a2], grad[0]);
+#pragma unroll
+                    for (int b2 = 1; b2 < ND; b2++) t = __fadd_rn(t, __fmul_rn(Li[b2 * ND + a2], grad[b2]));
+                    lg[a2] = t;
+                } else {
+                    float t = Li[a2] * grad[0];
+#pragma unroll
+                    for (int b2 = 1; b2 < ND; b2++) t = fmaf(Li[b2 * ND + a2], grad[b2], t);
+                    lg[a2] = t;
+                }
+            }
+#pragma unroll
+            for (int a2 = 0; a2 < ND; a2++) {
+                const float cd = __fsub_rn(xi[a2], xj[a2]);
+                const float nc = __fmul_rn(nvol, cd);
+#pragma unroll
+                for (int b2 = 0; b2 < ND; b2++) {
+                    if (EXACT) acc[b2 * ND + a2] = __fadd_rn(acc[b2 * ND + a2], __fmul_rn(nc, lg[b2]));
+                    else acc[b2 * ND + a2] = fmaf(nc, lg[b2], acc[b2 * ND + a2]);
+                }
+            }
+        }
     }
 #pragma unroll
     for (int e = 0; e < NN; e++) {
         float v = acc[e];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        for (int o = kG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         acc[e] = v;
     }
-    if (lane_id() == 0) {
+    if (have && sub == 0) {
 #pragma unroll
         for (int e = 0; e < NN; e++) F[i * NN + e] = acc[e];
     }
@@ -357,9 +453,10 @@ using namespace pnb;
 extern "C" void pnb_nlist_destroy(pnb_nlist *l)
 {
     if (!l) return;
-    cudaFree(l->offsets);
-    cudaFree(l->ids);
-    cudaFree(l->counts);
+    cached_free(0, l->offsets, l->bytes_offsets);
+    cached_free(1, l->ids, l->bytes_ids);
+    cached_free(2, l->counts, l->bytes_counts);
+    cached_free(3, l->pack, l->bytes_pack);
     cudaFree(l->d_err);
     if (l->h_err) cudaFreeHost(l->h_err);
     cudaGetLastError();
@@ -396,8 +493,8 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
         cudaError_t e__ = (expr);                                               \
         if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr));             \
     } while (0)
-    NL_CUDA(cudaMalloc(&l->offsets, sizeof(int64_t) * (size_t)(nx + 1)));
-    NL_CUDA(cudaMalloc(&l->counts, sizeof(uint32_t) * (size_t)(nx + 8)));
+    NL_CUDA(cached_malloc(0, (void **)&l->offsets, sizeof(int64_t) * (size_t)(nx + 1), &l->bytes_offsets));
+    NL_CUDA(cached_malloc(2, (void **)&l->counts, sizeof(uint32_t) * (size_t)(nx + 8), &l->bytes_counts));
     NL_CUDA(cudaMalloc(&l->d_err, sizeof(int)));
     NL_CUDA(cudaMemsetAsync(l->d_err, 0, sizeof(int), s));
     NL_CUDA(cudaMallocHost(&l->h_err, sizeof(int)));
@@ -410,7 +507,10 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
         st = ensure_canonical(g, s);
         if (st != PNB_OK) return fail(st);
     }
-    st = launch_list(g, fast, x, nx, ListCountCl{l->counts}, s);
+    // sorted lists do not depend on the visiting order: the tile kernel builds them; unsorted
+    // lists keep the reference's order and use the ordered kernel
+    const bool tiles = sort != 0;
+    st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListCountCl{l->counts}, s);
     if (st != PNB_OK) return fail(st);
     st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
     if (st != PNB_OK) return fail(st);
@@ -418,8 +518,8 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     NL_CUDA(cudaMemcpyAsync(&total, l->offsets + nx, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     NL_CUDA(cudaStreamSynchronize(s));
     l->n_pairs = total;
-    NL_CUDA(cudaMalloc(&l->ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
-    st = launch_list(g, fast, x, nx, ListFillCl{l->offsets, l->ids}, s);
+    NL_CUDA(cached_malloc(1, (void **)&l->ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1), &l->bytes_ids));
+    st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListFillCl{l->offsets, l->ids}, s);
     if (st != PNB_OK) return fail(st);
     if (sort && nx > 0 && total > 0) {
         ProfScope ps(PH_NLIST_SORT, s);
@@ -490,21 +590,31 @@ extern "C" pnb_status pnb_nlist_pairs_f32(const pnb_nlist *l, const pnb_grid *g,
     return PNB_OK;
 }
 
-extern "C" pnb_status pnb_tlsph_deformation_grad_f32(const pnb_nlist *l, const pnb_grid *g,
+extern "C" pnb_status pnb_tlsph_deformation_grad_f32(const pnb_nlist *l_, const pnb_grid *g,
                                                      const float *X0, const float *xcur,
                                                      const float *mass, const float *rho0,
                                                      const float *L, float smoothing_length,
                                                      float kernel_norm, float *F, void *stream)
 {
-    if (!l || !g) { set_error("handle is NULL"); return PNB_ERR_ARG; }
+    if (!l_ || !g) { set_error("handle is NULL"); return PNB_ERR_ARG; }
+    pnb_nlist *l = const_cast<pnb_nlist *>(l_);
     cudaStream_t s = (cudaStream_t)stream;
     if (l->nx > 0) {
-        const unsigned blocks = (unsigned)div_up(l->nx * 32, 256);
+        if (!l->pack)
+            PNB_CUDA(cached_malloc(3, (void **)&l->pack, sizeof(float4) * 2 * (size_t)l->nx, &l->bytes_pack));
+        const unsigned blocks = (unsigned)div_up(l->nx * 8, 256);   // 8 lanes per point
+        const unsigned pblocks = (unsigned)div_up(l->nx, 256);
         const bool per = g->p.periodic != 0;
+        const bool exact = pnb_get_exact_arithmetic() != 0;
         ProfScope ps(PH_NLIST_SWEEP, s);
 #define DEFGRAD(ND)                                                                                 \
-    if (per) k_tlsph_defgrad<ND, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, X0, xcur, mass, rho0, L, smoothing_length, kernel_norm, F); \
-    else k_tlsph_defgrad<ND, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, X0, xcur, mass, rho0, L, smoothing_length, kernel_norm, F)
+    do {                                                                                            \
+        k_pack_tlsph<ND><<<pblocks, 256, 0, s>>>(l->nx, X0, xcur, mass, rho0, l->pack);             \
+        if (per && exact) k_tlsph_defgrad<ND, true, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack, L, smoothing_length, kernel_norm, F); \
+        else if (per) k_tlsph_defgrad<ND, true, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack, L, smoothing_length, kernel_norm, F); \
+        else if (exact) k_tlsph_defgrad<ND, false, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack, L, smoothing_length, kernel_norm, F); \
+        else k_tlsph_defgrad<ND, false, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack, L, smoothing_length, kernel_norm, F); \
+    } while (0)
         switch (l->ndims) {
             case 1: DEFGRAD(1); break;
             case 2: DEFGRAD(2); break;

@@ -4,6 +4,7 @@
 #include "closures.cuh"
 #include "sweep.cuh"
 #include "sweep_tiles.cuh"
+#include "sweep_launch.cuh"
 
 namespace pnb {
 
@@ -45,8 +46,8 @@ __global__ void k_gather_wcsph(int64_t n, int nd, const float4 *__restrict__ sor
 // 1 = the oracle's IEEE operation sequence (sums bit-identical to the oracle).
 static int g_exact_arithmetic = 0;
 // measurement overrides of the tile sweep (0 = closure default): warps per cell, fp16 pre-filter
-static int g_tune_wpc = 0;
-static int g_tune_half = -1;
+int g_tune_wpc = 0;
+int g_tune_half = -1;
 
 static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
                                  int64_t *n_loop)
@@ -64,109 +65,6 @@ static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const i
 static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points)
 {
     return points == nullptr && g->full_build && x == g->y_built && nx == g->n_y_built;
-}
-
-template <class K>
-static pnb_status allow_smem(K kernel, size_t smem)
-{
-    // static + dynamic shared memory above 48 KB needs the opt-in; the kernels carry up to
-    // ~17 KB of static shared memory, so opt in whenever the dynamic part alone exceeds 28 KB
-    if (smem > 28 * 1024)
-        PNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return PNB_OK;
-}
-
-template <int ND, bool PER, class CL>
-static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
-                            const int32_t *points, int base, const CL &cl, cudaStream_t s)
-{
-    if (fast) {
-        const int nxc = g->p.gs[0] - 2;
-        const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
-        const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
-        if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
-        const size_t smem_rows = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
-        if (!tiles) {
-            const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
-            ProfScope ps(PH_SWEEP_CELLS, s);
-            k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem_rows, s>>>(
-                g->p, g->cell_start, g->sorted, cl);
-            PNB_LAUNCHED();
-            return PNB_OK;
-        }
-        const int64_t blocks = (int64_t)div_up(nxc, kFTX) * nyc * nzc;
-        if (blocks > g->ovf_cap) {
-            cudaFree(g->ovf_tiles);
-            g->ovf_tiles = nullptr;
-            g->ovf_cap = 0;
-            PNB_CUDA(cudaMalloc(&g->ovf_tiles, sizeof(int) * (size_t)blocks));
-            g->ovf_cap = blocks;
-        }
-        if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, sizeof(int)));
-        PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, sizeof(int), s));
-        // variant: warps per cell and the fp16 pre-filter (non-periodic grids only); the tuning
-        // overrides (pnb_set_tuning) exist for A/B measurements of the 3-D non-periodic kernels
-        constexpr bool kHalfOk = !PER;
-        int wpc = CL::kWarpsPerCell;
-        bool half = kHalfOk;
-        if (ND == 3 && !PER) {
-            if (g_tune_wpc == 2 || g_tune_wpc == 4) wpc = g_tune_wpc;
-            if (g_tune_half == 0) half = false;
-        }
-        pnb_status st = PNB_OK;
-#define PNB_TILES(WPC, HALF)                                                                      \
-    do {                                                                                          \
-        constexpr size_t smem = tiles_smem_bytes<ND, CL, HALF>();                                 \
-        st = allow_smem(k_sweep_tiles<ND, PER, CL, WPC, HALF>, smem);                             \
-        if (st != PNB_OK) return st;                                                              \
-        ProfScope ps(PH_SWEEP_CELLS, s);                                                          \
-        k_sweep_tiles<ND, PER, CL, WPC, HALF><<<(unsigned)blocks, kFTX * WPC * 32, smem, s>>>(    \
-            g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);                      \
-        PNB_LAUNCHED();                                                                           \
-    } while (0)
-        if constexpr (ND == 3 && !PER) {
-            if (wpc == 2 && half) PNB_TILES(2, true);
-            else if (wpc == 2) PNB_TILES(2, false);
-            else if (half) PNB_TILES(4, true);
-            else PNB_TILES(4, false);
-        } else {
-            PNB_TILES(CL::kWarpsPerCell, kHalfOk);
-        }
-#undef PNB_TILES
-        {
-            ProfScope ps(PH_SWEEP_OVERFLOW, s);
-            k_sweep_overflow<ND, PER, CL><<<148 * 2, kFTX * 32, smem_rows, s>>>(
-                g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);
-            PNB_LAUNCHED();
-        }
-    } else if (n_loop > 0) {
-        ProfScope ps(PH_SWEEP_POINTS, s);
-        k_sweep_points<ND, PER, CL><<<(unsigned)div_up(n_loop, 128), 128, 0, s>>>(
-            g->p, g->cell_start, g->sorted, x, n_loop, points, base, cl, g->d_err);
-        PNB_LAUNCHED();
-    }
-    return PNB_OK;
-}
-
-// tiles = true: the throughput kernel (any visiting order); false: the ordered kernel whose
-// candidate order is the reference's (needed for bit-identical sums in exact mode).
-template <class CL>
-static pnb_status launch_sweep(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
-                               const int32_t *points, int base, const CL &cl, cudaStream_t s)
-{
-    if (g->template_search || g->n_built == 0) return PNB_OK;  // every neighbourhood is empty
-    const bool per = g->p.periodic != 0;
-    switch (g->p.ndims) {
-        case 1:
-            return per ? launch_nd<1, true>(g, fast, tiles, x, n_loop, points, base, cl, s)
-                       : launch_nd<1, false>(g, fast, tiles, x, n_loop, points, base, cl, s);
-        case 2:
-            return per ? launch_nd<2, true>(g, fast, tiles, x, n_loop, points, base, cl, s)
-                       : launch_nd<2, false>(g, fast, tiles, x, n_loop, points, base, cl, s);
-        default:
-            return per ? launch_nd<3, true>(g, fast, tiles, x, n_loop, points, base, cl, s)
-                       : launch_nd<3, false>(g, fast, tiles, x, n_loop, points, base, cl, s);
-    }
 }
 
 }  // namespace pnb

@@ -43,19 +43,32 @@ constexpr int kFCap = 1728;                // staged candidates per tile incl. p
 constexpr int kFBlocks = kFCap / 32;
 constexpr int kFNBlkMax = 28;              // 32-blocks per cell (3 slots): up to 896 candidates
 constexpr float kHalfSentinel = 64.0f;     // padding candidates: farther than any real one
-constexpr float kHalfThreshold = 1.009765625f;   // 1 + 10 * 2^-10, exactly representable in fp16
-constexpr float kHalfSure = 0.990234375f;        // 1 - 20 * 2^-11: below this the exact test must pass
+// pre-filter thresholds in units of r^2, exactly representable in fp16.  Total rounding error of
+// the fp16 distance (derivation in DESIGN.md 5.2): < 0.0069 on non-periodic grids (|u_x| <= 3,
+// |u_yz| <= 1.5), < 0.011 on periodic grids (cell_size / r < 4/3: |u_x| < 4, |u_yz| < 2).
+__host__ __device__ constexpr float half_thr_hi(bool per) { return per ? 1.013671875f : 1.009765625f; }
+__host__ __device__ constexpr float half_thr_lo(bool per) { return per ? 0.986328125f : 0.990234375f; }
 
 __host__ __device__ constexpr int rows_of(int nd) { return nd == 3 ? 9 : (nd == 2 ? 3 : 1); }
 
 // dynamic shared memory of k_sweep_tiles
+// closures that need the masks of the test phase to be the exact neighbour set (neighbour-list
+// fill: the write position of a hit is its rank) declare kExactMasks = true
+template <class CL, class = void>
+struct needs_exact_masks { static constexpr bool value = false; };
+template <class CL>
+struct needs_exact_masks<CL, decltype((void)CL::kExactMasks)> { static constexpr bool value = CL::kExactMasks; };
+
 template <int ND, class CL, bool HALF>
 __host__ __device__ constexpr size_t tiles_smem_bytes()
 {
+    // mask planes: 1 = hit masks of the drain; 2 = certain hits + undecided band (exact modes)
+    constexpr int planes = (HALF && (CL::kCountOnly || needs_exact_masks<CL>::value)) ? 2
+                           : ((CL::kCountOnly && !HALF) ? 0 : 1);
     return sizeof(float4) * kFCap                               // exact positions + id
            + (HALF ? (size_t)kFBlocks * ND * 16 * 4 : 0)        // packed fp16 coordinates
            + (size_t)kFCap * CL::kPayBytes                      // closure payload planes
-           + ((CL::kCountOnly && !HALF) ? 0 : (size_t)kFTX * kFNBlkMax * 32 * 4);   // hit masks
+           + (size_t)planes * kFTX * kFNBlkMax * 32 * 4;
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t sa)
@@ -130,7 +143,6 @@ __global__ void __launch_bounds__(kFTX * kWPC * 32, 1024 / (kFTX * kWPC * 32))
 k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
               CL cl, int *__restrict__ overflow_tiles, int *__restrict__ overflow_count)
 {
-    static_assert(!(HALF && PER), "the fp16 pre-filter is for non-periodic grids");
     constexpr int NR = rows_of(ND);
     constexpr int NE = kFSlots * NR;          // staged cells per tile
     constexpr int kFThreads = kFTX * kWPC * 32;
@@ -241,15 +253,28 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     __half *s_half16 = reinterpret_cast<__half *>(s_half);
     for (int e = warp; e < NE; e += kFTX * kWPC) {
         const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
+        // periodic grids: a wrapped neighbour cell is staged at its NOMINAL position next to the
+        // tile (minimum image), i.e. its fp16 copy is shifted by whole periods.  Only the
+        // pre-filter sees the shifted copy; the exact test works on the raw coordinates.
+        float sh[3] = {0.f, 0.f, 0.f};
+        if (HALF && PER) {
+            const int slot = e / NR, row = e % NR;
+            const int sx = cx0 - 1 + slot;
+            const int ry = cy + (ND > 1 ? (row % 3) - 1 : 0);
+            const int rz = cz + (ND > 2 ? (row / 3) - 1 : 0);
+            sh[0] = (float)(sx - (floormod_i(sx - 2, g.nc[0]) + 2)) * g.cs[0];
+            if (ND > 1) sh[1] = (float)(ry - (floormod_i(ry - 2, g.nc[1]) + 2)) * g.cs[1];
+            if (ND > 2) sh[2] = (float)(rz - (floormod_i(rz - 2, g.nc[2]) + 2)) * g.cs[2];
+        }
         for (uint32_t k = lane; k < n; k += 32) {
             const float4 pj = sorted[b0 + k];
             const uint32_t q = d0 + k;
             s_pos[q] = pj;
             if (HALF) {
                 const uint32_t hb = (q >> 5) * (ND * 32) + (q & 15u) * 2u + ((q >> 4) & 1u);
-                s_half16[hb] = __float2half_rn((pj.x - org[0]) * inv_r);
-                if (ND > 1) s_half16[hb + 32] = __float2half_rn((pj.y - org[1]) * inv_r);
-                if (ND > 2) s_half16[hb + 64] = __float2half_rn((pj.z - org[2]) * inv_r);
+                s_half16[hb] = __float2half_rn(((pj.x - org[0]) + sh[0]) * inv_r);
+                if (ND > 1) s_half16[hb + 32] = __float2half_rn(((pj.y - org[1]) + sh[1]) * inv_r);
+                if (ND > 2) s_half16[hb + 64] = __float2half_rn(((pj.z - org[2]) + sh[2]) * inv_r);
             }
             cl.stage(s_pay, (int)q, b0 + k, kFCap);
         }
@@ -282,8 +307,8 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     const int nb4 = (nblk + kWPC - 1) / kWPC;                // blocks per share
     const int blk_lo = min(part * nb4, nblk), blk_hi = min(blk_lo + nb4, nblk);
     const uint32_t q_self0 = s_cpre[(my_cell + 1) * NR + NR / 2];
-    const __half2 thr = __float2half2_rn(kHalfThreshold);
-    const __half2 thr_lo = __float2half2_rn(kHalfSure);
+    const __half2 thr = __float2half2_rn(half_thr_hi(PER));
+    const __half2 thr_lo = __float2half2_rn(half_thr_lo(PER));
 
     for (int batch = 0; batch < n_batches; batch++) {
         const uint32_t i_sorted = c_p0 + (uint32_t)batch * 32u + (uint32_t)lane;
@@ -307,17 +332,20 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
         cl.init(st, active, (int)i_sorted, i_id);
 
         // ---- phase 1: test my contiguous share of the cell's blocks; masks to shared memory --
+        // kExact: the closure needs EXACT masks / counts (count only, list fill): certain hits
+        // (below the lower threshold) go to the hit masks, the undecided band between the two
+        // thresholds goes to a second mask plane and is decided below by the exact test.
+        constexpr bool kExact = HALF && (CL::kCountOnly || needs_exact_masks<CL>::value);
+        unsigned *my_band = my_mask + (size_t)kFTX * kFNBlkMax * 32;
         int cnt = 0, n_maybe = 0;
         for (int bb = blk_lo; bb < blk_hi; bb++) {
             unsigned hh;
-            if (HALF && CL::kCountOnly) {
-                // count only: certain neighbours are counted here, the band between the two
-                // thresholds is parked and decided by the exact test below
+            if (kExact) {
                 unsigned sure;
                 hh = test_block_half<ND, true>(s_half + (size_t)(B0 + bb) * (ND * 16), hx, hy, hz,
                                                thr, thr_lo, &sure);
                 if (!active) { hh = 0u; sure = 0u; }
-                my_mask[bb * 32] = hh & ~sure;
+                my_band[bb * 32] = hh & ~sure;
                 n_maybe += __popc(hh & ~sure);
                 hh = sure;
             } else if (HALF) {
@@ -337,22 +365,27 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
             if (!CL::kCountOnly) my_mask[bb * 32] = hh;
             cnt += __popc(hh);
         }
-        if (HALF && CL::kCountOnly) {
-            // exact test (the reference's operation sequence) of the undecided candidates of my
-            // own blocks
+        if (kExact) {
+            // exact test (the reference's operation sequence, periodic fix included) of the
+            // undecided candidates of my own blocks; accepted ones join the hit masks
             const int rounds = __reduce_max_sync(0xffffffffu, n_maybe);
             int bb = blk_lo - 1;
             unsigned mm = 0u;
             for (int t = 0; t < rounds; t++) {
                 if (t < n_maybe) {
-                    while (mm == 0u) { bb++; mm = my_mask[bb * 32]; }
+                    while (mm == 0u) { bb++; mm = my_band[bb * 32]; }
                     const int k = __ffs(mm) - 1;
                     mm &= mm - 1u;
                     const float4 pj = s_pos[32 * (B0 + bb) + k];
-                    const float px = __fsub_rn(xi, pj.x);
-                    const float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
-                    const float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
-                    cnt += (dist2<ND>(px, py, pz) <= pp.r2) ? 1 : 0;
+                    float px = __fsub_rn(xi, pj.x);
+                    float py = ND > 1 ? __fsub_rn(yi, pj.y) : 0.f;
+                    float pz = ND > 2 ? __fsub_rn(zi, pj.z) : 0.f;
+                    float d2 = dist2<ND>(px, py, pz);
+                    d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
+                    if (d2 <= pp.r2) {
+                        cnt++;
+                        if (!CL::kCountOnly) my_mask[bb * 32] |= 1u << k;
+                    }
                 }
             }
         }
@@ -393,6 +426,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                 for (; skip > 0; skip--) mm &= mm - 1u;
             }
             const int rounds = __reduce_max_sync(0xffffffffu, n_mine);
+            cl.seek(st, part * Q);
 
             // ---- phase 3: drain, one hit per lane and round ------------------------------------
             for (int t = 0; t < rounds; t++) {
@@ -408,7 +442,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                     float d2 = dist2<ND>(px, py, pz);
                     d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
                     // the decision: the reference's exact test (the fp16 pass only pre-selects)
-                    if (!HALF || d2 <= pp.r2)
+                    if (!HALF || kExact || d2 <= pp.r2)
                         cl.template pair_s<ND>(st, px, py, pz, d2, __float_as_int(pj.w), pay_sa, slot, kFCap);
                 }
             }
