@@ -561,3 +561,129 @@ def test_full_size_properties_16m(pn):
     pn.update_(nhs, coords, coords)
     cs2, cp2 = nhs.export_csr()
     assert torch.equal(cs, cs2) and torch.equal(cp, cp2)
+
+
+# ------------------------------------------------------------------------------------------
+# the fp16 pre-filter of the tile sweep must never change a neighbour set
+# ------------------------------------------------------------------------------------------
+def _shell_cloud(n_centres, r, seed, nd=3):
+    """Adversarial cloud: for many centres scattered over the cells of a grid, partners at
+    distance r * (1 + k ulp) for k in -4..4 in random directions, i.e. pairs whose d^2 straddles
+    r^2 by a few units in the last place -- the cases a sloppy pre-filter would get wrong."""
+    T = np.float32
+    rng = np.random.default_rng(seed)
+    centres = (rng.uniform(2.0, 10.0, (n_centres, nd)) * r).astype(T)
+    pts = [centres]
+    for k in range(-4, 5):
+        d = rng.normal(size=(n_centres, nd))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rad = np.float64(r) * (1.0 + k * 2.0 ** -23)
+        pts.append((centres.astype(np.float64) + rad * d).astype(T))
+    # axis-aligned partners: the worst case for a pre-filter built on cell-local coordinates
+    for ax in range(nd):
+        e = np.zeros(nd)
+        e[ax] = 1.0
+        for sgn in (-1.0, 1.0):
+            pts.append((centres.astype(np.float64) + sgn * np.float64(r) * e).astype(T))
+    return np.concatenate(pts).astype(T)
+
+
+@pytest.mark.parametrize("nd", [3, 2])
+def test_prefilter_never_changes_neighbor_sets(pn, oracle, nd):
+    """Pairs at distance r (1 +- few ulp): counts, sorted lists and the delivered pos_diff /
+    distance equal the oracle's bit for bit with the fp16 pre-filter on (default) and off, for
+    both warps-per-cell settings."""
+    r = np.float32(0.37)
+    c = _shell_cloud(1500, r, 17, nd)
+    mn, mx = c.min(0) - r, c.max(0) + r
+    og = oracle.Grid(nd, r, mn, mx)
+    og.build(c)
+    off_o, ids_o = og.neighbor_lists(c, c, sort=True)
+    off_t, ids_t = oracle.trivial_lists(c, c, r)
+    assert (off_o == off_t).all() and (ids_o == ids_t).all()
+    x = dev(c)
+    L = pn._lib.lib()
+    try:
+        for wpc, half in ((0, -1), (2, -1), (4, -1), (2, 0), (4, 0)):
+            L.pnb_set_tuning(wpc, half)
+            nhs = make_grid(pn, nd, r, mn, mx)
+            pn.initialize_(nhs, x, x)
+            cnt = torch.zeros(len(c), dtype=torch.int64, device="cuda")
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+            assert (cnt.cpu().numpy() == np.diff(off_o)).all(), (wpc, half)
+            pre = pn.PrecomputedNeighborhoodSearch[nd](search_radius=r, n_points=len(c),
+                                                       update_neighborhood_search=nhs,
+                                                       max_neighbors=4096)
+            pn.initialize_(pre, x, x)
+            off, ids = pre.export_csr()
+            assert (off.cpu().numpy() == off_o).all() and (ids.cpu().numpy() == ids_o).all(), (wpc, half)
+    finally:
+        L.pnb_set_tuning(0, -1)
+    # n-body over the same cloud: the fused closure sees exactly the oracle's pairs
+    mass, G = _nbody_inputs(len(c))
+    dv = torch.zeros((len(c), nd), dtype=torch.float32, device="cuda")
+    pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), G), x, x, nhs)
+    ref, ref64, refabs = og.nbody(c, c, mass, G, wide=True)
+    assert np.all(np.abs(dv.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30)
+
+
+@pytest.mark.parametrize("ratio", [1.0005, 1.17, 1.3329])
+def test_periodic_prefilter_cell_size_ratios(pn, oracle, ratio):
+    """Periodic boxes whose cell_size / r ranges up to the maximum 4/3 (3 cells per dimension is
+    the smallest legal grid): the pre-filter works on minimum-image copies staged next to the tile;
+    lists and counts must equal the oracle's and brute force."""
+    T = np.float32
+    r = T(0.11)
+    rng = np.random.default_rng(23)
+    size = np.array([3 * ratio, 4 * ratio, 5 * ratio]) * np.float64(r)
+    bmn = np.array([0.1, -0.2, 0.05], T)
+    bmx = (bmn.astype(np.float64) + size).astype(T)
+    n = 6000
+    c = (bmn.astype(np.float64) + rng.random((n, 3)) * (bmx.astype(np.float64) - bmn)).astype(T)
+    c = np.clip(c, bmn, np.nextafter(bmx, bmn)).astype(T)
+    og = oracle.Grid(3, r, bmn, bmx, periodic_box=(bmn, bmx))
+    nhs = make_grid(pn, 3, r, bmn, bmx, box=(bmn, bmx))
+    assert nhs.n_cells == og.n_cells
+    og.build(c)
+    x = dev(c)
+    pn.initialize_(nhs, x, x)
+    off_o, ids_o = og.neighbor_lists(c, c, sort=True)
+    off_t, ids_t = oracle.trivial_lists(c, c, r, periodic_box=(bmn, bmx))
+    assert (off_o == off_t).all() and (ids_o == ids_t).all()
+    cnt = torch.zeros(n, dtype=torch.int64, device="cuda")
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+    assert (cnt.cpu().numpy() == np.diff(off_o)).all()
+    pre = pn.PrecomputedNeighborhoodSearch[3](search_radius=r, n_points=n,
+                                              periodic_box=nhs.periodic_box,
+                                              update_neighborhood_search=nhs, max_neighbors=4096)
+    pn.initialize_(pre, x, x)
+    off, ids = pre.export_csr()
+    assert (off.cpu().numpy() == off_o).all() and (ids.cpu().numpy() == ids_o).all()
+    # fused closure over the periodic grid
+    mass, G = _nbody_inputs(n)
+    dv = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+    pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), G), x, x, nhs)
+    ref, ref64, refabs = og.nbody(c, c, mass, G, wide=True)
+    assert np.all(np.abs(dv.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30)
+
+
+def test_build_variants_identical(pn, oracle):
+    """Every variant of the counting-sort kernels (pnb_set_build_tuning) yields the oracle's CSR,
+    for a cell-sorted and for a shuffled cloud (thread-local runs vs. lane runs vs. no runs)."""
+    c, r, mn, mx = pn.benchmark_cloud((33, 31, 29), seed=12)
+    rng = np.random.default_rng(1)
+    L = pn._lib.lib()
+    try:
+        for cloud in (c, c[rng.permutation(len(c))]):
+            og = oracle.Grid(3, r, mn, mx)
+            og.build(cloud)
+            x = dev(cloud)
+            for variant in range(8):
+                L.pnb_set_build_tuning(variant)
+                nhs = make_grid(pn, 3, r, mn, mx)
+                pn.initialize_(nhs, x, x)
+                cs, cp = nhs.export_csr()
+                assert (cs.cpu().numpy() == og.cell_start).all(), variant
+                assert (cp.cpu().numpy() == og.cell_points).all(), variant
+    finally:
+        L.pnb_set_build_tuning(3)
