@@ -138,9 +138,10 @@ int pnb_get_exact_arithmetic(void);
  * closure's default) and the fp16 pre-filter of the distance test (0 = off: exact Float32 test,
  * -1 = default on).  Results are identical for every setting; only the speed changes. */
 void pnb_set_tuning(int warps_per_cell, int half_prefilter);
-/* Measurement variants of the counting-sort kernels (bit 0: histogram reads global memory
- * directly, bit 1: scatter uses the strided lane mapping, bit 2: histogram uses it too).
- * Results are identical for every setting. */
+/* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
+ * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
+ * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with
+ * lane runs; default 25).  Results are identical for every setting. */
 void pnb_set_build_tuning(int variant);
 
 /* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */
@@ -183,6 +184,9 @@ pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t nx, const fl
 void pnb_nlist_destroy(pnb_nlist *l);
 int64_t pnb_nlist_n_points(const pnb_nlist *l);
 int64_t pnb_nlist_n_pairs(const pnb_nlist *l);
+/* length of the longest list: the reference raises "cell list is full..." when it exceeds
+ * max_neighbors (src/vector_of_vectors.jl:114-121) */
+int64_t pnb_nlist_max_length(const pnb_nlist *list);
 /* offsets[nx+1] int64, ids[n_pairs] int32 (+ index_base) */
 pnb_status pnb_nlist_export_csr(const pnb_nlist *l, int64_t *offsets, int32_t *ids, int index_base,
                                 void *stream);

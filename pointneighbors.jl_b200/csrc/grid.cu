@@ -372,7 +372,7 @@ extern "C" int64_t pnb_grid_n_points(const pnb_grid *g) { return g ? g->n_built 
 // ---------------------------------------------------------------------------------------------
 namespace pnb {
 
-int g_tune_build = 3;   // measurement variants of the build kernels (pnb_set_build_tuning)
+int g_tune_build = 25;   // measurement variants of the build kernels (pnb_set_build_tuning)
 constexpr int kBuildThreads = 256;
 constexpr int kBuildPPT = 4;                                // points per thread
 constexpr int kBuildTile = kBuildThreads * kBuildPPT;       // points per block
@@ -475,6 +475,27 @@ k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
     __shared__ __align__(16) float s_xyz[kBuildTile * ND];
     const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
     bool bad = false;
+    if ((variant & 16) && idx == nullptr && block0 + kBuildTile <= n_idx) {
+        // full tile, no staging: lane-strided points, runs of equal cells merged across the
+        // lanes of a warp (one RED per run: ~2 per warp on a cell-sorted cloud)
+        float p[kBuildPPT][3];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const int64_t k = block0 + j * kBuildThreads + (int)threadIdx.x;
+#pragma unroll
+            for (int d = 0; d < 3; d++) p[j][d] = d < ND ? __ldg(y + k * ND + d) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const int lin = point_cell_fast<ND, PER>(g, bp, p[j]);
+            bad = bad || lin < 0;
+            int run_len;
+            const int h = run_head(lin, lin >= 0, &run_len);
+            if (lin >= 0 && h == lane_id()) atomicAdd(cell_count + lin, (unsigned)run_len);
+        }
+        if (bad) atomicOr(err, 1);
+        return;
+    }
     if ((variant & 1) && idx == nullptr && block0 + kBuildTile <= n_idx &&
         ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
         // full tile, no staging: every thread reads its kBuildPPT consecutive points straight
@@ -575,6 +596,36 @@ k_scatter_points(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
 {
     __shared__ __align__(16) float s_xyz[kBuildTile * ND];
     const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
+    if ((variant & 8) && idx == nullptr && block0 + kBuildTile <= n_idx) {
+        // full tile, no staging, no barrier: lane-strided points read with scalar loads (the
+        // three loads of a warp cover the same 384 contiguous bytes), all atomics of the
+        // kBuildPPT points are issued before the first record is stored
+        float p[kBuildPPT][3];
+        int lin[kBuildPPT], h[kBuildPPT], rl[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const int64_t k = block0 + j * kBuildThreads + (int)threadIdx.x;
+#pragma unroll
+            for (int d = 0; d < 3; d++) p[j][d] = d < ND ? __ldg(y + k * ND + d) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            lin[j] = point_cell_fast<ND, PER>(g, bp, p[j]);
+            h[j] = run_head(lin[j], lin[j] >= 0, &rl[j]);
+        }
+        unsigned basev[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++)
+            basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(cursor + lin[j], (unsigned)rl[j]) : 0u;
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const unsigned b = __shfl_sync(0xffffffffu, basev[j], h[j] & 31);
+            const int32_t id = (int32_t)(block0 + j * kBuildThreads + (int)threadIdx.x);
+            if (lin[j] >= 0)
+                sorted[b + (unsigned)(lane_id() - h[j])] = make_float4(p[j][0], p[j][1], p[j][2], __int_as_float(id));
+        }
+        return;
+    }
     if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
     if (!(variant & 2) && idx == nullptr && block0 + kBuildTile <= n_idx) {
         // full tile: consecutive points per thread, thread-local runs (see k_cell_hist); the

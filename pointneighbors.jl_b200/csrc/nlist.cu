@@ -15,6 +15,7 @@
 struct pnb_nlist {
     int64_t nx;        // number of lists (points of x)
     int64_t n_pairs;
+    int64_t max_len;   // longest list
     int64_t *offsets;  // [nx+1] device
     int32_t *ids;      // [n_pairs] device, 0-based
     uint32_t *counts;  // [nx] device
@@ -59,6 +60,15 @@ static void cached_free(int kind, void *p, size_t bytes)
     } else {
         cudaFree(p);
     }
+}
+
+// longest list -> out[0] (the reference's overflow check compares it with max_neighbors)
+__global__ void k_max_count(int64_t n, const uint32_t *__restrict__ counts, unsigned int *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = i < n ? counts[i] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (lane_id() == 0 && v > 0u) atomicMax(out, v);
 }
 
 // count pass: lengths of the lists (the `lengths[i] += 1` half of pushat!, vector_of_vectors.jl:83)
@@ -465,6 +475,7 @@ extern "C" void pnb_nlist_destroy(pnb_nlist *l)
 
 extern "C" int64_t pnb_nlist_n_points(const pnb_nlist *l) { return l ? l->nx : 0; }
 extern "C" int64_t pnb_nlist_n_pairs(const pnb_nlist *l) { return l ? l->n_pairs : 0; }
+extern "C" int64_t pnb_nlist_max_length(const pnb_nlist *l) { return l ? l->max_len : 0; }
 
 extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
                                           int64_t n, int sort, pnb_nlist **out, void *stream)
@@ -515,9 +526,17 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
     if (st != PNB_OK) return fail(st);
     int64_t total = 0;
+    unsigned int longest = 0;
+    if (nx > 0) {
+        // counts[nx .. nx+7] is zeroed padding: word nx holds the maximum
+        k_max_count<<<(unsigned)div_up(nx, 256), 256, 0, s>>>(nx, l->counts, l->counts + nx);
+        g_launch_count++;
+    }
     NL_CUDA(cudaMemcpyAsync(&total, l->offsets + nx, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    NL_CUDA(cudaMemcpyAsync(&longest, l->counts + nx, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     NL_CUDA(cudaStreamSynchronize(s));
     l->n_pairs = total;
+    l->max_len = longest;
     NL_CUDA(cached_malloc(1, (void **)&l->ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1), &l->bytes_ids));
     st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListFillCl{l->offsets, l->ids}, s);
     if (st != PNB_OK) return fail(st);

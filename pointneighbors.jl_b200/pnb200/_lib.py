@@ -66,6 +66,7 @@ SIGNATURES = {
     "pnb_nlist_destroy": (None, [_vp]),
     "pnb_nlist_n_points": (_i64, [_vp]),
     "pnb_nlist_n_pairs": (_i64, [_vp]),
+    "pnb_nlist_max_length": (_i64, [_vp]),
     "pnb_nlist_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "pnb_nlist_export_dvov": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, C.c_int, _vp]),
     "pnb_nlist_pairs_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

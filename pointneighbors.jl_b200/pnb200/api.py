@@ -694,12 +694,8 @@ class PrecomputedNeighborhoodSearch(metaclass=_Parametric):
         self._lists = _NeighborLists.build(self.neighborhood_search, x, y,
                                            sort=self.sort_neighbor_lists)
         # the reference errors when a list overflows `max_neighbors` (vector_of_vectors.jl:114-121)
-        torch = _torch()
-        off, _ = self._lists.export_csr(0)
-        if off.numel() > 1:
-            longest = int((off[1:] - off[:-1]).max())
-            if longest > self.max_neighbors:
-                raise PointNeighborsError("cell list is full. Use a larger `max_points_per_cell`.")
+        if int(_lib.lib().pnb_nlist_max_length(self._lists._handle)) > self.max_neighbors:
+            raise PointNeighborsError("cell list is full. Use a larger `max_points_per_cell`.")
 
     def neighbor_lists(self, index_base=1):
         """(backend, lengths) in the reference layout, see _NeighborLists.export_dvov."""

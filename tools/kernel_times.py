@@ -20,7 +20,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--closures", default="count,nbody,wcsph")
 ap.add_argument("--moving", action="store_true", help="non-zero velocities (viscosity branch active)")
 ap.add_argument("--wpc", type=int, default=0, help="warps per cell override (2 or 4)")
-ap.add_argument("--build", type=int, default=0, help="build kernel variant bits")
+ap.add_argument("--build", type=int, default=25, help="build kernel variant bits")
 ap.add_argument("--half", type=int, default=-1, help="0 = exact Float32 test instead of the fp16 pre-filter")
 args = ap.parse_args()
 n = args.lattice
