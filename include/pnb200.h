@@ -138,6 +138,9 @@ int pnb_get_exact_arithmetic(void);
  * closure's default) and the fp16 pre-filter of the distance test (0 = off: exact Float32 test,
  * -1 = default on).  Results are identical for every setting; only the speed changes. */
 void pnb_set_tuning(int warps_per_cell, int half_prefilter);
+/* Sweeps over two point sets (x != y, all points of x): 1 (default) = x is binned into the grid's
+ * cells and swept by the tile kernel, 0 = one thread per query point.  Same results. */
+void pnb_set_twoset_tiles(int on);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
  * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with

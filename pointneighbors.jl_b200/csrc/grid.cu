@@ -341,6 +341,8 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
 {
     if (!g) return;
     cudaFree(g->cell_start_alloc);
+    cudaFree(g->xq_start_alloc);
+    cudaFree(g->xq_sorted);
     cudaFree(g->cell_count);
     cudaFree(g->cell_points);
     cudaFree(g->sorted);
@@ -470,7 +472,7 @@ template <int ND, bool PER>
 __global__ void __launch_bounds__(kBuildThreads)
 k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
             const int32_t *__restrict__ idx, int base, uint32_t *__restrict__ cell_count,
-            int *__restrict__ err, int variant)
+            int *__restrict__ err, int variant, int err_bit)
 {
     __shared__ __align__(16) float s_xyz[kBuildTile * ND];
     const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
@@ -493,7 +495,7 @@ k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
             const int h = run_head(lin, lin >= 0, &run_len);
             if (lin >= 0 && h == lane_id()) atomicAdd(cell_count + lin, (unsigned)run_len);
         }
-        if (bad) atomicOr(err, 1);
+        if (bad) atomicOr(err, err_bit);
         return;
     }
     if ((variant & 1) && idx == nullptr && block0 + kBuildTile <= n_idx &&
@@ -524,7 +526,7 @@ k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
             }
         }
         if (cur >= 0) atomicAdd(cell_count + cur, (unsigned)n);
-        if (bad) atomicOr(err, 1);
+        if (bad) atomicOr(err, err_bit);
         return;
     }
     if (idx == nullptr) load_tile<ND>(y, block0, n_idx, s_xyz);
@@ -555,7 +557,7 @@ k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
             }
         }
         if (cur >= 0) atomicAdd(cell_count + cur, (unsigned)n);
-        if (bad) atomicOr(err, 1);
+        if (bad) atomicOr(err, err_bit);
         return;
     }
     // generic path (last tile, `eachindex_y` subsets): strided points, runs merged across lanes
@@ -580,7 +582,7 @@ k_cell_hist(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
         const int h = run_head(lin, valid, &run_len);
         if (valid && h == lane_id()) atomicAdd(cell_count + lin, (unsigned)run_len);
     }
-    if (bad) atomicOr(err, 1);
+    if (bad) atomicOr(err, err_bit);
 }
 
 // K_c: scatter.  `cursor` is cell_start + 1 holding the exclusive prefix E[c] at cursor[c]; the
@@ -948,9 +950,12 @@ pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s)
     return PNB_OK;
 }
 
+// The counting sort into (start[0 .. C], records): used for the cell list itself (y) and for the
+// cell-ordered copy of a second point set (x of a two-set sweep, build_query_list).
 template <int ND, bool PER>
-static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t *idx,
-                           int64_t n_idx, int base, cudaStream_t s)
+static pnb_status sort_into(pnb_grid *g, const float *y, const int32_t *idx, int64_t n_idx,
+                            int base, uint32_t *start, float4 *records, int err_bit,
+                            cudaStream_t s)
 {
     const int64_t C = g->p.total_cells;
     BuildP bp;
@@ -960,20 +965,59 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
     if (n_idx > 0) {
         ProfScope ps(PH_BUILD_CELL_COUNT, s);
         k_cell_hist<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, idx, base,
-                                                              g->cell_count, g->d_err, g_tune_build);
+                                                              g->cell_count, g->d_err, g_tune_build,
+                                                              err_bit);
         PNB_LAUNCHED();
     }
-    // exclusive prefix E[c] -> cell_start[c + 1]; cell_start[0] stays 0 (set at creation)
-    pnb_status st = scan_impl<uint32_t, true, false>(g, g->cell_count, g->cell_start + 1, C, s);
+    // exclusive prefix E[c] -> start[c + 1]; start[0] stays 0 (set at allocation)
+    pnb_status st = scan_impl<uint32_t, true, false>(g, g->cell_count, start + 1, C, s);
     if (st != PNB_OK) return st;
     if (n_idx > 0) {
         ProfScope ps(PH_BUILD_SCATTER, s);
         k_scatter_points<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, idx, base,
-                                                                   g->cell_start + 1, g->sorted, g_tune_build);
+                                                                   start + 1, records, g_tune_build);
         PNB_LAUNCHED();
     }
-    (void)n;
     return PNB_OK;
+}
+
+template <int ND, bool PER>
+static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t *idx,
+                           int64_t n_idx, int base, cudaStream_t s)
+{
+    (void)n;
+    return sort_into<ND, PER>(g, y, idx, n_idx, base, g->cell_start, g->sorted, 1, s);
+}
+
+// Cell-ordered copy of the QUERY points of a two-set sweep (x != y): the same counting sort with
+// the grid's cell arithmetic into xq_start / xq_sorted.  A query point outside the valid cells
+// 2 .. size-1 has a stencil that leaves the grid: the safe variant's BoundsError
+// (src/nhs_grid.jl:530-532) -> error bit 2.
+pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, cudaStream_t s)
+{
+    const int64_t C = g->p.total_cells;
+    if (!g->xq_start_alloc) {
+        PNB_CUDA(cudaMalloc(&g->xq_start_alloc, sizeof(uint32_t) * (size_t)(C + 8)));
+        PNB_CUDA(cudaMemsetAsync(g->xq_start_alloc, 0, sizeof(uint32_t) * (size_t)(C + 8), s));
+        g->xq_start = g->xq_start_alloc + 3;
+    }
+    if (nx > g->xq_cap) {
+        cudaFree(g->xq_sorted);
+        g->xq_sorted = nullptr;
+        g->xq_cap = 0;
+        const int64_t cap = nx + nx / 16 + 32;
+        PNB_CUDA(cudaMalloc(&g->xq_sorted, sizeof(float4) * (size_t)cap));
+        g->xq_cap = cap;
+    }
+    const bool per = g->p.periodic != 0;
+    switch (g->p.ndims) {
+        case 1: return per ? sort_into<1, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
+                           : sort_into<1, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s);
+        case 2: return per ? sort_into<2, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
+                           : sort_into<2, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s);
+        default: return per ? sort_into<3, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
+                            : sort_into<3, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s);
+    }
 }
 
 }  // namespace pnb

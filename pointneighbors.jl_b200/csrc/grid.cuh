@@ -25,6 +25,11 @@ struct pnb_grid {
     int64_t cap_points;
     bool canonical;         // records inside every cell are ordered by point id (ensure_canonical)
 
+    // cell-ordered copy of the query points of a two-set sweep (x != y), built per sweep
+    uint32_t *xq_start_alloc, *xq_start;   // [C+1]
+    float4 *xq_sorted;                     // [xq_cap]
+    int64_t xq_cap;
+
     // scan workspace
     unsigned long long *scan_status;
     int64_t scan_tiles_cap;
@@ -56,6 +61,7 @@ struct pnb_grid {
 namespace pnb {
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
+pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, cudaStream_t s);  // two-set sweeps
 pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s); // ids ascending inside every cell + cell_points
 pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
                               cudaStream_t s);

@@ -48,6 +48,7 @@ static int g_exact_arithmetic = 0;
 // measurement overrides of the tile sweep (0 = closure default): warps per cell, fp16 pre-filter
 int g_tune_wpc = 0;
 int g_tune_half = -1;
+int g_tune_twoset = 1;
 
 static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
                                  int64_t *n_loop)
@@ -73,6 +74,7 @@ using namespace pnb;
 
 extern "C" void pnb_set_exact_arithmetic(int on) { g_exact_arithmetic = on != 0; }
 extern "C" int pnb_get_exact_arithmetic(void) { return g_exact_arithmetic; }
+extern "C" void pnb_set_twoset_tiles(int on) { g_tune_twoset = on != 0; }
 extern "C" void pnb_set_tuning(int warps_per_cell, int half_prefilter)
 {
     g_tune_wpc = warps_per_cell;

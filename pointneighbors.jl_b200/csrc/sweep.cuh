@@ -57,11 +57,15 @@ __device__ __forceinline__ unsigned test_block(const PerP &g, const float4 *__re
 // Shared-memory view: payload planes are arrays of kCap elements.
 // Global view: payload planes are the cell-ordered arrays themselves.
 
+// (q_start, q_sorted): cell-ordered query points; the same arrays as (cell_start, sorted) for
+// x === y, the copy made by build_query_list for a second point set.
 template <int ND, bool PER, class CL, int TX>
 __device__ __forceinline__ void
 sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
-                const float4 *__restrict__ sorted, const CL &cl, int64_t tile)
+                const float4 *__restrict__ sorted, const uint32_t *__restrict__ q_start,
+                const float4 *__restrict__ q_sorted, const CL &cl, int64_t tile)
 {
+    const bool two = q_sorted != sorted;
     constexpr int kSlotsT = TX + 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_pos = reinterpret_cast<float4 *>(smem_raw);
@@ -87,8 +91,8 @@ sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
     const PerP pp = make_perp(g);
 
     // points of this tile are one contiguous range of the cell-ordered array
-    const uint32_t tile_p0 = cell_start[linear_cell(g, cx0, cy, cz)];
-    const uint32_t tile_p1 = cell_start[linear_cell(g, cx1, cy, cz) + 1];
+    const uint32_t tile_p0 = q_start[linear_cell(g, cx0, cy, cz)];
+    const uint32_t tile_p1 = q_start[linear_cell(g, cx1, cy, cz) + 1];
     if (tile_p0 == tile_p1) return;   // uniform for the CTA
 
     // work items of the tile: (cell, pass of 32 points); a batch gives every warp one item
@@ -96,8 +100,8 @@ sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
     uint32_t c_p0 = 0, c_p1 = 0;
     if (my_cx <= cx1) {
         const int lin = linear_cell(g, my_cx, cy, cz);
-        c_p0 = cell_start[lin];
-        c_p1 = cell_start[lin + 1];
+        c_p0 = q_start[lin];
+        c_p1 = q_start[lin + 1];
     }
     const int my_passes = (int)((c_p1 - c_p0 + 31) / 32);
     int max_passes = my_passes;
@@ -117,11 +121,11 @@ sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
         int i_id = 0;
         typename CL::State st;
         if (active) {
-            const float4 pi = sorted[i_sorted];
+            const float4 pi = q_sorted[i_sorted];
             xi = pi.x; yi = pi.y; zi = pi.z;
             i_id = __float_as_int(pi.w);
         }
-        cl.init(st, active, (int)i_sorted, i_id);
+        cl.init(st, active, two ? -1 : (int)i_sorted, i_id);
         const bool warp_active = __any_sync(0xffffffffu, active);
 
         // ---- neighbour rows in CartesianIndices order: dz outer, dy inner, dx = slots ------
@@ -220,7 +224,7 @@ sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
                 }
             }
         }
-        if (active) cl.finish(st, (int)i_sorted, i_id);
+        if (active) cl.finish(st, two ? -1 : (int)i_sorted, i_id);
         __syncthreads();
     }
 }
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(kCellThreads)
 k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
               CL cl)
 {
-    sweep_tile_rows<ND, PER, CL, kTX>(g, cell_start, sorted, cl, (int64_t)blockIdx.x);
+    sweep_tile_rows<ND, PER, CL, kTX>(g, cell_start, sorted, cell_start, sorted, cl, (int64_t)blockIdx.x);
 }
 
 // General path: one thread per query point ------------------------------------------------------

@@ -8,6 +8,7 @@ namespace pnb {
 
 extern int g_tune_wpc;    // pnb_set_tuning: warps per cell override (0 = closure default)
 extern int g_tune_half;   // pnb_set_tuning: 0 = exact Float32 test instead of the fp16 pre-filter
+extern int g_tune_twoset; // pnb_set_twoset_tiles: 0 = x != y always uses the per-point kernel
 
 template <class K>
 static pnb_status allow_smem(K kernel, size_t smem)
@@ -19,11 +20,25 @@ static pnb_status allow_smem(K kernel, size_t smem)
     return PNB_OK;
 }
 
+// two point sets (x != y) below this many query points use the per-point kernel: building the
+// query cell list does not pay off
+constexpr int64_t kTwoSetMinPoints = 4096;
+
 template <int ND, bool PER, class CL>
 static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
                             const int32_t *points, int base, const CL &cl, cudaStream_t s)
 {
-    if (fast) {
+    // x != y, all points looped over: bin the query points into the grid's cells
+    // (build_query_list) and run the tile kernel with queries from that copy
+    const bool two = !fast && tiles && points == nullptr && n_loop >= kTwoSetMinPoints &&
+                     g_tune_twoset != 0;
+    if (two) {
+        pnb_status stq = build_query_list(g, x, n_loop, s);
+        if (stq != PNB_OK) return stq;
+    }
+    if (fast || two) {
+        const uint32_t *q_start = two ? g->xq_start : g->cell_start;
+        const float4 *q_sorted = two ? g->xq_sorted : g->sorted;
         const int nxc = g->p.gs[0] - 2;
         const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
         const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
@@ -47,39 +62,40 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         }
         if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, sizeof(int)));
         PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, sizeof(int), s));
-        // variant: warps per cell and the fp16 pre-filter (non-periodic grids only); the tuning
-        // overrides (pnb_set_tuning) exist for A/B measurements of the 3-D non-periodic kernels
-        constexpr bool kHalfOk = true;
+        // variant: warps per cell and the fp16 pre-filter; the tuning overrides (pnb_set_tuning)
+        // exist for A/B measurements of the 3-D non-periodic x === y kernels
         int wpc = CL::kWarpsPerCell;
-        bool half = kHalfOk;
-        if (ND == 3 && !PER) {
+        bool half = true;
+        if (ND == 3 && !PER && !two) {
             if (g_tune_wpc == 2 || g_tune_wpc == 4) wpc = g_tune_wpc;
             if (g_tune_half == 0) half = false;
         }
         pnb_status st = PNB_OK;
-#define PNB_TILES(WPC, HALF)                                                                      \
+#define PNB_TILES(WPC, HALF, TWO)                                                                 \
     do {                                                                                          \
         constexpr size_t smem = tiles_smem_bytes<ND, CL, HALF>();                                 \
-        st = allow_smem(k_sweep_tiles<ND, PER, CL, WPC, HALF>, smem);                             \
+        st = allow_smem(k_sweep_tiles<ND, PER, CL, WPC, HALF, TWO>, smem);                        \
         if (st != PNB_OK) return st;                                                              \
         ProfScope ps(PH_SWEEP_CELLS, s);                                                          \
-        k_sweep_tiles<ND, PER, CL, WPC, HALF><<<(unsigned)blocks, kFTX * WPC * 32, smem, s>>>(    \
-            g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);                      \
+        k_sweep_tiles<ND, PER, CL, WPC, HALF, TWO><<<(unsigned)blocks, kFTX * WPC * 32, smem, s>>>( \
+            g->p, g->cell_start, g->sorted, q_start, q_sorted, cl, g->ovf_tiles, g->ovf_count);   \
         PNB_LAUNCHED();                                                                           \
     } while (0)
-        if constexpr (ND == 3 && !PER) {
-            if (wpc == 2 && half) PNB_TILES(2, true);
-            else if (wpc == 2) PNB_TILES(2, false);
-            else if (half) PNB_TILES(4, true);
-            else PNB_TILES(4, false);
+        if (two) {
+            PNB_TILES(CL::kWarpsPerCell, true, true);
+        } else if constexpr (ND == 3 && !PER) {
+            if (wpc == 2 && half) PNB_TILES(2, true, false);
+            else if (wpc == 2) PNB_TILES(2, false, false);
+            else if (half) PNB_TILES(4, true, false);
+            else PNB_TILES(4, false, false);
         } else {
-            PNB_TILES(CL::kWarpsPerCell, kHalfOk);
+            PNB_TILES(CL::kWarpsPerCell, true, false);
         }
 #undef PNB_TILES
         {
             ProfScope ps(PH_SWEEP_OVERFLOW, s);
             k_sweep_overflow<ND, PER, CL><<<148 * 2, kFTX * 32, smem_rows, s>>>(
-                g->p, g->cell_start, g->sorted, cl, g->ovf_tiles, g->ovf_count);
+                g->p, g->cell_start, g->sorted, q_start, q_sorted, cl, g->ovf_tiles, g->ovf_count);
             PNB_LAUNCHED();
         }
     } else if (n_loop > 0) {

@@ -138,9 +138,13 @@ __device__ __forceinline__ unsigned test_block_half(const uint32_t *__restrict__
     return hits;
 }
 
-template <int ND, bool PER, class CL, int kWPC, bool HALF>
+// TWO: the query points are a second point set (x != y) whose cell-ordered copy is
+// (q_start, q_sorted) (pnb::build_query_list); the candidates always come from the cell list
+// (cell_start, sorted).  For x === y both pairs of pointers are the same arrays.
+template <int ND, bool PER, class CL, int kWPC, bool HALF, bool TWO>
 __global__ void __launch_bounds__(kFTX * kWPC * 32, 1024 / (kFTX * kWPC * 32))
 k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
+              const uint32_t *__restrict__ q_start, const float4 *__restrict__ q_sorted,
               CL cl, int *__restrict__ overflow_tiles, int *__restrict__ overflow_count)
 {
     constexpr int NR = rows_of(ND);
@@ -174,9 +178,9 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const PerP pp = make_perp(g);
 
-    const uint32_t tile_p0 = cell_start[linear_cell(g, cx0, cy, cz)];
-    const uint32_t tile_p1 = cell_start[linear_cell(g, cx1, cy, cz) + 1];
-    if (tile_p0 == tile_p1) return;
+    const uint32_t tile_p0 = q_start[linear_cell(g, cx0, cy, cz)];
+    const uint32_t tile_p1 = q_start[linear_cell(g, cx1, cy, cz) + 1];
+    if (tile_p0 == tile_p1) return;   // no query points in this tile
 
     // ---- table of staged cells, entry e = slot * NR + row (rows in CartesianIndices order) ----
     if (warp == 0) {
@@ -222,8 +226,8 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     uint32_t c_p0 = 0, c_p1 = 0;
     if (my_cx <= cx1) {
         const int lin = linear_cell(g, my_cx, cy, cz);
-        c_p0 = cell_start[lin];
-        c_p1 = cell_start[lin + 1];
+        c_p0 = q_start[lin];
+        c_p1 = q_start[lin + 1];
     }
     if (part == 0 && lane == 0) s_maxpass[my_cell] = (int)((c_p1 - c_p0 + 31) / 32);
     __syncthreads();
@@ -250,21 +254,28 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
         if (ND > 2) org[2] = fmaf((float)(cz + g.off[2]) - 0.5f, g.cs[2], g.minc[2]);
         inv_r = __frcp_rn(g.r);
     }
+    float inv_bs[3] = {0.f, 0.f, 0.f};
+    if (HALF && PER) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) inv_bs[d] = __frcp_rn(pp.bs[d]);
+    }
     __half *s_half16 = reinterpret_cast<__half *>(s_half);
     for (int e = warp; e < NE; e += kFTX * kWPC) {
         const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
-        // periodic grids: a wrapped neighbour cell is staged at its NOMINAL position next to the
-        // tile (minimum image), i.e. its fp16 copy is shifted by whole periods.  Only the
-        // pre-filter sees the shifted copy; the exact test works on the raw coordinates.
-        float sh[3] = {0.f, 0.f, 0.f};
+        // periodic grids: every candidate is staged at the image closest to the NOMINAL position
+        // of its cell next to the tile (minimum image): its fp16 copy is shifted by whole
+        // periods, k = rint((cell centre - y) / box size) per point -- points may lie outside
+        // the box, the reference wraps cells, not coordinates.  Only the pre-filter sees the
+        // shifted copy; the exact test works on the raw coordinates.
+        float cen[3] = {0.f, 0.f, 0.f};
         if (HALF && PER) {
             const int slot = e / NR, row = e % NR;
             const int sx = cx0 - 1 + slot;
             const int ry = cy + (ND > 1 ? (row % 3) - 1 : 0);
             const int rz = cz + (ND > 2 ? (row / 3) - 1 : 0);
-            sh[0] = (float)(sx - (floormod_i(sx - 2, g.nc[0]) + 2)) * g.cs[0];
-            if (ND > 1) sh[1] = (float)(ry - (floormod_i(ry - 2, g.nc[1]) + 2)) * g.cs[1];
-            if (ND > 2) sh[2] = (float)(rz - (floormod_i(rz - 2, g.nc[2]) + 2)) * g.cs[2];
+            cen[0] = fmaf((float)(sx + g.off[0]) - 0.5f, g.cs[0], g.minc[0]);
+            if (ND > 1) cen[1] = fmaf((float)(ry + g.off[1]) - 0.5f, g.cs[1], g.minc[1]);
+            if (ND > 2) cen[2] = fmaf((float)(rz + g.off[2]) - 0.5f, g.cs[2], g.minc[2]);
         }
         for (uint32_t k = lane; k < n; k += 32) {
             const float4 pj = sorted[b0 + k];
@@ -272,9 +283,15 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
             s_pos[q] = pj;
             if (HALF) {
                 const uint32_t hb = (q >> 5) * (ND * 32) + (q & 15u) * 2u + ((q >> 4) & 1u);
-                s_half16[hb] = __float2half_rn(((pj.x - org[0]) + sh[0]) * inv_r);
-                if (ND > 1) s_half16[hb + 32] = __float2half_rn(((pj.y - org[1]) + sh[1]) * inv_r);
-                if (ND > 2) s_half16[hb + 64] = __float2half_rn(((pj.z - org[2]) + sh[2]) * inv_r);
+                float ux = pj.x - org[0], uy = pj.y - org[1], uz = pj.z - org[2];
+                if (PER) {
+                    ux = fmaf(rintf((cen[0] - pj.x) * inv_bs[0]), pp.bs[0], ux);
+                    if (ND > 1) uy = fmaf(rintf((cen[1] - pj.y) * inv_bs[1]), pp.bs[1], uy);
+                    if (ND > 2) uz = fmaf(rintf((cen[2] - pj.z) * inv_bs[2]), pp.bs[2], uz);
+                }
+                s_half16[hb] = __float2half_rn(ux * inv_r);
+                if (ND > 1) s_half16[hb + 32] = __float2half_rn(uy * inv_r);
+                if (ND > 2) s_half16[hb + 64] = __float2half_rn(uz * inv_r);
             }
             cl.stage(s_pay, (int)q, b0 + k, kFCap);
         }
@@ -317,7 +334,8 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
         int i_id = 0;
         __half2 hx = __float2half2_rn(0.f), hy = hx, hz = hx;
         typename CL::State st;
-        if (active) {
+        if (active && !TWO) {
+            // x === y: the point is one of the staged candidates of its own cell
             const uint32_t q = q_self0 + (uint32_t)batch * 32u + (uint32_t)lane;
             const float4 pi = s_pos[q];
             xi = pi.x; yi = pi.y; zi = pi.z;
@@ -329,7 +347,30 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                 if (ND > 2) hz = __half2half2(s_half16[hb + 64]);
             }
         }
-        cl.init(st, active, (int)i_sorted, i_id);
+        if (active && TWO) {
+            const float4 pi = q_sorted[i_sorted];
+            xi = pi.x; yi = pi.y; zi = pi.z;
+            i_id = __float_as_int(pi.w);
+            if (HALF) {
+                float ux = xi - org[0], uy = yi - org[1], uz = zi - org[2];
+                if (PER) {
+                    const float c0 = fmaf((float)(my_cx + g.off[0]) - 0.5f, g.cs[0], g.minc[0]);
+                    ux = fmaf(rintf((c0 - xi) * inv_bs[0]), pp.bs[0], ux);
+                    if (ND > 1) {
+                        const float c1 = fmaf((float)(cy + g.off[1]) - 0.5f, g.cs[1], g.minc[1]);
+                        uy = fmaf(rintf((c1 - yi) * inv_bs[1]), pp.bs[1], uy);
+                    }
+                    if (ND > 2) {
+                        const float c2 = fmaf((float)(cz + g.off[2]) - 0.5f, g.cs[2], g.minc[2]);
+                        uz = fmaf(rintf((c2 - zi) * inv_bs[2]), pp.bs[2], uz);
+                    }
+                }
+                hx = __float2half2_rn(ux * inv_r);
+                if (ND > 1) hy = __float2half2_rn(uy * inv_r);
+                if (ND > 2) hz = __float2half2_rn(uz * inv_r);
+            }
+        }
+        cl.init(st, active, TWO ? -1 : (int)i_sorted, i_id);
 
         // ---- phase 1: test my contiguous share of the cell's blocks; masks to shared memory --
         // kExact: the closure needs EXACT masks / counts (count only, list fill): certain hits
@@ -459,7 +500,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
             }
             if (batch + 1 < n_batches) cell_barrier(my_cell, kCellThreads_);
         }
-        if (part == 0 && active) cl.finish(st, (int)i_sorted, i_id);
+        if (part == 0 && active) cl.finish(st, TWO ? -1 : (int)i_sorted, i_id);
     }
     (void)kFThreads;
 }
@@ -469,12 +510,14 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
 template <int ND, bool PER, class CL>
 __global__ void __launch_bounds__(kFTX * 32)
 k_sweep_overflow(GridP g, const uint32_t *__restrict__ cell_start,
-                 const float4 *__restrict__ sorted, CL cl, const int *__restrict__ overflow_tiles,
+                 const float4 *__restrict__ sorted, const uint32_t *__restrict__ q_start,
+                 const float4 *__restrict__ q_sorted, CL cl, const int *__restrict__ overflow_tiles,
                  const int *__restrict__ overflow_count)
 {
     const int n = *overflow_count;
     for (int t = blockIdx.x; t < n; t += gridDim.x) {
-        sweep_tile_rows<ND, PER, CL, kFTX>(g, cell_start, sorted, cl, (int64_t)overflow_tiles[t]);
+        sweep_tile_rows<ND, PER, CL, kFTX>(g, cell_start, sorted, q_start, q_sorted, cl,
+                                           (int64_t)overflow_tiles[t]);
         __syncthreads();
     }
 }

@@ -329,6 +329,13 @@ function Adapt.adapt_structure(to::B200Backend, nhs::PrecomputedNeighborhoodSear
         PointNeighbors.transposed_backend(nhs.neighbor_lists))
 end
 
+# pushat! errors when a list overflows `max_neighbors` (src/vector_of_vectors.jl:114-121)
+function check_list_capacity(s::B200PrecomputedNeighborhoodSearch)
+    longest = ccall((:pnb_nlist_max_length, libpnb200), Int64, (Ptr{Cvoid},), s.lists.handle)
+    longest > s.max_neighbors && error("cell list is full. Use a larger `max_points_per_cell`.")
+    return s
+end
+
 # initialize! / update!      src/nhs_precomputed.jl:130-169
 function initialize!(s::B200PrecomputedNeighborhoodSearch, x::B200Array{Float32, 2},
                      y::B200Array{Float32, 2}; parallelization_backend = default_backend(x),
@@ -337,7 +344,7 @@ function initialize!(s::B200PrecomputedNeighborhoodSearch, x::B200Array{Float32,
         error("this neighborhood search does not support inactive points")
     initialize!(s.neighborhood_search, x, y)
     s.lists = NeighborLists(s.neighborhood_search, x, y; sort = s.sort_neighbor_lists)
-    return s
+    return check_list_capacity(s)
 end
 
 function update!(s::B200PrecomputedNeighborhoodSearch, x::B200Array{Float32, 2},
@@ -348,6 +355,7 @@ function update!(s::B200PrecomputedNeighborhoodSearch, x::B200Array{Float32, 2},
     update!(s.neighborhood_search, x, y; points_moving)
     if any(points_moving)
         s.lists = NeighborLists(s.neighborhood_search, x, y; sort = s.sort_neighbor_lists)
+        check_list_capacity(s)
     end
     return s
 end

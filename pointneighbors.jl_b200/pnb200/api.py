@@ -28,6 +28,7 @@ from . import _lib
 from ._lib import ArgumentError, BoundsError, PointNeighborsError, WcsphParams, check
 
 __all__ = [
+    "foreach_neighbor", "foreach_neighbor_unsafe", "mapreduce_neighbor", "mapreduce_neighbor_unsafe",
     "ArgumentError", "PointNeighborsError", "BoundsError",
     "ParallelUpdate", "SerialUpdate", "ParallelIncrementalUpdate", "SemiParallelUpdate",
     "SerialIncrementalUpdate", "DynamicVectorOfVectors",
@@ -534,6 +535,56 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
     else:
         raise TypeError("f must be a fused closure object or a callable f(i, j, pos_diff, d)")
     return None
+
+
+def _check_point(point, n):
+    i = int(point)
+    if not 0 <= i < n:
+        # the safe variants bounds-check `point` against system_coords (neighborhood_search.jl:250-262)
+        raise BoundsError(f"BoundsError: attempt to access {n}-column coordinates at index [{point}]")
+    return i
+
+
+def foreach_neighbor(f, system_coords, neighbor_coords, neighborhood_search, point, *,
+                     search_radius=None):
+    """foreach_neighbor(f, x, y, nhs, point)  (src/neighborhood_search.jl:236-276): f(i, j,
+    pos_diff, d) for every neighbour of ONE point, in the reference's visiting order.  The pairs
+    come from the device (a one-point neighbour list); f is host code.  0-based `point`."""
+    if search_radius is not None and np.float32(search_radius) != np.float32(
+            neighborhood_search.search_radius):
+        raise ArgumentError("a `search_radius` other than the one of the neighborhood search "
+                            "is not supported")
+    nhs = neighborhood_search
+    x = _coords(system_coords, nhs._ndims)
+    y = _coords(neighbor_coords, nhs._ndims)
+    i = _check_point(point, x.shape[0])
+    if isinstance(nhs, PrecomputedNeighborhoodSearch):
+        return nhs._foreach(f, x, y, [i])
+    # a one-point query set: list 0 of the device-built lists belongs to `point`
+    x_one = x[i:i + 1].contiguous()
+    lists = _NeighborLists.build(nhs, x_one, y, sort=False)
+    lists.call_host(lambda _i, j, pd, d: f(i, j, pd, d), x_one, y, nhs, None, radius_test=True)
+    return None
+
+
+foreach_neighbor_unsafe = foreach_neighbor   # the bounds checks are host-side and cost nothing here
+
+
+def mapreduce_neighbor(f, op, system_coords, neighbor_coords, neighborhood_search, point, *, init,
+                       search_radius=None):
+    """mapreduce_neighbor(f, op, x, y, nhs, point; init)  (src/neighborhood_search.jl:325-357):
+    op-reduction of f(i, j, pos_diff, d) over the neighbours of `point`, starting from `init`."""
+    acc = [init]
+
+    def g(i, j, pos_diff, d):
+        acc[0] = op(acc[0], f(i, j, pos_diff, d))
+
+    foreach_neighbor(g, system_coords, neighbor_coords, neighborhood_search, point,
+                     search_radius=search_radius)
+    return acc[0]
+
+
+mapreduce_neighbor_unsafe = mapreduce_neighbor
 
 
 # ---------------------------------------------------------------------------------------------

@@ -687,3 +687,100 @@ def test_build_variants_identical(pn, oracle):
                 assert (cp.cpu().numpy() == og.cell_points).all(), variant
     finally:
         L.pnb_set_build_tuning(25)
+
+
+def test_per_point_api(pn, oracle):
+    """foreach_neighbor / mapreduce_neighbor (src/neighborhood_search.jl:236-383) for single points
+    of a second point set: neighbours, pos_diff and distance equal the oracle's, in the reference's
+    visiting order; the reduction equals the host reduction; out-of-range point -> BoundsError."""
+    r = np.float32(2.5)
+    y = _cloud(pn, (14, 13, 12), r, 5)
+    rng = np.random.default_rng(2)
+    x = (y[rng.choice(len(y), 50, replace=False)] + rng.normal(0, 0.2, (50, 3))).astype(np.float32)
+    mn, mx = y.min(0) - 2 * r, y.max(0) + 2 * r
+    nhs = make_grid(pn, 3, r, mn, mx)
+    tx, ty = dev(x), dev(y)
+    pn.initialize_(nhs, tx, ty)
+    og = oracle.Grid(3, r, mn, mx)
+    og.build(y)
+    off_o, ids_o = og.neighbor_lists(x, y, sort=False)
+    pd_o, dist_o = oracle.list_pairs(x, y, off_o, ids_o, r)
+    for i in (0, 17, 49):
+        got = []
+        pn.foreach_neighbor(lambda a, j, pd, d: got.append((a, j, tuple(pd), float(d))), tx, ty, nhs, i)
+        lo, hi = off_o[i], off_o[i + 1]
+        assert [g[1] for g in got] == ids_o[lo:hi].tolist()
+        assert all(g[0] == i for g in got)
+        assert np.array_equal(np.array([g[2] for g in got], np.float32).reshape(-1, 3), pd_o[lo:hi])
+        assert np.array_equal(np.array([g[3] for g in got], np.float32), dist_o[lo:hi])
+        total = pn.mapreduce_neighbor(lambda a, j, pd, d: float(d), lambda u, v: u + v, tx, ty, nhs,
+                                      i, init=0.0)
+        assert total == sum(float(d) for d in dist_o[lo:hi])
+        nmax = pn.mapreduce_neighbor(lambda a, j, pd, d: j, max, tx, ty, nhs, i, init=-1)
+        assert nmax == (int(ids_o[lo:hi].max()) if hi > lo else -1)
+    with pytest.raises(pn.BoundsError):
+        pn.foreach_neighbor(lambda *a: None, tx, ty, nhs, 50)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_two_sets_tile_path(pn, oracle, periodic):
+    """x != y with many query points: the query points are binned into the grid's cells and swept
+    by the tile kernel (pnb_set_twoset_tiles).  Counts / unsorted-then-sorted lists bit-exact,
+    n-body and WCSPH within 1e-5, identical neighbour sets with the tile path on and off; periodic
+    case with points of both sets up to two periods outside the box."""
+    T = np.float32
+    rng = np.random.default_rng(31)
+    if periodic:
+        c, r, bmn, bmx = _periodic_case(pn, 26, 3)
+        y = c
+        size = (bmx - bmn).astype(np.float64)
+        x = (bmn + rng.random((9000, 3)) * size).astype(T)
+        # the reference wraps cells, not coordinates: move some points to other periods
+        y = (y + (rng.integers(-2, 3, y.shape) * (rng.random(y.shape) < 0.2)) * size).astype(T)
+        x = (x + (rng.integers(-2, 3, x.shape) * (rng.random(x.shape) < 0.2)) * size).astype(T)
+        mn, mx, box = bmn, bmx, (bmn, bmx)
+    else:
+        r = T(2.5)
+        y = _cloud(pn, (30, 28, 26), r, 4)
+        x = (y[rng.choice(len(y), 9000, replace=False)] + rng.normal(0, 0.4, (9000, 3))).astype(T)
+        mn, mx, box = y.min(0) - 2 * r, y.max(0) + 2 * r, None
+    og = oracle.Grid(3, r, mn, mx, periodic_box=box)
+    og.build(y)
+    cnt_o = og.count_neighbors(x, y)
+    off_o, ids_o = og.neighbor_lists(x, y, sort=True)
+    off_t, ids_t = oracle.trivial_lists(x, y, r, periodic_box=box)
+    assert (off_o == off_t).all() and (ids_o == ids_t).all()
+    tx, ty = dev(x), dev(y)
+    nhs = make_grid(pn, 3, r, mn, mx, box=box)
+    pn.initialize_(nhs, tx, ty)
+    mass, G = _nbody_inputs(len(y))
+    ref_nb, ref64_nb, refabs_nb = og.nbody(x, y, mass, G, wide=True)
+    L = pn._lib.lib()
+    try:
+        for tiles_on in (1, 0):
+            L.pnb_set_twoset_tiles(tiles_on)
+            cnt = torch.full((len(x),), -1, dtype=torch.int64, device="cuda")
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), tx, ty, nhs)
+            assert (cnt.cpu().numpy() == cnt_o).all(), tiles_on
+            lists = pn.api._NeighborLists.build(nhs, tx, ty, sort=True)
+            off, ids = lists.export_csr(0)
+            assert (off.cpu().numpy() == off_o).all() and (ids.cpu().numpy() == ids_o).all(), tiles_on
+            dv = torch.zeros((len(x), 3), dtype=torch.float32, device="cuda")
+            pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), G), tx, ty, nhs)
+            assert np.all(np.abs(dv.cpu().numpy() - ref64_nb) <= 1e-5 * refabs_nb + 1e-30), tiles_on
+    finally:
+        L.pnb_set_twoset_tiles(1)
+    if not periodic:
+        # WCSPH between two systems (fluid-boundary style)
+        vy, my, py_, kw = _wcsph_inputs(pn, y, r, 3, seed=3)
+        vx, mxx, px_, _ = _wcsph_inputs(pn, x, r, 3, seed=4)
+        dvw = torch.zeros((len(x), 4), dtype=torch.float32, device="cuda")
+        f = pn.WCSPHInteract(dvw, dev(vx), dev(vy), dev(mxx), dev(my), dev(px_), dev(py_), **kw)
+        pn.foreach_point_neighbor(f, tx, ty, nhs)
+        ref, ref64, refabs = og.wcsph(x, y, vx, vy, mxx, my, px_, py_, f.params_array(), wide=True)
+        assert np.all(np.abs(dvw.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30)
+        # a query point whose stencil leaves the grid -> BoundsError, as on the per-point path
+        x_bad = x.copy()
+        x_bad[11] = mx + 10 * r
+        with pytest.raises(pn.BoundsError):
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), dev(x_bad), ty, nhs)

@@ -141,6 +141,25 @@ for c in [int(v) for v in args.configs.split(",")]:
                     "tlsph_hbm_frac": bytes_sweep / (smin * 1e-3) / 1e9 / HBM,
                     "list_build_kernels_ms": {k: ms / max(cnt_, 1) * (cnt_ / max(prof["k_cell_hist"][1], 1))
                                               for k, (ms, cnt_) in prof.items() if cnt_}})
+    elif c == 6:
+        # two point sets (fluid-boundary style): x = every 4th lattice point
+        # moved by half a spacing, y = the 254^3 cloud
+        N, r, A, nhs = lattice(254)
+        X = (A[::4] + T(0.5) * (r / T(3))).clamp_(0.0, 1.0).contiguous()
+        nxp = X.shape[0]
+        cnt = torch.zeros(nxp, dtype=torch.int64, device=dev)
+        f = pn.CountNeighbors(cnt)
+        mn, med = timed(lambda: pn.foreach_point_neighbor(f, X, A, nhs), args.reps, False)
+        P = int(cnt.sum())
+        v, mass, pressure = bench.wcsph_state_torch(N, r, 3, dev)
+        vx, mx_, px_ = v[::4].contiguous(), mass[::4].contiguous(), pressure[::4].contiguous()
+        dv = torch.zeros((nxp, 4), device=dev)
+        fw = pn.WCSPHInteract(dv, vx, v, mx_, mass, px_, pressure, smoothing_length=r / T(2),
+                              sound_speed=T(10.0))
+        wmn, wmed = timed(lambda: pn.foreach_point_neighbor(fw, X, A, nhs), args.reps, False)
+        out.append({"config": 6, "what": "two sets: x = 4.1M, y = 16.4M (general path)", "Nx": nxp,
+                    "N": N, "pairs": P, "count_ms_min": mn, "count_gpairs_per_s": P / mn / 1e6,
+                    "wcsph_ms_min": wmn, "wcsph_gpairs_per_s": P / wmn / 1e6})
     torch.cuda.empty_cache()
 for o in out:
     print(json.dumps(o))
