@@ -139,7 +139,8 @@ int pnb_get_exact_arithmetic(void);
  * -1 = default on).  Results are identical for every setting; only the speed changes. */
 void pnb_set_tuning(int warps_per_cell, int half_prefilter);
 /* Sweeps over two point sets (x != y, all points of x): 1 (default) = x is binned into the grid's
- * cells and swept by the tile kernel, 0 = one thread per query point.  Same results. */
+ * cells and swept by the tile kernel when its occupied cells hold >= 12 query points on average,
+ * 2 = always, 0 = never (one thread per query point).  Same results. */
 void pnb_set_twoset_tiles(int on);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,

@@ -324,9 +324,9 @@ extern "C" pnb_status pnb_grid_create_window_f32(int ndims, float r, const float
         return fail(e, "cudaMemset");
     if ((e = cudaMemset(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
         return fail(e, "cudaMemset");
-    if ((e = cudaHostAlloc(&g->h_err, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
+    if ((e = cudaHostAlloc(&g->h_err, 2 * sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
         return fail(e, "cudaHostAlloc");
-    *g->h_err = 0;
+    g->h_err[0] = g->h_err[1] = 0;
     if ((e = cudaHostGetDevicePointer(&g->d_err, g->h_err, 0)) != cudaSuccess)
         return fail(e, "cudaHostGetDevicePointer");
     if ((e = cudaMalloc(&g->scan_ticket, sizeof(unsigned int))) != cudaSuccess)
@@ -993,7 +993,17 @@ static pnb_status build_nd(pnb_grid *g, const float *y, int64_t n, const int32_t
 // the grid's cell arithmetic into xq_start / xq_sorted.  A query point outside the valid cells
 // 2 .. size-1 has a stencil that leaves the grid: the safe variant's BoundsError
 // (src/nhs_grid.jl:530-532) -> error bit 2.
-pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, cudaStream_t s)
+__global__ void k_count_nonempty(int64_t n_cells, const uint32_t *__restrict__ start,
+                                 unsigned int *__restrict__ out)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ne = c < n_cells && start[c + 1] != start[c];
+    const unsigned m = __ballot_sync(0xffffffffu, ne);
+    if (lane_id() == 0 && m) atomicAdd(out, (unsigned)__popc(m));
+}
+
+pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *points_per_cell,
+                            cudaStream_t s)
 {
     const int64_t C = g->p.total_cells;
     if (!g->xq_start_alloc) {
@@ -1010,14 +1020,28 @@ pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, cudaStream_
         g->xq_cap = cap;
     }
     const bool per = g->p.periodic != 0;
+    pnb_status st;
     switch (g->p.ndims) {
-        case 1: return per ? sort_into<1, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
-                           : sort_into<1, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s);
-        case 2: return per ? sort_into<2, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
-                           : sort_into<2, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s);
-        default: return per ? sort_into<3, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
-                            : sort_into<3, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s);
+        case 1: st = per ? sort_into<1, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
+                         : sort_into<1, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s); break;
+        case 2: st = per ? sort_into<2, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
+                         : sort_into<2, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s); break;
+        default: st = per ? sort_into<3, true>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s)
+                          : sort_into<3, false>(g, x, nullptr, nx, 0, g->xq_start, g->xq_sorted, 2, s); break;
     }
+    if (st != PNB_OK) return st;
+    // query points per occupied cell: the tile kernel gives a lane to every point of a cell, so
+    // it only pays off when the occupied cells are reasonably full (the caller decides)
+    // (counter in device memory: thousands of atomics on the mapped host word would crawl)
+    unsigned int *d_ne = g->xq_start_alloc;      // word 0 of the allocation, below xq_start[0]
+    PNB_CUDA(cudaMemsetAsync(d_ne, 0, sizeof(unsigned int), s));
+    k_count_nonempty<<<(unsigned)div_up(C, 256), 256, 0, s>>>(C, g->xq_start, d_ne);
+    PNB_LAUNCHED();
+    PNB_CUDA(cudaMemcpyAsync(g->h_err + 1, d_ne, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
+    const unsigned ne = *(volatile unsigned int *)(g->h_err + 1);
+    *points_per_cell = ne ? (double)nx / (double)ne : 0.0;
+    return PNB_OK;
 }
 
 }  // namespace pnb

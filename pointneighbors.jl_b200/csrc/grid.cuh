@@ -61,7 +61,8 @@ struct pnb_grid {
 namespace pnb {
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
-pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, cudaStream_t s);  // two-set sweeps
+pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *points_per_cell,
+                            cudaStream_t s);  // two-set sweeps
 pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s); // ids ascending inside every cell + cell_points
 pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
                               cudaStream_t s);

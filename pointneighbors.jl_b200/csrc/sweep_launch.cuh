@@ -23,6 +23,7 @@ static pnb_status allow_smem(K kernel, size_t smem)
 // two point sets (x != y) below this many query points use the per-point kernel: building the
 // query cell list does not pay off
 constexpr int64_t kTwoSetMinPoints = 4096;
+constexpr double kTwoSetMinPerCell = 12.0;   // query points per occupied cell
 
 template <int ND, bool PER, class CL>
 static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
@@ -30,11 +31,14 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
 {
     // x != y, all points looped over: bin the query points into the grid's cells
     // (build_query_list) and run the tile kernel with queries from that copy
-    const bool two = !fast && tiles && points == nullptr && n_loop >= kTwoSetMinPoints &&
-                     g_tune_twoset != 0;
+    bool two = !fast && tiles && points == nullptr && n_loop >= kTwoSetMinPoints &&
+               g_tune_twoset != 0;
     if (two) {
-        pnb_status stq = build_query_list(g, x, n_loop, s);
+        double per_cell = 0.0;
+        pnb_status stq = build_query_list(g, x, n_loop, &per_cell, s);
         if (stq != PNB_OK) return stq;
+        // a lane per query point of a cell: sparse query sets are better served per point
+        if (per_cell < kTwoSetMinPerCell && g_tune_twoset != 2) two = false;
     }
     if (fast || two) {
         const uint32_t *q_start = two ? g->xq_start : g->cell_start;

@@ -757,7 +757,7 @@ def test_two_sets_tile_path(pn, oracle, periodic):
     ref_nb, ref64_nb, refabs_nb = og.nbody(x, y, mass, G, wide=True)
     L = pn._lib.lib()
     try:
-        for tiles_on in (1, 0):
+        for tiles_on in (2, 1, 0):     # 2 = tile kernel always, 1 = by occupancy, 0 = per point
             L.pnb_set_twoset_tiles(tiles_on)
             cnt = torch.full((len(x),), -1, dtype=torch.int64, device="cuda")
             pn.foreach_point_neighbor(pn.CountNeighbors(cnt), tx, ty, nhs)
@@ -776,9 +776,20 @@ def test_two_sets_tile_path(pn, oracle, periodic):
         vx, mxx, px_, _ = _wcsph_inputs(pn, x, r, 3, seed=4)
         dvw = torch.zeros((len(x), 4), dtype=torch.float32, device="cuda")
         f = pn.WCSPHInteract(dvw, dev(vx), dev(vy), dev(mxx), dev(my), dev(px_), dev(py_), **kw)
-        pn.foreach_point_neighbor(f, tx, ty, nhs)
         ref, ref64, refabs = og.wcsph(x, y, vx, vy, mxx, my, px_, py_, f.params_array(), wide=True)
-        assert np.all(np.abs(dvw.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30)
+        try:
+            for tiles_on in (2, 0):
+                L.pnb_set_twoset_tiles(tiles_on)
+                pn.foreach_point_neighbor(f, tx, ty, nhs)
+                assert np.all(np.abs(dvw.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30), tiles_on
+            L.pnb_set_twoset_tiles(2)
+            # a query point whose stencil leaves the grid -> BoundsError, as on the per-point path
+            x_bad = x.copy()
+            x_bad[11] = mx + 10 * r
+            with pytest.raises(pn.BoundsError):
+                pn.foreach_point_neighbor(pn.CountNeighbors(cnt), dev(x_bad), ty, nhs)
+        finally:
+            L.pnb_set_twoset_tiles(1)
         # a query point whose stencil leaves the grid -> BoundsError, as on the per-point path
         x_bad = x.copy()
         x_bad[11] = mx + 10 * r

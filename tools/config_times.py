@@ -142,24 +142,29 @@ for c in [int(v) for v in args.configs.split(",")]:
                     "list_build_kernels_ms": {k: ms / max(cnt_, 1) * (cnt_ / max(prof["k_cell_hist"][1], 1))
                                               for k, (ms, cnt_) in prof.items() if cnt_}})
     elif c == 6:
-        # two point sets (fluid-boundary style): x = every 4th lattice point
-        # moved by half a spacing, y = the 254^3 cloud
+        # two point sets (fluid-boundary style): x = a dense slab of the cloud
+        # (16 cell layers, jittered by a third of a spacing), y = the whole 254^3 cloud
         N, r, A, nhs = lattice(254)
-        X = (A[::4] + T(0.5) * (r / T(3))).clamp_(0.0, 1.0).contiguous()
+        sel = (A[:, 2] > 0.3) & (A[:, 2] < 0.3 + 16 * float(r))
+        X = (A[sel] + (T(1.0) / T(3.0)) * (r / T(3)) * torch.randn(int(sel.sum()), 3, device=dev)).clamp_(0.0, 1.0).contiguous()
         nxp = X.shape[0]
-        cnt = torch.zeros(nxp, dtype=torch.int64, device=dev)
-        f = pn.CountNeighbors(cnt)
-        mn, med = timed(lambda: pn.foreach_point_neighbor(f, X, A, nhs), args.reps, False)
-        P = int(cnt.sum())
         v, mass, pressure = bench.wcsph_state_torch(N, r, 3, dev)
-        vx, mx_, px_ = v[::4].contiguous(), mass[::4].contiguous(), pressure[::4].contiguous()
-        dv = torch.zeros((nxp, 4), device=dev)
-        fw = pn.WCSPHInteract(dv, vx, v, mx_, mass, px_, pressure, smoothing_length=r / T(2),
-                              sound_speed=T(10.0))
-        wmn, wmed = timed(lambda: pn.foreach_point_neighbor(fw, X, A, nhs), args.reps, False)
-        out.append({"config": 6, "what": "two sets: x = 4.1M, y = 16.4M (general path)", "Nx": nxp,
-                    "N": N, "pairs": P, "count_ms_min": mn, "count_gpairs_per_s": P / mn / 1e6,
-                    "wcsph_ms_min": wmn, "wcsph_gpairs_per_s": P / wmn / 1e6})
+        vx, mx_, px_ = v[sel].contiguous(), mass[sel].contiguous(), pressure[sel].contiguous()
+        res = {"config": 6, "what": "two sets: x = dense slab (16 cell layers), y = 254^3", "Nx": nxp, "N": N}
+        for mode, name in ((1, "tiles"), (0, "per_point")):
+            _lib.lib().pnb_set_twoset_tiles(mode)
+            cnt = torch.zeros(nxp, dtype=torch.int64, device=dev)
+            f = pn.CountNeighbors(cnt)
+            mn, med = timed(lambda: pn.foreach_point_neighbor(f, X, A, nhs), args.reps, False)
+            P = int(cnt.sum())
+            dv = torch.zeros((nxp, 4), device=dev)
+            fw = pn.WCSPHInteract(dv, vx, v, mx_, mass, px_, pressure, smoothing_length=r / T(2),
+                                  sound_speed=T(10.0))
+            wmn, wmed = timed(lambda: pn.foreach_point_neighbor(fw, X, A, nhs), args.reps, False)
+            res.update({"pairs": P, f"count_ms_{name}": mn, f"count_gpairs_per_s_{name}": P / mn / 1e6,
+                        f"wcsph_ms_{name}": wmn, f"wcsph_gpairs_per_s_{name}": P / wmn / 1e6})
+        _lib.lib().pnb_set_twoset_tiles(1)
+        out.append(res)
     torch.cuda.empty_cache()
 for o in out:
     print(json.dumps(o))
