@@ -429,7 +429,11 @@ def gpu_arm(args):
                 "serial_ms_per_step": e2e_serial_ms,
                 "serial_value": float(np.mean(pairs)) / (e2e_serial_ms * 1e-3)},
         "roofline": {"bound": "hbm", "kernel": "k_sweep_tiles<3,false,WcsphClT<false>,4,true>", "achieved": ach,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact
+                     # workload, from the ncu --set full capture summarised in
+                     # profiles/r1_wcsph_sweep_v5_ncu_summary.txt (793.0 MB + 255.4 MB)
+                     "traffic": 1048416000 if n == 254 else None,
                      "peak_source": peak_src, "launch_ms": sweep_avg,
                      "algorithmic_bytes": bytes_sweep,
                      "note": "the fused interaction is FP32-issue bound (~100 flop/B), not HBM bound "
@@ -439,6 +443,9 @@ def gpu_arm(args):
                       "model": "8*K_ref + 70*P non-FMA operations; peak = 148 SM x 128 lanes x max clock"},
         "roofline_update": {"bound": "hbm", "kernels": build_names, "achieved": ach_u,
                             "peak": hbm_peak, "unit": "GB/s", "frac": ach_u / hbm_peak,
+                            # profiles/r1_update_v3_ncu_summary.txt: hist 199.8 + 4.9 MB,
+                            # scan 2.7 MB, scatter 200.5 + 214.9 MB
+                            "traffic": 622800000 if n == 254 else None,
                             "device_ms": build_ms, "algorithmic_bytes": bytes_update,
                             "per_kernel_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in build_names}},
         "kernel_ms": {k: (v_[0] / v_[1] if v_[1] else 0.0) for k, v_ in prof.items()},
