@@ -63,8 +63,8 @@ template <int ND, class CL, bool HALF>
 __host__ __device__ constexpr size_t tiles_smem_bytes()
 {
     // mask planes: 1 = hit masks of the drain; 2 = certain hits + undecided band (exact modes)
-    constexpr int planes = (HALF && (CL::kCountOnly || needs_exact_masks<CL>::value)) ? 2
-                           : ((CL::kCountOnly && !HALF) ? 0 : 1);
+    constexpr int planes = CL::kCountOnly ? (HALF ? 1 : 0)            // only the undecided band
+                           : ((HALF && needs_exact_masks<CL>::value) ? 2 : 1);
     return sizeof(float4) * kFCap                               // exact positions + id
            + (HALF ? (size_t)kFBlocks * ND * 16 * 4 : 0)        // packed fp16 coordinates
            + (size_t)kFCap * CL::kPayBytes                      // closure payload planes
@@ -377,7 +377,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
         // (below the lower threshold) go to the hit masks, the undecided band between the two
         // thresholds goes to a second mask plane and is decided below by the exact test.
         constexpr bool kExact = HALF && (CL::kCountOnly || needs_exact_masks<CL>::value);
-        unsigned *my_band = my_mask + (size_t)kFTX * kFNBlkMax * 32;
+        unsigned *my_band = CL::kCountOnly ? my_mask : my_mask + (size_t)kFTX * kFNBlkMax * 32;
         int cnt = 0, n_maybe = 0;
         for (int bb = blk_lo; bb < blk_hi; bb++) {
             unsigned hh;
