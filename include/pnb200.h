@@ -88,6 +88,51 @@ pnb_status pnb_grid_create_window_f32(int ndims, float search_radius, const floa
                                       const float *max_corner, const float *box_min,
                                       const float *box_max, const int64_t *win_lo,
                                       const int64_t *win_hi, pnb_grid **out);
+/* Slab exchange bookkeeping in ONE pass over the owned points (multi-GPU):
+ * cell layer cz = floor((z - padded_min_z) / cell_size) + 1 of the last coordinate (the reference's
+ * arithmetic, src/cell_lists/full_grid.jl:93) and three compacted index lists (0-based, unordered):
+ *   up_idx    points with cz >= z_hi (sent to rank + 1: migrants and its ghost layer), if has_up
+ *   down_idx  points with cz <= z_lo (sent to rank - 1), if has_down
+ *   leave_idx points with cz outside [z_lo, z_hi] (they leave this rank)
+ * Every list holds at most `cap` entries; counts[0..2] (host) are the true lengths, so a count
+ * above `cap` tells the caller to retry with larger lists.  Synchronises the stream. */
+pnb_status pnb_slab_classify_f32(const float *coords, int64_t n, int ndims, float padded_min_z,
+                                 float cell_size_z, int64_t z_lo, int64_t z_hi, int has_up,
+                                 int has_down, int32_t *up_idx, int32_t *down_idx,
+                                 int32_t *leave_idx, int64_t cap, int32_t *counts_dev,
+                                 int64_t *counts, void *stream);
+
+/* Structure-of-arrays particle state of one rank: n_arrays float arrays with a common leading
+ * (capacity) dimension, array a has width[a] floats per point; array 0 = coordinates. */
+typedef struct pnb_slab_arrays {
+    float *ptr[8];
+    int32_t width[8];
+    int32_t n_arrays;
+} pnb_slab_arrays;
+
+/* Step 1 of the per-step exchange: classify the n owned points (as pnb_slab_classify_f32) and
+ * gather the rows of the up / down lists into the contiguous send buffers (row = all arrays'
+ * columns of one point, row_width = sum of widths).  counts = {n_up, n_down, n_leave}; if one
+ * exceeds cap nothing is packed (retry with larger buffers).  leave_idx is kept for step 2. */
+pnb_status pnb_slab_pack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndims,
+                             float padded_min_z, float cell_size_z, int64_t z_lo, int64_t z_hi,
+                             int has_up, int has_down, int32_t *up_idx, int32_t *down_idx,
+                             int32_t *leave_idx, int64_t cap, float *send_up, float *send_down,
+                             int32_t *counts_dev, int64_t *counts, void *stream);
+
+/* Step 2, after the rows have been exchanged: emigrants' holes are filled from the tail
+ * (n_stay = n - n_leave owned points remain), received rows that belong to this slab are appended
+ * as owned points, then the ghosts: received rows one layer outside the slab and the rows this
+ * rank sent that are now one layer outside it.  scratch: >= 3 * n_leave + n_recv_up + n_recv_down
+ * + n_up + n_down + 16 int32.  The arrays must have room for n_stay + all four row counts.
+ * out = {n_own, n_local}.  Synchronises the stream. */
+pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndims,
+                               float padded_min_z, float cell_size_z, int64_t z_lo, int64_t z_hi,
+                               int has_up, int has_down, const int32_t *leave_idx, int64_t n_leave,
+                               const float *recv_up, int64_t n_recv_up, const float *recv_down,
+                               int64_t n_recv_down, const float *send_up, int64_t n_up,
+                               const float *send_down, int64_t n_down, int32_t *scratch,
+                               int64_t *out, void *stream);
 void pnb_grid_destroy(pnb_grid *g);
 int64_t pnb_grid_total_cells(const pnb_grid *g);
 int64_t pnb_grid_n_points(const pnb_grid *g); /* points in the cell list after the last build */

@@ -1253,3 +1253,277 @@ extern "C" pnb_status pnb_stream_synchronize(void *stream)
     PNB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return PNB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// slab exchange bookkeeping (multi-GPU)
+// ---------------------------------------------------------------------------------------------
+namespace pnb {
+__device__ __forceinline__ void warp_append(bool flag, int32_t value, int32_t *list, int64_t cap,
+                                            int32_t *counter)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m == 0u) return;
+    const int lane = lane_id();
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (flag) {
+        const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) list[pos] = value;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_classify(const float *__restrict__ coords, int64_t n, int nd, float pmin, float cs,
+                long long z_lo, long long z_hi, int has_up, int has_down,
+                int32_t *__restrict__ up_idx, int32_t *__restrict__ down_idx,
+                int32_t *__restrict__ leave_idx, int64_t cap, int32_t *__restrict__ counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool up = false, down = false, leave = false;
+    if (i < n) {
+        const float z = __ldg(coords + i * nd + (nd - 1));
+        const float f = floorf(__fdiv_rn(__fsub_rn(z, pmin), cs));   // full_grid.jl:93
+        // NaN / huge values stay here: the following update! reports them as a domain error
+        if (fabsf(f) < 4.0e18f) {
+            const long long cz = (long long)f + 1;
+            up = has_up && cz >= z_hi;
+            down = has_down && cz <= z_lo;
+            leave = cz < z_lo || cz > z_hi;
+        }
+    }
+    warp_append(up, (int32_t)i, up_idx, cap, counts + 0);
+    warp_append(down, (int32_t)i, down_idx, cap, counts + 1);
+    warp_append(leave, (int32_t)i, leave_idx, cap, counts + 2);
+}
+}  // namespace pnb
+
+extern "C" pnb_status pnb_slab_classify_f32(const float *coords, int64_t n, int ndims,
+                                            float padded_min_z, float cell_size_z, int64_t z_lo,
+                                            int64_t z_hi, int has_up, int has_down,
+                                            int32_t *up_idx, int32_t *down_idx, int32_t *leave_idx,
+                                            int64_t cap, int32_t *counts_dev, int64_t *counts,
+                                            void *stream)
+{
+    if (!counts || !counts_dev) { set_error("counts is NULL"); return PNB_ERR_ARG; }
+    if (ndims < 1 || ndims > 3) { set_error("`NDIMS` must be 1, 2, or 3"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    PNB_CUDA(cudaMemsetAsync(counts_dev, 0, 3 * sizeof(int32_t), s));
+    if (n > 0) {
+        k_slab_classify<<<(unsigned)div_up(n, 256), 256, 0, s>>>(
+            coords, n, ndims, padded_min_z, cell_size_z, (long long)z_lo, (long long)z_hi, has_up,
+            has_down, up_idx, down_idx, leave_idx, cap, counts_dev);
+        PNB_LAUNCHED();
+    }
+    int32_t h[3] = {0, 0, 0};
+    PNB_CUDA(cudaMemcpyAsync(h, counts_dev, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; k++) counts[k] = h[k];
+    return PNB_OK;
+}
+
+namespace pnb {
+
+__device__ __forceinline__ long long slab_layer(float z, float pmin, float cs)
+{
+    const float f = floorf(__fdiv_rn(__fsub_rn(z, pmin), cs));   // full_grid.jl:93
+    return fabsf(f) < 4.0e18f ? (long long)f + 1 : (long long)0x4000000000000000LL;
+}
+
+// row r of `list` -> dst[r * W ...]
+__global__ void __launch_bounds__(256)
+k_slab_pack(pnb_slab_arrays A, int W, const int32_t *__restrict__ list, int64_t count,
+            float *__restrict__ dst)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= count) return;
+    const int64_t i = list[r];
+    int col = 0;
+    for (int a = 0; a < A.n_arrays; a++) {
+        const int w = A.width[a];
+        for (int k = 0; k < w; k++) dst[r * W + col + k] = A.ptr[a][i * w + k];
+        col += w;
+    }
+}
+
+// classes of the exchanged rows: 1 = becomes an owned point (migrant), 2 = ghost, 0 = dropped.
+// cls[row] = class | rank << 2 with the rank taken from the class counter.
+//   counters: [0] migrants, [1] ghosts
+__global__ void __launch_bounds__(256)
+k_slab_rows_classify(const float *__restrict__ rows, int64_t count, int W, int nd, float pmin,
+                     float cs, long long lo_mig, long long hi_mig, long long ghost_layer,
+                     int32_t *__restrict__ cls, int32_t *__restrict__ counters)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    if (r < count) {
+        const long long cz = slab_layer(rows[r * W + (nd - 1)], pmin, cs);
+        if (cz >= lo_mig && cz <= hi_mig) c = 1;
+        else if (cz == ghost_layer) c = 2;
+    }
+    // warp-aggregated ranks
+    for (int k = 1; k <= 2; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, c == k);
+        if (m == 0u) continue;
+        int base = 0;
+        if (lane_id() == __ffs(m) - 1) base = atomicAdd(counters + (k - 1), __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (c == k) cls[r] = k | ((base + __popc(m & ((1u << lane_id()) - 1u))) << 2);
+    }
+    if (r < count && c == 0) cls[r] = 0;
+}
+
+// place classified rows: migrants at n_stay + rank, ghosts at n_stay + n_mig + rank
+__global__ void __launch_bounds__(256)
+k_slab_rows_place(pnb_slab_arrays A, int W, const float *__restrict__ rows, int64_t count,
+                  const int32_t *__restrict__ cls, int64_t n_stay,
+                  const int32_t *__restrict__ counters)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= count) return;
+    const int c = cls[r] & 3;
+    if (c == 0) return;
+    const int64_t rank = cls[r] >> 2;
+    const int64_t i = n_stay + (c == 2 ? (int64_t)counters[0] : 0) + rank;
+    int col = 0;
+    for (int a = 0; a < A.n_arrays; a++) {
+        const int w = A.width[a];
+        for (int k = 0; k < w; k++) A.ptr[a][i * w + k] = rows[r * W + col + k];
+        col += w;
+    }
+}
+
+// emigrants: holes = leaving points below n_stay, fillers = staying points of the tail
+__global__ void k_slab_mark_tail(const int32_t *__restrict__ leave, int64_t n_leave, int64_t n_stay,
+                                 int32_t *__restrict__ tailflag, int32_t *__restrict__ holes,
+                                 int32_t *__restrict__ counters)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hole = false;
+    int32_t v = 0;
+    if (r < n_leave) {
+        v = leave[r];
+        if (v >= n_stay) tailflag[v - n_stay] = 1;
+        else hole = true;
+    }
+    warp_append(hole, v, holes, n_leave, counters + 2);
+}
+__global__ void k_slab_fillers(int64_t n_tail, int64_t n_stay, const int32_t *__restrict__ tailflag,
+                               int32_t *__restrict__ fillers, int32_t *__restrict__ counters)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = t < n_tail && tailflag[t] == 0;
+    warp_append(f, (int32_t)(n_stay + t), fillers, n_tail, counters + 3);
+}
+__global__ void k_slab_fill(pnb_slab_arrays A, const int32_t *__restrict__ holes,
+                            const int32_t *__restrict__ fillers, const int32_t *__restrict__ counters)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= counters[2]) return;      // counters[2] == counters[3] by construction
+    const int64_t h = holes[r], f = fillers[r];
+    for (int a = 0; a < A.n_arrays; a++) {
+        const int w = A.width[a];
+        for (int k = 0; k < w; k++) A.ptr[a][h * w + k] = A.ptr[a][f * w + k];
+    }
+}
+}  // namespace pnb
+
+static int slab_row_width(const pnb_slab_arrays *A)
+{
+    int W = 0;
+    for (int a = 0; a < A->n_arrays; a++) W += A->width[a];
+    return W;
+}
+
+extern "C" pnb_status pnb_slab_pack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndims,
+                                        float padded_min_z, float cell_size_z, int64_t z_lo,
+                                        int64_t z_hi, int has_up, int has_down, int32_t *up_idx,
+                                        int32_t *down_idx, int32_t *leave_idx, int64_t cap,
+                                        float *send_up, float *send_down, int32_t *counts_dev,
+                                        int64_t *counts, void *stream)
+{
+    if (!arrays || arrays->n_arrays < 1 || arrays->n_arrays > 8 || arrays->width[0] != ndims) {
+        set_error("arrays[0] must be the coordinates (width = NDIMS), at most 8 arrays");
+        return PNB_ERR_ARG;
+    }
+    pnb_status st = pnb_slab_classify_f32(arrays->ptr[0], n, ndims, padded_min_z, cell_size_z, z_lo,
+                                          z_hi, has_up, has_down, up_idx, down_idx, leave_idx, cap,
+                                          counts_dev, counts, stream);
+    if (st != PNB_OK) return st;
+    if (counts[0] > cap || counts[1] > cap || counts[2] > cap) return PNB_OK;   // caller retries
+    cudaStream_t s = (cudaStream_t)stream;
+    const int W = slab_row_width(arrays);
+    if (counts[0] > 0) {
+        k_slab_pack<<<(unsigned)div_up(counts[0], 256), 256, 0, s>>>(*arrays, W, up_idx, counts[0], send_up);
+        PNB_LAUNCHED();
+    }
+    if (counts[1] > 0) {
+        k_slab_pack<<<(unsigned)div_up(counts[1], 256), 256, 0, s>>>(*arrays, W, down_idx, counts[1], send_down);
+        PNB_LAUNCHED();
+    }
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndims,
+                                          float padded_min_z, float cell_size_z, int64_t z_lo,
+                                          int64_t z_hi, int has_up, int has_down,
+                                          const int32_t *leave_idx, int64_t n_leave,
+                                          const float *recv_up, int64_t n_recv_up,
+                                          const float *recv_down, int64_t n_recv_down,
+                                          const float *send_up, int64_t n_up,
+                                          const float *send_down, int64_t n_down, int32_t *scratch,
+                                          int64_t *out, void *stream)
+{
+    if (!arrays || !out || !scratch) { set_error("NULL argument"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int W = slab_row_width(arrays);
+    const int64_t n_stay = n - n_leave;
+    // scratch layout (int32): counters[16] | tailflag[n_leave] | holes[n_leave] | fillers[n_leave]
+    //                         | cls of recv_up, recv_down, send_up, send_down
+    int32_t *counters = scratch;
+    int32_t *tailflag = scratch + 16;
+    int32_t *holes = tailflag + n_leave;
+    int32_t *fillers = holes + n_leave;
+    int32_t *cls_ru = fillers + n_leave;
+    int32_t *cls_rd = cls_ru + n_recv_up;
+    int32_t *cls_su = cls_rd + n_recv_down;
+    int32_t *cls_sd = cls_su + n_up;
+    PNB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * (size_t)(16 + n_leave), s));
+    if (n_leave > 0) {
+        const unsigned b = (unsigned)div_up(n_leave, 256);
+        k_slab_mark_tail<<<b, 256, 0, s>>>(leave_idx, n_leave, n_stay, tailflag, holes, counters);
+        PNB_LAUNCHED();
+        k_slab_fillers<<<b, 256, 0, s>>>(n_leave, n_stay, tailflag, fillers, counters);
+        PNB_LAUNCHED();
+        k_slab_fill<<<b, 256, 0, s>>>(*arrays, holes, fillers, counters);
+        PNB_LAUNCHED();
+    }
+    const long long BIG = 0x3fffffffffffffffLL;
+    // received from rank + 1: cz <= z_hi -> owned, cz == z_hi + 1 -> ghost
+    // received from rank - 1: cz >= z_lo -> owned, cz == z_lo - 1 -> ghost
+    // sent upwards / downwards and now one layer outside the slab -> my own ghosts
+    struct Src { const float *rows; int64_t n; int32_t *cls; long long lo, hi, ghost; };
+    const Src src[4] = {
+        {recv_up, n_recv_up, cls_ru, -BIG, (long long)z_hi, (long long)z_hi + 1},
+        {recv_down, n_recv_down, cls_rd, (long long)z_lo, BIG, (long long)z_lo - 1},
+        {send_up, has_up ? n_up : 0, cls_su, BIG, -BIG, (long long)z_hi + 1},
+        {send_down, has_down ? n_down : 0, cls_sd, BIG, -BIG, (long long)z_lo - 1}};
+    for (const Src &q : src) {
+        if (q.n <= 0) continue;
+        k_slab_rows_classify<<<(unsigned)div_up(q.n, 256), 256, 0, s>>>(
+            q.rows, q.n, W, ndims, padded_min_z, cell_size_z, q.lo, q.hi, q.ghost, q.cls, counters);
+        PNB_LAUNCHED();
+    }
+    for (const Src &q : src) {
+        if (q.n <= 0) continue;
+        k_slab_rows_place<<<(unsigned)div_up(q.n, 256), 256, 0, s>>>(*arrays, W, q.rows, q.n, q.cls,
+                                                                   n_stay, counters);
+        PNB_LAUNCHED();
+    }
+    int32_t h[2] = {0, 0};
+    PNB_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
+    out[0] = n_stay + h[0];
+    out[1] = n_stay + h[0] + h[1];
+    return PNB_OK;
+}

@@ -36,6 +36,11 @@ class WcsphParams(C.Structure):
                 ("delta", C.c_float), ("kernel_norm", C.c_float)]
 
 
+class SlabArrays(C.Structure):
+    """pnb_slab_arrays (include/pnb200.h)."""
+    _fields_ = [("ptr", C.c_void_p * 8), ("width", C.c_int32 * 8), ("n_arrays", C.c_int32)]
+
+
 _lib = None
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
@@ -51,6 +56,13 @@ SIGNATURES = {
     "pnb_grid_create_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, C.POINTER(_vp)]),
     "pnb_grid_create_window_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, _pi64, _pi64,
                                              C.POINTER(_vp)]),
+    "pnb_slab_classify_f32": (C.c_int, [_vp, _i64, C.c_int, _f32, _f32, _i64, _i64, C.c_int, C.c_int,
+                                        _vp, _vp, _vp, _i64, _vp, _pi64, _vp]),
+    "pnb_slab_pack_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
+                                    C.c_int, C.c_int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _pi64, _vp]),
+    "pnb_slab_unpack_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
+                                      C.c_int, C.c_int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                      _vp, _i64, _vp, _pi64, _vp]),
     "pnb_grid_destroy": (None, [_vp]),
     "pnb_grid_total_cells": (_i64, [_vp]),
     "pnb_grid_n_points": (_i64, [_vp]),

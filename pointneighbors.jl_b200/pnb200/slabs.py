@@ -149,6 +149,103 @@ class SlabExchange:
         (coords, state), n_own, n_local = self.exchange_inplace([coords, state], n)
         return torch.cat([coords[:n_local], state[:n_local]], dim=1).contiguous(), n_own
 
+    def _classify_cuda(self, coords, n, has_up, has_down):
+        """up / down / leave index lists (ascending int64) from pnb_slab_classify_f32."""
+        import torch
+        dev = coords.device
+        cap = getattr(self, "_idx_cap", 0)
+        while True:
+            if cap == 0:
+                cap = max(n // 8, 1 << 16)
+            if getattr(self, "_idx_bufs", None) is None or self._idx_bufs[0].numel() < cap:
+                self._idx_bufs = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
+                self._idx_counts = torch.zeros(4, dtype=torch.int32, device=dev)
+                self._idx_cap = cap
+            counts = (C.c_int64 * 3)()
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            check(_lib.lib().pnb_slab_classify_f32(
+                coords.data_ptr(), n, self.ndims, np.float32(self.padded_min[-1]),
+                np.float32(self.search_radius), self.z_lo, self.z_hi, int(has_up), int(has_down),
+                self._idx_bufs[0].data_ptr(), self._idx_bufs[1].data_ptr(),
+                self._idx_bufs[2].data_ptr(), cap, self._idx_counts.data_ptr(), counts, stream))
+            if max(counts) <= cap:
+                break
+            cap = int(max(counts)) + int(max(counts)) // 4 + 1024      # lists were too short: retry
+            self._idx_bufs = None
+        # ascending order like torch.nonzero (the lists come out of the kernel unordered)
+        return tuple(torch.sort(b[:int(c)]).values.to(torch.int64)
+                     for b, c in zip(self._idx_bufs, counts))
+
+    def _exchange_inplace_cuda(self, arrays, n):
+        """exchange_inplace on the device: two library calls (pnb_slab_pack_f32 before and
+        pnb_slab_unpack_f32 after the NCCL exchange) instead of ~100 torch operations per step.
+        The order of the points inside the owned / ghost ranges is not deterministic."""
+        import torch
+        L = _lib.lib()
+        coords = arrays[0]
+        dev = coords.device
+        has_up, has_down = self.rank + 1 < self.world, self.rank > 0
+        widths = [1 if a.ndim == 1 else a.shape[1] for a in arrays]
+        W = sum(widths)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        pmin, cs = np.float32(self.padded_min[-1]), np.float32(self.search_radius)
+
+        def table(arrs):
+            t = _lib.SlabArrays()
+            for k, (a, w) in enumerate(zip(arrs, widths)):
+                t.ptr[k] = a.data_ptr()
+                t.width[k] = w
+            t.n_arrays = len(arrs)
+            return t
+
+        cap = getattr(self, "_x_cap", 0) or max(n // 8, 1 << 16)
+        while True:
+            if getattr(self, "_x_bufs", None) is None or self._x_cap < cap:
+                self._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
+                self._x_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+                self._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
+                self._x_cap = cap
+            counts = (C.c_int64 * 3)()
+            tab = table(arrays)
+            check(L.pnb_slab_pack_f32(C.byref(tab), n, self.ndims, pmin, cs, self.z_lo, self.z_hi,
+                                      int(has_up), int(has_down), self._x_idx[0].data_ptr(),
+                                      self._x_idx[1].data_ptr(), self._x_idx[2].data_ptr(),
+                                      self._x_cap, self._x_bufs[0].data_ptr(),
+                                      self._x_bufs[1].data_ptr(), self._x_cnt.data_ptr(), counts,
+                                      stream))
+            if max(counts) <= self._x_cap:
+                break
+            cap = int(max(counts)) + int(max(counts)) // 4 + 1024
+        n_up, n_down, n_leave = (int(c) for c in counts)
+        send_up, send_down = self._x_bufs[0][:n_up], self._x_bufs[1][:n_down]
+        recv_up, recv_down = self._sendrecv(send_up, send_down)
+        n_ru, n_rd = recv_up.shape[0], recv_down.shape[0]
+        n_stay = n - n_leave
+        need = n_stay + n_ru + n_rd + n_up + n_down
+        if need > coords.shape[0]:
+            new_cap = need + need // 8 + 1024
+            grown = []
+            for a in arrays:
+                g = torch.empty((new_cap,) + tuple(a.shape[1:]), dtype=a.dtype, device=dev)
+                g[:n] = a[:n]
+                grown.append(g)
+            arrays = grown
+        n_scratch = 16 + 3 * n_leave + n_ru + n_rd + n_up + n_down + 16
+        if getattr(self, "_x_scratch", None) is None or self._x_scratch.numel() < n_scratch:
+            self._x_scratch = torch.empty(n_scratch + n_scratch // 4, dtype=torch.int32, device=dev)
+        out = (C.c_int64 * 2)()
+        tab = table(arrays)
+        check(L.pnb_slab_unpack_f32(C.byref(tab), n, self.ndims, pmin, cs, self.z_lo, self.z_hi,
+                                    int(has_up), int(has_down), self._x_idx[2].data_ptr(), n_leave,
+                                    recv_up.data_ptr(), n_ru, recv_down.data_ptr(), n_rd,
+                                    send_up.data_ptr(), n_up, send_down.data_ptr(), n_down,
+                                    self._x_scratch.data_ptr(), out, stream))
+        n_own, n_local = int(out[0]), int(out[1])
+        self.last_stats = {"sent_up": n_up, "sent_down": n_down, "ghosts": n_local - n_own,
+                           "migrated_in": n_own - n_stay, "migrated_out": n_leave,
+                           "bytes_sent": (n_up + n_down) * W * 4}
+        return arrays, n_own, n_local
+
     def exchange_inplace(self, arrays, n):
         """Structure-of-arrays form used every step.  arrays: list of float32 tensors with a
         common leading capacity dimension, arrays[0] = coordinates (cap, ndims), the others (cap,)
@@ -161,12 +258,23 @@ class SlabExchange:
         nd = self.ndims
         coords = arrays[0]
         dev = coords.device
+        if coords.is_cuda and all(a.dtype == torch.float32 and a.is_contiguous() for a in arrays) \
+                and len(arrays) <= 8 and not getattr(self, "force_torch_path", False):
+            return self._exchange_inplace_cuda(arrays, n)
         has_up, has_down = self.rank + 1 < self.world, self.rank > 0
         widths = [1 if a.ndim == 1 else a.shape[1] for a in arrays]
-        cz = self.cell_layer(coords[:n])
         empty = torch.zeros(0, dtype=torch.int64, device=dev)
-        up_idx = torch.nonzero(cz >= self.z_hi).flatten() if has_up else empty
-        down_idx = torch.nonzero(cz <= self.z_lo).flatten() if has_down else empty
+        if coords.is_cuda:
+            # one pass of the library over the owned points instead of ~12 elementwise / nonzero
+            # passes (and three host synchronisations) of torch
+            up_idx, down_idx, leave_idx = self._classify_cuda(coords, n, has_up, has_down)
+        else:
+            cz = self.cell_layer(coords[:n])
+            up_idx = torch.nonzero(cz >= self.z_hi).flatten() if has_up else empty
+            down_idx = torch.nonzero(cz <= self.z_lo).flatten() if has_down else empty
+            leave_idx = torch.nonzero((cz < self.z_lo) | (cz > self.z_hi)).flatten()
+        cz_up = self.cell_layer(coords[up_idx])
+        cz_down = self.cell_layer(coords[down_idx])
 
         def pack(idx):
             return torch.cat([a[idx].reshape(idx.numel(), w) for a, w in zip(arrays, widths)],
@@ -177,14 +285,13 @@ class SlabExchange:
         cz_u = self.cell_layer(recv_up[:, :nd])
         cz_d = self.cell_layer(recv_down[:, :nd])
         # what I sent and is now one layer outside my slab stays with me as a ghost
-        my_ghost_up = send_up[cz[up_idx] == self.z_hi + 1] if has_up else send_up[:0]
-        my_ghost_down = send_down[cz[down_idx] == self.z_lo - 1] if has_down else send_down[:0]
+        my_ghost_up = send_up[cz_up == self.z_hi + 1] if has_up else send_up[:0]
+        my_ghost_down = send_down[cz_down == self.z_lo - 1] if has_down else send_down[:0]
         mig_in = torch.cat([recv_up[cz_u <= self.z_hi], recv_down[cz_d >= self.z_lo]])
         ghosts = torch.cat([recv_down[cz_d == self.z_lo - 1], my_ghost_down,
                             recv_up[cz_u == self.z_hi + 1], my_ghost_up])
         # emigrants: fill their holes from the tail (swap-with-last, like deleteatat!,
         # src/vector_of_vectors.jl:123-139)
-        leave_idx = torch.nonzero((cz < self.z_lo) | (cz > self.z_hi)).flatten()
         n_leave = int(leave_idx.numel())
         n_stay = n - n_leave
         if n_leave:
@@ -309,13 +416,22 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     del A, B, vfull, cand, vel, rho, mass, pressure
     h = T(r / T(2))
 
-    def step(s, count_only=False):
+    phase_ev = []
+
+    def step(s, count_only=False, timed=False):
         k = (s + 1) % 2
+        if timed:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs[0].record()
         bufs[k], n_own, nl = ex.exchange_inplace(bufs[k], n_cur[k])
         n_cur[k] = n_own
         cbuf, vbuf, mbuf, pbuf = bufs[k]
         coords = cbuf[:nl]
+        if timed:
+            evs[1].record()
         slab.update_(coords)
+        if timed:
+            evs[2].record()
         if count_only:
             cnt = torch.zeros(nl, dtype=torch.int64, device=dev)
             pn.foreach_point_neighbor(pn.CountNeighbors(cnt), coords, coords, slab.nhs)
@@ -324,6 +440,9 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
         dv = torch.empty((nl, 4), device=dev, dtype=torch.float32)
         f = pn.WCSPHInteract(dv, v, v, m, m, p, p, smoothing_length=h, sound_speed=T(10.0))
         pn.foreach_point_neighbor(f, coords, coords, slab.nhs)
+        if timed:
+            evs[3].record()
+            phase_ev.append(evs)
         return dv[:n_own], n_own
 
     pairs = [0, 0]
@@ -333,20 +452,37 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
         step(s)
     torch.cuda.synchronize()
     dist.barrier()
+    import os
+    if os.environ.get("PNB_PROFILE_EXCHANGE") and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for s in range(4):
+                step(s)
+            torch.cuda.synchronize()
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/exchange_prof_rank0.txt", "w") as fh:
+            fh.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45))
+    elif os.environ.get("PNB_PROFILE_EXCHANGE"):
+        for s in range(4):
+            step(s)
+    torch.cuda.synchronize()
+    dist.barrier()
     launches0 = int(_lib.lib().pnb_launch_count())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
     my_pairs = 0
     for s in range(args.steps):
-        step(s)
+        step(s, timed=True)
         my_pairs += pairs[(s + 1) % 2]
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in phase_ev]).mean(0)
     t = torch.tensor([ms, float(my_pairs), float(N), float(ex.last_stats.get("bytes_sent", 0)),
-                      float(ex.last_stats.get("ghosts", 0))], device=dev, dtype=torch.float64)
+                      float(ex.last_stats.get("ghosts", 0)), float(phases[0]), float(phases[1]),
+                      float(phases[2])], device=dev, dtype=torch.float64)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone()
@@ -367,6 +503,8 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
                        "ghost_points_per_rank_max": int(tmax[4]),
                        "exchange_bytes_per_rank_max": int(tmax[3]),
                        "l2": "per-GPU inputs larger than the 126 MB L2"},
+            "phase_ms_max_over_ranks": {"exchange": float(tmax[5]), "update": float(tmax[6]),
+                                        "interact": float(tmax[7])},
             "gpu_launches": launches,
             "e2e": None,
             "note": "device-resident multi-GPU step; the host-buffer e2e number is measured at N = 1",
