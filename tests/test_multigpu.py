@@ -95,3 +95,12 @@ def test_two_gpu_slabs_match_oracle(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def test_four_gpu_slabs_match_oracle(tmp_path):
+    """Interior ranks exchange with two neighbours (both directions of pnb_slab_pack/unpack)."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(4, _free_port(), str(tmp_path)), nprocs=4, join=True)
+    assert (tmp_path / "ok").exists()
