@@ -795,3 +795,52 @@ def test_two_sets_tile_path(pn, oracle, periodic):
         x_bad[11] = mx + 10 * r
         with pytest.raises(pn.BoundsError):
             pn.foreach_point_neighbor(pn.CountNeighbors(cnt), dev(x_bad), ty, nhs)
+
+
+def test_two_sets_edge_cases(pn, oracle):
+    """Two-set tile path on awkward inputs: query cells with more than 32 points (several passes),
+    candidate tiles beyond the staging capacity (overflow kernel with a separate query list),
+    queries in cells that hold no candidates, empty and tiny query sets."""
+    T = np.float32
+    mn, mx = np.zeros(3, T), np.ones(3, T)
+    r = T(0.1)
+    rng = np.random.default_rng(44)
+    # candidates: a dense blob (tiles overflow) + a sparse background
+    y = np.concatenate([0.5 + 0.05 * rng.random((3000, 3)), rng.random((3000, 3))]).astype(T)
+    # queries: a blob overlapping the candidates' blob (> 32 per cell), a blob in an empty corner
+    # of the background, and scattered points
+    x = np.concatenate([0.48 + 0.08 * rng.random((2500, 3)), 0.05 + 0.02 * rng.random((1500, 3)),
+                        rng.random((2000, 3))]).astype(T)
+    og = oracle.Grid(3, r, mn, mx)
+    og.build(y)
+    cnt_o = og.count_neighbors(x, y)
+    off_o, ids_o = og.neighbor_lists(x, y, sort=True)
+    mass, G = _nbody_inputs(len(y))
+    _, r64, rabs = og.nbody(x, y, mass, G, wide=True)
+    nhs = make_grid(pn, 3, r, mn, mx)
+    tx, ty = dev(x), dev(y)
+    pn.initialize_(nhs, tx, ty)
+    L = pn._lib.lib()
+    try:
+        for mode in (2, 0):
+            L.pnb_set_twoset_tiles(mode)
+            cnt = torch.full((len(x),), -3, dtype=torch.int64, device="cuda")
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), tx, ty, nhs)
+            assert (cnt.cpu().numpy() == cnt_o).all(), mode
+            lists = pn.api._NeighborLists.build(nhs, tx, ty, sort=True)
+            off, ids = lists.export_csr(0)
+            assert (off.cpu().numpy() == off_o).all() and (ids.cpu().numpy() == ids_o).all(), mode
+            dv = torch.zeros((len(x), 3), dtype=torch.float32, device="cuda")
+            pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), G), tx, ty, nhs)
+            assert np.all(np.abs(dv.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30), mode
+        L.pnb_set_twoset_tiles(2)
+        # empty and tiny query sets (below the tile path's threshold: per-point kernel)
+        e = torch.zeros((0, 3), dtype=torch.float32, device="cuda")
+        pn.foreach_point_neighbor(pn.CountNeighbors(torch.zeros(0, dtype=torch.int64, device="cuda")),
+                                  e, ty, nhs)
+        few = dev(x[:7])
+        c7 = torch.zeros(7, dtype=torch.int64, device="cuda")
+        pn.foreach_point_neighbor(pn.CountNeighbors(c7), few, ty, nhs)
+        assert (c7.cpu().numpy() == cnt_o[:7]).all()
+    finally:
+        L.pnb_set_twoset_tiles(1)
