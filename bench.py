@@ -397,8 +397,11 @@ def gpu_arm(args):
     sweep_avg = sweep_ms / max(sweep_n, 1)
     bytes_sweep = 56 * N + 4 * (C_cells + 1)          # WCSPH interact
     ach = bytes_sweep / (sweep_avg * 1e-3) / 1e9
-    build_names = ["k_cell_hist", "k_scan_lookback", "k_scatter_points"]
-    build_ms = sum(prof[k][0] for k in build_names) / max(prof["k_cell_hist"][1], 1)
+    # update! = one-pass bucket build (k_bucket_scatter) after the first build; the two-pass CSR
+    # build (hist + scan + scatter) when a cell overflowed its bucket or PNB_BUILD_LAYOUT=0
+    build_names = [k for k in ("k_bucket_scatter", "k_cell_hist", "k_scan_lookback", "k_scatter_points")
+                   if prof.get(k, (0.0, 0))[1]]
+    build_ms = sum(prof[k][0] for k in build_names) / args.steps
     bytes_update = 28 * N + 4 * (C_cells + 1)          # 16N + 4(C+1) + 12N (cell-ordered coordinates)
     ach_u = bytes_update / (build_ms * 1e-3) / 1e9
     P_avg = float(np.mean(pairs))
@@ -445,9 +448,12 @@ def gpu_arm(args):
                             "peak": hbm_peak, "unit": "GB/s", "frac": ach_u / hbm_peak,
                             # profiles/r1_update_v3_ncu_summary.txt: hist 199.8 + 4.9 MB,
                             # scan 2.7 MB, scatter 200.5 + 214.9 MB
-                            "traffic": 622800000 if n == 254 else None,
+                            "traffic": None,
                             "device_ms": build_ms, "algorithmic_bytes": bytes_update,
-                            "per_kernel_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in build_names}},
+                            "per_kernel_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in build_names},
+                            "call_ms": update_ms,
+                            "layout": "buckets (one pass)" if "k_bucket_scatter" in build_names
+                                      else "CSR (two passes)"},
         "kernel_ms": {k: (v_[0] / v_[1] if v_[1] else 0.0) for k, v_ in prof.items()},
     }
     if not args.no_cpu_baseline:

@@ -192,6 +192,10 @@ void pnb_set_twoset_tiles(int on);
  * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with
  * lane runs; default 25).  Results are identical for every setting. */
 void pnb_set_build_tuning(int variant);
+/* 1 (default): builds after the first one use the one-pass bucket layout (every cell owns K record
+ * slots, K from the fullest cell of the last CSR build; a cell that overflows falls back to the
+ * two-pass CSR build); 0: always the two-pass CSR build.  Same results. */
+void pnb_set_build_layout(int buckets);
 
 /* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */
 pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,

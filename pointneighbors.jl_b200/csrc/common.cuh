@@ -68,6 +68,7 @@ enum Phase {
     PH_NLIST_SORT,            // k_sort_lists
     PH_NLIST_SWEEP,           // k_tlsph_defgrad / k_nlist_pairs
     PH_EXPORT,                // export kernels
+    PH_BUILD_BUCKET,          // k_bucket_scatter (one-pass update!)
     PH_COUNT_
 };
 struct ProfScope {
@@ -197,6 +198,21 @@ __device__ __forceinline__ float maybe_periodic_fix(const PerP &q, float d2, flo
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// The cell list as the kernels see it.  Two layouts:
+//   CSR     (K == 0): start[0 .. C] offsets, cell c = rec[start[c] .. start[c+1])
+//   buckets (K  > 0): start[c] = number of points of cell c, cell c = rec[c K .. c K + start[c])
+//           (what the one-pass update! writes: every cell owns K record slots)
+struct CellsView {
+    const uint32_t *start;
+    const float4 *rec;
+    uint32_t K;
+};
+__device__ __forceinline__ void cell_range(const CellsView &v, int lin, uint32_t &b0, uint32_t &cnt)
+{
+    if (v.K) { b0 = (uint32_t)lin * v.K; cnt = v.start[lin]; }
+    else { b0 = v.start[lin]; cnt = v.start[lin + 1] - b0; }
+}
 
 #endif  // __CUDACC__
 

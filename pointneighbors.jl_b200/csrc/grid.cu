@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -83,7 +84,8 @@ static void prof_collect()
 
 static const char *kPhaseNames[PH_COUNT_] = {
     "k_cell_hist", "k_scan_lookback", "k_scatter_points", "k_canonicalize", "k_gather",
-    "k_sweep_cells", "k_sweep_overflow", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export"};
+    "k_sweep_cells", "k_sweep_overflow", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export",
+    "k_bucket_scatter"};
 
 static const char *kDomainMsg =
     "particle coordinates are NaN or outside the domain bounds of the cell list";
@@ -99,6 +101,7 @@ pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
     int e = *(volatile int *)g->h_err;
     if (e == 0) return PNB_OK;
     *(volatile int *)g->h_err = 0;
+    e &= ~8;   // bit 3 (bucket overflow) is consumed by the build itself
     if (e & 1) { set_error("%s", kDomainMsg); return PNB_ERR_DOMAIN; }
     if (e & 4) { set_error("%s", kListFullMsg); return PNB_ERR_LIST_FULL; }
     set_error("%s", kBoundsMsg);
@@ -343,6 +346,9 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->cell_start_alloc);
     cudaFree(g->xq_start_alloc);
     cudaFree(g->xq_sorted);
+    cudaFree(g->bcount);
+    cudaFree(g->brec);
+    cudaFree(g->d_maxcount);
     cudaFree(g->cell_count);
     cudaFree(g->cell_points);
     cudaFree(g->sorted);
@@ -374,6 +380,14 @@ extern "C" int64_t pnb_grid_n_points(const pnb_grid *g) { return g ? g->n_built 
 // ---------------------------------------------------------------------------------------------
 namespace pnb {
 
+// 1 = update! may use the one-pass bucket layout, 0 = always CSR, 2 = (tests) every build ends in
+// the bucket layout; PNB_BUILD_LAYOUT in the environment overrides the default
+static int initial_build_layout()
+{
+    const char *e = getenv("PNB_BUILD_LAYOUT");
+    return e ? atoi(e) : 1;
+}
+int g_build_layout = initial_build_layout();
 int g_tune_build = 25;   // measurement variants of the build kernels (pnb_set_build_tuning)
 constexpr int kBuildThreads = 256;
 constexpr int kBuildPPT = 4;                                // points per thread
@@ -917,6 +931,118 @@ pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *o
     return scan_impl<int64_t, false, true>(g, const_cast<uint32_t *>(in), out, n, s);
 }
 
+// ---------------------------------------------------------------------------------------------
+// one-pass update!: every cell owns K record slots ("buckets", the reference's own idea --
+// its cell matrix is 100 x C, src/cell_lists/full_grid.jl:74-78 -- with K chosen from the data).
+// One kernel: read the coordinates (12 N), cell index, the run head takes the cell's counter
+// (ATOM.ADD returns the first free slot), records stored at cell * K + slot (16 N).  No
+// histogram pass, no scan: 28 N + 4 C bytes, exactly the algorithmic minimum of SURVEY 8d.
+// A cell that receives more than K points sets error bit 3; the build is then redone as CSR.
+// ---------------------------------------------------------------------------------------------
+template <int ND, bool PER>
+__global__ void __launch_bounds__(kBuildThreads)
+k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
+                 const int32_t *__restrict__ idx, int base, uint32_t K,
+                 uint32_t *__restrict__ bcount, float4 *__restrict__ brec, int *__restrict__ err)
+{
+    const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
+    const int logK = 31 - __clz((int)K);            // K is a power of two
+    if (idx == nullptr && block0 + kBuildTile <= n_idx) {
+        // full tile: no bounds checks, all atomics of a thread's points before the first store
+        float p[kBuildPPT][3];
+        int lin[kBuildPPT], h[kBuildPPT], rl[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const int64_t k = block0 + j * kBuildThreads + (int)threadIdx.x;
+#pragma unroll
+            for (int d = 0; d < 3; d++) p[j][d] = d < ND ? __ldg(y + k * ND + d) : 0.f;
+        }
+        int bad = 0;
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            lin[j] = point_cell_fast<ND, PER>(g, bp, p[j]);
+            if (lin[j] < 0) bad |= 1;
+            h[j] = run_head(lin[j], lin[j] >= 0, &rl[j]);
+        }
+        unsigned basev[kBuildPPT];
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++)
+            basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(bcount + lin[j], (unsigned)rl[j]) : 0u;
+#pragma unroll
+        for (int j = 0; j < kBuildPPT; j++) {
+            const unsigned b = __shfl_sync(0xffffffffu, basev[j], h[j] & 31);
+            if (lin[j] >= 0) {
+                const unsigned slot = b + (unsigned)(lane_id() - h[j]);
+                const int32_t id = (int32_t)(block0 + j * kBuildThreads + (int)threadIdx.x);
+                if (slot < K)
+                    brec[((size_t)lin[j] << logK) + slot] = make_float4(p[j][0], p[j][1], p[j][2], __int_as_float(id));
+                else
+                    bad |= 8;
+            }
+        }
+        if (bad) atomicOr(err, bad);
+        return;
+    }
+    float p[kBuildPPT][3];
+    int32_t id[kBuildPPT];
+    bool in[kBuildPPT];
+#pragma unroll
+    for (int j = 0; j < kBuildPPT; j++) {
+        const int64_t k = block0 + j * kBuildThreads + (int)threadIdx.x;
+        in[j] = k < n_idx;
+        id[j] = (int32_t)k;
+        if (in[j] && idx) id[j] = idx[k] - base;
+#pragma unroll
+        for (int d = 0; d < 3; d++) p[j][d] = (in[j] && d < ND) ? __ldg(y + (int64_t)id[j] * ND + d) : 0.f;
+    }
+    int lin[kBuildPPT], h[kBuildPPT], rl[kBuildPPT];
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < kBuildPPT; j++) {
+        lin[j] = in[j] ? point_cell_fast<ND, PER>(g, bp, p[j]) : -1;
+        if (in[j] && lin[j] < 0) bad |= 1;
+        h[j] = run_head(lin[j], lin[j] >= 0, &rl[j]);
+    }
+    unsigned basev[kBuildPPT];
+#pragma unroll
+    for (int j = 0; j < kBuildPPT; j++)
+        basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(bcount + lin[j], (unsigned)rl[j]) : 0u;
+#pragma unroll
+    for (int j = 0; j < kBuildPPT; j++) {
+        const unsigned b = __shfl_sync(0xffffffffu, basev[j], h[j] & 31);
+        if (lin[j] >= 0) {
+            const unsigned slot = b + (unsigned)(lane_id() - h[j]);
+            if (slot < K)
+                brec[((size_t)lin[j] << logK) + slot] = make_float4(p[j][0], p[j][1], p[j][2], __int_as_float(id[j]));
+            else
+                bad |= 8;
+        }
+    }
+    if (bad) atomicOr(err, bad);
+}
+
+// buckets -> CSR records (one warp per cell), after the scan of the bucket counts
+__global__ void __launch_bounds__(256)
+k_bucket_to_csr(int total_cells, uint32_t K, const uint32_t *__restrict__ bcount,
+                const float4 *__restrict__ brec, const uint32_t *__restrict__ cell_start,
+                float4 *__restrict__ sorted)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= total_cells) return;
+    const uint32_t cnt = bcount[c], s0 = cell_start[c];
+    for (uint32_t e = lane_id(); e < cnt; e += 32) sorted[s0 + e] = brec[(size_t)c * K + e];
+}
+
+// fullest cell of a CSR cell list -> out[0]
+__global__ void k_max_cell_count(int64_t n_cells, const uint32_t *__restrict__ start,
+                                 unsigned int *__restrict__ out)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = c < n_cells ? start[c + 1] - start[c] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (lane_id() == 0 && v > 0u) atomicMax(out, v);
+}
+
 static pnb_status ensure_point_capacity(pnb_grid *g, int64_t n)
 {
     if (n <= g->cap_points) return PNB_OK;
@@ -933,9 +1059,34 @@ static pnb_status ensure_point_capacity(pnb_grid *g, int64_t n)
 // Sort every cell by point id (once per build, on demand): the CSR id list `cell_points` and
 // the cell-ordered records become reproducible (ids ascending inside a cell), which is what the
 // exports, the exact arithmetic mode and the neighbour-list fills are specified against.
+// CSR offsets and records from the bucket layout (consumers other than the tile kernels: the
+// exports, the ordered / per-point sweeps, the canonical order).
+pnb_status ensure_csr(pnb_grid *g, cudaStream_t s)
+{
+    if (g->csr_valid || !g->built || !g->bucket_valid) return PNB_OK;
+    const int64_t C = g->p.total_cells;
+    // exclusive prefix of the bucket counts = CSR offsets, total at cell_start[C]
+    pnb_status st = scan_impl<uint32_t, false, true>(g, g->bcount, g->cell_start, C, s);
+    if (st != PNB_OK) return st;
+    if (C > 0 && g->n_built > 0) {
+        ProfScope ps(PH_BUILD_FINALIZE, s);
+        k_bucket_to_csr<<<(unsigned)div_up(C * 32, 256), 256, 0, s>>>(
+            (int)C, (uint32_t)g->bucket_K, g->bcount, g->brec, g->cell_start, g->sorted);
+        PNB_LAUNCHED();
+    }
+    g->csr_valid = true;
+    return PNB_OK;
+}
+
 pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s)
 {
     if (g->canonical || !g->built || g->template_search || g->n_built == 0) return PNB_OK;
+    {
+        pnb_status stc = ensure_csr(g, s);
+        if (stc != PNB_OK) return stc;
+        // the canonical order lives in the CSR arrays: the tile kernels switch to them
+        g->bucket_valid = false;
+    }
     if (!g->sorted_alt) PNB_CUDA(cudaMalloc(&g->sorted_alt, sizeof(float4) * (size_t)g->cap_points));
     if (!g->cell_points) PNB_CUDA(cudaMalloc(&g->cell_points, sizeof(int32_t) * (size_t)g->cap_points));
     const int64_t C = g->p.total_cells;
@@ -1047,6 +1198,7 @@ pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *poi
 }  // namespace pnb
 
 extern "C" void pnb_set_build_tuning(int variant) { pnb::g_tune_build = variant; }
+extern "C" void pnb_set_build_layout(int buckets) { pnb::g_build_layout = buckets; }
 
 extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                                          const int32_t *eachindex_y, int64_t n_idx, int index_base,
@@ -1068,6 +1220,8 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         g->y_built = y;
         g->n_y_built = n;
         g->full_build = false;
+        g->bucket_valid = false;
+        g->csr_valid = true;
         return PNB_OK;
     }
     if (n_idx > 0x7ffffff0LL || n > 0x7ffffff0LL) {
@@ -1077,6 +1231,56 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
     if (n_idx > 0 && y == nullptr) { set_error("y is NULL"); return PNB_ERR_ARG; }
     pnb_status st = ensure_point_capacity(g, n_idx);
     if (st != PNB_OK) return st;
+    g->bucket_valid = false;
+    g->csr_valid = false;
+    // ---- one-pass build into the bucket layout (K chosen by the previous CSR build) -----------
+    if (g_build_layout != 0 && g->bucket_K > 0 && n_idx > 0 && C > 0) {
+        const int64_t slots = C * (int64_t)g->bucket_K;
+        if (slots > g->brec_slots) {
+            cudaFree(g->brec);
+            g->brec = nullptr;
+            g->brec_slots = 0;
+            PNB_CUDA(cudaMalloc(&g->brec, sizeof(float4) * (size_t)slots));
+            g->brec_slots = slots;
+        }
+        if (!g->bcount) PNB_CUDA(cudaMalloc(&g->bcount, sizeof(uint32_t) * (size_t)(C + 4)));
+        BuildP bp;
+        for (int d = 0; d < 3; d++) { volatile float rc = 1.0f / g->p.cs[d]; bp.rcs[d] = rc; }
+        const unsigned blocks = (unsigned)div_up(n_idx, kBuildTile);
+        {
+            ProfScope ps(PH_BUILD_BUCKET, s);     // the clearing of the counters is part of it
+            PNB_CUDA(cudaMemsetAsync(g->bcount, 0, sizeof(uint32_t) * (size_t)C, s));
+#define PNB_BUCKET(ND, PER)                                                                        \
+    k_bucket_scatter<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y,    \
+                                                               index_base, (uint32_t)g->bucket_K,  \
+                                                               g->bcount, g->brec, g->d_err)
+            const bool per = g->p.periodic != 0;
+            switch (g->p.ndims) {
+                case 1: if (per) PNB_BUCKET(1, true); else PNB_BUCKET(1, false); break;
+                case 2: if (per) PNB_BUCKET(2, true); else PNB_BUCKET(2, false); break;
+                default: if (per) PNB_BUCKET(3, true); else PNB_BUCKET(3, false); break;
+            }
+#undef PNB_BUCKET
+            PNB_LAUNCHED();
+        }
+        PNB_CUDA(cudaStreamSynchronize(s));     // initialize!/update! are blocking calls
+        const int e = *(volatile int *)g->h_err;
+        if ((e & 8) == 0) {
+            st = check_err_word(g, s);
+            if (st != PNB_OK) { g->n_built = 0; return st; }
+            g->bucket_valid = true;
+            g->n_built = n_idx;
+            g->y_built = y;
+            g->n_y_built = n;
+            g->full_build = (eachindex_y == nullptr);
+            g->built = true;
+            return PNB_OK;
+        }
+        // a cell overflowed its bucket: rebuild as CSR below (which also picks a larger K);
+        // a domain error found on the way is reported by that build again
+        *(volatile int *)g->h_err = 0;
+        g->bucket_K = 0;
+    }
     switch (g->p.ndims) {
         case 1: st = g->p.periodic ? build_nd<1, true>(g, y, n, eachindex_y, n_idx, index_base, s)
                                    : build_nd<1, false>(g, y, n, eachindex_y, n_idx, index_base, s); break;
@@ -1086,17 +1290,48 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                                     : build_nd<3, false>(g, y, n, eachindex_y, n_idx, index_base, s); break;
     }
     if (st != PNB_OK) return st;
+    // fullest cell -> bucket capacity of the following one-pass builds
+    unsigned int fullest = 0;
+    if (g_build_layout != 0 && C > 0 && n_idx > 0) {
+        if (!g->d_maxcount) PNB_CUDA(cudaMalloc(&g->d_maxcount, sizeof(unsigned int)));
+        PNB_CUDA(cudaMemsetAsync(g->d_maxcount, 0, sizeof(unsigned int), s));
+        k_max_cell_count<<<(unsigned)div_up(C, 256), 256, 0, s>>>(C, g->cell_start, g->d_maxcount);
+        PNB_LAUNCHED();
+        PNB_CUDA(cudaMemcpyAsync(g->h_err + 1, g->d_maxcount, sizeof(unsigned int),
+                                 cudaMemcpyDeviceToHost, s));
+    }
     st = check_err_word(g, s);  // also synchronizes: initialize!/update! are blocking calls
     if (st != PNB_OK) {
         // like the reference, a failed build leaves an unusable cell list behind
         g->n_built = 0;
         return st;
     }
+    if (g_build_layout != 0 && C > 0 && n_idx > 0) {
+        fullest = *(volatile unsigned int *)(g->h_err + 1);
+        // 25 % + 4 slots of head room, rounded up to a power of two (slot -> cell is a shift);
+        // only while the slots cost at most ~4x the records themselves (sparse grids with a few
+        // crowded cells stay CSR)
+        int64_t K = 16;
+        while (K < (int64_t)fullest + fullest / 4 + 4) K *= 2;
+        g->bucket_K = (C * K <= 4 * n_idx + (1 << 20)) ? (int)K : 0;
+    }
+    g->csr_valid = true;
     g->n_built = n_idx;
     g->y_built = y;
     g->n_y_built = n;
     g->full_build = (eachindex_y == nullptr);
     g->built = true;
+    if (g_build_layout == 2 && g->bucket_K > 0) {
+        // test mode: rebuild at once into the bucket layout, so that every consumer is
+        // exercised on it even after a first build
+        static thread_local bool nested = false;
+        if (!nested) {
+            nested = true;
+            pnb_status st2 = pnb_grid_build_f32(g, y, n, eachindex_y, n_idx, index_base, stream);
+            nested = false;
+            return st2;
+        }
+    }
     return PNB_OK;
 }
 

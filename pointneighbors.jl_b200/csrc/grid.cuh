@@ -25,6 +25,16 @@ struct pnb_grid {
     int64_t cap_points;
     bool canonical;         // records inside every cell are ordered by point id (ensure_canonical)
 
+    // bucket layout written by the one-pass update!: every cell owns bucket_K
+    // record slots, bcount[c] of them are used.  Valid instead of / next to the CSR arrays.
+    uint32_t *bcount;        // [C]
+    float4 *brec;            // [brec_slots] = C * bucket_K
+    int64_t brec_slots;
+    int bucket_K;            // 0 = not chosen yet (the next CSR build picks it from the fullest cell)
+    bool bucket_valid;       // bcount / brec describe the current build
+    bool csr_valid;          // cell_start / sorted describe the current build
+    unsigned int *d_maxcount;   // [1] device scratch
+
     // cell-ordered copy of the query points of a two-set sweep (x != y), built per sweep
     uint32_t *xq_start_alloc, *xq_start;   // [C+1]
     float4 *xq_sorted;                     // [xq_cap]
@@ -63,7 +73,14 @@ pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
 pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *points_per_cell,
                             cudaStream_t s);  // two-set sweeps
-pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s); // ids ascending inside every cell + cell_points
+pnb_status ensure_csr(pnb_grid *g, cudaStream_t s);       // CSR arrays from the bucket layout
+pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s);
+// the cell list for the tile kernels: buckets if that is what the last build wrote, else CSR
+static inline pnb::CellsView cells_view(const pnb_grid *g)
+{
+    if (g->bucket_valid) return pnb::CellsView{g->bcount, g->brec, (uint32_t)g->bucket_K};
+    return pnb::CellsView{g->cell_start, g->sorted, 0u};
+} // ids ascending inside every cell + cell_points
 pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
                               cudaStream_t s);
 pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *out, int64_t n,

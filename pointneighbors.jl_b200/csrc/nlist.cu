@@ -512,6 +512,12 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     NL_CUDA(cudaMemsetAsync(l->counts, 0, sizeof(uint32_t) * (size_t)(nx + 8), s));
     const bool fast = g->full_build && x == g->y_built && nx == g->n_y_built;
     pnb_status st = PNB_OK;
+    if (!fast && g->bucket_valid) {
+        // two-set and per-point list builds walk the CSR arrays
+        st = ensure_csr(g, s);
+        if (st != PNB_OK) return fail(st);
+        g->bucket_valid = false;
+    }
     if (!sort) {
         // unsorted lists keep the visiting order: make it the reproducible one (ids ascending
         // inside every cell); sorted lists do not depend on it

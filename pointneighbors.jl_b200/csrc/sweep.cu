@@ -10,22 +10,31 @@ namespace pnb {
 
 // payload of the neighbour points gathered into cell order (one coalesced pass), so that the
 // staging loops of k_sweep_cells read contiguous memory.
-// ids are the .w field of the cell-ordered records (no separate id list on this path)
-__global__ void k_gather_f32(int64_t n, const float4 *__restrict__ sorted,
-                             const float *__restrict__ src, float *__restrict__ dst)
+// Slots of the cell list: CSR -> records 0 .. n-1; buckets -> C * K slots of which the first
+// start[cell] of every cell are records.  The payload arrays use the same slot numbering.
+__device__ __forceinline__ bool slot_valid(const CellsView &v, int64_t slot)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __ldg(src + __float_as_int(__ldg(&sorted[i].w)));
+    if (v.K == 0) return true;
+    const uint32_t sl = (uint32_t)slot;             // C * K < 2^32; K is a power of two
+    return (sl & (v.K - 1u)) < v.start[sl >> (31 - __clz((int)v.K))];
 }
 
-__global__ void k_gather_wcsph(int64_t n, int nd, const float4 *__restrict__ sorted,
+// ids are the .w field of the cell-ordered records (no separate id list on this path)
+__global__ void k_gather_f32(int64_t n_slots, CellsView cv, const float *__restrict__ src,
+                             float *__restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots && slot_valid(cv, i)) dst[i] = __ldg(src + __float_as_int(__ldg(&cv.rec[i].w)));
+}
+
+__global__ void k_gather_wcsph(int64_t n, int nd, CellsView cv,
                                const float *__restrict__ v, const float *__restrict__ mass,
                                const float *__restrict__ pressure, float4 *__restrict__ vrho,
                                float4 *__restrict__ mp)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t id = __float_as_int(__ldg(&sorted[i].w));
+    if (i >= n || !slot_valid(cv, i)) return;
+    const int64_t id = __float_as_int(__ldg(&cv.rec[i].w));
     const int ns = nd + 1;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (nd == 3 && ((reinterpret_cast<uintptr_t>(v) & 15) == 0)) {
@@ -50,8 +59,16 @@ int g_tune_wpc = 0;
 int g_tune_half = -1;
 int g_tune_twoset = 1;
 
+static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points);
+
+// number of record slots of the view the sweeps will use (payload scratch is sized by it)
+static int64_t view_slots(const pnb_grid *g)
+{
+    return g->bucket_valid ? (int64_t)g->p.total_cells * g->bucket_K : g->n_built;
+}
+
 static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
-                                 int64_t *n_loop)
+                                 int64_t *n_loop, cudaStream_t s)
 {
     if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
     if (!g->built) {
@@ -60,6 +77,13 @@ static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const i
     }
     if (nx > 0 && !x) { set_error("x is NULL"); return PNB_ERR_ARG; }
     *n_loop = points ? *n_loop : nx;
+    // every sweep but the x === y tile sweep walks (or may walk) the CSR arrays: settle the
+    // layout BEFORE the payload is gathered into it
+    if (!is_fast_path(g, x, nx, points) && g->bucket_valid) {
+        pnb_status st = ensure_csr(g, s);
+        if (st != PNB_OK) return st;
+        g->bucket_valid = false;
+    }
     return PNB_OK;
 }
 
@@ -88,7 +112,7 @@ extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64
 {
     (void)y; (void)n;
     int64_t n_loop = n_points;
-    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop);
+    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop, (cudaStream_t)stream);
     if (st != PNB_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     // count_neighbors.jl:22  n_neighbors .= 0
@@ -106,22 +130,23 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
 {
     (void)y; (void)n;
     int64_t n_loop = n_points;
-    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop);
+    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop, (cudaStream_t)stream);
     if (st != PNB_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     const int nd = g->p.ndims;
     // n_body.jl:36  dv .= 0
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * nd, s));
     if (g->template_search || g->n_built == 0) return check_err_word(g, s);
-    st = ensure_scratch(g, sizeof(float) * (size_t)g->n_built);
-    if (st != PNB_OK) return st;
     // bit-identical sums need the reference's visiting order with ids ascending in a cell
     if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
+    const int64_t slots = view_slots(g);
+    st = ensure_scratch(g, sizeof(float) * (size_t)slots);
+    if (st != PNB_OK) return st;
     float *mass_sorted = reinterpret_cast<float *>(g->scratch);
     {
         ProfScope ps(PH_GATHER, s);
-        k_gather_f32<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(g->n_built, g->sorted,
-                                                                   mass, mass_sorted);
+        k_gather_f32<<<(unsigned)div_up(slots, 256), 256, 0, s>>>(slots, cells_view(g), mass,
+                                                               mass_sorted);
         PNB_LAUNCHED();
     }
     const bool fastp = is_fast_path(g, x, nx, points);
@@ -144,23 +169,23 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
 {
     (void)y; (void)n; (void)mass_x;
     int64_t n_loop = n_points;
-    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop);
+    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop, (cudaStream_t)stream);
     if (st != PNB_OK) return st;
     if (!params) { set_error("params is NULL"); return PNB_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     const int nd = g->p.ndims;
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * (nd + 1), s));
     if (g->template_search || g->n_built == 0) return check_err_word(g, s);
-    const int64_t nb = g->n_built;
+    if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
+    const int64_t nb = view_slots(g);
     const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
     st = ensure_scratch(g, off_mp + (int64_t)sizeof(float4) * nb);
     if (st != PNB_OK) return st;
-    if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
     float4 *vrho = reinterpret_cast<float4 *>(g->scratch);
     float4 *mp = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
     {
         ProfScope ps(PH_GATHER, s);
-        k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, g->sorted, v_y,
+        k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, cells_view(g), v_y,
                                                                  mass_y, pressure_y, vrho, mp);
         PNB_LAUNCHED();
     }

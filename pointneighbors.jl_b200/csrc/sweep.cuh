@@ -61,10 +61,11 @@ __device__ __forceinline__ unsigned test_block(const PerP &g, const float4 *__re
 // x === y, the copy made by build_query_list for a second point set.
 template <int ND, bool PER, class CL, int TX>
 __device__ __forceinline__ void
-sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
-                const float4 *__restrict__ sorted, const uint32_t *__restrict__ q_start,
-                const float4 *__restrict__ q_sorted, const CL &cl, int64_t tile)
+sweep_tile_rows(const GridP &g, const CellsView &cand, const CellsView &qry, const CL &cl,
+                int64_t tile)
 {
+    const float4 *__restrict__ sorted = cand.rec;
+    const float4 *__restrict__ q_sorted = qry.rec;
     const bool two = q_sorted != sorted;
     constexpr int kSlotsT = TX + 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -91,17 +92,23 @@ sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
     const PerP pp = make_perp(g);
 
     // points of this tile are one contiguous range of the cell-ordered array
-    const uint32_t tile_p0 = q_start[linear_cell(g, cx0, cy, cz)];
-    const uint32_t tile_p1 = q_start[linear_cell(g, cx1, cy, cz) + 1];
-    if (tile_p0 == tile_p1) return;   // uniform for the CTA
+    {
+        uint32_t n_tile = 0;   // query points of the tile (uniform for the CTA)
+        for (int cx = cx0; cx <= cx1; cx++) {
+            uint32_t b0, cnt;
+            cell_range(qry, linear_cell(g, cx, cy, cz), b0, cnt);
+            n_tile += cnt;
+        }
+        if (n_tile == 0) return;
+    }
 
     // work items of the tile: (cell, pass of 32 points); a batch gives every warp one item
     const int my_cx = cx0 + warp;
     uint32_t c_p0 = 0, c_p1 = 0;
     if (my_cx <= cx1) {
-        const int lin = linear_cell(g, my_cx, cy, cz);
-        c_p0 = q_start[lin];
-        c_p1 = q_start[lin + 1];
+        uint32_t cnt;
+        cell_range(qry, linear_cell(g, my_cx, cy, cz), c_p0, cnt);
+        c_p1 = c_p0 + cnt;
     }
     const int my_passes = (int)((c_p1 - c_p0 + 31) / 32);
     int max_passes = my_passes;
@@ -143,9 +150,7 @@ sweep_tile_rows(const GridP &g, const uint32_t *__restrict__ cell_start,
                     uint32_t b0 = 0, cnt = 0;
                     if (sx <= cx1 + 1) {
                         if (PER) sx = floormod_i(sx - 2, g.nc[0]) + 2;
-                        const int lin = linear_cell(g, sx, ry, rz);
-                        b0 = cell_start[lin];
-                        cnt = cell_start[lin + 1] - b0;
+                        cell_range(cand, linear_cell(g, sx, ry, rz), b0, cnt);
                     }
                     s_begin[threadIdx.x] = b0;
                     // exclusive prefix over <= 10 slots, done by the first warp
@@ -236,7 +241,8 @@ __global__ void __launch_bounds__(kCellThreads)
 k_sweep_cells(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
               CL cl)
 {
-    sweep_tile_rows<ND, PER, CL, kTX>(g, cell_start, sorted, cell_start, sorted, cl, (int64_t)blockIdx.x);
+    const CellsView v{cell_start, sorted, 0u};
+    sweep_tile_rows<ND, PER, CL, kTX>(g, v, v, cl, (int64_t)blockIdx.x);
 }
 
 // General path: one thread per query point ------------------------------------------------------

@@ -41,14 +41,18 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         if (per_cell < kTwoSetMinPerCell && g_tune_twoset != 2) two = false;
     }
     if (fast || two) {
-        const uint32_t *q_start = two ? g->xq_start : g->cell_start;
-        const float4 *q_sorted = two ? g->xq_sorted : g->sorted;
+        // candidates: buckets or CSR, whatever the last build wrote; queries: the same list
+        // (x === y) or the CSR copy of the second point set
+        const CellsView cand = cells_view(g);
+        const CellsView qry = two ? CellsView{g->xq_start, g->xq_sorted, 0u} : cand;
         const int nxc = g->p.gs[0] - 2;
         const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
         const int nzc = ND > 2 ? g->p.gs[2] - 2 : 1;
         if (nxc <= 0 || nyc <= 0 || nzc <= 0) return PNB_OK;
         const size_t smem_rows = sizeof(float4) * kCapPad + (size_t)kCap * CL::kPayBytes;
         if (!tiles) {
+            pnb_status stc = ensure_csr(g, s);     // the ordered kernel walks the CSR arrays
+            if (stc != PNB_OK) return stc;
             const int64_t blocks = (int64_t)div_up(nxc, kTX) * nyc * nzc;
             ProfScope ps(PH_SWEEP_CELLS, s);
             k_sweep_cells<ND, PER, CL><<<(unsigned)blocks, kCellThreads, smem_rows, s>>>(
@@ -82,7 +86,7 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         if (st != PNB_OK) return st;                                                              \
         ProfScope ps(PH_SWEEP_CELLS, s);                                                          \
         k_sweep_tiles<ND, PER, CL, WPC, HALF, TWO><<<(unsigned)blocks, kFTX * WPC * 32, smem, s>>>( \
-            g->p, g->cell_start, g->sorted, q_start, q_sorted, cl, g->ovf_tiles, g->ovf_count);   \
+            g->p, cand, qry, cl, g->ovf_tiles, g->ovf_count);                                     \
         PNB_LAUNCHED();                                                                           \
     } while (0)
         if (two) {
@@ -99,10 +103,12 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         {
             ProfScope ps(PH_SWEEP_OVERFLOW, s);
             k_sweep_overflow<ND, PER, CL><<<148 * 2, kFTX * 32, smem_rows, s>>>(
-                g->p, g->cell_start, g->sorted, q_start, q_sorted, cl, g->ovf_tiles, g->ovf_count);
+                g->p, cand, qry, cl, g->ovf_tiles, g->ovf_count);
             PNB_LAUNCHED();
         }
     } else if (n_loop > 0) {
+        pnb_status stc = ensure_csr(g, s);         // the per-point kernel walks the CSR arrays
+        if (stc != PNB_OK) return stc;
         ProfScope ps(PH_SWEEP_POINTS, s);
         k_sweep_points<ND, PER, CL><<<(unsigned)div_up(n_loop, 128), 128, 0, s>>>(
             g->p, g->cell_start, g->sorted, x, n_loop, points, base, cl, g->d_err);

@@ -143,10 +143,11 @@ __device__ __forceinline__ unsigned test_block_half(const uint32_t *__restrict__
 // (cell_start, sorted).  For x === y both pairs of pointers are the same arrays.
 template <int ND, bool PER, class CL, int kWPC, bool HALF, bool TWO>
 __global__ void __launch_bounds__(kFTX * kWPC * 32, 1024 / (kFTX * kWPC * 32))
-k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__restrict__ sorted,
-              const uint32_t *__restrict__ q_start, const float4 *__restrict__ q_sorted,
-              CL cl, int *__restrict__ overflow_tiles, int *__restrict__ overflow_count)
+k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ overflow_tiles,
+              int *__restrict__ overflow_count)
 {
+    const float4 *__restrict__ sorted = cand.rec;
+    const float4 *__restrict__ q_sorted = qry.rec;
     constexpr int NR = rows_of(ND);
     constexpr int NE = kFSlots * NR;          // staged cells per tile
     constexpr int kFThreads = kFTX * kWPC * 32;
@@ -178,9 +179,15 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const PerP pp = make_perp(g);
 
-    const uint32_t tile_p0 = q_start[linear_cell(g, cx0, cy, cz)];
-    const uint32_t tile_p1 = q_start[linear_cell(g, cx1, cy, cz) + 1];
-    if (tile_p0 == tile_p1) return;   // no query points in this tile
+    {
+        uint32_t n_tile = 0;   // query points of the tile (uniform for the CTA)
+        for (int cx = cx0; cx <= cx1; cx++) {
+            uint32_t b0, cnt;
+            cell_range(qry, linear_cell(g, cx, cy, cz), b0, cnt);
+            n_tile += cnt;
+        }
+        if (n_tile == 0) return;   // no query points in this tile
+    }
 
     // ---- table of staged cells, entry e = slot * NR + row (rows in CartesianIndices order) ----
     if (warp == 0) {
@@ -196,9 +203,7 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
                     if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
                     if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
                 }
-                const int lin = linear_cell(g, sx, ry, rz);
-                b0 = cell_start[lin];
-                cnt = cell_start[lin + 1] - b0;
+                cell_range(cand, linear_cell(g, sx, ry, rz), b0, cnt);
             }
             s_cbeg[e] = b0;
             s_ccnt[e] = cnt;
@@ -225,9 +230,9 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
     const int my_cx = cx0 + my_cell;
     uint32_t c_p0 = 0, c_p1 = 0;
     if (my_cx <= cx1) {
-        const int lin = linear_cell(g, my_cx, cy, cz);
-        c_p0 = q_start[lin];
-        c_p1 = q_start[lin + 1];
+        uint32_t cnt;
+        cell_range(qry, linear_cell(g, my_cx, cy, cz), c_p0, cnt);
+        c_p1 = c_p0 + cnt;
     }
     if (part == 0 && lane == 0) s_maxpass[my_cell] = (int)((c_p1 - c_p0 + 31) / 32);
     __syncthreads();
@@ -509,15 +514,12 @@ k_sweep_tiles(GridP g, const uint32_t *__restrict__ cell_start, const float4 *__
 // same tile shape (kFTX cells, one warp per cell), persistent over the overflow list.
 template <int ND, bool PER, class CL>
 __global__ void __launch_bounds__(kFTX * 32)
-k_sweep_overflow(GridP g, const uint32_t *__restrict__ cell_start,
-                 const float4 *__restrict__ sorted, const uint32_t *__restrict__ q_start,
-                 const float4 *__restrict__ q_sorted, CL cl, const int *__restrict__ overflow_tiles,
-                 const int *__restrict__ overflow_count)
+k_sweep_overflow(GridP g, CellsView cand, CellsView qry, CL cl,
+                 const int *__restrict__ overflow_tiles, const int *__restrict__ overflow_count)
 {
     const int n = *overflow_count;
     for (int t = blockIdx.x; t < n; t += gridDim.x) {
-        sweep_tile_rows<ND, PER, CL, kFTX>(g, cell_start, sorted, q_start, q_sorted, cl,
-                                           (int64_t)overflow_tiles[t]);
+        sweep_tile_rows<ND, PER, CL, kFTX>(g, cand, qry, cl, (int64_t)overflow_tiles[t]);
         __syncthreads();
     }
 }
