@@ -939,37 +939,37 @@ pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *o
 // histogram pass, no scan: 28 N + 4 C bytes, exactly the algorithmic minimum of SURVEY 8d.
 // A cell that receives more than K points sets error bit 3; the build is then redone as CSR.
 // ---------------------------------------------------------------------------------------------
-template <int ND, bool PER>
+template <int ND, bool PER, int PPT>
 __global__ void __launch_bounds__(kBuildThreads)
 k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
                  const int32_t *__restrict__ idx, int base, uint32_t K,
                  uint32_t *__restrict__ bcount, float4 *__restrict__ brec, int *__restrict__ err)
 {
-    const int64_t block0 = (int64_t)blockIdx.x * kBuildTile;
+    const int64_t block0 = (int64_t)blockIdx.x * (kBuildThreads * PPT);
     const int logK = 31 - __clz((int)K);            // K is a power of two
-    if (idx == nullptr && block0 + kBuildTile <= n_idx) {
+    if (idx == nullptr && block0 + (kBuildThreads * PPT) <= n_idx) {
         // full tile: no bounds checks, all atomics of a thread's points before the first store
-        float p[kBuildPPT][3];
-        int lin[kBuildPPT], h[kBuildPPT], rl[kBuildPPT];
+        float p[PPT][3];
+        int lin[PPT], h[PPT], rl[PPT];
 #pragma unroll
-        for (int j = 0; j < kBuildPPT; j++) {
+        for (int j = 0; j < PPT; j++) {
             const int64_t k = block0 + j * kBuildThreads + (int)threadIdx.x;
 #pragma unroll
             for (int d = 0; d < 3; d++) p[j][d] = d < ND ? __ldg(y + k * ND + d) : 0.f;
         }
         int bad = 0;
 #pragma unroll
-        for (int j = 0; j < kBuildPPT; j++) {
+        for (int j = 0; j < PPT; j++) {
             lin[j] = point_cell_fast<ND, PER>(g, bp, p[j]);
             if (lin[j] < 0) bad |= 1;
             h[j] = run_head(lin[j], lin[j] >= 0, &rl[j]);
         }
-        unsigned basev[kBuildPPT];
+        unsigned basev[PPT];
 #pragma unroll
-        for (int j = 0; j < kBuildPPT; j++)
+        for (int j = 0; j < PPT; j++)
             basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(bcount + lin[j], (unsigned)rl[j]) : 0u;
 #pragma unroll
-        for (int j = 0; j < kBuildPPT; j++) {
+        for (int j = 0; j < PPT; j++) {
             const unsigned b = __shfl_sync(0xffffffffu, basev[j], h[j] & 31);
             if (lin[j] >= 0) {
                 const unsigned slot = b + (unsigned)(lane_id() - h[j]);
@@ -983,11 +983,11 @@ k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
         if (bad) atomicOr(err, bad);
         return;
     }
-    float p[kBuildPPT][3];
-    int32_t id[kBuildPPT];
-    bool in[kBuildPPT];
+    float p[PPT][3];
+    int32_t id[PPT];
+    bool in[PPT];
 #pragma unroll
-    for (int j = 0; j < kBuildPPT; j++) {
+    for (int j = 0; j < PPT; j++) {
         const int64_t k = block0 + j * kBuildThreads + (int)threadIdx.x;
         in[j] = k < n_idx;
         id[j] = (int32_t)k;
@@ -995,20 +995,20 @@ k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
 #pragma unroll
         for (int d = 0; d < 3; d++) p[j][d] = (in[j] && d < ND) ? __ldg(y + (int64_t)id[j] * ND + d) : 0.f;
     }
-    int lin[kBuildPPT], h[kBuildPPT], rl[kBuildPPT];
+    int lin[PPT], h[PPT], rl[PPT];
     int bad = 0;
 #pragma unroll
-    for (int j = 0; j < kBuildPPT; j++) {
+    for (int j = 0; j < PPT; j++) {
         lin[j] = in[j] ? point_cell_fast<ND, PER>(g, bp, p[j]) : -1;
         if (in[j] && lin[j] < 0) bad |= 1;
         h[j] = run_head(lin[j], lin[j] >= 0, &rl[j]);
     }
-    unsigned basev[kBuildPPT];
+    unsigned basev[PPT];
 #pragma unroll
-    for (int j = 0; j < kBuildPPT; j++)
+    for (int j = 0; j < PPT; j++)
         basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(bcount + lin[j], (unsigned)rl[j]) : 0u;
 #pragma unroll
-    for (int j = 0; j < kBuildPPT; j++) {
+    for (int j = 0; j < PPT; j++) {
         const unsigned b = __shfl_sync(0xffffffffu, basev[j], h[j] & 31);
         if (lin[j] >= 0) {
             const unsigned slot = b + (unsigned)(lane_id() - h[j]);
@@ -1246,19 +1246,24 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         if (!g->bcount) PNB_CUDA(cudaMalloc(&g->bcount, sizeof(uint32_t) * (size_t)(C + 4)));
         BuildP bp;
         for (int d = 0; d < 3; d++) { volatile float rc = 1.0f / g->p.cs[d]; bp.rcs[d] = rc; }
-        const unsigned blocks = (unsigned)div_up(n_idx, kBuildTile);
         {
             ProfScope ps(PH_BUILD_BUCKET, s);     // the clearing of the counters is part of it
             PNB_CUDA(cudaMemsetAsync(g->bcount, 0, sizeof(uint32_t) * (size_t)C, s));
-#define PNB_BUCKET(ND, PER)                                                                        \
-    k_bucket_scatter<ND, PER><<<blocks, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y,    \
-                                                               index_base, (uint32_t)g->bucket_K,  \
-                                                               g->bcount, g->brec, g->d_err)
+#define PNB_BUCKET(ND, PER, PPT)                                                                   \
+    k_bucket_scatter<ND, PER, PPT><<<(unsigned)div_up(n_idx, kBuildThreads * PPT), kBuildThreads,  \
+                                     0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base,         \
+                                             (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err)
             const bool per = g->p.periodic != 0;
             switch (g->p.ndims) {
-                case 1: if (per) PNB_BUCKET(1, true); else PNB_BUCKET(1, false); break;
-                case 2: if (per) PNB_BUCKET(2, true); else PNB_BUCKET(2, false); break;
-                default: if (per) PNB_BUCKET(3, true); else PNB_BUCKET(3, false); break;
+                case 1: if (per) PNB_BUCKET(1, true, 4); else PNB_BUCKET(1, false, 4); break;
+                case 2: if (per) PNB_BUCKET(2, true, 4); else PNB_BUCKET(2, false, 4); break;
+                default:
+                    if (per) PNB_BUCKET(3, true, 4);
+                    else if (g_tune_build & 32) PNB_BUCKET(3, false, 8);
+                    else if (g_tune_build & 64) PNB_BUCKET(3, false, 2);
+                    else if (g_tune_build & 128) PNB_BUCKET(3, false, 1);
+                    else PNB_BUCKET(3, false, 4);
+                    break;
             }
 #undef PNB_BUCKET
             PNB_LAUNCHED();
@@ -1313,7 +1318,8 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         // crowded cells stay CSR)
         int64_t K = 16;
         while (K < (int64_t)fullest + fullest / 4 + 4) K *= 2;
-        g->bucket_K = (C * K <= 4 * n_idx + (1 << 20)) ? (int)K : 0;
+        // (slot numbers are 32-bit in the kernels)
+        g->bucket_K = (C * K <= 4 * n_idx + (1 << 20) && C * K < 0x7fffffffLL) ? (int)K : 0;
     }
     g->csr_valid = true;
     g->n_built = n_idx;

@@ -82,6 +82,7 @@ struct ListCountCl {
     __device__ __forceinline__ void save_acc(const State &, float *) const {}
     __device__ __forceinline__ void add_acc(State &, const float *) const {}
     __device__ __forceinline__ void seek(State &, int) const {}
+    __device__ __forceinline__ void flush(State &) const {}
     template <int ND>
     __device__ __forceinline__ void pair_s(State &, float, float, float, float, int, uint32_t, int,
                                            int) const {}
@@ -109,19 +110,42 @@ struct ListFillCl {
     static constexpr bool kExactMasks = true;
     const int64_t *offsets;
     int32_t *ids;
-    struct State { int64_t pos; };
+    // b0..b3: up to four ids waiting for one 16-byte store (tile kernel only)
+    struct State { int64_t pos; int b0, b1, b2, b3, nb; };
     __device__ __forceinline__ void save_acc(const State &, float *) const {}
     __device__ __forceinline__ void add_acc(State &, const float *) const {}
     __device__ __forceinline__ void seek(State &s, int first_rank) const { s.pos += first_rank; }
+    // Every lane appends to its own list, so a warp-wide 4-byte store touches 32 different
+    // sectors.  Ids are therefore collected four at a time and written with one 16-byte store
+    // once the write position is 16-byte aligned (scalar stores before that and in flush()).
     template <int ND>
     __device__ __forceinline__ void pair_s(State &s, float, float, float, float, int j_id, uint32_t,
                                            int, int) const
     {
-        ids[s.pos++] = j_id;
+        if (s.nb == 0 && (s.pos & 3) != 0) { ids[s.pos++] = j_id; return; }
+        if (s.nb == 0) s.b0 = j_id;
+        else if (s.nb == 1) s.b1 = j_id;
+        else if (s.nb == 2) s.b2 = j_id;
+        else s.b3 = j_id;
+        if (++s.nb == 4) {
+            *reinterpret_cast<int4 *>(ids + s.pos) = make_int4(s.b0, s.b1, s.b2, s.b3);
+            s.pos += 4;
+            s.nb = 0;
+        }
+    }
+    __device__ __forceinline__ void flush(State &s) const
+    {
+        if (s.nb > 0) ids[s.pos] = s.b0;
+        if (s.nb > 1) ids[s.pos + 1] = s.b1;
+        if (s.nb > 2) ids[s.pos + 2] = s.b2;
+        s.pos += s.nb;
+        s.nb = 0;
     }
     __device__ __forceinline__ void init(State &s, bool active, int, int i_id) const
     {
         s.pos = active ? offsets[i_id] : 0;
+        s.b0 = s.b1 = s.b2 = s.b3 = 0;
+        s.nb = 0;
     }
     __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
     __device__ __forceinline__ void count(State &, int) const {}

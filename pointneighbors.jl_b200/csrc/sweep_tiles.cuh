@@ -492,6 +492,7 @@ k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ o
                         cl.template pair_s<ND>(st, px, py, pz, d2, __float_as_int(pj.w), pay_sa, slot, kFCap);
                 }
             }
+            cl.flush(st);
             // ---- phase 4: add the kWPC partial accumulators of every point ---------------------
             // (the cell's mask words are free once all its warps have finished their drain)
             cell_barrier(my_cell, kCellThreads_);

@@ -27,4 +27,5 @@ for name, X in (("cell-sorted", A), ("shuffled", R)):
         ev1.record(); torch.cuda.synchronize()
         prof = _lib.profile(enable=False)
         line = "  ".join(f"{k}={ms / c:.4f}" for k, (ms, c) in prof.items() if c)
+        cs, _ = nhs.export_csr()          # next update! of this loop starts from a CSR build again
         print(f"{name:12s} variant={v}: {line}  call={ev0.elapsed_time(ev1) / 10:.4f} ms")

@@ -139,7 +139,7 @@ for c in [int(v) for v in args.configs.split(",")]:
                     "list_build_ms_median": bmed, "tlsph_ms_min": smin, "tlsph_ms_median": smed,
                     "tlsph_hbm_gbs": bytes_sweep / (smin * 1e-3) / 1e9,
                     "tlsph_hbm_frac": bytes_sweep / (smin * 1e-3) / 1e9 / HBM,
-                    "list_build_kernels_ms": {k: ms / max(cnt_, 1) * (cnt_ / max(prof["k_cell_hist"][1], 1))
+                    "list_build_kernels_ms": {k: ms / max(prof["k_sort_lists"][1], 1)
                                               for k, (ms, cnt_) in prof.items() if cnt_}})
     elif c == 6:
         # two point sets (fluid-boundary style): x = a dense slab of the cloud
