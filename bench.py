@@ -234,9 +234,15 @@ def gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device: pnb200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 or args.total_layers > 0:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            # one rank of the slab code path (strong-scaling base line of --total-layers)
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
         from pnb200 import slabs
         return slabs.bench_multi_gpu(args, rank, world, dev, METRIC, UNIT)
 
@@ -472,6 +478,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lattice", type=int, default=254, help="lattice points per dimension (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-layers", type=int, default=0,
+                    help="STRONG scaling: fixed lattice 254 x 254 x TOTAL_LAYERS split over the GPUs "
+                         "(2032 = the 131 M particle cloud of BASELINE config 5); 0 = weak scaling, "
+                         "254 layers per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -379,7 +379,8 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
 
     T = np.float32
     n = args.lattice
-    nz = n * world
+    strong = int(getattr(args, "total_layers", 0) or 0)
+    nz = strong if strong > 0 else n * world
     r = T(3.0) / T(nz + 1)
     mn = np.zeros(3, T)
     mx = (np.array([n, n, nz], dtype=np.float64) / nz).astype(T)
@@ -494,10 +495,11 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
         line = {
             "metric": metric, "value": total_pairs / (ms_max * 1e-3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if strong > 0 else "weak",
+            "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"WCSPH step 3D, slab-decomposed: {n}x{n}x{nz} = {int(tsum[2])} particles "
-                                   f"over {world} GPUs ({n} lattice layers per GPU, ~BASELINE config 5 at 8), "
+                                   f"over {world} GPUs ({nz // world} lattice layers per GPU, ~BASELINE config 5), "
                                    "per step: migrant+ghost exchange (NCCL send/recv), update!, interact!",
                        "particles_total": int(tsum[2]), "search_radius": float(r),
                        "ghost_points_per_rank_max": int(tmax[4]),
