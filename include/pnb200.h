@@ -288,6 +288,32 @@ int pnb_profile_phases(void);
 const char *pnb_profile_name(int phase);
 pnb_status pnb_profile_get(int phase, double *total_ms, int64_t *launches);
 
+/* ---------------------------------------------------------------------------------------------
+ * Float64 searches (coordinates, corners and search_radius all Float64): the searching part of
+ * the API -- constructors, initialize!/update!, neighbour counts, neighbour lists, pair geometry --
+ * with the reference's arithmetic evaluated in Float64 (the reference is generic in the element
+ * type, src/nhs_grid.jl:60-65).  The list handle and all exports are shared with Float32; the
+ * fused SPH closures exist in Float32 only.
+ * ------------------------------------------------------------------------------------------- */
+pnb_status pnb_grid_params_f64(int ndims, double search_radius, const double *min_corner,
+                               const double *max_corner, const double *box_min,
+                               const double *box_max, double *padded_min, double *padded_max,
+                               int64_t *grid_size, int64_t *n_cells, double *cell_size);
+pnb_status pnb_grid_create_f64(int ndims, double search_radius, const double *min_corner,
+                               const double *max_corner, const double *box_min,
+                               const double *box_max, pnb_grid **out);
+pnb_status pnb_grid_build_f64(pnb_grid *g, const double *y, int64_t n, const int32_t *eachindex_y,
+                              int64_t n_idx, int index_base, void *stream);
+pnb_status pnb_point_cells_f64(const pnb_grid *g, const double *x, int64_t n, int32_t *out_linear,
+                               void *stream);
+pnb_status pnb_count_neighbors_f64(pnb_grid *g, const double *x, int64_t nx, const double *y,
+                                   int64_t n, const int32_t *points, int64_t n_points,
+                                   int index_base, int64_t *out, void *stream);
+pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                               int sort, pnb_nlist **out, void *stream);
+pnb_status pnb_nlist_pairs_f64(const pnb_nlist *list, const pnb_grid *g, const double *x,
+                               const double *y, double *pos_diff, double *distance, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

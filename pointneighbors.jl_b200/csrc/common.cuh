@@ -30,6 +30,24 @@ struct GridP {
     int total_cells;
 };
 
+// Float64 searches (f64.cuh): the same scalars in double, and the cell-ordered record
+struct GridP64 {
+    int ndims;
+    int periodic;
+    double r, r2;
+    double minc[3];     // padded min corner
+    double cs[3];       // cell_size
+    int gs[3];          // allocated grid size
+    int nc[3];          // periodic cells per dim (-1 if not periodic)
+    double bsize[3];    // periodic box size
+    int total_cells;
+};
+
+struct alignas(32) Rec64 {
+    double x, y, z;
+    long long id;
+};
+
 // ---------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "grid.cuh"
+#include "f64.cuh"
 
 namespace pnb {
 
@@ -348,6 +349,8 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->xq_sorted);
     cudaFree(g->bcount);
     cudaFree(g->brec);
+    cudaFree(g->sorted64);
+    cudaFree(g->sorted64_tmp);
     cudaFree(g->d_maxcount);
     cudaFree(g->cell_count);
     cudaFree(g->cell_points);
@@ -1205,6 +1208,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                                          void *stream)
 {
     if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    if (g->f64) { set_error("Float64 grid handle passed to a Float32 entry point"); return PNB_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t C = g->p.total_cells;
     if (eachindex_y == nullptr) n_idx = n;
@@ -1767,4 +1771,333 @@ extern "C" pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t
     out[0] = n_stay + h[0];
     out[1] = n_stay + h[0] + h[1];
     return PNB_OK;
+}
+
+// =============================================================================================
+// Float64 searches (f64.cuh)
+// =============================================================================================
+namespace pnb {
+
+// constructors in Float64 (full_grid.jl:66-78, nhs_grid.jl:102-124): every operation is one
+// IEEE double operation (the host compiler uses SSE2 doubles: no excess precision)
+static pnb_status grid_params_host64(int ndims, double r, const double *min_corner,
+                                     const double *max_corner, const double *box_min,
+                                     const double *box_max, double *padded_min, double *padded_max,
+                                     int64_t *grid_size, int64_t *n_cells, double *cell_size)
+{
+    if (ndims < 1 || ndims > 3) { set_error("`NDIMS` must be 1, 2, or 3"); return PNB_ERR_ARG; }
+    if (!min_corner || !max_corner) {
+        set_error("min_corner and max_corner must have the same length");
+        return PNB_ERR_ARG;
+    }
+    volatile double factor = 1001.0 / 1000.0;       // Float64(1001 // 1000)
+    volatile double pad = factor * r;
+    const bool is_template = r < 2.220446049250313e-16;
+    for (int d = 0; d < ndims; d++) {
+        volatile double mn = min_corner[d] - pad;
+        volatile double mx = max_corner[d] + pad;
+        if (padded_min) padded_min[d] = mn;
+        if (padded_max) padded_max[d] = mx;
+        if (grid_size) {
+            if (is_template) grid_size[d] = 0;
+            else {
+                volatile double ext = mx - mn;
+                volatile double q = ext / r;
+                grid_size[d] = (int64_t)std::ceil(q);
+            }
+        }
+        if (n_cells) n_cells[d] = -1;
+        if (cell_size) cell_size[d] = r;
+    }
+    if (box_min && box_max && !is_template) {
+        for (int d = 0; d < ndims; d++) {
+            volatile double size = box_max[d] - box_min[d];
+            const double nc = std::floor((size + 10.0 * 2.220446049250313e-16) / r);
+            const int64_t nci = (int64_t)nc;
+            if (n_cells) n_cells[d] = nci;
+            if (cell_size) { volatile double cs = size / (double)nci; cell_size[d] = cs; }
+            if (nci < 3) {
+                set_error("the `GridNeighborhoodSearch` needs at least 3 cells in each dimension "
+                          "when used with periodicity. Please use no NHS for very small problems.");
+                return PNB_ERR_ARG;
+            }
+        }
+    }
+    return PNB_OK;
+}
+
+template <int ND>
+__global__ void k_hist64(GridP64 g, const double *__restrict__ y, int64_t n_idx,
+                         const int32_t *__restrict__ idx, int base,
+                         uint32_t *__restrict__ cell_count, int *__restrict__ err)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_idx) return;
+    const int64_t id = idx ? (int64_t)idx[k] - base : k;
+    double p[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; d++) p[d] = y[id * ND + d];
+    int cc[3];
+    const int lin = point_cell64<ND>(g, p, cc);
+    if (lin < 0) { atomicOr(err, 1); return; }
+    atomicAdd(cell_count + lin, 1u);
+}
+
+template <int ND>
+__global__ void k_scatter64(GridP64 g, const double *__restrict__ y, int64_t n_idx,
+                            const int32_t *__restrict__ idx, int base,
+                            uint32_t *__restrict__ cursor, Rec64 *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_idx) return;
+    const int64_t id = idx ? (int64_t)idx[k] - base : k;
+    double p[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; d++) p[d] = y[id * ND + d];
+    int cc[3];
+    const int lin = point_cell64<ND>(g, p, cc);
+    if (lin < 0) return;
+    const uint32_t slot = atomicAdd(cursor + lin, 1u);
+    Rec64 r;
+    r.x = p[0]; r.y = p[1]; r.z = p[2]; r.id = id;
+    out[slot] = r;
+}
+
+// ids ascending inside every cell (rank by counting), records + id list
+__global__ void k_canonicalize64(int total_cells, const uint32_t *__restrict__ cell_start,
+                                 const Rec64 *__restrict__ in, Rec64 *__restrict__ out,
+                                 int32_t *__restrict__ cell_points)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= total_cells) return;
+    const uint32_t s0 = cell_start[c], s1 = cell_start[c + 1];
+    const int cnt = (int)(s1 - s0);
+    for (int e = lane_id(); e < cnt; e += 32) {
+        const Rec64 rec = in[s0 + e];
+        int r = 0;
+        for (int k = 0; k < cnt; k++) r += (in[s0 + k].id < rec.id) ? 1 : 0;
+        cell_points[s0 + r] = (int32_t)rec.id;
+        out[s0 + r] = rec;
+    }
+}
+
+template <int ND>
+__global__ void k_point_cells64(GridP64 g, const double *__restrict__ x, int64_t n,
+                                int32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; d++) p[d] = x[i * ND + d];
+    int cc[3];
+    out[i] = point_cell64<ND>(g, p, cc);
+}
+
+}  // namespace pnb
+
+extern "C" pnb_status pnb_grid_params_f64(int ndims, double search_radius, const double *min_corner,
+                                          const double *max_corner, const double *box_min,
+                                          const double *box_max, double *padded_min,
+                                          double *padded_max, int64_t *grid_size, int64_t *n_cells,
+                                          double *cell_size)
+{
+    return grid_params_host64(ndims, search_radius, min_corner, max_corner, box_min, box_max,
+                              padded_min, padded_max, grid_size, n_cells, cell_size);
+}
+
+extern "C" pnb_status pnb_grid_create_f64(int ndims, double r, const double *min_corner,
+                                          const double *max_corner, const double *box_min,
+                                          const double *box_max, pnb_grid **out)
+{
+    if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
+    *out = nullptr;
+    if (pnb_device_count() <= 0) {
+        set_error("no CUDA device: libpnb200 has no CPU fallback");
+        return PNB_ERR_CUDA;
+    }
+    pnb_grid *g = new pnb_grid();
+    memset(g, 0, sizeof(*g));
+    g->f64 = true;
+    int64_t gsz[3] = {1, 1, 1}, ncl[3] = {-1, -1, -1};
+    pnb_status st = grid_params_host64(ndims, r, min_corner, max_corner, box_min, box_max,
+                                       g->padded_min64, g->padded_max64, gsz, ncl, g->cell_size64);
+    if (st != PNB_OK) { delete g; return st; }
+    g->template_search = r < 2.220446049250313e-16;
+    GridP64 &p = g->p64;
+    p.ndims = ndims;
+    p.periodic = (box_min && box_max && !g->template_search) ? 1 : 0;
+    p.r = r;
+    { volatile double r2 = r * r; p.r2 = r2; }
+    int64_t total = 1;
+    for (int d = 0; d < 3; d++) {
+        p.minc[d] = d < ndims ? g->padded_min64[d] : 0.0;
+        p.cs[d] = d < ndims ? g->cell_size64[d] : 1.0;
+        int64_t gs = d < ndims ? gsz[d] : 1;
+        if (g->template_search) gs = d < ndims ? 0 : 1;
+        if (gs > 0x7fffffff) gs = 0x7fffffff;
+        p.gs[d] = (int)gs;
+        p.nc[d] = d < ndims ? (int)ncl[d] : -1;
+        p.bsize[d] = 1.0;
+        if (d < ndims && p.periodic) { volatile double size = box_max[d] - box_min[d]; p.bsize[d] = size; }
+        g->grid_size[d] = gs;
+        g->n_cells[d] = ncl[d];
+        total *= gs;
+        if (total > 0x7fffff00LL) {
+            set_error("cell grid too large for this build: more than 2^31 cells");
+            delete g;
+            return PNB_ERR_ARG;
+        }
+    }
+    p.total_cells = (int)total;
+    // the shared (element-type independent) part of the Float32 scalars: exports read these
+    g->p.ndims = ndims;
+    g->p.periodic = p.periodic;
+    g->p.total_cells = p.total_cells;
+    for (int d = 0; d < 3; d++) { g->p.gs[d] = p.gs[d]; g->p.nc[d] = p.nc[d]; g->p.off[d] = 0; }
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaGetDevice"); }
+    auto fail = [&](cudaError_t err, const char *what) {
+        pnb_status s2 = cuda_fail(err, what);
+        pnb_grid_destroy(g);
+        return s2;
+    };
+    const int64_t C = total;
+    if ((e = cudaMalloc(&g->cell_start_alloc, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
+        return fail(e, "cudaMalloc cell_start");
+    g->cell_start = g->cell_start_alloc + 3;
+    if ((e = cudaMalloc(&g->cell_count, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
+        return fail(e, "cudaMalloc cell_count");
+    if ((e = cudaMemset(g->cell_start_alloc, 0, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
+        return fail(e, "cudaMemset");
+    if ((e = cudaMemset(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
+        return fail(e, "cudaMemset");
+    if ((e = cudaHostAlloc(&g->h_err, 2 * sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
+        return fail(e, "cudaHostAlloc");
+    g->h_err[0] = g->h_err[1] = 0;
+    if ((e = cudaHostGetDevicePointer(&g->d_err, g->h_err, 0)) != cudaSuccess)
+        return fail(e, "cudaHostGetDevicePointer");
+    if ((e = cudaMalloc(&g->scan_ticket, sizeof(unsigned int))) != cudaSuccess)
+        return fail(e, "cudaMalloc ticket");
+    if ((e = cudaMemset(g->scan_ticket, 0, sizeof(unsigned int))) != cudaSuccess)
+        return fail(e, "cudaMemset");
+    *out = g;
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_grid_build_f64(pnb_grid *g, const double *y, int64_t n,
+                                         const int32_t *eachindex_y, int64_t n_idx, int index_base,
+                                         void *stream)
+{
+    if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t C = g->p64.total_cells;
+    if (eachindex_y == nullptr) n_idx = n;
+    g->built = false;
+    g->bucket_valid = false;
+    if (g->template_search) {
+        PNB_CUDA(cudaMemsetAsync(g->cell_start, 0, sizeof(uint32_t) * (size_t)(C + 1), s));
+        PNB_CUDA(cudaStreamSynchronize(s));
+        g->n_built = 0; g->built = true; g->y_built = y; g->n_y_built = n; g->full_build = false;
+        g->csr_valid = true; g->canonical = true;
+        return PNB_OK;
+    }
+    if (n_idx > 0x7ffffff0LL || n > 0x7ffffff0LL) {
+        set_error("more than 2^31 points are not supported (ids are Int32, full_grid.jl:177)");
+        return PNB_ERR_ARG;
+    }
+    if (n_idx > 0 && y == nullptr) { set_error("y is NULL"); return PNB_ERR_ARG; }
+    if (n_idx > g->cap_points) {
+        cudaFree(g->cell_points); g->cell_points = nullptr;
+        cudaFree(g->sorted64); g->sorted64 = nullptr;
+        cudaFree(g->sorted64_tmp); g->sorted64_tmp = nullptr;
+        g->cap_points = 0;
+        const int64_t cap = n_idx + n_idx / 16 + 32;
+        PNB_CUDA(cudaMalloc(&g->cell_points, sizeof(int32_t) * (size_t)cap));
+        PNB_CUDA(cudaMalloc(&g->sorted64, sizeof(Rec64) * (size_t)cap));
+        PNB_CUDA(cudaMalloc(&g->sorted64_tmp, sizeof(Rec64) * (size_t)cap));
+        g->cap_points = cap;
+    }
+    const unsigned blocks = (unsigned)div_up(n_idx > 0 ? n_idx : 1, 256);
+#define PNB_ND64(K, ...)                                                        \
+    switch (g->p64.ndims) {                                                     \
+        case 1: K<1><<<blocks, 256, 0, s>>>(__VA_ARGS__); break;                \
+        case 2: K<2><<<blocks, 256, 0, s>>>(__VA_ARGS__); break;                \
+        default: K<3><<<blocks, 256, 0, s>>>(__VA_ARGS__); break;               \
+    }
+    if (n_idx > 0) {
+        PNB_ND64(k_hist64, g->p64, y, n_idx, eachindex_y, index_base, g->cell_count, g->d_err);
+        PNB_LAUNCHED();
+    }
+    pnb_status st = scan_impl<uint32_t, true, false>(g, g->cell_count, g->cell_start + 1, C, s);
+    if (st != PNB_OK) return st;
+    if (n_idx > 0) {
+        PNB_ND64(k_scatter64, g->p64, y, n_idx, eachindex_y, index_base, g->cell_start + 1,
+                 g->sorted64_tmp);
+        PNB_LAUNCHED();
+        k_canonicalize64<<<(unsigned)div_up(C * 32, 256), 256, 0, s>>>((int)C, g->cell_start,
+                                                                     g->sorted64_tmp, g->sorted64,
+                                                                     g->cell_points);
+        PNB_LAUNCHED();
+    }
+#undef PNB_ND64
+    st = check_err_word(g, s);
+    if (st != PNB_OK) { g->n_built = 0; return st; }
+    g->n_built = n_idx;
+    g->y_built = y;
+    g->n_y_built = n;
+    g->full_build = (eachindex_y == nullptr);
+    g->built = true;
+    g->csr_valid = true;
+    g->canonical = true;
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_point_cells_f64(const pnb_grid *g, const double *x, int64_t n,
+                                          int32_t *out_linear, void *stream)
+{
+    if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
+    if (g->template_search) {
+        set_error("`search_radius` is not defined for this cell list");
+        return PNB_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > 0) {
+        const unsigned blocks = (unsigned)div_up(n, 256);
+        switch (g->p64.ndims) {
+            case 1: k_point_cells64<1><<<blocks, 256, 0, s>>>(g->p64, x, n, out_linear); break;
+            case 2: k_point_cells64<2><<<blocks, 256, 0, s>>>(g->p64, x, n, out_linear); break;
+            default: k_point_cells64<3><<<blocks, 256, 0, s>>>(g->p64, x, n, out_linear); break;
+        }
+        PNB_LAUNCHED();
+    }
+    PNB_CUDA(cudaStreamSynchronize(s));
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_count_neighbors_f64(pnb_grid *g, const double *x, int64_t nx,
+                                              const double *y, int64_t n, const int32_t *points,
+                                              int64_t n_points, int index_base, int64_t *out,
+                                              void *stream)
+{
+    (void)y; (void)n;
+    if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
+    if (!g->built) {
+        set_error("the neighborhood search has not been initialized (call initialize! first)");
+        return PNB_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)nx, s));
+    const int64_t n_loop = points ? n_points : nx;
+    if (!g->template_search && g->n_built > 0 && n_loop > 0) {
+        const unsigned blocks = (unsigned)div_up(n_loop, 128);
+        ProfScope ps(PH_SWEEP_POINTS, s);
+        switch (g->p64.ndims) {
+            case 1: k_sweep_points64<1, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, out, nullptr, nullptr, nullptr, g->d_err); break;
+            case 2: k_sweep_points64<2, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, out, nullptr, nullptr, nullptr, g->d_err); break;
+            default: k_sweep_points64<3, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, out, nullptr, nullptr, nullptr, g->d_err); break;
+        }
+        PNB_LAUNCHED();
+    }
+    return check_err_word(g, s);
 }

@@ -35,6 +35,14 @@ struct pnb_grid {
     bool csr_valid;          // cell_start / sorted describe the current build
     unsigned int *d_maxcount;   // [1] device scratch
 
+    // Float64 search (f64.cuh): scalars in double and the cell-ordered Float64 records; the CSR
+    // offsets / ids (cell_start, cell_points) are shared with the Float32 path
+    bool f64;
+    pnb::GridP64 p64;
+    pnb::Rec64 *sorted64;      // [cap_points], canonical order (ids ascending inside a cell)
+    pnb::Rec64 *sorted64_tmp;  // scatter target before the per-cell sort
+    double padded_min64[3], padded_max64[3], cell_size64[3];
+
     // cell-ordered copy of the query points of a two-set sweep (x != y), built per sweep
     uint32_t *xq_start_alloc, *xq_start;   // [C+1]
     float4 *xq_sorted;                     // [xq_cap]

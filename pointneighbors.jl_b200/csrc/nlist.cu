@@ -11,6 +11,7 @@
 #include "closures.cuh"
 #include "sweep.cuh"
 #include "sweep_launch.cuh"
+#include "f64.cuh"
 
 struct pnb_nlist {
     int64_t nx;        // number of lists (points of x)
@@ -508,6 +509,7 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
     *out = nullptr;
     if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    if (g->f64) { set_error("Float64 grid handle passed to a Float32 entry point"); return PNB_ERR_ARG; }
     if (!g->built) {
         set_error("the neighborhood search has not been initialized (call initialize! first)");
         return PNB_ERR_STATE;
@@ -671,6 +673,137 @@ extern "C" pnb_status pnb_tlsph_deformation_grad_f32(const pnb_nlist *l_, const 
         }
 #undef DEFGRAD
         PNB_LAUNCHED();
+    }
+    PNB_CUDA(cudaStreamSynchronize(s));
+    return PNB_OK;
+}
+
+// =============================================================================================
+// Float64 neighbour lists (f64.cuh): count pass, scan, fill pass in the reference's visiting
+// order (the Float64 build leaves every cell in canonical order), optional per-list sort.
+// The list handle and its exports are the same as for Float32.
+// =============================================================================================
+namespace pnb {
+template <int ND>
+__global__ void k_nlist_pairs64(GridP64 g, int64_t nx, const int64_t *__restrict__ offsets,
+                                const int32_t *__restrict__ ids, const double *__restrict__ x,
+                                const double *__restrict__ y, double *__restrict__ pos_diff,
+                                double *__restrict__ dist)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nx) return;
+    double xi[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; d++) xi[d] = x[i * ND + d];
+    for (int64_t k = offsets[i] + lane_id(); k < offsets[i + 1]; k += 32) {
+        const int64_t j = ids[k];
+        Rec64 yj;
+        yj.x = y[j * ND];
+        yj.y = ND > 1 ? y[j * ND + 1] : 0.0;
+        yj.z = ND > 2 ? y[j * ND + 2] : 0.0;
+        yj.id = j;
+        double p[3];
+        // nhs_precomputed.jl:230-238: the periodic fix applies when d2 > r2, there is no radius test
+        const double d2 = pair_d2_64<ND>(g, xi, yj, p, true);
+        if (pos_diff) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) pos_diff[k * ND + d] = p[d];
+        }
+        if (dist) dist[k] = __dsqrt_rn(d2);
+    }
+}
+}  // namespace pnb
+
+extern "C" pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t nx, const double *y,
+                                          int64_t n, int sort, pnb_nlist **out, void *stream)
+{
+    (void)y;
+    if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
+    *out = nullptr;
+    if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
+    if (!g->built) {
+        set_error("the neighborhood search has not been initialized (call initialize! first)");
+        return PNB_ERR_STATE;
+    }
+    if (!g->template_search && (!g->full_build || n != g->n_y_built)) {
+        set_error("this neighborhood search does not support inactive points");
+        return PNB_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    pnb_nlist *l = new pnb_nlist();
+    memset(l, 0, sizeof(*l));
+    l->nx = nx;
+    l->ndims = g->p64.ndims;
+    auto fail = [&](pnb_status st) { pnb_nlist_destroy(l); return st; };
+#define NL_CUDA(expr)                                                           \
+    do {                                                                        \
+        cudaError_t e__ = (expr);                                               \
+        if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr));             \
+    } while (0)
+    NL_CUDA(cached_malloc(0, (void **)&l->offsets, sizeof(int64_t) * (size_t)(nx + 1), &l->bytes_offsets));
+    NL_CUDA(cached_malloc(2, (void **)&l->counts, sizeof(uint32_t) * (size_t)(nx + 8), &l->bytes_counts));
+    NL_CUDA(cudaMalloc(&l->d_err, sizeof(int)));
+    NL_CUDA(cudaMemsetAsync(l->d_err, 0, sizeof(int), s));
+    NL_CUDA(cudaMallocHost(&l->h_err, sizeof(int)));
+    NL_CUDA(cudaMemsetAsync(l->counts, 0, sizeof(uint32_t) * (size_t)(nx + 8), s));
+    const bool live = !g->template_search && g->n_built > 0 && nx > 0;
+    const unsigned blocks = (unsigned)div_up(nx > 0 ? nx : 1, 128);
+#define PNB_SWEEP64(MODE, ...)                                                                    \
+    switch (g->p64.ndims) {                                                                       \
+        case 1: k_sweep_points64<1, MODE><<<blocks, 128, 0, s>>>(__VA_ARGS__); break;             \
+        case 2: k_sweep_points64<2, MODE><<<blocks, 128, 0, s>>>(__VA_ARGS__); break;             \
+        default: k_sweep_points64<3, MODE><<<blocks, 128, 0, s>>>(__VA_ARGS__); break;            \
+    }
+    if (live) {
+        PNB_SWEEP64(1, g->p64, g->cell_start, g->sorted64, x, nx, nullptr, 0, nullptr, l->counts,
+                    nullptr, nullptr, g->d_err);
+        g_launch_count++;
+    }
+    pnb_status st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
+    if (st != PNB_OK) return fail(st);
+    int64_t total = 0;
+    unsigned int longest = 0;
+    if (nx > 0) {
+        k_max_count<<<(unsigned)div_up(nx, 256), 256, 0, s>>>(nx, l->counts, l->counts + nx);
+        g_launch_count++;
+    }
+    NL_CUDA(cudaMemcpyAsync(&total, l->offsets + nx, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    NL_CUDA(cudaMemcpyAsync(&longest, l->counts + nx, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    NL_CUDA(cudaStreamSynchronize(s));
+    l->n_pairs = total;
+    l->max_len = longest;
+    NL_CUDA(cached_malloc(1, (void **)&l->ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1), &l->bytes_ids));
+    if (live) {
+        PNB_SWEEP64(2, g->p64, g->cell_start, g->sorted64, x, nx, nullptr, 0, nullptr, nullptr,
+                    l->offsets, l->ids, g->d_err);
+        g_launch_count++;
+    }
+#undef PNB_SWEEP64
+    if (sort && nx > 0 && total > 0) {
+        k_sort_lists<<<(unsigned)div_up(nx, kSortWarps), kSortWarps * 32, 0, s>>>(nx, l->offsets, l->ids);
+        g_launch_count++;
+    }
+    st = check_err_word(g, s);
+    if (st != PNB_OK) return fail(st);
+#undef NL_CUDA
+    *out = l;
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_nlist_pairs_f64(const pnb_nlist *l, const pnb_grid *g, const double *x,
+                                          const double *y, double *pos_diff, double *distance,
+                                          void *stream)
+{
+    if (!l || !g || !g->f64) { set_error("not a Float64 grid / list handle"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (l->nx > 0) {
+        const unsigned blocks = (unsigned)div_up(l->nx * 32, 256);
+        switch (l->ndims) {
+            case 1: k_nlist_pairs64<1><<<blocks, 256, 0, s>>>(g->p64, l->nx, l->offsets, l->ids, x, y, pos_diff, distance); break;
+            case 2: k_nlist_pairs64<2><<<blocks, 256, 0, s>>>(g->p64, l->nx, l->offsets, l->ids, x, y, pos_diff, distance); break;
+            default: k_nlist_pairs64<3><<<blocks, 256, 0, s>>>(g->p64, l->nx, l->offsets, l->ids, x, y, pos_diff, distance); break;
+        }
+        g_launch_count++;
     }
     PNB_CUDA(cudaStreamSynchronize(s));
     return PNB_OK;

@@ -71,6 +71,7 @@ static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const i
                                  int64_t *n_loop, cudaStream_t s)
 {
     if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    if (g->f64) { set_error("Float64 grid handle passed to a Float32 entry point"); return PNB_ERR_ARG; }
     if (!g->built) {
         set_error("the neighborhood search has not been initialized (call initialize! first)");
         return PNB_ERR_STATE;

@@ -45,6 +45,8 @@ _lib = None
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 _pf = C.POINTER(C.c_float)
+_pd = C.POINTER(C.c_double)
+_f64 = C.c_double
 _pi64 = C.POINTER(C.c_int64)
 
 # name -> (restype, argtypes); must list every symbol declared in include/pnb200.h
@@ -63,6 +65,13 @@ SIGNATURES = {
     "pnb_slab_unpack_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
                                       C.c_int, C.c_int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                                       _vp, _i64, _vp, _pi64, _vp]),
+    "pnb_grid_params_f64": (C.c_int, [C.c_int, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pi64, _pi64, _pd]),
+    "pnb_grid_create_f64": (C.c_int, [C.c_int, _f64, _pd, _pd, _pd, _pd, C.POINTER(_vp)]),
+    "pnb_grid_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
+    "pnb_point_cells_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "pnb_count_neighbors_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
+    "pnb_nlist_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), _vp]),
+    "pnb_nlist_pairs_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnb_grid_destroy": (None, [_vp]),
     "pnb_grid_total_cells": (_i64, [_vp]),
     "pnb_grid_n_points": (_i64, [_vp]),

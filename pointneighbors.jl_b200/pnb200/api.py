@@ -154,6 +154,26 @@ class FullGridCellList:
         self.max_points_per_cell = int(max_points_per_cell)
         self.search_radius = search_radius
         self._ndims = int(mn.size)
+        # Float64 search: corners AND radius given as Float64 (np.float64 scalar / float64 arrays),
+        # like the reference, whose element type follows its arguments.  Everything else runs the
+        # Float32 path (python floats are taken as Float32 values, as before).
+        self.eltype = np.dtype(np.float64) if (isinstance(search_radius, np.float64)
+                                                and mn.dtype == np.float64
+                                                and mx.dtype == np.float64) else np.dtype(np.float32)
+        if self.eltype == np.float64:
+            if self._ndims > 3:
+                raise ArgumentError("`NDIMS` must be 1, 2, or 3")
+            pmin64, pmax64, gsz64 = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int64 * 3)()
+            mn64 = np.ascontiguousarray(mn, dtype=np.float64)
+            mx64 = np.ascontiguousarray(mx, dtype=np.float64)
+            check(_lib.lib().pnb_grid_params_f64(
+                self._ndims, float(search_radius), mn64.ctypes.data_as(_lib._pd),
+                mx64.ctypes.data_as(_lib._pd), None, None, pmin64, pmax64, gsz64, None, None))
+            self.min_corner = np.array(pmin64[:self._ndims], dtype=np.float64)
+            self.max_corner = np.array(pmax64[:self._ndims], dtype=np.float64)
+            self.n_cells_per_dimension = tuple(int(v) for v in gsz64[:self._ndims])
+            self._user_min, self._user_max = mn64, mx64
+            return
         r = np.float32(search_radius)
         # padding and grid size through the library's host arithmetic (bit-identical to Julia)
         pmin = (C.c_float * 3)()
@@ -240,6 +260,25 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
             if _eltype_of(search_radius) != periodic_box.eltype:
                 raise ArgumentError("the `search_radius` and the `PeriodicBox` must have "
                                     "the same element type")
+            if _eltype_of(search_radius) == np.dtype(np.float64) and \
+                    cell_list.eltype == np.float64:
+                nc = (C.c_int64 * 3)()
+                cs64 = (C.c_double * 3)()
+                bmn = np.ascontiguousarray(periodic_box.min_corner, dtype=np.float64)
+                bmx = np.ascontiguousarray(periodic_box.max_corner, dtype=np.float64)
+                check(_lib.lib().pnb_grid_params_f64(
+                    self._ndims, float(search_radius),
+                    cell_list._user_min.ctypes.data_as(_lib._pd),
+                    cell_list._user_max.ctypes.data_as(_lib._pd),
+                    bmn.ctypes.data_as(_lib._pd), bmx.ctypes.data_as(_lib._pd),
+                    None, None, None, nc, cs64))
+                self.n_cells = tuple(int(v) for v in nc[:self._ndims])
+                self.cell_size = tuple(np.float64(v) for v in cs64[:self._ndims])
+                self._handle = None
+                self._window = None
+                self._cell_list_radius = cell_list.search_radius
+                self.eltype = np.dtype(np.float64)
+                return
             if _eltype_of(search_radius) != np.dtype(np.float32):
                 raise ArgumentError("the B200 path computes in Float32: pass a Float32 "
                                     "`search_radius` and `PeriodicBox`")
@@ -258,9 +297,27 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
         self._handle = None
         self._window = None    # (lo, hi) global cell window for slab decomposition (slabs.py)
         self._cell_list_radius = cell_list.search_radius
+        # Float64 search: a Float64 cell list with a Float64 radius (np.float64)
+        self.eltype = np.dtype(np.float64) if (cell_list.eltype == np.float64 and
+                                               isinstance(search_radius, np.float64)) \
+            else np.dtype(np.float32)
 
     # -- device handle -----------------------------------------------------------------------
     def _grid(self):
+        if self._handle is None and self.eltype == np.float64:
+            if self._window is not None:
+                raise ArgumentError("slab windows exist for Float32 searches only")
+            cl = self.cell_list
+            h = C.c_void_p()
+            bmn = bmx = None
+            if self.periodic_box is not None:
+                bmn_a = np.ascontiguousarray(self.periodic_box.min_corner, dtype=np.float64)
+                bmx_a = np.ascontiguousarray(self.periodic_box.max_corner, dtype=np.float64)
+                bmn, bmx = bmn_a.ctypes.data_as(_lib._pd), bmx_a.ctypes.data_as(_lib._pd)
+            check(_lib.lib().pnb_grid_create_f64(
+                self._ndims, float(self.search_radius), cl._user_min.ctypes.data_as(_lib._pd),
+                cl._user_max.ctypes.data_as(_lib._pd), bmn, bmx, C.byref(h)))
+            self._handle = h
         if self._handle is None:
             if float(self.search_radius) >= _EPS64 and \
                     _eltype_of(self.search_radius) != np.dtype(np.float32):
@@ -324,10 +381,11 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
     def point_cells(self, x):
         """0-based linear cell index of every point of x, -1 outside (cell_coords + cell_index)."""
         torch = _torch()
-        x = _coords(x, self._ndims)
+        x = _coords(x, self._ndims, self.eltype)
         out = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
-        check(_lib.lib().pnb_point_cells_f32(self._grid(), x.data_ptr(), x.shape[0],
-                                             out.data_ptr(), _stream()))
+        fn = _lib.lib().pnb_point_cells_f64 if self.eltype == np.float64 \
+            else _lib.lib().pnb_point_cells_f32
+        check(fn(self._grid(), x.data_ptr(), x.shape[0], out.data_ptr(), _stream()))
         return out
 
 
@@ -336,15 +394,17 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _coords(x, nd):
+def _coords(x, nd, eltype=np.dtype(np.float32)):
     torch = _torch()
     if not isinstance(x, torch.Tensor):
         raise TypeError("coordinates must be a torch CUDA tensor of shape (N, NDIMS)")
     if not x.is_cuda:
         raise TypeError("coordinates must live on the GPU: pnb200 has no CPU path "
                         "(use adapt(...) / tensor.cuda())")
-    if x.dtype != torch.float32:
-        raise TypeError("coordinates must be float32")
+    want = torch.float64 if np.dtype(eltype) == np.float64 else torch.float32
+    if x.dtype != want:
+        raise TypeError(f"coordinates must be {str(want).split('.')[-1]} for this search "
+                        "(the element type follows the search radius and the cell list)")
     if x.ndim != 2 or x.shape[1] != nd:
         raise ArgumentError(f"coordinates must have shape (N, {nd}) "
                             "(the memory of Julia's NDIMS x N matrix)")
@@ -394,8 +454,14 @@ def initialize_(nhs, x, y, *, parallelization_backend=None, eachindex_y=None):
     """initialize!(nhs, x, y; eachindex_y)  (src/nhs_grid.jl:220-225, nhs_precomputed.jl:130-147)."""
     if isinstance(nhs, PrecomputedNeighborhoodSearch):
         return nhs._initialize(x, y, eachindex_y)
-    y = _coords(y, nhs._ndims)
+    y = _coords(y, nhs._ndims, nhs.eltype)
     idx = _index_tensor(eachindex_y, y.shape[0], "eachindex_y")
+    if nhs.eltype == np.float64:
+        check(_lib.lib().pnb_grid_build_f64(
+            nhs._grid(), y.data_ptr(), y.shape[0], None if idx is None else idx.data_ptr(),
+            0 if idx is None else idx.numel(), 0, _stream()))
+        nhs._y_ref = y
+        return nhs
     check(_lib.lib().pnb_grid_build_f32(
         nhs._grid(), y.data_ptr(), y.shape[0], None if idx is None else idx.data_ptr(),
         0 if idx is None else idx.numel(), 0, _stream()))
@@ -508,11 +574,24 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
     host code and runs on the host).  Returns None like the reference."""
     nhs = neighborhood_search
     nd = nhs._ndims
-    x = _coords(system_coords, nd)
-    y = _coords(neighbor_coords, nd)
+    x = _coords(system_coords, nd, nhs.eltype)
+    y = _coords(neighbor_coords, nd, nhs.eltype)
     if isinstance(nhs, PrecomputedNeighborhoodSearch):
         return nhs._foreach(f, x, y, points)
     L = _lib.lib()
+    if nhs.eltype == np.float64:
+        pts = _index_tensor(points, x.shape[0], "points")
+        if isinstance(f, CountNeighbors):
+            check(L.pnb_count_neighbors_f64(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(),
+                                            y.shape[0], _ptr(pts), 0 if pts is None else pts.numel(),
+                                            0, f.n_neighbors.data_ptr(), _stream()))
+        elif callable(f) and not isinstance(f, (NBodyGravity, WCSPHInteract,
+                                                 TLSPHDeformationGradient)):
+            lists = _NeighborLists.build(nhs, x, y, sort=False)
+            lists.call_host(f, x, y, nhs, points, radius_test=True)
+        else:
+            raise TypeError("the fused n-body / WCSPH / TLSPH closures exist in Float32 only")
+        return None
     pts = _index_tensor(points, x.shape[0], "points")
     npts = 0 if pts is None else pts.numel()
     g = nhs._grid()
@@ -555,8 +634,8 @@ def foreach_neighbor(f, system_coords, neighbor_coords, neighborhood_search, poi
         raise ArgumentError("a `search_radius` other than the one of the neighborhood search "
                             "is not supported")
     nhs = neighborhood_search
-    x = _coords(system_coords, nhs._ndims)
-    y = _coords(neighbor_coords, nhs._ndims)
+    x = _coords(system_coords, nhs._ndims, nhs.eltype)
+    y = _coords(neighbor_coords, nhs._ndims, nhs.eltype)
     i = _check_point(point, x.shape[0])
     if isinstance(nhs, PrecomputedNeighborhoodSearch):
         return nhs._foreach(f, x, y, [i])
@@ -600,9 +679,10 @@ class _NeighborLists:
     @classmethod
     def build(cls, grid_nhs, x, y, sort=True):
         h = C.c_void_p()
-        check(_lib.lib().pnb_nlist_build_f32(grid_nhs._grid(), x.data_ptr(), x.shape[0],
-                                             y.data_ptr(), y.shape[0], int(bool(sort)),
-                                             C.byref(h), _stream()))
+        fn = _lib.lib().pnb_nlist_build_f64 if grid_nhs.eltype == np.float64 \
+            else _lib.lib().pnb_nlist_build_f32
+        check(fn(grid_nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
+                 int(bool(sort)), C.byref(h), _stream()))
         return cls(h, grid_nhs._ndims)
 
     def __del__(self):
@@ -649,11 +729,13 @@ class _NeighborLists:
         """pos_diff (P, nd) and distance (P,) of every listed pair, in list order."""
         torch = _torch()
         P = self.n_pairs
-        pd = torch.empty((max(P, 1), self._nd), dtype=torch.float32, device="cuda")
-        dist = torch.empty(max(P, 1), dtype=torch.float32, device="cuda")
-        check(_lib.lib().pnb_nlist_pairs_f32(self._handle, grid_nhs._grid(), x.data_ptr(),
-                                             y.data_ptr(), pd.data_ptr(), dist.data_ptr(),
-                                             _stream()))
+        f64 = grid_nhs.eltype == np.float64
+        dt = torch.float64 if f64 else torch.float32
+        pd = torch.empty((max(P, 1), self._nd), dtype=dt, device="cuda")
+        dist = torch.empty(max(P, 1), dtype=dt, device="cuda")
+        fn = _lib.lib().pnb_nlist_pairs_f64 if f64 else _lib.lib().pnb_nlist_pairs_f32
+        check(fn(self._handle, grid_nhs._grid(), x.data_ptr(), y.data_ptr(), pd.data_ptr(),
+                 dist.data_ptr(), _stream()))
         return pd[:P], dist[:P]
 
     def call_host(self, f: Callable, x, y, grid_nhs, points, radius_test: bool):
@@ -711,12 +793,13 @@ class PrecomputedNeighborhoodSearch(metaclass=_Parametric):
         self.n_points = int(n_points)
         self._lists: Optional[_NeighborLists] = None
         self._grid_for_pairs = update_neighborhood_search
+        self.eltype = update_neighborhood_search.eltype
 
     # initialize! (nhs_precomputed.jl:130-147)
     def _initialize(self, x, y, eachindex_y):
         nd = self._ndims
-        x = _coords(x, nd)
-        y = _coords(y, nd)
+        x = _coords(x, nd, self.eltype)
+        y = _coords(y, nd, self.eltype)
         if _index_tensor(eachindex_y, y.shape[0], "eachindex_y") is not None:
             raise PointNeighborsError("this neighborhood search does not support inactive points")
         if self.neighborhood_search is None:
@@ -729,8 +812,8 @@ class PrecomputedNeighborhoodSearch(metaclass=_Parametric):
     # update! (nhs_precomputed.jl:149-169)
     def _update(self, x, y, points_moving, eachindex_y):
         nd = self._ndims
-        x = _coords(x, nd)
-        y = _coords(y, nd)
+        x = _coords(x, nd, self.eltype)
+        y = _coords(y, nd, self.eltype)
         if _index_tensor(eachindex_y, y.shape[0], "eachindex_y") is not None:
             raise PointNeighborsError("this neighborhood search does not support inactive points")
         if self.neighborhood_search is None:
@@ -761,6 +844,8 @@ class PrecomputedNeighborhoodSearch(metaclass=_Parametric):
         if isinstance(f, TLSPHDeformationGradient):
             if points is not None:
                 raise ArgumentError("the fused TLSPH sweep loops over all points")
+            if self.eltype == np.float64:
+                raise TypeError("the fused TLSPH sweep exists in Float32 only")
             check(_lib.lib().pnb_tlsph_deformation_grad_f32(
                 self._lists._handle, self._grid_for_pairs._grid(), x.data_ptr(),
                 f.current_coordinates.data_ptr(), f.mass.data_ptr(),

@@ -844,3 +844,101 @@ def test_two_sets_edge_cases(pn, oracle):
         assert (c7.cpu().numpy() == cnt_o[:7]).all()
     finally:
         L.pnb_set_twoset_tiles(1)
+
+
+# ------------------------------------------------------------------------------------------
+# Float64 searches: everything in Float64, bit-exact vs the Float64 oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(14, 13, 12), (40, 30), (200,)])
+def test_float64_search(pn, oracle, size):
+    """Float64 coordinates, corners and radius: cells, CSR cell list, counts, sorted and unsorted
+    neighbour lists and the pair geometry (pos_diff, distance) equal the Float64 oracle's bit for
+    bit; x != y and `points` subsets included; Float32 tensors are rejected."""
+    T = np.float64
+    nd = len(size)
+    r = T(2.5)
+    y = pn.point_cloud(size, 2.5, seed=3).astype(T)
+    rng = np.random.default_rng(8)
+    mn, mx = y.min(0) - 2 * r, y.max(0) + 2 * r
+    cl = pn.FullGridCellList(min_corner=mn, max_corner=mx, search_radius=r)
+    assert cl.eltype == np.float64
+    nhs = pn.GridNeighborhoodSearch[nd](search_radius=r, n_points=len(y), cell_list=cl)
+    og = oracle.Grid(nd, r, mn, mx, dtype=np.float64)
+    assert cl.n_cells_per_dimension == og.grid_size
+    assert np.array_equal(cl.min_corner, og.min_corner) and np.array_equal(cl.max_corner, og.max_corner)
+    ty = torch.as_tensor(y, device="cuda")
+    assert ty.dtype == torch.float64
+    pn.initialize_(nhs, ty, ty)
+    og.build(y)
+    assert (nhs.point_cells(ty).cpu().numpy() == og.point_cells(y)).all()
+    cs, cp = nhs.export_csr()
+    assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
+    cnt = torch.zeros(len(y), dtype=torch.int64, device="cuda")
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), ty, ty, nhs)
+    off_o, ids_o = og.neighbor_lists(y, y, sort=True)
+    assert (cnt.cpu().numpy() == np.diff(off_o)).all()
+    off_t, ids_t = oracle.trivial_lists(y, y, r, dtype=np.float64)
+    assert (off_o == off_t).all() and (ids_o == ids_t).all()
+    for sort in (True, False):
+        pre = pn.PrecomputedNeighborhoodSearch[nd](search_radius=r, n_points=len(y),
+                                                   update_neighborhood_search=nhs, max_neighbors=4096,
+                                                   sort_neighbor_lists=sort)
+        pn.initialize_(pre, ty, ty)
+        off, ids = pre.export_csr()
+        off_s, ids_s = og.neighbor_lists(y, y, sort=sort)
+        assert (off.cpu().numpy() == off_s).all() and (ids.cpu().numpy() == ids_s).all(), sort
+    pd, dist = pre._lists.pairs(nhs, ty, ty)
+    pd_o, dist_o = oracle.list_pairs(y, y, off_s, ids_s, r, dtype=np.float64)
+    assert pd.dtype == torch.float64
+    assert np.array_equal(pd.cpu().numpy(), pd_o) and np.array_equal(dist.cpu().numpy(), dist_o)
+    # second point set + points subset + callable
+    x = (y[rng.choice(len(y), 60, replace=False)] + rng.normal(0, 0.3, (60, nd))).astype(T)
+    tx = torch.as_tensor(x, device="cuda")
+    cx = torch.zeros(60, dtype=torch.int64, device="cuda")
+    pts = np.arange(3, 60, 4)
+    pn.foreach_point_neighbor(pn.CountNeighbors(cx), tx, ty, nhs, points=pts)
+    assert (cx.cpu().numpy() == og.count_neighbors(x, y, points=pts)).all()
+    got = []
+    pn.foreach_neighbor(lambda i, j, pdv, d: got.append((j, float(d))), tx, ty, nhs, 5)
+    off_x, ids_x = og.neighbor_lists(x, y, sort=False)
+    pdx, dx = oracle.list_pairs(x, y, off_x, ids_x, r, dtype=np.float64)
+    assert [g[0] for g in got] == ids_x[off_x[5]:off_x[6]].tolist()
+    assert [g[1] for g in got] == [float(v) for v in dx[off_x[5]:off_x[6]]]
+    with pytest.raises(TypeError):
+        pn.initialize_(nhs, ty.float(), ty.float())
+    with pytest.raises(TypeError):
+        pn.foreach_point_neighbor(pn.NBodyGravity(None, None, 1.0), ty, ty, nhs)
+
+
+def test_float64_periodic(pn, oracle):
+    """Float64 PeriodicBox: n_cells / cell_size from the Float64 constructor arithmetic, lists equal
+    to the oracle and to brute force, points outside the box included."""
+    T = np.float64
+    rng = np.random.default_rng(12)
+    r = T(0.11)
+    bmn = np.array([0.1, -0.2, 0.05], T)
+    bmx = bmn + np.array([0.37, 0.52, 0.61], T)
+    n = 4000
+    y = bmn + rng.random((n, 3)) * (bmx - bmn)
+    y = y + (rng.integers(-1, 2, y.shape) * (rng.random(y.shape) < 0.15)) * (bmx - bmn)
+    box = pn.PeriodicBox(min_corner=bmn, max_corner=bmx)
+    nhs = pn.GridNeighborhoodSearch[3](search_radius=r, n_points=n, periodic_box=box,
+                                       cell_list=pn.FullGridCellList(min_corner=bmn, max_corner=bmx,
+                                                                     search_radius=r))
+    og = oracle.Grid(3, r, bmn, bmx, periodic_box=(bmn, bmx), dtype=np.float64)
+    assert nhs.n_cells == og.n_cells
+    assert tuple(nhs.cell_size) == tuple(og.cell_size)
+    ty = torch.as_tensor(y, device="cuda")
+    pn.initialize_(nhs, ty, ty)
+    og.build(y)
+    off_o, ids_o = og.neighbor_lists(y, y, sort=True)
+    off_t, ids_t = oracle.trivial_lists(y, y, r, periodic_box=(bmn, bmx), dtype=np.float64)
+    assert (off_o == off_t).all() and (ids_o == ids_t).all()
+    pre = pn.PrecomputedNeighborhoodSearch[3](search_radius=r, n_points=n, periodic_box=box,
+                                              update_neighborhood_search=nhs, max_neighbors=4096)
+    pn.initialize_(pre, ty, ty)
+    off, ids = pre.export_csr()
+    assert (off.cpu().numpy() == off_o).all() and (ids.cpu().numpy() == ids_o).all()
+    pd, dist = pre._lists.pairs(nhs, ty, ty)
+    pd_o, dist_o = oracle.list_pairs(y, y, off_o, ids_o, r, periodic_box=(bmn, bmx), dtype=np.float64)
+    assert np.array_equal(pd.cpu().numpy(), pd_o) and np.array_equal(dist.cpu().numpy(), dist_o)
