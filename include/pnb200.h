@@ -79,6 +79,13 @@ pnb_status pnb_grid_params_f32(int ndims, float search_radius, const float *min_
 pnb_status pnb_grid_create_f32(int ndims, float search_radius, const float *min_corner,
                                const float *max_corner, const float *box_min, const float *box_max,
                                pnb_grid **out);
+/* The same from the corners STORED in a FullGridCellList (cell_list.min_corner / max_corner are
+ * already padded, src/cell_lists/full_grid.jl:66-67): no second padding, the grid size is
+ * ceil((max - min) / search_radius) of the stored corners (:74).  This is what the Julia glue
+ * calls from Adapt.adapt_structure, so the device grid is bit-identical to the host cell list. */
+pnb_status pnb_grid_create_padded_f32(int ndims, float search_radius, const float *padded_min,
+                                      const float *padded_max, const float *box_min,
+                                      const float *box_max, pnb_grid **out);
 /* A window of the same global grid (multi-GPU slab decomposition): cells
  * win_lo[d]..win_hi[d] (global 1-based cell coordinates, inclusive; the outermost layer on each
  * side acts as the empty padding layer) with the GLOBAL cell arithmetic, so cell assignments and
@@ -302,6 +309,9 @@ pnb_status pnb_grid_params_f64(int ndims, double search_radius, const double *mi
 pnb_status pnb_grid_create_f64(int ndims, double search_radius, const double *min_corner,
                                const double *max_corner, const double *box_min,
                                const double *box_max, pnb_grid **out);
+pnb_status pnb_grid_create_padded_f64(int ndims, double search_radius, const double *padded_min,
+                                      const double *padded_max, const double *box_min,
+                                      const double *box_max, pnb_grid **out);
 pnb_status pnb_grid_build_f64(pnb_grid *g, const double *y, int64_t n, const int32_t *eachindex_y,
                               int64_t n_idx, int index_base, void *stream);
 pnb_status pnb_point_cells_f64(const pnb_grid *g, const double *x, int64_t n, int32_t *out_linear,

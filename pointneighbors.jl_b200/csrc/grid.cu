@@ -126,6 +126,10 @@ pnb_status ensure_scratch(pnb_grid *g, int64_t bytes)
 // Compiled by the host compiler without -ffast-math; every operation below is a single
 // IEEE-754 float (or double) operation.
 // ---------------------------------------------------------------------------------------------
+// set while a grid is created from the corners STORED in a FullGridCellList (already padded,
+// src/cell_lists/full_grid.jl:66-67): the constructor arithmetic then starts at :74
+static thread_local bool t_corners_padded = false;
+
 static pnb_status grid_params_host(int ndims, float r, const float *min_corner,
                                    const float *max_corner, const float *box_min,
                                    const float *box_max, float *padded_min, float *padded_max,
@@ -141,7 +145,7 @@ static pnb_status grid_params_host(int ndims, float r, const float *min_corner,
     }
     // full_grid.jl:66-67  min_corner .- 1001 // 1000 * search_radius
     volatile float factor = 1001.0f / 1000.0f;
-    volatile float pad = factor * r;
+    volatile float pad = t_corners_padded ? 0.0f : factor * r;
     const bool is_template = (double)r < 2.220446049250313e-16;  // full_grid.jl:69, nhs_grid.jl:102
     for (int d = 0; d < ndims; d++) {
         volatile float mn = min_corner[d] - pad;
@@ -231,6 +235,17 @@ extern "C" pnb_status pnb_grid_params_f32(int ndims, float search_radius, const 
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
+extern "C" pnb_status pnb_grid_create_padded_f32(int ndims, float r, const float *padded_min,
+                                                 const float *padded_max, const float *box_min,
+                                                 const float *box_max, pnb_grid **out)
+{
+    t_corners_padded = true;
+    pnb_status st = pnb_grid_create_window_f32(ndims, r, padded_min, padded_max, box_min, box_max,
+                                               nullptr, nullptr, out);
+    t_corners_padded = false;
+    return st;
+}
+
 extern "C" pnb_status pnb_grid_create_f32(int ndims, float r, const float *min_corner,
                                           const float *max_corner, const float *box_min,
                                           const float *box_max, pnb_grid **out)
@@ -1791,7 +1806,7 @@ static pnb_status grid_params_host64(int ndims, double r, const double *min_corn
         return PNB_ERR_ARG;
     }
     volatile double factor = 1001.0 / 1000.0;       // Float64(1001 // 1000)
-    volatile double pad = factor * r;
+    volatile double pad = t_corners_padded ? 0.0 : factor * r;
     const bool is_template = r < 2.220446049250313e-16;
     for (int d = 0; d < ndims; d++) {
         volatile double mn = min_corner[d] - pad;
@@ -1983,6 +1998,16 @@ extern "C" pnb_status pnb_grid_create_f64(int ndims, double r, const double *min
         return fail(e, "cudaMemset");
     *out = g;
     return PNB_OK;
+}
+
+extern "C" pnb_status pnb_grid_create_padded_f64(int ndims, double r, const double *padded_min,
+                                                 const double *padded_max, const double *box_min,
+                                                 const double *box_max, pnb_grid **out)
+{
+    t_corners_padded = true;
+    pnb_status st = pnb_grid_create_f64(ndims, r, padded_min, padded_max, box_min, box_max, out);
+    t_corners_padded = false;
+    return st;
 }
 
 extern "C" pnb_status pnb_grid_build_f64(pnb_grid *g, const double *y, int64_t n,

@@ -109,25 +109,33 @@ Base.ndims(::B200GridNeighborhoodSearch{NDIMS}) where {NDIMS} = NDIMS
 requires_update(::B200GridNeighborhoodSearch) = (false, true)          # src/nhs_grid.jl:133
 
 function Adapt.adapt_structure(::B200Backend, nhs::GridNeighborhoodSearch{NDIMS}) where {NDIMS}
-    nhs.search_radius isa Float32 ||
-        throw(ArgumentError("the B200 path computes in Float32: pass a Float32 `search_radius`"))
+    T = typeof(nhs.search_radius)
+    T in (Float32, Float64) ||
+        throw(ArgumentError("the B200 path computes in Float32 or Float64: pass such a `search_radius`"))
     cl = nhs.cell_list
     cl isa FullGridCellList ||
         throw(ArgumentError("only the FullGridCellList is GPU-compatible (src/cell_lists/dictionary.jl:8-10)"))
+    eltype(cl.min_corner) == T ||
+        throw(ArgumentError("cell list corners and `search_radius` must have the same element type"))
     r = nhs.search_radius
-    # the library pads the USER corners itself; the FullGridCellList stores padded corners
-    # (src/cell_lists/full_grid.jl:66-67), so undo the padding with the same Float32 arithmetic
-    pad = (1001f0 / 1000f0) * r
-    min_corner = Float32.(collect(cl.min_corner)) .+ pad
-    max_corner = Float32.(collect(cl.max_corner)) .- pad
+    # cell_list.min_corner / max_corner are the PADDED corners (src/cell_lists/full_grid.jl:66-67):
+    # hand them over as they are, the library continues at :74 (grid size from the stored corners)
+    min_corner = collect(T, cl.min_corner)
+    max_corner = collect(T, cl.max_corner)
     box = nhs.periodic_box
-    bmin = isnothing(box) ? C_NULL : Float32.(collect(box.min_corner))
-    bmax = isnothing(box) ? C_NULL : Float32.(collect(box.max_corner))
+    bmin = isnothing(box) ? C_NULL : collect(T, box.min_corner)
+    bmax = isnothing(box) ? C_NULL : collect(T, box.max_corner)
     ref = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:pnb_grid_create_f32, libpnb200), Cint,
-                (Cint, Cfloat, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{Ptr{Cvoid}}),
-                NDIMS, r, min_corner, max_corner, bmin, bmax, ref))
-    out = B200GridNeighborhoodSearch{NDIMS, Float32, typeof(box), typeof(nhs.update_strategy)}(
+    if T === Float32
+        check(ccall((:pnb_grid_create_padded_f32, libpnb200), Cint,
+                    (Cint, Cfloat, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{Ptr{Cvoid}}),
+                    NDIMS, r, min_corner, max_corner, bmin, bmax, ref))
+    else
+        check(ccall((:pnb_grid_create_padded_f64, libpnb200), Cint,
+                    (Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                    NDIMS, r, min_corner, max_corner, bmin, bmax, ref))
+    end
+    out = B200GridNeighborhoodSearch{NDIMS, T, typeof(box), typeof(nhs.update_strategy)}(
         ref[], r, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs)
     finalizer(x -> ccall((:pnb_grid_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), x.handle), out)
     return out
@@ -141,21 +149,30 @@ end
 is_all(idx, n) = idx isa Base.OneTo ? length(idx) == n : (idx == 1:n)
 
 # initialize!(nhs, x, y; eachindex_y)      src/nhs_grid.jl:220-225, 255-281
-function initialize!(nhs::B200GridNeighborhoodSearch, x::B200Array{Float32, 2},
-                     y::B200Array{Float32, 2}; parallelization_backend = default_backend(x),
-                     eachindex_y = axes(y, 2))
+function initialize!(nhs::B200GridNeighborhoodSearch{NDIMS, T}, x::B200Array{T, 2},
+                     y::B200Array{T, 2}; parallelization_backend = default_backend(x),
+                     eachindex_y = axes(y, 2)) where {NDIMS, T <: Union{Float32, Float64}}
     n = size(y, 2)
     iv, ni = is_all(eachindex_y, n) ? (C_NULL, 0) : index_vector(eachindex_y)
-    GC.@preserve iv check(ccall((:pnb_grid_build_f32, libpnb200), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
-                nhs.handle, y.ptr, n, iv === C_NULL ? C_NULL : iv.ptr, ni, 1, C_NULL))
+    ivp = iv === C_NULL ? C_NULL : iv.ptr
+    # the element type of the search (radius, cell list, coordinates) selects the entry point
+    GC.@preserve iv if T === Float32
+        check(ccall((:pnb_grid_build_f32, libpnb200), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
+                    nhs.handle, y.ptr, n, ivp, ni, 1, C_NULL))
+    else
+        check(ccall((:pnb_grid_build_f64, libpnb200), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
+                    nhs.handle, y.ptr, n, ivp, ni, 1, C_NULL))
+    end
     return nhs
 end
 
 # update!(nhs, x, y; points_moving, eachindex_y)      src/nhs_grid.jl:283-292
-function update!(nhs::B200GridNeighborhoodSearch, x::B200Array{Float32, 2},
-                 y::B200Array{Float32, 2}; points_moving = (true, true),
-                 parallelization_backend = default_backend(x), eachindex_y = axes(y, 2))
+function update!(nhs::B200GridNeighborhoodSearch{NDIMS, T}, x::B200Array{T, 2},
+                 y::B200Array{T, 2}; points_moving = (true, true),
+                 parallelization_backend = default_backend(x),
+                 eachindex_y = axes(y, 2)) where {NDIMS, T <: Union{Float32, Float64}}
     points_moving[2] || return nhs
     return initialize!(nhs, x, y; eachindex_y)
 end
@@ -204,6 +221,22 @@ function foreach_point_neighbor(f::CountNeighbors, x::B200Array{Float32, 2},
                                 points = axes(x, 2))
     pv, np = points_arg(points, size(x, 2))
     GC.@preserve pv check(ccall((:pnb_count_neighbors_f32, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint,
+                 Ptr{Cvoid}, Ptr{Cvoid}),
+                nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2),
+                pv === C_NULL ? C_NULL : pv.ptr, np, 1, f.n_neighbors.ptr, C_NULL))
+    return nothing
+end
+
+# Float64 searches: neighbour counts (and neighbour lists, below) exist in Float64; the fused
+# n-body / WCSPH / TLSPH closures are Float32 only.
+function foreach_point_neighbor(f::CountNeighbors, x::B200Array{Float64, 2},
+                                y::B200Array{Float64, 2},
+                                nhs::B200GridNeighborhoodSearch{NDIMS, Float64};
+                                parallelization_backend = default_backend(x),
+                                points = axes(x, 2)) where {NDIMS}
+    pv, np = points_arg(points, size(x, 2))
+    GC.@preserve pv check(ccall((:pnb_count_neighbors_f64, libpnb200), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint,
                  Ptr{Cvoid}, Ptr{Cvoid}),
                 nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2),
@@ -263,10 +296,17 @@ mutable struct NeighborLists
     ndims  :: Int
     function NeighborLists(nhs::B200GridNeighborhoodSearch, x, y; sort = true)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:pnb_nlist_build_f32, libpnb200), Cint,
-                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ref{Ptr{Cvoid}},
-                     Ptr{Cvoid}),
-                    nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2), sort, ref, C_NULL))
+        if eltype(x) === Float64                 # Float64 search: same handle type, same exports
+            check(ccall((:pnb_nlist_build_f64, libpnb200), Cint,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ref{Ptr{Cvoid}},
+                         Ptr{Cvoid}),
+                        nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2), sort, ref, C_NULL))
+        else
+            check(ccall((:pnb_nlist_build_f32, libpnb200), Cint,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ref{Ptr{Cvoid}},
+                         Ptr{Cvoid}),
+                        nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2), sort, ref, C_NULL))
+        end
         l = new(ref[], ndims(nhs))
         finalizer(z -> ccall((:pnb_nlist_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), z.handle), l)
         return l

@@ -67,6 +67,8 @@ SIGNATURES = {
                                       _vp, _i64, _vp, _pi64, _vp]),
     "pnb_grid_params_f64": (C.c_int, [C.c_int, _f64, _pd, _pd, _pd, _pd, _pd, _pd, _pi64, _pi64, _pd]),
     "pnb_grid_create_f64": (C.c_int, [C.c_int, _f64, _pd, _pd, _pd, _pd, C.POINTER(_vp)]),
+    "pnb_grid_create_padded_f64": (C.c_int, [C.c_int, _f64, _pd, _pd, _pd, _pd, C.POINTER(_vp)]),
+    "pnb_grid_create_padded_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, C.POINTER(_vp)]),
     "pnb_grid_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pnb_point_cells_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_count_neighbors_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),

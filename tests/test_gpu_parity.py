@@ -942,3 +942,34 @@ def test_float64_periodic(pn, oracle):
     pd, dist = pre._lists.pairs(nhs, ty, ty)
     pd_o, dist_o = oracle.list_pairs(y, y, off_o, ids_o, r, periodic_box=(bmn, bmx), dtype=np.float64)
     assert np.array_equal(pd.cpu().numpy(), pd_o) and np.array_equal(dist.cpu().numpy(), dist_o)
+
+
+def test_grid_from_padded_corners(pn, oracle):
+    """pnb_grid_create_padded_f32/_f64 (what the Julia glue calls with the corners stored in a
+    FullGridCellList): same grid, same cell list as the constructor path from the user corners."""
+    import ctypes as C
+    L = pn._lib.lib()
+    for T, create, build, pf in ((np.float32, L.pnb_grid_create_padded_f32, L.pnb_grid_build_f32, pn._lib._pf),
+                                 (np.float64, L.pnb_grid_create_padded_f64, L.pnb_grid_build_f64, pn._lib._pd)):
+        r = T(2.5)
+        y = pn.point_cloud((12, 11, 10), 2.5, seed=7).astype(T)
+        mn, mx = (y.min(0) - r).astype(T), (y.max(0) + r).astype(T)
+        cl = pn.FullGridCellList(min_corner=mn, max_corner=mx, search_radius=r)
+        assert cl.eltype == np.dtype(T)
+        pmn = np.ascontiguousarray(cl.min_corner, dtype=T)
+        pmx = np.ascontiguousarray(cl.max_corner, dtype=T)
+        h = C.c_void_p()
+        pn._lib.check(create(3, r, pmn.ctypes.data_as(pf), pmx.ctypes.data_as(pf), None, None, C.byref(h)))
+        try:
+            assert int(L.pnb_grid_total_cells(h)) == int(np.prod(cl.n_cells_per_dimension))
+            ty = torch.as_tensor(y, device="cuda")
+            pn._lib.check(build(h, ty.data_ptr(), len(y), None, 0, 0, None))
+            Cn = int(L.pnb_grid_total_cells(h))
+            cs = torch.empty(Cn + 1, dtype=torch.int32, device="cuda")
+            cp = torch.empty(len(y), dtype=torch.int32, device="cuda")
+            pn._lib.check(L.pnb_grid_export_csr(h, cs.data_ptr(), cp.data_ptr(), 0, None))
+            og = oracle.Grid(3, r, mn, mx, dtype=T)
+            og.build(y)
+            assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
+        finally:
+            L.pnb_grid_destroy(h)
