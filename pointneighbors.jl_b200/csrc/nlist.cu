@@ -78,6 +78,7 @@ struct ListCountCl {
     static constexpr int kPayBytes = 0;
     static constexpr int kWarpsPerCell = 2;
     static constexpr int kAccWords = 1;
+    static constexpr bool kBigTiles = true;
     uint32_t *out;
     struct State { int cnt; };
     __device__ __forceinline__ void save_acc(const State &, float *) const {}
@@ -109,6 +110,7 @@ struct ListFillCl {
     // the position of a hit in its list is its rank among the point's hits: the tile kernel
     // must hand over exact hit masks (no fp16 pre-filter)
     static constexpr bool kExactMasks = true;
+    static constexpr bool kBigTiles = true;
     const int64_t *offsets;
     int32_t *ids;
     // b0..b3: up to four ids waiting for one 16-byte store (tile kernel only)

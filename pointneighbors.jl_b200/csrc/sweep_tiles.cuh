@@ -39,9 +39,18 @@ namespace pnb {
 
 constexpr int kFTX = 4;                    // cells per tile
 constexpr int kFSlots = kFTX + 2;
-constexpr int kFCap = 1728;                // staged candidates per tile incl. padding (typical 6 * 256)
-constexpr int kFBlocks = kFCap / 32;
-constexpr int kFNBlkMax = 28;              // 32-blocks per cell (3 slots): up to 896 candidates
+// Staging capacity of a tile (candidates incl. padding; typical 6 * 256) and 32-blocks per cell
+// (3 slots): 1728 / 28 keeps the shared memory small enough for 2 (WCSPH) to 4 (count) CTAs per
+// SM.  The neighbour-list passes declare kBigTiles: measured on the 8 M periodic cloud (27.8
+// points per cell), 5 % of the tiles exceeded 1728 and cost 1.4 ms in the overflow kernel,
+// more than the larger tiles cost in occupancy (count 5.2 -> 5.9 ms, n-body 10.8 -> 14.7 ms
+// at 16.4 M points when every closure got them).
+template <class CL, class = void>
+struct wants_big_tiles { static constexpr bool value = false; };
+template <class CL>
+struct wants_big_tiles<CL, decltype((void)CL::kBigTiles)> { static constexpr bool value = CL::kBigTiles; };
+template <class CL> __host__ __device__ constexpr int tile_cap() { return wants_big_tiles<CL>::value ? 2304 : 1728; }
+template <class CL> __host__ __device__ constexpr int tile_nblk_max() { return wants_big_tiles<CL>::value ? 36 : 28; }
 constexpr float kHalfSentinel = 64.0f;     // padding candidates: farther than any real one
 // pre-filter thresholds in units of r^2, exactly representable in fp16.  Total rounding error of
 // the fp16 distance (derivation in DESIGN.md 5.2): < 0.0069 on non-periodic grids (|u_x| <= 3,
@@ -65,6 +74,7 @@ __host__ __device__ constexpr size_t tiles_smem_bytes()
     // mask planes: 1 = hit masks of the drain; 2 = certain hits + undecided band (exact modes)
     constexpr int planes = CL::kCountOnly ? (HALF ? 1 : 0)            // only the undecided band
                            : ((HALF && needs_exact_masks<CL>::value) ? 2 : 1);
+    constexpr int kFCap = tile_cap<CL>(), kFBlocks = kFCap / 32, kFNBlkMax = tile_nblk_max<CL>();
     return sizeof(float4) * kFCap                               // exact positions + id
            + (HALF ? (size_t)kFBlocks * ND * 16 * 4 : 0)        // packed fp16 coordinates
            + (size_t)kFCap * CL::kPayBytes                      // closure payload planes
@@ -152,6 +162,7 @@ k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ o
     constexpr int NE = kFSlots * NR;          // staged cells per tile
     constexpr int kFThreads = kFTX * kWPC * 32;
     constexpr int kCellThreads_ = kWPC * 32;
+    constexpr int kFCap = tile_cap<CL>(), kFBlocks = kFCap / 32, kFNBlkMax = tile_nblk_max<CL>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_pos = reinterpret_cast<float4 *>(smem_raw);
     uint32_t *s_half = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * kFCap);
