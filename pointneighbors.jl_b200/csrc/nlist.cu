@@ -359,7 +359,7 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
 // EXACT: the oracle's IEEE operation sequence per term; fast (default): one MUFU.RSQ + FMAs,
 // grad W / d = (-5 sigma / h^2) t^3 with t = 1 - d / (2 h) (the d of w(q)/d cancels).
 template <int ND, bool PER, bool EXACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)   // 64 registers: 32 warps / SM (5 blocks spill: 5.3 ms)
 k_tlsph_defgrad(GridP g, int64_t n, const int64_t *__restrict__ offsets,
                 const int32_t *__restrict__ ids, const float4 *__restrict__ rec,
                 const float *__restrict__ L, float h, float kernel_norm, float *__restrict__ F)
@@ -392,15 +392,24 @@ k_tlsph_defgrad(GridP g, int64_t n, const int64_t *__restrict__ offsets,
     int max_len = len;
 #pragma unroll
     for (int o = 16; o >= kG; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    // the ids of the NEXT round are fetched while the records of this round are in flight
+    int jn[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) jn[u] = (sub + kG * u < len) ? __ldg(my_ids + sub + kG * u) : -1;
     for (int k0 = sub; k0 < max_len; k0 += kG * kU) {
         int jj[kU];
 #pragma unroll
-        for (int u = 0; u < kU; u++) jj[u] = (k0 + kG * u < len) ? __ldg(my_ids + k0 + kG * u) : -1;
+        for (int u = 0; u < kU; u++) jj[u] = jn[u];
         float4 ra4[kU], rb4[kU];
 #pragma unroll
         for (int u = 0; u < kU; u++) {
             const int64_t j = jj[u] >= 0 ? jj[u] : ii;
             ldg256(rec + 2 * j, ra4[u], rb4[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const int kn = k0 + kG * kU + kG * u;
+            jn[u] = kn < len ? __ldg(my_ids + kn) : -1;
         }
 #pragma unroll
         for (int u = 0; u < kU; u++) {
