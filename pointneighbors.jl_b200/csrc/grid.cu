@@ -958,7 +958,7 @@ pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *o
 // A cell that receives more than K points sets error bit 3; the build is then redone as CSR.
 // ---------------------------------------------------------------------------------------------
 template <int ND, bool PER, int PPT>
-__global__ void __launch_bounds__(kBuildThreads)
+__global__ void __launch_bounds__(kBuildThreads, 6)
 k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
                  const int32_t *__restrict__ idx, int base, uint32_t K,
                  uint32_t *__restrict__ bcount, float4 *__restrict__ brec, int *__restrict__ err)
