@@ -973,3 +973,66 @@ def test_grid_from_padded_corners(pn, oracle):
             assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
         finally:
             L.pnb_grid_destroy(h)
+
+
+def test_update_sequence_layouts(pn, oracle):
+    """A sequence of update! calls on ONE search that walks through every build path: first build
+    (CSR), one-pass bucket builds, a cloud whose crowded cells overflow the buckets (fallback to
+    the CSR build and a new K), growing and shrinking point counts, an `eachindex_y` subset, a
+    domain error in the middle, and CSR consumers (exports, two-set sweep) between the builds.
+    After every step counts, CSR cell list and WCSPH sums are checked against the oracle."""
+    T = np.float32
+    r = T(0.1)
+    mn, mx = np.zeros(3, T), np.ones(3, T)
+    rng = np.random.default_rng(77)
+    lat = pn.benchmark_cloud((28, 28, 28), seed=3)[0]           # ~27 points per cell at r = 3/29
+    r = pn.benchmark_cloud((28, 28, 28), seed=3)[1]
+    mx = pn.benchmark_cloud((28, 28, 28), seed=3)[3]
+    clouds = [
+        ("lattice", lat),
+        ("perturbed", (lat + T(4e-4) * r * rng.standard_normal(lat.shape).astype(T)).astype(T)),
+        ("perturbed2", (lat + T(4e-3) * r * rng.standard_normal(lat.shape).astype(T)).astype(T)),
+        ("blob", np.concatenate([lat, (0.5 + 0.02 * rng.random((2500, 3))).astype(T)])),   # overflows K
+        ("lattice-again", lat),
+        ("fewer", lat[: len(lat) // 2]),
+        ("more", np.concatenate([lat, np.clip(lat[:5000] + T(0.3) * r, 0, mx - 1e-6).astype(T)])),
+    ]
+    nhs = make_grid(pn, 3, r, mn, mx)
+    og = oracle.Grid(3, r, mn, mx)
+    for k, (name, c) in enumerate(clouds):
+        c = np.clip(c, 0, mx).astype(T)
+        x = dev(c)
+        pn.update_(nhs, x, x) if k else pn.initialize_(nhs, x, x)
+        og.build(c)
+        cnt = torch.zeros(len(c), dtype=torch.int64, device="cuda")
+        pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+        assert (cnt.cpu().numpy() == og.count_neighbors(c, c)).all(), name
+        v, m, p, kw = _wcsph_inputs(pn, c, r, 3, seed=k)
+        dv = torch.zeros((len(c), 4), dtype=torch.float32, device="cuda")
+        f = pn.WCSPHInteract(dv, dev(v), dev(v), dev(m), dev(m), dev(p), dev(p), **kw)
+        pn.foreach_point_neighbor(f, x, x, nhs)
+        _, r64, rabs = og.wcsph(c, c, v, v, m, m, p, p, f.params_array(), wide=True)
+        assert np.all(np.abs(dv.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30), name
+        if k % 2 == 1:
+            cs, cp = nhs.export_csr()                      # CSR + canonical order on demand
+            assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all(), name
+            q = dev(c[::7] + T(0.2) * r)                   # two-set sweep between the builds
+            cq = torch.zeros(q.shape[0], dtype=torch.int64, device="cuda")
+            pn.foreach_point_neighbor(pn.CountNeighbors(cq), q, x, nhs)
+            assert (cq.cpu().numpy() == og.count_neighbors(q.cpu().numpy(), c)).all(), name
+            # the fused sweep still works after the layout was switched to CSR
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+            assert (cnt.cpu().numpy() == og.count_neighbors(c, c)).all(), name
+    # a domain error in the middle leaves the search rebuildable
+    bad = lat.copy()
+    bad[17, 1] = np.nan
+    with pytest.raises(pn.PointNeighborsError, match="NaN or outside the domain"):
+        pn.update_(nhs, dev(bad), dev(bad))
+    x = dev(lat)
+    pn.update_(nhs, x, x)
+    og.build(lat)
+    idx = np.arange(100, 9000)
+    pn.update_(nhs, x, x, eachindex_y=idx)
+    og.build(lat, eachindex_y=idx)
+    cs, cp = nhs.export_csr()
+    assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
