@@ -225,3 +225,52 @@ def test_point_cloud_generator(pn):
     coords, r, mn, mx = pn.benchmark_cloud((8, 6, 4))
     assert coords.dtype == np.float32 and r == np.float32(3.0) / np.float32(9)
     assert np.array_equal(mx, np.array([1.0, 0.75, 0.5], np.float32))
+
+
+def test_grid_params_f64_match_oracle(pn, oracle):
+    """pnb_grid_params_f64 (host arithmetic of the Float64 constructors) against the Float64
+    oracle on random boxes, incl. the reference's Float64 KAT -1.001 / 11.001
+    (test/cell_lists/full_grid.jl:28-29) and the element-type rule of the host mirror."""
+    import ctypes as C
+    L = pn._lib.lib()
+    pd = pn._lib._pd
+
+    def params64(nd, r, mn, mx, box=None):
+        mn = np.ascontiguousarray(mn, np.float64)
+        mx = np.ascontiguousarray(mx, np.float64)
+        pmin, pmax, cs = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
+        gs, nc = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        bmn = bmx = None
+        if box is not None:
+            b0 = np.ascontiguousarray(box[0], np.float64)
+            b1 = np.ascontiguousarray(box[1], np.float64)
+            bmn, bmx = b0.ctypes.data_as(pd), b1.ctypes.data_as(pd)
+        st = L.pnb_grid_params_f64(nd, float(r), mn.ctypes.data_as(pd), mx.ctypes.data_as(pd), bmn, bmx,
+                                   pmin, pmax, gs, nc, cs)
+        return st, (np.array(pmin[:nd]), np.array(pmax[:nd]), tuple(gs[:nd]), tuple(nc[:nd]),
+                    np.array(cs[:nd]))
+
+    st, (pmin, pmax, gs, _, _) = params64(2, 1.0, [0.0, 0.0], [10.0, 10.0])
+    assert st == 0 and pmin.tolist() == [-1.001, -1.001] and pmax.tolist() == [11.001, 11.001]
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        nd = int(rng.integers(1, 4))
+        mn = rng.normal(0, 3, nd)
+        mx = mn + rng.uniform(0.5, 4, nd)
+        r = np.float64(rng.uniform(0.02, 0.15))
+        box = (mn, mx) if rng.integers(0, 2) else None
+        st, (pmin, pmax, gs, nc, cs) = params64(nd, r, mn, mx, box)
+        og = oracle.Grid(nd, r, mn, mx, periodic_box=box, dtype=np.float64)
+        assert st == 0
+        assert og.grid_size == gs and og.n_cells == nc
+        assert np.array_equal(og.min_corner, pmin) and np.array_equal(og.max_corner, pmax)
+        assert np.array_equal(og.cell_size, cs)
+    # host mirror: Float64 only when radius AND corners are Float64
+    mn, mx = np.zeros(3), np.ones(3)
+    assert pn.FullGridCellList(min_corner=mn, max_corner=mx, search_radius=np.float64(0.1)).eltype == np.float64
+    assert pn.FullGridCellList(min_corner=mn, max_corner=mx, search_radius=np.float32(0.1)).eltype == np.float32
+    assert pn.FullGridCellList(min_corner=mn.astype(np.float32), max_corner=mx.astype(np.float32),
+                               search_radius=np.float64(0.1)).eltype == np.float32
+    cl = pn.FullGridCellList(min_corner=mn, max_corner=mx, search_radius=np.float64(0.1))
+    nhs = pn.GridNeighborhoodSearch[3](search_radius=np.float64(0.1), cell_list=cl)
+    assert nhs.eltype == np.float64 and pn.search_radius(nhs) == np.float64(0.1)
