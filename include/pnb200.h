@@ -140,6 +140,31 @@ pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndi
                                int64_t n_recv_down, const float *send_up, int64_t n_up,
                                const float *send_down, int64_t n_down, int32_t *scratch,
                                int64_t *out, void *stream);
+/* ---------------------------------------------------------------------------------------------
+ * GridNeighborhoodSearch{NDIMS}(; search_radius, periodic_box,
+ *                               cell_list = SpatialHashingCellList{NDIMS}(; list_size))
+ *   replaces: src/cell_lists/spatial_hashing.jl:24-61 (the table), src/nhs_grid.jl:100-126
+ *             (cell_size / n_cells of the search), src/gpu.jl:37-44 (adapt)
+ * The handle is a pnb_grid: initialize!/update! (pnb_grid_build_f32), every sweep, the neighbour
+ * lists and the CSR / DVoV exports work on it unchanged, with the 0-based hash key
+ * (spatial_hash(cell, list_size) - 1, :159-174) in place of the linear cell index and
+ * pnb_grid_total_cells() == list_size.  Cells are floor(coords / cell_size) (no corners: the
+ * domain is unbounded, src/nhs_grid.jl:636-638); the sweep applies the reference's collision
+ * checks (src/nhs_grid.jl:479-513), so neighbour sets equal those of every other search.
+ * A cell coordinate outside Int32 is the reference's InexactError (:176-183) -> PNB_ERR_DOMAIN.
+ * ------------------------------------------------------------------------------------------- */
+pnb_status pnb_grid_create_hashed_f32(int ndims, float search_radius, int64_t list_size,
+                                      const float *box_min, const float *box_max, pnb_grid **out);
+/* cell_list.coords (list_size x UInt128 as 4 little-endian uint32 words, coordinates_flattened
+ * :176-183; 0 = unused entry) and cell_list.collisions (list_size x Bool) after the last build,
+ * as the reference's serial insertion in ascending id order leaves them (push_cell!, :79-97).
+ * Either pointer may be NULL. */
+pnb_status pnb_grid_export_hash_table(const pnb_grid *g, uint32_t *coords, uint8_t *collisions,
+                                      void *stream);
+/* spatial_hash (src/cell_lists/spatial_hashing.jl:159-174), host, 0-based (the reference's key - 1);
+ * -1 on invalid arguments */
+int64_t pnb_spatial_hash(int ndims, const int64_t *cell, int64_t list_size);
+
 void pnb_grid_destroy(pnb_grid *g);
 int64_t pnb_grid_total_cells(const pnb_grid *g);
 int64_t pnb_grid_n_points(const pnb_grid *g); /* points in the cell list after the last build */

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         for suf in ("_f32", "_f64"):
             getattr(_lib, "pno_total_cells" + suf).restype = C.c_int64
             getattr(_lib, "pno_candidate_tests" + suf).restype = C.c_int64
+            getattr(_lib, "pno_spatial_hash" + suf).restype = C.c_int64
     return _lib
 
 
@@ -70,6 +71,7 @@ ERR_TEXT = {
        "periodicity. Please use no NHS for very small problems.",
     3: "cell list is full. Use a larger `max_points_per_cell`.",
     4: "BoundsError: neighbouring cell outside the cell grid",
+    5: "InexactError: a cell coordinate does not fit Int32 (coordinates_flattened)",
 }
 
 
@@ -305,6 +307,123 @@ class Grid:
         if rc:
             raise OracleError(rc)
         return offsets, ids[:int(offsets[-1])]
+
+
+class HashGrid:
+    """GridNeighborhoodSearch + SpatialHashingCellList (+ PeriodicBox)
+    (/root/reference/src/cell_lists/spatial_hashing.jl, hooks src/nhs_grid.jl:479-513).
+    Keys are 0-based (the reference's hash key minus 1)."""
+
+    def __init__(self, ndims, search_radius, list_size, periodic_box=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.suf = "_f32" if self.dtype == np.float32 else "_f64"
+        self.real = C.c_float if self.dtype == np.float32 else C.c_double
+        self.g = (_GridF32 if self.dtype == np.float32 else _GridF64)()
+        self.ndims = int(ndims)
+        self.list_size = int(list_size)
+        if periodic_box is not None:
+            bmn = np.ascontiguousarray(periodic_box[0], dtype=self.dtype)
+            bmx = np.ascontiguousarray(periodic_box[1], dtype=self.dtype)
+        else:
+            bmn = bmx = None
+        rc = self._fn("pno_hash_grid_init")(C.byref(self.g), self.ndims, self.real(search_radius),
+                                            int(periodic_box is not None), _ptr(bmn, self.real),
+                                            _ptr(bmx, self.real))
+        if rc:
+            raise OracleError(rc)
+        self.key_start = self.key_points = self.coords = self.collisions = None
+
+    def _fn(self, name):
+        return getattr(lib(), name + self.suf)
+
+    def _coords(self, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        assert x.ndim == 2 and x.shape[1] == self.ndims
+        return x
+
+    @property
+    def n_cells(self):
+        return tuple(int(v) for v in self.g.n_cells[:self.ndims])
+
+    @property
+    def cell_size(self):
+        return np.array(self.g.cell_size[:self.ndims], dtype=self.dtype)
+
+    def spatial_hash(self, cell):
+        c = np.zeros(3, dtype=np.int64)
+        c[:self.ndims] = cell
+        return int(self._fn("pno_spatial_hash")(self.ndims, _ptr(c, C.c_int64),
+                                                C.c_int64(self.list_size)))
+
+    def cell_coords(self, point):
+        p = np.ascontiguousarray(point, dtype=self.dtype)
+        out = np.zeros(3, dtype=np.int64)
+        self._fn("pno_hash_cell_coords")(C.byref(self.g), _ptr(p, self.real), _ptr(out, C.c_int64))
+        return tuple(int(v) for v in out[:self.ndims])
+
+    def build(self, y, eachindex_y=None):
+        y = self._coords(y)
+        idx = None if eachindex_y is None else np.ascontiguousarray(eachindex_y, dtype=np.int64)
+        n_idx = y.shape[0] if idx is None else idx.size
+        L = self.list_size
+        self.key_start = np.zeros(L + 1, dtype=np.int64)
+        self.key_points = np.zeros(max(n_idx, 1), dtype=np.int32)
+        self.coords = np.zeros((L, 3), dtype=np.int32)
+        self.collisions = np.zeros(L, dtype=np.uint8)
+        rc = self._fn("pno_hash_build")(C.byref(self.g), C.c_int64(L), _ptr(y, self.real),
+                                        C.c_int64(y.shape[0]), _ptr(idx, C.c_int64),
+                                        C.c_int64(n_idx), _ptr(self.key_start, C.c_int64),
+                                        _ptr(self.key_points, C.c_int32),
+                                        _ptr(self.coords, C.c_int32),
+                                        _ptr(self.collisions, C.c_uint8))
+        if rc:
+            raise OracleError(rc)
+        self.key_points = self.key_points[:n_idx]
+        return self
+
+    def points_in_cell(self, cell):
+        """cell_list[cell] (spatial_hashing.jl:141-143): the list of the cell's hash key."""
+        k = self.spatial_hash(cell)
+        return self.key_points[self.key_start[k]:self.key_start[k + 1]].tolist()
+
+    def _table(self):
+        assert self.key_start is not None, "call build() first"
+        return (C.byref(self.g), C.c_int64(self.list_size), _ptr(self.key_start, C.c_int64),
+                _ptr(self.key_points, C.c_int32), _ptr(self.coords, C.c_int32),
+                _ptr(self.collisions, C.c_uint8))
+
+    def count_neighbors(self, x, y, points=None):
+        x, y = self._coords(x), self._coords(y)
+        p = None if points is None else np.ascontiguousarray(points, dtype=np.int64)
+        out = np.zeros(x.shape[0], dtype=np.int64)
+        self._fn("pno_hash_count_neighbors")(*self._table(), _ptr(x, self.real),
+                                             C.c_int64(x.shape[0]), _ptr(y, self.real),
+                                             _ptr(p, C.c_int64), C.c_int64(0 if p is None else p.size),
+                                             _ptr(out, C.c_int64))
+        return out
+
+    def neighbor_lists(self, x, y, sort=True):
+        x, y = self._coords(x), self._coords(y)
+        offsets = np.zeros(x.shape[0] + 1, dtype=np.int64)
+        fn = self._fn("pno_hash_neighbor_lists")
+        args = (*self._table(), _ptr(x, self.real), C.c_int64(x.shape[0]), _ptr(y, self.real),
+                _ptr(offsets, C.c_int64))
+        fn(*args, None, C.c_int(int(sort)))
+        ids = np.zeros(max(int(offsets[-1]), 1), dtype=np.int32)
+        fn(*args, _ptr(ids, C.c_int32), C.c_int(int(sort)))
+        return offsets, ids[:int(offsets[-1])]
+
+    def nbody(self, x, y, mass, G, wide=False):
+        x, y = self._coords(x), self._coords(y)
+        mass = np.ascontiguousarray(mass, dtype=self.dtype)
+        dv = np.zeros_like(x)
+        dv64 = np.zeros(x.shape, dtype=np.float64) if wide else None
+        dvabs = np.zeros(x.shape, dtype=np.float64) if wide else None
+        self._fn("pno_hash_nbody")(*self._table(), _ptr(x, self.real), C.c_int64(x.shape[0]),
+                                   _ptr(y, self.real), _ptr(mass, self.real), self.real(G),
+                                   _ptr(dv, self.real), _ptr(dv64, C.c_double),
+                                   _ptr(dvabs, C.c_double))
+        return (dv, dv64, dvabs) if wide else dv
 
 
 def trivial_lists(x, y, search_radius, periodic_box=None, dtype=np.float32):

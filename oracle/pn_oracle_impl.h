@@ -795,6 +795,200 @@ void FN(pno_periodic_coords)(int ndims, const REAL *box_min, const REAL *box_max
     }
 }
 
+
+/* ---------------------------------------------------------------------------------------
+ * SpatialHashingCellList (cell_lists/spatial_hashing.jl) behind a GridNeighborhoodSearch
+ * (SURVEY.md 8f rank 3).  The table has list_size entries (keys are 0-based here); per key:
+ * the list of point ids, the cell coordinates stored by the first insertion (`coords`, the
+ * reference flattens them into a UInt128 with 0 = "unused", spatial_hashing.jl:56,176-183) and
+ * the collision flag.  Serial insertion order (push_cell!, :79-97) = ascending ids: the
+ * reference's ParallelUpdate does the same with atomics (:99-118), where the stored cell of a
+ * colliding key depends on the arrival order.
+ * ------------------------------------------------------------------------------------- */
+
+/* GridNeighborhoodSearch ctor (nhs_grid.jl:100-126) for a cell list without corners */
+int FN(pno_hash_grid_init)(GRID *g, int ndims, REAL r, int periodic, const REAL *box_min,
+                           const REAL *box_max)
+{
+    REAL zero[3] = {0, 0, 0};
+    int rc = FN(pno_grid_init)(g, ndims, r, zero, zero, periodic, box_min, box_max);
+    for (int d = 0; d < 3; d++) { g->min_corner[d] = 0; g->max_corner[d] = 0; g->grid_size[d] = 0; }
+    return rc;
+}
+
+/* spatial_hash (spatial_hashing.jl:159-174), Julia Int64 products wrap; returned 0-based */
+int64_t FN(pno_spatial_hash)(int ndims, const int64_t *cell, int64_t list_size)
+{
+    uint64_t h = (uint64_t)cell[0] * 73856093ULL;
+    if (ndims > 1) h ^= (uint64_t)cell[1] * 19349663ULL;
+    if (ndims > 2) h ^= (uint64_t)cell[2] * 83492791ULL;
+    return FN(pno_floormod)((int64_t)h, list_size);
+}
+
+/* cell_coords (nhs_grid.jl:622-638): floor_to_int.(coords ./ cell_size), then the periodic wrap */
+void FN(pno_hash_cell_coords)(const GRID *g, const REAL *x, int64_t *cell)
+{
+    for (int d = 0; d < g->ndims; d++) cell[d] = FN(pno_floor_to_int)(x[d] / g->cell_size[d]);
+    for (int d = g->ndims; d < 3; d++) cell[d] = 0;
+    FN(pno_periodic_cell)(g, cell);
+}
+
+/*
+ * initialize_grid! (nhs_grid.jl:255-281) with push_cell! (spatial_hashing.jl:79-97), points
+ * visited in the order of idx (NULL = 0..n-1).  key_start[L+1] / key_points[n_idx] = the lists in
+ * insertion order, coords[3 L] (0 for unused dims), collisions[L].
+ * returns 0 ok, 5 = a cell coordinate does not fit Int32 (InexactError, :176-183).
+ */
+int FN(pno_hash_build)(const GRID *g, int64_t list_size, const REAL *y, int64_t n,
+                       const int64_t *idx, int64_t n_idx, int64_t *key_start, int32_t *key_points,
+                       int32_t *coords, uint8_t *collisions)
+{
+    const int64_t L = list_size;
+    if (idx == NULL) n_idx = n;
+    for (int64_t k = 0; k <= L; k++) key_start[k] = 0;
+    memset(coords, 0, sizeof(int32_t) * 3 * (size_t)L);
+    memset(collisions, 0, (size_t)L);
+    if ((double)g->search_radius < 2.220446049250313e-16) return 0;
+    int64_t *key = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_idx > 0 ? n_idx : 1));
+    for (int64_t k = 0; k < n_idx; k++) {
+        int64_t p = idx ? idx[k] : k, cell[3];
+        FN(pno_hash_cell_coords)(g, y + p * g->ndims, cell);
+        for (int d = 0; d < g->ndims; d++)
+            if (cell[d] > INT32_MAX || cell[d] < INT32_MIN) { free(key); return 5; }
+        key[k] = FN(pno_spatial_hash)(g->ndims, cell, L);
+        key_start[key[k] + 1]++;
+        int32_t *cc = coords + 3 * key[k];
+        if (cc[0] == 0 && cc[1] == 0 && cc[2] == 0) {         /* typemin(UInt128): unused */
+            for (int d = 0; d < 3; d++) cc[d] = (int32_t)cell[d];
+        } else if (cc[0] != cell[0] || cc[1] != cell[1] || cc[2] != cell[2]) {
+            collisions[key[k]] = 1;
+        }
+    }
+    for (int64_t k = 0; k < L; k++) key_start[k + 1] += key_start[k];
+    int64_t *cursor = (int64_t *)malloc(sizeof(int64_t) * (size_t)(L > 0 ? L : 1));
+    memcpy(cursor, key_start, sizeof(int64_t) * (size_t)L);
+    for (int64_t k = 0; k < n_idx; k++) key_points[cursor[key[k]]++] = (int32_t)(idx ? idx[k] : k);
+    free(cursor);
+    free(key);
+    return 0;
+}
+
+/* mapreduce_neighbor_inner (nhs_grid.jl:519-575) with the hashing hooks check_cell_collision
+ * (:501-513) and check_collision (:486-492) for one point */
+static inline void
+FN(pno_hash_sweep_point)(const GRID *g, int64_t L, const int64_t *key_start,
+                         const int32_t *key_points, const int32_t *coords,
+                         const uint8_t *collisions, const REAL *xi, int64_t i, const REAL *y,
+                         FN(pno_pair_fn) f, void *ctx)
+{
+    const int nd = g->ndims;
+    const REAL r = g->search_radius;
+    const REAL r2 = r * r;
+    int64_t cell[3];
+    FN(pno_hash_cell_coords)(g, xi, cell);
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int d = 0; d < nd; d++) { lo[d] = -1; hi[d] = 1; }
+    for (int o3 = lo[2]; o3 <= hi[2]; o3++)
+        for (int o2 = lo[1]; o2 <= hi[1]; o2++)
+            for (int o1 = lo[0]; o1 <= hi[0]; o1++) {
+                int64_t nc[3] = {FN(pno_wrap_add)(cell[0], o1), FN(pno_wrap_add)(cell[1], o2),
+                                 FN(pno_wrap_add)(cell[2], o3)};
+                FN(pno_periodic_cell)(g, nc);
+                const int64_t key = FN(pno_spatial_hash)(nd, nc, L);
+                const int32_t *cc = coords + 3 * key;
+                const int cell_collision = collisions[key] || cc[0] != (int32_t)nc[0] ||
+                                           cc[1] != (int32_t)nc[1] || cc[2] != (int32_t)nc[2];
+                for (int64_t k = key_start[key]; k < key_start[key + 1]; k++) {
+                    int64_t j = key_points[k];
+                    const REAL *yj = y + j * nd;
+                    REAL p[3] = {0, 0, 0};
+                    for (int d = 0; d < nd; d++) p[d] = xi[d] - yj[d];
+                    REAL d2 = p[0] * p[0];
+                    for (int d = 1; d < nd; d++) d2 = d2 + p[d] * p[d];
+                    d2 = FN(pno_periodic_fix)(g, p, d2, r2);
+                    if (d2 <= r2) {
+                        if (cell_collision) {
+                            int64_t jc[3];
+                            FN(pno_hash_cell_coords)(g, yj, jc);
+                            if (jc[0] != nc[0] || jc[1] != nc[1] || jc[2] != nc[2]) continue;
+                        }
+                        f(ctx, i, j, p, (REAL)sqrt((double)d2));
+                    }
+                }
+            }
+}
+
+static void FN(pno_hash_foreach)(const GRID *g, int64_t L, const int64_t *key_start,
+                                 const int32_t *key_points, const int32_t *coords,
+                                 const uint8_t *collisions, const REAL *x, int64_t nx,
+                                 const REAL *y, const int64_t *points, int64_t npoints,
+                                 FN(pno_pair_fn) f, void *ctx)
+{
+    if (points == NULL) npoints = nx;
+    if ((double)g->search_radius < 2.220446049250313e-16) return;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < npoints; k++) {
+        int64_t i = points ? points[k] : k;
+        FN(pno_hash_sweep_point)(g, L, key_start, key_points, coords, collisions,
+                                 x + i * g->ndims, i, y, f, ctx);
+    }
+}
+
+/* foreach_point_neighbor with the count closure (count_neighbors.jl:24-27) on the hashed list */
+void FN(pno_hash_count_neighbors)(const GRID *g, int64_t L, const int64_t *key_start,
+                                  const int32_t *key_points, const int32_t *coords,
+                                  const uint8_t *collisions, const REAL *x, int64_t nx,
+                                  const REAL *y, const int64_t *points, int64_t npoints,
+                                  int64_t *out)
+{
+    for (int64_t i = 0; i < nx; i++) out[i] = 0;
+    FN(pno_hash_foreach)(g, L, key_start, key_points, coords, collisions, x, nx, y, points,
+                         npoints, FN(pno_cl_count), out);
+}
+
+/* neighbour lists in sweep order (two passes like pno_neighbor_lists), optionally sorted */
+void FN(pno_hash_neighbor_lists)(const GRID *g, int64_t L, const int64_t *key_start,
+                                 const int32_t *key_points, const int32_t *coords,
+                                 const uint8_t *collisions, const REAL *x, int64_t nx,
+                                 const REAL *y, int64_t *offsets, int32_t *ids, int sort)
+{
+    int64_t *counts = (int64_t *)calloc((size_t)(nx > 0 ? nx : 1), sizeof(int64_t));
+    FN(pno_list_ctx) c = {counts, offsets, ids};
+    if (ids == NULL) {
+        FN(pno_hash_foreach)(g, L, key_start, key_points, coords, collisions, x, nx, y, NULL, nx,
+                             FN(pno_cl_list_count), &c);
+        offsets[0] = 0;
+        for (int64_t i = 0; i < nx; i++) offsets[i + 1] = offsets[i] + counts[i];
+    } else {
+        FN(pno_hash_foreach)(g, L, key_start, key_points, coords, collisions, x, nx, y, NULL, nx,
+                             FN(pno_cl_list_fill), &c);
+        if (sort) {
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < nx; i++)
+                qsort(ids + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), sizeof(int32_t),
+                      FN(pno_cmp_i32));
+        }
+    }
+    free(counts);
+}
+
+/* n-body / WCSPH closures over the hashed list (same closures as the full grid) */
+void FN(pno_hash_nbody)(const GRID *g, int64_t L, const int64_t *key_start,
+                        const int32_t *key_points, const int32_t *coords,
+                        const uint8_t *collisions, const REAL *x, int64_t nx, const REAL *y,
+                        const REAL *mass, REAL G, REAL *dv, double *dv64, double *dvabs)
+{
+    const int nd = g->ndims;
+    for (int64_t k = 0; k < nx * nd; k++) {
+        dv[k] = 0;
+        if (dv64) dv64[k] = 0.0;
+        if (dvabs) dvabs[k] = 0.0;
+    }
+    FN(pno_nbody_ctx) c = {nd, mass, G, dv, dv64, dvabs};
+    FN(pno_hash_foreach)(g, L, key_start, key_points, coords, collisions, x, nx, y, NULL, nx,
+                         FN(pno_cl_nbody), &c);
+}
+
 #undef PNO_VIEW
 #undef GRID
 #undef FN

@@ -27,7 +27,8 @@ struct GridP {
     int off[3];        // window offset: local cell = global cell - off (0 for a full grid)
     float bsize[3];    // periodic box size
     float wrap_d2;     // d2 below this can never be changed by the periodic fix (see periodic_fix)
-    int total_cells;
+    int total_cells;   // cells of the grid; entries of the hash table (list_size) when hashed
+    int hashed;        // SpatialHashingCellList: cell -> key = spatial_hash(cell, total_cells)
 };
 
 // Float64 searches (f64.cuh): the same scalars in double, and the cell-ordered record

@@ -13,6 +13,7 @@
 
 #include "grid.cuh"
 #include "f64.cuh"
+#include "hashgrid.cuh"
 
 namespace pnb {
 
@@ -184,6 +185,24 @@ static pnb_status grid_params_host(int ndims, float r, const float *min_corner,
     return PNB_OK;
 }
 
+
+pnb_status grid_alloc_common(pnb_grid *g, int64_t C)
+{
+    PNB_CUDA(cudaGetDevice(&g->device));
+    // cell_start = alloc + 3 so that cell_start + 1 (the scan output / scatter cursor) is 16-byte
+    // aligned; cell_start[0] = 0 is written here once and never again
+    PNB_CUDA(cudaMalloc(&g->cell_start_alloc, sizeof(uint32_t) * (size_t)(C + 8)));
+    g->cell_start = g->cell_start_alloc + 3;
+    PNB_CUDA(cudaMalloc(&g->cell_count, sizeof(uint32_t) * (size_t)(C + 4)));
+    PNB_CUDA(cudaMemset(g->cell_start_alloc, 0, sizeof(uint32_t) * (size_t)(C + 8)));
+    PNB_CUDA(cudaMemset(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 4)));
+    PNB_CUDA(cudaHostAlloc(&g->h_err, 2 * sizeof(int), cudaHostAllocMapped));
+    g->h_err[0] = g->h_err[1] = 0;
+    PNB_CUDA(cudaHostGetDevicePointer(&g->d_err, g->h_err, 0));
+    PNB_CUDA(cudaMalloc(&g->scan_ticket, sizeof(unsigned int)));
+    PNB_CUDA(cudaMemset(g->scan_ticket, 0, sizeof(unsigned int)));
+    return PNB_OK;
+}
 }  // namespace pnb
 
 using namespace pnb;
@@ -324,34 +343,8 @@ extern "C" pnb_status pnb_grid_create_window_f32(int ndims, float r, const float
     p.wrap_d2 = p.periodic ? (0.49f * min_size) * (0.49f * min_size) : INFINITY;
     if (p.periodic && !(p.wrap_d2 > p.r2)) p.wrap_d2 = p.r2;  // cannot happen with >= 3 cells; stay exact
 
-    cudaError_t e = cudaGetDevice(&g->device);
-    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaGetDevice"); }
-    auto fail = [&](cudaError_t err, const char *what) {
-        pnb_status s = cuda_fail(err, what);
-        pnb_grid_destroy(g);
-        return s;
-    };
-    int64_t C = total;
-    // cell_start = alloc + 3 so that cell_start + 1 (the scan output / scatter cursor) is 16-byte
-    // aligned; cell_start[0] = 0 is written here once and never again
-    if ((e = cudaMalloc(&g->cell_start_alloc, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
-        return fail(e, "cudaMalloc cell_start");
-    g->cell_start = g->cell_start_alloc + 3;
-    if ((e = cudaMalloc(&g->cell_count, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
-        return fail(e, "cudaMalloc cell_count");
-    if ((e = cudaMemset(g->cell_start_alloc, 0, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
-        return fail(e, "cudaMemset");
-    if ((e = cudaMemset(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
-        return fail(e, "cudaMemset");
-    if ((e = cudaHostAlloc(&g->h_err, 2 * sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
-        return fail(e, "cudaHostAlloc");
-    g->h_err[0] = g->h_err[1] = 0;
-    if ((e = cudaHostGetDevicePointer(&g->d_err, g->h_err, 0)) != cudaSuccess)
-        return fail(e, "cudaHostGetDevicePointer");
-    if ((e = cudaMalloc(&g->scan_ticket, sizeof(unsigned int))) != cudaSuccess)
-        return fail(e, "cudaMalloc ticket");
-    if ((e = cudaMemset(g->scan_ticket, 0, sizeof(unsigned int))) != cudaSuccess)
-        return fail(e, "cudaMemset");
+    st = grid_alloc_common(g, total);
+    if (st != PNB_OK) { pnb_grid_destroy(g); return st; }
     *out = g;
     return PNB_OK;
 }
@@ -361,6 +354,7 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     if (!g) return;
     cudaFree(g->cell_start_alloc);
     cudaFree(g->xq_start_alloc);
+    cudaFree(g->hmeta);
     cudaFree(g->xq_sorted);
     cudaFree(g->bcount);
     cudaFree(g->brec);
@@ -1061,7 +1055,7 @@ __global__ void k_max_cell_count(int64_t n_cells, const uint32_t *__restrict__ s
     if (lane_id() == 0 && v > 0u) atomicMax(out, v);
 }
 
-static pnb_status ensure_point_capacity(pnb_grid *g, int64_t n)
+pnb_status ensure_point_capacity(pnb_grid *g, int64_t n)
 {
     if (n <= g->cap_points) return PNB_OK;
     cudaFree(g->cell_points); g->cell_points = nullptr;
@@ -1233,6 +1227,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
     if (g->template_search) {
         // nhs_grid.jl:263-267: zero search radius -> emptied cell list, nothing else
         PNB_CUDA(cudaMemsetAsync(g->cell_start, 0, sizeof(uint32_t) * (size_t)(C + 1), s));
+        if (g->hashed) PNB_CUDA(cudaMemsetAsync(g->hmeta, 0, sizeof(int4) * (size_t)C, s));
         PNB_CUDA(cudaStreamSynchronize(s));
         g->n_built = 0;
         g->built = true;
@@ -1248,6 +1243,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         return PNB_ERR_ARG;
     }
     if (n_idx > 0 && y == nullptr) { set_error("y is NULL"); return PNB_ERR_ARG; }
+    if (g->hashed) return hash_build(g, y, n, eachindex_y, n_idx, index_base, s);
     pnb_status st = ensure_point_capacity(g, n_idx);
     if (st != PNB_OK) return st;
     g->bucket_valid = false;
@@ -1373,6 +1369,13 @@ __global__ void k_point_cells(GridP g, const float *__restrict__ x, int64_t n,
     float p[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int d = 0; d < ND; d++) p[d] = x[i * ND + d];
+    if (g.hashed) {
+        // SpatialHashingCellList: the 0-based table key of the point's cell (-1: not Int32)
+        long long hc[3];
+        bool ok = g.periodic ? hash_cell_coords<ND, true>(g, p, hc) : hash_cell_coords<ND, false>(g, p, hc);
+        out[i] = ok ? (int)spatial_hash_key<ND>(hc, g.total_cells) : -1;
+        return;
+    }
     int cc[3];
     out[i] = point_cell<ND>(g, p, cc);
 }

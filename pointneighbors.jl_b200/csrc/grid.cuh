@@ -43,6 +43,11 @@ struct pnb_grid {
     pnb::Rec64 *sorted64_tmp;  // scatter target before the per-cell sort
     double padded_min64[3], padded_max64[3], cell_size64[3];
 
+    // SpatialHashingCellList (hashgrid.cu): per key (c1, c2, c3, flags) = the cell stored by the
+    // first insertion (cell_list.coords) and bit 0 of flags = cell_list.collisions
+    bool hashed;
+    int4 *hmeta;               // [list_size]
+
     // cell-ordered copy of the query points of a two-set sweep (x != y), built per sweep
     uint32_t *xq_start_alloc, *xq_start;   // [C+1]
     float4 *xq_sorted;                     // [xq_cap]
@@ -77,6 +82,12 @@ struct pnb_grid {
 };
 
 namespace pnb {
+// device buffers every grid handle owns (offsets, histogram, error word, scan ticket) for C cells
+pnb_status grid_alloc_common(pnb_grid *g, int64_t C);
+pnb_status ensure_point_capacity(pnb_grid *g, int64_t n);
+// initialize!/update! of a hashed grid (hashgrid.cu)
+pnb_status hash_build(pnb_grid *g, const float *y, int64_t n, const int32_t *idx, int64_t n_idx,
+                      int base, cudaStream_t s);
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
 pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *points_per_cell,

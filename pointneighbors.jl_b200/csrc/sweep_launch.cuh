@@ -3,6 +3,7 @@
 
 #include "sweep.cuh"
 #include "sweep_tiles.cuh"
+#include "hashgrid.cuh"
 
 namespace pnb {
 
@@ -125,6 +126,25 @@ static pnb_status launch_sweep(pnb_grid *g, bool fast, bool tiles, const float *
 {
     if (g->template_search || g->n_built == 0) return PNB_OK;  // every neighbourhood is empty
     const bool per = g->p.periodic != 0;
+    if (g->hashed) {
+        // SpatialHashingCellList: always one thread per query point over the hash table
+        if (n_loop <= 0) return PNB_OK;
+        ProfScope ps(PH_SWEEP_POINTS, s);
+        const unsigned blocks = (unsigned)div_up(n_loop, 128);
+#define PNB_HASH(ND)                                                                               \
+    if (per) k_sweep_points_hash<ND, true, CL><<<blocks, 128, 0, s>>>(                             \
+        g->p, g->cell_start, g->sorted, g->hmeta, x, n_loop, points, base, cl, g->d_err);          \
+    else k_sweep_points_hash<ND, false, CL><<<blocks, 128, 0, s>>>(                                \
+        g->p, g->cell_start, g->sorted, g->hmeta, x, n_loop, points, base, cl, g->d_err)
+        switch (g->p.ndims) {
+            case 1: PNB_HASH(1); break;
+            case 2: PNB_HASH(2); break;
+            default: PNB_HASH(3); break;
+        }
+#undef PNB_HASH
+        PNB_LAUNCHED();
+        return PNB_OK;
+    }
     switch (g->p.ndims) {
         case 1:
             return per ? launch_nd<1, true>(g, fast, tiles, x, n_loop, points, base, cl, s)

@@ -74,6 +74,9 @@ SIGNATURES = {
     "pnb_count_neighbors_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
     "pnb_nlist_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), _vp]),
     "pnb_nlist_pairs_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnb_grid_create_hashed_f32": (C.c_int, [C.c_int, _f32, _i64, _pf, _pf, C.POINTER(_vp)]),
+    "pnb_grid_export_hash_table": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "pnb_spatial_hash": (_i64, [C.c_int, _pi64, _i64]),
     "pnb_grid_destroy": (None, [_vp]),
     "pnb_grid_total_cells": (_i64, [_vp]),
     "pnb_grid_n_points": (_i64, [_vp]),

@@ -32,7 +32,8 @@ __all__ = [
     "ArgumentError", "PointNeighborsError", "BoundsError",
     "ParallelUpdate", "SerialUpdate", "ParallelIncrementalUpdate", "SemiParallelUpdate",
     "SerialIncrementalUpdate", "DynamicVectorOfVectors",
-    "PeriodicBox", "FullGridCellList", "GridNeighborhoodSearch", "PrecomputedNeighborhoodSearch",
+    "PeriodicBox", "FullGridCellList", "SpatialHashingCellList", "spatial_hash",
+    "GridNeighborhoodSearch", "PrecomputedNeighborhoodSearch",
     "initialize_", "update_", "initialize", "update", "foreach_point_neighbor",
     "copy_neighborhood_search", "freeze_neighborhood_search", "requires_update",
     "search_radius", "ndims", "CountNeighbors", "NBodyGravity", "WCSPHInteract",
@@ -91,6 +92,16 @@ class DynamicVectorOfVectors:
 
     def __class_getitem__(cls, eltype):
         return cls(eltype)
+
+
+class _ParametricBase(type):
+    """`GridNeighborhoodSearch[3](...)` stands for Julia's `GridNeighborhoodSearch{3}(; ...)`."""
+
+    def __getitem__(cls, ndims_):
+        def ctor(**kwargs):
+            return cls(int(ndims_), **kwargs)
+        ctor.__name__ = f"{cls.__name__}[{ndims_}]"
+        return ctor
 
 
 def _as_real_vector(v, what):
@@ -201,27 +212,62 @@ class FullGridCellList:
         return float(self.search_radius) < _EPS64
 
 
+def spatial_hash(cell, list_size) -> int:
+    """spatial_hash(cell, list_size)  (src/cell_lists/spatial_hashing.jl:159-174), 1-based like the
+    reference (the device table uses key - 1)."""
+    c = (C.c_int64 * 3)(*([int(v) for v in cell] + [0] * (3 - len(cell))))
+    k = int(_lib.lib().pnb_spatial_hash(len(cell), c, int(list_size)))
+    if k < 0:
+        raise ArgumentError("spatial_hash takes a 1-, 2- or 3-tuple and a positive list_size")
+    return k + 1
+
+
+class SpatialHashingCellList(metaclass=_ParametricBase):
+    """SpatialHashingCellList{NDIMS}(; list_size, backend, max_points_per_cell)
+    (src/cell_lists/spatial_hashing.jl:24-61): an unbounded domain hashed into `list_size` lists
+    (about 2 * n_points is recommended, :9-10).  `SpatialHashingCellList[3](list_size=...)`."""
+
+    def __init__(self, ndims_: int, *, list_size: int,
+                 backend=DynamicVectorOfVectors[np.int32], max_points_per_cell: int = 100):
+        if not isinstance(backend, DynamicVectorOfVectors):
+            raise ArgumentError("only the DynamicVectorOfVectors backend is GPU-compatible "
+                                "(src/cell_lists/spatial_hashing.jl:42-49)")
+        if int(ndims_) not in (1, 2, 3):
+            raise ArgumentError("`NDIMS` must be 1, 2, or 3")
+        if int(list_size) < 1:
+            raise ArgumentError("`list_size` must be positive")
+        self._ndims = int(ndims_)
+        self.list_size = int(list_size)
+        self.backend = backend
+        self.max_points_per_cell = int(max_points_per_cell)
+        self.eltype = np.dtype(np.float32)
+        self.search_radius = np.float32(0)
+        self._user_min = np.zeros(3, dtype=np.float32)   # no corners: the domain is unbounded
+        self._user_max = np.zeros(3, dtype=np.float32)
+
+    def ndims(self):
+        return self._ndims
+
+
 def supported_update_strategies(cell_list):
     # src/cell_lists/full_grid.jl:39-42 lists five strategies for the CPU; on the device the two
     # full-rebuild strategies exist.
     return (ParallelUpdate, SerialUpdate)
 
 
-def copy_cell_list(cell_list: FullGridCellList, search_radius, periodic_box):
-    """src/cell_lists/full_grid.jl:179-185 -- re-pads from the STORED corners."""
+def copy_cell_list(cell_list, search_radius, periodic_box):
+    """src/cell_lists/full_grid.jl:179-185 -- re-pads from the STORED corners;
+    src/cell_lists/spatial_hashing.jl:129-139 -- same list_size, backend and capacity."""
+    if isinstance(cell_list, SpatialHashingCellList):
+        return SpatialHashingCellList(cell_list._ndims, list_size=cell_list.list_size,
+                                      backend=cell_list.backend,
+                                      max_points_per_cell=cell_list.max_points_per_cell)
     return FullGridCellList(min_corner=cell_list.min_corner, max_corner=cell_list.max_corner,
                             search_radius=search_radius, backend=cell_list.backend,
                             max_points_per_cell=cell_list.max_points_per_cell)
 
 
-class _Parametric(type):
-    """`GridNeighborhoodSearch[3](...)` stands for Julia's `GridNeighborhoodSearch{3}(; ...)`."""
-
-    def __getitem__(cls, ndims_):
-        def ctor(**kwargs):
-            return cls(int(ndims_), **kwargs)
-        ctor.__name__ = f"{cls.__name__}[{ndims_}]"
-        return ctor
+_Parametric = _ParametricBase
 
 
 class GridNeighborhoodSearch(metaclass=_Parametric):
@@ -233,7 +279,8 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
         self._ndims = int(ndims_)
         if cell_list is None:
             raise ArgumentError("the default DictionaryCellList is not GPU-compatible "
-                                "(src/cell_lists/dictionary.jl:8-10); pass a FullGridCellList")
+                                "(src/cell_lists/dictionary.jl:8-10); pass a FullGridCellList "
+                                "or a SpatialHashingCellList")
         if cell_list.ndims() != self._ndims:
             raise ArgumentError(f"a {self._ndims}D cell list is required for "
                                 f"a GridNeighborhoodSearch{{{self._ndims}}}")
@@ -325,6 +372,19 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
                                     "`search_radius` (src/nhs_grid.jl:60-65)")
             cl = self.cell_list
             h = C.c_void_p()
+            if isinstance(cl, SpatialHashingCellList):
+                if self._window is not None:
+                    raise ArgumentError("slab windows need a FullGridCellList")
+                bmn = bmx = None
+                if self.periodic_box is not None:
+                    bmn_a = np.ascontiguousarray(self.periodic_box.min_corner, dtype=np.float32)
+                    bmx_a = np.ascontiguousarray(self.periodic_box.max_corner, dtype=np.float32)
+                    bmn, bmx = bmn_a.ctypes.data_as(_lib._pf), bmx_a.ctypes.data_as(_lib._pf)
+                check(_lib.lib().pnb_grid_create_hashed_f32(
+                    self._ndims, np.float32(self.search_radius), cl.list_size, bmn, bmx,
+                    C.byref(h)))
+                self._handle = h
+                return self._handle
             bmn = bmx = None
             if self.periodic_box is not None:
                 bmn_a = np.ascontiguousarray(self.periodic_box.min_corner, dtype=np.float32)
@@ -377,6 +437,32 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
         check(_lib.lib().pnb_grid_export_dvov(self._grid(), backend.data_ptr(), lengths.data_ptr(),
                                               m, index_base, _stream()))
         return backend, lengths
+
+    def export_hash_table(self):
+        """SpatialHashingCellList only: (coords, collisions) = cell_list.coords as (list_size, 3)
+        int32 cell coordinates (the three low words of the reference's UInt128; zeros = unused
+        entry) and cell_list.collisions as bool (src/cell_lists/spatial_hashing.jl:24-29)."""
+        torch = _torch()
+        L = self.total_cells()
+        words = torch.zeros((L, 4), dtype=torch.int32, device="cuda")
+        coll = torch.zeros(L, dtype=torch.uint8, device="cuda")
+        check(_lib.lib().pnb_grid_export_hash_table(self._grid(), words.data_ptr(),
+                                                    coll.data_ptr(), _stream()))
+        return words[:, :3].contiguous(), coll.bool()
+
+    def points_in_cell(self, cell):
+        """cell_list[cell] (spatial_hashing.jl:141-143 / full_grid.jl:163-169): 0-based ids."""
+        cs, cp = self.export_csr()
+        if isinstance(self.cell_list, SpatialHashingCellList):
+            k = spatial_hash(cell, self.cell_list.list_size) - 1
+        else:
+            gs = self.cell_list.n_cells_per_dimension
+            k, stride = 0, 1
+            for d in range(self._ndims):
+                k += (int(cell[d]) - 1) * stride
+                stride *= gs[d]
+        cs = cs.cpu().numpy()
+        return cp.cpu().numpy()[cs[k]:cs[k + 1]].tolist()
 
     def point_cells(self, x):
         """0-based linear cell index of every point of x, -1 outside (cell_coords + cell_index)."""

@@ -206,3 +206,89 @@ def test_nbody_dvov_matches_csr(oracle):
     dv2 = g.nbody(c, c, mass, G, use_dvov=True)
     assert np.abs(dv2 - dv64).max() <= 1e-5 * dvabs.max()
     assert np.abs(dv - dv64).max() <= 1e-5 * dvabs.max()
+
+
+# ---------------------------------------------------------------------------------------------
+# SpatialHashingCellList
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", [0, 1])
+def test_spatial_hashing_collisions(oracle, kats, case, dtype):
+    """test/cell_lists/spatial_hashing.jl:2-67: two cells with the same hash key, one of them
+    empty / both occupied; the collision checks keep the neighbour sets exact."""
+    k = kats["spatial_hashing"]
+    c = k["cases"][case]
+    coords = np.array(c["coordinates_rows"], dtype=dtype).T.copy()
+    r = dtype(k["search_radius"])
+    h = oracle.HashGrid(2, r, c["list_size"], dtype=dtype).build(coords)
+    assert h.cell_coords(coords[0]) == tuple(c["cell1"])
+    assert h.spatial_hash(c["cell1"]) == h.spatial_hash(c["cell2"])
+    p1 = sorted(v + 1 for v in h.points_in_cell(c["cell1"]))
+    p2 = sorted(v + 1 for v in h.points_in_cell(c["cell2"]))
+    want = c.get("expected_points_in_cell1", c.get("expected_points_in_cell1_sorted"))
+    assert p1 == want and p2 == want
+    off, ids = h.neighbor_lists(coords, coords, sort=False)
+    got = [(ids[off[i]:off[i + 1]] + 1).tolist() for i in range(coords.shape[0])]
+    assert got == c["expected_neighbors"]
+    if case == 1:
+        key = h.spatial_hash(c["cell1"])
+        assert h.collisions[key] == 1
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_spatial_hashing_periodic_examples(oracle, kats, case):
+    """test/neighborhood_search.jl:121-123,177-181: the periodic examples give the same neighbours
+    with a SpatialHashingCellList(list_size = 2 n_points)."""
+    k = kats["periodic_neighbors"]
+    c = k["cases"][case]
+    coords = np.array(c["coordinates_rows"], dtype=np.float64).T.copy()
+    box = (np.array(c["box_min"]), np.array(c["box_max"]))
+    h = oracle.HashGrid(coords.shape[1], k["search_radius"], 2 * coords.shape[0],
+                        periodic_box=box, dtype=np.float64).build(coords)
+    off, ids = h.neighbor_lists(coords, coords, sort=True)
+    got = [(ids[off[i]:off[i + 1]] + 1).tolist() for i in range(coords.shape[0])]
+    assert got == k["expected_neighbors"]
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+@pytest.mark.parametrize("list_size", [1, 2, 13, 600])
+def test_spatial_hashing_matches_trivial(oracle, nd, list_size):
+    """The property test/neighborhood_search.jl:186-337 checks for every search, on a table small
+    enough that most keys collide: neighbour sets equal brute force, with and without a box."""
+    rng = np.random.default_rng(nd * 100 + list_size)
+    y = (rng.random((300, nd)) * 2 - 1).astype(np.float32)
+    x = (rng.random((40, nd)) * 2.4 - 1.2).astype(np.float32)
+    r = np.float32(0.23)
+    for box in (None, (np.full(nd, -1, np.float32), np.full(nd, 1, np.float32))):
+        h = oracle.HashGrid(nd, r, list_size, periodic_box=box).build(y)
+        for q in (y, x):
+            off, ids = h.neighbor_lists(q, y, sort=True)
+            off2, ids2 = oracle.trivial_lists(q, y, r, periodic_box=box)
+            assert np.array_equal(off, off2) and np.array_equal(ids, ids2)
+            assert np.array_equal(h.count_neighbors(q, y), np.diff(off2))
+        # the table itself: every key's list is ascending and holds exactly the points hashed there
+        keys = np.array([h.spatial_hash(h.cell_coords(p)) for p in y])
+        for key in range(list_size):
+            ids_k = h.key_points[h.key_start[key]:h.key_start[key + 1]]
+            assert np.array_equal(ids_k, np.nonzero(keys == key)[0])
+            cells = {h.cell_coords(y[i]) for i in ids_k}
+            if len(cells) > 1:
+                # more than one cell in the key: flagged, unless the sentinel quirk hides it
+                # (cell (0,..,0) flattens to the "unused" marker, spatial_hashing.jl:56,87-90)
+                assert h.collisions[key] == 1 or tuple([0] * nd) in cells
+
+
+def test_spatial_hashing_eachindex_y_and_inexact(oracle):
+    rng = np.random.default_rng(5)
+    y = rng.random((100, 3)).astype(np.float32)
+    r = np.float32(0.2)
+    idx = np.arange(20, 70)
+    h = oracle.HashGrid(3, r, 200).build(y, eachindex_y=idx)
+    off, ids = h.neighbor_lists(y, y, sort=True)
+    off2, ids2 = oracle.trivial_lists(y, y[idx], r)
+    assert np.array_equal(off, off2) and np.array_equal(ids, idx[ids2])
+    bad = y.copy()
+    bad[3, 1] = np.float32(1e12)     # cell 5e12 does not fit Int32 -> InexactError
+    with pytest.raises(oracle.OracleError) as e:
+        oracle.HashGrid(3, r, 200).build(bad)
+    assert e.value.code == 5
