@@ -295,6 +295,38 @@ pnb_status pnb_tlsph_deformation_grad_f32(const pnb_nlist *l, const pnb_grid *g,
                                           const float *L, float smoothing_length,
                                           float kernel_norm, float *F, void *stream);
 
+/* The other TLSPH kernel, TrixiParticles.interact_structure_structure! (called at
+ * benchmarks/smoothed_particle_hydrodynamics.jl:121), over the lists (no radius test,
+ * src/nhs_precomputed.jl:221-244): dv (nx x ndims) is overwritten with
+ *   sum_j m_j (PK1c_i / rho_i^2 + PK1c_j / rho_j^2) gradW(X0_i - X0_j)
+ *         + PenaltyForceGanzenmueller(alpha) / m_i          (pairs closer than sqrt(eps) skipped)
+ * pk1_corrected, F: ndims x ndims column-major per point.  Arithmetic definition: oracle
+ * pno_tlsph_interact (TrixiParticles is not vendored: parity unpinned). */
+typedef struct pnb_tlsph_params {
+    float smoothing_length; /* h = search_radius / 2 */
+    float kernel_norm;      /* sigma_d / h^d of the Wendland C2 kernel */
+    float young_modulus;    /* E */
+    float penalty_alpha;    /* PenaltyForceGanzenmueller(alpha) */
+} pnb_tlsph_params;
+pnb_status pnb_tlsph_interact_f32(const pnb_nlist *l, const pnb_grid *g, const float *X0,
+                                  const float *xcur, const float *mass, const float *rho0,
+                                  const float *pk1_corrected, const float *F,
+                                  const pnb_tlsph_params *params, float *dv, void *stream);
+/* TrixiParticles.compute_pk1_corrected! (benchmarks/smoothed_particle_hydrodynamics.jl:186),
+ * pointwise: PK1 of the St. Venant-Kirchhoff material from the deformation gradient F, times the
+ * kernel correction matrix L (all ndims x ndims column-major per point). */
+pnb_status pnb_tlsph_pk1_corrected_f32(int ndims, int64_t n, const float *F, const float *L,
+                                       float young_modulus, float poisson_ratio,
+                                       float *pk1_corrected, void *stream);
+/* TrixiParticles.compute_pressure! for ContinuityDensity + StateEquationCole
+ * (benchmarks/smoothed_particle_hydrodynamics.jl:64-69, 99), pointwise:
+ * pressure[i] = B ((rho_i / rho0)^exponent - 1) + background, B = rho0 c^2 / exponent,
+ * rho_i = v[i, ndims] (the density row of the (ndims + 1) x N state). */
+pnb_status pnb_wcsph_compute_pressure_f32(int ndims, int64_t n, const float *v, float sound_speed,
+                                          float reference_density, float exponent,
+                                          float background_pressure, float *pressure,
+                                          void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Device memory helpers for hosts without a CUDA binding (the Julia glue's B200Array;
  * replaces Adapt.adapt(backend, array), src/gpu.jl, benchmarks/run_benchmarks.jl:97-99)

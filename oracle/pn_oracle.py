@@ -502,6 +502,68 @@ def tlsph_deformation_grad(X0, xcur, offsets, ids, mass, rho0, L, h, kernel_norm
     return (F, F64, Fabs) if wide else F
 
 
+def tlsph_pk1_corrected(F, L, young_modulus, poisson_ratio, dtype=np.float32):
+    """compute_pk1_corrected! (unpinned; oracle pno_tlsph_pk1_corrected): (n, nd*nd) column-major."""
+    dtype = np.dtype(dtype)
+    suf, real = ("_f32", C.c_float) if dtype == np.float32 else ("_f64", C.c_double)
+    F = np.ascontiguousarray(F, dtype=dtype)
+    L = np.ascontiguousarray(L, dtype=dtype)
+    n, nn = F.shape
+    nd = int(round(nn ** 0.5))
+    out = np.zeros_like(F)
+    getattr(lib(), "pno_tlsph_pk1_corrected" + suf)(nd, C.c_int64(n), _ptr(F, real), _ptr(L, real),
+                                                     real(young_modulus), real(poisson_ratio),
+                                                     _ptr(out, real))
+    return out
+
+
+def tlsph_interact(X0, xcur, offsets, ids, mass, rho0, pk1c, F, h, kernel_norm, young_modulus,
+                   alpha, search_radius, periodic_box=None, dtype=np.float32, wide=False):
+    """interact_structure_structure! over precomputed lists (unpinned; oracle pno_tlsph_interact)."""
+    dtype = np.dtype(dtype)
+    suf, real = ("_f32", C.c_float) if dtype == np.float32 else ("_f64", C.c_double)
+    X0 = np.ascontiguousarray(X0, dtype=dtype)
+    xcur = np.ascontiguousarray(xcur, dtype=dtype)
+    n, nd = X0.shape
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    mass = np.ascontiguousarray(mass, dtype=dtype)
+    rho0 = np.ascontiguousarray(rho0, dtype=dtype)
+    pk1c = np.ascontiguousarray(pk1c, dtype=dtype)
+    F = np.ascontiguousarray(F, dtype=dtype)
+    assert pk1c.shape == (n, nd * nd) and F.shape == (n, nd * nd)
+    params = np.array([h, kernel_norm, young_modulus, alpha], dtype=dtype)
+    if periodic_box is not None:
+        bmn = np.ascontiguousarray(periodic_box[0], dtype=dtype)
+        bmx = np.ascontiguousarray(periodic_box[1], dtype=dtype)
+    else:
+        bmn = bmx = None
+    dv = np.zeros((n, nd), dtype=dtype)
+    dv64 = np.zeros(dv.shape, dtype=np.float64) if wide else None
+    dvabs = np.zeros(dv.shape, dtype=np.float64) if wide else None
+    getattr(lib(), "pno_tlsph_interact" + suf)(
+        nd, real(search_radius), int(periodic_box is not None), _ptr(bmn, real), _ptr(bmx, real),
+        _ptr(X0, real), _ptr(xcur, real), C.c_int64(n), _ptr(offsets, C.c_int64),
+        _ptr(ids, C.c_int32), _ptr(mass, real), _ptr(rho0, real), _ptr(pk1c, real), _ptr(F, real),
+        _ptr(params, real), _ptr(dv, real), _ptr(dv64, C.c_double), _ptr(dvabs, C.c_double))
+    return (dv, dv64, dvabs) if wide else dv
+
+
+def wcsph_compute_pressure(v, sound_speed, reference_density, exponent=1.0, background_pressure=0.0,
+                           dtype=np.float32):
+    """compute_pressure! with StateEquationCole (unpinned; oracle pno_wcsph_compute_pressure)."""
+    dtype = np.dtype(dtype)
+    suf, real = ("_f32", C.c_float) if dtype == np.float32 else ("_f64", C.c_double)
+    v = np.ascontiguousarray(v, dtype=dtype)
+    n, ns = v.shape
+    out = np.zeros(n, dtype=dtype)
+    getattr(lib(), "pno_wcsph_compute_pressure" + suf)(ns - 1, C.c_int64(n), _ptr(v, real),
+                                                        real(sound_speed), real(reference_density),
+                                                        real(exponent), real(background_pressure),
+                                                        _ptr(out, real))
+    return out
+
+
 def periodic_coords(x, box_min, box_max, dtype=np.float32):
     dtype = np.dtype(dtype)
     suf, real = ("_f32", C.c_float) if dtype == np.float32 else ("_f64", C.c_double)

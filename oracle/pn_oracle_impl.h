@@ -754,6 +754,175 @@ void FN(pno_tlsph_deformation_grad)(int ndims, REAL r, int periodic, const REAL 
     }
 }
 
+/* ---------------------------------------------------------------------------------------
+ * The rest of the TLSPH / WCSPH right-hand side either side of the neighbour sweep
+ * (SURVEY.md 8f rank 2).  All of it is TrixiParticles.jl arithmetic (not vendored, compat "0.5",
+ * no reference test checks values): PARITY UNPINNED, the formulas below are this repo's
+ * definition.
+ * ------------------------------------------------------------------------------------- */
+
+/*
+ * TrixiParticles.compute_pk1_corrected! (called at benchmarks/smoothed_particle_hydrodynamics.jl:186)
+ * per particle, nd x nd column-major matrices:
+ *   E = (F^T F - I) / 2,  S = lambda tr(E) I + 2 mu E  (St. Venant-Kirchhoff),  P = F S,
+ *   pk1_corrected = P L,   lambda = E nu / ((1 + nu)(1 - 2 nu)),  mu = E / (2 (1 + nu)).
+ */
+void FN(pno_tlsph_pk1_corrected)(int nd, int64_t n, const REAL *F, const REAL *L, REAL young,
+                                 REAL nu, REAL *out)
+{
+    const int nn = nd * nd;
+    const REAL lambda = (young * nu) / (((REAL)1 + nu) * ((REAL)1 - (REAL)2 * nu));
+    const REAL mu = young / ((REAL)2 * ((REAL)1 + nu));
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        const REAL *Fi = F + i * nn, *Li = L + i * nn;
+        REAL E[9], S[9], P[9];
+        REAL tr = 0;
+        for (int a = 0; a < nd; a++)
+            for (int b = 0; b < nd; b++) {
+                REAL t = Fi[a * nd + 0] * Fi[b * nd + 0];        /* (F^T F)[a,b] = sum_k F[k,a] F[k,b] */
+                for (int k = 1; k < nd; k++) t = t + Fi[a * nd + k] * Fi[b * nd + k];
+                E[b * nd + a] = (REAL)0.5 * (t - (a == b ? (REAL)1 : (REAL)0));
+            }
+        for (int a = 0; a < nd; a++) tr = (a == 0) ? E[0] : tr + E[a * nd + a];
+        for (int a = 0; a < nd; a++)
+            for (int b = 0; b < nd; b++) {
+                REAL t = ((REAL)2 * mu) * E[b * nd + a];
+                if (a == b) t = lambda * tr + t;
+                S[b * nd + a] = t;
+            }
+        for (int a = 0; a < nd; a++)
+            for (int b = 0; b < nd; b++) {
+                REAL t = Fi[0 * nd + a] * S[b * nd + 0];          /* (F S)[a,b] */
+                for (int k = 1; k < nd; k++) t = t + Fi[k * nd + a] * S[b * nd + k];
+                P[b * nd + a] = t;
+            }
+        for (int a = 0; a < nd; a++)
+            for (int b = 0; b < nd; b++) {
+                REAL t = P[0 * nd + a] * Li[b * nd + 0];          /* (P L)[a,b] */
+                for (int k = 1; k < nd; k++) t = t + P[k * nd + a] * Li[b * nd + k];
+                out[i * nn + b * nd + a] = t;
+            }
+    }
+}
+
+/*
+ * TrixiParticles.interact_structure_structure! (benchmarks/smoothed_particle_hydrodynamics.jl:121)
+ * over precomputed lists, neighbours / kernel on the INITIAL coordinates X0 (no radius test,
+ * nhs_precomputed.jl:221-244):
+ *   dv_i += m_j (PK1c_i / rho_i^2 + PK1c_j / rho_j^2) gradW(X_ij)
+ *   PenaltyForceGanzenmueller(alpha): with x_ij the CURRENT difference,
+ *     eps = (F_i + F_j) X_ij - 2 x_ij,  delta = eps . x_ij / |x_ij|,
+ *     f = alpha/2 V_i V_j W(|X_ij|) / |X_ij|^2 E delta x_ij / |x_ij|,  dv_i += f / m_i
+ * pairs with |X_ij| < sqrt(eps) are skipped.  params = {h, kernel_norm, young_modulus, alpha}.
+ */
+void FN(pno_tlsph_interact)(int ndims, REAL r, int periodic, const REAL *box_min,
+                            const REAL *box_max, const REAL *X0, const REAL *xcur, int64_t n,
+                            const int64_t *offsets, const int32_t *ids, const REAL *mass,
+                            const REAL *rho0, const REAL *pk1c, const REAL *F, const REAL *params,
+                            REAL *dv, double *dv64, double *dvabs)
+{
+    GRID g;
+    memset(&g, 0, sizeof(g));
+    g.ndims = ndims;
+    g.periodic = periodic;
+    for (int d = 0; d < ndims && periodic; d++) g.box_size[d] = box_max[d] - box_min[d];
+    const REAL r2 = r * r;
+    const int nd = ndims, nn = ndims * ndims;
+    const REAL h = params[0], kernel_norm = params[1], young = params[2], alpha = params[3];
+#if REAL_IS_FLOAT
+    const REAL sqrt_eps = 3.4526698300124393e-4f;
+#else
+    const REAL sqrt_eps = 1.4901161193847656e-8;
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        REAL acc[3] = {0, 0, 0};
+        double acc64[3] = {0, 0, 0}, accabs[3] = {0, 0, 0};
+        const REAL rho_i2 = rho0[i] * rho0[i];
+        const REAL vol_i = mass[i] / rho0[i];
+        for (int64_t k = offsets[i]; k < offsets[i + 1]; k++) {
+            int64_t j = ids[k];
+            REAL p[3] = {0, 0, 0};
+            for (int d = 0; d < nd; d++) p[d] = X0[i * nd + d] - X0[j * nd + d];
+            REAL d2 = p[0] * p[0];
+            for (int d = 1; d < nd; d++) d2 = d2 + p[d] * p[d];
+            d2 = FN(pno_periodic_fix)(&g, p, d2, r2);
+            REAL dist = (REAL)sqrt((double)d2);
+            if (dist < sqrt_eps) continue;
+            REAL q = dist / h, dw = 0, w = 0;
+            if (q < (REAL)2) {
+                REAL t = (REAL)1 - q * (REAL)0.5;
+                dw = ((REAL)-5 * q) * ((t * t) * t);
+                w = ((t * t) * (t * t)) * ((REAL)2 * q + (REAL)1);
+            }
+            REAL sg = ((kernel_norm / h) * dw) / dist;
+            REAL grad[3] = {0, 0, 0};
+            for (int d = 0; d < nd; d++) grad[d] = sg * p[d];
+            const REAL rho_j2 = rho0[j] * rho0[j];
+            const REAL m_j = mass[j];
+            REAL term[3] = {0, 0, 0}, pen[3] = {0, 0, 0};
+            for (int a = 0; a < nd; a++) {
+                REAL t = 0;
+                for (int b = 0; b < nd; b++) {
+                    REAL A = pk1c[i * nn + b * nd + a] / rho_i2 + pk1c[j * nn + b * nd + a] / rho_j2;
+                    t = (b == 0) ? A * grad[0] : t + A * grad[b];
+                }
+                term[a] = m_j * t;
+            }
+            /* penalty force */
+            REAL cp[3] = {0, 0, 0}, es[3] = {0, 0, 0};
+            for (int d = 0; d < nd; d++) cp[d] = xcur[i * nd + d] - xcur[j * nd + d];
+            REAL c2 = cp[0] * cp[0];
+            for (int d = 1; d < nd; d++) c2 = c2 + cp[d] * cp[d];
+            REAL cd = (REAL)sqrt((double)c2);
+            for (int a = 0; a < nd; a++) {
+                REAL t = 0;
+                for (int b = 0; b < nd; b++) {
+                    REAL Fs = F[i * nn + b * nd + a] + F[j * nn + b * nd + a];
+                    t = (b == 0) ? Fs * p[0] : t + Fs * p[b];
+                }
+                es[a] = t - (REAL)2 * cp[a];
+            }
+            REAL ds = es[0] * cp[0];
+            for (int d = 1; d < nd; d++) ds = ds + es[d] * cp[d];
+            ds = ds / cd;
+            REAL vol_j = m_j / rho0[j];
+            REAL c = ((alpha * (REAL)0.5) * vol_i) * vol_j;
+            c = (c * (kernel_norm * w)) / (dist * dist);
+            c = ((c * young) * ds) / cd;
+            for (int d = 0; d < nd; d++) pen[d] = (c * cp[d]) / mass[i];
+            for (int d = 0; d < nd; d++) {
+                acc[d] += term[d];
+                acc[d] += pen[d];
+                acc64[d] += (double)term[d] + (double)pen[d];
+                accabs[d] += fabs((double)term[d]) + fabs((double)pen[d]);
+            }
+        }
+        for (int d = 0; d < nd; d++) {
+            dv[i * nd + d] = acc[d];
+            if (dv64) dv64[i * nd + d] = acc64[d];
+            if (dvabs) dvabs[i * nd + d] = accabs[d];
+        }
+    }
+}
+
+/*
+ * TrixiParticles.compute_pressure! for ContinuityDensity + StateEquationCole
+ * (benchmarks/smoothed_particle_hydrodynamics.jl:64-69,99): density = last row of v,
+ *   p = B ((rho / rho0)^gamma - 1) + p_background,  B = rho0 c^2 / gamma.
+ */
+void FN(pno_wcsph_compute_pressure)(int nd, int64_t n, const REAL *v, REAL sound_speed, REAL rho0,
+                                    REAL exponent, REAL background, REAL *pressure)
+{
+    const REAL B = (rho0 * (sound_speed * sound_speed)) / exponent;
+    for (int64_t i = 0; i < n; i++) {
+        REAL ratio = v[i * (nd + 1) + nd] / rho0;
+        REAL pw = (exponent == (REAL)1) ? ratio : (REAL)pow((double)ratio, (double)exponent);
+        pressure[i] = B * (pw - (REAL)1) + background;
+    }
+}
+
 /* K_ref: candidate tests the reference performs = sum_i sum_{3^d cells} |cell| */
 int64_t FN(pno_candidate_tests)(const GRID *g, const int64_t *cell_start, const REAL *x, int64_t nx)
 {

@@ -12,6 +12,7 @@
 #include "sweep.cuh"
 #include "sweep_launch.cuh"
 #include "f64.cuh"
+#include "tlsph_interact.cuh"
 
 struct pnb_nlist {
     int64_t nx;        // number of lists (points of x)
@@ -24,7 +25,8 @@ struct pnb_nlist {
     int *d_err;
     int *h_err;
     float4 *pack;      // [2 nx] per-point records of the TLSPH sweep (allocated on first use)
-    size_t bytes_offsets, bytes_ids, bytes_counts, bytes_pack;
+    float4 *pack8;     // [8 nx] 128-byte records of the TLSPH force sweep (allocated on first use)
+    size_t bytes_offsets, bytes_ids, bytes_counts, bytes_pack, bytes_pack8;
 };
 
 namespace pnb {
@@ -33,7 +35,8 @@ namespace pnb {
 // step (update! of a PrecomputedNeighborhoodSearch) does not pay cudaMalloc / cudaFree of
 // gigabytes each time.  Keyed by the device the buffer lives on.
 struct SpareBuf { void *p; size_t bytes; int device; };
-static SpareBuf g_spare[4] = {{nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}};
+static SpareBuf g_spare[5] = {{nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1},
+                              {nullptr, 0, -1}};
 
 static cudaError_t cached_malloc(int kind, void **out, size_t bytes, size_t *got)
 {
@@ -503,6 +506,7 @@ extern "C" void pnb_nlist_destroy(pnb_nlist *l)
     cached_free(1, l->ids, l->bytes_ids);
     cached_free(2, l->counts, l->bytes_counts);
     cached_free(3, l->pack, l->bytes_pack);
+    cached_free(4, l->pack8, l->bytes_pack8);
     cudaFree(l->d_err);
     if (l->h_err) cudaFreeHost(l->h_err);
     cudaGetLastError();
@@ -815,6 +819,108 @@ extern "C" pnb_status pnb_nlist_pairs_f64(const pnb_nlist *l, const pnb_grid *g,
             default: k_nlist_pairs64<3><<<blocks, 256, 0, s>>>(g->p64, l->nx, l->offsets, l->ids, x, y, pos_diff, distance); break;
         }
         g_launch_count++;
+    }
+    PNB_CUDA(cudaStreamSynchronize(s));
+    return PNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TLSPH forces over the lists + the pointwise steps either side (tlsph_interact.cuh)
+// ---------------------------------------------------------------------------------------------
+extern "C" pnb_status pnb_tlsph_interact_f32(const pnb_nlist *l_, const pnb_grid *g,
+                                             const float *X0, const float *xcur,
+                                             const float *mass, const float *rho0,
+                                             const float *pk1_corrected, const float *F,
+                                             const pnb_tlsph_params *params, float *dv,
+                                             void *stream)
+{
+    if (!l_ || !g) { set_error("handle is NULL"); return PNB_ERR_ARG; }
+    if (!params) { set_error("params is NULL"); return PNB_ERR_ARG; }
+    pnb_nlist *l = const_cast<pnb_nlist *>(l_);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (l->nx > 0) {
+        if (!l->pack8)
+            PNB_CUDA(cached_malloc(4, (void **)&l->pack8, sizeof(float4) * kTlRecF4 * (size_t)l->nx,
+                                   &l->bytes_pack8));
+        const unsigned blocks = (unsigned)div_up(l->nx * 8, 256);   // 8 lanes per point
+        const unsigned pblocks = (unsigned)div_up(l->nx, 128);
+        const bool per = g->p.periodic != 0;
+        const bool exact = pnb_get_exact_arithmetic() != 0;
+        const float h = params->smoothing_length, kn = params->kernel_norm;
+        const float E = params->young_modulus, al = params->penalty_alpha;
+        ProfScope ps(PH_NLIST_SWEEP, s);
+#define TLFORCE(ND)                                                                                 \
+    do {                                                                                            \
+        k_pack_tlsph_full<ND><<<pblocks, 128, 0, s>>>(l->nx, X0, xcur, mass, rho0, pk1_corrected, F, l->pack8); \
+        if (per && exact) k_tlsph_interact<ND, true, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack8, h, kn, E, al, dv); \
+        else if (per) k_tlsph_interact<ND, true, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack8, h, kn, E, al, dv); \
+        else if (exact) k_tlsph_interact<ND, false, true><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack8, h, kn, E, al, dv); \
+        else k_tlsph_interact<ND, false, false><<<blocks, 256, 0, s>>>(g->p, l->nx, l->offsets, l->ids, l->pack8, h, kn, E, al, dv); \
+    } while (0)
+        switch (l->ndims) {
+            case 1: TLFORCE(1); break;
+            case 2: TLFORCE(2); break;
+            default: TLFORCE(3); break;
+        }
+#undef TLFORCE
+        g_launch_count++;
+        PNB_LAUNCHED();
+    }
+    PNB_CUDA(cudaStreamSynchronize(s));
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_tlsph_pk1_corrected_f32(int ndims, int64_t n, const float *F,
+                                                  const float *L, float young_modulus,
+                                                  float poisson_ratio, float *pk1_corrected,
+                                                  void *stream)
+{
+    if (ndims < 1 || ndims > 3) { set_error("`NDIMS` must be 1, 2, or 3"); return PNB_ERR_ARG; }
+    if (pnb_device_count() <= 0) {
+        set_error("no CUDA device: libpnb200 has no CPU fallback");
+        return PNB_ERR_CUDA;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // Lame parameters in Float32, one rounding per operation
+    volatile float a = young_modulus * poisson_ratio;
+    volatile float b1 = 1.0f + poisson_ratio;
+    volatile float two_nu = 2.0f * poisson_ratio;
+    volatile float b2 = 1.0f - two_nu;
+    volatile float den = b1 * b2;
+    volatile float lambda = a / den;
+    volatile float den2 = 2.0f * b1;
+    volatile float mu = young_modulus / den2;
+    if (n > 0) {
+        const unsigned blocks = (unsigned)div_up(n, 128);
+        switch (ndims) {
+            case 1: k_tlsph_pk1_corrected<1><<<blocks, 128, 0, s>>>(n, F, L, lambda, mu, pk1_corrected); break;
+            case 2: k_tlsph_pk1_corrected<2><<<blocks, 128, 0, s>>>(n, F, L, lambda, mu, pk1_corrected); break;
+            default: k_tlsph_pk1_corrected<3><<<blocks, 128, 0, s>>>(n, F, L, lambda, mu, pk1_corrected); break;
+        }
+        PNB_LAUNCHED();
+    }
+    PNB_CUDA(cudaStreamSynchronize(s));
+    return PNB_OK;
+}
+
+extern "C" pnb_status pnb_wcsph_compute_pressure_f32(int ndims, int64_t n, const float *v,
+                                                     float sound_speed, float reference_density,
+                                                     float exponent, float background_pressure,
+                                                     float *pressure, void *stream)
+{
+    if (ndims < 1 || ndims > 3) { set_error("`NDIMS` must be 1, 2, or 3"); return PNB_ERR_ARG; }
+    if (pnb_device_count() <= 0) {
+        set_error("no CUDA device: libpnb200 has no CPU fallback");
+        return PNB_ERR_CUDA;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    volatile float c2 = sound_speed * sound_speed;
+    volatile float rc2 = reference_density * c2;
+    volatile float B = rc2 / exponent;
+    if (n > 0) {
+        k_wcsph_compute_pressure<<<(unsigned)div_up(n, 256), 256, 0, s>>>(
+            n, ndims + 1, v, B, reference_density, exponent, background_pressure, pressure);
+        PNB_LAUNCHED();
     }
     PNB_CUDA(cudaStreamSynchronize(s));
     return PNB_OK;

@@ -36,6 +36,12 @@ class WcsphParams(C.Structure):
                 ("delta", C.c_float), ("kernel_norm", C.c_float)]
 
 
+class TlsphParams(C.Structure):
+    """pnb_tlsph_params (include/pnb200.h)."""
+    _fields_ = [("smoothing_length", C.c_float), ("kernel_norm", C.c_float),
+                ("young_modulus", C.c_float), ("penalty_alpha", C.c_float)]
+
+
 class SlabArrays(C.Structure):
     """pnb_slab_arrays (include/pnb200.h)."""
     _fields_ = [("ptr", C.c_void_p * 8), ("width", C.c_int32 * 8), ("n_arrays", C.c_int32)]
@@ -98,6 +104,11 @@ SIGNATURES = {
     "pnb_nlist_pairs_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnb_tlsph_deformation_grad_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                                  _vp, _vp]),
+    "pnb_tlsph_interact_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         C.POINTER(TlsphParams), _vp, _vp]),
+    "pnb_tlsph_pk1_corrected_f32": (C.c_int, [C.c_int, _i64, _vp, _vp, _f32, _f32, _vp, _vp]),
+    "pnb_wcsph_compute_pressure_f32": (C.c_int, [C.c_int, _i64, _vp, _f32, _f32, _f32, _f32, _vp,
+                                                 _vp]),
     "pnb_malloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "pnb_free": (C.c_int, [_vp]),
     "pnb_malloc_host": (C.c_int, [C.POINTER(_vp), _i64]),

@@ -25,7 +25,8 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import ArgumentError, BoundsError, PointNeighborsError, WcsphParams, check
+from ._lib import (ArgumentError, BoundsError, PointNeighborsError, TlsphParams, WcsphParams,
+                   check)
 
 __all__ = [
     "foreach_neighbor", "foreach_neighbor_unsafe", "mapreduce_neighbor", "mapreduce_neighbor_unsafe",
@@ -37,7 +38,8 @@ __all__ = [
     "initialize_", "update_", "initialize", "update", "foreach_point_neighbor",
     "copy_neighborhood_search", "freeze_neighborhood_search", "requires_update",
     "search_radius", "ndims", "CountNeighbors", "NBodyGravity", "WCSPHInteract",
-    "TLSPHDeformationGradient", "wendland_c2_norm", "set_exact_arithmetic",
+    "TLSPHDeformationGradient", "TLSPHInteract", "compute_pk1_corrected_", "compute_pressure_",
+    "wendland_c2_norm", "set_exact_arithmetic",
 ]
 
 _EPS64 = 2.220446049250313e-16
@@ -639,6 +641,52 @@ class TLSPHDeformationGradient:
                                       else wendland_c2_norm(ndims_, smoothing_length))
 
 
+class TLSPHInteract:
+    """TrixiParticles.interact_structure_structure!(dv, v, system, semi) over a
+    PrecomputedNeighborhoodSearch (benchmarks/smoothed_particle_hydrodynamics.jl:121, set-up
+    :136-189): PK1 stress forces + PenaltyForceGanzenmueller.  dv (N, NDIMS) is overwritten;
+    pk1_corrected and deformation_grad are (N, NDIMS*NDIMS), column-major per point."""
+
+    def __init__(self, dv, current_coordinates, mass, material_density, pk1_corrected,
+                 deformation_grad, *, smoothing_length, young_modulus, penalty_alpha=0.1,
+                 kernel_norm=None, ndims_=3):
+        self.dv = dv
+        self.current_coordinates = current_coordinates
+        self.mass = mass
+        self.material_density = material_density
+        self.pk1_corrected = pk1_corrected
+        self.deformation_grad = deformation_grad
+        if kernel_norm is None:
+            kernel_norm = wendland_c2_norm(ndims_, smoothing_length)
+        self.params = TlsphParams(np.float32(smoothing_length), np.float32(kernel_norm),
+                                  np.float32(young_modulus), np.float32(penalty_alpha))
+
+
+def compute_pk1_corrected_(pk1_corrected, deformation_grad, correction_matrix, *, young_modulus,
+                           poisson_ratio):
+    """TrixiParticles.compute_pk1_corrected!(system, semi)
+    (benchmarks/smoothed_particle_hydrodynamics.jl:186), pointwise on the device:
+    (N, NDIMS*NDIMS) float32 CUDA tensors, column-major per point."""
+    n, nn = deformation_grad.shape
+    nd = int(round(nn ** 0.5))
+    check(_lib.lib().pnb_tlsph_pk1_corrected_f32(
+        nd, n, deformation_grad.data_ptr(), correction_matrix.data_ptr(),
+        np.float32(young_modulus), np.float32(poisson_ratio), pk1_corrected.data_ptr(), _stream()))
+    return pk1_corrected
+
+
+def compute_pressure_(pressure, v, *, sound_speed, reference_density, exponent=1.0,
+                      background_pressure=0.0):
+    """TrixiParticles.compute_pressure!(system, v, semi) for ContinuityDensity +
+    StateEquationCole (benchmarks/smoothed_particle_hydrodynamics.jl:64-69, 99): v is the
+    (N, NDIMS+1) state whose last column is the density."""
+    n, ns = v.shape
+    check(_lib.lib().pnb_wcsph_compute_pressure_f32(
+        ns - 1, n, v.data_ptr(), np.float32(sound_speed), np.float32(reference_density),
+        np.float32(exponent), np.float32(background_pressure), pressure.data_ptr(), _stream()))
+    return pressure
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -672,7 +720,7 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
                                             y.shape[0], _ptr(pts), 0 if pts is None else pts.numel(),
                                             0, f.n_neighbors.data_ptr(), _stream()))
         elif callable(f) and not isinstance(f, (NBodyGravity, WCSPHInteract,
-                                                 TLSPHDeformationGradient)):
+                                                 TLSPHDeformationGradient, TLSPHInteract)):
             lists = _NeighborLists.build(nhs, x, y, sort=False)
             lists.call_host(f, x, y, nhs, points, radius_test=True)
         else:
@@ -938,10 +986,22 @@ class PrecomputedNeighborhoodSearch(metaclass=_Parametric):
                 f.material_density.data_ptr(), f.correction_matrix.data_ptr(),
                 f.smoothing_length, f.kernel_norm, f.F.data_ptr(), _stream()))
             return None
+        if isinstance(f, TLSPHInteract):
+            if points is not None:
+                raise ArgumentError("the fused TLSPH sweep loops over all points")
+            if self.eltype == np.float64:
+                raise TypeError("the fused TLSPH sweep exists in Float32 only")
+            check(_lib.lib().pnb_tlsph_interact_f32(
+                self._lists._handle, self._grid_for_pairs._grid(), x.data_ptr(),
+                f.current_coordinates.data_ptr(), f.mass.data_ptr(),
+                f.material_density.data_ptr(), f.pk1_corrected.data_ptr(),
+                f.deformation_grad.data_ptr(), C.byref(f.params), f.dv.data_ptr(), _stream()))
+            return None
         if callable(f):
             self._lists.call_host(f, x, y, self._grid_for_pairs, points, radius_test=False)
             return None
-        raise TypeError("f must be TLSPHDeformationGradient or a callable f(i, j, pos_diff, d)")
+        raise TypeError("f must be TLSPHDeformationGradient, TLSPHInteract or a callable "
+                        "f(i, j, pos_diff, d)")
 
 
 # ---------------------------------------------------------------------------------------------
