@@ -381,6 +381,24 @@ pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t nx, const d
 pnb_status pnb_nlist_pairs_f64(const pnb_nlist *list, const pnb_grid *g, const double *x,
                                const double *y, double *pos_diff, double *distance, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mixed precision: Float64 coordinates and cell-list corners with a Float32 search radius (and a
+ * Float32 PeriodicBox, src/nhs_grid.jl:107-110), "common in SPH" according to
+ * docs/literate/src/tut_gpu_usage.jl:45-50.  Julia's promotion rules decide the arithmetic: the
+ * padding is computed in Float32 and added to the Float64 corners (src/cell_lists/full_grid.jl:66-67),
+ * grid size and cell coordinates are Float64 (:74, :93), pos_diff = Float32.(x_i - y_j) and
+ * everything after it Float32 (src/nhs_grid.jl:547-555).  The handle is used with the _f64 entry
+ * points (build, point_cells, count, neighbour lists, pair geometry: pos_diff / distance are
+ * returned as doubles holding the Float32 values).
+ * ------------------------------------------------------------------------------------------- */
+pnb_status pnb_grid_params_mixed(int ndims, float search_radius, const double *min_corner,
+                                 const double *max_corner, const float *box_min,
+                                 const float *box_max, double *padded_min, double *padded_max,
+                                 int64_t *grid_size, int64_t *n_cells, float *cell_size);
+pnb_status pnb_grid_create_mixed(int ndims, float search_radius, const double *min_corner,
+                                 const double *max_corner, const float *box_min,
+                                 const float *box_max, pnb_grid **out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,8 @@
 #undef SUF
 #undef REAL_IS_FLOAT
 
+#include "pn_oracle_mixed.h"
+
 #ifdef _OPENMP
 #include <omp.h>
 int pno_max_threads(void) { return omp_get_max_threads(); }

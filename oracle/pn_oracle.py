@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(_HERE, "libpn_oracle.so")
 def build(force: bool = False) -> str:
     """Compile the C restatement (make -C oracle)."""
     src_mtime = max(os.path.getmtime(os.path.join(_HERE, f))
-                    for f in ("pn_oracle.c", "pn_oracle_impl.h", "Makefile"))
+                    for f in ("pn_oracle.c", "pn_oracle_impl.h", "pn_oracle_mixed.h", "Makefile"))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_mtime:
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
             getattr(_lib, "pno_total_cells" + suf).restype = C.c_int64
             getattr(_lib, "pno_candidate_tests" + suf).restype = C.c_int64
             getattr(_lib, "pno_spatial_hash" + suf).restype = C.c_int64
+        _lib.pno_total_cells_mix.restype = C.c_int64
     return _lib
 
 
@@ -424,6 +425,114 @@ class HashGrid:
                                    _ptr(dv, self.real), _ptr(dv64, C.c_double),
                                    _ptr(dvabs, C.c_double))
         return (dv, dv64, dvabs) if wide else dv
+
+
+class _GridMix(C.Structure):
+    _fields_ = [("ndims", C.c_int32), ("periodic", C.c_int32), ("search_radius", C.c_float),
+                ("min_corner", C.c_double * 3), ("max_corner", C.c_double * 3),
+                ("grid_size", C.c_int64 * 3), ("n_cells", C.c_int64 * 3),
+                ("cell_size", C.c_float * 3), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3),
+                ("box_size", C.c_float * 3)]
+
+
+class MixedGrid:
+    """Float64 coordinates / corners with a Float32 search radius (and Float32 PeriodicBox):
+    oracle/pn_oracle_mixed.h (docs/literate/src/tut_gpu_usage.jl:45-50)."""
+
+    def __init__(self, ndims, search_radius, min_corner, max_corner, periodic_box=None):
+        self.g = _GridMix()
+        self.ndims = int(ndims)
+        mn = np.ascontiguousarray(min_corner, dtype=np.float64)
+        mx = np.ascontiguousarray(max_corner, dtype=np.float64)
+        if periodic_box is not None:
+            bmn = np.ascontiguousarray(periodic_box[0], dtype=np.float32)
+            bmx = np.ascontiguousarray(periodic_box[1], dtype=np.float32)
+        else:
+            bmn = bmx = None
+        rc = lib().pno_grid_init_mix(C.byref(self.g), self.ndims, C.c_float(search_radius),
+                                     _ptr(mn, C.c_double), _ptr(mx, C.c_double),
+                                     int(periodic_box is not None), _ptr(bmn, C.c_float),
+                                     _ptr(bmx, C.c_float))
+        if rc:
+            raise OracleError(rc)
+        self.cell_start = self.cell_points = None
+
+    @property
+    def min_corner(self):
+        return np.array(self.g.min_corner[:self.ndims])
+
+    @property
+    def max_corner(self):
+        return np.array(self.g.max_corner[:self.ndims])
+
+    @property
+    def grid_size(self):
+        return tuple(int(v) for v in self.g.grid_size[:self.ndims])
+
+    @property
+    def n_cells(self):
+        return tuple(int(v) for v in self.g.n_cells[:self.ndims])
+
+    @property
+    def cell_size(self):
+        return np.array(self.g.cell_size[:self.ndims], dtype=np.float32)
+
+    @property
+    def total_cells(self):
+        return int(lib().pno_total_cells_mix(C.byref(self.g)))
+
+    def _coords(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.ndim == 2 and x.shape[1] == self.ndims
+        return x
+
+    def point_cells(self, x):
+        x = self._coords(x)
+        out = np.empty(x.shape[0], dtype=np.int64)
+        lib().pno_point_cells_mix(C.byref(self.g), _ptr(x, C.c_double), C.c_int64(x.shape[0]),
+                                  _ptr(out, C.c_int64))
+        return out
+
+    def build(self, y):
+        y = self._coords(y)
+        self.cell_start = np.zeros(self.total_cells + 1, dtype=np.int64)
+        self.cell_points = np.zeros(max(y.shape[0], 1), dtype=np.int32)
+        rc = lib().pno_build_csr_mix(C.byref(self.g), _ptr(y, C.c_double), C.c_int64(y.shape[0]),
+                                     _ptr(self.cell_start, C.c_int64),
+                                     _ptr(self.cell_points, C.c_int32))
+        if rc:
+            raise OracleError(rc)
+        self.cell_points = self.cell_points[:y.shape[0]]
+        return self
+
+    def neighbor_lists(self, x, y, brute=False, sort=False):
+        x, y = self._coords(x), self._coords(y)
+        offsets = np.zeros(x.shape[0] + 1, dtype=np.int64)
+        args = (C.byref(self.g), _ptr(self.cell_start, C.c_int64), _ptr(self.cell_points, C.c_int32),
+                _ptr(x, C.c_double), C.c_int64(x.shape[0]), _ptr(y, C.c_double),
+                C.c_int64(y.shape[0]), _ptr(offsets, C.c_int64))
+        rc = lib().pno_neighbor_lists_mix(*args, None, int(brute))
+        if rc:
+            raise OracleError(rc)
+        ids = np.zeros(max(int(offsets[-1]), 1), dtype=np.int32)
+        lib().pno_neighbor_lists_mix(*args, _ptr(ids, C.c_int32), int(brute))
+        ids = ids[:int(offsets[-1])]
+        if sort:
+            for i in range(x.shape[0]):
+                ids[offsets[i]:offsets[i + 1]].sort()
+        return offsets, ids
+
+    def list_pairs(self, x, y, offsets, ids):
+        x, y = self._coords(x), self._coords(y)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        P = int(offsets[-1])
+        pd = np.zeros((max(P, 1), self.ndims), dtype=np.float32)
+        dist = np.zeros(max(P, 1), dtype=np.float32)
+        lib().pno_list_pairs_mix(C.byref(self.g), _ptr(x, C.c_double), C.c_int64(x.shape[0]),
+                                 _ptr(y, C.c_double), _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32),
+                                 _ptr(pd, C.c_float), _ptr(dist, C.c_float))
+        return pd[:P], dist[:P]
 
 
 def trivial_lists(x, y, search_radius, periodic_box=None, dtype=np.float32):

@@ -42,6 +42,8 @@ struct GridP64 {
     int nc[3];          // periodic cells per dim (-1 if not periodic)
     double bsize[3];    // periodic box size
     int total_cells;
+    int mixed;          // Float64 coordinates, Float32 radius: r, r2, bsize hold Float32 values and
+                        // the pair arithmetic after pos_diff = Float32.(x_i - y_j) is Float32
 };
 
 struct alignas(32) Rec64 {

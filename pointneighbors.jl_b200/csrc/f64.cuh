@@ -57,6 +57,25 @@ template <int ND>
 __device__ __forceinline__ double pair_d2_64(const GridP64 &g, const double *xi, const Rec64 &yj,
                                              double *p, bool radius_test_fix)
 {
+    if (g.mixed) {
+        // mixed precision (tut_gpu_usage.jl:45-50): Float64 subtraction, ONE conversion, then the
+        // Float32 operation sequence of the Float32 path; the results are returned widened
+        float q[3];
+        q[0] = __double2float_rn(__dsub_rn(xi[0], yj.x));
+        q[1] = ND > 1 ? __double2float_rn(__dsub_rn(xi[1], yj.y)) : 0.f;
+        q[2] = ND > 2 ? __double2float_rn(__dsub_rn(xi[2], yj.z)) : 0.f;
+        float d2f = dist2<ND>(q[0], q[1], q[2]);
+        if (g.periodic && radius_test_fix && d2f > (float)g.r2) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                const float bs = (float)g.bsize[d];
+                q[d] = __fsub_rn(q[d], __fmul_rn(bs, rintf(__fdiv_rn(q[d], bs))));
+            }
+            d2f = dist2<ND>(q[0], q[1], q[2]);
+        }
+        p[0] = (double)q[0]; p[1] = (double)q[1]; p[2] = (double)q[2];
+        return (double)d2f;
+    }
     p[0] = __dsub_rn(xi[0], yj.x);
     p[1] = ND > 1 ? __dsub_rn(xi[1], yj.y) : 0.0;
     p[2] = ND > 2 ? __dsub_rn(xi[2], yj.z) : 0.0;

@@ -1914,6 +1914,48 @@ __global__ void k_point_cells64(GridP64 g, const double *__restrict__ x, int64_t
 
 }  // namespace pnb
 
+// the part of the Float64 / mixed constructors after the host arithmetic
+static pnb_status create64_common(pnb_grid *g, int ndims, double r, double r2, bool periodic,
+                                  const int64_t *gsz, const int64_t *ncl, const double *bsize,
+                                  pnb_grid **out)
+{
+    g->template_search = r < 2.220446049250313e-16;
+    GridP64 &p = g->p64;
+    p.ndims = ndims;
+    p.periodic = periodic ? 1 : 0;
+    p.r = r;
+    p.r2 = r2;
+    int64_t total = 1;
+    for (int d = 0; d < 3; d++) {
+        p.minc[d] = d < ndims ? g->padded_min64[d] : 0.0;
+        p.cs[d] = d < ndims ? g->cell_size64[d] : 1.0;
+        int64_t gs = d < ndims ? gsz[d] : 1;
+        if (g->template_search) gs = d < ndims ? 0 : 1;
+        if (gs > 0x7fffffff) gs = 0x7fffffff;
+        p.gs[d] = (int)gs;
+        p.nc[d] = d < ndims ? (int)ncl[d] : -1;
+        p.bsize[d] = (d < ndims && periodic) ? bsize[d] : 1.0;
+        g->grid_size[d] = gs;
+        g->n_cells[d] = ncl[d];
+        total *= gs;
+        if (total > 0x7fffff00LL) {
+            set_error("cell grid too large for this build: more than 2^31 cells");
+            delete g;
+            return PNB_ERR_ARG;
+        }
+    }
+    p.total_cells = (int)total;
+    // the shared (element-type independent) part of the Float32 scalars: exports read these
+    g->p.ndims = ndims;
+    g->p.periodic = p.periodic;
+    g->p.total_cells = p.total_cells;
+    for (int d = 0; d < 3; d++) { g->p.gs[d] = p.gs[d]; g->p.nc[d] = p.nc[d]; g->p.off[d] = 0; }
+    pnb_status st = grid_alloc_common(g, total);
+    if (st != PNB_OK) { pnb_grid_destroy(g); return st; }
+    *out = g;
+    return PNB_OK;
+}
+
 extern "C" pnb_status pnb_grid_params_f64(int ndims, double search_radius, const double *min_corner,
                                           const double *max_corner, const double *box_min,
                                           const double *box_max, double *padded_min,
@@ -1941,66 +1983,103 @@ extern "C" pnb_status pnb_grid_create_f64(int ndims, double r, const double *min
     pnb_status st = grid_params_host64(ndims, r, min_corner, max_corner, box_min, box_max,
                                        g->padded_min64, g->padded_max64, gsz, ncl, g->cell_size64);
     if (st != PNB_OK) { delete g; return st; }
-    g->template_search = r < 2.220446049250313e-16;
-    GridP64 &p = g->p64;
-    p.ndims = ndims;
-    p.periodic = (box_min && box_max && !g->template_search) ? 1 : 0;
-    p.r = r;
-    { volatile double r2 = r * r; p.r2 = r2; }
-    int64_t total = 1;
-    for (int d = 0; d < 3; d++) {
-        p.minc[d] = d < ndims ? g->padded_min64[d] : 0.0;
-        p.cs[d] = d < ndims ? g->cell_size64[d] : 1.0;
-        int64_t gs = d < ndims ? gsz[d] : 1;
-        if (g->template_search) gs = d < ndims ? 0 : 1;
-        if (gs > 0x7fffffff) gs = 0x7fffffff;
-        p.gs[d] = (int)gs;
-        p.nc[d] = d < ndims ? (int)ncl[d] : -1;
-        p.bsize[d] = 1.0;
-        if (d < ndims && p.periodic) { volatile double size = box_max[d] - box_min[d]; p.bsize[d] = size; }
-        g->grid_size[d] = gs;
-        g->n_cells[d] = ncl[d];
-        total *= gs;
-        if (total > 0x7fffff00LL) {
-            set_error("cell grid too large for this build: more than 2^31 cells");
-            delete g;
-            return PNB_ERR_ARG;
+    double bsize[3] = {1.0, 1.0, 1.0};
+    const bool periodic = box_min && box_max && !(r < 2.220446049250313e-16);
+    for (int d = 0; d < ndims && periodic; d++) { volatile double size = box_max[d] - box_min[d]; bsize[d] = size; }
+    volatile double r2 = r * r;
+    return create64_common(g, ndims, r, r2, periodic, gsz, ncl, bsize, out);
+}
+
+// Float64 coordinates / corners with a Float32 search radius (and Float32 PeriodicBox), the
+// combination docs/literate/src/tut_gpu_usage.jl:45-50 describes: Julia's promotion makes the
+// padding Float32 (1001//1000 * r, full_grid.jl:66-67) added to Float64 corners, the grid size and
+// the cell arithmetic Float64 (:74, :93), pos_diff = Float32.(x_i - y_j) and everything after it
+// Float32 (nhs_grid.jl:547-555).
+static pnb_status grid_params_host_mixed(int ndims, float r, const double *min_corner,
+                                         const double *max_corner, const float *box_min,
+                                         const float *box_max, double *padded_min,
+                                         double *padded_max, int64_t *grid_size, int64_t *n_cells,
+                                         float *cell_size)
+{
+    if (ndims < 1 || ndims > 3) { set_error("`NDIMS` must be 1, 2, or 3"); return PNB_ERR_ARG; }
+    if (!min_corner || !max_corner) {
+        set_error("min_corner and max_corner must have the same length");
+        return PNB_ERR_ARG;
+    }
+    volatile float factor = 1001.0f / 1000.0f;
+    volatile float pad = factor * r;
+    const bool is_template = (double)r < 2.220446049250313e-16;
+    for (int d = 0; d < ndims; d++) {
+        volatile double mn = min_corner[d] - (double)pad;
+        volatile double mx = max_corner[d] + (double)pad;
+        if (padded_min) padded_min[d] = mn;
+        if (padded_max) padded_max[d] = mx;
+        if (grid_size) {
+            if (is_template) grid_size[d] = 0;
+            else {
+                volatile double ext = mx - mn;
+                volatile double q = ext / (double)r;
+                grid_size[d] = (int64_t)std::ceil(q);
+            }
+        }
+        if (n_cells) n_cells[d] = -1;
+        if (cell_size) cell_size[d] = r;
+    }
+    if (box_min && box_max && !is_template) {
+        for (int d = 0; d < ndims; d++) {
+            volatile float size = box_max[d] - box_min[d];
+            const double nc = std::floor(((double)size + 10.0 * 2.220446049250313e-16) / (double)r);
+            const int64_t nci = (int64_t)nc;
+            if (n_cells) n_cells[d] = nci;
+            if (cell_size) { volatile float cs = size / (float)nci; cell_size[d] = cs; }
+            if (nci < 3) {
+                set_error("the `GridNeighborhoodSearch` needs at least 3 cells in each dimension "
+                          "when used with periodicity. Please use no NHS for very small problems.");
+                return PNB_ERR_ARG;
+            }
         }
     }
-    p.total_cells = (int)total;
-    // the shared (element-type independent) part of the Float32 scalars: exports read these
-    g->p.ndims = ndims;
-    g->p.periodic = p.periodic;
-    g->p.total_cells = p.total_cells;
-    for (int d = 0; d < 3; d++) { g->p.gs[d] = p.gs[d]; g->p.nc[d] = p.nc[d]; g->p.off[d] = 0; }
-    cudaError_t e = cudaGetDevice(&g->device);
-    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaGetDevice"); }
-    auto fail = [&](cudaError_t err, const char *what) {
-        pnb_status s2 = cuda_fail(err, what);
-        pnb_grid_destroy(g);
-        return s2;
-    };
-    const int64_t C = total;
-    if ((e = cudaMalloc(&g->cell_start_alloc, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
-        return fail(e, "cudaMalloc cell_start");
-    g->cell_start = g->cell_start_alloc + 3;
-    if ((e = cudaMalloc(&g->cell_count, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
-        return fail(e, "cudaMalloc cell_count");
-    if ((e = cudaMemset(g->cell_start_alloc, 0, sizeof(uint32_t) * (size_t)(C + 8))) != cudaSuccess)
-        return fail(e, "cudaMemset");
-    if ((e = cudaMemset(g->cell_count, 0, sizeof(uint32_t) * (size_t)(C + 4))) != cudaSuccess)
-        return fail(e, "cudaMemset");
-    if ((e = cudaHostAlloc(&g->h_err, 2 * sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
-        return fail(e, "cudaHostAlloc");
-    g->h_err[0] = g->h_err[1] = 0;
-    if ((e = cudaHostGetDevicePointer(&g->d_err, g->h_err, 0)) != cudaSuccess)
-        return fail(e, "cudaHostGetDevicePointer");
-    if ((e = cudaMalloc(&g->scan_ticket, sizeof(unsigned int))) != cudaSuccess)
-        return fail(e, "cudaMalloc ticket");
-    if ((e = cudaMemset(g->scan_ticket, 0, sizeof(unsigned int))) != cudaSuccess)
-        return fail(e, "cudaMemset");
-    *out = g;
     return PNB_OK;
+}
+
+extern "C" pnb_status pnb_grid_params_mixed(int ndims, float search_radius,
+                                            const double *min_corner, const double *max_corner,
+                                            const float *box_min, const float *box_max,
+                                            double *padded_min, double *padded_max,
+                                            int64_t *grid_size, int64_t *n_cells, float *cell_size)
+{
+    return grid_params_host_mixed(ndims, search_radius, min_corner, max_corner, box_min, box_max,
+                                  padded_min, padded_max, grid_size, n_cells, cell_size);
+}
+
+extern "C" pnb_status pnb_grid_create_mixed(int ndims, float r, const double *min_corner,
+                                            const double *max_corner, const float *box_min,
+                                            const float *box_max, pnb_grid **out)
+{
+    if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
+    *out = nullptr;
+    if (pnb_device_count() <= 0) {
+        set_error("no CUDA device: libpnb200 has no CPU fallback");
+        return PNB_ERR_CUDA;
+    }
+    pnb_grid *g = new pnb_grid();
+    memset(g, 0, sizeof(*g));
+    g->f64 = true;
+    int64_t gsz[3] = {1, 1, 1}, ncl[3] = {-1, -1, -1};
+    float csf[3] = {r, r, r};
+    pnb_status st = grid_params_host_mixed(ndims, r, min_corner, max_corner, box_min, box_max,
+                                           g->padded_min64, g->padded_max64, gsz, ncl, csf);
+    if (st != PNB_OK) { delete g; return st; }
+    double bsize[3] = {1.0, 1.0, 1.0};
+    const bool periodic = box_min && box_max && !((double)r < 2.220446049250313e-16);
+    for (int d = 0; d < 3; d++) {
+        g->cell_size64[d] = (double)csf[d];
+        g->cell_size[d] = csf[d];
+        if (d < ndims && periodic) { volatile float size = box_max[d] - box_min[d]; bsize[d] = (double)size; }
+    }
+    volatile float r2f = r * r;
+    g->p64.mixed = 1;
+    return create64_common(g, ndims, (double)r, (double)r2f, periodic, gsz, ncl, bsize, out);
 }
 
 extern "C" pnb_status pnb_grid_create_padded_f64(int ndims, double r, const double *padded_min,

@@ -724,7 +724,8 @@ __global__ void k_nlist_pairs64(GridP64 g, int64_t nx, const int64_t *__restrict
 #pragma unroll
             for (int d = 0; d < ND; d++) pos_diff[k * ND + d] = p[d];
         }
-        if (dist) dist[k] = __dsqrt_rn(d2);
+        // mixed precision: distance = sqrt of the Float32 d2, in Float32
+        if (dist) dist[k] = g.mixed ? (double)__fsqrt_rn((float)d2) : __dsqrt_rn(d2);
     }
 }
 }  // namespace pnb

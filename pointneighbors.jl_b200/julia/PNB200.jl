@@ -13,7 +13,7 @@
 module PNB200
 
 using PointNeighbors
-using PointNeighbors: GridNeighborhoodSearch, FullGridCellList, PeriodicBox,
+using PointNeighbors: GridNeighborhoodSearch, FullGridCellList, SpatialHashingCellList, PeriodicBox,
                       PrecomputedNeighborhoodSearch, AbstractNeighborhoodSearch
 using PointNeighbors.Adapt
 using GPUArraysCore: AbstractGPUArray
@@ -22,7 +22,8 @@ import PointNeighbors: initialize!, update!, foreach_point_neighbor, copy_neighb
                        freeze_neighborhood_search, requires_update, search_radius, default_backend
 
 export B200Array, B200Backend, CountNeighbors, NBodyGravity, WCSPHInteract,
-       TLSPHDeformationGradient, set_exact_arithmetic
+       TLSPHDeformationGradient, TLSPHInteract, TlsphParams, compute_pk1_corrected!,
+       compute_pressure!, set_exact_arithmetic
 
 const libpnb200 = get(ENV, "PNB200_LIB",
                       joinpath(@__DIR__, "..", "pnb200", "libpnb200.so"))
@@ -113,8 +114,24 @@ function Adapt.adapt_structure(::B200Backend, nhs::GridNeighborhoodSearch{NDIMS}
     T in (Float32, Float64) ||
         throw(ArgumentError("the B200 path computes in Float32 or Float64: pass such a `search_radius`"))
     cl = nhs.cell_list
+    if cl isa SpatialHashingCellList
+        # src/cell_lists/spatial_hashing.jl, src/gpu.jl:37-44: the table lives in the library
+        T === Float32 ||
+            throw(ArgumentError("the hashed cell list is available for Float32 searches"))
+        box = nhs.periodic_box
+        bmin = isnothing(box) ? C_NULL : collect(T, box.min_corner)
+        bmax = isnothing(box) ? C_NULL : collect(T, box.max_corner)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:pnb_grid_create_hashed_f32, libpnb200), Cint,
+                    (Cint, Cfloat, Int64, Ptr{Cfloat}, Ptr{Cfloat}, Ref{Ptr{Cvoid}}),
+                    NDIMS, nhs.search_radius, cl.list_size, bmin, bmax, ref))
+        out = B200GridNeighborhoodSearch{NDIMS, T, typeof(box), typeof(nhs.update_strategy)}(
+            ref[], nhs.search_radius, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs)
+        finalizer(x -> ccall((:pnb_grid_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), x.handle), out)
+        return out
+    end
     cl isa FullGridCellList ||
-        throw(ArgumentError("only the FullGridCellList is GPU-compatible (src/cell_lists/dictionary.jl:8-10)"))
+        throw(ArgumentError("only the FullGridCellList and the SpatialHashingCellList are GPU-compatible (src/cell_lists/dictionary.jl:8-10)"))
     eltype(cl.min_corner) == T ||
         throw(ArgumentError("cell list corners and `search_radius` must have the same element type"))
     r = nhs.search_radius
@@ -423,6 +440,55 @@ function foreach_point_neighbor(f::TLSPHDeformationGradient, x::B200Array{Float3
                 f.mass.ptr, f.material_density.ptr, f.correction_matrix.ptr, f.smoothing_length,
                 f.kernel_norm, f.F.ptr, C_NULL))
     return nothing
+end
+
+# The other TLSPH kernel and the pointwise steps either side of the sweeps
+# (benchmarks/smoothed_particle_hydrodynamics.jl:99, 121, 186)
+struct TlsphParams                          # pnb_tlsph_params
+    smoothing_length :: Float32
+    kernel_norm      :: Float32
+    young_modulus    :: Float32
+    penalty_alpha    :: Float32
+end
+
+struct TLSPHInteract{A}                     # TrixiParticles.interact_structure_structure!
+    dv :: A; current_coordinates :: A
+    mass :: Any; material_density :: Any; pk1_corrected :: Any; deformation_grad :: Any
+    params :: TlsphParams
+end
+
+function foreach_point_neighbor(f::TLSPHInteract, x::B200Array{Float32, 2},
+                                y::B200Array{Float32, 2}, s::B200PrecomputedNeighborhoodSearch;
+                                parallelization_backend = default_backend(x),
+                                points = axes(x, 2))
+    check(ccall((:pnb_tlsph_interact_f32, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ptr{Cvoid}, Ref{TlsphParams}, Ptr{Cvoid}, Ptr{Cvoid}),
+                s.lists.handle, s.grid_for_sweep.handle, x.ptr, f.current_coordinates.ptr,
+                f.mass.ptr, f.material_density.ptr, f.pk1_corrected.ptr, f.deformation_grad.ptr,
+                Ref(f.params), f.dv.ptr, C_NULL))
+    return nothing
+end
+
+# TrixiParticles.compute_pk1_corrected!: deformation_grad, correction_matrix, pk1_corrected are
+# NDIMS x NDIMS x N device arrays
+function compute_pk1_corrected!(pk1_corrected::B200Array{Float32, 3}, deformation_grad::B200Array{Float32, 3},
+                                correction_matrix::B200Array{Float32, 3}; young_modulus, poisson_ratio)
+    check(ccall((:pnb_tlsph_pk1_corrected_f32, libpnb200), Cint,
+                (Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cfloat, Cfloat, Ptr{Cvoid}, Ptr{Cvoid}),
+                size(deformation_grad, 1), size(deformation_grad, 3), deformation_grad.ptr,
+                correction_matrix.ptr, young_modulus, poisson_ratio, pk1_corrected.ptr, C_NULL))
+    return pk1_corrected
+end
+
+# TrixiParticles.compute_pressure! (ContinuityDensity + StateEquationCole): v is (NDIMS + 1) x N
+function compute_pressure!(pressure::B200Array{Float32, 1}, v::B200Array{Float32, 2}; sound_speed,
+                           reference_density, exponent = 1, background_pressure = 0)
+    check(ccall((:pnb_wcsph_compute_pressure_f32, libpnb200), Cint,
+                (Cint, Int64, Ptr{Cvoid}, Cfloat, Cfloat, Cfloat, Cfloat, Ptr{Cvoid}, Ptr{Cvoid}),
+                size(v, 1) - 1, size(v, 2), v.ptr, sound_speed, reference_density, exponent,
+                background_pressure, pressure.ptr, C_NULL))
+    return pressure
 end
 
 end # module

@@ -134,7 +134,21 @@ for c in [int(v) for v in args.configs.split(",")]:
         f = pn.TLSPHDeformationGradient(F, xcur, mass, rho0, Lm, smoothing_length=r / T(2), ndims_=3)
         smin, smed = timed(lambda: pn.foreach_point_neighbor(f, A, A, pre), args.reps, False)
         bytes_sweep = 108 * N + 4 * P + 4
+        # the other TLSPH kernel: PK1 stress + penalty forces over the same lists (8f rank 2)
+        pk1 = torch.zeros((N, 9), device=dev)
+        pmin, pmed = timed(lambda: pn.compute_pk1_corrected_(pk1, F, Lm, young_modulus=T(1.4e6),
+                                                            poisson_ratio=T(0.4)), args.reps, False)
+        dvs = torch.zeros((N, 3), device=dev)
+        fi = pn.TLSPHInteract(dvs, xcur, mass, rho0, pk1, F, smoothing_length=r / T(2),
+                              young_modulus=T(1.4e6), penalty_alpha=T(0.1))
+        imin, imed = timed(lambda: pn.foreach_point_neighbor(fi, A, A, pre), args.reps, False)
+        bytes_force = 4 * P + 8 * N + 104 * N + 12 * N
         out.append({"config": 4, "what": "Precomputed (periodic, sorted) + TLSPH F 200^3", "N": N,
+                    "tlsph_force_ms_min": imin, "tlsph_force_ms_median": imed,
+                    "tlsph_force_hbm_gbs": bytes_force / (imin * 1e-3) / 1e9,
+                    "tlsph_force_hbm_frac": bytes_force / (imin * 1e-3) / 1e9 / HBM,
+                    "pk1_corrected_ms_min": pmin,
+                    "pk1_corrected_hbm_frac": 108 * N / (pmin * 1e-3) / 1e9 / HBM,
                     "pairs": P, "n_cells": list(nhs.n_cells), "list_build_ms_min": bmin,
                     "list_build_ms_median": bmed, "tlsph_ms_min": smin, "tlsph_ms_median": smed,
                     "tlsph_hbm_gbs": bytes_sweep / (smin * 1e-3) / 1e9,
@@ -164,6 +178,26 @@ for c in [int(v) for v in args.configs.split(",")]:
             res.update({"pairs": P, f"count_ms_{name}": mn, f"count_gpairs_per_s_{name}": P / mn / 1e6,
                         f"wcsph_ms_{name}": wmn, f"wcsph_gpairs_per_s_{name}": P / wmn / 1e6})
         _lib.lib().pnb_set_twoset_tiles(1)
+        out.append(res)
+    elif c == 7:
+        # SpatialHashingCellList (8f rank 3) against the FullGridCellList on the same cloud
+        res = {"config": 7, "what": "SpatialHashingCellList(list_size = 2 N) vs FullGridCellList"}
+        for n in (64, 101):
+            N, r, A, full = lattice(n)
+            hashed = pn.GridNeighborhoodSearch[3](search_radius=r, n_points=N,
+                                                  cell_list=pn.SpatialHashingCellList[3](list_size=2 * N))
+            pn.initialize_(hashed, A, A)
+            cnt = torch.zeros(N, dtype=torch.int64, device=dev)
+            f = pn.CountNeighbors(cnt)
+            hmn, _ = timed(lambda: pn.foreach_point_neighbor(f, A, A, hashed), args.reps, True)
+            P = int(cnt.sum())
+            fmn, _ = timed(lambda: pn.foreach_point_neighbor(f, A, A, full), args.reps, True)
+            assert int(cnt.sum()) == P
+            umn, _ = timed(lambda: pn.update_(hashed, A, A), args.reps, True)
+            _, coll = hashed.export_hash_table()
+            res[f"n{n}"] = {"N": N, "pairs": P, "count_ms_hashed": hmn, "count_ms_full_grid": fmn,
+                            "gpairs_per_s_hashed": P / hmn / 1e6, "update_ms_hashed": umn,
+                            "colliding_keys": int(coll.sum())}
         out.append(res)
     torch.cuda.empty_cache()
 for o in out:
