@@ -951,7 +951,9 @@ pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *o
 // histogram pass, no scan: 28 N + 4 C bytes, exactly the algorithmic minimum of SURVEY 8d.
 // A cell that receives more than K points sets error bit 3; the build is then redone as CSR.
 // ---------------------------------------------------------------------------------------------
-template <int ND, bool PER, int PPT>
+// DIAG (measurement only, results invalid): 1 = non-returning atomics (slot from the lane run
+// alone), 2 = no stores, 4 = no atomics at all
+template <int ND, bool PER, int PPT, int DIAG = 0>
 __global__ void __launch_bounds__(kBuildThreads, 6)
 k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
                  const int32_t *__restrict__ idx, int base, uint32_t K,
@@ -978,15 +980,23 @@ k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
         }
         unsigned basev[PPT];
 #pragma unroll
-        for (int j = 0; j < PPT; j++)
-            basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(bcount + lin[j], (unsigned)rl[j]) : 0u;
+        for (int j = 0; j < PPT; j++) {
+            if (DIAG & 4) basev[j] = 0u;
+            else if (DIAG & 1) {
+                basev[j] = 0u;
+                if (lin[j] >= 0 && h[j] == lane_id()) atomicAdd(bcount + lin[j], (unsigned)rl[j]);
+            } else
+                basev[j] = (lin[j] >= 0 && h[j] == lane_id()) ? atomicAdd(bcount + lin[j], (unsigned)rl[j]) : 0u;
+        }
 #pragma unroll
         for (int j = 0; j < PPT; j++) {
             const unsigned b = __shfl_sync(0xffffffffu, basev[j], h[j] & 31);
             if (lin[j] >= 0) {
-                const unsigned slot = b + (unsigned)(lane_id() - h[j]);
+                unsigned slot = b + (unsigned)(lane_id() - h[j]);
                 const int32_t id = (int32_t)(block0 + j * kBuildThreads + (int)threadIdx.x);
-                if (slot < K)
+                if (DIAG & 5) slot = (slot + (unsigned)id) & 31u;
+                if (DIAG & 2) { if (slot == 0xffffffffu) bad |= 8; }
+                else if (slot < K)
                     brec[((size_t)lin[j] << logK) + slot] = make_float4(p[j][0], p[j][1], p[j][2], __int_as_float(id));
                 else
                     bad |= 8;
@@ -1277,6 +1287,17 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                     else if (g_tune_build & 32) PNB_BUCKET(3, false, 8);
                     else if (g_tune_build & 64) PNB_BUCKET(3, false, 2);
                     else if (g_tune_build & 128) PNB_BUCKET(3, false, 1);
+                    else if ((g_tune_build >> 8) & 7) {
+                        // measurement only (DIAG variants of the kernel; the layout is garbage)
+                        const unsigned nb = (unsigned)div_up(n_idx, kBuildThreads * 4);
+                        switch ((g_tune_build >> 8) & 7) {
+                            case 1: k_bucket_scatter<3, false, 4, 1><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+                            case 2: k_bucket_scatter<3, false, 4, 2><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+                            case 3: k_bucket_scatter<3, false, 4, 3><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+                            case 4: k_bucket_scatter<3, false, 4, 4><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+                            default: k_bucket_scatter<3, false, 4, 6><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+                        }
+                    }
                     else PNB_BUCKET(3, false, 4);
                     break;
             }

@@ -149,7 +149,11 @@ class FullGridCellList:
     (src/cell_lists/full_grid.jl:48-82).  Stores the PADDED corners like the reference."""
 
     def __init__(self, *, min_corner, max_corner, search_radius=None,
-                 backend=DynamicVectorOfVectors[np.int32], max_points_per_cell: int = 100):
+                 backend=DynamicVectorOfVectors[np.int32], max_points_per_cell: int = 100,
+                 mixed_precision: bool = False):
+        """mixed_precision=True: Float64 corners / coordinates with a Float32 `search_radius`
+        (docs/literate/src/tut_gpu_usage.jl:45-50).  Julia infers this from the argument types;
+        here it is explicit because Python floats and arrays carry no such intent."""
         mn = _as_real_vector(min_corner, "min_corner")
         mx = _as_real_vector(max_corner, "max_corner")
         if mn.size != mx.size:
@@ -173,6 +177,25 @@ class FullGridCellList:
         self.eltype = np.dtype(np.float64) if (isinstance(search_radius, np.float64)
                                                 and mn.dtype == np.float64
                                                 and mx.dtype == np.float64) else np.dtype(np.float32)
+        self.mixed = bool(mixed_precision)
+        if self.mixed:
+            if self._ndims > 3:
+                raise ArgumentError("`NDIMS` must be 1, 2, or 3")
+            if isinstance(search_radius, np.float64):
+                raise ArgumentError("mixed precision means a Float32 `search_radius` with Float64 "
+                                    "corners; pass np.float32")
+            self.eltype = np.dtype(np.float64)          # element type of corners / coordinates
+            pmin64, pmax64, gsz64 = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int64 * 3)()
+            mn64 = np.ascontiguousarray(mn, dtype=np.float64)
+            mx64 = np.ascontiguousarray(mx, dtype=np.float64)
+            check(_lib.lib().pnb_grid_params_mixed(
+                self._ndims, np.float32(search_radius), mn64.ctypes.data_as(_lib._pd),
+                mx64.ctypes.data_as(_lib._pd), None, None, pmin64, pmax64, gsz64, None, None))
+            self.min_corner = np.array(pmin64[:self._ndims], dtype=np.float64)
+            self.max_corner = np.array(pmax64[:self._ndims], dtype=np.float64)
+            self.n_cells_per_dimension = tuple(int(v) for v in gsz64[:self._ndims])
+            self._user_min, self._user_max = mn64, mx64
+            return
         if self.eltype == np.float64:
             if self._ndims > 3:
                 raise ArgumentError("`NDIMS` must be 1, 2, or 3")
@@ -266,7 +289,8 @@ def copy_cell_list(cell_list, search_radius, periodic_box):
                                       max_points_per_cell=cell_list.max_points_per_cell)
     return FullGridCellList(min_corner=cell_list.min_corner, max_corner=cell_list.max_corner,
                             search_radius=search_radius, backend=cell_list.backend,
-                            max_points_per_cell=cell_list.max_points_per_cell)
+                            max_points_per_cell=cell_list.max_points_per_cell,
+                            mixed_precision=getattr(cell_list, "mixed", False))
 
 
 _Parametric = _ParametricBase
@@ -309,6 +333,26 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
             if _eltype_of(search_radius) != periodic_box.eltype:
                 raise ArgumentError("the `search_radius` and the `PeriodicBox` must have "
                                     "the same element type")
+            if getattr(cell_list, "mixed", False):
+                if _eltype_of(search_radius) != np.dtype(np.float32):
+                    raise ArgumentError("mixed precision needs a Float32 `search_radius`")
+                nc = (C.c_int64 * 3)()
+                cs = (C.c_float * 3)()
+                bmn = np.ascontiguousarray(periodic_box.min_corner, dtype=np.float32)
+                bmx = np.ascontiguousarray(periodic_box.max_corner, dtype=np.float32)
+                check(_lib.lib().pnb_grid_params_mixed(
+                    self._ndims, np.float32(search_radius),
+                    cell_list._user_min.ctypes.data_as(_lib._pd),
+                    cell_list._user_max.ctypes.data_as(_lib._pd),
+                    bmn.ctypes.data_as(_lib._pf), bmx.ctypes.data_as(_lib._pf),
+                    None, None, None, nc, cs))
+                self.n_cells = tuple(int(v) for v in nc[:self._ndims])
+                self.cell_size = tuple(np.float32(v) for v in cs[:self._ndims])
+                self._handle = None
+                self._window = None
+                self._cell_list_radius = cell_list.search_radius
+                self.eltype = np.dtype(np.float64)
+                return
             if _eltype_of(search_radius) == np.dtype(np.float64) and \
                     cell_list.eltype == np.float64:
                 nc = (C.c_int64 * 3)()
@@ -348,7 +392,8 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
         self._cell_list_radius = cell_list.search_radius
         # Float64 search: a Float64 cell list with a Float64 radius (np.float64)
         self.eltype = np.dtype(np.float64) if (cell_list.eltype == np.float64 and
-                                               isinstance(search_radius, np.float64)) \
+                                               (isinstance(search_radius, np.float64) or
+                                                getattr(cell_list, "mixed", False))) \
             else np.dtype(np.float32)
 
     # -- device handle -----------------------------------------------------------------------
@@ -359,6 +404,17 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
             cl = self.cell_list
             h = C.c_void_p()
             bmn = bmx = None
+            if getattr(cl, "mixed", False):
+                if self.periodic_box is not None:
+                    bmn_a = np.ascontiguousarray(self.periodic_box.min_corner, dtype=np.float32)
+                    bmx_a = np.ascontiguousarray(self.periodic_box.max_corner, dtype=np.float32)
+                    bmn, bmx = bmn_a.ctypes.data_as(_lib._pf), bmx_a.ctypes.data_as(_lib._pf)
+                check(_lib.lib().pnb_grid_create_mixed(
+                    self._ndims, np.float32(self.search_radius),
+                    cl._user_min.ctypes.data_as(_lib._pd), cl._user_max.ctypes.data_as(_lib._pd),
+                    bmn, bmx, C.byref(h)))
+                self._handle = h
+                return self._handle
             if self.periodic_box is not None:
                 bmn_a = np.ascontiguousarray(self.periodic_box.min_corner, dtype=np.float64)
                 bmx_a = np.ascontiguousarray(self.periodic_box.max_corner, dtype=np.float64)

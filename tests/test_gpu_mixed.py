@@ -1,0 +1,93 @@
+"""GPU parity of mixed-precision searches: Float64 coordinates and corners
+with a Float32 search radius (docs/literate/src/tut_gpu_usage.jl:45-50) against
+oracle/pn_oracle_mixed.h.  Bar: cells, cell list, counts, neighbour lists and the pair geometry
+(Float32 pos_diff / distance) bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from test_gpu_parity import dev, lattice, pn  # noqa: E402,F401
+
+
+def make_mixed(pn, nd, r, mn, mx, box=None, n_points=0):
+    cl = pn.FullGridCellList(min_corner=np.asarray(mn, np.float64), max_corner=np.asarray(mx, np.float64),
+                             search_radius=np.float32(r), mixed_precision=True)
+    pb = None if box is None else pn.PeriodicBox(min_corner=np.asarray(box[0], np.float32),
+                                                 max_corner=np.asarray(box[1], np.float32))
+    return pn.GridNeighborhoodSearch[nd](search_radius=np.float32(r), n_points=n_points,
+                                         periodic_box=pb, cell_list=cl)
+
+
+def test_gpu_tutorial_mixed(pn, kats, oracle):
+    """test/gpu.jl:35 with the tutorial's Float64 coordinates and Float32 radius: (11, 29)."""
+    k = kats["gpu_tutorial_count"]
+    coords = lattice(k["lattice"], dtype=np.float64)
+    nhs = make_mixed(pn, 2, k["search_radius"], coords.min(0), coords.max(0), n_points=len(coords))
+    assert nhs.eltype == np.float64
+    x = dev(coords)
+    assert x.dtype == torch.float64
+    pn.initialize_(nhs, x, x)
+    cnt = torch.zeros(len(coords), dtype=torch.int64, device="cuda")
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+    assert [int(cnt.min()), int(cnt.max())] == k["expected_extrema"]
+    with pytest.raises(TypeError):
+        pn.initialize_(nhs, x.float(), x.float())     # Float32 coordinates do not match this search
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_mixed_bit_exact(pn, oracle, nd, periodic):
+    rng = np.random.default_rng(40 + nd)
+    n = 3000
+    # coordinates far from the origin: Float32 coordinates would lose the digits that decide
+    # cells and neighbours, which is why SPH codes keep them in Float64
+    shift = 1000.0
+    y = rng.random((n, nd)) * 2 - 1 + shift
+    xq = rng.random((257, nd)) * 2 - 1 + shift
+    r = np.float32(0.13 if nd == 3 else 0.06)
+    mn, mx = np.full(nd, shift - 1.0), np.full(nd, shift + 1.0)
+    box = (mn.astype(np.float32), mx.astype(np.float32)) if periodic else None
+    nhs = make_mixed(pn, nd, r, mn, mx, box=box, n_points=n)
+    og = oracle.MixedGrid(nd, r, mn, mx, periodic_box=box)
+    assert nhs.cell_list.n_cells_per_dimension == og.grid_size
+    assert np.array_equal(nhs.cell_list.min_corner, og.min_corner)
+    if periodic:
+        assert nhs.n_cells == og.n_cells
+        assert np.array_equal(np.array(nhs.cell_size, np.float32), og.cell_size)
+    ty, tx = dev(y), dev(xq)
+    pn.initialize_(nhs, ty, ty)
+    og.build(y)
+    assert np.array_equal(nhs.point_cells(ty).cpu().numpy(), og.point_cells(y))
+    cs, cp = nhs.export_csr()
+    assert np.array_equal(cs.cpu().numpy(), og.cell_start)
+    assert np.array_equal(cp.cpu().numpy(), og.cell_points)
+    for q, tq in ((y, ty), (xq, tx)):
+        if q is xq and not periodic:
+            # query points must keep their stencil inside the grid
+            q = np.clip(q, mn, mx)
+            tq = dev(q)
+        roff, rids = og.neighbor_lists(q, y)
+        boff, bids = og.neighbor_lists(q, y, brute=True)
+        so, si = og.neighbor_lists(q, y, sort=True)
+        assert np.array_equal(so, boff) and np.array_equal(si, bids)       # = brute force
+        cnt = torch.zeros(len(q), dtype=torch.int64, device="cuda")
+        pn.foreach_point_neighbor(pn.CountNeighbors(cnt), tq, ty, nhs)
+        assert np.array_equal(cnt.cpu().numpy(), np.diff(roff))
+        lists = pn.api._NeighborLists.build(nhs, tq, ty, sort=False)
+        off, ids = (t.cpu().numpy() for t in lists.export_csr(0))
+        assert np.array_equal(off, roff) and np.array_equal(ids, rids)     # reference visiting order
+        pd, dist = lists.pairs(nhs, tq, ty)
+        rpd, rdist = og.list_pairs(q, y, roff, rids)
+        pd, dist = pd.cpu().numpy(), dist.cpu().numpy()
+        # the library returns the Float32 values widened to Float64
+        assert np.array_equal(pd.astype(np.float32).astype(np.float64), pd)
+        assert np.array_equal(pd.astype(np.float32), rpd) and np.array_equal(dist.astype(np.float32), rdist)
+    # the same cloud in pure Float32 loses neighbours at this offset: the reason for mixed precision
+    full32 = oracle.Grid(nd, r, mn.astype(np.float32), mx.astype(np.float32), periodic_box=box)
+    full32.build(y.astype(np.float32))
+    o32, _ = full32.neighbor_lists(y.astype(np.float32), y.astype(np.float32))
+    roff, _ = og.neighbor_lists(y, y)
+    assert not np.array_equal(o32, roff)
