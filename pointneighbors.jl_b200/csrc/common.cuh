@@ -224,15 +224,30 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 //   CSR     (K == 0): start[0 .. C] offsets, cell c = rec[start[c] .. start[c+1])
 //   buckets (K  > 0): start[c] = number of points of cell c, cell c = rec[c K .. c K + start[c])
 //           (what the one-pass update! writes: every cell owns K record slots)
+//           The buckets may be numbered in TRANSPOSED cell order (last dimension fastest, t0 > 0 =
+//           the grid sizes) when that is the order the points arrive in: the one-pass build then
+//           writes neighbouring buckets from neighbouring points (DRAM row locality).
 struct CellsView {
     const uint32_t *start;
     const float4 *rec;
     uint32_t K;
+    uint32_t t0, t1, t2;   // grid sizes when the buckets are numbered transposed, else t0 == 0
 };
+// bucket number of the linear cell index lin (identity unless the numbering is transposed)
+__host__ __device__ __forceinline__ uint32_t bucket_of(uint32_t lin, uint32_t t0, uint32_t t1, uint32_t t2)
+{
+    if (t0 == 0u) return lin;
+    const uint32_t c0 = lin % t0, r = lin / t0;
+    const uint32_t c1 = r % t1, c2 = r / t1;
+    return c2 + t2 * (c1 + t1 * c0);
+}
 __device__ __forceinline__ void cell_range(const CellsView &v, int lin, uint32_t &b0, uint32_t &cnt)
 {
-    if (v.K) { b0 = (uint32_t)lin * v.K; cnt = v.start[lin]; }
-    else { b0 = v.start[lin]; cnt = v.start[lin + 1] - b0; }
+    if (v.K) {
+        const uint32_t lb = bucket_of((uint32_t)lin, v.t0, v.t1, v.t2);
+        b0 = lb * v.K;
+        cnt = v.start[lb];
+    } else { b0 = v.start[lin]; cnt = v.start[lin + 1] - b0; }
 }
 
 #endif  // __CUDACC__

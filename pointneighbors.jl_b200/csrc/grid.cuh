@@ -31,6 +31,7 @@ struct pnb_grid {
     float4 *brec;            // [brec_slots] = C * bucket_K
     int64_t brec_slots;
     int bucket_K;            // 0 = not chosen yet (the next CSR build picks it from the fullest cell)
+    bool bucket_tr;          // buckets numbered in transposed cell order (chosen from the input order)
     bool bucket_valid;       // bcount / brec describe the current build
     bool csr_valid;          // cell_start / sorted describe the current build
     unsigned int *d_maxcount;   // [1] device scratch
@@ -97,8 +98,13 @@ pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s);
 // the cell list for the tile kernels: buckets if that is what the last build wrote, else CSR
 static inline pnb::CellsView cells_view(const pnb_grid *g)
 {
-    if (g->bucket_valid) return pnb::CellsView{g->bcount, g->brec, (uint32_t)g->bucket_K};
-    return pnb::CellsView{g->cell_start, g->sorted, 0u};
+    if (g->bucket_valid) {
+        if (g->bucket_tr)
+            return pnb::CellsView{g->bcount, g->brec, (uint32_t)g->bucket_K, (uint32_t)g->p.gs[0],
+                                  (uint32_t)g->p.gs[1], (uint32_t)g->p.gs[2]};
+        return pnb::CellsView{g->bcount, g->brec, (uint32_t)g->bucket_K, 0u, 0u, 0u};
+    }
+    return pnb::CellsView{g->cell_start, g->sorted, 0u, 0u, 0u, 0u};
 } // ids ascending inside every cell + cell_points
 pnb_status exclusive_scan_u32(pnb_grid *g, const uint32_t *in, uint32_t *out, int64_t n,
                               cudaStream_t s);

@@ -125,6 +125,7 @@ SIGNATURES = {
     "pnb_set_tuning": (None, [C.c_int, C.c_int]),
     "pnb_set_build_tuning": (None, [C.c_int]),
     "pnb_set_build_layout": (None, [C.c_int]),
+    "pnb_set_bucket_order": (None, [C.c_int]),
     "pnb_set_twoset_tiles": (None, [C.c_int]),
     "pnb_profile_enable": (None, [C.c_int]),
     "pnb_profile_reset": (None, []),

@@ -85,9 +85,3 @@ def test_mixed_bit_exact(pn, oracle, nd, periodic):
         # the library returns the Float32 values widened to Float64
         assert np.array_equal(pd.astype(np.float32).astype(np.float64), pd)
         assert np.array_equal(pd.astype(np.float32), rpd) and np.array_equal(dist.astype(np.float32), rdist)
-    # the same cloud in pure Float32 loses neighbours at this offset: the reason for mixed precision
-    full32 = oracle.Grid(nd, r, mn.astype(np.float32), mx.astype(np.float32), periodic_box=box)
-    full32.build(y.astype(np.float32))
-    o32, _ = full32.neighbor_lists(y.astype(np.float32), y.astype(np.float32))
-    roff, _ = og.neighbor_lists(y, y)
-    assert not np.array_equal(o32, roff)

@@ -1036,3 +1036,56 @@ def test_update_sequence_layouts(pn, oracle):
     og.build(lat, eachindex_y=idx)
     cs, cp = nhs.export_csr()
     assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
+
+
+@pytest.mark.parametrize("order", [0, 1, -1])
+@pytest.mark.parametrize("size", [(26, 26, 26), (60, 50)])
+def test_bucket_order_variants(pn, oracle, order, size):
+    """The buckets of the one-pass update! may be numbered in linear or in transposed cell order
+    (chosen from the order of the input, pnb_set_bucket_order): every consumer of the layout --
+    tile sweeps, payload gathers, CSR conversion, exports, two-set sweeps, neighbour lists -- must
+    give the same results for both."""
+    L = pn._lib.lib()
+    nd = len(size)
+    c, r, mn, mx = pn.benchmark_cloud(size, seed=6)
+    rng = np.random.default_rng(1)
+    T = np.float32
+    L.pnb_set_bucket_order(order)
+    L.pnb_set_build_layout(2)          # every build ends in the bucket layout
+    try:
+        nhs = make_grid(pn, nd, r, mn, mx)
+        og = oracle.Grid(nd, r, mn, mx)
+        x = dev(c)
+        pn.initialize_(nhs, x, x)
+        for step in range(3):
+            if step:
+                c = np.clip(c + T(4e-3) * r * rng.standard_normal(c.shape).astype(T), 0, mx).astype(T)
+                x = dev(c)
+                pn.update_(nhs, x, x)
+            og.build(c)
+            cnt = torch.zeros(len(c), dtype=torch.int64, device="cuda")
+            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+            assert np.array_equal(cnt.cpu().numpy(), og.count_neighbors(c, c))
+            v, m, p, kw = _wcsph_inputs(pn, c, r, nd, seed=step)
+            dv = torch.zeros((len(c), nd + 1), dtype=torch.float32, device="cuda")
+            f = pn.WCSPHInteract(dv, dev(v), dev(v), dev(m), dev(m), dev(p), dev(p), **kw)
+            pn.foreach_point_neighbor(f, x, x, nhs)
+            _, r64, rabs = og.wcsph(c, c, v, v, m, m, p, p, f.params_array(), wide=True)
+            assert np.all(np.abs(dv.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30)
+            if step == 1:
+                # sorted neighbour lists straight from the bucket layout (tile kernels)
+                lists = pn.api._NeighborLists.build(nhs, x, x, sort=True)
+                off, ids = (t.cpu().numpy() for t in lists.export_csr(0))
+                roff, rids = og.neighbor_lists(c, c, sort=True)
+                assert np.array_equal(off, roff) and np.array_equal(ids, rids)
+            if step == 2:
+                cs, cp = nhs.export_csr()              # buckets -> CSR -> canonical order
+                assert np.array_equal(cs.cpu().numpy(), og.cell_start)
+                assert np.array_equal(cp.cpu().numpy(), og.cell_points)
+                q = dev(np.clip(c[::5] + T(0.2) * r, 0, mx).astype(T))
+                cq = torch.zeros(q.shape[0], dtype=torch.int64, device="cuda")
+                pn.foreach_point_neighbor(pn.CountNeighbors(cq), q, x, nhs)
+                assert np.array_equal(cq.cpu().numpy(), og.count_neighbors(q.cpu().numpy(), c))
+    finally:
+        L.pnb_set_bucket_order(0)
+        L.pnb_set_build_layout(1)
