@@ -403,6 +403,11 @@ pnb_status pnb_grid_params_mixed(int ndims, float search_radius, const double *m
 pnb_status pnb_grid_create_mixed(int ndims, float search_radius, const double *min_corner,
                                  const double *max_corner, const float *box_min,
                                  const float *box_max, pnb_grid **out);
+/* the same from the (already padded) corners stored in a FullGridCellList, as
+ * pnb_grid_create_padded_f32 does for Float32: what the Julia glue's adapt calls */
+pnb_status pnb_grid_create_padded_mixed(int ndims, float search_radius, const double *padded_min,
+                                        const double *padded_max, const float *box_min,
+                                        const float *box_max, pnb_grid **out);
 
 #ifdef __cplusplus
 }

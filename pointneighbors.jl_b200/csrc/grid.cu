@@ -2110,7 +2110,7 @@ static pnb_status grid_params_host_mixed(int ndims, float r, const double *min_c
         return PNB_ERR_ARG;
     }
     volatile float factor = 1001.0f / 1000.0f;
-    volatile float pad = factor * r;
+    volatile float pad = t_corners_padded ? 0.0f : factor * r;
     const bool is_template = (double)r < 2.220446049250313e-16;
     for (int d = 0; d < ndims; d++) {
         volatile double mn = min_corner[d] - (double)pad;
@@ -2183,6 +2183,16 @@ extern "C" pnb_status pnb_grid_create_mixed(int ndims, float r, const double *mi
     volatile float r2f = r * r;
     g->p64.mixed = 1;
     return create64_common(g, ndims, (double)r, (double)r2f, periodic, gsz, ncl, bsize, out);
+}
+
+extern "C" pnb_status pnb_grid_create_padded_mixed(int ndims, float r, const double *padded_min,
+                                                   const double *padded_max, const float *box_min,
+                                                   const float *box_max, pnb_grid **out)
+{
+    t_corners_padded = true;
+    pnb_status st = pnb_grid_create_mixed(ndims, r, padded_min, padded_max, box_min, box_max, out);
+    t_corners_padded = false;
+    return st;
 }
 
 extern "C" pnb_status pnb_grid_create_padded_f64(int ndims, double r, const double *padded_min,

@@ -55,7 +55,10 @@ __device__ __forceinline__ uint32_t spatial_hash_key(const long long *cc, int li
 // entry; entries that hold (or may hold) points of other cells -- check_cell_collision,
 // :501-513 -- re-derive the cell of every accepted candidate (check_collision, :486-492).
 // Candidates of a key are visited in ascending id order (the build leaves them canonical).
-template <int ND, bool PER, class CL>
+// SELF (x === y, all points): thread t takes the t-th record of the table itself, so the lanes
+// of a warp are points of the same (or a neighbouring) cell: uniform trip counts, broadcast
+// loads, payload of the query read from the cell-ordered copy.
+template <int ND, bool PER, class CL, bool SELF>
 __global__ void __launch_bounds__(128)
 k_sweep_points_hash(GridP g, const uint32_t *__restrict__ key_start,
                     const float4 *__restrict__ sorted, const int4 *__restrict__ meta,
@@ -64,14 +67,21 @@ k_sweep_points_hash(GridP g, const uint32_t *__restrict__ key_start,
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_loop) return;
-    const int i_id = points ? points[t] - base : (int)t;
+    int i_id;
     float p[3] = {0.f, 0.f, 0.f};
+    if (SELF) {
+        const float4 q = __ldg(sorted + t);
+        p[0] = q.x; p[1] = q.y; p[2] = q.z;
+        i_id = __float_as_int(q.w);
+    } else {
+        i_id = points ? points[t] - base : (int)t;
 #pragma unroll
-    for (int d = 0; d < ND; d++) p[d] = __ldg(x + (int64_t)i_id * ND + d);
+        for (int d = 0; d < ND; d++) p[d] = __ldg(x + (int64_t)i_id * ND + d);
+    }
     long long cc[3];
     hash_cell_coords<ND, PER>(g, p, cc);
     typename CL::State st;
-    cl.init(st, true, -1, i_id);
+    cl.init(st, true, SELF ? (int)t : -1, i_id);
     const PerP pp = make_perp(g);
     bool inexact = false;
     for (int oz = (ND > 2 ? -1 : 0); oz <= (ND > 2 ? 1 : 0); oz++)
@@ -118,7 +128,7 @@ k_sweep_points_hash(GridP g, const uint32_t *__restrict__ key_start,
                 }
             }
     if (inexact) atomicOr(err, 2);
-    cl.finish(st, -1, i_id);
+    cl.finish(st, SELF ? (int)t : -1, i_id);
 }
 
 #endif  // __CUDACC__

@@ -131,10 +131,15 @@ static pnb_status launch_sweep(pnb_grid *g, bool fast, bool tiles, const float *
         if (n_loop <= 0) return PNB_OK;
         ProfScope ps(PH_SWEEP_POINTS, s);
         const unsigned blocks = (unsigned)div_up(n_loop, 128);
+        // x === y: loop over the table's own records (cell order) instead of the input order
 #define PNB_HASH(ND)                                                                               \
-    if (per) k_sweep_points_hash<ND, true, CL><<<blocks, 128, 0, s>>>(                             \
+    if (fast && per) k_sweep_points_hash<ND, true, CL, true><<<blocks, 128, 0, s>>>(               \
         g->p, g->cell_start, g->sorted, g->hmeta, x, n_loop, points, base, cl, g->d_err);          \
-    else k_sweep_points_hash<ND, false, CL><<<blocks, 128, 0, s>>>(                                \
+    else if (fast) k_sweep_points_hash<ND, false, CL, true><<<blocks, 128, 0, s>>>(                \
+        g->p, g->cell_start, g->sorted, g->hmeta, x, n_loop, points, base, cl, g->d_err);          \
+    else if (per) k_sweep_points_hash<ND, true, CL, false><<<blocks, 128, 0, s>>>(                 \
+        g->p, g->cell_start, g->sorted, g->hmeta, x, n_loop, points, base, cl, g->d_err);          \
+    else k_sweep_points_hash<ND, false, CL, false><<<blocks, 128, 0, s>>>(                         \
         g->p, g->cell_start, g->sorted, g->hmeta, x, n_loop, points, base, cl, g->d_err)
         switch (g->p.ndims) {
             case 1: PNB_HASH(1); break;

@@ -132,6 +132,22 @@ function Adapt.adapt_structure(::B200Backend, nhs::GridNeighborhoodSearch{NDIMS}
     end
     cl isa FullGridCellList ||
         throw(ArgumentError("only the FullGridCellList and the SpatialHashingCellList are GPU-compatible (src/cell_lists/dictionary.jl:8-10)"))
+    if T === Float32 && eltype(cl.min_corner) === Float64
+        # mixed precision (docs/literate/src/tut_gpu_usage.jl:45-50): Float64 corners and
+        # coordinates, Float32 radius; used with B200Array{Float64} coordinates afterwards
+        box = nhs.periodic_box
+        bmin = isnothing(box) ? C_NULL : collect(Float32, box.min_corner)
+        bmax = isnothing(box) ? C_NULL : collect(Float32, box.max_corner)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:pnb_grid_create_padded_mixed, libpnb200), Cint,
+                    (Cint, Cfloat, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{Ptr{Cvoid}}),
+                    NDIMS, nhs.search_radius, collect(Float64, cl.min_corner),
+                    collect(Float64, cl.max_corner), bmin, bmax, ref))
+        out = B200GridNeighborhoodSearch{NDIMS, Float64, typeof(box), typeof(nhs.update_strategy)}(
+            ref[], nhs.search_radius, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs)
+        finalizer(x -> ccall((:pnb_grid_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), x.handle), out)
+        return out
+    end
     eltype(cl.min_corner) == T ||
         throw(ArgumentError("cell list corners and `search_radius` must have the same element type"))
     r = nhs.search_radius

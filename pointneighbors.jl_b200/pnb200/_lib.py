@@ -77,6 +77,7 @@ SIGNATURES = {
     "pnb_grid_create_padded_f32": (C.c_int, [C.c_int, _f32, _pf, _pf, _pf, _pf, C.POINTER(_vp)]),
     "pnb_grid_params_mixed": (C.c_int, [C.c_int, _f32, _pd, _pd, _pf, _pf, _pd, _pd, _pi64, _pi64, _pf]),
     "pnb_grid_create_mixed": (C.c_int, [C.c_int, _f32, _pd, _pd, _pf, _pf, C.POINTER(_vp)]),
+    "pnb_grid_create_padded_mixed": (C.c_int, [C.c_int, _f32, _pd, _pd, _pf, _pf, C.POINTER(_vp)]),
     "pnb_grid_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pnb_point_cells_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_count_neighbors_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),

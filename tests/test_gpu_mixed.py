@@ -85,3 +85,32 @@ def test_mixed_bit_exact(pn, oracle, nd, periodic):
         # the library returns the Float32 values widened to Float64
         assert np.array_equal(pd.astype(np.float32).astype(np.float64), pd)
         assert np.array_equal(pd.astype(np.float32), rpd) and np.array_equal(dist.astype(np.float32), rdist)
+
+
+def test_mixed_from_padded_corners(pn, oracle):
+    """The Julia glue adapts a FullGridCellList from its STORED (already padded) corners:
+    pnb_grid_create_padded_mixed must give the same grid as the constructor from user corners."""
+    import ctypes as C
+    L = pn._lib.lib()
+    rng = np.random.default_rng(4)
+    y = rng.random((2000, 3)) * 3 + 50.0
+    r = np.float32(0.21)
+    mn, mx = y.min(0), y.max(0)
+    nhs = make_mixed(pn, 3, r, mn, mx, n_points=len(y))
+    cl = nhs.cell_list
+    h = C.c_void_p()
+    pmn = np.ascontiguousarray(cl.min_corner, dtype=np.float64)
+    pmx = np.ascontiguousarray(cl.max_corner, dtype=np.float64)
+    pn._lib.check(L.pnb_grid_create_padded_mixed(3, r, pmn.ctypes.data_as(pn._lib._pd),
+                                                 pmx.ctypes.data_as(pn._lib._pd), None, None,
+                                                 C.byref(h)))
+    try:
+        assert L.pnb_grid_total_cells(h) == nhs.total_cells() == int(np.prod(cl.n_cells_per_dimension))
+        ty = dev(y)
+        a = torch.empty(len(y), dtype=torch.int32, device="cuda")
+        pn._lib.check(L.pnb_point_cells_f64(h, ty.data_ptr(), len(y), a.data_ptr(), None))
+        assert torch.equal(a, nhs.point_cells(ty))
+        og = oracle.MixedGrid(3, r, mn, mx)
+        assert np.array_equal(a.cpu().numpy(), og.point_cells(y))
+    finally:
+        L.pnb_grid_destroy(h)
