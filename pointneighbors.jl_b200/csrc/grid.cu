@@ -371,6 +371,7 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->scratch);
     cudaFree(g->ovf_tiles);
     cudaFree(g->ovf_count);
+    cudaFree(g->left_ids);
     cudaGetLastError();
     delete g;
 }

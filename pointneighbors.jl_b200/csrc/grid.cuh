@@ -79,7 +79,9 @@ struct pnb_grid {
     // tiles of k_sweep_tiles that did not fit its staging buffer (handled by k_sweep_overflow)
     int *ovf_tiles;
     int64_t ovf_cap;
-    int *ovf_count;
+    int *ovf_count;          // [2]: overflow tiles, surplus points (k_sweep_left)
+    int *left_ids;           // surplus points of cells with a few more than 32 points
+    int64_t left_cap;
 };
 
 namespace pnb {

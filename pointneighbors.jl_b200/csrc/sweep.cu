@@ -1,6 +1,8 @@
 // sweep.cu -- C-ABI entry points of the fused sweeps (count, n-body, WCSPH).
 // reference: foreach_point_neighbor (src/neighborhood_search.jl:183-201) with the closures of
 // benchmarks/count_neighbors.jl, benchmarks/n_body.jl, benchmarks/smoothed_particle_hydrodynamics.jl.
+#include <cstdlib>
+
 #include "closures.cuh"
 #include "sweep.cuh"
 #include "sweep_tiles.cuh"
@@ -58,6 +60,7 @@ static int g_exact_arithmetic = 0;
 int g_tune_wpc = 0;
 int g_tune_half = -1;
 int g_tune_twoset = 1;
+int g_tune_left = getenv("PNB_SWEEP_LEFT") ? atoi(getenv("PNB_SWEEP_LEFT")) : 1;
 
 static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points);
 

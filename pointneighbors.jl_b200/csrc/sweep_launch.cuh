@@ -10,6 +10,7 @@ namespace pnb {
 extern int g_tune_wpc;    // pnb_set_tuning: warps per cell override (0 = closure default)
 extern int g_tune_half;   // pnb_set_tuning: 0 = exact Float32 test instead of the fp16 pre-filter
 extern int g_tune_twoset; // pnb_set_twoset_tiles: 0 = x != y always uses the per-point kernel
+extern int g_tune_left;   // PNB_SWEEP_LEFT=0: cells with > 32 points always run further batches
 
 template <class K>
 static pnb_status allow_smem(K kernel, size_t smem)
@@ -69,8 +70,18 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
             PNB_CUDA(cudaMalloc(&g->ovf_tiles, sizeof(int) * (size_t)blocks));
             g->ovf_cap = blocks;
         }
-        if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, sizeof(int)));
-        PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, sizeof(int), s));
+        if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, 2 * sizeof(int)));
+        PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, 2 * sizeof(int), s));
+        // list of the surplus points (at most kLeftMax of the >= 33 points of a cell)
+        const int64_t left_need = n_loop / 4 + 64;
+        if (g_tune_left != 0 && left_need > g->left_cap) {
+            cudaFree(g->left_ids);
+            g->left_ids = nullptr;
+            g->left_cap = 0;
+            PNB_CUDA(cudaMalloc(&g->left_ids, sizeof(int) * (size_t)left_need));
+            g->left_cap = left_need;
+        }
+        int *left_ids = g_tune_left != 0 ? g->left_ids : nullptr;
         // variant: warps per cell and the fp16 pre-filter; the tuning overrides (pnb_set_tuning)
         // exist for A/B measurements of the 3-D non-periodic x === y kernels
         int wpc = CL::kWarpsPerCell;
@@ -87,7 +98,7 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         if (st != PNB_OK) return st;                                                              \
         ProfScope ps(PH_SWEEP_CELLS, s);                                                          \
         k_sweep_tiles<ND, PER, CL, WPC, HALF, TWO><<<(unsigned)blocks, kFTX * WPC * 32, smem, s>>>( \
-            g->p, cand, qry, cl, g->ovf_tiles, g->ovf_count);                                     \
+            g->p, cand, qry, cl, g->ovf_tiles, g->ovf_count, left_ids);                           \
         PNB_LAUNCHED();                                                                           \
     } while (0)
         if (two) {
@@ -106,6 +117,11 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
             k_sweep_overflow<ND, PER, CL><<<148 * 2, kFTX * 32, smem_rows, s>>>(
                 g->p, cand, qry, cl, g->ovf_tiles, g->ovf_count);
             PNB_LAUNCHED();
+            if (left_ids) {
+                k_sweep_left<ND, PER, CL><<<148 * 16, 128, 0, s>>>(g->p, cand, x, left_ids,
+                                                                 g->ovf_count + 1, cl);
+                PNB_LAUNCHED();
+            }
         }
     } else if (n_loop > 0) {
         pnb_status stc = ensure_csr(g, s);         // the per-point kernel walks the CSR arrays

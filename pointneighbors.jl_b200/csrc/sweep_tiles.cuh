@@ -52,6 +52,7 @@ struct wants_big_tiles<CL, decltype((void)CL::kBigTiles)> { static constexpr boo
 template <class CL> __host__ __device__ constexpr int tile_cap() { return wants_big_tiles<CL>::value ? 2304 : 1728; }
 template <class CL> __host__ __device__ constexpr int tile_nblk_max() { return wants_big_tiles<CL>::value ? 36 : 28; }
 constexpr float kHalfSentinel = 64.0f;     // padding candidates: farther than any real one
+constexpr int kLeftMax = 8;                // surplus points of a cell handed to k_sweep_left
 // pre-filter thresholds in units of r^2, exactly representable in fp16.  Total rounding error of
 // the fp16 distance (derivation in DESIGN.md 5.2): < 0.0069 on non-periodic grids (|u_x| <= 3,
 // |u_yz| <= 1.5), < 0.011 on periodic grids (cell_size / r < 4/3: |u_x| < 4, |u_yz| < 2).
@@ -154,7 +155,7 @@ __device__ __forceinline__ unsigned test_block_half(const uint32_t *__restrict__
 template <int ND, bool PER, class CL, int kWPC, bool HALF, bool TWO>
 __global__ void __launch_bounds__(kFTX * kWPC * 32, 1024 / (kFTX * kWPC * 32))
 k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ overflow_tiles,
-              int *__restrict__ overflow_count)
+              int *__restrict__ overflow_count, int *__restrict__ left_ids)
 {
     const float4 *__restrict__ sorted = cand.rec;
     const float4 *__restrict__ q_sorted = qry.rec;
@@ -256,9 +257,26 @@ k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ o
         if (threadIdx.x == 0) overflow_tiles[atomicAdd(overflow_count, 1)] = (int)blockIdx.x;
         return;
     }
-    int n_batches = 0;
-#pragma unroll
-    for (int w = 0; w < kFTX; w++) n_batches = max(n_batches, s_maxpass[w]);
+    // A cell with a few points more than a warp (33 .. 32 + kLeftMax; 4.8 % of the cells of the
+    // benchmark cloud, 18 % of the tiles) would need a second batch that repeats the whole test
+    // phase for a handful of active lanes: those points go to a list that k_sweep_left works
+    // off (one thread per point), and the cell runs ONE batch.  overflow_count[1] = list length.
+    if (left_ids != nullptr) {
+        const uint32_t cnt = c_p1 - c_p0;
+        if (cnt > 32u && cnt <= 32u + (uint32_t)kLeftMax) {
+            if (part == 0) {
+                const uint32_t nl = cnt - 32u;
+                int base_l = 0;
+                if (lane == 0) base_l = atomicAdd(overflow_count + 1, (int)nl);
+                base_l = __shfl_sync(0xffffffffu, base_l, 0);
+                if ((uint32_t)lane < nl)
+                    left_ids[base_l + lane] = __float_as_int(__ldg(&q_sorted[c_p0 + 32u + (uint32_t)lane].w));
+            }
+            c_p1 = c_p0 + 32u;
+        }
+    }
+    // batches of THIS cell (its warps synchronise among themselves only: named barriers)
+    const int n_batches = (int)((c_p1 - c_p0 + 31u) / 32u);
 
     // ---- stage every cell of the table: exact positions, fp16 copies, closure payload ---------
     // tile centre (local cell c covers [minc + (c + off - 1) cs, minc + (c + off) cs))
@@ -520,6 +538,102 @@ k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ o
         if (part == 0 && active) cl.finish(st, TWO ? -1 : (int)i_sorted, i_id);
     }
     (void)kFThreads;
+}
+
+// The surplus points of cells with 33 .. 32 + kLeftMax points (see k_sweep_tiles).  G = 8 lanes
+// share a point: lane s takes candidates s, s + 8, ... of every neighbour cell (one coalesced
+// 128-byte read per round), the reference's exact test, the closure's global-memory pair
+// function; the partial results are merged through the closure's own save_acc / add_acc (or
+// summed, for count-only closures).  Closures whose result depends on the rank of a hit
+// (neighbour-list fill) keep one thread per point.
+template <int ND, bool PER, class CL>
+__global__ void __launch_bounds__(128)
+k_sweep_left(GridP g, CellsView cand, const float *__restrict__ x,
+             const int *__restrict__ left_ids, const int *__restrict__ left_count, CL cl)
+{
+    constexpr int G = needs_exact_masks<CL>::value ? 1 : 8;
+    constexpr int kWords = CL::kAccWords > 0 ? CL::kAccWords : 1;
+    __shared__ float s_red[4][kWords][32];
+    const int n = *left_count;
+    const PerP pp = make_perp(g);
+    const int lane = lane_id(), sub = lane % G;
+    const int groups_total = (int)(gridDim.x * blockDim.x) / G;
+    const int gidx = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G;
+    // the groups of a warp hold consecutive t: the warp leaves the loop together
+    for (int t = gidx; t - lane / G < n; t += groups_total) {
+        const bool have = t < n;
+        const int i_id = have ? left_ids[t] : left_ids[0];
+        float p[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < ND; d++) p[d] = __ldg(x + (int64_t)i_id * ND + d);
+        int cc[3];
+#pragma unroll
+        for (int d = 0; d < ND; d++) cc[d] = cell_coord(p[d], g.minc[d], g.cs[d], g.periodic, g.nc[d], g.off[d]);
+#pragma unroll
+        for (int d = ND; d < 3; d++) cc[d] = 1;
+        typename CL::State st;
+        cl.init(st, have, -1, i_id);
+        int hits = 0;
+        // the point sits in a valid cell (it came out of the cell list), so its stencil is inside
+        // the padded grid.  All cell ranges first, then the candidates with several loads in flight.
+        constexpr int NC = ND == 3 ? 27 : (ND == 2 ? 9 : 3);
+        uint32_t cb[NC], cn[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) {
+            int c0 = cc[0] + (e % 3) - 1;
+            int c1 = cc[1] + (ND > 1 ? (e / 3) % 3 - 1 : 0);
+            int c2 = cc[2] + (ND > 2 ? e / 9 - 1 : 0);
+            if (PER) {
+                c0 = floormod_i(c0 - 2, g.nc[0]) + 2;
+                if (ND > 1) c1 = floormod_i(c1 - 2, g.nc[1]) + 2;
+                if (ND > 2) c2 = floormod_i(c2 - 2, g.nc[2]) + 2;
+            }
+            cell_range(cand, linear_cell(g, c0, c1, c2), cb[e], cn[e]);
+            if (!have) cn[e] = 0u;
+        }
+        constexpr int U = G == 1 ? 8 : 4;          // loads in flight per lane
+#pragma unroll 1
+        for (int e = 0; e < NC; e++) {
+            const uint32_t b0 = cb[e], cnt = cn[e];
+            for (uint32_t k = (uint32_t)sub; k < cnt; k += (uint32_t)(G * U)) {
+                float4 pj[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    pj[u] = __ldg(cand.rec + b0 + min(k + (uint32_t)(u * G), cnt - 1u));
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (k + (uint32_t)(u * G) >= cnt) break;
+                    const uint32_t gi = b0 + k + (uint32_t)(u * G);
+                    float px = __fsub_rn(p[0], pj[u].x);
+                    float py = ND > 1 ? __fsub_rn(p[1], pj[u].y) : 0.f;
+                    float pz = ND > 2 ? __fsub_rn(p[2], pj[u].z) : 0.f;
+                    float d2 = dist2<ND>(px, py, pz);
+                    d2 = maybe_periodic_fix<ND, PER>(pp, d2, px, py, pz);
+                    if (d2 <= pp.r2) {
+                        if (CL::kCountOnly) hits++;
+                        else cl.template pair_global<ND>(st, px, py, pz, d2, __float_as_int(pj[u].w), gi);
+                    }
+                }
+            }
+        }
+        if (G > 1) {
+            if (CL::kCountOnly) {
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+            } else {
+                float *mine = &s_red[threadIdx.x >> 5][0][lane];
+                __syncwarp();
+                if (sub != 0) cl.save_acc(st, mine);
+                __syncwarp();
+                if (sub == 0) {
+#pragma unroll
+                    for (int u = 1; u < G; u++) cl.add_acc(st, mine + u);
+                }
+            }
+        }
+        if (CL::kCountOnly) cl.count(st, hits);
+        if (have && sub == 0) cl.finish(st, -1, i_id);
+    }
 }
 
 // Tiles that did not fit the staging buffer of k_sweep_tiles: ordered row-by-row sweep with the
