@@ -219,6 +219,11 @@ void pnb_set_tuning(int warps_per_cell, int half_prefilter);
  * cells and swept by the tile kernel when its occupied cells hold >= 12 query points on average,
  * 2 = always, 0 = never (one thread per query point).  Same results. */
 void pnb_set_twoset_tiles(int on);
+/* Cells with 33 .. 40 points in the tile sweep: 1 (default) = for the n-body / WCSPH closures on
+ * clouds of >= 200 000 points the first 32 points run in the tile kernel and the surplus points
+ * in a per-point kernel (instead of a second, nearly empty batch of the whole cell); 0 = never,
+ * 2 = always when the closure allows it (tests).  Same results. */
+void pnb_set_sweep_left(int mode);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
  * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with

@@ -103,6 +103,7 @@ using namespace pnb;
 extern "C" void pnb_set_exact_arithmetic(int on) { g_exact_arithmetic = on != 0; }
 extern "C" int pnb_get_exact_arithmetic(void) { return g_exact_arithmetic; }
 extern "C" void pnb_set_twoset_tiles(int on) { g_tune_twoset = on; }
+extern "C" void pnb_set_sweep_left(int mode) { g_tune_left = mode; }
 extern "C" void pnb_set_tuning(int warps_per_cell, int half_prefilter)
 {
     g_tune_wpc = warps_per_cell;

@@ -10,7 +10,7 @@ namespace pnb {
 extern int g_tune_wpc;    // pnb_set_tuning: warps per cell override (0 = closure default)
 extern int g_tune_half;   // pnb_set_tuning: 0 = exact Float32 test instead of the fp16 pre-filter
 extern int g_tune_twoset; // pnb_set_twoset_tiles: 0 = x != y always uses the per-point kernel
-extern int g_tune_left;   // PNB_SWEEP_LEFT=0: cells with > 32 points always run further batches
+extern int g_tune_left;   // pnb_set_sweep_left / PNB_SWEEP_LEFT: 0 never, 1 default, 2 always (tests)
 
 template <class K>
 static pnb_status allow_smem(K kernel, size_t smem)
@@ -72,16 +72,22 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         }
         if (!g->ovf_count) PNB_CUDA(cudaMalloc(&g->ovf_count, 2 * sizeof(int)));
         PNB_CUDA(cudaMemsetAsync(g->ovf_count, 0, 2 * sizeof(int), s));
-        // list of the surplus points (at most kLeftMax of the >= 33 points of a cell)
+        // list of the surplus points (at most kLeftMax of the >= 33 points of a cell).  Only for
+        // closures with a drain worth saving (n-body, WCSPH) on clouds large enough to amortise
+        // one more launch: count-only closures repeat just the test phase (config 1: 0.123 ms
+        // without, 0.151 ms with the extra kernel), rank-dependent list fills would run it with one
+        // thread per point (config 4 list build: +0.1 ms).
+        const bool use_left = g_tune_left != 0 && !CL::kCountOnly && !needs_exact_masks<CL>::value &&
+                              (n_loop >= 200000 || g_tune_left == 2);
         const int64_t left_need = n_loop / 4 + 64;
-        if (g_tune_left != 0 && left_need > g->left_cap) {
+        if (use_left && left_need > g->left_cap) {
             cudaFree(g->left_ids);
             g->left_ids = nullptr;
             g->left_cap = 0;
             PNB_CUDA(cudaMalloc(&g->left_ids, sizeof(int) * (size_t)left_need));
             g->left_cap = left_need;
         }
-        int *left_ids = g_tune_left != 0 ? g->left_ids : nullptr;
+        int *left_ids = use_left ? g->left_ids : nullptr;
         // variant: warps per cell and the fp16 pre-filter; the tuning overrides (pnb_set_tuning)
         // exist for A/B measurements of the 3-D non-periodic x === y kernels
         int wpc = CL::kWarpsPerCell;

@@ -128,6 +128,7 @@ SIGNATURES = {
     "pnb_set_build_layout": (None, [C.c_int]),
     "pnb_set_bucket_order": (None, [C.c_int]),
     "pnb_set_twoset_tiles": (None, [C.c_int]),
+    "pnb_set_sweep_left": (None, [C.c_int]),
     "pnb_profile_enable": (None, [C.c_int]),
     "pnb_profile_reset": (None, []),
     "pnb_profile_phases": (C.c_int, []),

@@ -1089,3 +1089,59 @@ def test_bucket_order_variants(pn, oracle, order, size):
     finally:
         L.pnb_set_bucket_order(0)
         L.pnb_set_build_layout(1)
+
+
+@pytest.mark.parametrize("layout", [0, 2], ids=["csr", "buckets"])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_surplus_points_kernel(pn, oracle, layout, periodic):
+    """Cells with 33 .. 40 points hand their surplus points to k_sweep_left (default only for large
+    clouds; forced here with pnb_set_sweep_left(2)).  The benchmark lattice has such cells (4.8 %);
+    a blob adds cells far above 40 points, which keep their additional batches.  n-body and WCSPH
+    against the oracle, x === y and two point sets, both cell-list layouts."""
+    L = pn._lib.lib()
+    T = np.float32
+    if periodic:
+        c, r, bmn, bmx = _periodic_case(pn, 26, 3, seed=8)
+        box = (bmn, bmx)
+        mn, mx = bmn, bmx
+    else:
+        c, r, mn, mx = pn.benchmark_cloud((26, 26, 26), seed=8)
+        rng = np.random.default_rng(0)
+        c = np.concatenate([c, (0.5 + 0.03 * rng.random((900, 3))).astype(T)])
+        box = None
+    L.pnb_set_sweep_left(2)
+    L.pnb_set_build_layout(layout)
+    try:
+        nhs = make_grid(pn, 3, r, mn, mx, box=box)
+        og = oracle.Grid(3, r, mn, mx, periodic_box=box)
+        x = dev(c)
+        pn.initialize_(nhs, x, x)
+        og.build(c)
+        cells = np.diff(og.cell_start)
+        assert ((cells > 32) & (cells <= 40)).sum() > 10      # the kernel has work to do
+        if not periodic:
+            assert (cells > 40).sum() > 0
+        mass, G = _nbody_inputs(len(c))
+        dv = torch.zeros((len(c), 3), dtype=torch.float32, device="cuda")
+        pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), G), x, x, nhs)
+        _, r64, rabs = og.nbody(c, c, mass, G, wide=True)
+        assert np.all(np.abs(dv.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30)
+        v, m, p, kw = _wcsph_inputs(pn, c, r, 3, seed=3)
+        dvw = torch.full((len(c), 4), 2.0, dtype=torch.float32, device="cuda")
+        f = pn.WCSPHInteract(dvw, dev(v), dev(v), dev(m), dev(m), dev(p), dev(p), **kw)
+        pn.foreach_point_neighbor(f, x, x, nhs)
+        _, r64, rabs = og.wcsph(c, c, v, v, m, m, p, p, f.params_array(), wide=True)
+        assert np.all(np.abs(dvw.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30)
+        # two point sets through the tile kernel (forced), surplus QUERY points
+        q = np.clip(c + T(0.15) * r, mn, mx).astype(T) if not periodic else c[::-1].copy()
+        L.pnb_set_twoset_tiles(2)
+        vq, mq, pq, _ = _wcsph_inputs(pn, q, r, 3, seed=4)
+        dq = torch.zeros((len(q), 4), dtype=torch.float32, device="cuda")
+        f2 = pn.WCSPHInteract(dq, dev(vq), dev(v), dev(mq), dev(m), dev(pq), dev(p), **kw)
+        pn.foreach_point_neighbor(f2, dev(q), x, nhs)
+        _, r64, rabs = og.wcsph(q, c, vq, v, mq, m, pq, p, f2.params_array(), wide=True)
+        assert np.all(np.abs(dq.cpu().numpy() - r64) <= 1e-5 * rabs + 1e-30)
+    finally:
+        L.pnb_set_sweep_left(1)
+        L.pnb_set_build_layout(1)
+        L.pnb_set_twoset_tiles(1)
