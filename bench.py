@@ -441,8 +441,8 @@ def gpu_arm(args):
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact
                      # workload, from the ncu --set full capture summarised in
-                     # profiles/r1_wcsph_sweep_v5_ncu_summary.txt (793.0 MB + 255.4 MB)
-                     "traffic": 1048416000 if n == 254 else None,
+                     # profiles/r1_wcsph_sweep_v6_ncu_summary.txt (900.8 MB + 255.3 MB)
+                     "traffic": 1156059136 if n == 254 else None,
                      "peak_source": peak_src, "launch_ms": sweep_avg,
                      "algorithmic_bytes": bytes_sweep,
                      "note": "the fused interaction is FP32-issue bound (~100 flop/B), not HBM bound "
@@ -452,9 +452,9 @@ def gpu_arm(args):
                       "model": "8*K_ref + 70*P non-FMA operations; peak = 148 SM x 128 lanes x max clock"},
         "roofline_update": {"bound": "hbm", "kernels": build_names, "achieved": ach_u,
                             "peak": hbm_peak, "unit": "GB/s", "frac": ach_u / hbm_peak,
-                            # profiles/r1_update_v3_ncu_summary.txt: hist 199.8 + 4.9 MB,
-                            # scan 2.7 MB, scatter 200.5 + 214.9 MB
-                            "traffic": None,
+                            # one-pass bucket build: profiles/r1_update_v4_bucket_ncu_summary.txt
+                            # (209.5 MB read + 223.6 MB written per launch at this workload)
+                            "traffic": 433141504 if (n == 254 and "k_bucket_scatter" in build_names) else None,
                             "device_ms": build_ms, "algorithmic_bytes": bytes_update,
                             "per_kernel_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in build_names},
                             "call_ms": update_ms,
