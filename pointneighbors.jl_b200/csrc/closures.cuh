@@ -34,6 +34,7 @@ struct CountCl {
     __device__ __forceinline__ void save_acc(const State &, float *) const {}
     __device__ __forceinline__ void add_acc(State &, const float *) const {}
     __device__ __forceinline__ void seek(State &, int) const {}
+    __device__ __forceinline__ void total(State &, int, bool) const {}
     __device__ __forceinline__ void flush(State &) const {}
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.cnt = 0; }
     __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
@@ -92,6 +93,7 @@ struct NBodyClT {
         s.a[0] += p[0]; s.a[1] += p[32]; s.a[2] += p[64];
     }
     __device__ __forceinline__ void seek(State &, int) const {}
+    __device__ __forceinline__ void total(State &, int, bool) const {}
     __device__ __forceinline__ void flush(State &) const {}
     __device__ __forceinline__ void init(State &s, bool, int, int) const { s.a[0] = s.a[1] = s.a[2] = 0.f; }
     __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi, int) const
@@ -181,6 +183,7 @@ struct WcsphClT {
         s.acc[0] += p[0]; s.acc[1] += p[32]; s.acc[2] += p[64]; s.acc[3] += p[96];
     }
     __device__ __forceinline__ void seek(State &, int) const {}
+    __device__ __forceinline__ void total(State &, int, bool) const {}
     __device__ __forceinline__ void flush(State &) const {}
 
     __device__ __forceinline__ void init(State &s, bool active, int i_sorted, int i_id) const

@@ -72,6 +72,9 @@ struct pnb_grid {
     bool built;
     bool full_build;        // eachindex_y == all
 
+    // capacity hint for one-pass neighbour-list builds (nlist.cu): longest list of the last build
+    int nl_cap_hint;
+
     // per-sweep scratch (payload gathered into cell order), grown on demand
     void *scratch;
     int64_t scratch_bytes;

@@ -6,6 +6,7 @@
 // reference: src/nhs_precomputed.jl:130-247 (initialize!, initialize_neighbor_lists!, sweep),
 // src/vector_of_vectors.jl:3-31,177-212 (layout, sorteach!),
 // benchmarks/smoothed_particle_hydrodynamics.jl:136-189 (TLSPH set-up).
+#include <cstdlib>
 #include <cstring>
 
 #include "closures.cuh"
@@ -35,8 +36,8 @@ namespace pnb {
 // step (update! of a PrecomputedNeighborhoodSearch) does not pay cudaMalloc / cudaFree of
 // gigabytes each time.  Keyed by the device the buffer lives on.
 struct SpareBuf { void *p; size_t bytes; int device; };
-static SpareBuf g_spare[5] = {{nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1},
-                              {nullptr, 0, -1}};
+static SpareBuf g_spare[6] = {{nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1},
+                              {nullptr, 0, -1}, {nullptr, 0, -1}};
 
 static cudaError_t cached_malloc(int kind, void **out, size_t bytes, size_t *got)
 {
@@ -87,6 +88,7 @@ struct ListCountCl {
     __device__ __forceinline__ void save_acc(const State &, float *) const {}
     __device__ __forceinline__ void add_acc(State &, const float *) const {}
     __device__ __forceinline__ void seek(State &, int) const {}
+    __device__ __forceinline__ void total(State &, int, bool) const {}
     __device__ __forceinline__ void flush(State &) const {}
     template <int ND>
     __device__ __forceinline__ void pair_s(State &, float, float, float, float, int, uint32_t, int,
@@ -121,6 +123,7 @@ struct ListFillCl {
     __device__ __forceinline__ void save_acc(const State &, float *) const {}
     __device__ __forceinline__ void add_acc(State &, const float *) const {}
     __device__ __forceinline__ void seek(State &s, int first_rank) const { s.pos += first_rank; }
+    __device__ __forceinline__ void total(State &, int, bool) const {}
     // Every lane appends to its own list, so a warp-wide 4-byte store touches 32 different
     // sectors.  Ids are therefore collected four at a time and written with one 16-byte store
     // once the write position is 16-byte aligned (scalar stores before that and in flush()).
@@ -168,6 +171,88 @@ struct ListFillCl {
         ids[s.pos++] = j_id;
     }
     __device__ __forceinline__ void finish(State &, int, int) const {}
+};
+
+// One-pass fill into rows of fixed capacity (the reference's own layout, max_neighbors x N,
+// vector_of_vectors.jl:3-31, with the capacity taken from the longest list of the previous
+// build): no count pass, no scan before the fill.  The tile kernel tells the closure the total
+// number of hits of a point (total()), which becomes lengths[i]; a list longer than the capacity
+// sets bit 3 of *err and is not written (the caller then falls back to the two-pass build).
+struct ListFillRowsCl {
+    static constexpr bool kCountOnly = false;
+    static constexpr int kPayBytes = 0;
+    static constexpr int kWarpsPerCell = 4;
+    static constexpr int kAccWords = 1;
+    static constexpr bool kExactMasks = true;
+    static constexpr bool kBigTiles = true;
+    int32_t *rows;       // [nx * cap]
+    uint32_t *lengths;   // [nx]
+    int cap;             // multiple of 4: every row starts 16-byte aligned
+    int *err;
+    // n >= 0: hits appended by a kernel that walks the candidates one by one (overflow / per-point
+    // kernels; finish() writes the length); n == -1: the tile kernel already wrote it (total())
+    struct State { int64_t pos; int b0, b1, b2, b3, nb; int n; int i; bool skip; };
+    __device__ __forceinline__ void save_acc(const State &, float *) const {}
+    __device__ __forceinline__ void add_acc(State &, const float *) const {}
+    __device__ __forceinline__ void seek(State &s, int first_rank) const { s.pos += first_rank; }
+    __device__ __forceinline__ void total(State &s, int hits, bool writer) const
+    {
+        s.n = -1;
+        if (hits > cap) { s.skip = true; if (writer) atomicOr(err, 8); }
+        if (writer) lengths[s.i] = (uint32_t)hits;
+    }
+    template <int ND>
+    __device__ __forceinline__ void pair_s(State &s, float, float, float, float, int j_id, uint32_t,
+                                           int, int) const
+    {
+        if (s.skip) return;
+        if (s.nb == 0 && (s.pos & 3) != 0) { rows[s.pos++] = j_id; return; }
+        if (s.nb == 0) s.b0 = j_id;
+        else if (s.nb == 1) s.b1 = j_id;
+        else if (s.nb == 2) s.b2 = j_id;
+        else s.b3 = j_id;
+        if (++s.nb == 4) {
+            *reinterpret_cast<int4 *>(rows + s.pos) = make_int4(s.b0, s.b1, s.b2, s.b3);
+            s.pos += 4;
+            s.nb = 0;
+        }
+    }
+    __device__ __forceinline__ void flush(State &s) const
+    {
+        if (s.nb > 0) rows[s.pos] = s.b0;
+        if (s.nb > 1) rows[s.pos + 1] = s.b1;
+        if (s.nb > 2) rows[s.pos + 2] = s.b2;
+        s.pos += s.nb;
+        s.nb = 0;
+    }
+    __device__ __forceinline__ void init(State &s, bool active, int, int i_id) const
+    {
+        s.pos = active ? (int64_t)i_id * cap : 0;
+        s.b0 = s.b1 = s.b2 = s.b3 = 0;
+        s.nb = 0;
+        s.n = 0;
+        s.i = i_id;
+        s.skip = !active;
+    }
+    __device__ __forceinline__ void stage(unsigned char *, int, uint32_t, int) const {}
+    __device__ __forceinline__ void count(State &, int) const {}
+    __device__ __forceinline__ void append(State &s, int j_id) const
+    {
+        if (s.n < cap) rows[s.pos + s.n] = j_id;
+        s.n++;
+    }
+    template <int ND>
+    __device__ __forceinline__ void pair(State &s, float, float, float, float, int j_id,
+                                         const unsigned char *, int, int) const { append(s, j_id); }
+    template <int ND>
+    __device__ __forceinline__ void pair_global(State &s, float, float, float, float, int j_id,
+                                                uint32_t) const { append(s, j_id); }
+    __device__ __forceinline__ void finish(State &s, int, int i_id) const
+    {
+        if (s.n < 0) return;
+        if (s.n > cap) atomicOr(err, 8);
+        lengths[i_id] = (uint32_t)s.n;
+    }
 };
 
 // sorteach! (vector_of_vectors.jl:177-183): every list ascending.  One warp per list.
@@ -260,6 +345,64 @@ k_sort_lists(int64_t nx, const int64_t *__restrict__ offsets, int32_t *__restric
             for (int e = (pass & 1) + 2 * lane; e + 1 < len; e += 64) {
                 const int32_t a = lst[e], b = lst[e + 1];
                 if (a > b) { lst[e] = b; lst[e + 1] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// sorteach! fused with the compaction of the fixed-capacity rows into the CSR list: one warp per
+// list reads its row, sorts (registers up to 128 entries) and writes ids[offsets[i] ...].
+template <int NR>
+__device__ __forceinline__ void sort_row_regs(const int32_t *src, int32_t *dst, int len, int lane)
+{
+    int32_t v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) v[r] = (r * 32 + lane < len) ? src[r * 32 + lane] : 0x7fffffff;
+    bitonic_sort_regs<NR>(v, lane);
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+        if (r * 32 + lane < len) dst[r * 32 + lane] = v[r];
+}
+
+__global__ void __launch_bounds__(kSortWarps * 32)
+k_sort_compact_rows(int64_t nx, int cap, const int32_t *__restrict__ rows,
+                    const uint32_t *__restrict__ lengths, const int64_t *__restrict__ offsets,
+                    int32_t *__restrict__ ids, int sort)
+{
+    __shared__ int32_t s_buf[kSortWarps][kSortCap];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int64_t i = (int64_t)blockIdx.x * kSortWarps + warp;
+    if (i >= nx) return;
+    const int len = (int)lengths[i];
+    if (len == 0) return;
+    const int32_t *src = rows + i * (int64_t)cap;
+    int32_t *dst = ids + offsets[i];
+    if (!sort) {
+        for (int e = lane; e < len; e += 32) dst[e] = src[e];
+    } else if (len <= 32) {
+        sort_row_regs<1>(src, dst, len, lane);
+    } else if (len <= 64) {
+        sort_row_regs<2>(src, dst, len, lane);
+    } else if (len <= 128) {
+        sort_row_regs<4>(src, dst, len, lane);
+    } else if (len <= kSortCap) {
+        int32_t *buf = s_buf[warp];
+        for (int e = lane; e < len; e += 32) buf[e] = src[e];
+        __syncwarp();
+        for (int e = lane; e < len; e += 32) {
+            const int32_t v = buf[e];
+            int r = 0;
+            for (int k = 0; k < len; k++) r += (buf[k] < v);
+            dst[r] = v;
+        }
+    } else {
+        for (int e = lane; e < len; e += 32) dst[e] = src[e];
+        __syncwarp();
+        for (int pass = 0; pass < len; pass++) {
+            for (int e = (pass & 1) + 2 * lane; e + 1 < len; e += 64) {
+                const int32_t a = dst[e], b = dst[e + 1];
+                if (a > b) { dst[e] = b; dst[e + 1] = a; }
             }
             __syncwarp();
         }
@@ -517,6 +660,15 @@ extern "C" int64_t pnb_nlist_n_points(const pnb_nlist *l) { return l ? l->nx : 0
 extern "C" int64_t pnb_nlist_n_pairs(const pnb_nlist *l) { return l ? l->n_pairs : 0; }
 extern "C" int64_t pnb_nlist_max_length(const pnb_nlist *l) { return l ? l->max_len : 0; }
 
+// capacity of the rows of the next one-pass build: the longest list + 12.5 % + 8, multiple of 4
+static int nlist_cap_for(unsigned int longest)
+{
+    const int64_t c = ((int64_t)longest + longest / 8 + 8 + 3) / 4 * 4;
+    return c > 4096 ? 0 : (int)c;       // very long lists: keep the two-pass build
+}
+// PNB_NLIST_ONE_PASS=0: always count + fill (two test passes)
+static int g_nlist_one_pass = getenv("PNB_NLIST_ONE_PASS") ? atoi(getenv("PNB_NLIST_ONE_PASS")) : 1;
+
 extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
                                           int64_t n, int sort, pnb_nlist **out, void *stream)
 {
@@ -568,6 +720,52 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     // sorted lists do not depend on the visiting order: the tile kernel builds them; unsorted
     // lists keep the reference's order and use the ordered kernel
     const bool tiles = sort != 0;
+    // ---- one test pass (repeated builds of sorted x === y lists): rows of fixed capacity taken
+    // from the longest list of the previous build, then sort + compaction into the CSR list ----
+    if (g_nlist_one_pass && fast && tiles && g->nl_cap_hint > 0 && nx > 0 && !g->hashed &&
+        (int64_t)nx * g->nl_cap_hint < (int64_t)1 << 34) {
+        const int cap = g->nl_cap_hint;
+        int32_t *rows = nullptr;
+        size_t bytes_rows = 0;
+        NL_CUDA(cached_malloc(5, (void **)&rows, sizeof(int32_t) * (size_t)nx * cap, &bytes_rows));
+        auto drop_rows = [&]() { cached_free(5, rows, bytes_rows); };
+        st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListFillRowsCl{rows, l->counts, cap, l->d_err}, s);
+        if (st == PNB_OK) st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
+        if (st != PNB_OK) { drop_rows(); return fail(st); }
+        int64_t total1 = 0;
+        unsigned int longest1 = 0;
+        int err1 = 0;
+        k_max_count<<<(unsigned)div_up(nx, 256), 256, 0, s>>>(nx, l->counts, l->counts + nx);
+        g_launch_count++;
+        cudaError_t e1 = cudaMemcpyAsync(&total1, l->offsets + nx, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(&longest1, l->counts + nx, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(&err1, l->d_err, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(s);
+        if (e1 != cudaSuccess) { drop_rows(); return fail(cuda_fail(e1, "one-pass list build")); }
+        if ((err1 & 8) == 0) {
+            l->n_pairs = total1;
+            l->max_len = longest1;
+            e1 = cached_malloc(1, (void **)&l->ids, sizeof(int32_t) * (size_t)(total1 > 0 ? total1 : 1), &l->bytes_ids);
+            if (e1 != cudaSuccess) { drop_rows(); return fail(cuda_fail(e1, "cudaMalloc ids")); }
+            {
+                ProfScope ps(PH_NLIST_SORT, s);
+                k_sort_compact_rows<<<(unsigned)div_up(nx, kSortWarps), kSortWarps * 32, 0, s>>>(
+                    nx, cap, rows, l->counts, l->offsets, l->ids, 1);
+                g_launch_count++;
+            }
+            st = check_err_word(g, s);
+            drop_rows();
+            if (st != PNB_OK) return fail(st);
+            g->nl_cap_hint = nlist_cap_for(longest1);
+            *out = l;
+            return PNB_OK;
+        }
+        // a list outgrew the capacity: forget the hint, build in two passes below
+        drop_rows();
+        g->nl_cap_hint = 0;
+        NL_CUDA(cudaMemsetAsync(l->d_err, 0, sizeof(int), s));
+        NL_CUDA(cudaMemsetAsync(l->counts, 0, sizeof(uint32_t) * (size_t)(nx + 8), s));
+    }
     st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListCountCl{l->counts}, s);
     if (st != PNB_OK) return fail(st);
     st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
@@ -597,6 +795,7 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     }
     st = check_err_word(g, s);
     if (st != PNB_OK) return fail(st);
+    if (fast && tiles) g->nl_cap_hint = nlist_cap_for(longest);   // the next build can fill in one pass
 #undef NL_CUDA
     *out = l;
     return PNB_OK;

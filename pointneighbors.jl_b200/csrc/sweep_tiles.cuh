@@ -484,6 +484,7 @@ k_sweep_tiles(GridP g, CellsView cand, CellsView qry, CL cl, int *__restrict__ o
             int H = 0;
 #pragma unroll
             for (int p = 0; p < kWPC; p++) { pc[p] = s_cnt[my_cell][p][lane]; H += pc[p]; }
+            cl.total(st, H, part == 0 && active);
             const int Q = (H + kWPC - 1) / kWPC;
             int skip = part * Q;
             const int n_mine = max(0, min(Q, H - skip));

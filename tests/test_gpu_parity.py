@@ -479,7 +479,7 @@ def test_edge_cases(pn, oracle):
     assert int(np.diff(off_o2).max()) > 512
     pn.initialize_(nhs, td, td)
     pre_mid = pn.PrecomputedNeighborhoodSearch[3](search_radius=T(0.1), n_points=300,
-                                                  update_neighborhood_search=nhs, max_neighbors=400)
+                                                  update_neighborhood_search=nhs, max_neighbors=640)
     pn.initialize_(pre_mid, td, td)
     off_m, ids_m = pre_mid.export_csr()
     off_o1, ids_o1 = og.neighbor_lists(dense, dense, sort=True)
@@ -1145,3 +1145,45 @@ def test_surplus_points_kernel(pn, oracle, layout, periodic):
         L.pnb_set_sweep_left(1)
         L.pnb_set_build_layout(1)
         L.pnb_set_twoset_tiles(1)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_neighbor_lists_one_pass_rebuilds(pn, oracle, periodic):
+    """Repeated builds of sorted x === y lists fill fixed-capacity rows in ONE test pass (capacity =
+    longest list of the previous build + margin) and sort + compact them into the CSR list; a list
+    that outgrows the capacity falls back to count + fill.  Every rebuild must give the oracle's
+    lists; PNB_NLIST_ONE_PASS-independent."""
+    T = np.float32
+    rng = np.random.default_rng(12)
+    if periodic:
+        c, r, bmn, bmx = _periodic_case(pn, 22, 3, seed=4)
+        box, mn, mx = (bmn, bmx), bmn, bmx
+    else:
+        c, r, mn, mx = pn.benchmark_cloud((24, 24, 24), seed=4)
+        box = None
+    nhs = make_grid(pn, 3, r, mn, mx, box=box)
+    og = oracle.Grid(3, r, mn, mx, periodic_box=box)
+    pre = pn.PrecomputedNeighborhoodSearch[3](search_radius=r, n_points=len(c),
+                                              periodic_box=nhs.periodic_box,
+                                              update_neighborhood_search=nhs, max_neighbors=640)
+    clouds = [c]
+    for k in range(2):
+        clouds.append(np.clip(clouds[-1] + T(0.02) * r * rng.standard_normal(c.shape).astype(T),
+                              mn + T(1e-6), mx - T(1e-6)).astype(T))
+    # a blob: the longest list grows far beyond the capacity derived from the previous build
+    blob = clouds[-1].copy()
+    blob[:300] = (T(0.5) * (mn + mx) + T(0.3) * r * rng.random((300, 3)).astype(T)).astype(T)
+    clouds.append(blob)
+    clouds.append(clouds[1])          # and back: one pass again with the larger capacity
+    for k, cl in enumerate(clouds):
+        x = dev(cl)
+        if k == 0:
+            pn.initialize_(pre, x, x)
+        else:
+            pn.update_(pre, x, x, points_moving=(True, True))
+        og.build(cl)
+        roff, rids = og.neighbor_lists(cl, cl, sort=True)
+        off, ids = (t.cpu().numpy() for t in pre.export_csr())
+        assert np.array_equal(off, roff) and np.array_equal(ids, rids), k
+        backend, lengths = pre.neighbor_lists(index_base=1)
+        assert np.array_equal(lengths.cpu().numpy(), np.diff(roff)), k
