@@ -47,48 +47,79 @@ k_hash_points(GridP g, const float *__restrict__ y, int64_t n_idx, const int32_t
     }
 }
 
-// coords / collisions of every key from its finished list (ids ascending = the serial insertion
-// order of push_cell!, spatial_hashing.jl:79-97): `coords` is overwritten while it is still 0,
-// i.e. it ends up as the cell F of the first point whose flattened cell is not 0; a collision is
-// recorded by every later point whose cell differs from F.  One warp per key.
+// One warp per 32 keys: a table of list_size = 2 N keys (the recommended size) has one occupied
+// key in ~50, so every lane first looks at ITS key and the warp then works through the occupied
+// ones together (one warp per key would launch 64 N threads to find 98 % of the keys empty).
+// Per occupied key: sort the list by point id (canonical order, into `out` / `cell_points`) and
+// derive coords / collisions from it.
 template <int ND, bool PER>
 __global__ void __launch_bounds__(256)
-k_hash_meta(GridP g, const uint32_t *__restrict__ key_start, const float4 *__restrict__ sorted,
-            int4 *__restrict__ meta)
+k_hash_finish(GridP g, const uint32_t *__restrict__ key_start, const float4 *__restrict__ in,
+              float4 *__restrict__ out, int32_t *__restrict__ cell_points, int4 *__restrict__ meta)
 {
-    const int64_t key = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (key >= g.total_cells) return;
     const int lane = lane_id();
-    const uint32_t s0 = key_start[key], s1 = key_start[key + 1];
-    // phase 1: first entry with a non-zero flattened cell
-    uint32_t first = 0xffffffffu;
-    for (uint32_t e = s0 + lane; e < s1 && first == 0xffffffffu; e += 32) {
-        const float4 r = sorted[e];
-        const float p[3] = {r.x, r.y, r.z};
-        long long cc[3];
-        hash_cell_coords<ND, PER>(g, p, cc);
-        if (cc[0] != 0 || cc[1] != 0 || cc[2] != 0) first = e;
-    }
-    first = __reduce_min_sync(0xffffffffu, first);
-    int4 m = make_int4(0, 0, 0, 0);
-    if (first != 0xffffffffu) {
-        const float4 r = sorted[first];
-        const float p[3] = {r.x, r.y, r.z};
-        long long cf[3];
-        hash_cell_coords<ND, PER>(g, p, cf);
-        m.x = (int)cf[0]; m.y = (int)cf[1]; m.z = (int)cf[2];
-        // phase 2: any later entry from another cell
-        int coll = 0;
-        for (uint32_t e = first + 1 + lane; e < s1 && !coll; e += 32) {
-            const float4 q = sorted[e];
-            const float pq[3] = {q.x, q.y, q.z};
-            long long cc[3];
-            hash_cell_coords<ND, PER>(g, pq, cc);
-            if (cc[0] != cf[0] || cc[1] != cf[1] || cc[2] != cf[2]) coll = 1;
+    const int64_t key0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    const int64_t my_key = key0 + lane;
+    uint32_t my_s0 = 0, my_s1 = 0;
+    if (my_key < g.total_cells) { my_s0 = key_start[my_key]; my_s1 = key_start[my_key + 1]; }
+    if (my_key < g.total_cells && my_s0 == my_s1) meta[my_key] = make_int4(0, 0, 0, 0);
+    unsigned todo = __ballot_sync(0xffffffffu, my_s1 > my_s0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t s0 = __shfl_sync(0xffffffffu, my_s0, src);
+        const uint32_t s1 = __shfl_sync(0xffffffffu, my_s1, src);
+        const int cnt = (int)(s1 - s0);
+        // ---- ids ascending inside the key (rank by counting) ----
+        if (cnt <= 32) {
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            int v = 0x7fffffff;
+            if (lane < cnt) { rec = in[s0 + lane]; v = __float_as_int(rec.w); }
+            int r = 0;
+            for (int k = 0; k < cnt; k++) r += (__shfl_sync(0xffffffffu, v, k) < v) ? 1 : 0;
+            if (lane < cnt) { cell_points[s0 + r] = v; out[s0 + r] = rec; }
+        } else {
+            for (int e = lane; e < cnt; e += 32) {
+                const float4 rec = in[s0 + e];
+                const int v = __float_as_int(rec.w);
+                int r = 0;
+                for (int k = 0; k < cnt; k++) r += (__float_as_int(in[s0 + k].w) < v) ? 1 : 0;
+                cell_points[s0 + r] = v;
+                out[s0 + r] = rec;
+            }
         }
-        m.w = __any_sync(0xffffffffu, coll) ? 1 : 0;
+        __syncwarp();
+        // ---- coords / collisions from the list in ascending id order (push_cell!, :79-97):
+        // `coords` is overwritten while it is still 0, i.e. it ends up as the cell F of the first
+        // point whose flattened cell is not 0; every later point from another cell is a collision
+        uint32_t first = 0xffffffffu;
+        for (uint32_t e = s0 + lane; e < s1 && first == 0xffffffffu; e += 32) {
+            const float4 r4 = out[e];
+            const float p[3] = {r4.x, r4.y, r4.z};
+            long long cc[3];
+            hash_cell_coords<ND, PER>(g, p, cc);
+            if (cc[0] != 0 || cc[1] != 0 || cc[2] != 0) first = e;
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        int4 m = make_int4(0, 0, 0, 0);
+        if (first != 0xffffffffu) {
+            const float4 r4 = out[first];
+            const float p[3] = {r4.x, r4.y, r4.z};
+            long long cf[3];
+            hash_cell_coords<ND, PER>(g, p, cf);
+            m.x = (int)cf[0]; m.y = (int)cf[1]; m.z = (int)cf[2];
+            int coll = 0;
+            for (uint32_t e = first + 1 + lane; e < s1 && !coll; e += 32) {
+                const float4 q = out[e];
+                const float pq[3] = {q.x, q.y, q.z};
+                long long cc[3];
+                hash_cell_coords<ND, PER>(g, pq, cc);
+                if (cc[0] != cf[0] || cc[1] != cf[1] || cc[2] != cf[2]) coll = 1;
+            }
+            m.w = __any_sync(0xffffffffu, coll) ? 1 : 0;
+        }
+        if (lane == 0) meta[key0 + src] = m;
     }
-    if (lane == 0) meta[key] = m;
 }
 
 // the table in the reference's field layout: coords = Vector{UInt128} (4 little-endian 32-bit
@@ -135,13 +166,17 @@ static pnb_status hash_build_nd(pnb_grid *g, const float *y, const int32_t *idx,
 }
 
 template <int ND, bool PER>
-static pnb_status hash_meta_nd(pnb_grid *g, cudaStream_t s)
+static pnb_status hash_finish_nd(pnb_grid *g, cudaStream_t s)
 {
     const int64_t L = g->p.total_cells;
+    if (!g->sorted_alt) PNB_CUDA(cudaMalloc(&g->sorted_alt, sizeof(float4) * (size_t)g->cap_points));
+    if (!g->cell_points) PNB_CUDA(cudaMalloc(&g->cell_points, sizeof(int32_t) * (size_t)g->cap_points));
     ProfScope ps(PH_BUILD_FINALIZE, s);
-    k_hash_meta<ND, PER><<<(unsigned)div_up(L * 32, 256), 256, 0, s>>>(g->p, g->cell_start, g->sorted,
-                                                                     g->hmeta);
+    k_hash_finish<ND, PER><<<(unsigned)div_up(div_up(L, 32) * 32, 256), 256, 0, s>>>(
+        g->p, g->cell_start, g->sorted, g->sorted_alt, g->cell_points, g->hmeta);
     PNB_LAUNCHED();
+    float4 *t = g->sorted; g->sorted = g->sorted_alt; g->sorted_alt = t;
+    g->canonical = true;
     return PNB_OK;
 }
 
@@ -180,15 +215,13 @@ pnb_status hash_build(pnb_grid *g, const float *y, int64_t n, const int32_t *idx
     g->full_build = (idx == nullptr);
     g->built = true;
     g->canonical = false;
-    // ids ascending inside every key: the serial insertion order that `coords` / `collisions`
-    // and the visiting order of the sweeps are defined by
-    st = ensure_canonical(g, s);
-    if (st != PNB_OK) return st;
+    // ids ascending inside every key (the serial insertion order that `coords` / `collisions` and
+    // the visiting order of the sweeps are defined by) + the table's coords / collisions
     if (L > 0) {
         switch (g->p.ndims) {
-            case 1: st = per ? hash_meta_nd<1, true>(g, s) : hash_meta_nd<1, false>(g, s); break;
-            case 2: st = per ? hash_meta_nd<2, true>(g, s) : hash_meta_nd<2, false>(g, s); break;
-            default: st = per ? hash_meta_nd<3, true>(g, s) : hash_meta_nd<3, false>(g, s); break;
+            case 1: st = per ? hash_finish_nd<1, true>(g, s) : hash_finish_nd<1, false>(g, s); break;
+            case 2: st = per ? hash_finish_nd<2, true>(g, s) : hash_finish_nd<2, false>(g, s); break;
+            default: st = per ? hash_finish_nd<3, true>(g, s) : hash_finish_nd<3, false>(g, s); break;
         }
         if (st != PNB_OK) return st;
     }
