@@ -414,7 +414,11 @@ def gpu_arm(args):
     K_avg = float(np.mean(kref))
     flops = 8.0 * K_avg + 70.0 * P_avg                 # non-FMA FP32 operations
     fp32_peak = SM_COUNT * FP32_LANES * sm_max_mhz * 1e6 / 1e12
-    fp32_ach = flops / (sweep_avg * 1e-3) / 1e12
+    # the whole interaction's flops over ALL its sweep kernels: the tile kernel plus the overflow /
+    # surplus-point kernels that finish the same sweep (k_sweep_overflow phase)
+    ovf_ms, ovf_n = prof.get("k_sweep_overflow", (0.0, 0))
+    sweep_all = sweep_avg + (ovf_ms / max(sweep_n, 1))
+    fp32_ach = flops / (sweep_all * 1e-3) / 1e12
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -449,7 +453,9 @@ def gpu_arm(args):
                              "(SURVEY.md 8d); see fp32_pipe for the binding roofline"},
         "fp32_pipe": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak,
                       "frac": fp32_ach / fp32_peak,
-                      "model": "8*K_ref + 70*P non-FMA operations; peak = 148 SM x 128 lanes x max clock"},
+                      "sweep_ms": sweep_all,
+                      "model": "8*K_ref + 70*P non-FMA operations over the tile kernel + the overflow / "
+                               "surplus-point kernels of the same sweep; peak = 148 SM x 128 lanes x max clock"},
         "roofline_update": {"bound": "hbm", "kernels": build_names, "achieved": ach_u,
                             "peak": hbm_peak, "unit": "GB/s", "frac": ach_u / hbm_peak,
                             # one-pass bucket build: profiles/r1_update_v4_bucket_ncu_summary.txt
