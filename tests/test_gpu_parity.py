@@ -685,6 +685,17 @@ def test_build_variants_identical(pn, oracle):
                 cs, cp = nhs.export_csr()
                 assert (cs.cpu().numpy() == og.cell_start).all(), variant
                 assert (cp.cpu().numpy() == og.cell_points).all(), variant
+            # one-pass update! into buckets: match.any lane groups (default) and runs of
+            # adjacent lanes (bit 2048) fill the same buckets
+            for variant in (25, 25 | 2048):
+                L.pnb_set_build_tuning(variant)
+                nhs = make_grid(pn, 3, r, mn, mx)
+                pn.initialize_(nhs, x, x)
+                pn.update_(nhs, x, x)
+                pn.update_(nhs, x, x)
+                cs, cp = nhs.export_csr()
+                assert (cs.cpu().numpy() == og.cell_start).all(), variant
+                assert (cp.cpu().numpy() == og.cell_points).all(), variant
     finally:
         L.pnb_set_build_tuning(25)
 
