@@ -11,13 +11,15 @@ from oracle import pn_oracle as oracle
 import bench
 T = np.float32; dev = torch.device("cuda")
 L = _lib.lib()
+# 25 default (match.any lane groups); +2048 runs of adjacent lanes
+VARIANTS = (25, 25 | 2048)
 # parity on a small cloud (sorted and shuffled), update! path = buckets
 c, r, mn, mx = pn.benchmark_cloud((33, 31, 29), seed=12)
 rng = np.random.default_rng(1)
 for cloud in (c, c[rng.permutation(len(c))]):
     og = oracle.Grid(3, r, mn, mx); og.build(cloud)
     x = torch.from_numpy(np.ascontiguousarray(cloud)).to(dev)
-    for variant in (25, 25 | 2048):
+    for variant in VARIANTS:
         L.pnb_set_build_tuning(variant)
         nhs = pn.GridNeighborhoodSearch[3](search_radius=r, n_points=len(cloud), cell_list=pn.FullGridCellList(
             min_corner=mn, max_corner=mx, search_radius=r))
@@ -34,7 +36,7 @@ nhs = pn.GridNeighborhoodSearch[3](search_radius=r, n_points=N, cell_list=pn.Ful
     min_corner=np.zeros(3, T), max_corner=np.ones(3, T), search_radius=r))
 pn.initialize_(nhs, A, A)
 pn.update_(nhs, A, A)
-for variant in (25, 25 | 2048, 25, 25 | 2048):
+for variant in VARIANTS + VARIANTS:
     L.pnb_set_build_tuning(variant)
     for _ in range(3):
         pn.update_(nhs, A, A)
