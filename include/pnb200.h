@@ -168,6 +168,10 @@ int64_t pnb_spatial_hash(int ndims, const int64_t *cell, int64_t list_size);
 void pnb_grid_destroy(pnb_grid *g);
 int64_t pnb_grid_total_cells(const pnb_grid *g);
 int64_t pnb_grid_n_points(const pnb_grid *g); /* points in the cell list after the last build */
+/* layout the last build wrote: 0 = CSR (two-pass counting sort), 1 = buckets (one-pass update!),
+ * -1 = not built.  Inspection only (the reference's cell storage is one layout,
+ * src/vector_of_vectors.jl:3-31; both layouts here export to it). */
+int pnb_grid_layout(const pnb_grid *g);
 
 /* initialize!(nhs, x, y; eachindex_y) / update!(nhs, x, y; points_moving = (_, true), eachindex_y)
  *   src/nhs_grid.jl:220-225, 255-292, 470-477; src/cell_lists/full_grid.jl:96-139
@@ -227,7 +231,11 @@ void pnb_set_sweep_left(int mode);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
  * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with
- * lane runs; default 25).  Results are identical for every setting. */
+ * lane runs; default 25).  Results are identical for every setting.  (The variants of the
+ * one-pass kernel that leave out its atomics or stores -- bits 8..10, invalid layouts, used by
+ * tools/bucket_diag.py to attribute its time -- exist only in a library compiled with -DPNB_DIAG,
+ * which _build.py does when PNB_DIAG=1 is set in the environment; the shipped binary ignores
+ * those bits.) */
 void pnb_set_build_tuning(int variant);
 /* 1 (default): builds after the first one use the one-pass bucket layout (every cell owns K record
  * slots, K from the fullest cell of the last CSR build; a cell that overflows falls back to the

@@ -110,6 +110,15 @@ pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
     return PNB_ERR_BOUNDS;
 }
 
+pnb_status check_built_y(const pnb_grid *g, const void *y, int64_t n)
+{
+    if (y == g->y_built && n == g->n_y_built) return PNB_OK;
+    set_error("neighbor_coords (%p, %lld points) are not the coordinates the search was last "
+              "initialized / updated with (%p, %lld points): call update! first",
+              y, (long long)n, g->y_built, (long long)g->n_y_built);
+    return PNB_ERR_STATE;
+}
+
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes)
 {
     if (bytes <= g->scratch_bytes) return PNB_OK;
@@ -378,6 +387,11 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
 
 extern "C" int64_t pnb_grid_total_cells(const pnb_grid *g) { return g ? g->p.total_cells : 0; }
 extern "C" int64_t pnb_grid_n_points(const pnb_grid *g) { return g ? g->n_built : 0; }
+extern "C" int pnb_grid_layout(const pnb_grid *g)
+{
+    if (!g || !g->built) return -1;
+    return g->bucket_valid ? 1 : 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernels of the counting sort
@@ -966,8 +980,9 @@ pnb_status exclusive_scan_u32_to_i64(pnb_grid *g, const uint32_t *in, int64_t *o
 // histogram pass, no scan: 28 N + 4 C bytes, exactly the algorithmic minimum of SURVEY 8d.
 // A cell that receives more than K points sets error bit 3; the build is then redone as CSR.
 // ---------------------------------------------------------------------------------------------
-// DIAG (measurement only, results invalid): 1 = non-returning atomics (slot from the lane run
-// alone), 2 = no stores, 4 = no atomics at all.  DIAG 8 (valid results, the default of the launch
+// DIAG (measurement only, results invalid, instantiated only when the library is compiled with
+// -DPNB_DIAG for tools/bucket_diag.py -- never in the shipped binary): 1 = non-returning atomics
+// (slot from the lane run alone), 2 = no stores, 4 = no atomics at all.  DIAG 8 (valid results, the default of the launch
 // below): in full tiles the lanes of a warp are grouped by cell with match.any instead of by runs
 // of adjacent lanes -- one atomic and one contiguous piece of the bucket per distinct cell
 // (0.1354 -> 0.1316 ms on config 3).
@@ -1372,6 +1387,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                         // before; valid results, kept for tools/match_diag.py)
                         k_bucket_scatter<3, false, 4, 0><<<(unsigned)div_up(n_idx, kBuildThreads * 4), kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err);
                     }
+#ifdef PNB_DIAG   /* tools/ builds only: these variants write garbage layouts */
                     else if ((g_tune_build >> 8) & 7) {
                         // measurement only (DIAG variants of the kernel; the layout is garbage)
                         const unsigned nb = (unsigned)div_up(n_idx, kBuildThreads * 4);
@@ -1383,6 +1399,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                             default: k_bucket_scatter<3, false, 4, 6><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
                         }
                     }
+#endif
                     else PNB_BUCKET(3, false, 4);
                     break;
             }
@@ -1674,7 +1691,10 @@ k_slab_classify(const float *__restrict__ coords, int64_t n, int nd, float pmin,
             const long long cz = (long long)f + 1;
             up = has_up && cz >= z_hi;
             down = has_down && cz <= z_lo;
-            leave = cz < z_lo || cz > z_hi;
+            // a point that leaves through the global bottom / top has no rank to go to: it is
+            // KEPT, so that the following update! reports it exactly like the undecomposed search
+            // ("particle coordinates are NaN or outside the domain bounds", full_grid.jl:211)
+            leave = (cz < z_lo && has_down) || (cz > z_hi && has_up);
         }
     }
     warp_append(up, (int32_t)i, up_idx, cap, counts + 0);
@@ -2319,12 +2339,12 @@ extern "C" pnb_status pnb_count_neighbors_f64(pnb_grid *g, const double *x, int6
                                               int64_t n_points, int index_base, int64_t *out,
                                               void *stream)
 {
-    (void)y; (void)n;
     if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
     if (!g->built) {
         set_error("the neighborhood search has not been initialized (call initialize! first)");
         return PNB_ERR_STATE;
     }
+    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
     cudaStream_t s = (cudaStream_t)stream;
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)nx, s));
     const int64_t n_loop = points ? n_points : nx;

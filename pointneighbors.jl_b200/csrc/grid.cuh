@@ -95,6 +95,9 @@ pnb_status ensure_point_capacity(pnb_grid *g, int64_t n);
 pnb_status hash_build(pnb_grid *g, const float *y, int64_t n, const int32_t *idx, int64_t n_idx,
                       int base, cudaStream_t s);
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
+// neighbor_coords of a sweep / list build must be the array of the last initialize!/update!
+// (the sweeps read the snapshot taken there; the reference reads y live, src/nhs_grid.jl:543-548)
+pnb_status check_built_y(const pnb_grid *g, const void *y, int64_t n);
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
 pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *points_per_cell,
                             cudaStream_t s);  // two-set sweeps

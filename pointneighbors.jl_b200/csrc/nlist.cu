@@ -6,6 +6,7 @@
 // reference: src/nhs_precomputed.jl:130-247 (initialize!, initialize_neighbor_lists!, sweep),
 // src/vector_of_vectors.jl:3-31,177-212 (layout, sorteach!),
 // benchmarks/smoothed_particle_hydrodynamics.jl:136-189 (TLSPH set-up).
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 
@@ -35,19 +36,26 @@ namespace pnb {
 // One spare device buffer per kind survives pnb_nlist_destroy, so that rebuilding the lists every
 // step (update! of a PrecomputedNeighborhoodSearch) does not pay cudaMalloc / cudaFree of
 // gigabytes each time.  Keyed by the device the buffer lives on.
+// Thread-safe (mutex); a buffer is handed out again only after the device has finished with it:
+// cached_free synchronises the device before parking the buffer, which costs nothing on the
+// paths that call it (pnb_nlist_destroy follows blocking calls).
 struct SpareBuf { void *p; size_t bytes; int device; };
 static SpareBuf g_spare[6] = {{nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1}, {nullptr, 0, -1},
                               {nullptr, 0, -1}, {nullptr, 0, -1}};
+static std::mutex g_spare_mutex;
 
 static cudaError_t cached_malloc(int kind, void **out, size_t bytes, size_t *got)
 {
     int dev = 0;
     cudaGetDevice(&dev);
-    SpareBuf &sp = g_spare[kind];
-    if (sp.p && sp.device == dev && sp.bytes >= bytes && sp.bytes <= 2 * bytes + (1u << 20)) {
-        *out = sp.p; *got = sp.bytes;
-        sp.p = nullptr; sp.bytes = 0;
-        return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(g_spare_mutex);
+        SpareBuf &sp = g_spare[kind];
+        if (sp.p && sp.device == dev && sp.bytes >= bytes && sp.bytes <= 2 * bytes + (1u << 20)) {
+            *out = sp.p; *got = sp.bytes;
+            sp.p = nullptr; sp.bytes = 0;
+            return cudaSuccess;
+        }
     }
     *got = bytes;
     return cudaMalloc(out, bytes);
@@ -58,13 +66,20 @@ static void cached_free(int kind, void *p, size_t bytes)
     if (!p) return;
     int dev = 0;
     cudaGetDevice(&dev);
-    SpareBuf &sp = g_spare[kind];
-    if (sp.p == nullptr || sp.bytes < bytes) {
-        if (sp.p) cudaFree(sp.p);
-        sp.p = p; sp.bytes = bytes; sp.device = dev;
-    } else {
-        cudaFree(p);
+    // kernels of ANY stream may still read the buffer (lists are swept on the caller's streams)
+    cudaDeviceSynchronize();
+    void *drop = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_spare_mutex);
+        SpareBuf &sp = g_spare[kind];
+        if (sp.p == nullptr || sp.bytes < bytes) {
+            drop = sp.p;
+            sp.p = p; sp.bytes = bytes; sp.device = dev;
+        } else {
+            drop = p;
+        }
     }
+    if (drop) cudaFree(drop);
 }
 
 // longest list -> out[0] (the reference's overflow check compares it with max_neighbors)
@@ -672,7 +687,6 @@ static int g_nlist_one_pass = getenv("PNB_NLIST_ONE_PASS") ? atoi(getenv("PNB_NL
 extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
                                           int64_t n, int sort, pnb_nlist **out, void *stream)
 {
-    (void)y;
     if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
     *out = nullptr;
     if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
@@ -686,6 +700,7 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
         set_error("this neighborhood search does not support inactive points");
         return PNB_ERR_ARG;
     }
+    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
     cudaStream_t s = (cudaStream_t)stream;
     pnb_nlist *l = new pnb_nlist();
     memset(l, 0, sizeof(*l));
@@ -727,7 +742,15 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
         const int cap = g->nl_cap_hint;
         int32_t *rows = nullptr;
         size_t bytes_rows = 0;
-        NL_CUDA(cached_malloc(5, (void **)&rows, sizeof(int32_t) * (size_t)nx * cap, &bytes_rows));
+        // the rows are nx * cap ids (many gigabytes for large clouds): when that allocation fails
+        // the much smaller two-pass build below is still possible
+        if (cached_malloc(5, (void **)&rows, sizeof(int32_t) * (size_t)nx * cap, &bytes_rows) != cudaSuccess) {
+            cudaGetLastError();
+            rows = nullptr;
+            g->nl_cap_hint = 0;
+            goto two_pass;
+        }
+      {
         auto drop_rows = [&]() { cached_free(5, rows, bytes_rows); };
         st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListFillRowsCl{rows, l->counts, cap, l->d_err}, s);
         if (st == PNB_OK) st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
@@ -765,7 +788,9 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
         g->nl_cap_hint = 0;
         NL_CUDA(cudaMemsetAsync(l->d_err, 0, sizeof(int), s));
         NL_CUDA(cudaMemsetAsync(l->counts, 0, sizeof(uint32_t) * (size_t)(nx + 8), s));
+      }
     }
+two_pass:
     st = launch_sweep(g, fast, tiles, x, nx, nullptr, 0, ListCountCl{l->counts}, s);
     if (st != PNB_OK) return fail(st);
     st = exclusive_scan_u32_to_i64(g, l->counts, l->offsets, nx, s);
@@ -932,7 +957,6 @@ __global__ void k_nlist_pairs64(GridP64 g, int64_t nx, const int64_t *__restrict
 extern "C" pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t nx, const double *y,
                                           int64_t n, int sort, pnb_nlist **out, void *stream)
 {
-    (void)y;
     if (!out) { set_error("out is NULL"); return PNB_ERR_ARG; }
     *out = nullptr;
     if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
@@ -944,6 +968,7 @@ extern "C" pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t 
         set_error("this neighborhood search does not support inactive points");
         return PNB_ERR_ARG;
     }
+    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
     cudaStream_t s = (cudaStream_t)stream;
     pnb_nlist *l = new pnb_nlist();
     memset(l, 0, sizeof(*l));

@@ -70,8 +70,8 @@ static int64_t view_slots(const pnb_grid *g)
     return g->bucket_valid ? (int64_t)g->p.total_cells * g->bucket_K : g->n_built;
 }
 
-static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const int32_t *points,
-                                 int64_t *n_loop, cudaStream_t s)
+static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const void *y, int64_t n,
+                                 const int32_t *points, int64_t *n_loop, cudaStream_t s)
 {
     if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
     if (g->f64) { set_error("Float64 grid handle passed to a Float32 entry point"); return PNB_ERR_ARG; }
@@ -80,6 +80,11 @@ static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const i
         return PNB_ERR_STATE;
     }
     if (nx > 0 && !x) { set_error("x is NULL"); return PNB_ERR_ARG; }
+    // The reference reads neighbor_coords live at sweep time (src/nhs_grid.jl:543-548); this
+    // library sweeps the cell-ordered snapshot taken by the last initialize!/update!.  The two
+    // agree exactly when y IS the array of that build, so anything else is a call-order error
+    // (the reference requires update! after y changed, src/neighborhood_search.jl:161-164).
+    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
     *n_loop = points ? *n_loop : nx;
     // every sweep but the x === y tile sweep walks (or may walk) the CSR arrays: settle the
     // layout BEFORE the payload is gathered into it
@@ -115,9 +120,8 @@ extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64
                                               int64_t n_points, int index_base, int64_t *out,
                                               void *stream)
 {
-    (void)y; (void)n;
     int64_t n_loop = n_points;
-    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop, (cudaStream_t)stream);
+    pnb_status st = sweep_precheck(g, x, nx, y, n, points, &n_loop, (cudaStream_t)stream);
     if (st != PNB_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     // count_neighbors.jl:22  n_neighbors .= 0
@@ -133,9 +137,8 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
                                     int index_base, const float *mass, float G, float *dv,
                                     void *stream)
 {
-    (void)y; (void)n;
     int64_t n_loop = n_points;
-    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop, (cudaStream_t)stream);
+    pnb_status st = sweep_precheck(g, x, nx, y, n, points, &n_loop, (cudaStream_t)stream);
     if (st != PNB_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     const int nd = g->p.ndims;
@@ -172,9 +175,9 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
                                              const pnb_wcsph_params *params, float *dv,
                                              void *stream)
 {
-    (void)y; (void)n; (void)mass_x;
+    (void)mass_x;
     int64_t n_loop = n_points;
-    pnb_status st = sweep_precheck(g, x, nx, points, &n_loop, (cudaStream_t)stream);
+    pnb_status st = sweep_precheck(g, x, nx, y, n, points, &n_loop, (cudaStream_t)stream);
     if (st != PNB_OK) return st;
     if (!params) { set_error("params is NULL"); return PNB_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;

@@ -104,6 +104,8 @@ mutable struct B200GridNeighborhoodSearch{NDIMS, ELTYPE, PB, US} <: AbstractNeig
     cell_size       :: NTuple{NDIMS, ELTYPE}
     update_strategy :: US
     host            :: Any        # the GridNeighborhoodSearch it was adapted from (for copy_...)
+    y_ref           :: Any        # the coordinates of the last initialize!/update!: kept alive,
+                                  # the library checks that sweeps are called with this array
 end
 
 Base.ndims(::B200GridNeighborhoodSearch{NDIMS}) where {NDIMS} = NDIMS
@@ -126,7 +128,7 @@ function Adapt.adapt_structure(::B200Backend, nhs::GridNeighborhoodSearch{NDIMS}
                     (Cint, Cfloat, Int64, Ptr{Cfloat}, Ptr{Cfloat}, Ref{Ptr{Cvoid}}),
                     NDIMS, nhs.search_radius, cl.list_size, bmin, bmax, ref))
         out = B200GridNeighborhoodSearch{NDIMS, T, typeof(box), typeof(nhs.update_strategy)}(
-            ref[], nhs.search_radius, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs)
+            ref[], nhs.search_radius, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs, nothing)
         finalizer(x -> ccall((:pnb_grid_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), x.handle), out)
         return out
     end
@@ -144,7 +146,7 @@ function Adapt.adapt_structure(::B200Backend, nhs::GridNeighborhoodSearch{NDIMS}
                     NDIMS, nhs.search_radius, collect(Float64, cl.min_corner),
                     collect(Float64, cl.max_corner), bmin, bmax, ref))
         out = B200GridNeighborhoodSearch{NDIMS, Float64, typeof(box), typeof(nhs.update_strategy)}(
-            ref[], nhs.search_radius, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs)
+            ref[], nhs.search_radius, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs, nothing)
         finalizer(x -> ccall((:pnb_grid_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), x.handle), out)
         return out
     end
@@ -169,7 +171,7 @@ function Adapt.adapt_structure(::B200Backend, nhs::GridNeighborhoodSearch{NDIMS}
                     NDIMS, r, min_corner, max_corner, bmin, bmax, ref))
     end
     out = B200GridNeighborhoodSearch{NDIMS, T, typeof(box), typeof(nhs.update_strategy)}(
-        ref[], r, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs)
+        ref[], r, box, nhs.n_cells, nhs.cell_size, nhs.update_strategy, nhs, nothing)
     finalizer(x -> ccall((:pnb_grid_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), x.handle), out)
     return out
 end
@@ -198,6 +200,7 @@ function initialize!(nhs::B200GridNeighborhoodSearch{NDIMS, T}, x::B200Array{T, 
                     (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}),
                     nhs.handle, y.ptr, n, ivp, ni, 1, C_NULL))
     end
+    nhs.y_ref = y
     return nhs
 end
 

@@ -6,9 +6,9 @@ this package is the thin host-side mirror of the reference's Julia interface for
 from . import _build, _lib
 from .api import *  # noqa: F401,F403
 from .api import __all__ as _api_all
-from .point_cloud import point_cloud, perturb_, benchmark_cloud
+from .point_cloud import point_cloud, perturb_, benchmark_cloud, benchmark_cloud_torch
 
-__all__ = list(_api_all) + ["point_cloud", "perturb_", "benchmark_cloud", "build", "library_path"]
+__all__ = list(_api_all) + ["point_cloud", "perturb_", "benchmark_cloud", "benchmark_cloud_torch", "build", "library_path"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -37,15 +37,30 @@ def nvcc() -> str:
     return "nvcc"
 
 
-def _deps_mtime() -> float:
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+HASHFILE = LIB + ".srchash"
+
+
+def _source_hash() -> str:
+    """Content hash of everything the binary is built from (file mtimes do not survive the copy
+    to the GPU box, contents do)."""
+    import hashlib
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     files.append(os.path.join(REPO, "include", "pnb200.h"))
     files.append(os.path.abspath(__file__))
-    return max(os.path.getmtime(f) for f in files)
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def is_stale() -> bool:
-    return (not os.path.exists(LIB)) or os.path.getmtime(LIB) < _deps_mtime()
+    """True when there is no binary or it was built from other sources than the ones present."""
+    if not os.path.exists(LIB) or not os.path.exists(HASHFILE):
+        return True
+    with open(HASHFILE) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -54,6 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("PNB_DIAG") == "1":      # measurement-only kernel variants (tools/)
+        extra.append("-DPNB_DIAG")
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
@@ -72,7 +89,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with open(HASHFILE, "w") as fh:
+        fh.write(_source_hash() + "\n")
     return LIB
+
+
+def build_locked(force: bool = False, verbose: bool = False) -> str:
+    """build() serialised across processes (ranks of one node share the source tree): the first
+    process compiles, the others wait on the lock and then find a fresh binary."""
+    import fcntl
+    os.makedirs(OBJDIR, exist_ok=True)
+    with open(os.path.join(OBJDIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

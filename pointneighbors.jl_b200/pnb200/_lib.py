@@ -89,6 +89,7 @@ SIGNATURES = {
     "pnb_grid_destroy": (None, [_vp]),
     "pnb_grid_total_cells": (_i64, [_vp]),
     "pnb_grid_n_points": (_i64, [_vp]),
+    "pnb_grid_layout": (C.c_int, [_vp]),
     "pnb_grid_build_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pnb_point_cells_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_grid_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
@@ -147,14 +148,20 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path):
-        # fail loudly: no silent fallback
+    if _build.is_stale():
+        # sources newer than the binary (or no binary): rebuild under a file lock so that the
+        # ranks of a torchrun job do not compile into the same objects at the same time.  Fail
+        # loudly when that is impossible: there is no silent fallback.
         try:
-            _build.build()
+            _build.build_locked()
         except Exception as exc:  # pragma: no cover - depends on toolchain
-            raise ImportError(
-                f"libpnb200.so is missing and could not be built ({exc}); the CUDA library is "
-                "required, pnb200 has no CPU fallback") from exc
+            if not os.path.exists(path):
+                raise ImportError(
+                    f"libpnb200.so is missing and could not be built ({exc}); the CUDA library "
+                    "is required, pnb200 has no CPU fallback") from exc
+            import warnings
+            warnings.warn(f"libpnb200.so is older than its sources and could not be rebuilt "
+                          f"({exc}); running the stale binary")
     handle = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)

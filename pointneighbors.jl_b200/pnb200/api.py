@@ -398,6 +398,19 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
 
     # -- device handle -----------------------------------------------------------------------
     def _grid(self):
+        if self._handle is None and isinstance(self.cell_list, FullGridCellList) and \
+                float(self.search_radius) >= _EPS64 and \
+                float(self._cell_list_radius) != float(self.search_radius):
+            # The reference keeps the cell list's own grid (padded and sized with ITS radius,
+            # src/cell_lists/full_grid.jl:66-78) and only takes cell_size from the search; with
+            # two different radii its sweeps index cells that do not exist (BoundsError / domain
+            # error).  The device grid is derived from one radius, so refuse instead of silently
+            # working on another grid than `cell_list` describes.
+            raise ArgumentError(
+                f"the cell list was created with search_radius = {self._cell_list_radius}, the "
+                f"neighborhood search with {self.search_radius}: create the cell list with the "
+                "search's radius, or pass a template and use copy_neighborhood_search "
+                "(src/nhs_grid.jl:640-649)")
         if self._handle is None and self.eltype == np.float64:
             if self._window is not None:
                 raise ArgumentError("slab windows exist for Float32 searches only")
@@ -472,6 +485,11 @@ class GridNeighborhoodSearch(metaclass=_Parametric):
     # -- inspection (tests, exports) ------------------------------------------------------------
     def total_cells(self) -> int:
         return int(_lib.lib().pnb_grid_total_cells(self._grid()))
+
+    def layout(self) -> str:
+        """Layout the last initialize!/update! wrote: "csr" (two-pass counting sort) or "buckets"
+        (one-pass update!); inspection only, every consumer handles both."""
+        return {1: "buckets", 0: "csr"}.get(int(_lib.lib().pnb_grid_layout(self._grid())), "unbuilt")
 
     def export_csr(self):
         """(cell_start[C+1], cell_points[n]) int32 CUDA tensors, 0-based ids."""

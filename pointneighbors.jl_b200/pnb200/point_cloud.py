@@ -63,3 +63,41 @@ def benchmark_cloud(n_points_per_dimension, search_radius_factor=np.float32(3.0)
     min_corner = np.zeros(len(dims), dtype=np.float32)
     max_corner = (np.asarray(dims, dtype=np.float64) / max(dims)).astype(np.float32)
     return np.ascontiguousarray(coords), r, min_corner, max_corner
+
+
+def benchmark_cloud_torch(dims, domain_n=None, *, z0=0, seed=1, device="cuda", sort=True):
+    """`benchmark_cloud` for clouds too large to generate with numpy in reasonable time: the same
+    distribution (test/point_cloud.jl:4-58 + benchmarks/run_benchmarks.jl:81-89) generated with
+    torch on `device`.  Lattice indices 1..dims[0] x 1..dims[1] x (z0+1)..(z0+dims[2]), sigma =
+    0.05 applied twice, stably sorted by the cell tuple of the once-perturbed positions with
+    dimension 1 most significant, Float32, divided by (domain_n + 1).
+
+    Returns (coordinates float32 (N, 3) torch tensor on `device`, search_radius float32,
+    min_corner, max_corner).  Input generation only -- nothing here is on the measured path."""
+    import torch
+    nx, ny, nz = (int(v) for v in dims)
+    if domain_n is None:
+        domain_n = max(nx, ny, nz)
+    N = nx * ny * nz
+    gen = torch.Generator(device=device).manual_seed(seed)
+    k = torch.arange(N, device=device, dtype=torch.int64)
+    c = torch.stack([(k % nx).to(torch.float64) + 1.0,
+                     ((k // nx) % ny).to(torch.float64) + 1.0,
+                     (k // (nx * ny)).to(torch.float64) + 1.0 + z0], dim=1)
+    del k
+    c += 0.05 * torch.randn(N, 3, device=device, dtype=torch.float64, generator=gen)
+    if sort:
+        cell = torch.floor(c / 3.0).to(torch.int64)
+        key = (cell[:, 0] * (ny + 8) + cell[:, 1]) * (nz + z0 + 8) + cell[:, 2]
+        del cell
+    c += 0.05 * torch.randn(N, 3, device=device, dtype=torch.float64, generator=gen)
+    if sort:
+        perm = torch.sort(key, stable=True).indices
+        del key
+        c = c[perm]
+        del perm
+    out = (c.to(torch.float32) / np.float32(domain_n + 1)).contiguous()
+    r = np.float32(np.float32(3.0) / np.float32(domain_n + 1))
+    mn = np.zeros(3, np.float32)
+    mx = (np.asarray([nx, ny, nz + z0], np.float64) / domain_n).astype(np.float32)
+    return out, r, mn, mx

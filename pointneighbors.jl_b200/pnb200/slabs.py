@@ -272,7 +272,14 @@ class SlabExchange:
             cz = self.cell_layer(coords[:n])
             up_idx = torch.nonzero(cz >= self.z_hi).flatten() if has_up else empty
             down_idx = torch.nonzero(cz <= self.z_lo).flatten() if has_down else empty
-            leave_idx = torch.nonzero((cz < self.z_lo) | (cz > self.z_hi)).flatten()
+            # leaving through the global bottom / top: kept, the following update! raises the
+            # reference's domain error instead of losing the particle
+            leave = torch.zeros_like(cz, dtype=torch.bool)
+            if has_down:
+                leave |= cz < self.z_lo
+            if has_up:
+                leave |= cz > self.z_hi
+            leave_idx = torch.nonzero(leave).flatten()
         cz_up = self.cell_layer(coords[up_idx])
         cz_down = self.cell_layer(coords[down_idx])
 
