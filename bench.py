@@ -2,13 +2,15 @@
 """bench.py -- the headline benchmark of BASELINE.json on B200.
 
 metric   : accepted neighbour pair-evals/s of one 3D WCSPH step (update! + interact!), FP32
-workload : config 3 of BASELINE.json at N = 1: 254^3 = 16 387 064 particles on a perturbed cubic
+workload : N = 1: config 3 of BASELINE.json: 254^3 = 16 387 064 particles on a perturbed cubic
            lattice, search_radius = 3 * spacing, FullGridCellList, one step = update!(nhs, y, y;
            points_moving = (true, true)) on coordinates perturbed by sigma = 4e-4 * r
            (benchmarks/update.jl:28-49) + the WCSPH continuity + momentum interaction
-           (benchmarks/smoothed_particle_hydrodynamics.jl:45-102).  At N > 1 every rank owns a
-           slab of 254 lattice layers (weak scaling: 254 x 254 x 254N particles, ~config 5 at
-           N = 8) and exchanges one ghost cell layer per step over NCCL.
+           (benchmarks/smoothed_particle_hydrodynamics.jl:45-102).
+           N > 1: config 5: the 504^3 = 128 024 064 particle cloud (171^3 cells) slab-decomposed
+           along the last cell dimension over the N GPUs (STRONG scaling), one migrant + ghost
+           layer exchange per step over NCCL, overlapped with the sweep of the interior layers
+           (pnb200/slabs.py).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm
@@ -21,6 +23,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -36,6 +39,7 @@ METRIC = "neighbour pair-evals/s (3D WCSPH step incl. update!, FP32)"
 UNIT = "pair-evals/s"
 SM_COUNT = 148
 FP32_LANES = 128
+T = np.float32
 
 
 def measured_peaks():
@@ -47,43 +51,78 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", REPO, "rev-parse", "--short", "HEAD"], capture_output=True,
+                              text=True, timeout=5).stdout.strip() or None
+    except Exception:
+        return None
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at config 3, from the
+    ncu --set full capture recorded in profiles/r2_traffic.json (with the git hash and the summary
+    file it came from) -- never a constant in this file."""
+    path = os.path.join(REPO, "profiles", "r2_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(kernel)
+    except Exception:
+        return None, None
+    if not rec:
+        return None, None
+    return int(rec["dram_bytes"]), {k: rec.get(k) for k in ("git", "capture", "workload")}
+
+
+def workload_config(n):
+    """`config` of the JSON line: identical in the GPU arm and the reference arm."""
+    N = n ** 3
+    r = T(3.0) / T(n + 1)
+    return {"workload": f"WCSPH step 3D: {n}^3 = {N} particles (BASELINE config 3), "
+                        "update!(points_moving=(true,true)) on sigma=4e-4*r perturbed "
+                        "coordinates + continuity+momentum interact!",
+            "lattice": n, "particles": N, "search_radius": float(r),
+            "velocities": "zero (reference benchmark)",
+            "l2": "inputs (197 MB coordinates + 328 MB state) larger than the 126 MB L2"}
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic input (the distribution of test/point_cloud.jl + benchmarks/run_benchmarks.jl:81-89)
 # ------------------------------------------------------------------------------------------------
 def lattice_cloud_torch(dims, domain_n, z0, seed, device):
-    """Perturbed lattice slab generated on the device: lattice indices 1..dims[0] x 1..dims[1] x
-    (z0+1)..(z0+dims[2]), sigma = 0.05 applied twice, cell-sorted with dimension 1 most
-    significant, Float32, normalised by (domain_n + 1)."""
-    import torch
-    nx, ny, nz = dims
-    N = nx * ny * nz
-    gen = torch.Generator(device=device).manual_seed(seed)
-    k = torch.arange(N, device=device, dtype=torch.int64)
-    ix = (k % nx).to(torch.float64) + 1.0
-    iy = ((k // nx) % ny).to(torch.float64) + 1.0
-    iz = (k // (nx * ny)).to(torch.float64) + 1.0 + z0
-    c = torch.stack([ix, iy, iz], dim=1)
-    c += 0.05 * torch.randn(N, 3, device=device, dtype=torch.float64, generator=gen)
-    cell = torch.floor(c / 3.0).to(torch.int64)
-    c += 0.05 * torch.randn(N, 3, device=device, dtype=torch.float64, generator=gen)
-    key = (cell[:, 0] * (ny + 8) + cell[:, 1]) * (nz + z0 + 8) + cell[:, 2]
-    perm = torch.sort(key, stable=True).indices
-    c = c[perm]
-    out = (c.to(torch.float32) / np.float32(domain_n + 1)).contiguous()
-    return out
+    import pnb200
+    return pnb200.benchmark_cloud_torch(dims, domain_n, z0=z0, seed=seed, device=device)[0]
 
 
-def wcsph_state_torch(N, r, seed, device):
+def lattice_cloud_numpy(n, seed):
+    """The same distribution on the host (reference arm: no CUDA on its path), with one combined
+    sort key instead of a lexsort of three."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(n ** 3, dtype=np.int64)
+    c = np.empty((n ** 3, 3), np.float64)
+    c[:, 0] = k % n + 1
+    c[:, 1] = (k // n) % n + 1
+    c[:, 2] = k // (n * n) + 1
+    c += 0.05 * rng.standard_normal(c.shape)
+    cell = np.floor(c / 3.0).astype(np.int64)
+    key = (cell[:, 0] * (n + 8) + cell[:, 1]) * (n + 8) + cell[:, 2]
+    c += 0.05 * rng.standard_normal(c.shape)
+    c = c[np.argsort(key, kind="stable")]
+    return np.ascontiguousarray((c.astype(T) / T(n + 1)).astype(T))
+
+
+def wcsph_state_torch(N, r, seed, device, moving=False):
     """benchmarks/smoothed_particle_hydrodynamics.jl:54-95: rho = 1000 + rand, v = 0,
     m = 0.1 * spacing, Cole EOS (exponent 1, c = 10), h = r / 2."""
     import torch
     gen = torch.Generator(device=device).manual_seed(seed)
     rho = (1000.0 + torch.rand(N, device=device, generator=gen, dtype=torch.float32))
     v = torch.zeros((N, 4), device=device, dtype=torch.float32)
+    if moving:
+        v[:, :3] = 0.1 * torch.randn(N, 3, device=device, generator=gen, dtype=torch.float32)
     v[:, 3] = rho
-    mass = torch.full((N,), float(np.float32(0.1) * (np.float32(r) / np.float32(3))),
-                      device=device, dtype=torch.float32)
-    pressure = (np.float32(100.0) * (rho - np.float32(1000.0))).contiguous()
+    mass = torch.full((N,), float(T(0.1) * (T(r) / T(3))), device=device, dtype=torch.float32)
+    pressure = (T(100.0) * (rho - T(1000.0))).contiguous()
     return v.contiguous(), mass, pressure
 
 
@@ -139,17 +178,32 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU algorithm (C restatement in oracle/, the reference is pure Julia and
-# cannot run here) on all host threads, on a bounded sample of the same workload
+# cannot run here) on ALL host threads, always on the headline cloud (254^3); a step = update! of
+# the whole cloud + interact! over a bounded, contiguous sample of the points
 # ------------------------------------------------------------------------------------------------
-def cpu_step_factory(n_lattice, seed=1):
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_cpu_arm(n, steps, warmup, budget_s):
+    """update! (DVoV atomic push, the reference's ParallelUpdate, src/nhs_grid.jl:255-281) of the
+    WHOLE n^3 cloud + WCSPH interact! over the first m points (a slab of the cloud, which is
+    sorted with dimension 1 most significant), m chosen so that steps + warmup fit budget_s.
+    torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly to all host cores."""
     from oracle import pn_oracle
     import pnb200
-    T = np.float32
-    c, r, mn, mx = pnb200.benchmark_cloud((n_lattice,) * 3, seed=seed)
-    rng = np.random.default_rng(seed + 1)
+    threads = host_threads()
+    pn_oracle.set_threads(threads)
+    N = n ** 3
+    r = T(3.0) / T(n + 1)
+    mn, mx = np.zeros(3, T), np.ones(3, T)
+    c = lattice_cloud_numpy(n, 1)
+    rng = np.random.default_rng(2)
     c2 = (c + (T(4e-4) * r) * rng.standard_normal(c.shape).astype(T)).astype(T)
-    N = len(c)
-    rho = (T(1000) + rng.random(N).astype(T)).astype(T)
+    rho = (T(1000) + rng.random(N, dtype=np.float32)).astype(T)
     v = np.zeros((N, 4), T)
     v[:, 3] = rho
     mass = np.full(N, T(0.1) * (r / T(3)), T)
@@ -157,63 +211,76 @@ def cpu_step_factory(n_lattice, seed=1):
     h = T(r / T(2))
     params = np.array([h, 10.0, 0.02, 0.0, 0.01, 0.1, pnb200.wendland_c2_norm(3, h)], T)
     g = pn_oracle.Grid(3, r, mn, mx)
-    g.build(c)
-    pairs = [int(g.count_neighbors(c, c).sum())]
-    g.build(c2)
-    pairs.append(int(g.count_neighbors(c2, c2).sum()))
     coords = [c, c2]
+    # calibration: one update! and the interaction of 1 % of the points
+    t0 = time.perf_counter()
+    g.build_dvov(c)
+    t_upd = time.perf_counter() - t0
+    probe = np.arange(0, N, 100, dtype=np.int64)
+    t0 = time.perf_counter()
+    g.wcsph(c, c, v, v, mass, mass, pressure, pressure, params, points=probe, use_dvov=True, parallel=True)
+    t_pp = (time.perf_counter() - t0) / len(probe)
+    per_step = budget_s / max(steps + warmup, 1)
+    frac = min(1.0, max(0.02, (per_step - t_upd) / (t_pp * N)))
+    m = N if frac >= 0.999 else int(frac * N)
+    sample = None if m == N else np.arange(m, dtype=np.int64)
+    pairs = []
+    for y in coords:
+        g.build_dvov(y)
+        cn = g.count_neighbors(y, y, points=sample, use_dvov=True)
+        pairs.append(int(cn.sum() if sample is None else cn[:m].sum()))
+    t_u, t_i = [], []
 
-    def step(s):
+    def step(s, timed):
         y = coords[(s + 1) % 2]
+        a = time.perf_counter()
         g.build_dvov(y)                                   # update! (ParallelUpdate, DVoV layout)
-        g.wcsph(y, y, v, v, mass, mass, pressure, pressure, params, use_dvov=True, parallel=True)
+        b = time.perf_counter()
+        g.wcsph(y, y, v, v, mass, mass, pressure, pressure, params, points=sample, use_dvov=True,
+                parallel=True)
+        e = time.perf_counter()
+        if timed:
+            t_u.append(b - a)
+            t_i.append(e - b)
         return pairs[(s + 1) % 2]
 
-    return step, N, pn_oracle.max_threads()
-
-
-def run_cpu_arm(steps, warmup, budget_s=120.0):
-    """Times `steps` steps of the CPU restatement on a sample sized to fit the budget."""
-    step64, N64, threads = cpu_step_factory(64)
-    t0 = time.perf_counter()
-    step64(0)
-    t64 = time.perf_counter() - t0
-    per_point = t64 / N64
-    n_s = 64
-    for cand in (96, 128, 160, 200, 254):
-        if per_point * cand ** 3 * (steps + warmup) <= budget_s:
-            n_s = cand
-    step, N, threads = (step64, N64, threads) if n_s == 64 else cpu_step_factory(n_s)
     for s in range(warmup):
-        step(s)
-    t0 = time.perf_counter()
-    pairs = 0
+        step(s, False)
+    total_pairs = 0
     for s in range(steps):
-        pairs += step(s)
-    dt = time.perf_counter() - t0
-    return {"value": pairs / dt, "ms_per_step": 1e3 * dt / steps, "cores": threads,
-            "sample": f"{n_s}^3 = {N} particles of the same perturbed lattice (density, r = 3 spacings "
-                      f"identical), {steps} steps of update! (DVoV atomic push) + WCSPH interact!",
-            "n_sample": N}
+        total_pairs += step(s, True)
+    f = m / N
+    # the sample's share of the (whole-cloud) update! is charged, its interact! in full
+    dt = float(np.sum(t_i) + f * np.sum(t_u))
+    what = (f"update! (DVoV atomic push) of all {N} particles + WCSPH interact! over "
+            + ("all of them" if m == N else f"the first {m} ({100 * f:.1f} %, a slab of the cloud; its "
+               f"share of the update! time is charged)"))
+    return {"value": total_pairs / dt, "ms_per_step": 1e3 * dt / steps / f, "cores": threads,
+            "sample": what, "n_sample": m, "update_ms": 1e3 * float(np.mean(t_u)),
+            "interact_ms_sample": 1e3 * float(np.mean(t_i))}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    res = run_cpu_arm(args.steps, max(args.warmup, 1), budget_s=150.0)
+    n = args.lattice
+    res = run_cpu_arm(n, args.steps, min(args.warmup, 1), budget_s=170.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "WCSPH step 3D (config 3), bounded CPU sample: " + res["sample"]},
+        "config": workload_config(n),
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
-                         "sample": res["sample"]},
+                         "sample": res["sample"], "update_ms": res["update_ms"],
+                         "interact_ms_sample": res["interact_ms_sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "note": "reference is pure Julia (no julia binary in this image): this is the C/OpenMP "
-                "restatement of its CPU path (oracle/), reference data structures, all host threads",
+                "restatement of its CPU path (oracle/), reference data structures, all host threads; "
+                "ms_per_step is extrapolated to the whole cloud from the sample",
     }
     print(json.dumps(line))
     return 0
@@ -222,6 +289,175 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def timed_events(fn, reps, flush_buf=None, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    times = []
+    for _ in range(reps):
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return float(np.min(times)), float(np.median(times))
+
+
+def sub_configs(dev, hbm_peak, fp32_peak):
+    """BASELINE configs 1, 2 and 4 at full size: device time (CUDA events around the API call, L2
+    flushed between repetitions where the working set fits it), roofline figures, and a check of
+    the result against the CPU oracle (all points for config 1, samples for 2 and 4)."""
+    import torch
+    import pnb200 as pn
+    from oracle import pn_oracle
+    pn_oracle.set_threads(host_threads())
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    mn, mx = np.zeros(3, T), np.ones(3, T)
+
+    def grid(n, A, box=None):
+        N = A.shape[0]
+        r = T(3.0) / T(n + 1)
+        if box is None:
+            cl = pn.FullGridCellList(min_corner=mn, max_corner=mx, search_radius=r)
+            nhs = pn.GridNeighborhoodSearch[3](search_radius=r, n_points=N, cell_list=cl)
+        else:
+            cl = pn.FullGridCellList(min_corner=box[0], max_corner=box[1], search_radius=r)
+            nhs = pn.GridNeighborhoodSearch[3](search_radius=r, n_points=N, cell_list=cl,
+                                               periodic_box=pn.PeriodicBox(min_corner=box[0], max_corner=box[1]))
+        pn.initialize_(nhs, A, A)
+        return nhs, r
+
+    # ---- config 1: count_neighbors, 64^3 -------------------------------------------------------
+    n = 64
+    A = lattice_cloud_torch((n, n, n), n, 0, 11, dev)
+    nhs, r = grid(n, A)
+    N, C = A.shape[0], nhs.total_cells()
+    cnt = torch.zeros(N, dtype=torch.int64, device=dev)
+    f = pn.CountNeighbors(cnt)
+    pn.update_(nhs, A, A)
+    t_min, t_med = timed_events(lambda: pn.foreach_point_neighbor(f, A, A, nhs), 20, flush)
+    u_min, _ = timed_events(lambda: pn.update_(nhs, A, A, blocking=False), 20, flush)
+    c = A.cpu().numpy()
+    og = pn_oracle.Grid(3, r, mn, mx)
+    og.build(c)
+    ref = og.count_neighbors(c, c)
+    P = int(ref.sum())
+    K = og.candidate_tests(c)
+    ok = bool((cnt.cpu().numpy() == ref).all())
+    by = 24 * N + 4 * (C + 1)
+    out["config1_count_64"] = {
+        "workload": "count_neighbors, 64^3 = 262144 points (BASELINE config 1)", "pairs": P,
+        "sweep_ms_min": t_min, "sweep_ms_median": t_med, "value": P / (t_min * 1e-3), "unit": UNIT,
+        "update_ms_min": u_min, "l2": "flushed between repetitions (256 MB write)",
+        "roofline": {"bound": "hbm", "achieved": by / (t_min * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": by / (t_min * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": by},
+        "fp32_pipe_frac": 8.0 * K / (t_min * 1e-3) / 1e12 / fp32_peak,
+        "oracle_checked": {"what": "neighbour counts of all points", "equal": ok}}
+    del nhs, A, cnt
+
+    # ---- config 2: n-body, 101^3 ---------------------------------------------------------------
+    n = 101
+    A = lattice_cloud_torch((n, n, n), n, 0, 12, dev)
+    nhs, r = grid(n, A)
+    N, C = A.shape[0], nhs.total_cells()
+    gen = torch.Generator(device=dev).manual_seed(5)
+    m_nb = (1e10 * (torch.rand(N, device=dev, generator=gen) + 1)).to(torch.float32)
+    dv3 = torch.zeros((N, 3), device=dev)
+    G = T(6.6743e-11)
+    f = pn.NBodyGravity(dv3, m_nb, G)
+    pn.update_(nhs, A, A)
+    t_min, t_med = timed_events(lambda: pn.foreach_point_neighbor(f, A, A, nhs), 20, flush)
+    c = A.cpu().numpy()
+    og = pn_oracle.Grid(3, r, mn, mx)
+    og.build(c)
+    pts = np.arange(0, N, 37, dtype=np.int64)
+    _, r64, rabs = og.nbody(c, c, m_nb.cpu().numpy(), G, points=pts, wide=True)
+    got = dv3[torch.as_tensor(pts, device=dev)].cpu().numpy()
+    ok = bool(np.all(np.abs(got - r64[pts]) <= 1e-5 * rabs[pts] + 1e-30))
+    cntd = torch.zeros(N, dtype=torch.int64, device=dev)
+    pn.foreach_point_neighbor(pn.CountNeighbors(cntd), A, A, nhs)
+    P = int(cntd.sum())
+    ok = ok and bool((cntd[torch.as_tensor(pts, device=dev)].cpu().numpy() ==
+                      og.count_neighbors(c, c, points=pts)[pts]).all())
+    K = og.candidate_tests(c)
+    by = 32 * N + 4 * (C + 1)
+    out["config2_nbody_101"] = {
+        "workload": "n-body gravity, 101^3 = 1030301 points (BASELINE config 2)", "pairs": P,
+        "sweep_ms_min": t_min, "sweep_ms_median": t_med, "value": P / (t_min * 1e-3), "unit": UNIT,
+        "l2": "flushed between repetitions (256 MB write)",
+        "roofline": {"bound": "hbm", "achieved": by / (t_min * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": by / (t_min * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": by},
+        "fp32_pipe_frac": (8.0 * K + 14.0 * P) / (t_min * 1e-3) / 1e12 / fp32_peak,
+        "oracle_checked": {"what": f"dv of {len(pts)} sampled points within 1e-5 * sum|term|, their counts exact",
+                           "equal": ok}}
+    del nhs, A, dv3, m_nb, cntd
+
+    # ---- config 4: neighbour lists + TLSPH deformation gradient, 200^3 periodic ---------------
+    n = 200
+    s_ = T(1.0) / T(n + 1)
+    A = lattice_cloud_torch((n, n, n), n, 0, 13, dev)
+    bmn, bmx = np.full(3, s_ / T(2), T), np.full(3, (T(n) + T(0.5)) * s_, T)
+    nhs, r = grid(n, A, box=(bmn, bmx))
+    N = A.shape[0]
+    pre = pn.PrecomputedNeighborhoodSearch[3](search_radius=r, n_points=N, periodic_box=nhs.periodic_box,
+                                              update_neighborhood_search=nhs, max_neighbors=160,
+                                              transpose_backend=True)
+    pn.initialize_(pre, A, A)
+    b_min, b_med = timed_events(lambda: pn.update_(pre, A, A), 4, None, warm=1)
+    off, ids = pre.export_csr()
+    P = int(off[-1])
+    gen = torch.Generator(device=dev).manual_seed(6)
+    xcur = (A + (T(0.01) * r) * torch.sin(2 * np.pi * A)).contiguous()
+    m0 = torch.full((N,), 0.1, device=dev)
+    rho0 = torch.full((N,), 1000.0, device=dev)
+    Lm = (torch.eye(3, device=dev).reshape(1, 9) + 0.05 * torch.randn(N, 9, device=dev, generator=gen)).contiguous()
+    F = torch.zeros((N, 9), device=dev)
+    h = T(r / T(2))
+    fd = pn.TLSPHDeformationGradient(F, xcur, m0, rho0, Lm, smoothing_length=h, ndims_=3)
+    s_min, s_med = timed_events(lambda: pn.foreach_point_neighbor(fd, A, A, pre), 10, None)
+    c = A.cpu().numpy()
+    og = pn_oracle.Grid(3, r, bmn, bmx, periodic_box=(bmn, bmx))
+    og.build(c)
+    pts = np.arange(0, N, 2003, dtype=np.int64)
+    ro, ri = og.neighbor_lists(c[pts], c, sort=True)
+    sel = torch.as_tensor(pts, device=dev)
+    lens = off[sel + 1] - off[sel]
+    ok = bool((lens.cpu().numpy() == np.diff(ro)).all())
+    if ok:
+        rep = torch.repeat_interleave(torch.arange(len(pts), device=dev), lens)
+        pos = torch.arange(int(lens.sum()), device=dev) - torch.as_tensor(ro[:-1], device=dev)[rep]
+        ok = bool((ids[off[sel][rep] + pos].cpu().numpy() == ri).all())
+    lens_full = np.zeros(N, np.int64)
+    lens_full[pts] = np.diff(ro)
+    off_sparse = np.concatenate([[0], np.cumsum(lens_full)])
+    _, r64, rabs = pn_oracle.tlsph_deformation_grad(c, xcur.cpu().numpy(), off_sparse, ri, m0.cpu().numpy(),
+                                                    rho0.cpu().numpy(), Lm.cpu().numpy(), h, fd.kernel_norm,
+                                                    r, periodic_box=(bmn, bmx), wide=True)
+    ok = ok and bool(np.all(np.abs(F[sel].cpu().numpy() - r64[pts]) <= 1e-5 * rabs[pts] + 1e-30))
+    by_build = 12 * N + 4 * N + 4 * (nhs.total_cells() + 1) + 4 * (N + 1) + 4 * P
+    by_sweep = 108 * N + 4 * P + 4
+    out["config4_nlist_tlsph_200_periodic"] = {
+        "workload": "PrecomputedNeighborhoodSearch build (sorted lists) + TLSPH deformation gradient, "
+                    "200^3 = 8000000 points, PeriodicBox (BASELINE config 4)", "pairs": P,
+        "list_build_ms_min": b_min, "list_build_ms_median": b_med,
+        "tlsph_sweep_ms_min": s_min, "tlsph_sweep_ms_median": s_med,
+        "value": P / ((b_min + s_min) * 1e-3), "unit": UNIT,
+        "l2": "working set (3.5 GB of lists) far larger than the L2",
+        "roofline_build": {"bound": "hbm", "achieved": by_build / (b_min * 1e-3) / 1e9, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": by_build / (b_min * 1e-3) / 1e9 / hbm_peak,
+                           "algorithmic_bytes": by_build},
+        "roofline": {"bound": "hbm", "kernel": "k_tlsph_defgrad", "achieved": by_sweep / (s_min * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": by_sweep / (s_min * 1e-3) / 1e9 / hbm_peak,
+                     "algorithmic_bytes": by_sweep},
+        "oracle_checked": {"what": f"sorted lists and F of {len(pts)} sampled points (lists exact, F within "
+                                   "1e-5 * sum|term|)", "equal": ok}}
+    return out
+
+
 def gpu_arm(args):
     import torch
     import pnb200 as pn
@@ -234,12 +470,12 @@ def gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device: pnb200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1 or args.total_layers > 0:
+    if world > 1 or args.slabs:
         import torch.distributed as dist
         if world > 1:
             dist.init_process_group("nccl", device_id=dev)
         else:
-            # one rank of the slab code path (strong-scaling base line of --total-layers)
+            # one rank of the slab code path (strong-scaling base line: the 504^3 cloud on 1 GPU)
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29533")
             dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
@@ -247,7 +483,6 @@ def gpu_arm(args):
         return slabs.bench_multi_gpu(args, rank, world, dev, METRIC, UNIT)
 
     n = args.lattice
-    T = np.float32
     N = n ** 3
     r = T(3.0) / T(n + 1)
     mn, mx = np.zeros(3, T), np.ones(3, T)
@@ -264,11 +499,6 @@ def gpu_arm(args):
                                sound_speed=T(10.0), alpha=T(0.02), beta=T(0.0), delta=T(0.1))
     coords = [A, B]
 
-    def step(s):
-        y = coords[(s + 1) % 2]
-        pn.update_(nhs, y, y, points_moving=(True, True))
-        pn.foreach_point_neighbor(closure, y, y, nhs)
-
     # accepted pairs P and candidate tests K_ref of both clouds (device side, untimed)
     cnt = torch.zeros(N, dtype=torch.int64, device=dev)
     pairs, kref = [], []
@@ -283,6 +513,28 @@ def gpu_arm(args):
                                                                        dtype=torch.float64), padding=1)
         kref.append(int((counts * nb[0, 0]).sum().item()))
     C_cells = nhs.total_cells()
+    # the GPU's pair count (the numerator of `value`) against the CPU oracle on a sampled slab
+    oracle_check = None
+    if not args.no_cpu_baseline:
+        from oracle import pn_oracle
+        pn_oracle.set_threads(host_threads())
+        cB = B.cpu().numpy()
+        og = pn_oracle.Grid(3, r, mn, mx)
+        og.build(cB)
+        m = 250_000
+        pts = np.concatenate([np.arange(m), np.arange(N // 2, N // 2 + m), np.arange(N - m, N)]).astype(np.int64)
+        ref = og.count_neighbors(cB, cB, points=pts)[pts]
+        got = cnt[torch.as_tensor(pts, device=dev)].cpu().numpy()     # cnt holds the counts of B
+        oracle_check = {"what": f"neighbour counts of {len(pts)} points (three slabs of the update! target "
+                                "cloud) against the CPU oracle", "equal": bool((ref == got).all()),
+                        "pairs_in_sample": int(ref.sum())}
+        assert oracle_check["equal"], "GPU pair counts differ from the oracle"
+        del og, cB
+
+    def step(s):
+        y = coords[(s + 1) % 2]
+        pn.update_(nhs, y, y, points_moving=(True, True), blocking=False)
+        pn.foreach_point_neighbor(closure, y, y, nhs)
 
     for s in range(args.warmup):
         step(s)
@@ -301,7 +553,7 @@ def gpu_arm(args):
     for s in range(args.steps):
         y = coords[(s + 1) % 2]
         upd_ev[s][0].record()
-        pn.update_(nhs, y, y, points_moving=(True, True))
+        pn.update_(nhs, y, y, points_moving=(True, True), blocking=False)
         upd_ev[s][1].record()
         pn.foreach_point_neighbor(closure, y, y, nhs)
         total_pairs += pairs[(s + 1) % 2]
@@ -313,87 +565,70 @@ def gpu_arm(args):
     prof = _lib.profile(enable=False)
     update_ms = float(np.mean([a.elapsed_time(b) for a, b in upd_ev]))
     value = total_pairs / (ms_total * 1e-3)
+    # the blocking form of update! (the reference's semantics) for comparison
+    ub_min, ub_med = timed_events(lambda: pn.update_(nhs, A, A, points_moving=(True, True)), 10)
 
-    # ---- e2e: same step through the public API with HOST (pinned) buffers ---------------------
-    # Every step copies its inputs (coordinates, state, pressure) from pinned host memory and
-    # copies its result (dv) back.  Two measurements:
-    #   serial    : H2D -> update! -> interact! -> D2H on one stream (latency of one step)
-    #   pipelined : three streams, double-buffered device arrays: the H2D of step s+1 and the
-    #               D2H of step s-1 overlap the kernels of step s (throughput; this is `value`)
-    hA, hB = A.cpu().pin_memory(), B.cpu().pin_memory()
-    hv, hp = v.cpu().pin_memory(), pressure.cpu().pin_memory()
-    hdv = [torch.empty((N, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
-    dy = [torch.empty_like(A) for _ in range(2)]
-    dvv = [v, torch.empty_like(v)]
-    dpp = [pressure, torch.empty_like(pressure)]
-    dvo = [dv, torch.empty_like(dv)]
-    cls = [closure, pn.WCSPHInteract(dvo[1], dvv[1], dvv[1], mass, mass, dpp[1], dpp[1],
-                                     smoothing_length=h, sound_speed=T(10.0), alpha=T(0.02),
-                                     beta=T(0.0), delta=T(0.1))]
-    hcoords = [hA, hB]
-
-    def e2e_serial_step(s):
-        dy[0].copy_(hcoords[(s + 1) % 2], non_blocking=True)
-        dvv[0].copy_(hv, non_blocking=True)
-        dpp[0].copy_(hp, non_blocking=True)
-        pn.update_(nhs, dy[0], dy[0], points_moving=(True, True))
-        pn.foreach_point_neighbor(cls[0], dy[0], dy[0], nhs)
-        hdv[0].copy_(dvo[0], non_blocking=True)
-
-    e2e_steps = max(4, min(args.steps, 10))
+    # ---- the same step with non-zero velocities (viscosity branch active) ----------------------
+    vm, _, _ = wcsph_state_torch(N, r, 3, dev, moving=True)
+    closure_m = pn.WCSPHInteract(dv, vm, vm, mass, mass, pressure, pressure, smoothing_length=h,
+                                 sound_speed=T(10.0), alpha=T(0.02), beta=T(0.0), delta=T(0.1))
     for s in range(2):
-        e2e_serial_step(s)
+        pn.update_(nhs, coords[s % 2], coords[s % 2], blocking=False)
+        pn.foreach_point_neighbor(closure_m, coords[s % 2], coords[s % 2], nhs)
+    m0_, m1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m_steps = max(2, min(args.steps, 6))
+    m0_.record()
+    for s in range(m_steps):
+        y = coords[(s + 1) % 2]
+        pn.update_(nhs, y, y, blocking=False)
+        pn.foreach_point_neighbor(closure_m, y, y, nhs)
+    m1_.record()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(e2e_steps):
-        e2e_serial_step(s)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_serial_ms = e0.elapsed_time(e1) / e2e_steps
+    moving_ms = m0_.elapsed_time(m1_) / m_steps
+    del vm, closure_m
 
-    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_cmp = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
+    # ---- e2e: the same step through the library's host-buffer entry point -----------------------
+    # pnb200.HostStepper (pnb_hoststep_*, include/pnb200.h): every step copies its coordinates,
+    # state and pressure from pinned host memory and its dv back; three streams and double
+    # buffers inside the library overlap the copies of neighbouring steps with the kernels.
+    hA, hB = A.cpu().pin_memory(), B.cpu().pin_memory()
+    hv, hp, hm = v.cpu().pin_memory(), pressure.cpu().pin_memory(), mass.cpu().pin_memory()
+    hdv = [torch.empty((N, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    hcoords = [hA, hB]
+    stepper = pn.HostStepper(nhs, N)
+    e2e_steps = max(4, min(args.steps, 10))
 
-    def issue_h2d(s):
-        bb = s % 2
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_cmp[bb])           # the kernels of step s-2 are done with these buffers
-            dy[bb].copy_(hcoords[(s + 1) % 2], non_blocking=True)
-            dvv[bb].copy_(hv, non_blocking=True)
-            dpp[bb].copy_(hp, non_blocking=True)
-            ev_in[bb].record(s_in)
+    def run_e2e(k):
+        done = 0
+        for s in range(k):
+            stepper.submit(hcoords[(s + 1) % 2], hv, hp, hdv[s % 2], closure, mass_host=hm if s == 0 else None)
+            done += pairs[(s + 1) % 2]
+        stepper.wait()
+        return done
 
-    def run_pipelined(n_steps):
-        pairs_done = 0
-        issue_h2d(0)
-        for s in range(n_steps):
-            bb = s % 2
-            if s + 1 < n_steps:
-                issue_h2d(s + 1)
-            with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(ev_in[bb])
-                s_cmp.wait_event(ev_out[bb])      # dv buffer of step s-2 has reached the host
-                pn.update_(nhs, dy[bb], dy[bb], points_moving=(True, True))
-                pn.foreach_point_neighbor(cls[bb], dy[bb], dy[bb], nhs)
-                ev_cmp[bb].record(s_cmp)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_cmp[bb])
-                hdv[bb].copy_(dvo[bb], non_blocking=True)
-                ev_out[bb].record(s_out)
-            pairs_done += pairs[(s + 1) % 2]
-        return pairs_done
-
-    torch.cuda.synchronize()
-    run_pipelined(2)
+    run_e2e(3)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e0.record()
-    e2e_pairs = run_pipelined(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0)      # wall clock across the three streams
+    e2e_pairs = run_e2e(e2e_steps)
+    e2e_ms = 1e3 * (time.perf_counter() - t0)      # wall clock around submit ... wait
+    # the device result of the last step must be what the resident path computes
+    e2e_same = None
+    try:
+        yl = coords[e2e_steps % 2]
+        pn.update_(nhs, yl, yl)
+        pn.foreach_point_neighbor(closure, yl, yl, nhs)
+        ref_dv = dv.cpu()
+        got_dv = hdv[(e2e_steps - 1) % 2]
+        e2e_same = bool(torch.allclose(ref_dv, got_dv, rtol=1e-4, atol=1e-6))
+    except Exception:
+        pass
+    # one step alone (latency): submit + wait
+    t0 = time.perf_counter()
+    for s in range(3):
+        stepper.submit(hcoords[s % 2], hv, hp, hdv[0], closure)
+        stepper.wait()
+    e2e_serial_ms = 1e3 * (time.perf_counter() - t0) / 3
+    del stepper
     h2d = int(hA.numel() * 4 + hv.numel() * 4 + hp.numel() * 4)
     d2h = int(hdv[0].numel() * 4)
 
@@ -403,50 +638,53 @@ def gpu_arm(args):
     sweep_avg = sweep_ms / max(sweep_n, 1)
     bytes_sweep = 56 * N + 4 * (C_cells + 1)          # WCSPH interact
     ach = bytes_sweep / (sweep_avg * 1e-3) / 1e9
-    # update! = one-pass bucket build (k_bucket_scatter) after the first build; the two-pass CSR
-    # build (hist + scan + scatter) when a cell overflowed its bucket or PNB_BUILD_LAYOUT=0
-    build_names = [k for k in ("k_bucket_scatter", "k_cell_hist", "k_scan_lookback", "k_scatter_points")
+    build_names = [k for k in ("k_bucket_scatter", "k_cell_hist", "k_scatter_points")
                    if prof.get(k, (0.0, 0))[1]]
     build_ms = sum(prof[k][0] for k in build_names) / args.steps
     bytes_update = 28 * N + 4 * (C_cells + 1)          # 16N + 4(C+1) + 12N (cell-ordered coordinates)
     ach_u = bytes_update / (build_ms * 1e-3) / 1e9
+    ach_call = bytes_update / (update_ms * 1e-3) / 1e9
     P_avg = float(np.mean(pairs))
     K_avg = float(np.mean(kref))
     flops = 8.0 * K_avg + 70.0 * P_avg                 # non-FMA FP32 operations
     fp32_peak = SM_COUNT * FP32_LANES * sm_max_mhz * 1e6 / 1e12
-    # the whole interaction's flops over ALL its sweep kernels: the tile kernel plus the overflow /
-    # surplus-point kernels that finish the same sweep (k_sweep_overflow phase)
-    ovf_ms, ovf_n = prof.get("k_sweep_overflow", (0.0, 0))
-    sweep_all = sweep_avg + (ovf_ms / max(sweep_n, 1))
+    ovf_ms, _ = prof.get("k_sweep_overflow", (0.0, 0))
+    prep_ms, _ = prof.get("k_flat_tiles", (0.0, 0))
+    sweep_all = sweep_avg + (ovf_ms + prep_ms) / max(sweep_n, 1)
     fp32_ach = flops / (sweep_all * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic("k_sweep_flat<3,false,WcsphClT<false>,false>") if n == 254 else (None, None)
+    traffic_u, traffic_u_src = ncu_traffic("k_bucket_scatter") if n == 254 else (None, None)
 
+    cfg = workload_config(n)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"WCSPH step 3D: {n}^3 = {N} particles (BASELINE config 3), "
-                               "update!(points_moving=(true,true)) on sigma=4e-4*r perturbed "
-                               "coordinates + continuity+momentum interact!",
-                   "search_radius": float(r), "cells": C_cells, "pairs_per_step": P_avg,
-                   "candidate_tests_per_step": K_avg, "velocities": "zero (reference benchmark)",
-                   "l2": "inputs (197 MB coordinates + 328 MB state) larger than the 126 MB L2"},
+        "config": cfg,
+        "workload_stats": {"cells": C_cells, "pairs_per_step": P_avg, "candidate_tests_per_step": K_avg,
+                           "pairs_oracle_check": oracle_check, "git": git_head()},
         "update_ms": update_ms,
+        "update_ms_blocking_call": ub_med,
         "interact_ms": (ms_total / args.steps) - update_ms,
+        "moving": {"what": "same step with velocities ~ N(0, 0.1^2): the viscosity branch runs for "
+                           "approaching pairs (two more MUFU per pair)",
+                   "ms_per_step": moving_ms, "value": P_avg / (moving_ms * 1e-3)},
         "points_per_s": N / (ms_total / args.steps * 1e-3),
         "gpu_launches": launches,
         "clocks": clocks,
         "e2e": {"value": e2e_pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                "mode": "pipelined: 3 streams, double-buffered device arrays, every step copies "
-                        "its inputs from pinned host memory and its dv back (wall clock)",
+                "api": "pnb200.HostStepper.submit/wait = pnb_hoststep_wcsph_submit / pnb_hoststep_wait "
+                       "(include/pnb200.h): host pointers in, host pointer out",
+                "mode": "pipelined inside the library: 3 streams, double-buffered device arrays, every "
+                        "step copies its inputs from pinned host memory and its dv back (wall clock "
+                        "around the submits and the final wait)",
                 "serial_ms_per_step": e2e_serial_ms,
-                "serial_value": float(np.mean(pairs)) / (e2e_serial_ms * 1e-3)},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_tiles<3,false,WcsphClT<false>,4,true>", "achieved": ach,
+                "serial_value": P_avg / (e2e_serial_ms * 1e-3),
+                "matches_resident_path": e2e_same},
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_flat<3,false,WcsphClT<false>,false>", "achieved": ach,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact
-                     # workload, from the ncu --set full capture summarised in
-                     # profiles/r1_wcsph_sweep_v6_ncu_summary.txt (900.8 MB + 255.3 MB)
-                     "traffic": 1156059136 if n == 254 else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "launch_ms": sweep_avg,
                      "algorithmic_bytes": bytes_sweep,
                      "note": "the fused interaction is FP32-issue bound (~100 flop/B), not HBM bound "
@@ -454,22 +692,29 @@ def gpu_arm(args):
         "fp32_pipe": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak,
                       "frac": fp32_ach / fp32_peak,
                       "sweep_ms": sweep_all,
-                      "model": "8*K_ref + 70*P non-FMA operations over the tile kernel + the overflow / "
-                               "surplus-point kernels of the same sweep; peak = 148 SM x 128 lanes x max clock"},
+                      "model": "8*K_ref + 70*P non-FMA operations over the tile kernel + its tile-table "
+                               "and overflow kernels; peak = 148 SM x 128 lanes x max clock"},
         "roofline_update": {"bound": "hbm", "kernels": build_names, "achieved": ach_u,
                             "peak": hbm_peak, "unit": "GB/s", "frac": ach_u / hbm_peak,
-                            # one-pass bucket build: profiles/r1_update_v4_bucket_ncu_summary.txt
-                            # (209.5 MB read + 223.6 MB written per launch at this workload)
-                            "traffic": 433141504 if (n == 254 and "k_bucket_scatter" in build_names) else None,
+                            "achieved_call": ach_call, "frac_call": ach_call / hbm_peak,
+                            "traffic": traffic_u, "traffic_source": traffic_u_src,
                             "device_ms": build_ms, "algorithmic_bytes": bytes_update,
                             "per_kernel_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in build_names},
                             "call_ms": update_ms,
+                            "call": "update_(nhs, y, y, blocking=False): stream-ordered, CUDA events around "
+                                    "the call; the error word is read by the blocking sweep that follows",
                             "layout": "buckets (one pass)" if "k_bucket_scatter" in build_names
                                       else "CSR (two passes)"},
         "kernel_ms": {k: (v_[0] / v_[1] if v_[1] else 0.0) for k, v_ in prof.items()},
     }
+    del hA, hB, hv, hp, hdv
+    if not args.no_sub_configs:
+        try:
+            line["configs"] = sub_configs(dev, hbm_peak, fp32_peak)
+        except Exception as exc:      # the headline must survive a failing side measurement
+            line["configs"] = {"error": repr(exc)}
     if not args.no_cpu_baseline:
-        cb = run_cpu_arm(3, 1, budget_s=25.0)
+        cb = run_cpu_arm(n, 2, 0, budget_s=25.0)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"],
                                 "kind": "port", "sample": cb["sample"]}
     print(json.dumps(line))
@@ -482,12 +727,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lattice", type=int, default=254, help="lattice points per dimension (per GPU)")
+    ap.add_argument("--lattice", type=int, default=254, help="lattice points per dimension (N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--total-layers", type=int, default=0,
-                    help="STRONG scaling: fixed lattice 254 x 254 x TOTAL_LAYERS split over the GPUs "
-                         "(2032 = the 131 M particle cloud of BASELINE config 5); 0 = weak scaling, "
-                         "254 layers per GPU")
+    ap.add_argument("--no-sub-configs", action="store_true", help="skip the config 1 / 2 / 4 sub-lines")
+    ap.add_argument("--slabs", action="store_true",
+                    help="run the slab-decomposed config 5 path even on one GPU (strong-scaling base line)")
+    ap.add_argument("--slab-lattice", type=int, default=504,
+                    help="lattice of the slab-decomposed cloud (504 = BASELINE config 5)")
+    ap.add_argument("--no-overlap", action="store_true", help="slab path: exchange not overlapped (A/B)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -182,6 +182,17 @@ int pnb_grid_layout(const pnb_grid *g);
 pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n, const int32_t *eachindex_y,
                               int64_t n_idx, int index_base, void *stream);
 
+/* Stream-ordered update! (no reference counterpart: the reference blocks after every launch,
+ * src/util.jl:166-170).  From the second build on (full rebuild, FullGridCellList) the one-pass
+ * build is only ENQUEUED on `stream`: nothing is synchronised and the error word is not read.
+ * The next blocking call on the handle settles it: a sweep reports "particle coordinates are NaN
+ * or outside the domain bounds..." then, and a bucket that overflowed makes the
+ * library rebuild the cell list (two-pass, blocking) and repeat that sweep, invisibly to the
+ * caller.  First builds, hashed and template searches fall back to pnb_grid_build_f32.
+ * pnb_grid_check synchronises `stream` and returns what a blocking update! would have returned. */
+pnb_status pnb_grid_build_async_f32(pnb_grid *g, const float *y, int64_t n, void *stream);
+pnb_status pnb_grid_check(pnb_grid *g, void *stream);
+
 /* cell_coords + cell_index of arbitrary points (src/nhs_grid.jl:622-628, full_grid.jl:84-94,157-161):
  * out[i] = 0-based linear cell index, or -1 when the cell is outside 2:(size-1). */
 pnb_status pnb_point_cells_f32(const pnb_grid *g, const float *x, int64_t n, int32_t *out_linear,
@@ -228,6 +239,10 @@ void pnb_set_twoset_tiles(int on);
  * in a per-point kernel (instead of a second, nearly empty batch of the whole cell); 0 = never,
  * 2 = always when the closure allows it (tests).  Same results. */
 void pnb_set_sweep_left(int mode);
+/* Tile sweep kernel: 1 (default) = k_sweep_flat (tiles are ranges of 96 points, full warps,
+ * persistent CTAs), 0 = k_sweep_tiles of round 1 (tiles are 4 cells, one warp
+ * group per cell), kept for A/B measurements.  Same results. */
+void pnb_set_sweep_kernel(int flat);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
  * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with
@@ -275,6 +290,36 @@ pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_t nx, const
                                   const float *mass_x, const float *mass_y,
                                   const float *pressure_x, const float *pressure_y,
                                   const pnb_wcsph_params *params, float *dv, void *stream);
+
+/* Stream-ordered form of pnb_wcsph_interact_f32 for x === y, all points (y must be the array of
+ * the last update!): gather + sweep are enqueued on `stream`, nothing is synchronised;
+ * pnb_grid_check settles it together with a preceding pnb_grid_build_async_f32. */
+pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, int64_t n, const float *v,
+                                        const float *mass, const float *pressure,
+                                        const pnb_wcsph_params *params, float *dv, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The WCSPH step from HOST buffers, pipelined (the end-to-end call of a host-side caller).
+ *   replaces, per step: copyto!(device arrays, host arrays) (Adapt, benchmarks/run_benchmarks.jl:97-99),
+ *   update!(nhs, y, y; points_moving = (true, true)) (src/nhs_grid.jl:283-292), interact!
+ *   (benchmarks/smoothed_particle_hydrodynamics.jl:99-101) and the copy of dv back to the host.
+ * Three streams and double-buffered device arrays inside the handle: the host->device copy of
+ * step s + 1 and the device->host copy of step s - 1 overlap the kernels of step s.
+ * submit() enqueues step s and returns once step s - 1's kernels are done and checked (a domain
+ * error of step s - 1 is returned by this call); dv_host of step s is valid after
+ * pnb_hoststep_wait(), or once the submit of step s + 2 has returned.
+ * y_host: n x ndims, v_host: n x (ndims + 1) (velocity, density), pressure_host: n, mass_host: n
+ * or NULL (= unchanged since the last submit that passed it), dv_host: n x (ndims + 1).
+ * Pinned host memory (pnb_malloc_host) is needed for the copies to overlap.  The grid handle
+ * must not be used by other calls while steps are in flight.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pnb_hoststep pnb_hoststep;
+pnb_status pnb_hoststep_create(pnb_grid *g, int64_t n, pnb_hoststep **out);
+pnb_status pnb_hoststep_wcsph_submit(pnb_hoststep *h, const float *y_host, const float *v_host,
+                                     const float *mass_host, const float *pressure_host,
+                                     const pnb_wcsph_params *params, float *dv_host);
+pnb_status pnb_hoststep_wait(pnb_hoststep *h);
+void pnb_hoststep_destroy(pnb_hoststep *h);
 
 /* ---------------------------------------------------------------------------------------------
  * Neighbour lists = PrecomputedNeighborhoodSearch (src/nhs_precomputed.jl:67-277)

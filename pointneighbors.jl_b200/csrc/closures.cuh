@@ -146,6 +146,36 @@ struct NBodyClT {
     {
         term<ND>(s, px, py, pz, d2, __ldg(mass_sorted + gi));
     }
+    static constexpr int kPayBytesTile = 4;
+    __device__ __forceinline__ void stage_tile(unsigned char *pay, int slot, uint32_t gi, int cap) const
+    {
+        stage(pay, slot, gi, cap);
+    }
+    __device__ __forceinline__ void stage_async(uint32_t pay_sa, int slot, uint32_t gi, int) const
+    {
+        cp_async4(pay_sa + 4u * (uint32_t)slot, mass_sorted + gi);
+    }
+    template <int ND>
+    __device__ __forceinline__ void pair_tile(State &s, float px, float py, float pz, float d2, int j,
+                                              uint32_t pay_sa, int slot, int cap) const
+    {
+        pair_s<ND>(s, px, py, pz, d2, j, pay_sa, slot, cap);
+    }
+    template <int ND>
+    __device__ __forceinline__ void pair_tile_pred(State &s, float px, float py, float pz, float d2,
+                                                   int j, uint32_t pay_sa, int slot, int cap, bool ok) const
+    {
+        if (EXACT) { if (ok) pair_s<ND>(s, px, py, pz, d2, j, pay_sa, slot, cap); return; }
+        float m;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(pay_sa + 4u * (uint32_t)slot));
+        const bool use = ok && d2 >= PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32;
+        const float inv_d = fast_rsqrt(use ? d2 : 1.0f);
+        float c = (negG * m) * (inv_d * inv_d * inv_d);
+        c = use ? c : 0.f;
+        s.a[0] = fmaf(c, px, s.a[0]);
+        if (ND > 1) s.a[1] = fmaf(c, py, s.a[1]);
+        if (ND > 2) s.a[2] = fmaf(c, pz, s.a[2]);
+    }
     __device__ __forceinline__ void finish(State &s, int, int i_id) const
     {
         for (int k = 0; k < nd; k++) dv[(int64_t)i_id * nd + k] = s.a[k];
@@ -193,9 +223,14 @@ struct WcsphClT {
         if (!active) return;
         if (i_sorted >= 0) {
             const float4 a = vrho_sorted[i_sorted];
-            const float4 b = mp_sorted[i_sorted];
             s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.rho = a.w;
-            s.p = b.y; s.inv_rho = b.z;
+            if (EXACT) {
+                const float4 b = mp_sorted[i_sorted];
+                s.p = b.y; s.inv_rho = b.z;
+            } else {
+                s.p = vp_sorted[i_sorted].y;
+                s.inv_rho = __fdiv_rn(1.f, a.w);
+            }
         } else {
             const int ns = nd + 1;
             for (int k = 0; k < nd; k++) s.v[k] = v_x[(int64_t)i_id * ns + k];
@@ -208,7 +243,12 @@ struct WcsphClT {
     __device__ __forceinline__ void stage(unsigned char *pay, int slot, uint32_t gi, int cap) const
     {
         reinterpret_cast<float4 *>(pay)[slot] = vrho_sorted[gi];
-        reinterpret_cast<float4 *>(pay + 16 * cap)[slot] = mp_sorted[gi];   // plane 1
+        if (EXACT) {
+            reinterpret_cast<float4 *>(pay + 16 * cap)[slot] = mp_sorted[gi];   // plane 1
+        } else {
+            const float2 vp = vp_sorted[gi];      // the fast term reads (.w, .y) = (m/rho, p)
+            reinterpret_cast<float4 *>(pay + 16 * cap)[slot] = make_float4(0.f, vp.y, 0.f, vp.x);
+        }
     }
     __device__ __forceinline__ void count(State &, int) const {}
     __device__ __forceinline__ void merge(State &s, const State &o) const
@@ -216,9 +256,11 @@ struct WcsphClT {
         s.acc[0] += o.acc[0]; s.acc[1] += o.acc[1]; s.acc[2] += o.acc[2]; s.acc[3] += o.acc[3];
     }
 
+    // vol_b = m_b / rho_b and p_b are all the fast term needs of (mass, pressure, 1/rho, m/rho);
+    // m_b itself only appears in the viscosity of approaching pairs: m_b = vol_b * rho_b
     template <int ND>
     __device__ __forceinline__ void term_fast(State &s, float px, float py, float pz, float d2,
-                                              float4 vb, float4 mpb) const
+                                              float4 vb, float vol_b, float p_b) const
     {
         // pairs closer than sqrt(eps) (the self pair) contribute exactly zero in the reference
         if (d2 < PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32) return;
@@ -230,7 +272,6 @@ struct WcsphClT {
         const float t = fmaxf(fmaf(prm_nhalf_inv_h, d, 1.f), 0.f);   // w = 0 beyond the support q >= 2
         const float sg = (prm_k5 * t) * (t * t);
         const float rho_a = s.rho, rho_b = vb.w;
-        const float m_b = mpb.x, p_b = mpb.y, vol_b = mpb.w;
         float coef = (vol_b * (s.p + p_b)) * s.neg_inv_rho;       // -m_b (p_a + p_b) / (rho_a rho_b)
         const float vdx = s.v[0] - vb.x, vdy = s.v[1] - vb.y, vdz = s.v[2] - vb.z;
         float vr = vdx * px;
@@ -239,7 +280,7 @@ struct WcsphClT {
         if (vr < 0.f) {
             const float mu = (h * vr) * fast_rcp(fmaf(prm.epsilon, h * h, d2));
             const float pi_ab = (prm_ac * mu - prm.beta * (mu * mu)) * fast_rcp(0.5f * (rho_a + rho_b));
-            coef = fmaf(m_b, pi_ab, coef);
+            coef = fmaf(vol_b * rho_b, pi_ab, coef);
         }
         coef *= sg;
         s.acc[0] = fmaf(coef, px, s.acc[0]);
@@ -252,7 +293,7 @@ struct WcsphClT {
     __device__ __forceinline__ void term(State &s, float px, float py, float pz, float d2,
                                          float4 vb, float4 mpb4) const
     {
-        if (!EXACT) { term_fast<ND>(s, px, py, pz, d2, vb, mpb4); return; }
+        if (!EXACT) { term_fast<ND>(s, px, py, pz, d2, vb, mpb4.w, mpb4.y); return; }
         const float2 mpb = make_float2(mpb4.x, mpb4.y);
         const float d = __fsqrt_rn(d2);
         const float rho_a = s.rho, rho_b = vb.w;
@@ -338,8 +379,85 @@ struct WcsphClT {
     __device__ __forceinline__ void pair_global(State &s, float px, float py, float pz, float d2,
                                                 int, uint32_t gi) const
     {
-        term<ND>(s, px, py, pz, d2, __ldg(vrho_sorted + gi), __ldg(mp_sorted + gi));
+        if (EXACT) {
+            term<ND>(s, px, py, pz, d2, __ldg(vrho_sorted + gi), __ldg(mp_sorted + gi));
+        } else {
+            const float2 vp = __ldg(vp_sorted + gi);
+            term_fast<ND>(s, px, py, pz, d2, __ldg(vrho_sorted + gi), vp.x, vp.y);
+        }
     }
+    // k_sweep_flat stages 24 instead of 32 bytes per candidate: (vx, vy, vz, rho) and (m/rho, p)
+    static constexpr int kPayBytesTile = EXACT ? 32 : 24;
+    __device__ __forceinline__ void stage_tile(unsigned char *pay, int slot, uint32_t gi, int cap) const
+    {
+        reinterpret_cast<float4 *>(pay)[slot] = vrho_sorted[gi];
+        if (EXACT) reinterpret_cast<float4 *>(pay + 16 * cap)[slot] = mp_sorted[gi];
+        else reinterpret_cast<float2 *>(pay + 16 * cap)[slot] = vp_sorted[gi];
+    }
+    // the same as asynchronous copies global -> shared (LDGSTS), no registers in between
+    __device__ __forceinline__ void stage_async(uint32_t pay_sa, int slot, uint32_t gi, int cap) const
+    {
+        cp_async16(pay_sa + 16u * (uint32_t)slot, vrho_sorted + gi);
+        if (EXACT) cp_async16(pay_sa + 16u * (uint32_t)cap + 16u * (uint32_t)slot, mp_sorted + gi);
+        else cp_async8(pay_sa + 16u * (uint32_t)cap + 8u * (uint32_t)slot, vp_sorted + gi);
+    }
+    // branch-free form for the drain of k_sweep_flat: the payload is loaded unconditionally (the
+    // loads do not wait for the radius test), `ok` only decides whether the term counts
+    template <int ND>
+    __device__ __forceinline__ void pair_tile_pred(State &s, float px, float py, float pz, float d2,
+                                                   int, uint32_t pay_sa, int slot, int cap, bool ok) const
+    {
+        if (EXACT) { if (ok) pair_s<ND>(s, px, py, pz, d2, 0, pay_sa, slot, cap); return; }
+        float4 vb;
+        float vol_b, p_b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(vb.x), "=f"(vb.y), "=f"(vb.z), "=f"(vb.w) : "r"(pay_sa + 16u * (uint32_t)slot));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(vol_b), "=f"(p_b) : "r"(pay_sa + 16u * (uint32_t)cap + 8u * (uint32_t)slot));
+        // pairs closer than sqrt(eps) (the self pair) and lanes without a hit in this round
+        // contribute exactly zero: sg = 0
+        const bool use = ok && d2 >= PNB_SQRT_EPS_F32 * PNB_SQRT_EPS_F32;
+        const float d2s = use ? d2 : 1.0f;
+        const float h = prm.smoothing_length;
+        const float inv_d = fast_rsqrt(d2s);
+        const float d = d2s * inv_d;
+        const float t = fmaxf(fmaf(prm_nhalf_inv_h, d, 1.f), 0.f);
+        float sg = (prm_k5 * t) * (t * t);
+        sg = use ? sg : 0.f;
+        const float rho_a = s.rho, rho_b = vb.w;
+        float coef = (vol_b * (s.p + p_b)) * s.neg_inv_rho;
+        const float vdx = s.v[0] - vb.x, vdy = s.v[1] - vb.y, vdz = s.v[2] - vb.z;
+        float vr = vdx * px;
+        if (ND > 1) vr = fmaf(vdy, py, vr);
+        if (ND > 2) vr = fmaf(vdz, pz, vr);
+        if (vr < 0.f) {
+            const float mu = (h * vr) * fast_rcp(fmaf(prm.epsilon, h * h, d2s));
+            const float pi_ab = (prm_ac * mu - prm.beta * (mu * mu)) * fast_rcp(0.5f * (rho_a + rho_b));
+            coef = fmaf(vol_b * rho_b, pi_ab, coef);
+        }
+        coef *= sg;
+        s.acc[0] = fmaf(coef, px, s.acc[0]);
+        if (ND > 1) s.acc[1] = fmaf(coef, py, s.acc[1]);
+        if (ND > 2) s.acc[2] = fmaf(coef, pz, s.acc[2]);
+        s.acc[3] = fmaf(vol_b * sg, fmaf(rho_a, vr, prm_dhc2 * (rho_a - rho_b)), s.acc[3]);
+    }
+    template <int ND>
+    __device__ __forceinline__ void pair_tile(State &s, float px, float py, float pz, float d2, int,
+                                              uint32_t pay_sa, int slot, int cap) const
+    {
+        if (EXACT) { pair_s<ND>(s, px, py, pz, d2, 0, pay_sa, slot, cap); return; }
+        float4 vb;
+        float vol_b, p_b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(vb.x), "=f"(vb.y), "=f"(vb.z), "=f"(vb.w) : "r"(pay_sa + 16u * (uint32_t)slot));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(vol_b), "=f"(p_b) : "r"(pay_sa + 16u * (uint32_t)cap + 8u * (uint32_t)slot));
+        term_fast<ND>(s, px, py, pz, d2, vb, vol_b, p_b);
+    }
+    // the fast term vanishes identically for d >= 2 h (t = 0): when the kernel support 2 h does
+    // not exceed the search radius, candidates of the fp16 pre-filter band (r < d <= 1.005 r)
+    // contribute exactly zero and the exact radius test of the drain is redundant
+    __device__ __forceinline__ bool no_radius_test() const { return !EXACT && support_in_radius; }
     __device__ __forceinline__ void finish(State &s, int, int i_id) const
     {
         const int ns = nd + 1;
@@ -351,6 +469,9 @@ struct WcsphClT {
     float prm_k5;            // -5 kernel_norm / h^2
     float prm_ac;      // alpha * c
     float prm_dhc2;    // 2 * delta * h * c
+    bool support_in_radius;   // 2 h <= search_radius (see no_radius_test)
+    const float2 *vp_sorted;  // fast mode: (mass / rho, pressure) of the neighbour points, cell order
+                              // (mp_sorted is filled in exact mode only)
 };
 
 }  // namespace pnb

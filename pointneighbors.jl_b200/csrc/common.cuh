@@ -90,6 +90,7 @@ enum Phase {
     PH_NLIST_SWEEP,           // k_tlsph_defgrad / k_nlist_pairs
     PH_EXPORT,                // export kernels
     PH_BUILD_BUCKET,          // k_bucket_scatter (one-pass update!)
+    PH_SWEEP_TILES_PREP,      // k_flat_tiles / k_flat_scan (tile table of k_sweep_flat)
     PH_COUNT_
 };
 struct ProfScope {
@@ -220,6 +221,25 @@ __device__ __forceinline__ float maybe_periodic_fix(const PerP &q, float d2, flo
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// asynchronous global -> shared copies (LDGSTS): no register staging, all copies of a tile in flight
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+
 // The cell list as the kernels see it.  Two layouts:
 //   CSR     (K == 0): start[0 .. C] offsets, cell c = rec[start[c] .. start[c+1])
 //   buckets (K  > 0): start[c] = number of points of cell c, cell c = rec[c K .. c K + start[c])
@@ -246,7 +266,9 @@ __device__ __forceinline__ void cell_range(const CellsView &v, int lin, uint32_t
     if (v.K) {
         const uint32_t lb = bucket_of((uint32_t)lin, v.t0, v.t1, v.t2);
         b0 = lb * v.K;
-        cnt = v.start[lb];
+        // (a count above K only exists while an overflowed stream-ordered update! is waiting for
+        // its blocking rebuild: stay inside the bucket, the results are discarded then)
+        cnt = min(v.start[lb], v.K);
     } else { b0 = v.start[lin]; cnt = v.start[lin + 1] - b0; }
 }
 

@@ -87,7 +87,7 @@ static void prof_collect()
 static const char *kPhaseNames[PH_COUNT_] = {
     "k_cell_hist", "k_scan_lookback", "k_scatter_points", "k_canonicalize", "k_gather",
     "k_sweep_cells", "k_sweep_overflow", "k_sweep_points", "k_sort_lists", "k_nlist_sweep", "k_export",
-    "k_bucket_scatter"};
+    "k_bucket_scatter", "k_flat_tiles"};
 
 static const char *kDomainMsg =
     "particle coordinates are NaN or outside the domain bounds of the cell list";
@@ -95,28 +95,136 @@ static const char *kListFullMsg = "cell list is full. Use a larger `max_points_p
 static const char *kBoundsMsg =
     "BoundsError: a neighboring cell of a query point is outside the cell grid";
 
-pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
+static pnb_status translate_err_word(pnb_grid *g)
 {
-    // the error word lives in mapped pinned host memory (kernels OR their bits into it through
-    // d_err): one stream synchronisation, no copy
-    PNB_CUDA(cudaStreamSynchronize(s));
     int e = *(volatile int *)g->h_err;
     if (e == 0) return PNB_OK;
     *(volatile int *)g->h_err = 0;
     e &= ~8;   // bit 3 (bucket overflow) is consumed by the build itself
     if (e & 1) { set_error("%s", kDomainMsg); return PNB_ERR_DOMAIN; }
     if (e & 4) { set_error("%s", kListFullMsg); return PNB_ERR_LIST_FULL; }
+    if (e == 0) return PNB_OK;
     set_error("%s", kBoundsMsg);
     return PNB_ERR_BOUNDS;
 }
 
-pnb_status check_built_y(const pnb_grid *g, const void *y, int64_t n)
+// After the stream of a stream-ordered update! has been synchronised: a bucket overflow means
+// the cell list is incomplete -> blocking two-pass rebuild from the same coordinates (which also
+// picks a larger K).  *rebuilt tells the caller that work launched on the old list is void.
+static pnb_status settle_async_build(pnb_grid *g, bool *rebuilt)
+{
+    *rebuilt = false;
+    if (!g->async_pending) return PNB_OK;
+    g->async_pending = false;
+    const int e = *(volatile int *)g->h_err;
+    if ((e & 8) == 0) {
+        if (e & 1) {       // domain error of the build: like the blocking build, the list is unusable
+            *(volatile int *)g->h_err = 0;
+            g->n_built = 0;
+            g->built = false;
+            set_error("%s", kDomainMsg);
+            return PNB_ERR_DOMAIN;
+        }
+        return PNB_OK;
+    }
+    *(volatile int *)g->h_err = 0;
+    g->bucket_K = 0;
+    g->bcount_alt_clean = false;
+    *rebuilt = true;
+    return pnb_grid_build_f32(g, (const float *)g->y_built, g->n_y_built, nullptr, 0, 0,
+                              (void *)g->async_stream);
+}
+
+pnb_status resolve_pending(pnb_grid *g)
+{
+    if (!g->async_pending) return PNB_OK;
+    PNB_CUDA(cudaStreamSynchronize(g->async_stream));
+    bool rebuilt = false;
+    return settle_async_build(g, &rebuilt);
+}
+
+pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
+{
+    // the error word lives in mapped pinned host memory (kernels OR their bits into it through
+    // d_err): one stream synchronisation, no copy
+    PNB_CUDA(cudaStreamSynchronize(s));
+    if (g->async_pending) {
+        if (g->async_stream != s) PNB_CUDA(cudaStreamSynchronize(g->async_stream));
+        bool rebuilt = false;
+        pnb_status st = settle_async_build(g, &rebuilt);
+        if (st != PNB_OK) return st;
+        if (rebuilt) return PNB_RETRY_INTERNAL;
+    }
+    return translate_err_word(g);
+}
+
+// The reference reads neighbor_coords LIVE at sweep time (src/nhs_grid.jl:543-548) while its
+// cell list is the one of the last initialize!/update!; this library sweeps cell-ordered records
+// (x, y, z, id) snapshotted at that build.  Same array as at build time: the snapshot is current
+// (moving y in place requires update!, src/neighborhood_search.jl:161-164).  Another array with
+// the same number of points: the reference's semantics are "old cell list, coordinates of THIS
+// array", so the records' coordinates are re-read from it through their ids (one gather pass);
+// afterwards the snapshot belongs to the new array.  A different number of points is a
+// call-order error.
+__global__ void k_refresh_records(int64_t n_slots, int nd, CellsView cv, const float *__restrict__ y,
+                                  float4 *__restrict__ rec)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    if (cv.K) {
+        const uint32_t sl = (uint32_t)i;
+        if ((sl & (cv.K - 1u)) >= cv.start[sl >> (31 - __clz((int)cv.K))]) return;
+    }
+    float4 r = rec[i];
+    const int64_t id = __float_as_int(r.w);
+    r.x = __ldg(y + id * nd);
+    if (nd > 1) r.y = __ldg(y + id * nd + 1);
+    if (nd > 2) r.z = __ldg(y + id * nd + 2);
+    rec[i] = r;
+}
+__global__ void k_refresh_records64(int64_t n, int nd, const double *__restrict__ y,
+                                    Rec64 *__restrict__ rec)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rec64 r = rec[i];
+    r.x = y[r.id * nd];
+    if (nd > 1) r.y = y[r.id * nd + 1];
+    if (nd > 2) r.z = y[r.id * nd + 2];
+    rec[i] = r;
+}
+
+pnb_status check_built_y(pnb_grid *g, const void *y, int64_t n, cudaStream_t s)
 {
     if (y == g->y_built && n == g->n_y_built) return PNB_OK;
-    set_error("neighbor_coords (%p, %lld points) are not the coordinates the search was last "
-              "initialized / updated with (%p, %lld points): call update! first",
-              y, (long long)n, g->y_built, (long long)g->n_y_built);
-    return PNB_ERR_STATE;
+    { pnb_status sp = resolve_pending(g); if (sp != PNB_OK) return sp; }
+    if (n != g->n_y_built) {
+        set_error("neighbor_coords hold %lld points, the search was last initialized / updated "
+                  "with %lld: call update! first", (long long)n, (long long)g->n_y_built);
+        return PNB_ERR_STATE;
+    }
+    if (g->template_search || g->n_built == 0 || y == nullptr) { g->y_built = y; return PNB_OK; }
+    if (g->f64) {
+        k_refresh_records64<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(
+            g->n_built, g->p64.ndims, (const double *)y, g->sorted64);
+        PNB_LAUNCHED();
+    } else {
+        if (g->bucket_valid) {
+            const int64_t slots = (int64_t)g->p.total_cells * g->bucket_K;
+            k_refresh_records<<<(unsigned)div_up(slots, 256), 256, 0, s>>>(
+                slots, g->p.ndims, cells_view(g), (const float *)y, g->brec);
+            PNB_LAUNCHED();
+        }
+        if (g->csr_valid || !g->bucket_valid) {
+            const CellsView csr{g->cell_start, g->sorted, 0u, 0u, 0u, 0u};
+            k_refresh_records<<<(unsigned)div_up(g->n_built, 256), 256, 0, s>>>(
+                g->n_built, g->p.ndims, csr, (const float *)y, g->sorted);
+            PNB_LAUNCHED();
+        }
+    }
+    g->y_built = y;
+    g->y_refreshed = true;
+    return PNB_OK;
 }
 
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes)
@@ -366,6 +474,7 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->hmeta);
     cudaFree(g->xq_sorted);
     cudaFree(g->bcount);
+    cudaFree(g->bcount_alt);
     cudaFree(g->brec);
     cudaFree(g->sorted64);
     cudaFree(g->sorted64_tmp);
@@ -381,6 +490,10 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->ovf_tiles);
     cudaFree(g->ovf_count);
     cudaFree(g->left_ids);
+    cudaFree(g->flat_tiles);
+    cudaFree(g->flat_ovf);
+    cudaFree(g->flat_seg);
+    cudaFree(g->flat_ctl);
     cudaGetLastError();
     delete g;
 }
@@ -990,8 +1103,13 @@ template <int ND, bool PER, int PPT, int DIAG = 0, bool TR = false>
 __global__ void __launch_bounds__(kBuildThreads, 6)
 k_bucket_scatter(GridP g, BuildP bp, const float *__restrict__ y, int64_t n_idx,
                  const int32_t *__restrict__ idx, int base, uint32_t K,
-                 uint32_t *__restrict__ bcount, float4 *__restrict__ brec, int *__restrict__ err)
+                 uint32_t *__restrict__ bcount, float4 *__restrict__ brec, int *__restrict__ err,
+                 uint4 *__restrict__ clear4, int n_clear4)
 {
+    // the counters of the NEXT build (the other array) are cleared on the side: no memset launch
+    for (int64_t i = (int64_t)blockIdx.x * kBuildThreads + threadIdx.x; i < n_clear4;
+         i += (int64_t)gridDim.x * kBuildThreads)
+        clear4[i] = make_uint4(0u, 0u, 0u, 0u);
     const int64_t block0 = (int64_t)blockIdx.x * (kBuildThreads * PPT);
     const int logK = 31 - __clz((int)K);            // K is a power of two
     if (idx == nullptr && block0 + (kBuildThreads * PPT) <= n_idx) {
@@ -1162,6 +1280,7 @@ pnb_status ensure_point_capacity(pnb_grid *g, int64_t n)
 // exports, the ordered / per-point sweeps, the canonical order).
 pnb_status ensure_csr(pnb_grid *g, cudaStream_t s)
 {
+    { pnb_status sp = resolve_pending(g); if (sp != PNB_OK) return sp; }
     if (g->csr_valid || !g->built || !g->bucket_valid) return PNB_OK;
     const int64_t C = g->p.total_cells;
     const uint32_t t0 = g->bucket_tr ? (uint32_t)g->p.gs[0] : 0u;
@@ -1189,6 +1308,7 @@ pnb_status ensure_csr(pnb_grid *g, cudaStream_t s)
 
 pnb_status ensure_canonical(pnb_grid *g, cudaStream_t s)
 {
+    { pnb_status sp = resolve_pending(g); if (sp != PNB_OK) return sp; }
     if (g->canonical || !g->built || g->template_search || g->n_built == 0) return PNB_OK;
     {
         pnb_status stc = ensure_csr(g, s);
@@ -1310,6 +1430,9 @@ extern "C" void pnb_set_build_tuning(int variant) { pnb::g_tune_build = variant;
 extern "C" void pnb_set_build_layout(int buckets) { pnb::g_build_layout = buckets; }
 extern "C" void pnb_set_bucket_order(int order) { pnb::g_bucket_order = order; }
 
+// set while pnb_grid_build_async_f32 runs the build below
+static thread_local bool t_async_build = false;
+
 extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                                          const int32_t *eachindex_y, int64_t n_idx, int index_base,
                                          void *stream)
@@ -1319,7 +1442,17 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t C = g->p.total_cells;
     if (eachindex_y == nullptr) n_idx = n;
+    if (g->async_pending) {
+        // a stream-ordered update! nobody looked at: its error word must not leak into this build
+        PNB_CUDA(cudaStreamSynchronize(g->async_stream));
+        g->async_pending = false;
+        const int e = *(volatile int *)g->h_err;
+        *(volatile int *)g->h_err = 0;
+        if (e & 8) { g->bucket_K = 0; g->bcount_alt_clean = false; }
+        if (e & 1) { set_error("%s", kDomainMsg); g->n_built = 0; g->built = false; return PNB_ERR_DOMAIN; }
+    }
     g->built = false;
+    g->y_refreshed = false;
     g->canonical = false;
     // empty!(cell_list)  (src/cell_lists/full_grid.jl:96-105)
     if (g->template_search) {
@@ -1356,22 +1489,33 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
             PNB_CUDA(cudaMalloc(&g->brec, sizeof(float4) * (size_t)slots));
             g->brec_slots = slots;
         }
-        if (!g->bcount) PNB_CUDA(cudaMalloc(&g->bcount, sizeof(uint32_t) * (size_t)(C + 4)));
+        if (!g->bcount) {
+            PNB_CUDA(cudaMalloc(&g->bcount, sizeof(uint32_t) * (size_t)(C + 8)));
+            PNB_CUDA(cudaMalloc(&g->bcount_alt, sizeof(uint32_t) * (size_t)(C + 8)));
+            g->bcount_alt_clean = false;
+        }
         BuildP bp;
         for (int d = 0; d < 3; d++) { volatile float rc = 1.0f / g->p.cs[d]; bp.rcs[d] = rc; }
         {
             ProfScope ps(PH_BUILD_BUCKET, s);     // the clearing of the counters is part of it
-            PNB_CUDA(cudaMemsetAsync(g->bcount, 0, sizeof(uint32_t) * (size_t)C, s));
+            // two counter arrays: this build counts into the one the previous build cleared and
+            // clears the other one for the next build
+            if (!g->bcount_alt_clean)
+                PNB_CUDA(cudaMemsetAsync(g->bcount_alt, 0, sizeof(uint32_t) * (size_t)(C + 8), s));
+            { uint32_t *t = g->bcount; g->bcount = g->bcount_alt; g->bcount_alt = t; }
+            g->bcount_alt_clean = true;
+            uint4 *clear4 = reinterpret_cast<uint4 *>(g->bcount_alt);
+            const int n_clear4 = (int)((C + 3) / 4);
 #define PNB_BUCKET(ND, PER, PPT)                                                                   \
     do {                                                                                           \
         if (g->bucket_tr)                                                                          \
             k_bucket_scatter<ND, PER, PPT, 8, true><<<(unsigned)div_up(n_idx, kBuildThreads * PPT), \
                 kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base,                \
-                                       (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err);       \
+                                       (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4);       \
         else                                                                                       \
             k_bucket_scatter<ND, PER, PPT, 8><<<(unsigned)div_up(n_idx, kBuildThreads * PPT),      \
                 kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base,                \
-                                       (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err);       \
+                                       (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4);       \
     } while (0)
             const bool per = g->p.periodic != 0;
             switch (g->p.ndims) {
@@ -1385,18 +1529,18 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                     else if (g_tune_build & 2048) {
                         // runs of adjacent lanes instead of match.any lane groups (the version
                         // before; valid results, kept for tools/match_diag.py)
-                        k_bucket_scatter<3, false, 4, 0><<<(unsigned)div_up(n_idx, kBuildThreads * 4), kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err);
+                        k_bucket_scatter<3, false, 4, 0><<<(unsigned)div_up(n_idx, kBuildThreads * 4), kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4);
                     }
 #ifdef PNB_DIAG   /* tools/ builds only: these variants write garbage layouts */
                     else if ((g_tune_build >> 8) & 7) {
                         // measurement only (DIAG variants of the kernel; the layout is garbage)
                         const unsigned nb = (unsigned)div_up(n_idx, kBuildThreads * 4);
                         switch ((g_tune_build >> 8) & 7) {
-                            case 1: k_bucket_scatter<3, false, 4, 1><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
-                            case 2: k_bucket_scatter<3, false, 4, 2><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
-                            case 3: k_bucket_scatter<3, false, 4, 3><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
-                            case 4: k_bucket_scatter<3, false, 4, 4><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
-                            default: k_bucket_scatter<3, false, 4, 6><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+                            case 1: k_bucket_scatter<3, false, 4, 1><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4); break;
+                            case 2: k_bucket_scatter<3, false, 4, 2><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4); break;
+                            case 3: k_bucket_scatter<3, false, 4, 3><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4); break;
+                            case 4: k_bucket_scatter<3, false, 4, 4><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4); break;
+                            default: k_bucket_scatter<3, false, 4, 6><<<nb, kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4); break;
                         }
                     }
 #endif
@@ -1405,6 +1549,18 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
             }
 #undef PNB_BUCKET
             PNB_LAUNCHED();
+        }
+        if (t_async_build) {
+            // stream-ordered update!: the error word is looked at by the next blocking call
+            g->bucket_valid = true;
+            g->n_built = n_idx;
+            g->y_built = y;
+            g->n_y_built = n;
+            g->full_build = (eachindex_y == nullptr);
+            g->built = true;
+            g->async_pending = true;
+            g->async_stream = s;
+            return PNB_OK;
         }
         PNB_CUDA(cudaStreamSynchronize(s));     // initialize!/update! are blocking calls
         const int e = *(volatile int *)g->h_err;
@@ -1423,6 +1579,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         // a domain error found on the way is reported by that build again
         *(volatile int *)g->h_err = 0;
         g->bucket_K = 0;
+        g->bcount_alt_clean = false;
     }
     switch (g->p.ndims) {
         case 1: st = g->p.periodic ? build_nd<1, true>(g, y, n, eachindex_y, n_idx, index_base, s)
@@ -1493,6 +1650,24 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         }
     }
     return PNB_OK;
+}
+
+extern "C" pnb_status pnb_grid_build_async_f32(pnb_grid *g, const float *y, int64_t n, void *stream)
+{
+    if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    // only the one-pass bucket build can run without looking at its result; everything else
+    // (first build, hashed / template searches, CSR layout forced) is the blocking build
+    t_async_build = !g->f64 && !g->hashed && !g->template_search && g->bucket_K > 0 && n > 0;
+    const pnb_status st = pnb_grid_build_f32(g, y, n, nullptr, 0, 0, stream);
+    t_async_build = false;
+    return st;
+}
+
+extern "C" pnb_status pnb_grid_check(pnb_grid *g, void *stream)
+{
+    if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    const pnb_status st = check_err_word(g, (cudaStream_t)stream);
+    return st == PNB_RETRY_INTERNAL ? PNB_OK : st;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1583,6 +1758,9 @@ extern "C" pnb_status pnb_grid_export_csr(const pnb_grid *g_, int32_t *cell_star
     cudaStream_t s = (cudaStream_t)stream;
     if (cell_points) {
         pnb_status stc = ensure_canonical(g, s);
+        if (stc != PNB_OK) return stc;
+    } else {
+        pnb_status stc = ensure_csr(g, s);
         if (stc != PNB_OK) return stc;
     }
     int64_t C1 = (int64_t)g->p.total_cells + 1;
@@ -2253,6 +2431,7 @@ extern "C" pnb_status pnb_grid_build_f64(pnb_grid *g, const double *y, int64_t n
     const int64_t C = g->p64.total_cells;
     if (eachindex_y == nullptr) n_idx = n;
     g->built = false;
+    g->y_refreshed = false;
     g->bucket_valid = false;
     if (g->template_search) {
         PNB_CUDA(cudaMemsetAsync(g->cell_start, 0, sizeof(uint32_t) * (size_t)(C + 1), s));
@@ -2344,7 +2523,7 @@ extern "C" pnb_status pnb_count_neighbors_f64(pnb_grid *g, const double *x, int6
         set_error("the neighborhood search has not been initialized (call initialize! first)");
         return PNB_ERR_STATE;
     }
-    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
+    { pnb_status sy = check_built_y(g, y, n, (cudaStream_t)stream); if (sy != PNB_OK) return sy; }
     cudaStream_t s = (cudaStream_t)stream;
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)nx, s));
     const int64_t n_loop = points ? n_points : nx;

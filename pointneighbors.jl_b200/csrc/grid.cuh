@@ -33,6 +33,13 @@ struct pnb_grid {
     int bucket_K;            // 0 = not chosen yet (the next CSR build picks it from the fullest cell)
     bool bucket_tr;          // buckets numbered in transposed cell order (chosen from the input order)
     bool bucket_valid;       // bcount / brec describe the current build
+    uint32_t *bcount_alt;    // [C] second counter array: all zero between builds; every one-pass
+                             // build clears the array of the NEXT build while it runs (no memset)
+    bool bcount_alt_clean;
+    // stream-ordered update! (pnb_grid_build_async_f32): the one-pass build was launched but its
+    // error word (domain error, bucket overflow) has not been looked at yet
+    bool async_pending;
+    cudaStream_t async_stream;
     bool csr_valid;          // cell_start / sorted describe the current build
     unsigned int *d_maxcount;   // [1] device scratch
 
@@ -71,6 +78,9 @@ struct pnb_grid {
     int64_t n_y_built;      // columns of y at build time
     bool built;
     bool full_build;        // eachindex_y == all
+    bool y_refreshed;       // the records' coordinates were re-read from another array than the one
+                            // of the build (check_built_y): points may sit in other cells than
+                            // the ones they are listed in, so x === y sweeps bin x like a second set
 
     // capacity hint for one-pass neighbour-list builds (nlist.cu): longest list of the last build
     int nl_cap_hint;
@@ -85,6 +95,14 @@ struct pnb_grid {
     int *ovf_count;          // [2]: overflow tiles, surplus points (k_sweep_left)
     int *left_ids;           // surplus points of cells with a few more than 32 points
     int64_t left_cap;
+
+    // k_sweep_flat (sweep_flat.cuh): tile table of one sweep and its control words
+    void *flat_tiles;        // FlatTile[flat_tiles_cap]
+    int *flat_ovf;           // [flat_tiles_cap] tiles handed to k_sweep_flat_overflow
+    int64_t flat_tiles_cap;
+    uint32_t *flat_seg;      // [2 * (flat_seg_cap + 1)] tiles per row segment, exclusive prefix
+    int64_t flat_seg_cap;
+    uint32_t *flat_ctl;      // [4] number of tiles, tile counter, overflow tiles
 };
 
 namespace pnb {
@@ -95,10 +113,17 @@ pnb_status ensure_point_capacity(pnb_grid *g, int64_t n);
 pnb_status hash_build(pnb_grid *g, const float *y, int64_t n, const int32_t *idx, int64_t n_idx,
                       int base, cudaStream_t s);
 pnb_status ensure_scratch(pnb_grid *g, int64_t bytes);
-// neighbor_coords of a sweep / list build must be the array of the last initialize!/update!
-// (the sweeps read the snapshot taken there; the reference reads y live, src/nhs_grid.jl:543-548)
-pnb_status check_built_y(const pnb_grid *g, const void *y, int64_t n);
+// neighbor_coords of a sweep / list build: the array of the last initialize!/update! (snapshot
+// current), or another array of the same length (the records are re-read from it: old cell
+// list + live coordinates, the reference's semantics, src/nhs_grid.jl:543-548)
+pnb_status check_built_y(pnb_grid *g, const void *y, int64_t n, cudaStream_t s);
 pnb_status check_err_word(pnb_grid *g, cudaStream_t s);  // sync + translate the error word
+// PNB_RETRY_INTERNAL from check_err_word: a stream-ordered update! had overflowed a bucket; the
+// cell list has been rebuilt (blocking), the sweep that ran on it must be repeated
+constexpr pnb_status PNB_RETRY_INTERNAL = (pnb_status)100;
+// settle a pending stream-ordered update! before anything but the x === y tile sweeps touches
+// the cell list (blocks; rebuilds after a bucket overflow)
+pnb_status resolve_pending(pnb_grid *g);
 pnb_status build_query_list(pnb_grid *g, const float *x, int64_t nx, double *points_per_cell,
                             cudaStream_t s);  // two-set sweeps
 pnb_status ensure_csr(pnb_grid *g, cudaStream_t s);       // CSR arrays from the bucket layout

@@ -700,7 +700,8 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
         set_error("this neighborhood search does not support inactive points");
         return PNB_ERR_ARG;
     }
-    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
+    { pnb_status sp = resolve_pending(g); if (sp != PNB_OK) return sp; }
+    { pnb_status sy = check_built_y(g, y, n, (cudaStream_t)stream); if (sy != PNB_OK) return sy; }
     cudaStream_t s = (cudaStream_t)stream;
     pnb_nlist *l = new pnb_nlist();
     memset(l, 0, sizeof(*l));
@@ -718,7 +719,7 @@ extern "C" pnb_status pnb_nlist_build_f32(pnb_grid *g, const float *x, int64_t n
     NL_CUDA(cudaMemsetAsync(l->d_err, 0, sizeof(int), s));
     NL_CUDA(cudaMallocHost(&l->h_err, sizeof(int)));
     NL_CUDA(cudaMemsetAsync(l->counts, 0, sizeof(uint32_t) * (size_t)(nx + 8), s));
-    const bool fast = g->full_build && x == g->y_built && nx == g->n_y_built;
+    const bool fast = g->full_build && !g->y_refreshed && x == g->y_built && nx == g->n_y_built;
     pnb_status st = PNB_OK;
     if (!fast && g->bucket_valid) {
         // two-set and per-point list builds walk the CSR arrays
@@ -968,7 +969,8 @@ extern "C" pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t 
         set_error("this neighborhood search does not support inactive points");
         return PNB_ERR_ARG;
     }
-    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
+    { pnb_status sp = resolve_pending(g); if (sp != PNB_OK) return sp; }
+    { pnb_status sy = check_built_y(g, y, n, (cudaStream_t)stream); if (sy != PNB_OK) return sy; }
     cudaStream_t s = (cudaStream_t)stream;
     pnb_nlist *l = new pnb_nlist();
     memset(l, 0, sizeof(*l));

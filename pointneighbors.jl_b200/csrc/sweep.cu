@@ -29,10 +29,11 @@ __global__ void k_gather_f32(int64_t n_slots, CellsView cv, const float *__restr
     if (i < n_slots && slot_valid(cv, i)) dst[i] = __ldg(src + __float_as_int(__ldg(&cv.rec[i].w)));
 }
 
+// exact mode: mp = (mass, pressure, 1/rho, mass/rho); fast mode: vp = (mass/rho, pressure) only
 __global__ void k_gather_wcsph(int64_t n, int nd, CellsView cv,
                                const float *__restrict__ v, const float *__restrict__ mass,
                                const float *__restrict__ pressure, float4 *__restrict__ vrho,
-                               float4 *__restrict__ mp)
+                               float4 *__restrict__ mp, float2 *__restrict__ vp)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !slot_valid(cv, i)) return;
@@ -50,7 +51,8 @@ __global__ void k_gather_wcsph(int64_t n, int nd, CellsView cv,
     vrho[i] = a;
     const float m = __ldg(mass + id);
     // 1/rho_b and m_b/rho_b once per neighbour instead of once per pair (fast path)
-    mp[i] = make_float4(m, __ldg(pressure + id), __fdiv_rn(1.f, a.w), __fdiv_rn(m, a.w));
+    if (mp) mp[i] = make_float4(m, __ldg(pressure + id), __fdiv_rn(1.f, a.w), __fdiv_rn(m, a.w));
+    else vp[i] = make_float2(__fdiv_rn(m, a.w), __ldg(pressure + id));
 }
 
 // pnb_set_exact_arithmetic: 0 (default) = fast per-pair terms (MUFU + FMA, |error| << 1e-5),
@@ -61,6 +63,7 @@ int g_tune_wpc = 0;
 int g_tune_half = -1;
 int g_tune_twoset = 1;
 int g_tune_left = getenv("PNB_SWEEP_LEFT") ? atoi(getenv("PNB_SWEEP_LEFT")) : 1;
+int g_tune_flat = getenv("PNB_SWEEP_FLAT") ? atoi(getenv("PNB_SWEEP_FLAT")) : 1;
 
 static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points);
 
@@ -80,11 +83,9 @@ static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const v
         return PNB_ERR_STATE;
     }
     if (nx > 0 && !x) { set_error("x is NULL"); return PNB_ERR_ARG; }
-    // The reference reads neighbor_coords live at sweep time (src/nhs_grid.jl:543-548); this
-    // library sweeps the cell-ordered snapshot taken by the last initialize!/update!.  The two
-    // agree exactly when y IS the array of that build, so anything else is a call-order error
-    // (the reference requires update! after y changed, src/neighborhood_search.jl:161-164).
-    { pnb_status sy = check_built_y(g, y, n); if (sy != PNB_OK) return sy; }
+    // the reference reads neighbor_coords live (src/nhs_grid.jl:543-548): another array than the
+    // one of the last build refreshes the cell-ordered snapshot (grid.cu, check_built_y)
+    { pnb_status sy = check_built_y(g, y, n, s); if (sy != PNB_OK) return sy; }
     *n_loop = points ? *n_loop : nx;
     // every sweep but the x === y tile sweep walks (or may walk) the CSR arrays: settle the
     // layout BEFORE the payload is gathered into it
@@ -98,24 +99,35 @@ static pnb_status sweep_precheck(pnb_grid *g, const void *x, int64_t nx, const v
 
 static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points)
 {
-    return points == nullptr && g->full_build && x == g->y_built && nx == g->n_y_built;
+    return points == nullptr && g->full_build && !g->y_refreshed && x == g->y_built && nx == g->n_y_built;
 }
 
 }  // namespace pnb
 
 using namespace pnb;
 
+// end of a sweep entry point: blocking calls synchronise and translate the error word (a
+// stream-ordered update! that overflowed a bucket is rebuilt there -> PNB_RETRY_INTERNAL, the
+// wrappers below repeat the sweep once); the *_async entry points return without looking
+static thread_local bool t_async_sweep = false;
+static pnb_status finish_sweep(pnb_grid *g, cudaStream_t s)
+{
+    if (t_async_sweep) return PNB_OK;
+    return check_err_word(g, s);
+}
+
 extern "C" void pnb_set_exact_arithmetic(int on) { g_exact_arithmetic = on != 0; }
 extern "C" int pnb_get_exact_arithmetic(void) { return g_exact_arithmetic; }
 extern "C" void pnb_set_twoset_tiles(int on) { g_tune_twoset = on; }
 extern "C" void pnb_set_sweep_left(int mode) { g_tune_left = mode; }
+extern "C" void pnb_set_sweep_kernel(int flat) { g_tune_flat = flat; }
 extern "C" void pnb_set_tuning(int warps_per_cell, int half_prefilter)
 {
     g_tune_wpc = warps_per_cell;
     g_tune_half = half_prefilter;
 }
 
-extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx,
+static pnb_status count_neighbors_impl(pnb_grid *g, const float *x, int64_t nx,
                                               const float *y, int64_t n, const int32_t *points,
                                               int64_t n_points, int index_base, int64_t *out,
                                               void *stream)
@@ -129,10 +141,10 @@ extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64
     CountCl cl{out};
     st = launch_sweep(g, is_fast_path(g, x, nx, points), true, x, n_loop, points, index_base, cl, s);
     if (st != PNB_OK) return st;
-    return check_err_word(g, s);
+    return finish_sweep(g, s);
 }
 
-extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
+static pnb_status nbody_impl(pnb_grid *g, const float *x, int64_t nx, const float *y,
                                     int64_t n, const int32_t *points, int64_t n_points,
                                     int index_base, const float *mass, float G, float *dv,
                                     void *stream)
@@ -144,7 +156,7 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
     const int nd = g->p.ndims;
     // n_body.jl:36  dv .= 0
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * nd, s));
-    if (g->template_search || g->n_built == 0) return check_err_word(g, s);
+    if (g->template_search || g->n_built == 0) return finish_sweep(g, s);
     // bit-identical sums need the reference's visiting order with ids ascending in a cell
     if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
     const int64_t slots = view_slots(g);
@@ -163,10 +175,10 @@ extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, con
     else
         st = launch_sweep(g, fastp, true, x, n_loop, points, index_base, NBodyClT<false>{mass_sorted, -G, dv, nd}, s);
     if (st != PNB_OK) return st;
-    return check_err_word(g, s);
+    return finish_sweep(g, s);
 }
 
-extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_t nx,
+static pnb_status wcsph_interact_impl(pnb_grid *g, const float *x, int64_t nx,
                                              const float *y, int64_t n, const int32_t *points,
                                              int64_t n_points, int index_base, const float *v_x,
                                              const float *v_y, const float *mass_x,
@@ -183,18 +195,21 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
     cudaStream_t s = (cudaStream_t)stream;
     const int nd = g->p.ndims;
     if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * (nd + 1), s));
-    if (g->template_search || g->n_built == 0) return check_err_word(g, s);
+    if (g->template_search || g->n_built == 0) return finish_sweep(g, s);
     if (g_exact_arithmetic && (st = ensure_canonical(g, s)) != PNB_OK) return st;
     const int64_t nb = view_slots(g);
     const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
     st = ensure_scratch(g, off_mp + (int64_t)sizeof(float4) * nb);
     if (st != PNB_OK) return st;
     float4 *vrho = reinterpret_cast<float4 *>(g->scratch);
-    float4 *mp = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
+    float4 *mp = g_exact_arithmetic
+        ? reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp) : nullptr;
+    float2 *vp = g_exact_arithmetic
+        ? nullptr : reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
     {
         ProfScope ps(PH_GATHER, s);
         k_gather_wcsph<<<(unsigned)div_up(nb, 256), 256, 0, s>>>(nb, nd, cells_view(g), v_y,
-                                                                 mass_y, pressure_y, vrho, mp);
+                                                                 mass_y, pressure_y, vrho, mp, vp);
         PNB_LAUNCHED();
     }
     const bool fastp = is_fast_path(g, x, nx, points);
@@ -202,12 +217,72 @@ extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_
     const float inv_h = -0.5f / h, kh = -5.0f * params->kernel_norm / (h * h);
     const float ac = params->alpha * params->sound_speed;
     const float dhc2 = 2.0f * params->delta * h * params->sound_speed;
+    const bool in_radius = 2.0f * h <= g->p.r;     // kernel support inside the search radius
     if (g_exact_arithmetic)
         st = launch_sweep(g, fastp, false, x, n_loop, points, index_base,
-                          WcsphClT<true>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2}, s);
+                          WcsphClT<true>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2, false, nullptr}, s);
     else
         st = launch_sweep(g, fastp, true, x, n_loop, points, index_base,
-                          WcsphClT<false>{vrho, mp, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2}, s);
+                          WcsphClT<false>{vrho, nullptr, v_x, pressure_x, *params, dv, nd, inv_h, kh, ac, dhc2, in_radius, vp}, s);
     if (st != PNB_OK) return st;
-    return check_err_word(g, s);
+    return finish_sweep(g, s);
+}
+
+// ---- C entry points: blocking (the reference's semantics, src/util.jl:166-170) and stream-ordered
+#define PNB_RETRY_ONCE(call)                                                                  \
+    do {                                                                                      \
+        pnb_status st__ = (call);                                                             \
+        if (st__ == PNB_RETRY_INTERNAL) st__ = (call);                                        \
+        if (st__ == PNB_RETRY_INTERNAL) { set_error("cell list changed during the sweep"); st__ = PNB_ERR_STATE; } \
+        return st__;                                                                          \
+    } while (0)
+
+extern "C" pnb_status pnb_count_neighbors_f32(pnb_grid *g, const float *x, int64_t nx,
+                                              const float *y, int64_t n, const int32_t *points,
+                                              int64_t n_points, int index_base, int64_t *out,
+                                              void *stream)
+{
+    PNB_RETRY_ONCE(count_neighbors_impl(g, x, nx, y, n, points, n_points, index_base, out, stream));
+}
+
+extern "C" pnb_status pnb_nbody_f32(pnb_grid *g, const float *x, int64_t nx, const float *y,
+                                    int64_t n, const int32_t *points, int64_t n_points,
+                                    int index_base, const float *mass, float G, float *dv,
+                                    void *stream)
+{
+    PNB_RETRY_ONCE(nbody_impl(g, x, nx, y, n, points, n_points, index_base, mass, G, dv, stream));
+}
+
+extern "C" pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_t nx,
+                                             const float *y, int64_t n, const int32_t *points,
+                                             int64_t n_points, int index_base, const float *v_x,
+                                             const float *v_y, const float *mass_x,
+                                             const float *mass_y, const float *pressure_x,
+                                             const float *pressure_y,
+                                             const pnb_wcsph_params *params, float *dv,
+                                             void *stream)
+{
+    PNB_RETRY_ONCE(wcsph_interact_impl(g, x, nx, y, n, points, n_points, index_base, v_x, v_y, mass_x,
+                                       mass_y, pressure_x, pressure_y, params, dv, stream));
+}
+
+// Stream-ordered form of the x === y WCSPH sweep (all points): everything is enqueued on
+// `stream`, nothing is synchronised and no error word is read; pnb_grid_check(g, stream) settles
+// both this sweep and a preceding pnb_grid_build_async_f32.
+extern "C" pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, int64_t n,
+                                                   const float *v, const float *mass,
+                                                   const float *pressure,
+                                                   const pnb_wcsph_params *params, float *dv,
+                                                   void *stream)
+{
+    if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    if (!is_fast_path(g, y, n, nullptr) || y != g->y_built) {
+        set_error("the stream-ordered sweep needs the coordinates of the last update! (x === y)");
+        return PNB_ERR_STATE;
+    }
+    t_async_sweep = true;
+    const pnb_status st = wcsph_interact_impl(g, y, n, y, n, nullptr, 0, 0, v, v, mass, mass, pressure,
+                                              pressure, params, dv, stream);
+    t_async_sweep = false;
+    return st;
 }

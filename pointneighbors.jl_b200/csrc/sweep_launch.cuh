@@ -3,6 +3,7 @@
 
 #include "sweep.cuh"
 #include "sweep_tiles.cuh"
+#include "sweep_flat.cuh"
 #include "hashgrid.cuh"
 
 namespace pnb {
@@ -11,6 +12,7 @@ extern int g_tune_wpc;    // pnb_set_tuning: warps per cell override (0 = closur
 extern int g_tune_half;   // pnb_set_tuning: 0 = exact Float32 test instead of the fp16 pre-filter
 extern int g_tune_twoset; // pnb_set_twoset_tiles: 0 = x != y always uses the per-point kernel
 extern int g_tune_left;   // pnb_set_sweep_left / PNB_SWEEP_LEFT: 0 never, 1 default, 2 always (tests)
+extern int g_tune_flat;   // pnb_set_sweep_kernel / PNB_SWEEP_FLAT: 1 (default) k_sweep_flat, 0 k_sweep_tiles
 
 template <class K>
 static pnb_status allow_smem(K kernel, size_t smem)
@@ -26,6 +28,123 @@ static pnb_status allow_smem(K kernel, size_t smem)
 // query cell list does not pay off
 constexpr int64_t kTwoSetMinPoints = 4096;
 constexpr double kTwoSetMinPerCell = 12.0;   // query points per occupied cell
+
+// exclusive prefix of the tiles per row segment (a few thousand entries): one block
+static __global__ void __launch_bounds__(1024)
+k_flat_scan(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0u;
+    __syncthreads();
+    for (int64_t i0 = 0; i0 < n; i0 += 1024) {
+        const int64_t i = i0 + threadIdx.x;
+        const uint32_t v = i < n ? in[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_w[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t base = s_run + s_w[warp];
+        if (i < n) out[i] = base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = base + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_run;
+}
+
+// The flat tile sweep over the cell layers [lay0, lay0 + n_lay) of the last used dimension
+// (0-based among the valid layers; all of them for an ordinary sweep, one part of a slab for the
+// overlapped multi-GPU step): tile table (3 small kernels), persistent sweep, overflow tiles.
+template <int ND, bool PER, class CL, bool TWO>
+static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsView &qry, int64_t n_q,
+                              const CL &cl, int lay0, int n_lay, cudaStream_t s)
+{
+    const int nxc = g->p.gs[0] - 2;
+    const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
+    if (ND == 1) { lay0 = 0; n_lay = 1; }
+    if (nxc <= 0 || n_lay <= 0 || n_q <= 0) return PNB_OK;
+    const int n_seg_row = (int)div_up(nxc, kFSegCells);
+    const int64_t rows = ND == 3 ? (int64_t)nyc * n_lay : (ND == 2 ? n_lay : 1);
+    const int64_t n_segs = (int64_t)n_seg_row * rows;
+    // non-empty tiles: at most one per query point, and at most the weighted length / 96 + 1 per segment
+    int64_t max_tiles = (n_q + (int64_t)kFMinW * nxc * rows) / kFTP + n_segs + 1;
+    if (max_tiles > n_q) max_tiles = n_q;
+    if (max_tiles > g->flat_tiles_cap) {
+        cudaFree(g->flat_tiles); cudaFree(g->flat_ovf);
+        g->flat_tiles = nullptr; g->flat_ovf = nullptr; g->flat_tiles_cap = 0;
+        const int64_t want = max_tiles + max_tiles / 8 + 64;
+        PNB_CUDA(cudaMalloc(&g->flat_tiles, sizeof(FlatTile) * (size_t)want));
+        PNB_CUDA(cudaMalloc(&g->flat_ovf, sizeof(int) * (size_t)want));
+        g->flat_tiles_cap = want;
+    }
+    if (n_segs > g->flat_seg_cap) {
+        cudaFree(g->flat_seg);
+        g->flat_seg = nullptr; g->flat_seg_cap = 0;
+        PNB_CUDA(cudaMalloc(&g->flat_seg, sizeof(uint32_t) * 2 * (size_t)(n_segs + 65)));
+        g->flat_seg_cap = n_segs + 64;
+    }
+    if (!g->flat_ctl) {
+        PNB_CUDA(cudaMalloc(&g->flat_ctl, sizeof(uint32_t) * kFlatCtl));
+        PNB_CUDA(cudaMemsetAsync(g->flat_ctl, 0, sizeof(uint32_t) * kFlatCtl, s));
+    }
+    uint32_t *seg_tiles = g->flat_seg, *seg_first = g->flat_seg + (g->flat_seg_cap + 1);
+    FlatTile *tiles = reinterpret_cast<FlatTile *>(g->flat_tiles);
+    constexpr int threads = kFG * flat_wpc<CL>() * 32;
+    constexpr size_t smem = flat_smem_bytes<ND, CL>();
+    auto kern = k_sweep_flat<ND, PER, CL, TWO>;
+    static int ctas_per_sm = 0;          // per instantiation
+    if (ctas_per_sm == 0) {
+        pnb_status st = allow_smem(kern, smem);
+        if (st != PNB_OK) return st;
+        int nb = 0;
+        PNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
+        if (nb < 1) { set_error("k_sweep_flat does not fit an SM (%zu bytes of shared memory)", smem); return PNB_ERR_CUDA; }
+        ctas_per_sm = nb;
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g->device);
+    const unsigned n_ctas = (unsigned)(n_sm * ctas_per_sm);
+    {
+        ProfScope ps(PH_SWEEP_TILES_PREP, s);
+        const unsigned pb = (unsigned)div_up(n_segs, 4);
+        k_flat_tiles<ND, false><<<pb, 128, 0, s>>>(g->p, qry, lay0, n_lay, n_seg_row, seg_tiles, seg_first,
+                                                   tiles, g->flat_ctl, n_ctas);
+        PNB_LAUNCHED();
+        k_flat_scan<<<1, 1024, 0, s>>>(seg_tiles, seg_first, n_segs);
+        PNB_LAUNCHED();
+        k_flat_tiles<ND, true><<<pb, 128, 0, s>>>(g->p, qry, lay0, n_lay, n_seg_row, seg_tiles, seg_first,
+                                                  tiles, g->flat_ctl, n_ctas);
+        PNB_LAUNCHED();
+    }
+    {
+        ProfScope ps(PH_SWEEP_CELLS, s);
+        kern<<<n_ctas, threads, smem, s>>>(g->p, cand, qry, cl, tiles, g->flat_ctl, g->flat_ovf);
+        PNB_LAUNCHED();
+    }
+    {
+        ProfScope ps(PH_SWEEP_OVERFLOW, s);
+        k_sweep_flat_overflow<ND, PER, CL, TWO><<<(unsigned)(n_sm * 8), 128, 0, s>>>(
+            g->p, cand, qry, cl, tiles, g->flat_ctl, g->flat_ovf);
+        PNB_LAUNCHED();
+    }
+    return PNB_OK;
+}
 
 template <int ND, bool PER, class CL>
 static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, int64_t n_loop,
@@ -61,6 +180,10 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
                 g->p, g->cell_start, g->sorted, cl);
             PNB_LAUNCHED();
             return PNB_OK;
+        }
+        if (g_tune_flat != 0) {
+            if (two) return launch_flat<ND, PER, CL, true>(g, cand, qry, n_loop, cl, 0, ND == 2 ? nyc : nzc, s);
+            return launch_flat<ND, PER, CL, false>(g, cand, qry, n_loop, cl, 0, ND == 2 ? nyc : nzc, s);
         }
         const int64_t blocks = (int64_t)div_up(nxc, kFTX) * nyc * nzc;
         if (blocks > g->ovf_cap) {

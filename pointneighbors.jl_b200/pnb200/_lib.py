@@ -91,6 +91,14 @@ SIGNATURES = {
     "pnb_grid_n_points": (_i64, [_vp]),
     "pnb_grid_layout": (C.c_int, [_vp]),
     "pnb_grid_build_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
+    "pnb_grid_build_async_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pnb_grid_check": (C.c_int, [_vp, _vp]),
+    "pnb_wcsph_interact_async_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp,
+                                               C.POINTER(WcsphParams), _vp, _vp]),
+    "pnb_hoststep_create": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
+    "pnb_hoststep_wcsph_submit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(WcsphParams), _vp]),
+    "pnb_hoststep_wait": (C.c_int, [_vp]),
+    "pnb_hoststep_destroy": (None, [_vp]),
     "pnb_point_cells_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_grid_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "pnb_grid_export_dvov": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, _vp]),
@@ -130,6 +138,7 @@ SIGNATURES = {
     "pnb_set_bucket_order": (None, [C.c_int]),
     "pnb_set_twoset_tiles": (None, [C.c_int]),
     "pnb_set_sweep_left": (None, [C.c_int]),
+    "pnb_set_sweep_kernel": (None, [C.c_int]),
     "pnb_profile_enable": (None, [C.c_int]),
     "pnb_profile_reset": (None, []),
     "pnb_profile_phases": (C.c_int, []),

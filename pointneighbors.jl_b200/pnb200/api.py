@@ -35,7 +35,7 @@ __all__ = [
     "SerialIncrementalUpdate", "DynamicVectorOfVectors",
     "PeriodicBox", "FullGridCellList", "SpatialHashingCellList", "spatial_hash",
     "GridNeighborhoodSearch", "PrecomputedNeighborhoodSearch",
-    "initialize_", "update_", "initialize", "update", "foreach_point_neighbor",
+    "initialize_", "update_", "check_", "HostStepper", "initialize", "update", "foreach_point_neighbor",
     "copy_neighborhood_search", "freeze_neighborhood_search", "requires_update",
     "search_radius", "ndims", "CountNeighbors", "NBodyGravity", "WCSPHInteract",
     "TLSPHDeformationGradient", "TLSPHInteract", "compute_pk1_corrected_", "compute_pressure_",
@@ -632,14 +632,92 @@ def initialize_(nhs, x, y, *, parallelization_backend=None, eachindex_y=None):
 
 
 def update_(nhs, x, y, *, points_moving=(True, True), parallelization_backend=None,
-            eachindex_y=None):
-    """update!(nhs, x, y; points_moving, eachindex_y)  (src/nhs_grid.jl:283-292)."""
+            eachindex_y=None, blocking=True):
+    """update!(nhs, x, y; points_moving, eachindex_y)  (src/nhs_grid.jl:283-292).
+
+    blocking=False (no reference counterpart; the reference synchronises after every launch,
+    src/util.jl:166-170): the rebuild is only enqueued on the current stream.  A domain error of
+    that build is raised by the next blocking call on the search (the sweep that follows, or
+    `check_(nhs)`); Float32 FullGridCellList searches only, everything else stays blocking."""
     if isinstance(nhs, PrecomputedNeighborhoodSearch):
         return nhs._update(x, y, points_moving, eachindex_y)
     # "Only update when the second set is moving." (nhs_grid.jl:289)
     if not points_moving[1]:
         return nhs
+    if not blocking and eachindex_y is None and nhs.eltype != np.float64:
+        y = _coords(y, nhs._ndims, nhs.eltype)
+        check(_lib.lib().pnb_grid_build_async_f32(nhs._grid(), y.data_ptr(), y.shape[0], _stream()))
+        nhs._y_ref = y
+        return nhs
     return initialize_(nhs, x, y, eachindex_y=eachindex_y)
+
+
+class HostStepper:
+    """The WCSPH step (update! + interact!) from HOST buffers, pipelined over three streams with
+    double-buffered device arrays (pnb_hoststep_*, include/pnb200.h): what a host-side caller of
+    the reference does per step -- copy coordinates and state to the device, update!, interact!,
+    copy dv back -- with the copies of neighbouring steps overlapping the kernels.
+
+        stepper = HostStepper(nhs, n_points)
+        stepper.submit(y_host, v_host, pressure_host, dv_host, params, mass_host=mass_host)
+        ...
+        stepper.wait()            # every dv_host passed so far is complete
+
+    Host arrays: contiguous float32 numpy arrays or CPU torch tensors (pin them for overlap)."""
+
+    def __init__(self, nhs, n_points: int):
+        if isinstance(nhs, PrecomputedNeighborhoodSearch) or nhs.eltype == np.float64:
+            raise ArgumentError("HostStepper needs a Float32 GridNeighborhoodSearch")
+        self.nhs = nhs
+        self.n = int(n_points)
+        h = C.c_void_p()
+        check(_lib.lib().pnb_hoststep_create(nhs._grid(), self.n, C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    @staticmethod
+    def _hptr(a, n_elems, what):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda or a.dtype != torch.float32 or not a.is_contiguous() or a.numel() != n_elems:
+                raise TypeError(f"{what}: contiguous float32 CPU tensor with {n_elems} elements expected")
+            return a.data_ptr()
+        a = np.asarray(a)
+        if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != n_elems:
+            raise TypeError(f"{what}: contiguous float32 array with {n_elems} elements expected")
+        return a.ctypes.data
+
+    def submit(self, y_host, v_host, pressure_host, dv_host, params, mass_host=None):
+        nd = self.nhs._ndims
+        n = self.n
+        prm = params.params if isinstance(params, WCSPHInteract) else params
+        self._keep = (self._keep + [(y_host, v_host, pressure_host, dv_host, mass_host)])[-3:]
+        check(_lib.lib().pnb_hoststep_wcsph_submit(
+            self._h, self._hptr(y_host, n * nd, "y_host"), self._hptr(v_host, n * (nd + 1), "v_host"),
+            None if mass_host is None else self._hptr(mass_host, n, "mass_host"),
+            self._hptr(pressure_host, n, "pressure_host"), C.byref(prm),
+            self._hptr(dv_host, n * (nd + 1), "dv_host")))
+
+    def wait(self):
+        check(_lib.lib().pnb_hoststep_wait(self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None:
+            try:
+                _lib.lib().pnb_hoststep_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def check_(nhs):
+    """Synchronise the current stream and raise what a blocking update! would have raised
+    (settles `update_(..., blocking=False)`)."""
+    if isinstance(nhs, PrecomputedNeighborhoodSearch) or nhs.eltype == np.float64:
+        return nhs
+    check(_lib.lib().pnb_grid_check(nhs._grid(), _stream()))
+    return nhs
 
 
 initialize = initialize_

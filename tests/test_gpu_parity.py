@@ -1198,3 +1198,93 @@ def test_neighbor_lists_one_pass_rebuilds(pn, oracle, periodic):
         assert np.array_equal(off, roff) and np.array_equal(ids, rids), k
         backend, lengths = pre.neighbor_lists(index_base=1)
         assert np.array_equal(lengths.cpu().numpy(), np.diff(roff)), k
+
+
+def test_live_neighbor_coords_semantics(pn, oracle):
+    """The reference's sweep reads neighbor_coords LIVE with the cell list of the last
+    initialize!/update! (src/nhs_grid.jl:543-548).  Passing another array than the one the search
+    was built from (same length, slightly moved points, no update!) must therefore give: old
+    cell list + new coordinates -- what the oracle computes when it is built from the old cloud
+    and swept with the new one.  A different number of points is a call-order error."""
+    c, r, mn, mx = pn.benchmark_cloud((18, 18, 18), seed=12)
+    rng = np.random.default_rng(4)
+    c2 = (c + np.float32(0.02) * r * rng.standard_normal(c.shape).astype(np.float32)).astype(np.float32)
+    nhs = make_grid(pn, 3, r, mn, mx, n_points=len(c))
+    x, x2 = dev(c), dev(c2)
+    pn.initialize_(nhs, x, x)
+    pn.update_(nhs, x, x, points_moving=(True, True))        # bucket layout
+    og = oracle.Grid(3, r, mn, mx)
+    og.build(c)
+    cnt = torch.zeros(len(c), dtype=torch.int64, device="cuda")
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x2, x2, nhs)
+    assert (cnt.cpu().numpy() == og.count_neighbors(c2, c2)).all()
+    # same contents in a new buffer: identical to the original array
+    x_copy = x.clone()
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x_copy, x_copy, nhs)
+    assert (cnt.cpu().numpy() == og.count_neighbors(c, c)).all()
+    # two-set: queries from one array, neighbours live from another
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x2, nhs)
+    assert (cnt.cpu().numpy() == og.count_neighbors(c, c2)).all()
+    pre = pn.PrecomputedNeighborhoodSearch[3](search_radius=r, n_points=len(c),
+                                              update_neighborhood_search=nhs, max_neighbors=200)
+    with pytest.raises(pn.PointNeighborsError, match="call update! first"):
+        pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x[:100].contiguous(), nhs)
+    del pre
+
+
+def test_stream_ordered_update(pn, oracle):
+    """update_(..., blocking=False): the one-pass build is only enqueued; results of the sweep
+    that follows equal the blocking path; a domain error is raised by the next blocking call;
+    a bucket overflow (a cell that outgrows the capacity chosen from the previous build) is
+    repaired invisibly: the library rebuilds and repeats the sweep."""
+    c, r, mn, mx = pn.benchmark_cloud((20, 20, 20), seed=3)
+    nhs = make_grid(pn, 3, r, mn, mx, n_points=len(c))
+    x = dev(c)
+    pn.initialize_(nhs, x, x)
+    og = oracle.Grid(3, r, mn, mx)
+    rng = np.random.default_rng(5)
+    cnt = torch.zeros(len(c), dtype=torch.int64, device="cuda")
+    for step in range(4):
+        c = (c + np.float32(0.05) * r * rng.standard_normal(c.shape).astype(np.float32)).astype(np.float32)
+        c = np.clip(c, mn, mx).astype(np.float32)
+        x = dev(c)
+        pn.update_(nhs, x, x, points_moving=(True, True), blocking=False)
+        pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x, x, nhs)
+        og.build(c)
+        assert (cnt.cpu().numpy() == og.count_neighbors(c, c)).all()
+        assert nhs.layout() == "buckets"
+    cs, cp = nhs.export_csr()
+    assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
+    # bucket overflow: 200 points moved into one cell
+    c2 = c.copy()
+    c2[:200] = c[0] + np.float32(1e-4) * r * rng.standard_normal((200, 3)).astype(np.float32)
+    c2 = np.clip(c2, mn, mx).astype(np.float32)
+    x2 = dev(c2)
+    pn.update_(nhs, x2, x2, points_moving=(True, True), blocking=False)
+    v, mass, pressure, kw = _wcsph_inputs(pn, c2, r, 3)
+    tv, tm, tp = dev(v), dev(mass), dev(pressure)
+    dv = torch.zeros((len(c2), 4), dtype=torch.float32, device="cuda")
+    f = pn.WCSPHInteract(dv, tv, tv, tm, tm, tp, tp, **kw)
+    pn.foreach_point_neighbor(f, x2, x2, nhs)          # runs on the overflowed list, is repeated
+    og.build(c2)
+    _, ref64, refabs = og.wcsph(c2, c2, v, v, mass, mass, pressure, pressure, f.params_array(), wide=True)
+    assert np.all(np.abs(dv.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30)
+    pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x2, x2, nhs)
+    assert (cnt.cpu().numpy() == og.count_neighbors(c2, c2)).all()
+    # the same through an export instead of a sweep
+    pn.update_(nhs, x, x, points_moving=(True, True))
+    pn.update_(nhs, x2, x2, points_moving=(True, True), blocking=False)
+    cs, cp = nhs.export_csr()
+    assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
+    # domain error: raised by the next blocking call
+    c3 = c.copy()
+    c3[7] = mx + np.float32(5.0) * r
+    x3 = dev(c3)
+    pn.update_(nhs, x, x, points_moving=(True, True))
+    pn.update_(nhs, x3, x3, points_moving=(True, True), blocking=False)
+    with pytest.raises(pn.PointNeighborsError, match="outside the domain bounds"):
+        pn.foreach_point_neighbor(pn.CountNeighbors(cnt), x3, x3, nhs)
+    pn.update_(nhs, x, x, points_moving=(True, True))
+    pn.update_(nhs, x3, x3, points_moving=(True, True), blocking=False)
+    with pytest.raises(pn.PointNeighborsError, match="outside the domain bounds"):
+        pn.check_(nhs)

@@ -22,6 +22,7 @@ ap.add_argument("--moving", action="store_true", help="non-zero velocities (visc
 ap.add_argument("--wpc", type=int, default=0, help="warps per cell override (2 or 4)")
 ap.add_argument("--build", type=int, default=25, help="build kernel variant bits")
 ap.add_argument("--half", type=int, default=-1, help="0 = exact Float32 test instead of the fp16 pre-filter")
+ap.add_argument("--flat", type=int, default=1, help="1 = k_sweep_flat (default), 0 = k_sweep_tiles of round 1")
 args = ap.parse_args()
 n = args.lattice
 T = np.float32
@@ -45,6 +46,7 @@ cl = {
                               sound_speed=T(10.0)),
 }
 _lib.lib().pnb_set_tuning(args.wpc, args.half)
+_lib.lib().pnb_set_sweep_kernel(args.flat)
 _lib.lib().pnb_set_build_tuning(args.build)
 pn.initialize_(nhs, A, A)
 pn.foreach_point_neighbor(cl["count"], A, A, nhs)
