@@ -531,13 +531,20 @@ def gpu_arm(args):
         assert oracle_check["equal"], "GPU pair counts differ from the oracle"
         del og, cB
 
-    def step(s):
+    # The timed loop uses the stream-ordered forms of both calls (update_(..., blocking=False),
+    # foreach_point_neighbor(..., blocking=False)): every step is only enqueued, check_(nhs) after
+    # the loop synchronises and reads the error word of the whole chain.  The blocking forms (the
+    # reference's semantics) are timed next to it (`blocking` in the JSON line).
+    def step(s, blocking=False):
         y = coords[(s + 1) % 2]
-        pn.update_(nhs, y, y, points_moving=(True, True), blocking=False)
-        pn.foreach_point_neighbor(closure, y, y, nhs)
+        pn.update_(nhs, y, y, points_moving=(True, True), blocking=blocking)
+        pn.foreach_point_neighbor(closure, y, y, nhs, blocking=blocking)
 
     for s in range(args.warmup):
+        step(s, blocking=True)
+    for s in range(2):
         step(s)
+    pn.check_(nhs)
     torch.cuda.synchronize()
     _lib.profile(enable=True, reset=True)
     _lib.profile(reset=True)
@@ -555,9 +562,10 @@ def gpu_arm(args):
         upd_ev[s][0].record()
         pn.update_(nhs, y, y, points_moving=(True, True), blocking=False)
         upd_ev[s][1].record()
-        pn.foreach_point_neighbor(closure, y, y, nhs)
+        pn.foreach_point_neighbor(closure, y, y, nhs, blocking=False)
         total_pairs += pairs[(s + 1) % 2]
     ev1.record()
+    pn.check_(nhs)
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
@@ -565,8 +573,16 @@ def gpu_arm(args):
     prof = _lib.profile(enable=False)
     update_ms = float(np.mean([a.elapsed_time(b) for a, b in upd_ev]))
     value = total_pairs / (ms_total * 1e-3)
-    # the blocking form of update! (the reference's semantics) for comparison
+    # the blocking forms of both calls (the reference's semantics) for comparison
     ub_min, ub_med = timed_events(lambda: pn.update_(nhs, A, A, points_moving=(True, True)), 10)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b_steps = max(2, min(args.steps, 6))
+    b0.record()
+    for s in range(b_steps):
+        step(s, blocking=True)
+    b1.record()
+    torch.cuda.synchronize()
+    blocking_ms = b0.elapsed_time(b1) / b_steps
 
     # ---- the same step with non-zero velocities (viscosity branch active) ----------------------
     vm, _, _ = wcsph_state_torch(N, r, 3, dev, moving=True)
@@ -617,9 +633,11 @@ def gpu_arm(args):
         yl = coords[e2e_steps % 2]
         pn.update_(nhs, yl, yl)
         pn.foreach_point_neighbor(closure, yl, yl, nhs)
-        ref_dv = dv.cpu()
-        got_dv = hdv[(e2e_steps - 1) % 2]
-        e2e_same = bool(torch.allclose(ref_dv, got_dv, rtol=1e-4, atol=1e-6))
+        ref_dv = dv.cpu().double()
+        got_dv = hdv[(e2e_steps - 1) % 2].double()
+        # same kernels, but the order of the records inside a cell (atomic arrival order of the
+        # one-pass build) differs from run to run: equal up to summation order
+        e2e_same = bool(((ref_dv - got_dv).norm() <= 1e-5 * ref_dv.norm()).item())
     except Exception:
         pass
     # one step alone (latency): submit + wait
@@ -665,6 +683,9 @@ def gpu_arm(args):
                            "pairs_oracle_check": oracle_check, "git": git_head()},
         "update_ms": update_ms,
         "update_ms_blocking_call": ub_med,
+        "calls": "stream-ordered (update_ / foreach_point_neighbor with blocking=False, check_ after the "
+                 "loop); blocking = the same steps with the blocking calls of the reference's semantics",
+        "blocking": {"ms_per_step": blocking_ms, "value": P_avg / (blocking_ms * 1e-3)},
         "interact_ms": (ms_total / args.steps) - update_ms,
         "moving": {"what": "same step with velocities ~ N(0, 0.1^2): the viscosity branch runs for "
                            "approaching pairs (two more MUFU per pair)",
@@ -702,7 +723,7 @@ def gpu_arm(args):
                             "per_kernel_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in build_names},
                             "call_ms": update_ms,
                             "call": "update_(nhs, y, y, blocking=False): stream-ordered, CUDA events around "
-                                    "the call; the error word is read by the blocking sweep that follows",
+                                    "the call inside the step loop; the error word is read by check_ after it",
                             "layout": "buckets (one pass)" if "k_bucket_scatter" in build_names
                                       else "CSR (two passes)"},
         "kernel_ms": {k: (v_[0] / v_[1] if v_[1] else 0.0) for k, v_ in prof.items()},

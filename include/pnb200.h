@@ -140,6 +140,24 @@ pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndi
                                int64_t n_recv_down, const float *send_up, int64_t n_up,
                                const float *send_down, int64_t n_down, int32_t *scratch,
                                int64_t *out, void *stream);
+/* Overlapped step: the received rows are appended behind the n_own owned points WITHOUT filling the
+ * holes of the leavers (the ids of the owned points stay valid for the sweep that is already
+ * running); flags[n_own + r] = 1 for a row that now belongs to this slab (migrant), 0 for a ghost.
+ * counters_dev (>= 4 int32, zeroed by the call): [0] migrants, [1] != 0 if a migrant landed `depth`
+ * or more layers inside the slab (the interior sweep missed it: repeat the step without overlap). */
+pnb_status pnb_slab_append_f32(const pnb_slab_arrays *arrays, int64_t n_own, int ndims,
+                               float padded_min_z, float cell_size_z, int64_t z_lo, int64_t z_hi,
+                               int64_t depth, const float *recv_up, int64_t n_recv_up,
+                               const float *recv_down, int64_t n_recv_down, uint8_t *flags,
+                               int32_t *counters_dev, void *stream);
+/* End of the overlapped step: owned points [0, n_own) minus the n_leave leavers (leave_idx of
+ * pnb_slab_pack_f32) plus the n_mig migrants among the n_app appended rows become the owned points
+ * [0, n_own - n_leave + n_mig): holes are filled with owned rows from behind.  Every array is
+ * permuted alike.  scratch: >= 2 * (n_leave + n_app + 8) int32. */
+pnb_status pnb_slab_compact_f32(const pnb_slab_arrays *arrays, int64_t n_own, int64_t n_app,
+                                const int32_t *leave_idx, int64_t n_leave, int64_t n_mig,
+                                uint8_t *flags, int32_t *scratch, int32_t *counters_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * GridNeighborhoodSearch{NDIMS}(; search_radius, periodic_box,
  *                               cell_list = SpatialHashingCellList{NDIMS}(; list_size))
@@ -240,8 +258,10 @@ void pnb_set_twoset_tiles(int on);
  * 2 = always when the closure allows it (tests).  Same results. */
 void pnb_set_sweep_left(int mode);
 /* Tile sweep kernel: 1 (default) = k_sweep_flat (tiles are ranges of 96 points, full warps,
- * persistent CTAs), 0 = k_sweep_tiles of round 1 (tiles are 4 cells, one warp
- * group per cell), kept for A/B measurements.  Same results. */
+ * persistent CTAs) for the closures with a drain (n-body, WCSPH, list fills) and
+ * k_sweep_tiles of round 1 (tiles are 4 cells, one warp group per cell) for the count-only
+ * closures, which it serves faster; 2 = always k_sweep_flat, 0 = always k_sweep_tiles (A/B
+ * measurements, tests).  Same results. */
 void pnb_set_sweep_kernel(int flat);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
@@ -297,6 +317,23 @@ pnb_status pnb_wcsph_interact_f32(pnb_grid *g, const float *x, int64_t nx, const
 pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, int64_t n, const float *v,
                                         const float *mass, const float *pressure,
                                         const pnb_wcsph_params *params, float *dv, void *stream);
+
+/* The pieces of the OVERLAPPED multi-GPU step (pnb200/slabs.py; no reference
+ * counterpart, the reference is single-device).  Per step and rank: pack the boundary rows, start
+ * the NCCL exchange on a side stream, pnb_grid_build_async_f32 of the owned points, sweep the
+ * interior cell layers (pnb_wcsph_interact_layers_async_f32) while the rows travel,
+ * pnb_slab_append_f32 + pnb_grid_append_f32 of what arrived, sweep the boundary layers,
+ * pnb_grid_check, pnb_slab_compact_f32.
+ *   pnb_grid_append_f32: the points y[first .. first + n_more) join the bucket cell list built from
+ *     y[0 .. first) (ids first + k); y must be the array of that build.
+ *   pnb_wcsph_interact_layers_async_f32: gather the payload of the cell layers [gz_a, gz_b], then
+ *     sweep the layers [cz_a, cz_b] (local 1-based cell coordinates of the last dimension); dv is
+ *     zeroed first when zero_dv != 0.  Nothing is synchronised. */
+pnb_status pnb_grid_append_f32(pnb_grid *g, const float *y, int64_t first, int64_t n_more, void *stream);
+pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const float *y, int64_t n, const float *v,
+                                               const float *mass, const float *pressure,
+                                               const pnb_wcsph_params *params, float *dv, int cz_a,
+                                               int cz_b, int gz_a, int gz_b, int zero_dv, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The WCSPH step from HOST buffers, pipelined (the end-to-end call of a host-side caller).
@@ -420,7 +457,8 @@ pnb_status pnb_profile_get(int phase, double *total_ms, int64_t *launches);
  * the API -- constructors, initialize!/update!, neighbour counts, neighbour lists, pair geometry --
  * with the reference's arithmetic evaluated in Float64 (the reference is generic in the element
  * type, src/nhs_grid.jl:60-65).  The list handle and all exports are shared with Float32; the
- * fused SPH closures exist in Float32 only.
+ * fused n-body / WCSPH closures exist in Float64 too (one thread per point, bit-exact); the TLSPH
+ * closures are Float32 only.
  * ------------------------------------------------------------------------------------------- */
 pnb_status pnb_grid_params_f64(int ndims, double search_radius, const double *min_corner,
                                const double *max_corner, const double *box_min,
@@ -439,6 +477,22 @@ pnb_status pnb_point_cells_f64(const pnb_grid *g, const double *x, int64_t n, in
 pnb_status pnb_count_neighbors_f64(pnb_grid *g, const double *x, int64_t nx, const double *y,
                                    int64_t n, const int32_t *points, int64_t n_points,
                                    int index_base, int64_t *out, void *stream);
+/* The fused n-body / WCSPH closures in Float64 (the reference is generic in the element type and
+ * publishes Float64 WCSPH numbers, benchmarks/plot_benchmarks.jl:67): every array double, every
+ * operation the IEEE double operation of the Julia closure in its order, candidates visited in
+ * the reference's order -> sums bit-identical to the Float64 oracle.  One thread per point. */
+pnb_status pnb_nbody_f64(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                         const int32_t *points, int64_t n_points, int index_base, const double *mass,
+                         double G, double *dv, void *stream);
+typedef struct pnb_wcsph_params_f64 {
+    double smoothing_length, sound_speed, alpha, beta, epsilon, delta, kernel_norm;
+} pnb_wcsph_params_f64;
+pnb_status pnb_wcsph_interact_f64(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                                  const int32_t *points, int64_t n_points, int index_base,
+                                  const double *v_x, const double *v_y, const double *mass_x,
+                                  const double *mass_y, const double *pressure_x,
+                                  const double *pressure_y, const pnb_wcsph_params_f64 *params,
+                                  double *dv, void *stream);
 pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
                                int sort, pnb_nlist **out, void *stream);
 pnb_status pnb_nlist_pairs_f64(const pnb_nlist *list, const pnb_grid *g, const double *x,

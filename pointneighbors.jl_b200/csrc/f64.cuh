@@ -147,6 +147,145 @@ k_sweep_points64(GridP64 g, const uint32_t *__restrict__ cell_start,
     if (MODE == 0) out_count[i] = cnt;
     if (MODE == 1) list_count[i] = (uint32_t)cnt;
 }
+
+// Fused closures in Float64 (the reference is generic in the element type and publishes Float64
+// WCSPH numbers, benchmarks/plot_benchmarks.jl:67): one thread per query point, candidates in the
+// reference's order (3^d cells in CartesianIndices order, ids ascending inside a cell), every
+// operation an explicit IEEE double operation in the oracle's order (pno_cl_nbody / pno_cl_wcsph
+// instantiated for double) -> sums bit-identical to the Float64 oracle.  Per-point state is read
+// by id straight from the caller's arrays.
+struct Wcsph64P {
+    double h, sound_speed, alpha, beta, epsilon, delta, kernel_norm;
+};
+//   KIND 0: n-body   (benchmarks/n_body.jl:38-48)            state: mass[n], out dv[nx x nd]
+//   KIND 1: WCSPH    (smoothed_particle_hydrodynamics.jl:45-102)  state: v (nd+1), mass, pressure
+template <int ND, int KIND>
+__global__ void __launch_bounds__(128)
+k_sweep_closure64(GridP64 g, const uint32_t *__restrict__ cell_start,
+                  const Rec64 *__restrict__ sorted, const double *__restrict__ x, int64_t n_loop,
+                  const int32_t *__restrict__ points, int base, const double *__restrict__ v_x,
+                  const double *__restrict__ v_y, const double *__restrict__ mass_y,
+                  const double *__restrict__ p_x, const double *__restrict__ p_y, double G,
+                  Wcsph64P prm, double *__restrict__ dv, int *__restrict__ err)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_loop) return;
+    const int64_t i = points ? (int64_t)points[t] - base : t;
+    constexpr int NS = ND + 1;
+    const double sqrt_eps = 1.4901161193847656e-8;
+    double xi[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; d++) xi[d] = x[i * ND + d];
+    int cc[3] = {1, 1, 1};
+#pragma unroll
+    for (int d = 0; d < ND; d++) cc[d] = cell_coord64(xi[d], g.minc[d], g.cs[d], g.periodic, g.nc[d]);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double va[4] = {0.0, 0.0, 0.0, 0.0}, p_a = 0.0;
+    if (KIND == 1) {
+#pragma unroll
+        for (int k = 0; k < NS; k++) va[k] = v_x[i * NS + k];
+        p_a = p_x[i];
+    }
+    bool oob = false;
+    for (int oz = (ND > 2 ? -1 : 0); oz <= (ND > 2 ? 1 : 0); oz++)
+        for (int oy = (ND > 1 ? -1 : 0); oy <= (ND > 1 ? 1 : 0); oy++)
+            for (int ox = -1; ox <= 1; ox++) {
+                int c0 = cc[0] + ox, c1 = cc[1] + oy, c2 = cc[2] + oz;
+                if (g.periodic) {
+                    c0 = floormod_i(c0 - 2, g.nc[0]) + 2;
+                    if (ND > 1) c1 = floormod_i(c1 - 2, g.nc[1]) + 2;
+                    if (ND > 2) c2 = floormod_i(c2 - 2, g.nc[2]) + 2;
+                }
+                if (c0 < 1 || c0 > g.gs[0] || c1 < 1 || c1 > g.gs[1] || c2 < 1 || c2 > g.gs[2]) {
+                    oob = true;
+                    continue;
+                }
+                const int lin = (c0 - 1) + (c1 - 1) * g.gs[0] + (c2 - 1) * g.gs[0] * g.gs[1];
+                const uint32_t b0 = cell_start[lin], b1 = cell_start[lin + 1];
+                for (uint32_t kk = b0; kk < b1; kk++) {
+                    const Rec64 yj = sorted[kk];
+                    double p[3];
+                    const double d2 = pair_d2_64<ND>(g, xi, yj, p, true);
+                    if (!(d2 <= g.r2)) continue;
+                    const double d = __dsqrt_rn(d2);
+                    const int64_t j = yj.id;
+                    if (KIND == 0) {
+                        if (d < sqrt_eps) continue;
+                        const double tt = __dmul_rn(-G, mass_y[j]);
+                        const double d3 = __dmul_rn(__dmul_rn(d, d), d);
+#pragma unroll
+                        for (int k = 0; k < ND; k++)
+                            acc[k] = __dadd_rn(acc[k], __ddiv_rn(__dmul_rn(tt, p[k]), d3));
+                    } else {
+                        double vb[4];
+#pragma unroll
+                        for (int k = 0; k < NS; k++) vb[k] = v_y[j * NS + k];
+                        const double rho_a = va[ND], rho_b = vb[ND];
+                        const double rho_mean = __dmul_rn(0.5, __dadd_rn(rho_a, rho_b));
+                        const double m_b = mass_y[j], p_b = p_y[j];
+                        const bool far = !(d < sqrt_eps);
+                        double grad[3] = {0.0, 0.0, 0.0};
+                        if (far) {
+                            const double q = __ddiv_rn(d, prm.h);
+                            double w = 0.0;
+                            if (q < 2.0) {
+                                const double t1 = __dsub_rn(1.0, __dmul_rn(q, 0.5));
+                                w = __dmul_rn(__dmul_rn(-5.0, q), __dmul_rn(__dmul_rn(t1, t1), t1));
+                            }
+                            const double dw = __dmul_rn(__ddiv_rn(prm.kernel_norm, prm.h), w);
+                            const double sg = __ddiv_rn(dw, d);
+#pragma unroll
+                            for (int k = 0; k < ND; k++) grad[k] = __dmul_rn(sg, p[k]);
+                        }
+                        const double pf = __ddiv_rn(__dmul_rn(-m_b, __dadd_rn(p_a, p_b)), __dmul_rn(rho_a, rho_b));
+                        double vdiff[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int k = 0; k < ND; k++) vdiff[k] = __dsub_rn(va[k], vb[k]);
+                        double vr = __dmul_rn(vdiff[0], p[0]);
+#pragma unroll
+                        for (int k = 1; k < ND; k++) vr = __dadd_rn(vr, __dmul_rn(vdiff[k], p[k]));
+                        double visc = 0.0;
+                        if (vr < 0.0) {
+                            const double mu = __ddiv_rn(__dmul_rn(prm.h, vr),
+                                                        __dadd_rn(__dmul_rn(d, d), __dmul_rn(prm.epsilon, __dmul_rn(prm.h, prm.h))));
+                            const double pi_ab = __ddiv_rn(
+                                __dsub_rn(__dmul_rn(__dmul_rn(prm.alpha, prm.sound_speed), mu),
+                                          __dmul_rn(prm.beta, __dmul_rn(mu, mu))), rho_mean);
+                            visc = __dmul_rn(m_b, pi_ab);
+                        }
+#pragma unroll
+                        for (int k = 0; k < ND; k++)
+                            acc[k] = __dadd_rn(acc[k], __dadd_rn(__dmul_rn(pf, grad[k]), __dmul_rn(visc, grad[k])));
+                        double vg = __dmul_rn(vdiff[0], grad[0]);
+#pragma unroll
+                        for (int k = 1; k < ND; k++) vg = __dadd_rn(vg, __dmul_rn(vdiff[k], grad[k]));
+                        double drho = __dmul_rn(__dmul_rn(__ddiv_rn(rho_a, rho_b), m_b), vg);
+                        if (far) {
+                            const double vol_b = __ddiv_rn(m_b, rho_b);
+                            const double two_drho = __dmul_rn(2.0, __dsub_rn(rho_a, rho_b));
+                            const double dd = __dmul_rn(d, d);
+                            double pg = 0.0;
+#pragma unroll
+                            for (int k = 0; k < ND; k++) {
+                                const double psi = __ddiv_rn(__dmul_rn(two_drho, p[k]), dd);
+                                pg = (k == 0) ? __dmul_rn(psi, grad[k]) : __dadd_rn(pg, __dmul_rn(psi, grad[k]));
+                            }
+                            drho = __dadd_rn(drho, __dmul_rn(__dmul_rn(__dmul_rn(prm.delta, prm.h), prm.sound_speed),
+                                                             __dmul_rn(pg, vol_b)));
+                        }
+                        acc[ND] = __dadd_rn(acc[ND], drho);
+                    }
+                }
+            }
+    if (oob) atomicOr(err, 2);
+    if (KIND == 0) {
+#pragma unroll
+        for (int k = 0; k < ND; k++) dv[i * ND + k] = acc[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NS; k++) dv[i * NS + k] = acc[k];
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace pnb

@@ -118,6 +118,7 @@ static pnb_status settle_async_build(pnb_grid *g, bool *rebuilt)
     g->async_pending = false;
     const int e = *(volatile int *)g->h_err;
     if ((e & 8) == 0) {
+        g->async_chain = 0;
         if (e & 1) {       // domain error of the build: like the blocking build, the list is unusable
             *(volatile int *)g->h_err = 0;
             g->n_built = 0;
@@ -131,6 +132,17 @@ static pnb_status settle_async_build(pnb_grid *g, bool *rebuilt)
     g->bucket_K = 0;
     g->bcount_alt_clean = false;
     *rebuilt = true;
+    if (g->async_chain > 1) {
+        // several stream-ordered steps were chained without a check: the overflow may have
+        // happened in any of them, their sweeps cannot be repeated
+        const int chain = g->async_chain;
+        g->async_chain = 0;
+        pnb_grid_build_f32(g, (const float *)g->y_built, g->n_y_built, nullptr, 0, 0, (void *)g->async_stream);
+        set_error("a bucket of the one-pass update! overflowed inside a chain of %d stream-ordered "
+                  "steps: their results are invalid (check every step, or use the blocking update!)", chain);
+        return PNB_ERR_STATE;
+    }
+    g->async_chain = 0;
     return pnb_grid_build_f32(g, (const float *)g->y_built, g->n_y_built, nullptr, 0, 0,
                               (void *)g->async_stream);
 }
@@ -1442,6 +1454,12 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t C = g->p.total_cells;
     if (eachindex_y == nullptr) n_idx = n;
+    if (g->async_pending && t_async_build && g->async_stream == s && g->bucket_K > 0 &&
+        eachindex_y == nullptr && n > 0) {
+        // stream-ordered update! after stream-ordered update!: the error word keeps collecting
+        // bits until somebody looks (settle_async_build knows the length of the chain)
+        g->async_pending = false;
+    }
     if (g->async_pending) {
         // a stream-ordered update! nobody looked at: its error word must not leak into this build
         PNB_CUDA(cudaStreamSynchronize(g->async_stream));
@@ -1560,6 +1578,7 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
             g->built = true;
             g->async_pending = true;
             g->async_stream = s;
+            g->async_chain++;
             return PNB_OK;
         }
         PNB_CUDA(cudaStreamSynchronize(s));     // initialize!/update! are blocking calls
@@ -1661,6 +1680,76 @@ extern "C" pnb_status pnb_grid_build_async_f32(pnb_grid *g, const float *y, int6
     const pnb_status st = pnb_grid_build_f32(g, y, n, nullptr, 0, 0, stream);
     t_async_build = false;
     return st;
+}
+
+// ---- append to the bucket layout (overlapped multi-GPU step) -----------------------
+// The points y[first .. first + n_more) join the cell list of the current one-pass build with
+// ids first + k: the migrants and ghosts that arrive from the neighbouring slabs while the
+// interior layers are already being swept.  One point per thread, the lanes of a warp that hit
+// the same cell share one atomic.
+namespace pnb {
+template <int ND>
+__global__ void __launch_bounds__(256)
+k_bucket_append(GridP g, BuildP bp, const float *__restrict__ y, int64_t first, int64_t n_more,
+                uint32_t K, uint32_t *__restrict__ bcount, float4 *__restrict__ brec,
+                int *__restrict__ err)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = k < n_more;
+    float p[3] = {0.f, 0.f, 0.f};
+    if (in) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) p[d] = __ldg(y + (first + k) * ND + d);
+    }
+    const int lin = in ? point_cell_fast<ND, false, false>(g, bp, p) : -1;
+    int bad = (in && lin < 0) ? 1 : 0;
+    const unsigned m = __match_any_sync(0xffffffffu, lin);
+    const int head = __ffs(m) - 1;
+    unsigned base = 0u;
+    if (lin >= 0 && head == lane_id()) base = atomicAdd(bcount + lin, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, head);
+    if (lin >= 0) {
+        const unsigned slot = base + (unsigned)__popc(m & ((1u << lane_id()) - 1u));
+        if (slot < K) brec[(size_t)lin * K + slot] = make_float4(p[0], p[1], p[2], __int_as_float((int)(first + k)));
+        else bad |= 8;
+    }
+    if (bad) atomicOr(err, bad);
+}
+}  // namespace pnb
+
+extern "C" pnb_status pnb_grid_append_f32(pnb_grid *g, const float *y, int64_t first, int64_t n_more,
+                                          void *stream)
+{
+    if (!g || g->f64 || g->hashed || g->p.periodic) {
+        set_error("pnb_grid_append_f32 needs a Float32 non-periodic FullGridCellList search");
+        return PNB_ERR_ARG;
+    }
+    if (!g->built || !g->bucket_valid || g->bucket_tr || y != g->y_built || first != g->n_y_built ||
+        !g->full_build) {
+        set_error("pnb_grid_append_f32: the cell list must be the one-pass (bucket) build of the "
+                  "first `first` points of the same array");
+        return PNB_ERR_STATE;
+    }
+    if (first + n_more > 0x7ffffff0LL) { set_error("more than 2^31 points are not supported"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_more > 0) {
+        BuildP bp;
+        for (int d = 0; d < 3; d++) { volatile float rc = 1.0f / g->p.cs[d]; bp.rcs[d] = rc; }
+        ProfScope ps(PH_BUILD_BUCKET, s);
+        const unsigned nb = (unsigned)div_up(n_more, 256);
+        switch (g->p.ndims) {
+            case 1: k_bucket_append<1><<<nb, 256, 0, s>>>(g->p, bp, y, first, n_more, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+            case 2: k_bucket_append<2><<<nb, 256, 0, s>>>(g->p, bp, y, first, n_more, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+            default: k_bucket_append<3><<<nb, 256, 0, s>>>(g->p, bp, y, first, n_more, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err); break;
+        }
+        PNB_LAUNCHED();
+    }
+    g->n_built += n_more;
+    g->n_y_built = first + n_more;
+    g->canonical = false;
+    g->csr_valid = false;
+    if (!g->async_pending) return check_err_word(g, s) == PNB_OK ? PNB_OK : PNB_ERR_DOMAIN;
+    return PNB_OK;
 }
 
 extern "C" pnb_status pnb_grid_check(pnb_grid *g, void *stream)
@@ -2111,6 +2200,133 @@ extern "C" pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t
     return PNB_OK;
 }
 
+// ---- slab bookkeeping of the overlapped step ----------------------------------------------------
+namespace pnb {
+// received rows -> arrays[n_own + r]; flag = 1 if the row now belongs to this slab (migrant),
+// 0 = ghost.  counters[0] += migrants; counters[1] |= 1 if a migrant landed deeper than `depth`
+// layers inside the slab (the interior layers were swept without it: the caller must repeat).
+__global__ void __launch_bounds__(256)
+k_slab_append(pnb_slab_arrays A, int W, int nd, int64_t n_own, const float *__restrict__ rows_a,
+              int64_t n_a, const float *__restrict__ rows_b, int64_t n_b, float pmin, float cs,
+              long long z_lo, long long z_hi, long long depth, unsigned char *__restrict__ flags,
+              int32_t *__restrict__ counters)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool mig = false, deep = false;
+    if (r < n_a + n_b) {
+        const float *row = r < n_a ? rows_a + r * W : rows_b + (r - n_a) * W;
+        const int64_t i = n_own + r;
+        int col = 0;
+        for (int a = 0; a < A.n_arrays; a++) {
+            const int w = A.width[a];
+            for (int k = 0; k < w; k++) A.ptr[a][i * w + k] = row[col + k];
+            col += w;
+        }
+        const long long cz = slab_layer(row[nd - 1], pmin, cs);
+        mig = cz >= z_lo && cz <= z_hi;
+        deep = mig && cz >= z_lo + depth && cz <= z_hi - depth;
+        flags[i] = mig ? 1 : 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mig);
+    if (m && lane_id() == __ffs(m) - 1) atomicAdd(counters + 0, __popc(m));
+    if (__any_sync(0xffffffffu, deep) && lane_id() == 0) atomicOr(counters + 1, 1);
+}
+
+__global__ void k_slab_clear_flags(const int32_t *__restrict__ leave, int64_t n_leave,
+                                   unsigned char *__restrict__ flags)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_leave) flags[leave[r]] = 0;
+}
+// holes: rows below n_new that are not owned; movers: owned rows at or above n_new
+__global__ void __launch_bounds__(256)
+k_slab_compact_lists(const unsigned char *__restrict__ flags, int64_t n_rows, int64_t n_new,
+                     int32_t *__restrict__ holes, int32_t *__restrict__ movers, int64_t cap,
+                     int32_t *__restrict__ counters)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n_rows;
+    const bool own = in && flags[i] != 0;
+    warp_append(in && !own && i < n_new, (int32_t)i, holes, cap, counters + 2);
+    warp_append(own && i >= n_new, (int32_t)i, movers, cap, counters + 3);
+}
+__global__ void k_slab_compact_move(pnb_slab_arrays A, const int32_t *__restrict__ holes,
+                                    const int32_t *__restrict__ movers,
+                                    const int32_t *__restrict__ counters)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= counters[2]) return;        // counters[2] == counters[3] by construction
+    const int64_t h = holes[r], f = movers[r];
+    for (int a = 0; a < A.n_arrays; a++) {
+        const int w = A.width[a];
+        for (int k = 0; k < w; k++) A.ptr[a][h * w + k] = A.ptr[a][f * w + k];
+    }
+}
+}  // namespace pnb
+
+// Received rows appended behind the owned points (no hole filling: the ids of the owned points
+// stay valid for the sweep that is already running).  counters_dev: >= 4 int32, zeroed here;
+// after the call counters_dev[0] = migrants among the rows, counters_dev[1] = 1 if one of them
+// lies deeper than `depth` layers inside the slab.
+extern "C" pnb_status pnb_slab_append_f32(const pnb_slab_arrays *arrays, int64_t n_own, int ndims,
+                                          float padded_min_z, float cell_size_z, int64_t z_lo,
+                                          int64_t z_hi, int64_t depth, const float *recv_up,
+                                          int64_t n_recv_up, const float *recv_down,
+                                          int64_t n_recv_down, uint8_t *flags, int32_t *counters_dev,
+                                          void *stream)
+{
+    if (!arrays || arrays->n_arrays < 1 || arrays->n_arrays > 8 || arrays->width[0] != ndims || !flags ||
+        !counters_dev) {
+        set_error("pnb_slab_append_f32: bad arguments");
+        return PNB_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PNB_CUDA(cudaMemsetAsync(counters_dev, 0, 4 * sizeof(int32_t), s));
+    const int64_t n = n_recv_up + n_recv_down;
+    if (n > 0) {
+        int W = 0;
+        for (int a = 0; a < arrays->n_arrays; a++) W += arrays->width[a];
+        k_slab_append<<<(unsigned)div_up(n, 256), 256, 0, s>>>(
+            *arrays, W, ndims, n_own, recv_up, n_recv_up, recv_down, n_recv_down, padded_min_z,
+            cell_size_z, (long long)z_lo, (long long)z_hi, (long long)depth, flags, counters_dev);
+        PNB_LAUNCHED();
+    }
+    return PNB_OK;
+}
+
+// End of the step: rows [0, n_own) minus the n_leave leavers plus the n_mig migrants among the
+// appended rows [n_own, n_own + n_app) become the owned points [0, n_new), n_new = n_own - n_leave
+// + n_mig (every array of `arrays` is permuted alike: pass dv too if it is still needed).
+// scratch: >= 2 * (n_leave + n_app) + 16 int32; counters_dev as above ([2], [3] are used here).
+extern "C" pnb_status pnb_slab_compact_f32(const pnb_slab_arrays *arrays, int64_t n_own, int64_t n_app,
+                                           const int32_t *leave_idx, int64_t n_leave, int64_t n_mig,
+                                           uint8_t *flags, int32_t *scratch, int32_t *counters_dev,
+                                           void *stream)
+{
+    if (!arrays || !flags || !scratch || !counters_dev) { set_error("NULL argument"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n_new = n_own - n_leave + n_mig, n_rows = n_own + n_app;
+    const int64_t cap = n_leave + n_app + 8;
+    if (n_own > 0) PNB_CUDA(cudaMemsetAsync(flags, 1, (size_t)n_own, s));
+    PNB_CUDA(cudaMemsetAsync(counters_dev + 2, 0, 2 * sizeof(int32_t), s));
+    if (n_leave > 0) {
+        k_slab_clear_flags<<<(unsigned)div_up(n_leave, 256), 256, 0, s>>>(leave_idx, n_leave, flags);
+        PNB_LAUNCHED();
+    }
+    if (n_rows > 0 && (n_leave > 0 || n_mig > 0)) {
+        // only the rows from min(n_new, first leaver ...) on can be holes or movers; scanning all
+        // of them costs a byte per row
+        k_slab_compact_lists<<<(unsigned)div_up(n_rows, 256), 256, 0, s>>>(flags, n_rows, n_new, scratch,
+                                                                          scratch + cap, cap, counters_dev);
+        PNB_LAUNCHED();
+        k_slab_compact_move<<<(unsigned)div_up(cap, 256), 256, 0, s>>>(*arrays, scratch, scratch + cap,
+                                                                       counters_dev);
+        PNB_LAUNCHED();
+    }
+    return PNB_OK;
+}
+
+
 // =============================================================================================
 // Float64 searches (f64.cuh)
 // =============================================================================================
@@ -2511,6 +2727,79 @@ extern "C" pnb_status pnb_point_cells_f64(const pnb_grid *g, const double *x, in
     }
     PNB_CUDA(cudaStreamSynchronize(s));
     return PNB_OK;
+}
+
+// ---- fused closures in Float64 (f64.cuh) ---------------------------------------------------------
+static pnb_status closure64_precheck(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                                     cudaStream_t s)
+{
+    if (!g || !g->f64) { set_error("not a Float64 grid handle"); return PNB_ERR_ARG; }
+    if (g->p64.mixed) {
+        set_error("the fused closures exist for Float32 and Float64 searches; a mixed-precision search "
+                  "(Float64 coordinates, Float32 radius) delivers Float32 pos_diff / distance through its "
+                  "neighbour lists");
+        return PNB_ERR_ARG;
+    }
+    if (!g->built) {
+        set_error("the neighborhood search has not been initialized (call initialize! first)");
+        return PNB_ERR_STATE;
+    }
+    if (nx > 0 && !x) { set_error("x is NULL"); return PNB_ERR_ARG; }
+    return check_built_y(g, y, n, s);
+}
+
+extern "C" pnb_status pnb_nbody_f64(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                                    const int32_t *points, int64_t n_points, int index_base,
+                                    const double *mass, double G, double *dv, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    pnb_status st = closure64_precheck(g, x, nx, y, n, s);
+    if (st != PNB_OK) return st;
+    const int nd = g->p64.ndims;
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(double) * (size_t)nx * nd, s));
+    const int64_t n_loop = points ? n_points : nx;
+    if (!g->template_search && g->n_built > 0 && n_loop > 0) {
+        const unsigned blocks = (unsigned)div_up(n_loop, 128);
+        const Wcsph64P none{};
+        ProfScope ps(PH_SWEEP_POINTS, s);
+        switch (nd) {
+            case 1: k_sweep_closure64<1, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            case 2: k_sweep_closure64<2, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            default: k_sweep_closure64<3, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+        }
+        PNB_LAUNCHED();
+    }
+    return check_err_word(g, s);
+}
+
+extern "C" pnb_status pnb_wcsph_interact_f64(pnb_grid *g, const double *x, int64_t nx, const double *y,
+                                             int64_t n, const int32_t *points, int64_t n_points,
+                                             int index_base, const double *v_x, const double *v_y,
+                                             const double *mass_x, const double *mass_y,
+                                             const double *pressure_x, const double *pressure_y,
+                                             const pnb_wcsph_params_f64 *params, double *dv, void *stream)
+{
+    (void)mass_x;
+    cudaStream_t s = (cudaStream_t)stream;
+    pnb_status st = closure64_precheck(g, x, nx, y, n, s);
+    if (st != PNB_OK) return st;
+    if (!params) { set_error("params is NULL"); return PNB_ERR_ARG; }
+    const int nd = g->p64.ndims;
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(double) * (size_t)nx * (nd + 1), s));
+    const int64_t n_loop = points ? n_points : nx;
+    if (!g->template_search && g->n_built > 0 && n_loop > 0) {
+        const unsigned blocks = (unsigned)div_up(n_loop, 128);
+        const Wcsph64P prm{params->smoothing_length, params->sound_speed, params->alpha, params->beta,
+                           params->epsilon, params->delta, params->kernel_norm};
+        ProfScope ps(PH_SWEEP_POINTS, s);
+        switch (nd) {
+            case 1: k_sweep_closure64<1, 1><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+            case 2: k_sweep_closure64<2, 1><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+            default: k_sweep_closure64<3, 1><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+        }
+        PNB_LAUNCHED();
+    }
+    return check_err_word(g, s);
 }
 
 extern "C" pnb_status pnb_count_neighbors_f64(pnb_grid *g, const double *x, int64_t nx,

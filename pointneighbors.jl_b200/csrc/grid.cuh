@@ -39,6 +39,7 @@ struct pnb_grid {
     // stream-ordered update! (pnb_grid_build_async_f32): the one-pass build was launched but its
     // error word (domain error, bucket overflow) has not been looked at yet
     bool async_pending;
+    int async_chain;         // stream-ordered builds since the error word was last looked at
     cudaStream_t async_stream;
     bool csr_valid;          // cell_start / sorted describe the current build
     unsigned int *d_maxcount;   // [1] device scratch

@@ -33,9 +33,9 @@ __global__ void k_gather_f32(int64_t n_slots, CellsView cv, const float *__restr
 __global__ void k_gather_wcsph(int64_t n, int nd, CellsView cv,
                                const float *__restrict__ v, const float *__restrict__ mass,
                                const float *__restrict__ pressure, float4 *__restrict__ vrho,
-                               float4 *__restrict__ mp, float2 *__restrict__ vp)
+                               float4 *__restrict__ mp, float2 *__restrict__ vp, int64_t i0 = 0)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !slot_valid(cv, i)) return;
     const int64_t id = __float_as_int(__ldg(&cv.rec[i].w));
     const int ns = nd + 1;
@@ -285,4 +285,62 @@ extern "C" pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, 
                                               pressure, params, dv, stream);
     t_async_sweep = false;
     return st;
+}
+
+// The WCSPH sweep of the cell layers [cz_a, cz_b] (local 1-based coordinates of the LAST used
+// dimension) only, stream-ordered: the payload of the layers [gz_a, gz_b] is gathered first
+// (gz_a > gz_b: nothing), dv is zeroed when zero_dv != 0.  The overlapped multi-GPU step sweeps
+// the interior layers of a slab while the ghost layers are still in flight, then appends them
+// (pnb_grid_append_f32) and sweeps the boundary layers.  Needs the one-pass (bucket) layout.
+extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const float *y, int64_t n,
+                                                          const float *v, const float *mass,
+                                                          const float *pressure,
+                                                          const pnb_wcsph_params *params, float *dv,
+                                                          int cz_a, int cz_b, int gz_a, int gz_b,
+                                                          int zero_dv, void *stream)
+{
+    if (!g || !params) { set_error("NULL argument"); return PNB_ERR_ARG; }
+    if (g->f64 || g->hashed || g->p.periodic || !g->built || !g->bucket_valid || g->bucket_tr ||
+        !g->full_build || y != g->y_built || n != g->n_y_built || g_exact_arithmetic) {
+        set_error("the layered sweep needs the one-pass (bucket) build of exactly these coordinates, "
+                  "a non-periodic FullGridCellList and the fast arithmetic mode");
+        return PNB_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nd = g->p.ndims;
+    const int gl = g->p.gs[nd - 1];
+    if (cz_a < 2) cz_a = 2;
+    if (cz_b > gl - 1) cz_b = gl - 1;
+    if (gz_a < 1) gz_a = 1;
+    if (gz_b > gl) gz_b = gl;
+    if (zero_dv && n > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)n * (nd + 1), s));
+    const int64_t nb = view_slots(g);
+    const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
+    pnb_status st = ensure_scratch(g, off_mp + (int64_t)sizeof(float4) * nb);
+    if (st != PNB_OK) return st;
+    float4 *vrho = reinterpret_cast<float4 *>(g->scratch);
+    float2 *vp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
+    int64_t layer_cells = 1;
+    for (int d = 0; d < nd - 1; d++) layer_cells *= g->p.gs[d];
+    if (gz_a <= gz_b) {
+        const int64_t i0 = (int64_t)(gz_a - 1) * layer_cells * g->bucket_K;
+        const int64_t i1 = (int64_t)gz_b * layer_cells * g->bucket_K;
+        ProfScope ps(PH_GATHER, s);
+        k_gather_wcsph<<<(unsigned)div_up(i1 - i0, 256), 256, 0, s>>>(i1, nd, cells_view(g), v, mass, pressure,
+                                                                     vrho, nullptr, vp, i0);
+        PNB_LAUNCHED();
+    }
+    if (cz_a > cz_b) return PNB_OK;
+    const float h = params->smoothing_length;
+    const float inv_h = -0.5f / h, kh = -5.0f * params->kernel_norm / (h * h);
+    const float ac = params->alpha * params->sound_speed;
+    const float dhc2 = 2.0f * params->delta * h * params->sound_speed;
+    const bool in_radius = 2.0f * h <= g->p.r;
+    const WcsphClT<false> cl{vrho, nullptr, v, pressure, *params, dv, nd, inv_h, kh, ac, dhc2, in_radius, vp};
+    const CellsView cv = cells_view(g);
+    switch (nd) {
+        case 2: return launch_flat<2, false, WcsphClT<false>, false>(g, cv, cv, n, cl, cz_a - 2, cz_b - cz_a + 1, s);
+        case 3: return launch_flat<3, false, WcsphClT<false>, false>(g, cv, cv, n, cl, cz_a - 2, cz_b - cz_a + 1, s);
+        default: set_error("the layered sweep needs 2 or 3 dimensions"); return PNB_ERR_ARG;
+    }
 }

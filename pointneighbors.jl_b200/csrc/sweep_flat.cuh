@@ -253,7 +253,7 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
     __shared__ uint32_t s_qb[kFSMax], s_qt[kFSMax + 1];   // per tile cell: first record, first tile point
     __shared__ int s_cnt[kFG][kWPC][32];
     __shared__ nz_t s_nz[kFG][kWPC][32];
-    __shared__ int s_nsl, s_next;
+    __shared__ int s_nsl;
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int group = warp / kWPC, part = warp % kWPC;
@@ -273,72 +273,154 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
     unsigned *my_mask = s_mask + (size_t)group * kNBlkMax * 32 + lane;   // word of block b: my_mask[b * 32]
     unsigned *my_band = CL::kCountOnly ? my_mask : my_mask + (size_t)kFG * kNBlkMax * 32;
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles;) {
+    // ---- tile pipeline of the persistent CTA ------------------------------------------------------
+    // While tile t is processed, warp 0 has already requested the index of tile t + 2 (atomic
+    // counter), read the record of tile t + 1 and started asynchronous copies (LDGSTS) of the cell
+    // list words of its <= 7 x 9 staged cells and <= 5 query cells into s_raw: the prologue of a
+    // tile then works from shared memory only, no global round trip sits between two tiles.
+    __shared__ FlatTile s_ft, s_ftn;                         // current / prefetched tile record
+    __shared__ uint32_t s_raw[2 * (NEmax + kFSMax)];         // raw cell list words of the next tile
+    __shared__ uint32_t s_tile;
+    const uint32_t raw_sa = (uint32_t)__cvta_generic_to_shared(s_raw);
+    auto cell_words_async = [&](const CellsView &v, int lin, uint32_t sa) {
+        if (v.K) {
+            cp_async4(sa, v.start + bucket_of((uint32_t)lin, v.t0, v.t1, v.t2));
+        } else {
+            cp_async4(sa, v.start + lin);
+            cp_async4(sa + 4u, v.start + lin + 1);
+        }
+    };
+    auto cell_from_words = [&](const CellsView &v, int lin, uint32_t w0, uint32_t w1, uint32_t &b0, uint32_t &cnt) {
+        if (v.K) { b0 = bucket_of((uint32_t)lin, v.t0, v.t1, v.t2) * v.K; cnt = min(w0, v.K); }
+        else { b0 = w0; cnt = w1 - w0; }
+    };
+    auto staged_cell = [&](int e, int cx0_, int cy_, int cz_, bool &valid) {
+        const int slot = e / NR, row = e % NR;
+        int sx = cx0_ - 1 + slot;
+        int ry = cy_ + (ND > 1 ? (row % 3) - 1 : 0);
+        int rz = cz_ + (ND > 2 ? (row / 3) - 1 : 0);
+        valid = sx <= g.gs[0];
+        if (PER) {
+            sx = floormod_i(sx - 2, g.nc[0]) + 2;
+            if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
+            if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
+        }
+        return linear_cell(g, sx, ry, rz);
+    };
+    const uint32_t ftn_sa = (uint32_t)__cvta_generic_to_shared(&s_ftn);
+    // warp 0, step 1: the record of tile t (one 16-byte asynchronous copy)
+    auto prefetch_record = [&](uint32_t t) {
+        if (lane == 0) cp_async16(ftn_sa, tiles + t);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // warp 0, step 2 (the record has arrived): the cell list words of its staged and query cells
+    auto prefetch_cells = [&]() {
+        const FlatTile f = s_ftn;
+        const int lin0 = (int)f.cell;
+        const int cx0_ = lin0 % g.gs[0] + 1;
+        const int cy_ = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
+        const int cz_ = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
+        for (int e = lane; e < NEmax; e += 32) {
+            bool valid;
+            const int lin = staged_cell(e, cx0_, cy_, cz_, valid);
+            if (valid) cell_words_async(cand, lin, raw_sa + 8u * (uint32_t)e);
+            else { s_raw[2 * e] = 0u; s_raw[2 * e + 1] = 0u; }
+        }
+        if (lane < kFSMax) {
+            if (cx0_ + lane <= g.gs[0] - 1)
+                cell_words_async(qry, linear_cell(g, cx0_ + lane, cy_, cz_), raw_sa + 8u * (uint32_t)(NEmax + lane));
+            else { s_raw[2 * (NEmax + lane)] = 0u; s_raw[2 * (NEmax + lane) + 1] = 0u; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t cur = blockIdx.x, nxt = 0xffffffffu;            // warp 0: this tile, the one after it
+    if (warp == 0) {
+        if (lane == 0) nxt = atomicAdd(ctl + 1, 1u);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        if (cur < n_tiles) {
+            prefetch_record(cur);
+            cp_async_wait_all();
+            __syncwarp();
+            prefetch_cells();
+        }
+    }
+
+    for (;;) {
         __syncthreads();                         // shared memory of the previous tile is free
-        const FlatTile ft = tiles[tile];
+        // ---- cells of the tile and table of staged cells (warp 0, from the prefetched words) ----
+        if (warp == 0) {
+            if (lane == 0) s_tile = cur;
+            if (cur < n_tiles) {
+                cp_async_wait_all();
+                __syncwarp();
+                const FlatTile ft = s_ftn;
+                if (lane == 0) s_ft = ft;
+                const int lin0 = (int)ft.cell;
+                const int cx0 = lin0 % g.gs[0] + 1;
+                const int cy = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
+                const int cz = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
+                // tile cells: lane s = cell cx0 + s
+                uint32_t b0 = 0, cntq = 0;
+                if (lane < kFSMax && cx0 + lane <= g.gs[0] - 1)
+                    cell_from_words(qry, linear_cell(g, cx0 + lane, cy, cz), s_raw[2 * (NEmax + lane)],
+                                    s_raw[2 * (NEmax + lane) + 1], b0, cntq);
+                uint32_t avail = cntq;
+                if (lane == 0) { avail -= ft.off; b0 += ft.off; }
+                uint32_t incl = avail;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t excl = incl - avail;
+                // cells that hold a point of the tile: exclusive prefix < npts
+                const unsigned touch = __ballot_sync(0xffffffffu, lane < kFSMax && excl < ft.npts && avail > 0u);
+                const int S = 32 - __clz((int)touch);            // index of the last touched cell + 1
+                if (lane < kFSMax) { s_qb[lane] = b0; s_qt[lane] = min(excl, ft.npts); }
+                if (lane == 0) { s_qt[kFSMax] = ft.npts; s_nsl = S + 2; }
+                const int NE = (S + 2) * NR;
+                for (int e = lane; e < NEmax; e += 32) {
+                    bool valid;
+                    const int lin = staged_cell(e, cx0, cy, cz, valid);
+                    uint32_t c0 = 0, cn = 0;
+                    if (e < NE && valid) cell_from_words(cand, lin, s_raw[2 * e], s_raw[2 * e + 1], c0, cn);
+                    s_cbeg[e] = c0;
+                    s_ccnt[e] = cn;
+                }
+                __syncwarp();
+                if (lane < kFNSL) {
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int r = 0; r < NR; r++) { s_cpre[lane * NR + r] = run; run += s_ccnt[lane * NR + r]; }
+                    s_spop[lane] = run;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int sl = 0; sl < kFNSL; sl++) { s_slot0[sl] = run; run += (s_spop[sl] + 31u) & ~31u; }
+                    s_slot0[kFNSL] = run;
+                }
+                __syncwarp();
+                for (int e = lane; e < NEmax; e += 32) s_cpre[e] += s_slot0[e / NR];
+            }
+        }
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const FlatTile ft = s_ft;
         const int lin0 = (int)ft.cell;
         const int cx0 = lin0 % g.gs[0] + 1;
         const int cy = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
         const int cz = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
-        // ---- cells of the tile and table of staged cells (warp 0) ---------------------------
+        uint32_t nn = 0u;
         if (warp == 0) {
-            if (lane == 0) s_next = (int)atomicAdd(ctl + 1, 1u);     // next tile of this CTA
-            // tile cells: lane s = cell cx0 + s
-            uint32_t b0 = 0, cntq = 0;
-            if (lane < kFSMax && cx0 + lane <= g.gs[0] - 1)
-                cell_range(qry, linear_cell(g, cx0 + lane, cy, cz), b0, cntq);
-            uint32_t avail = cntq;
-            if (lane == 0) { avail -= ft.off; b0 += ft.off; }
-            uint32_t incl = avail;
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t excl = incl - avail;
-            // cells that hold a point of the tile: exclusive prefix < npts
-            const unsigned touch = __ballot_sync(0xffffffffu, lane < kFSMax && excl < ft.npts && avail > 0u);
-            const int S = 32 - __clz((int)touch);            // index of the last touched cell + 1
-            if (lane < kFSMax) { s_qb[lane] = b0; s_qt[lane] = min(excl, ft.npts); }
-            if (lane == 0) { s_qt[kFSMax] = ft.npts; s_nsl = S + 2; }
-            const int NSL = S + 2, NE = NSL * NR;
-            for (int e = lane; e < NEmax; e += 32) {
-                const int slot = e / NR, row = e % NR;
-                int sx = cx0 - 1 + slot;
-                int ry = cy + (ND > 1 ? (row % 3) - 1 : 0);
-                int rz = cz + (ND > 2 ? (row / 3) - 1 : 0);
-                uint32_t c0 = 0, cn = 0;
-                if (e < NE && sx <= g.gs[0]) {
-                    if (PER) {
-                        sx = floormod_i(sx - 2, g.nc[0]) + 2;
-                        if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
-                        if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
-                    }
-                    cell_range(cand, linear_cell(g, sx, ry, rz), c0, cn);
-                }
-                s_cbeg[e] = c0;
-                s_ccnt[e] = cn;
-            }
-            __syncwarp();
-            if (lane < kFNSL) {
-                uint32_t run = 0;
-#pragma unroll
-                for (int r = 0; r < NR; r++) { s_cpre[lane * NR + r] = run; run += s_ccnt[lane * NR + r]; }
-                s_spop[lane] = run;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                uint32_t run = 0;
-#pragma unroll
-                for (int sl = 0; sl < kFNSL; sl++) { s_slot0[sl] = run; run += (s_spop[sl] + 31u) & ~31u; }
-                s_slot0[kFNSL] = run;
-            }
-            __syncwarp();
-            for (int e = lane; e < NEmax; e += 32) s_cpre[e] += s_slot0[e / NR];
+            // the tile after this one: request the index behind it and copy its record (both
+            // asynchronous: nothing here waits; its cells follow once this tile is staged)
+            if (lane == 0) nn = atomicAdd(ctl + 1, 1u);
+            if (nxt < n_tiles) prefetch_record(nxt);
         }
-        __syncthreads();
         const int NSL = s_nsl;
-        const int next_tile = s_next;
         // too dense for the staging buffer or the mask table: hand the tile to the per-point kernel
         bool too_big = s_slot0[NSL] > (uint32_t)kCap;
 #pragma unroll
@@ -346,7 +428,11 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
             if (w + 3 <= NSL) too_big = too_big || (s_slot0[w + 3] - s_slot0[w]) > (uint32_t)(kNBlkMax * 32);
         if (too_big) {
             if (threadIdx.x == 0) overflow_tiles[atomicAdd(ctl + 2, 1u)] = (int)tile;
-            tile = (uint32_t)next_tile;
+            if (warp == 0) {
+                if (nxt < n_tiles) { cp_async_wait_all(); __syncwarp(); prefetch_cells(); }
+                cur = nxt;
+                nxt = __shfl_sync(0xffffffffu, nn, 0);
+            }
             continue;
         }
 
@@ -424,6 +510,13 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
             }
         }
         __syncthreads();
+        if (warp == 0) {
+            // the record of the next tile arrived with this warp's staging copies: start the
+            // copies of its cell list words, they land while this tile is tested and drained
+            if (nxt < n_tiles) { cp_async_wait_all(); __syncwarp(); prefetch_cells(); }
+            cur = nxt;
+            nxt = __shfl_sync(0xffffffffu, nn, 0);
+        }
 
         // ---- my point: tile point tp = group * 32 + lane -------------------------------------
         const uint32_t tp = (uint32_t)(group * 32 + lane);
@@ -637,7 +730,6 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
                 if (active) cl.finish(st, TWO ? -1 : (int)i_sorted, i_id);
             }
         }
-        tile = (uint32_t)next_tile;
     }
 }
 

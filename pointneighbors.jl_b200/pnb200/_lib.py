@@ -36,6 +36,13 @@ class WcsphParams(C.Structure):
                 ("delta", C.c_float), ("kernel_norm", C.c_float)]
 
 
+class WcsphParams64(C.Structure):
+    """pnb_wcsph_params_f64 (include/pnb200.h)."""
+    _fields_ = [("smoothing_length", C.c_double), ("sound_speed", C.c_double), ("alpha", C.c_double),
+                ("beta", C.c_double), ("epsilon", C.c_double), ("delta", C.c_double),
+                ("kernel_norm", C.c_double)]
+
+
 class TlsphParams(C.Structure):
     """pnb_tlsph_params (include/pnb200.h)."""
     _fields_ = [("smoothing_length", C.c_float), ("kernel_norm", C.c_float),
@@ -81,6 +88,9 @@ SIGNATURES = {
     "pnb_grid_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pnb_point_cells_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_count_neighbors_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
+    "pnb_nbody_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp]),
+    "pnb_wcsph_interact_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _vp,
+                                         _vp, _vp, _vp, C.POINTER(WcsphParams64), _vp, _vp]),
     "pnb_nlist_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), _vp]),
     "pnb_nlist_pairs_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnb_grid_create_hashed_f32": (C.c_int, [C.c_int, _f32, _i64, _pf, _pf, C.POINTER(_vp)]),
@@ -99,6 +109,14 @@ SIGNATURES = {
     "pnb_hoststep_wcsph_submit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(WcsphParams), _vp]),
     "pnb_hoststep_wait": (C.c_int, [_vp]),
     "pnb_hoststep_destroy": (None, [_vp]),
+    "pnb_grid_append_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "pnb_wcsph_interact_layers_async_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp,
+                                                      C.POINTER(WcsphParams), _vp, C.c_int, C.c_int,
+                                                      C.c_int, C.c_int, C.c_int, _vp]),
+    "pnb_slab_append_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
+                                      _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "pnb_slab_compact_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, _i64, _vp, _i64, _i64, _vp, _vp,
+                                       _vp, _vp]),
     "pnb_point_cells_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_grid_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "pnb_grid_export_dvov": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, _vp]),

@@ -770,6 +770,9 @@ class WCSPHInteract:
         self.params = WcsphParams(np.float32(smoothing_length), np.float32(sound_speed),
                                   np.float32(alpha), np.float32(beta), np.float32(epsilon),
                                   np.float32(delta), np.float32(kernel_norm))
+        # the same in Float64 (Float64 searches, pnb_wcsph_interact_f64)
+        self.params64 = (float(smoothing_length), float(sound_speed), float(alpha), float(beta),
+                         float(epsilon), float(delta), float(kernel_norm))
 
     def params_array(self):
         p = self.params
@@ -851,13 +854,16 @@ def set_exact_arithmetic(on: bool) -> None:
 
 
 def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_search, *,
-                           parallelization_backend=None, points=None):
+                           parallelization_backend=None, points=None, blocking=True):
     """foreach_point_neighbor(f, x, y, nhs; points)  (src/neighborhood_search.jl:183-201).
 
     f is one of the fused closures (CountNeighbors, NBodyGravity, WCSPHInteract,
     TLSPHDeformationGradient) or any Python callable f(i, j, pos_diff, distance); a callable is
     served from a device-built neighbour list (the pairs are computed on the GPU, the callable is
-    host code and runs on the host).  Returns None like the reference."""
+    host code and runs on the host).  Returns None like the reference.
+
+    blocking=False (WCSPHInteract over all points with x === y only; no reference counterpart):
+    gather + sweep are only enqueued on the current stream; `check_(nhs)` settles the chain."""
     nhs = neighborhood_search
     nd = nhs._ndims
     x = _coords(system_coords, nd, nhs.eltype)
@@ -871,12 +877,26 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
             check(L.pnb_count_neighbors_f64(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(),
                                             y.shape[0], _ptr(pts), 0 if pts is None else pts.numel(),
                                             0, f.n_neighbors.data_ptr(), _stream()))
+        elif isinstance(f, NBodyGravity) and not getattr(nhs.cell_list, "mixed", False):
+            check(L.pnb_nbody_f64(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
+                                  _ptr(pts), 0 if pts is None else pts.numel(), 0, f.mass.data_ptr(),
+                                  float(f.G), f.dv.data_ptr(), _stream()))
+        elif isinstance(f, WCSPHInteract) and not getattr(nhs.cell_list, "mixed", False):
+            p64 = _lib.WcsphParams64(*f.params64)
+            check(L.pnb_wcsph_interact_f64(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(),
+                                           y.shape[0], _ptr(pts), 0 if pts is None else pts.numel(), 0,
+                                           f.v_x.data_ptr(), f.v_y.data_ptr(), f.mass_x.data_ptr(),
+                                           f.mass_y.data_ptr(), f.pressure_x.data_ptr(),
+                                           f.pressure_y.data_ptr(), C.byref(p64), f.dv.data_ptr(),
+                                           _stream()))
         elif callable(f) and not isinstance(f, (NBodyGravity, WCSPHInteract,
                                                  TLSPHDeformationGradient, TLSPHInteract)):
             lists = _NeighborLists.build(nhs, x, y, sort=False)
             lists.call_host(f, x, y, nhs, points, radius_test=True)
         else:
-            raise TypeError("the fused n-body / WCSPH / TLSPH closures exist in Float32 only")
+            raise TypeError("Float64 searches have the fused n-body / WCSPH closures (all arrays "
+                            "float64); the TLSPH closures and mixed-precision searches use Float32 / "
+                            "neighbour lists")
         return None
     pts = _index_tensor(points, x.shape[0], "points")
     npts = 0 if pts is None else pts.numel()
@@ -888,6 +908,11 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
         check(L.pnb_nbody_f32(g, x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], _ptr(pts),
                               npts, 0, f.mass.data_ptr(), np.float32(f.G), f.dv.data_ptr(),
                               _stream()))
+    elif isinstance(f, WCSPHInteract) and not blocking and pts is None and \
+            x.data_ptr() == y.data_ptr() and x.shape[0] == y.shape[0]:
+        check(L.pnb_wcsph_interact_async_f32(g, y.data_ptr(), y.shape[0], f.v_y.data_ptr(),
+                                             f.mass_y.data_ptr(), f.pressure_y.data_ptr(),
+                                             C.byref(f.params), f.dv.data_ptr(), _stream()))
     elif isinstance(f, WCSPHInteract):
         check(L.pnb_wcsph_interact_f32(g, x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
                                        _ptr(pts), npts, 0, f.v_x.data_ptr(), f.v_y.data_ptr(),

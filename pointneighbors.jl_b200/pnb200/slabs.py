@@ -357,6 +357,177 @@ class SlabNeighborhoodSearch:
 
 
 # ---------------------------------------------------------------------------------------------
+# the overlapped WCSPH step of one rank (CUDA only)
+# ---------------------------------------------------------------------------------------------
+class OverlappedWCSPHStep:
+    """update! + WCSPH interact! of one slab with the ghost exchange hidden behind the sweep of the
+    interior cell layers:
+
+        pack the boundary rows (pnb_slab_pack_f32)
+        side stream : NCCL send/recv with both neighbours (counts, then rows)
+        main stream : stream-ordered update! of the OWNED points, gather + sweep of the interior
+                      layers [z_lo + 2, z_hi - 2]        <- runs while the rows travel
+        main stream : wait for the rows, append them to the arrays (pnb_slab_append_f32) and to
+                      the cell list (pnb_grid_append_f32), gather + sweep of the boundary layers
+        check, then compaction (pnb_slab_compact_f32): leavers out, migrants in
+
+    Only the owned layers are swept (the ghosts are candidates, never query points).  The first
+    step of a search (no bucket capacity known yet) and steps whose update! overflowed a bucket or
+    received a migrant deeper than one layer inside the slab run the same sequence without the
+    overlap.  Results: dv[:n_own_new] belongs to arrays[k][:n_own_new]."""
+
+    DEPTH = 2          # boundary layers per side that wait for the exchange
+
+    def __init__(self, slab: "SlabNeighborhoodSearch", closure_kwargs: dict):
+        import torch
+        self.slab = slab
+        self.ex = slab.exchange
+        self.kw = dict(closure_kwargs)
+        self.side = torch.cuda.Stream()
+        self.flags = None
+        self.scratch = None
+        self.counters = None
+        self.last = {}
+
+    def _table(self, arrs):
+        t = _lib.SlabArrays()
+        for k, a in enumerate(arrs):
+            t.ptr[k] = a.data_ptr()
+            t.width[k] = 1 if a.ndim == 1 else a.shape[1]
+        t.n_arrays = len(arrs)
+        return t
+
+    def step(self, arrays, n, dv, overlap=True):
+        """arrays = [coords (cap, nd), v (cap, nd + 1), mass (cap,), pressure (cap,)], the first n rows
+        owned; dv (cap, nd + 1).  Returns (arrays, dv, n_own_new)."""
+        import torch
+        from . import api as pn
+        L = _lib.lib()
+        ex, nhs, nd = self.ex, self.slab.nhs, self.slab.ndims
+        dev = arrays[0].device
+        main = torch.cuda.current_stream()
+        stream = C.c_void_p(main.cuda_stream)
+        has_up, has_down = ex.rank + 1 < ex.world, ex.rank > 0
+        W = sum(1 if a.ndim == 1 else a.shape[1] for a in arrays)
+        pmin, cs = np.float32(ex.padded_min[-1]), np.float32(ex.search_radius)
+        # ---- 1. pack (classification of the owned points, rows of the two boundary lists) ----
+        cap = getattr(ex, "_x_cap", 0) or max(n // 8, 1 << 16)
+        while True:
+            if getattr(ex, "_x_bufs", None) is None or ex._x_cap < cap:
+                ex._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
+                ex._x_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+                ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
+                ex._x_cap = cap
+            counts = (C.c_int64 * 3)()
+            tab = self._table(arrays)
+            check(L.pnb_slab_pack_f32(C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi, int(has_up),
+                                      int(has_down), ex._x_idx[0].data_ptr(), ex._x_idx[1].data_ptr(),
+                                      ex._x_idx[2].data_ptr(), ex._x_cap, ex._x_bufs[0].data_ptr(),
+                                      ex._x_bufs[1].data_ptr(), ex._x_cnt.data_ptr(), counts, stream))
+            if max(counts) <= ex._x_cap:
+                break
+            cap = int(max(counts)) + int(max(counts)) // 4 + 1024
+        n_up, n_down, n_leave = (int(c) for c in counts)
+        send_up, send_down = ex._x_bufs[0][:n_up], ex._x_bufs[1][:n_down]
+        # ---- 2. exchange on the side stream -----------------------------------------------------
+        self.side.wait_stream(main)
+        coords = arrays[0]
+        closure = pn.WCSPHInteract(dv, arrays[1], arrays[1], arrays[2], arrays[2], arrays[3], arrays[3],
+                                   **self.kw)
+        off = ex.window[0][-1] - 1                       # local cell layer = global - off
+        D = self.DEPTH
+        lo_i, hi_i = ex.z_lo + D, ex.z_hi - D            # interior layers (global)
+        can_overlap = overlap and nhs._handle is not None and nhs.layout() == "buckets" and lo_i <= hi_i
+        g = nhs._grid()
+        if can_overlap:
+            # ---- 3. owned points: stream-ordered update!, interior layers -----------------------
+            check(L.pnb_grid_build_async_f32(g, coords.data_ptr(), n, stream))
+            nhs._y_ref = coords
+            can_overlap = nhs.layout() == "buckets"
+        if can_overlap:
+            check(L.pnb_wcsph_interact_layers_async_f32(
+                g, coords.data_ptr(), n, arrays[1].data_ptr(), arrays[2].data_ptr(), arrays[3].data_ptr(),
+                C.byref(closure.params), dv.data_ptr(), lo_i - off, hi_i - off, lo_i - 1 - off,
+                hi_i + 1 - off, 0, stream))
+        with torch.cuda.stream(self.side):
+            recv_up, recv_down = ex._sendrecv(send_up, send_down)
+        main.wait_stream(self.side)
+        recv_up.record_stream(main)
+        recv_down.record_stream(main)
+        n_ru, n_rd = recv_up.shape[0], recv_down.shape[0]
+        n_app = n_ru + n_rd
+        n_rows = n + n_app
+        # ---- 4. append what arrived ---------------------------------------------------------------
+        if n_rows > coords.shape[0]:
+            # (rare: capacity exceeded) grow the arrays; the cell list was built from the old
+            # coordinate array, so this step finishes without the overlap
+            new_cap = n_rows + n_rows // 8 + 1024
+            torch.cuda.synchronize()
+            grown = []
+            for a in arrays + [dv]:
+                t = torch.empty((new_cap,) + tuple(a.shape[1:]), dtype=a.dtype, device=dev)
+                t[:n] = a[:n]
+                grown.append(t)
+            arrays, dv = grown[:-1], grown[-1]
+            coords = arrays[0]
+            closure = pn.WCSPHInteract(dv, arrays[1], arrays[1], arrays[2], arrays[2], arrays[3],
+                                       arrays[3], **self.kw)
+            can_overlap = False
+        if self.flags is None or self.flags.numel() < coords.shape[0]:
+            self.flags = torch.empty(coords.shape[0], dtype=torch.uint8, device=dev)
+            self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        tab = self._table(arrays)
+        check(L.pnb_slab_append_f32(C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi, D - 1,
+                                    recv_up.data_ptr(), n_ru, recv_down.data_ptr(), n_rd,
+                                    self.flags.data_ptr(), self.counters.data_ptr(), stream))
+        redo = not can_overlap
+        if can_overlap:
+            check(L.pnb_grid_append_f32(g, coords.data_ptr(), n, n_app, stream))
+            # ---- 5. boundary layers ------------------------------------------------------------
+            for a, b in ((ex.z_lo, min(ex.z_lo + D - 1, ex.z_hi)), (max(ex.z_hi - D + 1, ex.z_lo + D), ex.z_hi)):
+                if a > b:
+                    continue
+                check(L.pnb_wcsph_interact_layers_async_f32(
+                    g, coords.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
+                    arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), a - off, b - off,
+                    a - 1 - off, b + 1 - off, 0, stream))
+            cnt_h = self.counters.tolist()                 # end of the step: the one synchronisation
+            pn.check_(nhs)
+            # a bucket overflowed (the library rebuilt the list) or a migrant landed deep inside
+            # the slab: the sweeps above are void
+            redo = nhs.layout() != "buckets" or cnt_h[1] != 0
+        else:
+            cnt_h = self.counters.tolist()
+        n_mig = int(cnt_h[0])
+        if redo:
+            loc = coords[:n_rows]
+            pn.update_(nhs, loc, loc, points_moving=(True, True))
+            if nhs.layout() == "buckets":
+                check(L.pnb_wcsph_interact_layers_async_f32(
+                    g, loc.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
+                    arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), ex.z_lo - off,
+                    ex.z_hi - off, ex.z_lo - 1 - off, ex.z_hi + 1 - off, 0, stream))
+                pn.check_(nhs)
+            else:
+                f = pn.WCSPHInteract(dv[:n_rows], arrays[1][:n_rows], arrays[1][:n_rows], arrays[2][:n_rows],
+                                     arrays[2][:n_rows], arrays[3][:n_rows], arrays[3][:n_rows], **self.kw)
+                pn.foreach_point_neighbor(f, loc, loc, nhs)
+        # ---- 6. compaction: leavers out, migrants in (dv travels with its rows) ------------------
+        need = 2 * (n_leave + n_app + 8) + 16
+        if self.scratch is None or self.scratch.numel() < need:
+            self.scratch = torch.empty(need + need // 4, dtype=torch.int32, device=dev)
+        tab = self._table(arrays + [dv])
+        check(L.pnb_slab_compact_f32(C.byref(tab), n, n_app, ex._x_idx[2].data_ptr(), n_leave, n_mig,
+                                     self.flags.data_ptr(), self.scratch.data_ptr(),
+                                     self.counters.data_ptr(), stream))
+        n_new = n - n_leave + n_mig
+        self.last = {"sent_up": n_up, "sent_down": n_down, "received": n_app, "migrated_in": n_mig,
+                     "migrated_out": n_leave, "ghosts": n_app - n_mig + n_leave, "overlapped": bool(can_overlap and not redo),
+                     "bytes_sent": (n_up + n_down) * W * 4, "rows": n_rows}
+        return arrays, dv, n_new
+
+
+# ---------------------------------------------------------------------------------------------
 # benchmark at N > 1 (called by bench.py): weak scaling, 254 lattice layers per GPU
 # ---------------------------------------------------------------------------------------------
 def lattice_planes(n, k_lo, k_hi, domain_n, seed, device):
@@ -379,39 +550,50 @@ def lattice_planes(n, k_lo, k_hi, domain_n, seed, device):
 
 
 def bench_multi_gpu(args, rank, world, dev, metric, unit):
+    """BASELINE config 5: the n^3 cloud (n = 504: 128 024 064 particles, 171^3 cells) cut into
+    `world` slabs along the last cell dimension -- STRONG scaling, the cloud is the same for every
+    N.  A step = migrant + ghost exchange, update!, WCSPH interact! of the owned layers, with the
+    exchange hidden behind the sweep of the interior layers (OverlappedWCSPHStep)."""
     import json
+    import time
     import torch
     import torch.distributed as dist
     from . import api as pn
 
     T = np.float32
-    n = args.lattice
-    strong = int(getattr(args, "total_layers", 0) or 0)
-    nz = strong if strong > 0 else n * world
-    r = T(3.0) / T(nz + 1)
-    mn = np.zeros(3, T)
-    mx = (np.array([n, n, nz], dtype=np.float64) / nz).astype(T)
+    n = int(getattr(args, "slab_lattice", 504))
+    overlap = not bool(getattr(args, "no_overlap", False))
+    r = T(3.0) / T(n + 1)
+    mn, mx = np.zeros(3, T), np.ones(3, T)
     slab = SlabNeighborhoodSearch(3, r, mn, mx, rank, world)
     ex = slab.exchange
     # lattice planes that can fall into my layers (3 planes per layer, one plane of margin)
     k_lo = max(1, 3 * (ex.z_lo - 2) - 1)
-    k_hi = min(nz, 3 * (ex.z_hi - 2) + 3)
-    cand = lattice_planes(n, k_lo, k_hi, nz, 1, dev)
-    A = cand[ex.owned_mask(cand)].contiguous()
+    k_hi = min(n, 3 * (ex.z_hi - 2) + 3)
+    parts = []
+    for k0 in range(k_lo, k_hi + 1, 32):          # plane blocks: bounded temporary memory
+        cand = lattice_planes(n, k0, min(k0 + 31, k_hi), n, 1, dev)
+        parts.append(cand[ex.owned_mask(cand)])
+        del cand
+    A = torch.cat(parts).contiguous()
+    del parts
     # cell-sorted order like the single-GPU cloud (dimension 1 most significant)
-    cellk = torch.floor(A.to(torch.float64) * (nz + 1) / 3.0).to(torch.int64)
-    key = (cellk[:, 0] * (n + 8) + cellk[:, 1]) * (nz + 8) + cellk[:, 2]
+    cellk = torch.floor(A.to(torch.float64) * (n + 1) / 3.0).to(torch.int64)
+    key = (cellk[:, 0] * (n + 8) + cellk[:, 1]) * (n + 8) + cellk[:, 2]
+    del cellk
     A = A[torch.sort(key, stable=True).indices].contiguous()
+    del key
     N = A.shape[0]
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     B = (A + (T(4e-4) * r) * torch.randn(N, 3, device=dev, generator=gen)).contiguous()
     gen2 = torch.Generator(device=dev).manual_seed(2000 + rank)
     rho = 1000.0 + torch.rand(N, device=dev, generator=gen2, dtype=torch.float32)
-    vel = torch.zeros((N, 3), device=dev, dtype=torch.float32)
     mass = torch.full((N,), float(T(0.1) * (r / T(3))), device=dev, dtype=torch.float32)
     pressure = T(100.0) * (rho - T(1000.0))
-    vfull = torch.cat([vel, rho[:, None]], dim=1)      # v = vcat(velocity, density'), (N, 4)
-    cap = N + N // 16 + 4096
+    vfull = torch.zeros((N, 4), device=dev, dtype=torch.float32)     # v = vcat(velocity, density')
+    vfull[:, 3] = rho
+    layer_pts = int(N / max(ex.z_hi - ex.z_lo + 1, 1))
+    cap = N + 4 * layer_pts + N // 64 + 4096          # owned + ghost layers + head room
 
     def with_cap(t):
         out = torch.empty((cap,) + tuple(t.shape[1:]), device=dev, dtype=torch.float32)
@@ -420,59 +602,53 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
 
     # two independent particle buffers (positions A / B of the same cloud), each [coords, v, m, p]
     bufs = [[with_cap(X), with_cap(vfull), with_cap(mass), with_cap(pressure)] for X in (A, B)]
+    dvs = [torch.empty((cap, 4), device=dev, dtype=torch.float32) for _ in range(2)]
     n_cur = [N, N]
-    del A, B, vfull, cand, vel, rho, mass, pressure
+    # pinned host copies of what a host-side caller owns (e2e leg)
+    host = [[t[:N].cpu().pin_memory() for t in (b[0], b[1], b[3])] for b in bufs]
+    host_dv = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+    del A, B, vfull, rho, mass, pressure
     h = T(r / T(2))
-
+    stepper = OverlappedWCSPHStep(slab, dict(smoothing_length=h, sound_speed=T(10.0), alpha=T(0.02),
+                                             beta=T(0.0), delta=T(0.1)))
     phase_ev = []
 
-    def step(s, count_only=False, timed=False):
+    def step(s, timed=False, ovl=True, e2e=False):
         k = (s + 1) % 2
+        if e2e:
+            # the owned rows' coordinates, state and pressure come from pinned host memory
+            m = min(n_cur[k], host[k][0].shape[0])
+            bufs[k][0][:m].copy_(host[k][0][:m], non_blocking=True)
+            bufs[k][1][:m].copy_(host[k][1][:m], non_blocking=True)
+            bufs[k][3][:m].copy_(host[k][2][:m], non_blocking=True)
         if timed:
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             evs[0].record()
-        bufs[k], n_own, nl = ex.exchange_inplace(bufs[k], n_cur[k])
-        n_cur[k] = n_own
-        cbuf, vbuf, mbuf, pbuf = bufs[k]
-        coords = cbuf[:nl]
+        bufs[k], dvs[k], n_cur[k] = stepper.step(bufs[k], n_cur[k], dvs[k], overlap=ovl)
         if timed:
             evs[1].record()
-        slab.update_(coords)
-        if timed:
-            evs[2].record()
-        if count_only:
-            cnt = torch.zeros(nl, dtype=torch.int64, device=dev)
-            pn.foreach_point_neighbor(pn.CountNeighbors(cnt), coords, coords, slab.nhs)
-            return int(cnt[:n_own].sum()), n_own
-        v, m, p = vbuf[:nl], mbuf[:nl], pbuf[:nl]
-        dv = torch.empty((nl, 4), device=dev, dtype=torch.float32)
-        f = pn.WCSPHInteract(dv, v, v, m, m, p, p, smoothing_length=h, sound_speed=T(10.0))
-        pn.foreach_point_neighbor(f, coords, coords, slab.nhs)
-        if timed:
-            evs[3].record()
             phase_ev.append(evs)
-        return dv[:n_own], n_own
+        if e2e:
+            host_dv[:n_cur[k]].copy_(dvs[k][:n_cur[k]], non_blocking=True)
+        return n_cur[k]
 
+    # pairs of the owned points of both clouds (untimed): full count sweep on the local window
+    def owned_pairs(k):
+        # rebuild the local cloud (owned + ghosts) the way the step saw it: one more exchange
+        arrs, n_own, n_local = ex.exchange_inplace([a.clone() for a in bufs[k]], n_cur[k])
+        loc = arrs[0][:n_local].contiguous()
+        pn.update_(slab.nhs, loc, loc, points_moving=(True, True))
+        cnt = torch.zeros(n_local, dtype=torch.int64, device=dev)
+        pn.foreach_point_neighbor(pn.CountNeighbors(cnt), loc, loc, slab.nhs)
+        return int(cnt[:n_own].sum())
+
+    step(0, ovl=False)
+    step(1, ovl=False)
     pairs = [0, 0]
-    pairs[1], _ = step(0, count_only=True)   # step 0 uses rows[1] = B
-    pairs[0], _ = step(1, count_only=True)
+    pairs[1] = owned_pairs(1)                 # step s uses buffer (s + 1) % 2
+    pairs[0] = owned_pairs(0)
     for s in range(max(args.warmup, 3)):
-        step(s)
-    torch.cuda.synchronize()
-    dist.barrier()
-    import os
-    if os.environ.get("PNB_PROFILE_EXCHANGE") and rank == 0:
-        from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            for s in range(4):
-                step(s)
-            torch.cuda.synchronize()
-        os.makedirs("gpurun_out", exist_ok=True)
-        with open("gpurun_out/exchange_prof_rank0.txt", "w") as fh:
-            fh.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45))
-    elif os.environ.get("PNB_PROFILE_EXCHANGE"):
-        for s in range(4):
-            step(s)
+        step(s, ovl=overlap)
     torch.cuda.synchronize()
     dist.barrier()
     launches0 = int(_lib.lib().pnb_launch_count())
@@ -480,43 +656,76 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     torch.cuda.synchronize()
     ev0.record()
     my_pairs = 0
+    n_overlapped = 0
     for s in range(args.steps):
-        step(s, timed=True)
+        step(s, timed=True, ovl=overlap)
+        n_overlapped += int(stepper.last.get("overlapped", False))
         my_pairs += pairs[(s + 1) % 2]
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
     ms = ev0.elapsed_time(ev1)
-    phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in phase_ev]).mean(0)
-    t = torch.tensor([ms, float(my_pairs), float(N), float(ex.last_stats.get("bytes_sent", 0)),
-                      float(ex.last_stats.get("ghosts", 0)), float(phases[0]), float(phases[1]),
-                      float(phases[2])], device=dev, dtype=torch.float64)
+    launches = int(_lib.lib().pnb_launch_count()) - launches0
+    stats = dict(stepper.last)
+    # the same steps without the overlap (exposed exchange = difference), then from host buffers
+    k_ab = max(2, min(args.steps, 4))
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    a0.record()
+    for s in range(k_ab):
+        step(s, ovl=False)
+    a1.record()
+    torch.cuda.synchronize()
+    ms_noovl = a0.elapsed_time(a1) / k_ab
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_pairs = 0
+    for s in range(k_ab):
+        step(s, ovl=overlap, e2e=True)
+        e2e_pairs += pairs[(s + 1) % 2]
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / k_ab
+    h2d = int(sum(t.numel() * 4 for t in host[0]))
+    d2h = int(n_cur[0] * 16)
+    t = torch.tensor([ms, float(my_pairs), float(N), float(stats.get("bytes_sent", 0)),
+                      float(stats.get("ghosts", 0)), ms_noovl, e2e_ms, float(e2e_pairs), float(h2d),
+                      float(d2h), float(n_overlapped)], device=dev, dtype=torch.float64)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone()
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    launches = int(_lib.lib().pnb_launch_count()) - launches0
+    tmin = t.clone()
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     if rank == 0:
         ms_max = float(tmax[0])
         total_pairs = float(tsum[1])
+        gs = ex.grid_size
         line = {
             "metric": metric, "value": total_pairs / (ms_max * 1e-3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong" if strong > 0 else "weak",
+            "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"WCSPH step 3D, slab-decomposed: {n}x{n}x{nz} = {int(tsum[2])} particles "
-                                   f"over {world} GPUs ({nz // world} lattice layers per GPU, ~BASELINE config 5), "
-                                   "per step: migrant+ghost exchange (NCCL send/recv), update!, interact!",
+            "config": {"workload": f"WCSPH step 3D, slab-decomposed (BASELINE config 5): {n}^3 = {int(tsum[2])} "
+                                   f"particles, {gs[0]}x{gs[1]}x{gs[2]} cells, over {world} GPU(s) "
+                                   f"({(gs[2] - 2) // world} cell layers per GPU), per step: migrant + ghost "
+                                   "exchange (NCCL send/recv), update!, interact! of the owned layers",
                        "particles_total": int(tsum[2]), "search_radius": float(r),
+                       "velocities": "zero (reference benchmark)",
                        "ghost_points_per_rank_max": int(tmax[4]),
                        "exchange_bytes_per_rank_max": int(tmax[3]),
                        "l2": "per-GPU inputs larger than the 126 MB L2"},
-            "phase_ms_max_over_ranks": {"exchange": float(tmax[5]), "update": float(tmax[6]),
-                                        "interact": float(tmax[7])},
+            "overlap": {"enabled": overlap, "steps_overlapped_min_over_ranks": int(tmin[10]),
+                        "ms_per_step_without_overlap": float(tmax[5]),
+                        "what": "exchange on a side stream behind the sweep of the interior layers; the "
+                                "boundary layers (2 per side) wait for it"},
             "gpu_launches": launches,
-            "e2e": None,
-            "note": "device-resident multi-GPU step; the host-buffer e2e number is measured at N = 1",
+            "e2e": {"value": float(tsum[7]) / k_ab / (float(tmax[6]) * 1e-3), "unit": unit,
+                    "h2d_bytes_per_step": int(tsum[8]), "d2h_bytes_per_step": int(tsum[9]),
+                    "ms_per_step": float(tmax[6]), "steps": k_ab,
+                    "mode": "every rank copies the coordinates, state and pressure of its owned rows from "
+                            "pinned host memory before the step and its dv back after it (serial, wall "
+                            "clock, max over ranks)"},
         }
         print(json.dumps(line))
     dist.barrier()

@@ -917,8 +917,34 @@ def test_float64_search(pn, oracle, size):
     assert [g[1] for g in got] == [float(v) for v in dx[off_x[5]:off_x[6]]]
     with pytest.raises(TypeError):
         pn.initialize_(nhs, ty.float(), ty.float())
+    # fused closures in Float64: the oracle's IEEE double operation sequence, candidates in the
+    # reference's order -> bit-identical sums (n-body in every dimension, WCSPH in 2-D / 3-D)
+    mass = (1e10 * (rng.random(len(y)) + 1)).astype(T)
+    G = T(6.6743e-11)
+    dv = torch.full((len(y), nd), 3.0, dtype=torch.float64, device="cuda")
+    pn.foreach_point_neighbor(pn.NBodyGravity(dv, torch.as_tensor(mass, device="cuda"), G), ty, ty, nhs)
+    assert np.array_equal(dv.cpu().numpy(), og.nbody(y, y, mass, G))
+    dvx = torch.zeros((60, nd), dtype=torch.float64, device="cuda")
+    pn.foreach_point_neighbor(pn.NBodyGravity(dvx, torch.as_tensor(mass, device="cuda"), G), tx, ty, nhs,
+                              points=pts)
+    assert np.array_equal(dvx.cpu().numpy()[pts], og.nbody(x, y, mass, G, points=pts)[pts])
+    if nd >= 2:
+        rho = (1000.0 + rng.random(len(y))).astype(T)
+        v = np.concatenate([rng.normal(0, 0.1, (len(y), nd)), rho[:, None]], axis=1).astype(T)
+        m = np.full(len(y), 0.1 * (r / 3), T)
+        p = (100.0 * (rho - 1000.0)).astype(T)
+        h = T(r / 2)
+        sigma = 21.0 / (16.0 * np.pi) / h ** 3 if nd == 3 else 7.0 / (4.0 * np.pi) / h ** 2
+        tv, tm, tp = (torch.as_tensor(a, device="cuda") for a in (v, m, p))
+        dvw = torch.zeros((len(y), nd + 1), dtype=torch.float64, device="cuda")
+        f = pn.WCSPHInteract(dvw, tv, tv, tm, tm, tp, tp, smoothing_length=h, sound_speed=T(10.0),
+                             alpha=0.02, beta=0.3, epsilon=0.01, delta=0.1, kernel_norm=T(sigma), ndims_=nd)
+        pn.foreach_point_neighbor(f, ty, ty, nhs)
+        prm = np.array(f.params64, dtype=T)
+        assert np.array_equal(dvw.cpu().numpy(), og.wcsph(y, y, v, v, m, m, p, p, prm))
     with pytest.raises(TypeError):
-        pn.foreach_point_neighbor(pn.NBodyGravity(None, None, 1.0), ty, ty, nhs)
+        pn.foreach_point_neighbor(pn.TLSPHDeformationGradient(None, None, None, None, None,
+                                                              smoothing_length=1.0), ty, ty, nhs)
 
 
 def test_float64_periodic(pn, oracle):
