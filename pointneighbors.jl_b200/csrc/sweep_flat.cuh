@@ -78,7 +78,7 @@ struct has_pair_pred { static constexpr bool value = false; };
 template <class CL>
 struct has_pair_pred<CL, decltype((void)&CL::template pair_tile_pred<3>)> { static constexpr bool value = true; };
 
-struct FlatTile {
+struct alignas(16) FlatTile {
     uint32_t cell;   // linear index of the first cell with points of the tile
     uint32_t off;    // first point of the tile inside that cell
     uint32_t npts;   // points of the tile (1 .. kFTP)

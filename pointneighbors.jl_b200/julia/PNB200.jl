@@ -205,12 +205,28 @@ function initialize!(nhs::B200GridNeighborhoodSearch{NDIMS, T}, x::B200Array{T, 
 end
 
 # update!(nhs, x, y; points_moving, eachindex_y)      src/nhs_grid.jl:283-292
+# blocking = false (no reference counterpart, the reference synchronises after every launch,
+# src/util.jl:166-170): the rebuild is only enqueued; a domain error is raised by the next
+# blocking call on the search or by check!(nhs).  Float32 full rebuilds only.
 function update!(nhs::B200GridNeighborhoodSearch{NDIMS, T}, x::B200Array{T, 2},
                  y::B200Array{T, 2}; points_moving = (true, true),
                  parallelization_backend = default_backend(x),
-                 eachindex_y = axes(y, 2)) where {NDIMS, T <: Union{Float32, Float64}}
+                 eachindex_y = axes(y, 2), blocking = true) where {NDIMS, T <: Union{Float32, Float64}}
     points_moving[2] || return nhs
+    if !blocking && T === Float32 && is_all(eachindex_y, size(y, 2))
+        check(ccall((:pnb_grid_build_async_f32, libpnb200), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                    nhs.handle, y.ptr, size(y, 2), C_NULL))
+        nhs.y_ref = y
+        return nhs
+    end
     return initialize!(nhs, x, y; eachindex_y)
+end
+
+# synchronise and raise what a blocking update! would have raised
+function check!(nhs::B200GridNeighborhoodSearch)
+    check(ccall((:pnb_grid_check, libpnb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), nhs.handle, C_NULL))
+    return nhs
 end
 
 # copy_neighborhood_search(nhs, search_radius, n_points)      src/nhs_grid.jl:640-649
@@ -308,6 +324,95 @@ function foreach_point_neighbor(f::WCSPHInteract, x::B200Array{Float32, 2},
                 f.mass_y.ptr, f.pressure_x.ptr, f.pressure_y.ptr, prm, f.dv.ptr, C_NULL))
     return nothing
 end
+
+# stream-ordered form (x === y, all points): nothing is synchronised, check!(nhs) settles it
+function foreach_point_neighbor_async(f::WCSPHInteract, y::B200Array{Float32, 2},
+                                      nhs::B200GridNeighborhoodSearch)
+    prm = Ref(f.params)
+    check(ccall((:pnb_wcsph_interact_async_f32, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ref{WcsphParams}, Ptr{Cvoid}, Ptr{Cvoid}),
+                nhs.handle, y.ptr, size(y, 2), f.v_y.ptr, f.mass_y.ptr, f.pressure_y.ptr, prm,
+                f.dv.ptr, C_NULL))
+    return nothing
+end
+
+# Float64 searches: the fused closures with Float64 arrays (bit-identical to the Float64 oracle)
+struct NBodyGravity64{A, M}
+    dv   :: A
+    mass :: M
+    G    :: Float64
+end
+struct WcsphParams64                        # pnb_wcsph_params_f64
+    smoothing_length :: Cdouble
+    sound_speed      :: Cdouble
+    alpha            :: Cdouble
+    beta             :: Cdouble
+    epsilon          :: Cdouble
+    delta            :: Cdouble
+    kernel_norm      :: Cdouble
+end
+struct WCSPHInteract64{A}
+    dv :: A; v_x :: A; v_y :: A
+    mass_x :: Any; mass_y :: Any; pressure_x :: Any; pressure_y :: Any
+    params :: WcsphParams64
+end
+function foreach_point_neighbor(f::NBodyGravity64, x::B200Array{Float64, 2}, y::B200Array{Float64, 2},
+                                nhs::B200GridNeighborhoodSearch{NDIMS, Float64};
+                                parallelization_backend = default_backend(x),
+                                points = axes(x, 2)) where {NDIMS}
+    pv, np = points_arg(points, size(x, 2))
+    GC.@preserve pv check(ccall((:pnb_nbody_f64, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint,
+                 Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}),
+                nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2),
+                pv === C_NULL ? C_NULL : pv.ptr, np, 1, f.mass.ptr, f.G, f.dv.ptr, C_NULL))
+    return nothing
+end
+function foreach_point_neighbor(f::WCSPHInteract64, x::B200Array{Float64, 2}, y::B200Array{Float64, 2},
+                                nhs::B200GridNeighborhoodSearch{NDIMS, Float64};
+                                parallelization_backend = default_backend(x),
+                                points = axes(x, 2)) where {NDIMS}
+    pv, np = points_arg(points, size(x, 2))
+    prm = Ref(f.params)
+    GC.@preserve pv check(ccall((:pnb_wcsph_interact_f64, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint,
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ref{WcsphParams64}, Ptr{Cvoid}, Ptr{Cvoid}),
+                nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2),
+                pv === C_NULL ? C_NULL : pv.ptr, np, 1, f.v_x.ptr, f.v_y.ptr, f.mass_x.ptr,
+                f.mass_y.ptr, f.pressure_x.ptr, f.pressure_y.ptr, prm, f.dv.ptr, C_NULL))
+    return nothing
+end
+
+# The WCSPH step from HOST arrays, pipelined inside the library (pnb_hoststep_*): what a host-side
+# caller does per step -- copy coordinates and state to the device, update!, interact!, copy dv
+# back -- with the copies of neighbouring steps overlapping the kernels.  Host arrays should be
+# pinned (pnb_malloc_host) for the overlap.
+mutable struct HostStepper
+    handle :: Ptr{Cvoid}
+    nhs    :: B200GridNeighborhoodSearch
+    keep   :: Vector{Any}
+    function HostStepper(nhs::B200GridNeighborhoodSearch, n_points::Integer)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:pnb_hoststep_create, libpnb200), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
+                    nhs.handle, n_points, ref))
+        s = new(ref[], nhs, Any[])
+        finalizer(z -> ccall((:pnb_hoststep_destroy, libpnb200), Cvoid, (Ptr{Cvoid},), z.handle), s)
+        return s
+    end
+end
+function submit!(s::HostStepper, y::Matrix{Float32}, v::Matrix{Float32}, pressure::Vector{Float32},
+                 dv::Matrix{Float32}, params::WcsphParams; mass::Union{Nothing, Vector{Float32}} = nothing)
+    push!(s.keep, (y, v, pressure, dv, mass)); length(s.keep) > 3 && popfirst!(s.keep)
+    prm = Ref(params)
+    check(ccall((:pnb_hoststep_wcsph_submit, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{WcsphParams},
+                 Ptr{Cfloat}),
+                s.handle, y, v, isnothing(mass) ? C_NULL : mass, pressure, prm, dv))
+    return s
+end
+Base.wait(s::HostStepper) = (check(ccall((:pnb_hoststep_wait, libpnb200), Cint, (Ptr{Cvoid},), s.handle)); s)
 
 # Any other f: the pairs are found on the device (neighbour list), f runs on the host over the
 # exported CSR.  f must only touch host data (scalar indexing of a B200Array is not defined).

@@ -84,6 +84,7 @@ def _julia_types_for(cparam):
                  "int": {"Ptr{Cint}", "Ref{Cint}"}, "uint32_t": {"Ptr{UInt32}"}, "uint8_t": {"Ptr{UInt8}"},
                  "pnb_wcsph_params": {"Ref{WcsphParams}", "Ptr{WcsphParams}"},
                  "pnb_tlsph_params": {"Ref{TlsphParams}", "Ptr{TlsphParams}"},
+                 "pnb_wcsph_params_f64": {"Ref{WcsphParams64}", "Ptr{WcsphParams64}"},
                  "pnb_slab_arrays": {"Ref{SlabArrays}"},
                  "char": {"Cstring", "Ptr{UInt8}"}}
         return generic | typed.get(tname, set())
