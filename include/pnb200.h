@@ -263,6 +263,11 @@ void pnb_set_sweep_left(int mode);
  * closures, which it serves faster; 2 = always k_sweep_flat, 0 = always k_sweep_tiles (A/B
  * measurements, tests).  Same results. */
 void pnb_set_sweep_kernel(int flat);
+/* k_sweep_flat is a persistent kernel (one CTA per slot of every SM): kernels of OTHER streams --
+ * the NCCL send / recv of the overlapped multi-GPU step, which need a mostly empty SM -- would not
+ * run before it ends.  pnb_set_sweep_reserve(n) makes the CTAs that land on the last n SMs leave at
+ * once (default 0), so that those SMs stay free. */
+void pnb_set_sweep_reserve(int sms);
 /* Measurement variants of the counting-sort kernels (bits: 1 histogram reads 4 consecutive points
  * per thread straight from global memory, 2 staged scatter with the lane-strided mapping,
  * 4 staged histogram with it, 8 scatter without staging, 16 histogram without staging and with
@@ -326,14 +331,18 @@ pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, int64_t n, 
  * pnb_grid_check, pnb_slab_compact_f32.
  *   pnb_grid_append_f32: the points y[first .. first + n_more) join the bucket cell list built from
  *     y[0 .. first) (ids first + k); y must be the array of that build.
- *   pnb_wcsph_interact_layers_async_f32: gather the payload of the cell layers [gz_a, gz_b], then
- *     sweep the layers [cz_a, cz_b] (local 1-based cell coordinates of the last dimension); dv is
- *     zeroed first when zero_dv != 0.  Nothing is synchronised. */
+ *   pnb_wcsph_interact_layers_async_f32: sweep the cell layers [cz_a, cz_b] and [cz_c, cz_d] (local
+ *     1-based cell coordinates of the last dimension, an empty range has first > last) with one
+ *     launch, after gathering the payload of these layers and their neighbours.  dv is written for
+ *     the points of the swept layers only.  Nothing is synchronised.
+ *   pnb_slab_pack_rows_f32: rows of `arrays` listed in `list` -> contiguous send buffer. */
 pnb_status pnb_grid_append_f32(pnb_grid *g, const float *y, int64_t first, int64_t n_more, void *stream);
+pnb_status pnb_slab_pack_rows_f32(const pnb_slab_arrays *arrays, const int32_t *list, int64_t count,
+                                  float *dst, void *stream);
 pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const float *y, int64_t n, const float *v,
                                                const float *mass, const float *pressure,
                                                const pnb_wcsph_params *params, float *dv, int cz_a,
-                                               int cz_b, int gz_a, int gz_b, int zero_dv, void *stream);
+                                               int cz_b, int cz_c, int cz_d, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The WCSPH step from HOST buffers, pipelined (the end-to-end call of a host-side caller).

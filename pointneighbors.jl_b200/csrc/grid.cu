@@ -2136,6 +2136,19 @@ extern "C" pnb_status pnb_slab_pack_f32(const pnb_slab_arrays *arrays, int64_t n
     return PNB_OK;
 }
 
+// rows of `arrays` listed in list[0 .. count) -> dst (count x row_width), stream-ordered: the
+// second half of pnb_slab_pack_f32 for callers that classify on another stream
+extern "C" pnb_status pnb_slab_pack_rows_f32(const pnb_slab_arrays *arrays, const int32_t *list,
+                                             int64_t count, float *dst, void *stream)
+{
+    if (!arrays || arrays->n_arrays < 1 || arrays->n_arrays > 8) { set_error("bad arrays"); return PNB_ERR_ARG; }
+    if (count <= 0) return PNB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_slab_pack<<<(unsigned)div_up(count, 256), 256, 0, s>>>(*arrays, slab_row_width(arrays), list, count, dst);
+    PNB_LAUNCHED();
+    return PNB_OK;
+}
+
 extern "C" pnb_status pnb_slab_unpack_f32(const pnb_slab_arrays *arrays, int64_t n, int ndims,
                                           float padded_min_z, float cell_size_z, int64_t z_lo,
                                           int64_t z_hi, int has_up, int has_down,
@@ -2307,6 +2320,7 @@ extern "C" pnb_status pnb_slab_compact_f32(const pnb_slab_arrays *arrays, int64_
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n_new = n_own - n_leave + n_mig, n_rows = n_own + n_app;
     const int64_t cap = n_leave + n_app + 8;
+    if (n_leave == 0 && n_mig == 0) return PNB_OK;      // nothing leaves, nothing joins
     if (n_own > 0) PNB_CUDA(cudaMemsetAsync(flags, 1, (size_t)n_own, s));
     PNB_CUDA(cudaMemsetAsync(counters_dev + 2, 0, 2 * sizeof(int32_t), s));
     if (n_leave > 0) {

@@ -63,6 +63,7 @@ int g_tune_wpc = 0;
 int g_tune_half = -1;
 int g_tune_twoset = 1;
 int g_tune_left = getenv("PNB_SWEEP_LEFT") ? atoi(getenv("PNB_SWEEP_LEFT")) : 1;
+int g_reserve_ctas = 0;
 int g_tune_flat = getenv("PNB_SWEEP_FLAT") ? atoi(getenv("PNB_SWEEP_FLAT")) : 1;
 
 static bool is_fast_path(const pnb_grid *g, const void *x, int64_t nx, const int32_t *points);
@@ -121,6 +122,7 @@ extern "C" int pnb_get_exact_arithmetic(void) { return g_exact_arithmetic; }
 extern "C" void pnb_set_twoset_tiles(int on) { g_tune_twoset = on; }
 extern "C" void pnb_set_sweep_left(int mode) { g_tune_left = mode; }
 extern "C" void pnb_set_sweep_kernel(int flat) { g_tune_flat = flat; }
+extern "C" void pnb_set_sweep_reserve(int ctas) { g_reserve_ctas = ctas; }
 extern "C" void pnb_set_tuning(int warps_per_cell, int half_prefilter)
 {
     g_tune_wpc = warps_per_cell;
@@ -287,17 +289,18 @@ extern "C" pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, 
     return st;
 }
 
-// The WCSPH sweep of the cell layers [cz_a, cz_b] (local 1-based coordinates of the LAST used
-// dimension) only, stream-ordered: the payload of the layers [gz_a, gz_b] is gathered first
-// (gz_a > gz_b: nothing), dv is zeroed when zero_dv != 0.  The overlapped multi-GPU step sweeps
-// the interior layers of a slab while the ghost layers are still in flight, then appends them
-// (pnb_grid_append_f32) and sweeps the boundary layers.  Needs the one-pass (bucket) layout.
+// The WCSPH sweep of the cell layers [cz_a, cz_b] and [cz_c, cz_d] (local 1-based coordinates of
+// the LAST used dimension; an empty range has first > last) only, stream-ordered: the payload of
+// the layers [cz_a - 1, cz_b + 1] and [cz_c - 1, cz_d + 1] is gathered first.  The overlapped
+// multi-GPU step sweeps the interior layers of a slab while the ghost layers are still in flight,
+// then appends them (pnb_grid_append_f32) and sweeps the boundary layers of both sides with one
+// launch.  Needs the one-pass (bucket) layout.
 extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const float *y, int64_t n,
                                                           const float *v, const float *mass,
                                                           const float *pressure,
                                                           const pnb_wcsph_params *params, float *dv,
-                                                          int cz_a, int cz_b, int gz_a, int gz_b,
-                                                          int zero_dv, void *stream)
+                                                          int cz_a, int cz_b, int cz_c, int cz_d,
+                                                          void *stream)
 {
     if (!g || !params) { set_error("NULL argument"); return PNB_ERR_ARG; }
     if (g->f64 || g->hashed || g->p.periodic || !g->built || !g->bucket_valid || g->bucket_tr ||
@@ -308,12 +311,11 @@ extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const flo
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int nd = g->p.ndims;
+    if (nd < 2) { set_error("the layered sweep needs 2 or 3 dimensions"); return PNB_ERR_ARG; }
     const int gl = g->p.gs[nd - 1];
-    if (cz_a < 2) cz_a = 2;
-    if (cz_b > gl - 1) cz_b = gl - 1;
-    if (gz_a < 1) gz_a = 1;
-    if (gz_b > gl) gz_b = gl;
-    if (zero_dv && n > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)n * (nd + 1), s));
+    auto clip = [&](int &a, int &b) { if (a < 2) a = 2; if (b > gl - 1) b = gl - 1; };
+    clip(cz_a, cz_b);
+    clip(cz_c, cz_d);
     const int64_t nb = view_slots(g);
     const int64_t off_mp = ((int64_t)sizeof(float4) * nb + 255) / 256 * 256;
     pnb_status st = ensure_scratch(g, off_mp + (int64_t)sizeof(float4) * nb);
@@ -322,15 +324,27 @@ extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const flo
     float2 *vp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(g->scratch) + off_mp);
     int64_t layer_cells = 1;
     for (int d = 0; d < nd - 1; d++) layer_cells *= g->p.gs[d];
-    if (gz_a <= gz_b) {
-        const int64_t i0 = (int64_t)(gz_a - 1) * layer_cells * g->bucket_K;
-        const int64_t i1 = (int64_t)gz_b * layer_cells * g->bucket_K;
+    auto gather = [&](int ga, int gb) -> pnb_status {
+        if (ga < 1) ga = 1;
+        if (gb > gl) gb = gl;
+        if (ga > gb) return PNB_OK;
+        const int64_t i0 = (int64_t)(ga - 1) * layer_cells * g->bucket_K;
+        const int64_t i1 = (int64_t)gb * layer_cells * g->bucket_K;
         ProfScope ps(PH_GATHER, s);
         k_gather_wcsph<<<(unsigned)div_up(i1 - i0, 256), 256, 0, s>>>(i1, nd, cells_view(g), v, mass, pressure,
                                                                      vrho, nullptr, vp, i0);
         PNB_LAUNCHED();
+        return PNB_OK;
+    };
+    const bool has1 = cz_a <= cz_b, has2 = cz_c <= cz_d;
+    if (!has1 && !has2) return PNB_OK;
+    if (has1 && has2 && cz_c - 1 <= cz_b + 1 && cz_a - 1 <= cz_d + 1) {
+        st = gather(min(cz_a, cz_c) - 1, max(cz_b, cz_d) + 1);      // the two ranges touch
+    } else {
+        st = has1 ? gather(cz_a - 1, cz_b + 1) : PNB_OK;
+        if (st == PNB_OK && has2) st = gather(cz_c - 1, cz_d + 1);
     }
-    if (cz_a > cz_b) return PNB_OK;
+    if (st != PNB_OK) return st;
     const float h = params->smoothing_length;
     const float inv_h = -0.5f / h, kh = -5.0f * params->kernel_norm / (h * h);
     const float ac = params->alpha * params->sound_speed;
@@ -338,9 +352,8 @@ extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const flo
     const bool in_radius = 2.0f * h <= g->p.r;
     const WcsphClT<false> cl{vrho, nullptr, v, pressure, *params, dv, nd, inv_h, kh, ac, dhc2, in_radius, vp};
     const CellsView cv = cells_view(g);
-    switch (nd) {
-        case 2: return launch_flat<2, false, WcsphClT<false>, false>(g, cv, cv, n, cl, cz_a - 2, cz_b - cz_a + 1, s);
-        case 3: return launch_flat<3, false, WcsphClT<false>, false>(g, cv, cv, n, cl, cz_a - 2, cz_b - cz_a + 1, s);
-        default: set_error("the layered sweep needs 2 or 3 dimensions"); return PNB_ERR_ARG;
-    }
+    const int l0 = has1 ? cz_a - 2 : 0, n0 = has1 ? cz_b - cz_a + 1 : 0;
+    const int l1 = has2 ? cz_c - 2 : 0, n1 = has2 ? cz_d - cz_c + 1 : 0;
+    if (nd == 2) return launch_flat<2, false, WcsphClT<false>, false>(g, cv, cv, n, cl, l0, n0, s, l1, n1);
+    return launch_flat<3, false, WcsphClT<false>, false>(g, cv, cv, n, cl, l0, n0, s, l1, n1);
 }

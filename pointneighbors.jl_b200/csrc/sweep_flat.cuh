@@ -85,8 +85,9 @@ struct alignas(16) FlatTile {
     uint32_t pad_;
 };
 // control words of one sweep: [0] number of tiles, [1] tile counter of the persistent CTAs,
-// [2] overflow tiles, [3] unused
+// [2] overflow tiles, [3] SMs that have reported in (reserved-SM election)
 constexpr int kFlatCtl = 4;
+constexpr int kFlatSmStates = 1024;   // per-SM state words behind the control words (pnb_set_sweep_reserve)
 
 template <int ND, class CL>
 __host__ __device__ constexpr size_t flat_smem_bytes()
@@ -117,7 +118,8 @@ __device__ __forceinline__ void group_barrier(int group, int nthreads)
 // layers (last used dimension) that are swept: all of them, or the layers of one slab pass.
 template <int ND, bool EMIT>
 __global__ void __launch_bounds__(128)
-k_flat_tiles(GridP g, CellsView qry, int lay0, int n_lay, int n_seg_row, uint32_t *__restrict__ seg_tiles,
+k_flat_tiles(GridP g, CellsView qry, int lay0, int n_lay, int lay1, int n_lay1, int n_seg_row,
+             uint32_t *__restrict__ seg_tiles,
              const uint32_t *__restrict__ seg_first, FlatTile *__restrict__ tiles,
              uint32_t *__restrict__ ctl, uint32_t n_ctas)
 {
@@ -126,22 +128,26 @@ k_flat_tiles(GridP g, CellsView qry, int lay0, int n_lay, int n_seg_row, uint32_
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int nx = g.gs[0] - 2;
     const int ny = ND > 1 ? g.gs[1] - 2 : 1;
-    const int nrow_y = (ND == 2) ? n_lay : ny;            // rows per layer selection
-    const int nrow_z = (ND == 3) ? n_lay : 1;
+    // two layer ranges: [lay0, lay0 + n_lay) and [lay1, lay1 + n_lay1) (the second may be empty)
+    const int nrow_y = (ND == 2) ? n_lay + n_lay1 : ny;   // rows per layer selection
+    const int nrow_z = (ND == 3) ? n_lay + n_lay1 : 1;
     const int64_t n_segs = (int64_t)n_seg_row * nrow_y * nrow_z;
     const int64_t seg = (int64_t)blockIdx.x * 4 + warp;
     if (EMIT && blockIdx.x == 0 && threadIdx.x == 0) {
         ctl[1] = n_ctas;          // tile counter: the first n_ctas tiles are taken by blockIdx
         ctl[2] = 0u;              // overflow tiles
+        ctl[3] = 0u;
     }
+    if (EMIT && blockIdx.x == 0)
+        for (int k = threadIdx.x; k < kFlatSmStates; k += blockDim.x) ctl[kFlatCtl + k] = 0u;
     if (seg >= n_segs) return;
     int64_t b = seg;
     const int isg = (int)(b % n_seg_row); b /= n_seg_row;
     const int iy = (int)(b % nrow_y);     b /= nrow_y;
     const int iz = (int)b;
     int cy = 1, cz = 1;
-    if (ND == 2) cy = 2 + lay0 + iy;
-    if (ND == 3) { cy = 2 + iy; cz = 2 + lay0 + iz; }
+    if (ND == 2) cy = 2 + (iy < n_lay ? lay0 + iy : lay1 + (iy - n_lay));
+    if (ND == 3) { cy = 2 + iy; cz = 2 + (iz < n_lay ? lay0 + iz : lay1 + (iz - n_lay)); }
     const int cxa = 2 + isg * kFSegCells;                         // first cell of the segment
     const int ncell = min(kFSegCells, nx - isg * kFSegCells);     // its cells
     uint32_t *W = s_w[warp], *P = s_p[warp];
@@ -230,8 +236,33 @@ __host__ __device__ constexpr int flat_min_blocks()
 template <int ND, bool PER, class CL, bool TWO>
 __global__ void __launch_bounds__(kFG * flat_wpc<CL>() * 32, flat_min_blocks<ND, CL>())
 k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__restrict__ tiles,
-             uint32_t *__restrict__ ctl, int *__restrict__ overflow_tiles)
+             uint32_t *__restrict__ ctl, int *__restrict__ overflow_tiles, int reserve_sms)
 {
+    // A persistent grid that fills every SM keeps the kernels of other streams (the NCCL send /
+    // recv of the overlapped multi-GPU step need a mostly empty SM) from running before it ends:
+    // CTAs that find themselves on one of the last `reserve_sms` SMs leave at once, the others
+    // take their tiles from the common counter.
+    // (SM ids need not be contiguous: the first `reserve_sms` DISTINCT SMs that report in are the
+    // reserved ones.  sm_state[smid]: 0 unseen, 1 being decided, 2 reserved, 3 working.)
+    if (reserve_sms > 0) {
+        __shared__ int s_leave;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned *sm_state = ctl + kFlatCtl + (smid & 1023u);
+            unsigned st = atomicCAS(sm_state, 0u, 1u);
+            if (st == 0u) {
+                const unsigned rank = atomicAdd(ctl + 3, 1u);
+                st = rank < (unsigned)reserve_sms ? 2u : 3u;
+                atomicExch(sm_state, st);
+            } else {
+                while (st < 2u) st = atomicAdd(sm_state, 0u);
+            }
+            s_leave = st == 2u;
+        }
+        __syncthreads();
+        if (s_leave) return;
+    }
     constexpr int kWPC = flat_wpc<CL>();
     constexpr int NR = rows_of(ND);
     constexpr int NEmax = kFNSL * NR;
@@ -335,6 +366,12 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
     };
     uint32_t cur = blockIdx.x, nxt = 0xffffffffu;            // warp 0: this tile, the one after it
     if (warp == 0) {
+        // (with reserved SMs the CTAs that left do not take the tile of their blockIdx: every
+        // tile index then comes from the counter, which the tile pre-pass set to 0)
+        if (reserve_sms > 0) {
+            if (lane == 0) cur = atomicAdd(ctl + 1, 1u);
+            cur = __shfl_sync(0xffffffffu, cur, 0);
+        }
         if (lane == 0) nxt = atomicAdd(ctl + 1, 1u);
         nxt = __shfl_sync(0xffffffffu, nxt, 0);
         if (cur < n_tiles) {

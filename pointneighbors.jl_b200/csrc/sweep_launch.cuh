@@ -12,6 +12,7 @@ extern int g_tune_wpc;    // pnb_set_tuning: warps per cell override (0 = closur
 extern int g_tune_half;   // pnb_set_tuning: 0 = exact Float32 test instead of the fp16 pre-filter
 extern int g_tune_twoset; // pnb_set_twoset_tiles: 0 = x != y always uses the per-point kernel
 extern int g_tune_left;   // pnb_set_sweep_left / PNB_SWEEP_LEFT: 0 never, 1 default, 2 always (tests)
+extern int g_reserve_ctas; // pnb_set_sweep_reserve: SMs the persistent sweep leaves to other streams' kernels
 extern int g_tune_flat;   // pnb_set_sweep_kernel / PNB_SWEEP_FLAT: 1 (default) k_sweep_flat except for
                           // count-only closures, 2 always k_sweep_flat, 0 always k_sweep_tiles
 
@@ -74,14 +75,17 @@ k_flat_scan(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t
 // overlapped multi-GPU step): tile table (3 small kernels), persistent sweep, overflow tiles.
 template <int ND, bool PER, class CL, bool TWO>
 static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsView &qry, int64_t n_q,
-                              const CL &cl, int lay0, int n_lay, cudaStream_t s)
+                              const CL &cl, int lay0, int n_lay, cudaStream_t s, int lay1 = 0,
+                              int n_lay1 = 0)
 {
     const int nxc = g->p.gs[0] - 2;
     const int nyc = ND > 1 ? g->p.gs[1] - 2 : 1;
-    if (ND == 1) { lay0 = 0; n_lay = 1; }
-    if (nxc <= 0 || n_lay <= 0 || n_q <= 0) return PNB_OK;
+    if (ND == 1) { lay0 = 0; n_lay = 1; n_lay1 = 0; }
+    if (n_lay < 0) n_lay = 0;
+    if (n_lay1 < 0) n_lay1 = 0;
+    if (nxc <= 0 || n_lay + n_lay1 <= 0 || n_q <= 0) return PNB_OK;
     const int n_seg_row = (int)div_up(nxc, kFSegCells);
-    const int64_t rows = ND == 3 ? (int64_t)nyc * n_lay : (ND == 2 ? n_lay : 1);
+    const int64_t rows = ND == 3 ? (int64_t)nyc * (n_lay + n_lay1) : (ND == 2 ? n_lay + n_lay1 : 1);
     const int64_t n_segs = (int64_t)n_seg_row * rows;
     // non-empty tiles: at most one per query point, and at most the weighted length / 96 + 1 per segment
     int64_t max_tiles = (n_q + (int64_t)kFMinW * nxc * rows) / kFTP + n_segs + 1;
@@ -101,8 +105,8 @@ static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsVie
         g->flat_seg_cap = n_segs + 64;
     }
     if (!g->flat_ctl) {
-        PNB_CUDA(cudaMalloc(&g->flat_ctl, sizeof(uint32_t) * kFlatCtl));
-        PNB_CUDA(cudaMemsetAsync(g->flat_ctl, 0, sizeof(uint32_t) * kFlatCtl, s));
+        PNB_CUDA(cudaMalloc(&g->flat_ctl, sizeof(uint32_t) * (kFlatCtl + kFlatSmStates)));
+        PNB_CUDA(cudaMemsetAsync(g->flat_ctl, 0, sizeof(uint32_t) * (kFlatCtl + kFlatSmStates), s));
     }
     uint32_t *seg_tiles = g->flat_seg, *seg_first = g->flat_seg + (g->flat_seg_cap + 1);
     FlatTile *tiles = reinterpret_cast<FlatTile *>(g->flat_tiles);
@@ -120,22 +124,24 @@ static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsVie
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g->device);
+    // pnb_set_sweep_reserve: SMs the persistent grid leaves to the kernels of other streams
     const unsigned n_ctas = (unsigned)(n_sm * ctas_per_sm);
+    const int reserve_sms = g_reserve_ctas > 0 ? (g_reserve_ctas < n_sm / 2 ? g_reserve_ctas : n_sm / 2) : 0;
     {
         ProfScope ps(PH_SWEEP_TILES_PREP, s);
         const unsigned pb = (unsigned)div_up(n_segs, 4);
-        k_flat_tiles<ND, false><<<pb, 128, 0, s>>>(g->p, qry, lay0, n_lay, n_seg_row, seg_tiles, seg_first,
-                                                   tiles, g->flat_ctl, n_ctas);
+        k_flat_tiles<ND, false><<<pb, 128, 0, s>>>(g->p, qry, lay0, n_lay, lay1, n_lay1, n_seg_row, seg_tiles, seg_first,
+                                                   tiles, g->flat_ctl, reserve_sms > 0 ? 0u : n_ctas);
         PNB_LAUNCHED();
         k_flat_scan<<<1, 1024, 0, s>>>(seg_tiles, seg_first, n_segs);
         PNB_LAUNCHED();
-        k_flat_tiles<ND, true><<<pb, 128, 0, s>>>(g->p, qry, lay0, n_lay, n_seg_row, seg_tiles, seg_first,
-                                                  tiles, g->flat_ctl, n_ctas);
+        k_flat_tiles<ND, true><<<pb, 128, 0, s>>>(g->p, qry, lay0, n_lay, lay1, n_lay1, n_seg_row, seg_tiles, seg_first,
+                                                  tiles, g->flat_ctl, reserve_sms > 0 ? 0u : n_ctas);
         PNB_LAUNCHED();
     }
     {
         ProfScope ps(PH_SWEEP_CELLS, s);
-        kern<<<n_ctas, threads, smem, s>>>(g->p, cand, qry, cl, tiles, g->flat_ctl, g->flat_ovf);
+        kern<<<n_ctas, threads, smem, s>>>(g->p, cand, qry, cl, tiles, g->flat_ctl, g->flat_ovf, reserve_sms);
         PNB_LAUNCHED();
     }
     {

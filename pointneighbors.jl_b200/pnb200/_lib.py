@@ -112,7 +112,8 @@ SIGNATURES = {
     "pnb_grid_append_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "pnb_wcsph_interact_layers_async_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp,
                                                       C.POINTER(WcsphParams), _vp, C.c_int, C.c_int,
-                                                      C.c_int, C.c_int, C.c_int, _vp]),
+                                                      C.c_int, C.c_int, _vp]),
+    "pnb_slab_pack_rows_f32": (C.c_int, [C.POINTER(SlabArrays), _vp, _i64, _vp, _vp]),
     "pnb_slab_append_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
                                       _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "pnb_slab_compact_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, _i64, _vp, _i64, _i64, _vp, _vp,
@@ -157,6 +158,7 @@ SIGNATURES = {
     "pnb_set_twoset_tiles": (None, [C.c_int]),
     "pnb_set_sweep_left": (None, [C.c_int]),
     "pnb_set_sweep_kernel": (None, [C.c_int]),
+    "pnb_set_sweep_reserve": (None, [C.c_int]),
     "pnb_profile_enable": (None, [C.c_int]),
     "pnb_profile_reset": (None, []),
     "pnb_profile_phases": (C.c_int, []),

@@ -377,6 +377,7 @@ class OverlappedWCSPHStep:
     overlap.  Results: dv[:n_own_new] belongs to arrays[k][:n_own_new]."""
 
     DEPTH = 2          # boundary layers per side that wait for the exchange
+    RESERVE_CTAS = 2   # SMs the interior sweep leaves to the NCCL kernels
 
     def __init__(self, slab: "SlabNeighborhoodSearch", closure_kwargs: dict):
         import torch
@@ -397,9 +398,10 @@ class OverlappedWCSPHStep:
         t.n_arrays = len(arrs)
         return t
 
-    def step(self, arrays, n, dv, overlap=True):
-        """arrays = [coords (cap, nd), v (cap, nd + 1), mass (cap,), pressure (cap,)], the first n rows
-        owned; dv (cap, nd + 1).  Returns (arrays, dv, n_own_new)."""
+    def step(self, arrays, n, dv, overlap=True, profile=False):
+        """arrays = [coords (cap, nd), v (cap, nd + 1), mass (cap,), pressure (cap,), ...], the first n
+        rows owned; dv (cap, nd + 1).  Returns (arrays, dv, n_own_new).  profile=True records
+        CUDA events between the phases on the main stream (self.last["phase_ms"])."""
         import torch
         from . import api as pn
         L = _lib.lib()
@@ -407,53 +409,75 @@ class OverlappedWCSPHStep:
         dev = arrays[0].device
         main = torch.cuda.current_stream()
         stream = C.c_void_p(main.cuda_stream)
+        sstream = C.c_void_p(self.side.cuda_stream)
         has_up, has_down = ex.rank + 1 < ex.world, ex.rank > 0
         W = sum(1 if a.ndim == 1 else a.shape[1] for a in arrays)
         pmin, cs = np.float32(ex.padded_min[-1]), np.float32(ex.search_radius)
-        # ---- 1. pack (classification of the owned points, rows of the two boundary lists) ----
-        cap = getattr(ex, "_x_cap", 0) or max(n // 8, 1 << 16)
-        while True:
-            if getattr(ex, "_x_bufs", None) is None or ex._x_cap < cap:
-                ex._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
-                ex._x_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
-                ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
-                ex._x_cap = cap
-            counts = (C.c_int64 * 3)()
-            tab = self._table(arrays)
-            check(L.pnb_slab_pack_f32(C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi, int(has_up),
-                                      int(has_down), ex._x_idx[0].data_ptr(), ex._x_idx[1].data_ptr(),
-                                      ex._x_idx[2].data_ptr(), ex._x_cap, ex._x_bufs[0].data_ptr(),
-                                      ex._x_bufs[1].data_ptr(), ex._x_cnt.data_ptr(), counts, stream))
-            if max(counts) <= ex._x_cap:
-                break
-            cap = int(max(counts)) + int(max(counts)) // 4 + 1024
-        n_up, n_down, n_leave = (int(c) for c in counts)
-        send_up, send_down = ex._x_bufs[0][:n_up], ex._x_bufs[1][:n_down]
-        # ---- 2. exchange on the side stream -----------------------------------------------------
-        self.side.wait_stream(main)
+        marks = []
+
+        def mark(name):
+            if profile:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(main)
+                marks.append((name, e))
+
+        mark("start")
         coords = arrays[0]
         closure = pn.WCSPHInteract(dv, arrays[1], arrays[1], arrays[2], arrays[2], arrays[3], arrays[3],
                                    **self.kw)
         off = ex.window[0][-1] - 1                       # local cell layer = global - off
         D = self.DEPTH
         lo_i, hi_i = ex.z_lo + D, ex.z_hi - D            # interior layers (global)
-        can_overlap = overlap and nhs._handle is not None and nhs.layout() == "buckets" and lo_i <= hi_i
         g = nhs._grid()
+        can_overlap = overlap and nhs._handle is not None and nhs.layout() == "buckets" and lo_i <= hi_i
+        # ---- 1. classification of the owned points on the SIDE stream (nothing on the main
+        #         stream waits for it), 2. owned points: stream-ordered update! + interior layers ----
+        self.side.wait_stream(main)
+        cap = getattr(ex, "_x_cap", 0) or max(n // 8, 1 << 16)
+        if getattr(ex, "_x_bufs", None) is None or ex._x_cap < cap:
+            ex._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
+            ex._x_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+            ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
+            ex._x_cap = cap
         if can_overlap:
-            # ---- 3. owned points: stream-ordered update!, interior layers -----------------------
             check(L.pnb_grid_build_async_f32(g, coords.data_ptr(), n, stream))
             nhs._y_ref = coords
             can_overlap = nhs.layout() == "buckets"
+        mark("update!")
         if can_overlap:
+            # the interior sweep is a persistent kernel: leave a few CTA slots free, otherwise the
+            # NCCL kernels of the side stream are not scheduled before it ends (measured: the
+            # whole exchange, 0.43 ms at 8 GPUs, was exposed behind a full grid)
+            L.pnb_set_sweep_reserve(self.RESERVE_CTAS if (has_up or has_down) else 0)
             check(L.pnb_wcsph_interact_layers_async_f32(
                 g, coords.data_ptr(), n, arrays[1].data_ptr(), arrays[2].data_ptr(), arrays[3].data_ptr(),
-                C.byref(closure.params), dv.data_ptr(), lo_i - off, hi_i - off, lo_i - 1 - off,
-                hi_i + 1 - off, 0, stream))
+                C.byref(closure.params), dv.data_ptr(), lo_i - off, hi_i - off, 1, 0, stream))
+            L.pnb_set_sweep_reserve(0)
+        mark("interior")
+        counts = (C.c_int64 * 3)()
+        while True:
+            check(L.pnb_slab_classify_f32(coords.data_ptr(), n, nd, pmin, cs, ex.z_lo, ex.z_hi, int(has_up),
+                                          int(has_down), ex._x_idx[0].data_ptr(), ex._x_idx[1].data_ptr(),
+                                          ex._x_idx[2].data_ptr(), ex._x_cap, ex._x_cnt.data_ptr(), counts,
+                                          sstream))           # synchronises the side stream only
+            if max(counts) <= ex._x_cap:
+                break
+            cap = int(max(counts)) + int(max(counts)) // 4 + 1024
+            ex._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
+            ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
+            ex._x_cap = cap
+        n_up, n_down, n_leave = (int(c) for c in counts)
+        send_up, send_down = ex._x_bufs[0][:n_up], ex._x_bufs[1][:n_down]
+        tab = self._table(arrays)
+        check(L.pnb_slab_pack_rows_f32(C.byref(tab), ex._x_idx[0].data_ptr(), n_up, send_up.data_ptr(), sstream))
+        check(L.pnb_slab_pack_rows_f32(C.byref(tab), ex._x_idx[1].data_ptr(), n_down, send_down.data_ptr(), sstream))
+        # ---- 3. exchange on the side stream ------------------------------------------------------
         with torch.cuda.stream(self.side):
             recv_up, recv_down = ex._sendrecv(send_up, send_down)
         main.wait_stream(self.side)
         recv_up.record_stream(main)
         recv_down.record_stream(main)
+        mark("wait for the exchange")
         n_ru, n_rd = recv_up.shape[0], recv_down.shape[0]
         n_app = n_ru + n_rd
         n_rows = n + n_app
@@ -483,14 +507,15 @@ class OverlappedWCSPHStep:
         redo = not can_overlap
         if can_overlap:
             check(L.pnb_grid_append_f32(g, coords.data_ptr(), n, n_app, stream))
-            # ---- 5. boundary layers ------------------------------------------------------------
-            for a, b in ((ex.z_lo, min(ex.z_lo + D - 1, ex.z_hi)), (max(ex.z_hi - D + 1, ex.z_lo + D), ex.z_hi)):
-                if a > b:
-                    continue
-                check(L.pnb_wcsph_interact_layers_async_f32(
-                    g, coords.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
-                    arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), a - off, b - off,
-                    a - 1 - off, b + 1 - off, 0, stream))
+            mark("append")
+            # ---- 5. boundary layers of both sides, one launch -----------------------------------
+            a0, b0 = ex.z_lo, min(ex.z_lo + D - 1, ex.z_hi)
+            a1, b1 = max(ex.z_hi - D + 1, ex.z_lo + D), ex.z_hi
+            check(L.pnb_wcsph_interact_layers_async_f32(
+                g, coords.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
+                arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), a0 - off, b0 - off,
+                a1 - off, b1 - off, stream))
+            mark("boundary")
             cnt_h = self.counters.tolist()                 # end of the step: the one synchronisation
             pn.check_(nhs)
             # a bucket overflowed (the library rebuilt the list) or a migrant landed deep inside
@@ -506,12 +531,13 @@ class OverlappedWCSPHStep:
                 check(L.pnb_wcsph_interact_layers_async_f32(
                     g, loc.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
                     arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), ex.z_lo - off,
-                    ex.z_hi - off, ex.z_lo - 1 - off, ex.z_hi + 1 - off, 0, stream))
+                    ex.z_hi - off, 1, 0, stream))
                 pn.check_(nhs)
             else:
                 f = pn.WCSPHInteract(dv[:n_rows], arrays[1][:n_rows], arrays[1][:n_rows], arrays[2][:n_rows],
                                      arrays[2][:n_rows], arrays[3][:n_rows], arrays[3][:n_rows], **self.kw)
                 pn.foreach_point_neighbor(f, loc, loc, nhs)
+            mark("sweep (not overlapped)")
         # ---- 6. compaction: leavers out, migrants in (dv travels with its rows) ------------------
         need = 2 * (n_leave + n_app + 8) + 16
         if self.scratch is None or self.scratch.numel() < need:
@@ -520,10 +546,15 @@ class OverlappedWCSPHStep:
         check(L.pnb_slab_compact_f32(C.byref(tab), n, n_app, ex._x_idx[2].data_ptr(), n_leave, n_mig,
                                      self.flags.data_ptr(), self.scratch.data_ptr(),
                                      self.counters.data_ptr(), stream))
+        mark("compaction")
         n_new = n - n_leave + n_mig
         self.last = {"sent_up": n_up, "sent_down": n_down, "received": n_app, "migrated_in": n_mig,
                      "migrated_out": n_leave, "ghosts": n_app - n_mig + n_leave, "overlapped": bool(can_overlap and not redo),
                      "bytes_sent": (n_up + n_down) * W * 4, "rows": n_rows}
+        if profile:
+            torch.cuda.synchronize()
+            self.last["phase_ms"] = {marks[k + 1][0]: marks[k][1].elapsed_time(marks[k + 1][1])
+                                     for k in range(len(marks) - 1)}
         return arrays, dv, n_new
 
 
@@ -667,6 +698,13 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     ms = ev0.elapsed_time(ev1)
     launches = int(_lib.lib().pnb_launch_count()) - launches0
     stats = dict(stepper.last)
+    # phases of the overlapped step (CUDA events on the main stream, a few extra steps)
+    phase_acc = {}
+    for s in range(4):
+        k = (s + 1) % 2
+        bufs[k], dvs[k], n_cur[k] = stepper.step(bufs[k], n_cur[k], dvs[k], overlap=overlap, profile=True)
+        for name, v_ in stepper.last.get("phase_ms", {}).items():
+            phase_acc[name] = phase_acc.get(name, 0.0) + v_ / 4
     # the same steps without the overlap (exposed exchange = difference), then from host buffers
     k_ab = max(2, min(args.steps, 4))
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -719,6 +757,7 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
                         "ms_per_step_without_overlap": float(tmax[5]),
                         "what": "exchange on a side stream behind the sweep of the interior layers; the "
                                 "boundary layers (2 per side) wait for it"},
+            "phase_ms_rank0": phase_acc,
             "gpu_launches": launches,
             "e2e": {"value": float(tsum[7]) / k_ab / (float(tmax[6]) * 1e-3), "unit": unit,
                     "h2d_bytes_per_step": int(tsum[8]), "d2h_bytes_per_step": int(tsum[9]),
