@@ -504,6 +504,7 @@ extern "C" void pnb_grid_destroy(pnb_grid *g)
     cudaFree(g->left_ids);
     cudaFree(g->flat_tiles);
     cudaFree(g->flat_ovf);
+    cudaFree(g->flat_tabs);
     cudaFree(g->flat_seg);
     cudaFree(g->flat_ctl);
     cudaGetLastError();

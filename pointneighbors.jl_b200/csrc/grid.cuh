@@ -100,6 +100,7 @@ struct pnb_grid {
     // k_sweep_flat (sweep_flat.cuh): tile table of one sweep and its control words
     void *flat_tiles;        // FlatTile[flat_tiles_cap]
     int *flat_ovf;           // [flat_tiles_cap] tiles handed to k_sweep_flat_overflow
+    uint32_t *flat_tabs;     // [flat_tiles_cap x 224] staging tables of the tiles (k_flat_tables)
     int64_t flat_tiles_cap;
     uint32_t *flat_seg;      // [2 * (flat_seg_cap + 1)] tiles per row segment, exclusive prefix
     int64_t flat_seg_cap;

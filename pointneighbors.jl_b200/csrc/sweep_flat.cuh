@@ -219,6 +219,112 @@ k_flat_tiles(GridP g, CellsView qry, int lay0, int n_lay, int lay1, int n_lay1, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// pre-pass, step 2: the staging tables of every tile
+// ------------------------------------------------------------------------------------------------
+// What a CTA needs before it can stage a tile -- begin / count / staged position of its <= 7 x 9
+// cells, the padded start of every x-column, the query cells -- is computed HERE, one warp per
+// tile with all tiles in flight, and written as one 896-byte table; the persistent CTAs copy the
+// table of their next tile with cp.async while they work on the current one (in round 2's first
+// version warp 0 of every CTA computed it serially: 133 dependent instructions per tile with
+// 14 warps waiting at a barrier, 6.7 % of the warp samples).
+constexpr int kTabWords = 224;
+template <int ND>
+struct FlatTab {
+    static constexpr int NR = rows_of(ND);
+    static constexpr int NE = kFNSL * NR;
+    static constexpr int oCbeg = 0, oCcnt = NE, oCpre = 2 * NE, oSlot0 = 3 * NE;
+    static constexpr int oSpop = oSlot0 + kFNSL + 1, oQb = oSpop + kFNSL, oQt = oQb + kFSMax;
+    static constexpr int oNsl = oQt + kFSMax + 1, oCell = oNsl + 1, oOff = oCell + 1, oNpts = oOff + 1;
+    static constexpr int oBig = oNpts + 1, oEnd = oBig + 1;
+    static_assert(oEnd <= kTabWords, "table layout");
+};
+
+template <int ND, bool PER, int CAP, int NBM>
+__global__ void __launch_bounds__(256)
+k_flat_tables(GridP g, CellsView cand, CellsView qry, const FlatTile *__restrict__ tiles,
+              const uint32_t *__restrict__ ctl, uint32_t *__restrict__ tabs)
+{
+    using L = FlatTab<ND>;
+    constexpr int NR = L::NR, NEmax = L::NE;
+    __shared__ uint32_t s_all[8][kTabWords];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t tile = blockIdx.x * 8u + (uint32_t)warp;
+    if (tile >= ctl[0]) return;
+    uint32_t *T = s_all[warp];
+    const FlatTile ft = tiles[tile];
+    const int lin0 = (int)ft.cell;
+    const int cx0 = lin0 % g.gs[0] + 1;
+    const int cy = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
+    const int cz = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
+    for (int k = lane; k < kTabWords; k += 32) T[k] = 0u;
+    __syncwarp();
+    // tile cells: lane s = cell cx0 + s
+    uint32_t b0 = 0, cntq = 0;
+    if (lane < kFSMax && cx0 + lane <= g.gs[0] - 1)
+        cell_range(qry, linear_cell(g, cx0 + lane, cy, cz), b0, cntq);
+    uint32_t avail = cntq;
+    if (lane == 0) { avail -= ft.off; b0 += ft.off; }
+    uint32_t incl = avail;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - avail;
+    // cells that hold a point of the tile: exclusive prefix < npts
+    const unsigned touch = __ballot_sync(0xffffffffu, lane < kFSMax && excl < ft.npts && avail > 0u);
+    const int S = 32 - __clz((int)touch);            // index of the last touched cell + 1
+    if (lane < kFSMax) { T[L::oQb + lane] = b0; T[L::oQt + lane] = min(excl, ft.npts); }
+    const int NSL = S + 2, NE = NSL * NR;
+    if (lane == 0) {
+        T[L::oQt + kFSMax] = ft.npts; T[L::oNsl] = (uint32_t)NSL;
+        T[L::oCell] = ft.cell; T[L::oOff] = ft.off; T[L::oNpts] = ft.npts;
+    }
+    for (int e = lane; e < NEmax; e += 32) {
+        const int slot = e / NR, row = e % NR;
+        int sx = cx0 - 1 + slot;
+        int ry = cy + (ND > 1 ? (row % 3) - 1 : 0);
+        int rz = cz + (ND > 2 ? (row / 3) - 1 : 0);
+        uint32_t c0 = 0, cn = 0;
+        if (e < NE && sx <= g.gs[0]) {
+            if (PER) {
+                sx = floormod_i(sx - 2, g.nc[0]) + 2;
+                if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
+                if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
+            }
+            cell_range(cand, linear_cell(g, sx, ry, rz), c0, cn);
+        }
+        T[L::oCbeg + e] = c0;
+        T[L::oCcnt + e] = cn;
+    }
+    __syncwarp();
+    if (lane < kFNSL) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int r = 0; r < NR; r++) { T[L::oCpre + lane * NR + r] = run; run += T[L::oCcnt + lane * NR + r]; }
+        T[L::oSpop + lane] = run;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int sl = 0; sl < kFNSL; sl++) { T[L::oSlot0 + sl] = run; run += (T[L::oSpop + sl] + 31u) & ~31u; }
+        T[L::oSlot0 + kFNSL] = run;
+        // too dense for the staging buffer or the mask table: the per-point kernel takes the tile
+        bool too_big = run > (uint32_t)CAP;
+#pragma unroll
+        for (int w = 0; w < kFSMax; w++)
+            if (w + 3 <= NSL) too_big = too_big || (T[L::oSlot0 + w + 3] - T[L::oSlot0 + w]) > (uint32_t)(NBM * 32);
+        T[L::oBig] = too_big ? 1u : 0u;
+    }
+    __syncwarp();
+    for (int e = lane; e < NEmax; e += 32) T[L::oCpre + e] += T[L::oSlot0 + e / NR];
+    __syncwarp();
+    uint32_t *out = tabs + (size_t)tile * kTabWords;
+    for (int k = lane; k < kTabWords; k += 32) out[k] = T[k];
+}
+
+// ------------------------------------------------------------------------------------------------
 // the sweep
 // ------------------------------------------------------------------------------------------------
 // resident CTAs per SM the register allocation is tuned for: what the shared memory allows
@@ -235,7 +341,7 @@ __host__ __device__ constexpr int flat_min_blocks()
 
 template <int ND, bool PER, class CL, bool TWO>
 __global__ void __launch_bounds__(kFG * flat_wpc<CL>() * 32, flat_min_blocks<ND, CL>())
-k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__restrict__ tiles,
+k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const uint32_t *__restrict__ tabs,
              uint32_t *__restrict__ ctl, int *__restrict__ overflow_tiles, int reserve_sms)
 {
     // A persistent grid that fills every SM keeps the kernels of other streams (the NCCL send /
@@ -279,12 +385,11 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
     __half *s_half16 = reinterpret_cast<__half *>(s_half);
     unsigned char *s_pay = smem_raw + sizeof(float4) * kCap + (size_t)kBlocks * ND * 64;
     unsigned *s_mask = reinterpret_cast<unsigned *>(s_pay + (size_t)kCap * kPayB);
-    __shared__ uint32_t s_cbeg[NEmax], s_ccnt[NEmax], s_cpre[NEmax];
-    __shared__ uint32_t s_slot0[kFNSL + 1], s_spop[kFNSL];
-    __shared__ uint32_t s_qb[kFSMax], s_qt[kFSMax + 1];   // per tile cell: first record, first tile point
+    using TL = FlatTab<ND>;
+    __shared__ __align__(16) uint32_t s_tab[2][kTabWords];   // staging tables: this tile / the next one
     __shared__ int s_cnt[kFG][kWPC][32];
     __shared__ nz_t s_nz[kFG][kWPC][32];
-    __shared__ int s_nsl;
+    __shared__ uint32_t s_tile;
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int group = warp / kWPC, part = warp % kWPC;
@@ -306,65 +411,19 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
 
     // ---- tile pipeline of the persistent CTA ------------------------------------------------------
     // While tile t is processed, warp 0 has already requested the index of tile t + 2 (atomic
-    // counter), read the record of tile t + 1 and started asynchronous copies (LDGSTS) of the cell
-    // list words of its <= 7 x 9 staged cells and <= 5 query cells into s_raw: the prologue of a
-    // tile then works from shared memory only, no global round trip sits between two tiles.
-    __shared__ FlatTile s_ft, s_ftn;                         // current / prefetched tile record
-    __shared__ uint32_t s_raw[2 * (NEmax + kFSMax)];         // raw cell list words of the next tile
-    __shared__ uint32_t s_tile;
-    const uint32_t raw_sa = (uint32_t)__cvta_generic_to_shared(s_raw);
-    auto cell_words_async = [&](const CellsView &v, int lin, uint32_t sa) {
-        if (v.K) {
-            cp_async4(sa, v.start + bucket_of((uint32_t)lin, v.t0, v.t1, v.t2));
-        } else {
-            cp_async4(sa, v.start + lin);
-            cp_async4(sa + 4u, v.start + lin + 1);
-        }
-    };
-    auto cell_from_words = [&](const CellsView &v, int lin, uint32_t w0, uint32_t w1, uint32_t &b0, uint32_t &cnt) {
-        if (v.K) { b0 = bucket_of((uint32_t)lin, v.t0, v.t1, v.t2) * v.K; cnt = min(w0, v.K); }
-        else { b0 = w0; cnt = w1 - w0; }
-    };
-    auto staged_cell = [&](int e, int cx0_, int cy_, int cz_, bool &valid) {
-        const int slot = e / NR, row = e % NR;
-        int sx = cx0_ - 1 + slot;
-        int ry = cy_ + (ND > 1 ? (row % 3) - 1 : 0);
-        int rz = cz_ + (ND > 2 ? (row / 3) - 1 : 0);
-        valid = sx <= g.gs[0];
-        if (PER) {
-            sx = floormod_i(sx - 2, g.nc[0]) + 2;
-            if (ND > 1) ry = floormod_i(ry - 2, g.nc[1]) + 2;
-            if (ND > 2) rz = floormod_i(rz - 2, g.nc[2]) + 2;
-        }
-        return linear_cell(g, sx, ry, rz);
-    };
-    const uint32_t ftn_sa = (uint32_t)__cvta_generic_to_shared(&s_ftn);
-    // warp 0, step 1: the record of tile t (one 16-byte asynchronous copy)
-    auto prefetch_record = [&](uint32_t t) {
-        if (lane == 0) cp_async16(ftn_sa, tiles + t);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // warp 0, step 2 (the record has arrived): the cell list words of its staged and query cells
-    auto prefetch_cells = [&]() {
-        const FlatTile f = s_ftn;
-        const int lin0 = (int)f.cell;
-        const int cx0_ = lin0 % g.gs[0] + 1;
-        const int cy_ = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
-        const int cz_ = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
-        for (int e = lane; e < NEmax; e += 32) {
-            bool valid;
-            const int lin = staged_cell(e, cx0_, cy_, cz_, valid);
-            if (valid) cell_words_async(cand, lin, raw_sa + 8u * (uint32_t)e);
-            else { s_raw[2 * e] = 0u; s_raw[2 * e + 1] = 0u; }
-        }
-        if (lane < kFSMax) {
-            if (cx0_ + lane <= g.gs[0] - 1)
-                cell_words_async(qry, linear_cell(g, cx0_ + lane, cy_, cz_), raw_sa + 8u * (uint32_t)(NEmax + lane));
-            else { s_raw[2 * (NEmax + lane)] = 0u; s_raw[2 * (NEmax + lane) + 1] = 0u; }
-        }
+    // counter) and started the asynchronous copy (LDGSTS) of the 896-byte staging table of tile
+    // t + 1 (written by k_flat_tables) into the other table buffer: a tile's prologue is one
+    // cp.async wait and one barrier.
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&s_tab[0][0]);
+    auto prefetch_table = [&](uint32_t t, int buf) {         // warp 0
+        const uint32_t *src = tabs + (size_t)t * kTabWords;
+        const uint32_t dst = tab_sa + (uint32_t)buf * (kTabWords * 4u);
+        cp_async16(dst + 16u * (uint32_t)lane, src + 4 * lane);
+        if (lane < kTabWords / 4 - 32) cp_async16(dst + 16u * (uint32_t)(32 + lane), src + 4 * (32 + lane));
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     uint32_t cur = blockIdx.x, nxt = 0xffffffffu;            // warp 0: this tile, the one after it
+    int par = 0;
     if (warp == 0) {
         // (with reserved SMs the CTAs that left do not take the tile of their blockIdx: every
         // tile index then comes from the counter, which the tile pre-pass set to 0)
@@ -374,102 +433,40 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
         }
         if (lane == 0) nxt = atomicAdd(ctl + 1, 1u);
         nxt = __shfl_sync(0xffffffffu, nxt, 0);
-        if (cur < n_tiles) {
-            prefetch_record(cur);
-            cp_async_wait_all();
-            __syncwarp();
-            prefetch_cells();
-        }
+        if (cur < n_tiles) prefetch_table(cur, 0);
     }
 
-    for (;;) {
+    for (;; par ^= 1) {
         __syncthreads();                         // shared memory of the previous tile is free
-        // ---- cells of the tile and table of staged cells (warp 0, from the prefetched words) ----
         if (warp == 0) {
             if (lane == 0) s_tile = cur;
-            if (cur < n_tiles) {
-                cp_async_wait_all();
-                __syncwarp();
-                const FlatTile ft = s_ftn;
-                if (lane == 0) s_ft = ft;
-                const int lin0 = (int)ft.cell;
-                const int cx0 = lin0 % g.gs[0] + 1;
-                const int cy = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
-                const int cz = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
-                // tile cells: lane s = cell cx0 + s
-                uint32_t b0 = 0, cntq = 0;
-                if (lane < kFSMax && cx0 + lane <= g.gs[0] - 1)
-                    cell_from_words(qry, linear_cell(g, cx0 + lane, cy, cz), s_raw[2 * (NEmax + lane)],
-                                    s_raw[2 * (NEmax + lane) + 1], b0, cntq);
-                uint32_t avail = cntq;
-                if (lane == 0) { avail -= ft.off; b0 += ft.off; }
-                uint32_t incl = avail;
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const uint32_t excl = incl - avail;
-                // cells that hold a point of the tile: exclusive prefix < npts
-                const unsigned touch = __ballot_sync(0xffffffffu, lane < kFSMax && excl < ft.npts && avail > 0u);
-                const int S = 32 - __clz((int)touch);            // index of the last touched cell + 1
-                if (lane < kFSMax) { s_qb[lane] = b0; s_qt[lane] = min(excl, ft.npts); }
-                if (lane == 0) { s_qt[kFSMax] = ft.npts; s_nsl = S + 2; }
-                const int NE = (S + 2) * NR;
-                for (int e = lane; e < NEmax; e += 32) {
-                    bool valid;
-                    const int lin = staged_cell(e, cx0, cy, cz, valid);
-                    uint32_t c0 = 0, cn = 0;
-                    if (e < NE && valid) cell_from_words(cand, lin, s_raw[2 * e], s_raw[2 * e + 1], c0, cn);
-                    s_cbeg[e] = c0;
-                    s_ccnt[e] = cn;
-                }
-                __syncwarp();
-                if (lane < kFNSL) {
-                    uint32_t run = 0;
-#pragma unroll
-                    for (int r = 0; r < NR; r++) { s_cpre[lane * NR + r] = run; run += s_ccnt[lane * NR + r]; }
-                    s_spop[lane] = run;
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    uint32_t run = 0;
-#pragma unroll
-                    for (int sl = 0; sl < kFNSL; sl++) { s_slot0[sl] = run; run += (s_spop[sl] + 31u) & ~31u; }
-                    s_slot0[kFNSL] = run;
-                }
-                __syncwarp();
-                for (int e = lane; e < NEmax; e += 32) s_cpre[e] += s_slot0[e / NR];
-            }
+            if (cur < n_tiles) cp_async_wait_all();     // the table of this tile has landed
         }
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= n_tiles) break;
-        const FlatTile ft = s_ft;
+        const uint32_t *T = s_tab[par];
+        const uint32_t *s_cbeg = T + TL::oCbeg, *s_ccnt = T + TL::oCcnt, *s_cpre = T + TL::oCpre;
+        const uint32_t *s_slot0 = T + TL::oSlot0, *s_spop = T + TL::oSpop;
+        const uint32_t *s_qb = T + TL::oQb, *s_qt = T + TL::oQt;   // per tile cell: first record, first tile point
+        FlatTile ft;
+        ft.cell = T[TL::oCell]; ft.off = T[TL::oOff]; ft.npts = T[TL::oNpts]; ft.pad_ = 0u;
         const int lin0 = (int)ft.cell;
         const int cx0 = lin0 % g.gs[0] + 1;
         const int cy = ND > 1 ? (lin0 / g.gs[0]) % g.gs[1] + 1 : 1;
         const int cz = ND > 2 ? lin0 / (g.gs[0] * g.gs[1]) + 1 : 1;
         uint32_t nn = 0u;
         if (warp == 0) {
-            // the tile after this one: request the index behind it and copy its record (both
-            // asynchronous: nothing here waits; its cells follow once this tile is staged)
+            // the tile after this one: request the index behind it, copy its table (both
+            // asynchronous: the counter's answer is only looked at once this tile is staged)
             if (lane == 0) nn = atomicAdd(ctl + 1, 1u);
-            if (nxt < n_tiles) prefetch_record(nxt);
+            if (nxt < n_tiles) prefetch_table(nxt, par ^ 1);
         }
-        const int NSL = s_nsl;
+        const int NSL = (int)T[TL::oNsl];
         // too dense for the staging buffer or the mask table: hand the tile to the per-point kernel
-        bool too_big = s_slot0[NSL] > (uint32_t)kCap;
-#pragma unroll
-        for (int w = 0; w < kFSMax; w++)
-            if (w + 3 <= NSL) too_big = too_big || (s_slot0[w + 3] - s_slot0[w]) > (uint32_t)(kNBlkMax * 32);
-        if (too_big) {
+        if (T[TL::oBig]) {
             if (threadIdx.x == 0) overflow_tiles[atomicAdd(ctl + 2, 1u)] = (int)tile;
-            if (warp == 0) {
-                if (nxt < n_tiles) { cp_async_wait_all(); __syncwarp(); prefetch_cells(); }
-                cur = nxt;
-                nxt = __shfl_sync(0xffffffffu, nn, 0);
-            }
+            if (warp == 0) { cur = nxt; nxt = __shfl_sync(0xffffffffu, nn, 0); }
             continue;
         }
 
@@ -547,13 +544,7 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const FlatTile *__re
             }
         }
         __syncthreads();
-        if (warp == 0) {
-            // the record of the next tile arrived with this warp's staging copies: start the
-            // copies of its cell list words, they land while this tile is tested and drained
-            if (nxt < n_tiles) { cp_async_wait_all(); __syncwarp(); prefetch_cells(); }
-            cur = nxt;
-            nxt = __shfl_sync(0xffffffffu, nn, 0);
-        }
+        if (warp == 0) { cur = nxt; nxt = __shfl_sync(0xffffffffu, nn, 0); }
 
         // ---- my point: tile point tp = group * 32 + lane -------------------------------------
         const uint32_t tp = (uint32_t)(group * 32 + lane);

@@ -91,11 +91,12 @@ static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsVie
     int64_t max_tiles = (n_q + (int64_t)kFMinW * nxc * rows) / kFTP + n_segs + 1;
     if (max_tiles > n_q) max_tiles = n_q;
     if (max_tiles > g->flat_tiles_cap) {
-        cudaFree(g->flat_tiles); cudaFree(g->flat_ovf);
-        g->flat_tiles = nullptr; g->flat_ovf = nullptr; g->flat_tiles_cap = 0;
+        cudaFree(g->flat_tiles); cudaFree(g->flat_ovf); cudaFree(g->flat_tabs);
+        g->flat_tiles = nullptr; g->flat_ovf = nullptr; g->flat_tabs = nullptr; g->flat_tiles_cap = 0;
         const int64_t want = max_tiles + max_tiles / 8 + 64;
         PNB_CUDA(cudaMalloc(&g->flat_tiles, sizeof(FlatTile) * (size_t)want));
         PNB_CUDA(cudaMalloc(&g->flat_ovf, sizeof(int) * (size_t)want));
+        PNB_CUDA(cudaMalloc(&g->flat_tabs, sizeof(uint32_t) * kTabWords * (size_t)want));
         g->flat_tiles_cap = want;
     }
     if (n_segs > g->flat_seg_cap) {
@@ -140,8 +141,14 @@ static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsVie
         PNB_LAUNCHED();
     }
     {
+        ProfScope ps(PH_SWEEP_TILES_PREP, s);
+        k_flat_tables<ND, PER, flat_cap<CL>(), flat_nblk_max<CL>()><<<(unsigned)div_up(max_tiles, 8), 256, 0, s>>>(
+            g->p, cand, qry, tiles, g->flat_ctl, g->flat_tabs);
+        PNB_LAUNCHED();
+    }
+    {
         ProfScope ps(PH_SWEEP_CELLS, s);
-        kern<<<n_ctas, threads, smem, s>>>(g->p, cand, qry, cl, tiles, g->flat_ctl, g->flat_ovf, reserve_sms);
+        kern<<<n_ctas, threads, smem, s>>>(g->p, cand, qry, cl, g->flat_tabs, g->flat_ctl, g->flat_ovf, reserve_sms);
         PNB_LAUNCHED();
     }
     {
