@@ -281,10 +281,11 @@ void pnb_set_build_tuning(int variant);
  * slots, K from the fullest cell of the last CSR build; a cell that overflows falls back to the
  * two-pass CSR build); 0: always the two-pass CSR build.  Same results. */
 void pnb_set_build_layout(int buckets);
-/* Numbering of the buckets of the one-pass layout: 0 (default) = linear cell order, 1 = transposed
- * (last dimension fastest), -1 = chosen from the order of the input at the first build
+/* Numbering of the buckets of the one-pass layout: 0 = linear cell order, 1 = transposed (last
+ * dimension fastest), -1 (default) = chosen from the order of the input at the first build
  * (transposed when that is how the points step through the cells, e.g. the reference's benchmark
- * clouds, test/point_cloud.jl:49).  Same results; measured trade-off in DESIGN.md 5.1. */
+ * clouds, test/point_cloud.jl:49: consecutive points then write neighbouring buckets).  Same
+ * results; measured trade-off in DESIGN.md 5.1. */
 void pnb_set_bucket_order(int order);
 
 /* benchmarks/count_neighbors.jl:16-28: out[i] = number of neighbours (int64, zeroed first) */

@@ -434,6 +434,7 @@ extern "C" pnb_status pnb_grid_create_window_f32(int ndims, float r, const float
         if (g->template_search) gs = d < ndims ? 0 : 1;
         p.off[d] = 0;
         if (win_lo && win_hi && d < ndims && !g->template_search) {
+            g->windowed = true;
             // window of the global grid (slab decomposition): global cells win_lo..win_hi
             // (1-based, inclusive, outermost layer = padding) become local cells 1..(hi-lo+1)
             if (box_min && box_max) {
@@ -541,15 +542,20 @@ static int initial_build_layout()
     return e ? atoi(e) : 1;
 }
 int g_build_layout = initial_build_layout();
-// numbering of the buckets: 0 = linear cell order (default), 1 = transposed (last dimension
-// fastest), -1 = chosen from the order of the input; PNB_BUCKET_ORDER overrides the default.
-// Measured (config 3, the reference generator's order = last dimension fastest): transposed
-// buckets make the one-pass build 5 % faster (0.128 vs 0.134 ms) but the tile sweep 4 % slower
-// (13.9 vs 13.35 ms: x-rows are no longer contiguous for the staging reads), hence the default.
+// numbering of the buckets: 0 = linear cell order, 1 = transposed (last dimension fastest),
+// -1 (default) = chosen from the order of the input at the first build; PNB_BUCKET_ORDER overrides.
+// Measured (config 3, the reference generator's order = last dimension fastest).  Round 1:
+// transposed buckets made the one-pass build 5 % faster (0.128 vs 0.134 ms) but k_sweep_tiles 4 %
+// slower (x-rows no longer contiguous for its register staging), so linear was the default.
+// Round 2: k_sweep_flat stages cell by cell with cp.async and does not care (11.07 ms either
+// way); the build goes from 0.124 to 0.112 ms (consecutive points write neighbouring buckets:
+// DRAM page locality) = 64 % of the HBM peak, the tile pre-pass from 0.068 to 0.085 ms (strided
+// count reads).  Windows of a slab decomposition keep the plain order (their layered gathers
+// rely on it).
 static int initial_bucket_order()
 {
     const char *e = getenv("PNB_BUCKET_ORDER");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
 }
 int g_bucket_order = initial_bucket_order();
 int g_tune_build = 25;   // measurement variants of the build kernels (pnb_set_build_tuning)
@@ -1649,7 +1655,8 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
         // tuple, test/point_cloud.jl:49); windows of a slab decomposition keep the plain order
         const unsigned first_steps = *(volatile unsigned int *)(g->h_err + 2);
         const unsigned last_steps = *(volatile unsigned int *)(g->h_err + 3);
-        if (g_bucket_order >= 0) g->bucket_tr = g_bucket_order == 1 && g->p.ndims > 1;
+        if (g->windowed) g->bucket_tr = false;
+        else if (g_bucket_order >= 0) g->bucket_tr = g_bucket_order == 1 && g->p.ndims > 1;
         else g->bucket_tr = g->p.ndims > 1 && last_steps > 2u * first_steps + 64u;
     }
     g->csr_valid = true;

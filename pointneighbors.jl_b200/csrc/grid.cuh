@@ -32,6 +32,7 @@ struct pnb_grid {
     int64_t brec_slots;
     int bucket_K;            // 0 = not chosen yet (the next CSR build picks it from the fullest cell)
     bool bucket_tr;          // buckets numbered in transposed cell order (chosen from the input order)
+    bool windowed;           // window of a larger grid (slab decomposition): plain bucket order
     bool bucket_valid;       // bcount / brec describe the current build
     uint32_t *bcount_alt;    // [C] second counter array: all zero between builds; every one-pass
                              // build clears the array of the NEXT build while it runs (no memset)

@@ -198,7 +198,9 @@ static pnb_status launch_nd(pnb_grid *g, bool fast, bool tiles, const float *x, 
         // count-only closures spend their time in the test phase, where the 4-cell tiles of
         // round 1 stage less per point and need no tile table (config 3 count: 4.98 vs 5.29 ms,
         // config 1: 0.117 vs 0.132 ms): they keep k_sweep_tiles unless the flat kernel is forced
-        if (g_tune_flat == 2 || (g_tune_flat == 1 && !CL::kCountOnly)) {
+        // (measured with the table pipeline: config 3 count 4.80 + 0.07 ms flat vs 4.95 ms; config 1
+        // 0.095 + 0.012 vs 0.096 ms: the fixed cost of the tile pre-pass decides on small clouds)
+        if (g_tune_flat == 2 || (g_tune_flat == 1 && (!CL::kCountOnly || n_loop >= 2000000))) {
             if (two) return launch_flat<ND, PER, CL, true>(g, cand, qry, n_loop, cl, 0, ND == 2 ? nyc : nzc, s);
             return launch_flat<ND, PER, CL, false>(g, cand, qry, n_loop, cl, 0, ND == 2 ? nyc : nzc, s);
         }
