@@ -1554,7 +1554,10 @@ extern "C" pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n,
                     else if (g_tune_build & 2048) {
                         // runs of adjacent lanes instead of match.any lane groups (the version
                         // before; valid results, kept for tools/match_diag.py)
-                        k_bucket_scatter<3, false, 4, 0><<<(unsigned)div_up(n_idx, kBuildThreads * 4), kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4);
+                        if (g->bucket_tr)
+                            k_bucket_scatter<3, false, 4, 0, true><<<(unsigned)div_up(n_idx, kBuildThreads * 4), kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4);
+                        else
+                            k_bucket_scatter<3, false, 4, 0><<<(unsigned)div_up(n_idx, kBuildThreads * 4), kBuildThreads, 0, s>>>(g->p, bp, y, n_idx, eachindex_y, index_base, (uint32_t)g->bucket_K, g->bcount, g->brec, g->d_err, clear4, n_clear4);
                     }
 #ifdef PNB_DIAG   /* tools/ builds only: these variants write garbage layouts */
                     else if ((g_tune_build >> 8) & 7) {
