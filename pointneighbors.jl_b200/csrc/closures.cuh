@@ -398,6 +398,13 @@ struct WcsphClT {
     __device__ __forceinline__ void stage_async(uint32_t pay_sa, int slot, uint32_t gi, int cap) const
     {
         cp_async16(pay_sa + 16u * (uint32_t)slot, vrho_sorted + gi);
+        stage_async_rest(pay_sa, slot, gi, cap);
+    }
+    // k_sweep_flat copies plane 0 (16 bytes per candidate) cell by cell with the TMA unit
+    // (bulk_plane) and only the rest per candidate
+    __device__ __forceinline__ const float4 *bulk_plane() const { return vrho_sorted; }
+    __device__ __forceinline__ void stage_async_rest(uint32_t pay_sa, int slot, uint32_t gi, int cap) const
+    {
         if (EXACT) cp_async16(pay_sa + 16u * (uint32_t)cap + 16u * (uint32_t)slot, mp_sorted + gi);
         else cp_async8(pay_sa + 16u * (uint32_t)cap + 8u * (uint32_t)slot, vp_sorted + gi);
     }
@@ -457,7 +464,7 @@ struct WcsphClT {
     // the fast term vanishes identically for d >= 2 h (t = 0): when the kernel support 2 h does
     // not exceed the search radius, candidates of the fp16 pre-filter band (r < d <= 1.005 r)
     // contribute exactly zero and the exact radius test of the drain is redundant
-    __device__ __forceinline__ bool no_radius_test() const { return !EXACT && support_in_radius; }
+    __host__ __device__ __forceinline__ bool no_radius_test() const { return !EXACT && support_in_radius; }
     __device__ __forceinline__ void finish(State &s, int, int i_id) const
     {
         const int ns = nd + 1;

@@ -234,6 +234,34 @@ __device__ __forceinline__ void cp_async4(uint32_t saddr, const void *gptr)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
 }
+// 1-D bulk copies global -> shared by the TMA unit (cp.async.bulk, UBLKCP in the SASS), completion
+// through an mbarrier's transaction count.  dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_sa), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar_sa, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_sa, const void *src, uint32_t bytes, uint32_t mbar_sa)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_sa), "l"(src), "r"(bytes), "r"(mbar_sa) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_sa, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(mbar_sa), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");

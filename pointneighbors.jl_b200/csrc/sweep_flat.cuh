@@ -37,6 +37,8 @@ constexpr int kFMinW = kFTP / 4;        // weight floor of a cell -> a tile touc
 constexpr int kFSMax = 5;               // cells per tile
 constexpr int kFNSL = kFSMax + 2;       // staged x-columns ("slots") per tile
 constexpr int kFSegCells = 1024;        // rows longer than this are cut into segments
+constexpr bool kFlatBulkRecords = false; // stage the exact records with TMA bulk copies (measured slower)
+constexpr bool kFlatBulkPayload = false; // ... and payload plane 0 as well
 
 // staged candidates per tile (incl. the padding of every slot to a multiple of 32) and 32-blocks
 // per cell (3 slots).  7 slots x 9 cells x 27 points = 1701 (+ padding) on the benchmark cloud.
@@ -73,6 +75,10 @@ template <class CL, class = void>
 struct has_stage_async { static constexpr bool value = false; };
 template <class CL>
 struct has_stage_async<CL, decltype((void)&CL::stage_async)> { static constexpr bool value = true; };
+template <class CL, class = void>
+struct has_bulk_plane { static constexpr bool value = false; };
+template <class CL>
+struct has_bulk_plane<CL, decltype((void)&CL::bulk_plane)> { static constexpr bool value = true; };
 template <class CL, class = void>
 struct has_pair_pred { static constexpr bool value = false; };
 template <class CL>
@@ -339,7 +345,9 @@ __host__ __device__ constexpr int flat_min_blocks()
     return m < 1 ? 1 : (m > 4 ? 4 : m);
 }
 
-template <int ND, bool PER, class CL, bool TWO>
+// NOR2: the closure's term vanishes identically beyond the search radius (skip_radius_test,
+// decided on the host): the exact radius test of the drain is compiled out.
+template <int ND, bool PER, class CL, bool TWO, bool NOR2 = false>
 __global__ void __launch_bounds__(kFG * flat_wpc<CL>() * 32, flat_min_blocks<ND, CL>())
 k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const uint32_t *__restrict__ tabs,
              uint32_t *__restrict__ ctl, int *__restrict__ overflow_tiles, int reserve_sms)
@@ -390,6 +398,7 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const uint32_t *__re
     __shared__ int s_cnt[kFG][kWPC][32];
     __shared__ nz_t s_nz[kFG][kWPC][32];
     __shared__ uint32_t s_tile;
+    __shared__ __align__(8) unsigned long long s_mbar;      // completion of the TMA bulk copies of a tile
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int group = warp / kWPC, part = warp % kWPC;
@@ -406,6 +415,13 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const uint32_t *__re
     const __half2 thr = __float2half2_rn(half_thr_hi(PER));
     const __half2 thr_lo = __float2half2_rn(half_thr_lo(PER));
     const uint32_t n_tiles = ctl[0];
+    const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    uint32_t mbar_phase = 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(mbar_sa, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     unsigned *my_mask = s_mask + (size_t)group * kNBlkMax * 32 + lane;   // word of block b: my_mask[b * 32]
     unsigned *my_band = CL::kCountOnly ? my_mask : my_mask + (size_t)kFG * kNBlkMax * 32;
 
@@ -483,13 +499,56 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const uint32_t *__re
             // between, one memory round trip per tile instead of one per cell), waits for its own
             // copies and derives the fp16 copies from the records it has just staged.
             constexpr bool kAsync = has_stage_async<CL>::value || pay_bytes_tile<CL>::value == 0;
+            // TMA bulk copies (cp.async.bulk + mbarrier, UBLKCP / SYNCS in the SASS) were measured
+            // against the per-thread cp.async below and LOST on this access pattern: a tile is 63
+            // cells of ~430 bytes per plane, and the TMA unit works through such small requests
+            // one after the other.  Config 3, WCSPH: per-thread LDGSTS 11.07 ms, records through
+            // TMA 11.60 ms, records + payload plane 0 through TMA 12.22 ms (n-body 7.57 / 7.67 /
+            // 7.66 ms; count 4.80 / 4.75 / 4.74 ms).  The path is kept behind this constant.
+            constexpr bool kBulk = kFlatBulkRecords;
+            constexpr bool kBulkPay = kBulk && kFlatBulkPayload && has_bulk_plane<CL>::value;
             if (kAsync) {
-                for (int e = warp; e < NE; e += kFG * kWPC) {
-                    const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
-                    for (uint32_t k = lane; k < n; k += 32) {
-                        cp_async16(pos_sa + 16u * (d0 + k), sorted + b0 + k);
-                        if constexpr (has_stage_async<CL>::value) cl.stage_async(pay_sa, (int)(d0 + k), b0 + k, kCap);
+                // The 16-byte planes (exact records; plane 0 of the payload) go cell by cell through
+                // the TMA unit: one cp.async.bulk per staged cell and plane, issued by the lanes
+                // of the last warp, completion counted in bytes by an mbarrier.  What is left per
+                // candidate (8 or 4 payload bytes) stays a per-thread cp.async.
+                if (kBulk && warp == kFG * kWPC - 1) {
+                    uint32_t bytes = 0;
+                    for (int e = lane; e < NE; e += 32) bytes += s_ccnt[e] * 16u * (kBulkPay ? 2u : 1u);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+                    if (lane == 0) mbar_arrive_expect_tx(mbar_sa, bytes);
+                    // (the previous tile's reads of these buffers, ordered before this point by the
+                    // CTA barrier, must also be ordered before the async proxy's writes)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    for (int e = lane; e < NE; e += 32) {
+                        const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
+                        if (n == 0u) continue;
+                        bulk_copy_g2s(pos_sa + 16u * d0, sorted + b0, 16u * n, mbar_sa);
+                        if constexpr (kBulkPay) bulk_copy_g2s(pay_sa + 16u * d0, cl.bulk_plane() + b0, 16u * n, mbar_sa);
                     }
+                }
+                if constexpr (!kBulk) {
+                    for (int e = warp; e < NE; e += kFG * kWPC) {
+                        const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
+                        for (uint32_t k = lane; k < n; k += 32) {
+                            cp_async16(pos_sa + 16u * (d0 + k), sorted + b0 + k);
+                            if constexpr (has_stage_async<CL>::value) cl.stage_async(pay_sa, (int)(d0 + k), b0 + k, kCap);
+                        }
+                    }
+                } else if constexpr (has_stage_async<CL>::value) {
+                    for (int e = warp; e < NE; e += kFG * kWPC) {
+                        const uint32_t b0 = s_cbeg[e], d0 = s_cpre[e], n = s_ccnt[e];
+                        for (uint32_t k = lane; k < n; k += 32) {
+                            if constexpr (kBulkPay) cl.stage_async_rest(pay_sa, (int)(d0 + k), b0 + k, kCap);
+                            else cl.stage_async(pay_sa, (int)(d0 + k), b0 + k, kCap);
+                        }
+                    }
+                }
+                if constexpr (kBulk) {
+                    mbar_wait(mbar_sa, mbar_phase);   // the bulk copies of this tile have landed
+                    mbar_phase ^= 1u;
                 }
                 cp_async_wait_all();
             }
@@ -688,7 +747,7 @@ k_sweep_flat(GridP g, CellsView cand, CellsView qry, CL cl, const uint32_t *__re
             }
             const int rounds = __reduce_max_sync(0xffffffffu, n_mine);
             cl.seek(st, part * Q);
-            const bool no_r2 = !kExact && skip_radius_test(cl);
+            constexpr bool no_r2 = !kExact && NOR2;
 
             // ---- phase 3: drain, one hit per lane and round -----------------------------------
             if constexpr (has_pair_pred<CL>::value && !kExact) {

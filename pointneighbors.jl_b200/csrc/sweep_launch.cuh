@@ -113,11 +113,20 @@ static pnb_status launch_flat(pnb_grid *g, const CellsView &cand, const CellsVie
     FlatTile *tiles = reinterpret_cast<FlatTile *>(g->flat_tiles);
     constexpr int threads = kFG * flat_wpc<CL>() * 32;
     constexpr size_t smem = flat_smem_bytes<ND, CL>();
-    auto kern = k_sweep_flat<ND, PER, CL, TWO>;
+    // closures whose term is identically zero beyond the search radius (WCSPH with 2 h <= r) run
+    // the variant without the exact radius test in the drain
+    bool nor2 = false;
+    if constexpr (has_no_radius_test<CL>::value) nor2 = cl.no_radius_test();
+    auto kern = k_sweep_flat<ND, PER, CL, TWO, false>;
+    if constexpr (has_no_radius_test<CL>::value) { if (nor2) kern = k_sweep_flat<ND, PER, CL, TWO, true>; }
     static int ctas_per_sm = 0;          // per instantiation
-    if (ctas_per_sm == 0) {
-        pnb_status st = allow_smem(kern, smem);
+    static bool smem_allowed[2] = {false, false};   // per instantiation and variant
+    if (!smem_allowed[nor2 ? 1 : 0]) {
+        pnb_status st = allow_smem(kern, smem);     // (both variants share the occupancy)
         if (st != PNB_OK) return st;
+        smem_allowed[nor2 ? 1 : 0] = true;
+    }
+    if (ctas_per_sm == 0) {
         int nb = 0;
         PNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
         if (nb < 1) { set_error("k_sweep_flat does not fit an SM (%zu bytes of shared memory)", smem); return PNB_ERR_CUDA; }
