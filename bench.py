@@ -480,6 +480,7 @@ def gpu_arm(args):
             os.environ.setdefault("MASTER_PORT", "29533")
             dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
         from pnb200 import slabs
+        args.clock_sampler_cls = ClockSampler        # rank 0 samples its GPU during the timed loop
         return slabs.bench_multi_gpu(args, rank, world, dev, METRIC, UNIT)
 
     n = args.lattice

@@ -683,6 +683,12 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     torch.cuda.synchronize()
     dist.barrier()
     launches0 = int(_lib.lib().pnb_launch_count())
+    _lib.profile(enable=True, reset=True)
+    _lib.profile(reset=True)
+    sampler = None
+    if rank == 0 and getattr(args, "clock_sampler_cls", None) is not None:
+        sampler = args.clock_sampler_cls(dev.index or 0)
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
@@ -694,9 +700,11 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
         my_pairs += pairs[(s + 1) % 2]
     ev1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
     dist.barrier()
     ms = ev0.elapsed_time(ev1)
     launches = int(_lib.lib().pnb_launch_count()) - launches0
+    prof = _lib.profile(enable=False)
     stats = dict(stepper.last)
     # phases of the overlapped step (CUDA events on the main stream, a few extra steps)
     phase_acc = {}
@@ -738,6 +746,27 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
         ms_max = float(tmax[0])
         total_pairs = float(tsum[1])
         gs = ex.grid_size
+        # the dominant kernel on rank 0: k_sweep_flat, one interior + one boundary launch per step
+        import os as _os
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        pk = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))),
+                           "MEASURED_PEAKS.json")
+        if _os.path.exists(pk):
+            with open(pk) as fh:
+                hbm_peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        sw_ms, sw_n = prof.get("k_sweep_cells", (0.0, 0))
+        sweep_step_ms = sw_ms / max(args.steps, 1)
+        cells_window = 1
+        for a_, b_ in zip(ex.window[0], ex.window[1]):
+            cells_window *= (b_ - a_ + 1)
+        alg_bytes = 56 * N + 4 * (cells_window + 1)
+        ach = alg_bytes / max(sweep_step_ms * 1e-3, 1e-9) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_sweep_flat<3,false,WcsphClT<false>,false> (rank 0: interior + "
+                    "boundary launch of a step)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "launch_ms": sw_ms / max(sw_n, 1), "launches_per_step": sw_n / max(args.steps, 1),
+                    "algorithmic_bytes": alg_bytes,
+                    "note": "FP32-issue bound, not HBM bound (see the N = 1 line and DESIGN.md 5.2)"}
         line = {
             "metric": metric, "value": total_pairs / (ms_max * 1e-3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
@@ -758,7 +787,9 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
                         "what": "exchange on a side stream behind the sweep of the interior layers; the "
                                 "boundary layers (2 per side) wait for it"},
             "phase_ms_rank0": phase_acc,
+            "roofline": roofline,
             "gpu_launches": launches,
+            "clocks": clocks,
             "e2e": {"value": float(tsum[7]) / k_ab / (float(tmax[6]) * 1e-3), "unit": unit,
                     "h2d_bytes_per_step": int(tsum[8]), "d2h_bytes_per_step": int(tsum[9]),
                     "ms_per_step": float(tmax[6]), "steps": k_ab,

@@ -2,6 +2,7 @@
 # round-2 validation on one B200: full GPU test suite, bench line, launch list, ncu captures of
 # the two hot kernels, compute-sanitizer on the new kernels.  Outputs under gpurun_out/.
 o=gpurun_out
+python tools/smoke_only.py 2>&1 | tail -2
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $o/r2_pytest_gpu.txt; cat $o/r2_pytest_gpu.txt
 python bench.py --steps 20 --warmup 5 > $o/r2_bench_n1.json 2> $o/r2_bench_n1.err; tail -c 300 $o/r2_bench_n1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/r2_launches.csv \
