@@ -752,6 +752,8 @@ def main():
     ap.add_argument("--lattice", type=int, default=254, help="lattice points per dimension (N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-configs", action="store_true", help="skip the config 1 / 2 / 4 sub-lines")
+    ap.add_argument("--slab-mode", choices=["gather", "split"], default=None,
+                    help="how the multi-GPU step hides the exchange (default: gather)")
     ap.add_argument("--slabs", action="store_true",
                     help="run the slab-decomposed config 5 path even on one GPU (strong-scaling base line)")
     ap.add_argument("--slab-lattice", type=int, default=504,

@@ -150,6 +150,14 @@ pnb_status pnb_slab_append_f32(const pnb_slab_arrays *arrays, int64_t n_own, int
                                int64_t depth, const float *recv_up, int64_t n_recv_up,
                                const float *recv_down, int64_t n_recv_down, uint8_t *flags,
                                int32_t *counters_dev, void *stream);
+/* The same for received rows that are row_stride floats apart (0 = dense; the receive buffers of a
+ * pnb_slab_link pad rows to pnb_slab_link_row_stride() floats). */
+pnb_status pnb_slab_append_strided_f32(const pnb_slab_arrays *arrays, int64_t n_own, int ndims,
+                                       float padded_min_z, float cell_size_z, int64_t z_lo,
+                                       int64_t z_hi, int64_t depth, const float *recv_up,
+                                       int64_t n_recv_up, const float *recv_down, int64_t n_recv_down,
+                                       int64_t row_stride, uint8_t *flags, int32_t *counters_dev,
+                                       void *stream);
 /* End of the overlapped step: owned points [0, n_own) minus the n_leave leavers (leave_idx of
  * pnb_slab_pack_f32) plus the n_mig migrants among the n_app appended rows become the owned points
  * [0, n_own - n_leave + n_mig): holes are filled with owned rows from behind.  Every array is
@@ -157,6 +165,32 @@ pnb_status pnb_slab_append_f32(const pnb_slab_arrays *arrays, int64_t n_own, int
 pnb_status pnb_slab_compact_f32(const pnb_slab_arrays *arrays, int64_t n_own, int64_t n_app,
                                 const int32_t *leave_idx, int64_t n_leave, int64_t n_mig,
                                 uint8_t *flags, int32_t *scratch, int32_t *counters_dev, void *stream);
+
+/* The per-step row exchange of neighbouring slabs over NVLink PEER MEMORY instead of NCCL
+ * (csrc/link.cu; no reference counterpart).  Every rank creates a link (its receive area), passes
+ * the 64-byte handle of pnb_slab_link_export to rank - 1 and rank + 1 (any transport), and connects
+ * the handles it got (NULL: no neighbour on that side).  Per step `seq` = 1, 2, 3, ... (the same
+ * on all ranks):
+ *   pnb_slab_link_send: ONE kernel classifies the n owned points (as pnb_slab_classify_f32), stores
+ *     the rows of the leaving / boundary points straight into the neighbours' receive buffers and
+ *     the leavers' indices into leave_idx (>= 2 * cap_rows int32); a second kernel publishes
+ *     (count, seq).  Nothing is synchronised.
+ *   pnb_slab_link_recv (same stream): waits for step `seq` of both neighbours, SYNCHRONISES the
+ *     stream; rows_down / rows_up point into this rank's receive area (valid until step seq + 2 is
+ *     received; rows are pnb_slab_link_row_stride() floats apart, the width rounded up to 4), counts = {n_from_down, n_from_up, n_sent_down, n_sent_up, n_leave}.
+ *     PNB_ERR_LIST_FULL if a message exceeded cap_rows, PNB_ERR_STATE if a neighbour did not
+ *     answer within 20 s. */
+typedef struct pnb_slab_link pnb_slab_link;
+pnb_status pnb_slab_link_create(int64_t cap_rows, int width, pnb_slab_link **out);
+pnb_status pnb_slab_link_export(pnb_slab_link *l, void *handle_out);
+pnb_status pnb_slab_link_connect(pnb_slab_link *l, const void *handle_down, const void *handle_up);
+pnb_status pnb_slab_link_send(pnb_slab_link *l, const pnb_slab_arrays *arrays, int64_t n, int ndims,
+                              float padded_min_z, float cell_size_z, int64_t z_lo, int64_t z_hi,
+                              int32_t *leave_idx, uint64_t seq, void *stream);
+pnb_status pnb_slab_link_recv(pnb_slab_link *l, uint64_t seq, const float **rows_down,
+                              const float **rows_up, int64_t *counts, void *stream);
+int pnb_slab_link_row_stride(const pnb_slab_link *l);
+void pnb_slab_link_destroy(pnb_slab_link *l);
 
 /* ---------------------------------------------------------------------------------------------
  * GridNeighborhoodSearch{NDIMS}(; search_radius, periodic_box,
@@ -210,6 +244,10 @@ pnb_status pnb_grid_build_f32(pnb_grid *g, const float *y, int64_t n, const int3
  * pnb_grid_check synchronises `stream` and returns what a blocking update! would have returned. */
 pnb_status pnb_grid_build_async_f32(pnb_grid *g, const float *y, int64_t n, void *stream);
 pnb_status pnb_grid_check(pnb_grid *g, void *stream);
+/* The same without any synchronisation, for a caller that has already waited for an event it
+ * recorded behind the update! (and pnb_grid_append_f32): kernels launched after that event keep
+ * running; error bits they set are returned by the next check. */
+pnb_status pnb_grid_check_settled(pnb_grid *g);
 
 /* cell_coords + cell_index of arbitrary points (src/nhs_grid.jl:622-628, full_grid.jl:84-94,157-161):
  * out[i] = 0-based linear cell index, or -1 when the cell is outside 2:(size-1). */
@@ -334,8 +372,9 @@ pnb_status pnb_wcsph_interact_async_f32(pnb_grid *g, const float *y, int64_t n, 
  *     y[0 .. first) (ids first + k); y must be the array of that build.
  *   pnb_wcsph_interact_layers_async_f32: sweep the cell layers [cz_a, cz_b] and [cz_c, cz_d] (local
  *     1-based cell coordinates of the last dimension, an empty range has first > last) with one
- *     launch, after gathering the payload of these layers and their neighbours.  dv is written for
- *     the points of the swept layers only.  Nothing is synchronised.
+ *     launch, after gathering the payload of these layers and their neighbours (mode 0); mode 1
+ *     ONLY gathers the payload of exactly these layers, mode 2 ONLY sweeps.  dv is written for the
+ *     points of the swept layers only.  Nothing is synchronised.
  *   pnb_slab_pack_rows_f32: rows of `arrays` listed in `list` -> contiguous send buffer. */
 pnb_status pnb_grid_append_f32(pnb_grid *g, const float *y, int64_t first, int64_t n_more, void *stream);
 pnb_status pnb_slab_pack_rows_f32(const pnb_slab_arrays *arrays, const int32_t *list, int64_t count,
@@ -343,7 +382,7 @@ pnb_status pnb_slab_pack_rows_f32(const pnb_slab_arrays *arrays, const int32_t *
 pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const float *y, int64_t n, const float *v,
                                                const float *mass, const float *pressure,
                                                const pnb_wcsph_params *params, float *dv, int cz_a,
-                                               int cz_b, int cz_c, int cz_d, void *stream);
+                                               int cz_b, int cz_c, int cz_d, int mode, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The WCSPH step from HOST buffers, pipelined (the end-to-end call of a host-side caller).

@@ -155,19 +155,24 @@ pnb_status resolve_pending(pnb_grid *g)
     return settle_async_build(g, &rebuilt);
 }
 
-pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
+static pnb_status check_err_word_settled(pnb_grid *g)
 {
-    // the error word lives in mapped pinned host memory (kernels OR their bits into it through
-    // d_err): one stream synchronisation, no copy
-    PNB_CUDA(cudaStreamSynchronize(s));
     if (g->async_pending) {
-        if (g->async_stream != s) PNB_CUDA(cudaStreamSynchronize(g->async_stream));
         bool rebuilt = false;
         pnb_status st = settle_async_build(g, &rebuilt);
         if (st != PNB_OK) return st;
         if (rebuilt) return PNB_RETRY_INTERNAL;
     }
     return translate_err_word(g);
+}
+
+pnb_status check_err_word(pnb_grid *g, cudaStream_t s)
+{
+    // the error word lives in mapped pinned host memory (kernels OR their bits into it through
+    // d_err): one stream synchronisation, no copy
+    PNB_CUDA(cudaStreamSynchronize(s));
+    if (g->async_pending && g->async_stream != s) PNB_CUDA(cudaStreamSynchronize(g->async_stream));
+    return check_err_word_settled(g);
 }
 
 // The reference reads neighbor_coords LIVE at sweep time (src/nhs_grid.jl:543-548) while its
@@ -1770,6 +1775,16 @@ extern "C" pnb_status pnb_grid_check(pnb_grid *g, void *stream)
     return st == PNB_RETRY_INTERNAL ? PNB_OK : st;
 }
 
+// The same for a caller that has ALREADY waited (cudaEventSynchronize on an event it recorded
+// behind the update! / append) -- nothing is synchronised here, so kernels launched after that
+// event (the sweep) keep running.  Error bits they set are reported by the next check.
+extern "C" pnb_status pnb_grid_check_settled(pnb_grid *g)
+{
+    if (!g) { set_error("grid handle is NULL"); return PNB_ERR_ARG; }
+    const pnb_status st = check_err_word_settled(g);
+    return st == PNB_RETRY_INTERNAL ? PNB_OK : st;
+}
+
 // ---------------------------------------------------------------------------------------------
 // pnb_point_cells
 // ---------------------------------------------------------------------------------------------
@@ -2230,7 +2245,7 @@ namespace pnb {
 // 0 = ghost.  counters[0] += migrants; counters[1] |= 1 if a migrant landed deeper than `depth`
 // layers inside the slab (the interior layers were swept without it: the caller must repeat).
 __global__ void __launch_bounds__(256)
-k_slab_append(pnb_slab_arrays A, int W, int nd, int64_t n_own, const float *__restrict__ rows_a,
+k_slab_append(pnb_slab_arrays A, int64_t W, int nd, int64_t n_own, const float *__restrict__ rows_a,
               int64_t n_a, const float *__restrict__ rows_b, int64_t n_b, float pmin, float cs,
               long long z_lo, long long z_hi, long long depth, unsigned char *__restrict__ flags,
               int32_t *__restrict__ counters)
@@ -2241,7 +2256,9 @@ k_slab_append(pnb_slab_arrays A, int W, int nd, int64_t n_own, const float *__re
         const float *row = r < n_a ? rows_a + r * W : rows_b + (r - n_a) * W;
         const int64_t i = n_own + r;
         int col = 0;
-        for (int a = 0; a < A.n_arrays; a++) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {              // static indices: A stays in the parameter bank
+            if (a >= A.n_arrays) break;
             const int w = A.width[a];
             for (int k = 0; k < w; k++) A.ptr[a][i * w + k] = row[col + k];
             col += w;
@@ -2292,6 +2309,36 @@ __global__ void k_slab_compact_move(pnb_slab_arrays A, const int32_t *__restrict
 // stay valid for the sweep that is already running).  counters_dev: >= 4 int32, zeroed here;
 // after the call counters_dev[0] = migrants among the rows, counters_dev[1] = 1 if one of them
 // lies deeper than `depth` layers inside the slab.
+// row_stride: floats between two rows of recv_up / recv_down (0 = dense, the row width; the
+// receive buffers of a pnb_slab_link pad rows to a multiple of 4 floats)
+extern "C" pnb_status pnb_slab_append_strided_f32(const pnb_slab_arrays *arrays, int64_t n_own, int ndims,
+                                                  float padded_min_z, float cell_size_z, int64_t z_lo,
+                                                  int64_t z_hi, int64_t depth, const float *recv_up,
+                                                  int64_t n_recv_up, const float *recv_down,
+                                                  int64_t n_recv_down, int64_t row_stride, uint8_t *flags,
+                                                  int32_t *counters_dev, void *stream)
+{
+    if (!arrays || arrays->n_arrays < 1 || arrays->n_arrays > 8 || arrays->width[0] != ndims || !flags ||
+        !counters_dev) {
+        set_error("pnb_slab_append_f32: bad arguments");
+        return PNB_ERR_ARG;
+    }
+    int W = 0;
+    for (int a = 0; a < arrays->n_arrays; a++) W += arrays->width[a];
+    if (row_stride == 0) row_stride = W;
+    if (row_stride < W) { set_error("pnb_slab_append_f32: row_stride < row width"); return PNB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    PNB_CUDA(cudaMemsetAsync(counters_dev, 0, 4 * sizeof(int32_t), s));
+    const int64_t n = n_recv_up + n_recv_down;
+    if (n > 0) {
+        k_slab_append<<<(unsigned)div_up(n, 256), 256, 0, s>>>(
+            *arrays, row_stride, ndims, n_own, recv_up, n_recv_up, recv_down, n_recv_down, padded_min_z,
+            cell_size_z, (long long)z_lo, (long long)z_hi, (long long)depth, flags, counters_dev);
+        PNB_LAUNCHED();
+    }
+    return PNB_OK;
+}
+
 extern "C" pnb_status pnb_slab_append_f32(const pnb_slab_arrays *arrays, int64_t n_own, int ndims,
                                           float padded_min_z, float cell_size_z, int64_t z_lo,
                                           int64_t z_hi, int64_t depth, const float *recv_up,
@@ -2299,23 +2346,9 @@ extern "C" pnb_status pnb_slab_append_f32(const pnb_slab_arrays *arrays, int64_t
                                           int64_t n_recv_down, uint8_t *flags, int32_t *counters_dev,
                                           void *stream)
 {
-    if (!arrays || arrays->n_arrays < 1 || arrays->n_arrays > 8 || arrays->width[0] != ndims || !flags ||
-        !counters_dev) {
-        set_error("pnb_slab_append_f32: bad arguments");
-        return PNB_ERR_ARG;
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    PNB_CUDA(cudaMemsetAsync(counters_dev, 0, 4 * sizeof(int32_t), s));
-    const int64_t n = n_recv_up + n_recv_down;
-    if (n > 0) {
-        int W = 0;
-        for (int a = 0; a < arrays->n_arrays; a++) W += arrays->width[a];
-        k_slab_append<<<(unsigned)div_up(n, 256), 256, 0, s>>>(
-            *arrays, W, ndims, n_own, recv_up, n_recv_up, recv_down, n_recv_down, padded_min_z,
-            cell_size_z, (long long)z_lo, (long long)z_hi, (long long)depth, flags, counters_dev);
-        PNB_LAUNCHED();
-    }
-    return PNB_OK;
+    return pnb_slab_append_strided_f32(arrays, n_own, ndims, padded_min_z, cell_size_z, z_lo, z_hi, depth,
+                                       recv_up, n_recv_up, recv_down, n_recv_down, 0, flags, counters_dev,
+                                       stream);
 }
 
 // End of the step: rows [0, n_own) minus the n_leave leavers plus the n_mig migrants among the

@@ -300,8 +300,11 @@ extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const flo
                                                           const float *pressure,
                                                           const pnb_wcsph_params *params, float *dv,
                                                           int cz_a, int cz_b, int cz_c, int cz_d,
-                                                          void *stream)
+                                                          int mode, void *stream)
 {
+    // mode 0: gather the payload of the layers [cz_a - 1, cz_b + 1] and [cz_c - 1, cz_d + 1], then
+    //         sweep [cz_a, cz_b] and [cz_c, cz_d];  1: ONLY gather exactly [cz_a, cz_b] and
+    //         [cz_c, cz_d];  2: ONLY sweep (the payload of the neighbouring layers is in place)
     if (!g || !params) { set_error("NULL argument"); return PNB_ERR_ARG; }
     if (g->f64 || g->hashed || g->p.periodic || !g->built || !g->bucket_valid || g->bucket_tr ||
         !g->full_build || y != g->y_built || n != g->n_y_built || g_exact_arithmetic) {
@@ -313,7 +316,10 @@ extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const flo
     const int nd = g->p.ndims;
     if (nd < 2) { set_error("the layered sweep needs 2 or 3 dimensions"); return PNB_ERR_ARG; }
     const int gl = g->p.gs[nd - 1];
-    auto clip = [&](int &a, int &b) { if (a < 2) a = 2; if (b > gl - 1) b = gl - 1; };
+    auto clip = [&](int &a, int &b) {
+        if (mode == 1) { if (a < 1) a = 1; if (b > gl) b = gl; }
+        else { if (a < 2) a = 2; if (b > gl - 1) b = gl - 1; }
+    };
     clip(cz_a, cz_b);
     clip(cz_c, cz_d);
     const int64_t nb = view_slots(g);
@@ -338,13 +344,17 @@ extern "C" pnb_status pnb_wcsph_interact_layers_async_f32(pnb_grid *g, const flo
     };
     const bool has1 = cz_a <= cz_b, has2 = cz_c <= cz_d;
     if (!has1 && !has2) return PNB_OK;
-    if (has1 && has2 && cz_c - 1 <= cz_b + 1 && cz_a - 1 <= cz_d + 1) {
-        st = gather(min(cz_a, cz_c) - 1, max(cz_b, cz_d) + 1);      // the two ranges touch
-    } else {
-        st = has1 ? gather(cz_a - 1, cz_b + 1) : PNB_OK;
-        if (st == PNB_OK && has2) st = gather(cz_c - 1, cz_d + 1);
+    if (mode != 2) {
+        const int w = mode == 1 ? 0 : 1;          // mode 0 also gathers the neighbouring layers
+        if (has1 && has2 && cz_c - w <= cz_b + w + 1 && cz_a - w <= cz_d + w + 1) {
+            st = gather(min(cz_a, cz_c) - w, max(cz_b, cz_d) + w);      // the two ranges touch
+        } else {
+            st = has1 ? gather(cz_a - w, cz_b + w) : PNB_OK;
+            if (st == PNB_OK && has2) st = gather(cz_c - w, cz_d + w);
+        }
+        if (st != PNB_OK) return st;
+        if (mode == 1) return PNB_OK;
     }
-    if (st != PNB_OK) return st;
     const float h = params->smoothing_length;
     const float inv_h = -0.5f / h, kh = -5.0f * params->kernel_norm / (h * h);
     const float ac = params->alpha * params->sound_speed;

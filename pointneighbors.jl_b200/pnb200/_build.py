@@ -15,7 +15,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libpnb200.so")
 OBJDIR = os.path.join(CSRC, "build")
 
-SOURCES = ["grid.cu", "sweep.cu", "nlist.cu", "hashgrid.cu", "hoststep.cu"]
+SOURCES = ["grid.cu", "sweep.cu", "nlist.cu", "hashgrid.cu", "hoststep.cu", "link.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

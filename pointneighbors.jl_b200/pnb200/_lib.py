@@ -103,6 +103,7 @@ SIGNATURES = {
     "pnb_grid_build_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pnb_grid_build_async_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "pnb_grid_check": (C.c_int, [_vp, _vp]),
+    "pnb_grid_check_settled": (C.c_int, [_vp]),
     "pnb_wcsph_interact_async_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp,
                                                C.POINTER(WcsphParams), _vp, _vp]),
     "pnb_hoststep_create": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
@@ -112,12 +113,23 @@ SIGNATURES = {
     "pnb_grid_append_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "pnb_wcsph_interact_layers_async_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp,
                                                       C.POINTER(WcsphParams), _vp, C.c_int, C.c_int,
-                                                      C.c_int, C.c_int, _vp]),
+                                                      C.c_int, C.c_int, C.c_int, _vp]),
     "pnb_slab_pack_rows_f32": (C.c_int, [C.POINTER(SlabArrays), _vp, _i64, _vp, _vp]),
     "pnb_slab_append_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
                                       _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "pnb_slab_append_strided_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
+                                              _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "pnb_slab_link_row_stride": (C.c_int, [_vp]),
     "pnb_slab_compact_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, _i64, _vp, _i64, _i64, _vp, _vp,
                                        _vp, _vp]),
+    "pnb_slab_link_create": (C.c_int, [_i64, C.c_int, C.POINTER(_vp)]),
+    "pnb_slab_link_export": (C.c_int, [_vp, _vp]),
+    "pnb_slab_link_connect": (C.c_int, [_vp, _vp, _vp]),
+    "pnb_slab_link_send": (C.c_int, [_vp, C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
+                                     _vp, C.c_uint64, _vp]),
+    "pnb_slab_link_recv": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), C.POINTER(_vp),
+                                     C.POINTER(C.c_int64), _vp]),
+    "pnb_slab_link_destroy": (None, [_vp]),
     "pnb_point_cells_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pnb_grid_export_csr": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "pnb_grid_export_dvov": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, _vp]),

@@ -711,12 +711,16 @@ class HostStepper:
             self._h = None
 
 
-def check_(nhs):
+def check_(nhs, settled=False):
     """Synchronise the current stream and raise what a blocking update! would have raised
-    (settles `update_(..., blocking=False)`)."""
+    (settles `update_(..., blocking=False)`).  settled=True: the caller has already waited for an
+    event recorded behind the update!; nothing is synchronised (later kernels keep running)."""
     if isinstance(nhs, PrecomputedNeighborhoodSearch) or nhs.eltype == np.float64:
         return nhs
-    check(_lib.lib().pnb_grid_check(nhs._grid(), _stream()))
+    if settled:
+        check(_lib.lib().pnb_grid_check_settled(nhs._grid()))
+    else:
+        check(_lib.lib().pnb_grid_check(nhs._grid(), _stream()))
     return nhs
 
 

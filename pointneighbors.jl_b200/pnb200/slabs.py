@@ -23,6 +23,7 @@ The exchange logic is plain torch + torch.distributed and runs on CPU tensors wi
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -357,6 +358,49 @@ class SlabNeighborhoodSearch:
 
 
 # ---------------------------------------------------------------------------------------------
+# row exchange over NVLink peer memory (csrc/link.cu)
+# ---------------------------------------------------------------------------------------------
+class SlabLink:
+    """Receive area of this rank + the mapped areas of rank - 1 / rank + 1 (cudaIpc).  The handles
+    travel once through torch.distributed (all_gather of 64 bytes); afterwards a step's exchange is
+    two kernels on the sender and one on the receiver, no NCCL call."""
+
+    def __init__(self, exchange: "SlabExchange", cap_rows: int, width: int, device):
+        import torch
+        import torch.distributed as dist
+        L = _lib.lib()
+        self.handle = C.c_void_p()
+        self.cap, self.width = int(cap_rows), int(width)
+        # every rank must use the same capacity
+        c = torch.tensor([self.cap], dtype=torch.int64, device=device)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX, group=exchange.group)
+        self.cap = int(c.item())
+        check(L.pnb_slab_link_create(self.cap, self.width, C.byref(self.handle)))
+        blob = (C.c_ubyte * 64)()
+        check(L.pnb_slab_link_export(self.handle, blob))
+        mine = torch.tensor(list(blob), dtype=torch.uint8, device=device)
+        every = [torch.zeros_like(mine) for _ in range(exchange.world)]
+        dist.all_gather(every, mine, group=exchange.group)
+        r = exchange.rank
+
+        def raw(k):
+            if k < 0 or k >= exchange.world:
+                return None
+            return (C.c_ubyte * 64)(*every[k].cpu().tolist())
+
+        down, up = raw(r - 1), raw(r + 1)
+        check(L.pnb_slab_link_connect(self.handle, down, up))
+        self.seq = 0
+        self.leave_idx = torch.empty(2 * self.cap, dtype=torch.int32, device=device)
+        dist.barrier(group=exchange.group)
+
+    def close(self):
+        if self.handle:
+            _lib.lib().pnb_slab_link_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+# ---------------------------------------------------------------------------------------------
 # the overlapped WCSPH step of one rank (CUDA only)
 # ---------------------------------------------------------------------------------------------
 class OverlappedWCSPHStep:
@@ -377,17 +421,30 @@ class OverlappedWCSPHStep:
     overlap.  Results: dv[:n_own_new] belongs to arrays[k][:n_own_new]."""
 
     DEPTH = 2          # boundary layers per side that wait for the exchange
-    RESERVE_CTAS = 2   # SMs the interior sweep leaves to the NCCL kernels
+    RESERVE_CTAS = 2   # SMs the interior sweep leaves to the NCCL kernels (MODE "split")
+    SIDE_PRIORITY = os.environ.get("PNB_SLAB_PRIORITY", "1") != "0"
+    PIPELINE = os.environ.get("PNB_SLAB_PIPELINE", "1") != "0"     # no host wait for the sweep
+    EXCHANGE = os.environ.get("PNB_SLAB_EXCHANGE", "p2p")           # "p2p" (csrc/link.cu) | "nccl"
+    LINK_SEND_ON_MAIN = os.environ.get("PNB_SLAB_SEND_ON_MAIN", "1") != "0"
+    LINK_LAYERS = 4    # capacity of a link message in cell layers of owned points
+    MODE = "gather"    # "gather": the exchange hides behind update! + the payload gather of the
+    #                    interior layers, then ONE sweep of all owned layers;  "split": it hides
+    #                    behind a separate sweep of the interior layers (two sweep launches)
 
     def __init__(self, slab: "SlabNeighborhoodSearch", closure_kwargs: dict):
         import torch
         self.slab = slab
         self.ex = slab.exchange
         self.kw = dict(closure_kwargs)
-        self.side = torch.cuda.Stream()
+        # HIGH priority: the block scheduler hands free slots to the oldest kernel first, so the
+        # classification / pack / NCCL kernels of an equal-priority side stream only start at the
+        # tail of the main stream's kernel (measured: 0.92 ms of waiting behind 1.8 ms of cover)
+        self.side = torch.cuda.Stream(priority=-1 if self.SIDE_PRIORITY else 0)
         self.flags = None
         self.scratch = None
         self.counters = None
+        self.cnt_host = None
+        self.link = None
         self.last = {}
 
     def _table(self, arrs):
@@ -421,6 +478,14 @@ class OverlappedWCSPHStep:
                 e.record(main)
                 marks.append((name, e))
 
+        smarks = []
+
+        def smark(name):
+            if profile:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.side)
+                smarks.append((name, e))
+
         mark("start")
         coords = arrays[0]
         closure = pn.WCSPHInteract(dv, arrays[1], arrays[1], arrays[2], arrays[2], arrays[3], arrays[3],
@@ -439,46 +504,94 @@ class OverlappedWCSPHStep:
             ex._x_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
             ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
             ex._x_cap = cap
+        use_link = self.EXCHANGE == "p2p" and ex.world > 1
+        if use_link:
+            # ---- exchange over peer memory, part 1: classify + pack + NVLink stores in ONE kernel
+            #      on the side stream (csrc/link.cu), enqueued before anything else of the step ------
+            if self.link is None:
+                layers = max(ex.z_hi - ex.z_lo + 1, 1)
+                self.link = SlabLink(ex, max(self.LINK_LAYERS * n // layers, 1 << 16), W, dev)
+            link = self.link
+            link.seq += 1
+            tab = self._table(arrays)
+            if self.LINK_SEND_ON_MAIN:
+                # (next to the one-pass update! the send kernel and the build slow each other down:
+                #  measured 0.9 + 1.3 ms side by side at 64 M points, 0.45 ms for the build alone)
+                check(L.pnb_slab_link_send(link.handle, C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi,
+                                           link.leave_idx.data_ptr(), link.seq, stream))
+                self.side.wait_stream(main)
+                mark("send")
+            else:
+                check(L.pnb_slab_link_send(link.handle, C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi,
+                                           link.leave_idx.data_ptr(), link.seq, sstream))
+                smark("sent")
         if can_overlap:
             check(L.pnb_grid_build_async_f32(g, coords.data_ptr(), n, stream))
             nhs._y_ref = coords
             can_overlap = nhs.layout() == "buckets"
         mark("update!")
-        if can_overlap:
+        split = self.MODE == "split"
+        if can_overlap and split:
             # the interior sweep is a persistent kernel: leave a few CTA slots free, otherwise the
             # NCCL kernels of the side stream are not scheduled before it ends (measured: the
             # whole exchange, 0.43 ms at 8 GPUs, was exposed behind a full grid)
             L.pnb_set_sweep_reserve(self.RESERVE_CTAS if (has_up or has_down) else 0)
             check(L.pnb_wcsph_interact_layers_async_f32(
                 g, coords.data_ptr(), n, arrays[1].data_ptr(), arrays[2].data_ptr(), arrays[3].data_ptr(),
-                C.byref(closure.params), dv.data_ptr(), lo_i - off, hi_i - off, 1, 0, stream))
+                C.byref(closure.params), dv.data_ptr(), lo_i - off, hi_i - off, 1, 0, 0, stream))
             L.pnb_set_sweep_reserve(0)
-        mark("interior")
-        counts = (C.c_int64 * 3)()
-        while True:
-            check(L.pnb_slab_classify_f32(coords.data_ptr(), n, nd, pmin, cs, ex.z_lo, ex.z_hi, int(has_up),
-                                          int(has_down), ex._x_idx[0].data_ptr(), ex._x_idx[1].data_ptr(),
-                                          ex._x_idx[2].data_ptr(), ex._x_cap, ex._x_cnt.data_ptr(), counts,
-                                          sstream))           # synchronises the side stream only
-            if max(counts) <= ex._x_cap:
-                break
-            cap = int(max(counts)) + int(max(counts)) // 4 + 1024
-            ex._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
-            ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
-            ex._x_cap = cap
-        n_up, n_down, n_leave = (int(c) for c in counts)
-        send_up, send_down = ex._x_bufs[0][:n_up], ex._x_bufs[1][:n_down]
-        tab = self._table(arrays)
-        check(L.pnb_slab_pack_rows_f32(C.byref(tab), ex._x_idx[0].data_ptr(), n_up, send_up.data_ptr(), sstream))
-        check(L.pnb_slab_pack_rows_f32(C.byref(tab), ex._x_idx[1].data_ptr(), n_down, send_down.data_ptr(), sstream))
-        # ---- 3. exchange on the side stream ------------------------------------------------------
-        with torch.cuda.stream(self.side):
-            recv_up, recv_down = ex._sendrecv(send_up, send_down)
+            mark("interior")
+        elif can_overlap:
+            # payload of the interior layers (the rest follows after the append)
+            check(L.pnb_wcsph_interact_layers_async_f32(
+                g, coords.data_ptr(), n, arrays[1].data_ptr(), arrays[2].data_ptr(), arrays[3].data_ptr(),
+                C.byref(closure.params), dv.data_ptr(), lo_i - off, hi_i - off, 1, 0, 1, stream))
+            mark("gather (interior)")
+        if use_link:
+            # ---- 3. part 2: wait for the neighbours' rows (one host synchronisation) ---------------
+            p_down, p_up = C.c_void_p(), C.c_void_p()
+            cnts = (C.c_int64 * 5)()
+            check(L.pnb_slab_link_recv(link.handle, link.seq, C.byref(p_down), C.byref(p_up), cnts, sstream))
+            smark("received")
+            n_rd, n_ru, n_down, n_up, n_leave = (int(c) for c in cnts)
+            recv_down_ptr, recv_up_ptr = p_down.value or 0, p_up.value or 0
+            leave_ptr = link.leave_idx.data_ptr()
+        elif ex.world == 1:
+            # one slab: nothing to exchange (a point outside the grid is reported by update!)
+            n_up = n_down = n_leave = n_ru = n_rd = 0
+            recv_down_ptr = recv_up_ptr = 0
+            leave_ptr = ex._x_idx[2].data_ptr()
+        else:
+            counts = (C.c_int64 * 3)()
+            while True:
+                check(L.pnb_slab_classify_f32(coords.data_ptr(), n, nd, pmin, cs, ex.z_lo, ex.z_hi, int(has_up),
+                                              int(has_down), ex._x_idx[0].data_ptr(), ex._x_idx[1].data_ptr(),
+                                              ex._x_idx[2].data_ptr(), ex._x_cap, ex._x_cnt.data_ptr(), counts,
+                                              sstream))           # synchronises the side stream only
+                if max(counts) <= ex._x_cap:
+                    break
+                cap = int(max(counts)) + int(max(counts)) // 4 + 1024
+                ex._x_idx = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)]
+                ex._x_bufs = [torch.empty((cap, W), dtype=torch.float32, device=dev) for _ in range(2)]
+                ex._x_cap = cap
+            smark("classified")
+            n_up, n_down, n_leave = (int(c) for c in counts)
+            send_up, send_down = ex._x_bufs[0][:n_up], ex._x_bufs[1][:n_down]
+            tab = self._table(arrays)
+            check(L.pnb_slab_pack_rows_f32(C.byref(tab), ex._x_idx[0].data_ptr(), n_up, send_up.data_ptr(), sstream))
+            check(L.pnb_slab_pack_rows_f32(C.byref(tab), ex._x_idx[1].data_ptr(), n_down, send_down.data_ptr(), sstream))
+            # ---- 3. exchange on the side stream (NCCL: counts, then rows) ---------------------------
+            smark("packed")
+            with torch.cuda.stream(self.side):
+                recv_up, recv_down = ex._sendrecv(send_up, send_down)
+            smark("received")
+            recv_up.record_stream(main)
+            recv_down.record_stream(main)
+            n_ru, n_rd = recv_up.shape[0], recv_down.shape[0]
+            recv_down_ptr, recv_up_ptr = recv_down.data_ptr(), recv_up.data_ptr()
+            leave_ptr = ex._x_idx[2].data_ptr()
         main.wait_stream(self.side)
-        recv_up.record_stream(main)
-        recv_down.record_stream(main)
         mark("wait for the exchange")
-        n_ru, n_rd = recv_up.shape[0], recv_down.shape[0]
         n_app = n_ru + n_rd
         n_rows = n + n_app
         # ---- 4. append what arrived ---------------------------------------------------------------
@@ -501,23 +614,46 @@ class OverlappedWCSPHStep:
             self.flags = torch.empty(coords.shape[0], dtype=torch.uint8, device=dev)
             self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         tab = self._table(arrays)
-        check(L.pnb_slab_append_f32(C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi, D - 1,
-                                    recv_up.data_ptr(), n_ru, recv_down.data_ptr(), n_rd,
-                                    self.flags.data_ptr(), self.counters.data_ptr(), stream))
+        row_stride = int(L.pnb_slab_link_row_stride(link.handle)) if use_link else 0
+        check(L.pnb_slab_append_strided_f32(C.byref(tab), n, nd, pmin, cs, ex.z_lo, ex.z_hi,
+                                            D - 1 if split else D, recv_up_ptr, n_ru, recv_down_ptr, n_rd,
+                                            row_stride, self.flags.data_ptr(), self.counters.data_ptr(), stream))
         redo = not can_overlap
         if can_overlap:
             check(L.pnb_grid_append_f32(g, coords.data_ptr(), n, n_app, stream))
             mark("append")
+            # what the host has to know about this step (migrants, bucket overflow) is final here:
+            # an event behind the append, waited for AFTER the sweep has been launched, so that
+            # the host never waits for the sweep itself and the next step's launches queue behind it
+            if self.cnt_host is None:
+                self.cnt_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+            self.cnt_host.copy_(self.counters, non_blocking=True)
+            settled = torch.cuda.Event()
+            settled.record(main)
             # ---- 5. boundary layers of both sides, one launch -----------------------------------
             a0, b0 = ex.z_lo, min(ex.z_lo + D - 1, ex.z_hi)
             a1, b1 = max(ex.z_hi - D + 1, ex.z_lo + D), ex.z_hi
-            check(L.pnb_wcsph_interact_layers_async_f32(
-                g, coords.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
-                arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), a0 - off, b0 - off,
-                a1 - off, b1 - off, stream))
-            mark("boundary")
-            cnt_h = self.counters.tolist()                 # end of the step: the one synchronisation
-            pn.check_(nhs)
+            ptrs = (g, coords.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
+                    arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr())
+            if split:
+                check(L.pnb_wcsph_interact_layers_async_f32(*ptrs, a0 - off, b0 - off, a1 - off, b1 - off,
+                                                            0, stream))
+                mark("boundary")
+            else:
+                # payload of the layers the appended rows can lie in, then ONE sweep of all owned layers
+                check(L.pnb_wcsph_interact_layers_async_f32(*ptrs, a0 - 1 - off, b0 - off, a1 - off,
+                                                            b1 + 1 - off, 1, stream))
+                mark("gather (boundary)")
+                check(L.pnb_wcsph_interact_layers_async_f32(*ptrs, ex.z_lo - off, ex.z_hi - off, 1, 0, 2,
+                                                            stream))
+                mark("sweep")
+            if self.PIPELINE:
+                settled.synchronize()
+                cnt_h = self.cnt_host.tolist()
+                pn.check_(nhs, settled=True)
+            else:
+                cnt_h = self.counters.tolist()
+                pn.check_(nhs)
             # a bucket overflowed (the library rebuilt the list) or a migrant landed deep inside
             # the slab: the sweeps above are void
             redo = nhs.layout() != "buckets" or cnt_h[1] != 0
@@ -531,7 +667,7 @@ class OverlappedWCSPHStep:
                 check(L.pnb_wcsph_interact_layers_async_f32(
                     g, loc.data_ptr(), n_rows, arrays[1].data_ptr(), arrays[2].data_ptr(),
                     arrays[3].data_ptr(), C.byref(closure.params), dv.data_ptr(), ex.z_lo - off,
-                    ex.z_hi - off, 1, 0, stream))
+                    ex.z_hi - off, 1, 0, 0, stream))
                 pn.check_(nhs)
             else:
                 f = pn.WCSPHInteract(dv[:n_rows], arrays[1][:n_rows], arrays[1][:n_rows], arrays[2][:n_rows],
@@ -543,7 +679,7 @@ class OverlappedWCSPHStep:
         if self.scratch is None or self.scratch.numel() < need:
             self.scratch = torch.empty(need + need // 4, dtype=torch.int32, device=dev)
         tab = self._table(arrays + [dv])
-        check(L.pnb_slab_compact_f32(C.byref(tab), n, n_app, ex._x_idx[2].data_ptr(), n_leave, n_mig,
+        check(L.pnb_slab_compact_f32(C.byref(tab), n, n_app, leave_ptr, n_leave, n_mig,
                                      self.flags.data_ptr(), self.scratch.data_ptr(),
                                      self.counters.data_ptr(), stream))
         mark("compaction")
@@ -555,6 +691,8 @@ class OverlappedWCSPHStep:
             torch.cuda.synchronize()
             self.last["phase_ms"] = {marks[k + 1][0]: marks[k][1].elapsed_time(marks[k + 1][1])
                                      for k in range(len(marks) - 1)}
+            # when the side stream reached its marks, counted from the start of the step
+            self.last["phase_ms"].update({"side: " + nm: marks[0][1].elapsed_time(e) for nm, e in smarks})
         return arrays, dv, n_new
 
 
@@ -642,6 +780,7 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     h = T(r / T(2))
     stepper = OverlappedWCSPHStep(slab, dict(smoothing_length=h, sound_speed=T(10.0), alpha=T(0.02),
                                              beta=T(0.0), delta=T(0.1)))
+    stepper.MODE = str(getattr(args, "slab_mode", None) or OverlappedWCSPHStep.MODE)
     phase_ev = []
 
     def step(s, timed=False, ovl=True, e2e=False):
@@ -681,7 +820,6 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     for s in range(max(args.warmup, 3)):
         step(s, ovl=overlap)
     torch.cuda.synchronize()
-    dist.barrier()
     launches0 = int(_lib.lib().pnb_launch_count())
     _lib.profile(enable=True, reset=True)
     _lib.profile(reset=True)
@@ -690,6 +828,8 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
         sampler = args.clock_sampler_cls(dev.index or 0)
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()                 # all ranks start the timed steps together (the contract's barrier)
     torch.cuda.synchronize()
     ev0.record()
     my_pairs = 0
@@ -724,6 +864,21 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     torch.cuda.synchronize()
     ms_noovl = a0.elapsed_time(a1) / k_ab
     dist.barrier()
+    # ... and with the other way of hiding the exchange
+    mode_main = stepper.MODE
+    stepper.MODE = "split" if mode_main == "gather" else "gather"
+    step(0, ovl=True)
+    step(1, ovl=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a0.record()
+    for s in range(k_ab):
+        step(s, ovl=True)
+    a1.record()
+    torch.cuda.synchronize()
+    ms_other = a0.elapsed_time(a1) / k_ab
+    mode_other, stepper.MODE = stepper.MODE, mode_main
+    dist.barrier()
     t0 = time.perf_counter()
     e2e_pairs = 0
     for s in range(k_ab):
@@ -735,18 +890,41 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     d2h = int(n_cur[0] * 16)
     t = torch.tensor([ms, float(my_pairs), float(N), float(stats.get("bytes_sent", 0)),
                       float(stats.get("ghosts", 0)), ms_noovl, e2e_ms, float(e2e_pairs), float(h2d),
-                      float(d2h), float(n_overlapped)], device=dev, dtype=torch.float64)
+                      float(d2h), float(n_overlapped), ms_other], device=dev, dtype=torch.float64)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone()
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     tmin = t.clone()
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    names = sorted(phase_acc)
+    ph = torch.tensor([phase_acc[k_] for k_ in names], device=dev, dtype=torch.float64)
+    if ph.numel():
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    phase_max = {k_: float(v_) for k_, v_ in zip(names, ph.tolist())}
+    ph_mine = torch.tensor([phase_acc[k_] for k_ in names], device=dev, dtype=torch.float64)
+    ph_all = [torch.zeros_like(ph_mine) for _ in range(world)] if names else []
+    if ph_all:
+        dist.all_gather(ph_all, ph_mine)
+    phase_by_rank = {k_: [round(float(t_[i_]), 3) for t_ in ph_all] for i_, k_ in enumerate(names)}
+    st_all = [torch.zeros(args.steps, device=dev, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(st_all, torch.tensor([a_.elapsed_time(b_) for a_, b_ in phase_ev[:args.steps]],
+                                         device=dev, dtype=torch.float64))
+    step_by_rank = [round(float(t_.median()), 3) for t_ in st_all]
+    # where the timed loop spent its time besides the steps themselves (start-up skew of the ranks)
+    gaps = [ev0.elapsed_time(phase_ev[0][0])] + \
+           [phase_ev[k_][1].elapsed_time(phase_ev[k_ + 1][0]) for k_ in range(args.steps - 1)] + \
+           [phase_ev[args.steps - 1][1].elapsed_time(ev1)]
+    gp_all = [torch.zeros(len(gaps), device=dev, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gp_all, torch.tensor(gaps, device=dev, dtype=torch.float64))
+    loop_by_rank = {"loop_ms": [round(float(a_.sum() + b_.sum()), 3) for a_, b_ in zip(st_all, gp_all)],
+                    "first_step_ms": [round(float(t_[0]), 3) for t_ in st_all],
+                    "gaps_ms": [[round(float(x_), 3) for x_ in t_] for t_ in gp_all]}
     if rank == 0:
         ms_max = float(tmax[0])
         total_pairs = float(tsum[1])
         gs = ex.grid_size
-        # the dominant kernel on rank 0: k_sweep_flat, one interior + one boundary launch per step
+        # the dominant kernel on rank 0: k_sweep_flat (launches_per_step says how many per step)
         import os as _os
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         pk = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))),
@@ -761,8 +939,8 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
             cells_window *= (b_ - a_ + 1)
         alg_bytes = 56 * N + 4 * (cells_window + 1)
         ach = alg_bytes / max(sweep_step_ms * 1e-3, 1e-9) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_sweep_flat<3,false,WcsphClT<false>,false> (rank 0: interior + "
-                    "boundary launch of a step)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_sweep_flat<3,false,WcsphClT<false>,false> (rank 0, all launches "
+                    "of a step)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "launch_ms": sw_ms / max(sw_n, 1), "launches_per_step": sw_n / max(args.steps, 1),
                     "algorithmic_bytes": alg_bytes,
@@ -784,9 +962,19 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
                        "l2": "per-GPU inputs larger than the 126 MB L2"},
             "overlap": {"enabled": overlap, "steps_overlapped_min_over_ranks": int(tmin[10]),
                         "ms_per_step_without_overlap": float(tmax[5]),
-                        "what": "exchange on a side stream behind the sweep of the interior layers; the "
-                                "boundary layers (2 per side) wait for it"},
+                        "mode": mode_main,
+                        "ms_per_step_mode_" + mode_other: float(tmax[11]),
+                        "what": {"gather": "exchange on a side stream behind update! and the payload gather "
+                                           "of the interior layers; then the rows are appended and ONE "
+                                           "sweep covers all owned layers",
+                                 "split": "exchange on a side stream behind the sweep of the interior "
+                                          "layers; the boundary layers (2 per side) wait for it"}[mode_main]},
+            "step_ms_rank0": [round(a_.elapsed_time(b_), 3) for a_, b_ in phase_ev[:args.steps]],
             "phase_ms_rank0": phase_acc,
+            "phase_ms_max_over_ranks": phase_max,
+            "phase_ms_by_rank": phase_by_rank,
+            "step_ms_median_by_rank": step_by_rank,
+            "timed_loop_by_rank": loop_by_rank,
             "roofline": roofline,
             "gpu_launches": launches,
             "clocks": clocks,

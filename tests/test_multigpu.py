@@ -84,44 +84,46 @@ def _worker(rank, world, port, out_dir):
             assert np.all(np.abs(got - ref64) <= 1e-5 * refabs + 1e-30)
             assert ex.last_stats["ghosts"] > 0
         dist.barrier()
-        # ---- the overlapped step (exchange behind the interior sweep) on the same clouds ----------
+        # ---- the overlapped step (both ways of hiding the exchange) on the same clouds ----------
         from pnb200.slabs import OverlappedWCSPHStep
-        slab2 = SlabNeighborhoodSearch(3, r, mn, mx, rank, world)
-        stepper = OverlappedWCSPHStep(slab2, dict(smoothing_length=h, sound_speed=T(10.0)))
-        own0 = rows_all_t[ex.owned_mask(rows_all_t[:, :3])].contiguous()
-        n0 = own0.shape[0]
-        cap = 2 * n0 + 4096
-        def padded(t):
-            out = torch.zeros((cap,) + tuple(t.shape[1:]), device=dev, dtype=torch.float32)
-            out[:n0] = t
-            return out
-        arrs = [padded(own0[:, :3].contiguous()), padded(own0[:, 3:7].contiguous()),
-                padded(own0[:, 7].contiguous()), padded(own0[:, 8].contiguous()),
-                padded(own0[:, 9].contiguous())]
-        dvo = torch.zeros((cap, 4), device=dev)
-        n_own2 = n0
-        clouds = [c, moved,
-                  np.clip(moved + (T(0.2) * r) * rng.uniform(-1, 1, c.shape).astype(T), mn, mx).astype(T)]
-        overlapped = []
-        for it, cloud in enumerate(clouds):
-            gid2 = arrs[4][:n_own2].to(torch.int64)
-            arrs[0][:n_own2] = torch.as_tensor(cloud, device=dev)[gid2]
-            arrs, dvo, n_own2 = stepper.step(arrs, n_own2, dvo)
-            overlapped.append(stepper.last["overlapped"])
-            gid2 = arrs[4][:n_own2].to(torch.int64)
-            dv_g = torch.zeros((N, 4), dtype=torch.float32, device=dev)
-            seen = torch.zeros(N, dtype=torch.int64, device=dev)
-            dv_g[gid2] = dvo[:n_own2]
-            seen[gid2] = 1
-            for t in (dv_g, seen):
-                dist.all_reduce(t)
-            if rank == 0:
-                assert bool((seen == 1).all()), f"ownership broken in overlapped step {it}"
-                og.build(cloud)
-                _, ref64, refabs = og.wcsph(cloud, cloud, vv, vv, mass, mass, pres, pres,
-                                            f.params_array(), wide=True)
-                assert np.all(np.abs(dv_g.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30), it
-        assert overlapped[0] is False and overlapped[-1] is True, overlapped
+        for mode in ("gather", "split"):
+            slab2 = SlabNeighborhoodSearch(3, r, mn, mx, rank, world)
+            stepper = OverlappedWCSPHStep(slab2, dict(smoothing_length=h, sound_speed=T(10.0)))
+            stepper.MODE = mode
+            own0 = rows_all_t[ex.owned_mask(rows_all_t[:, :3])].contiguous()
+            n0 = own0.shape[0]
+            cap = 2 * n0 + 4096
+            def padded(t):
+                out = torch.zeros((cap,) + tuple(t.shape[1:]), device=dev, dtype=torch.float32)
+                out[:n0] = t
+                return out
+            arrs = [padded(own0[:, :3].contiguous()), padded(own0[:, 3:7].contiguous()),
+                    padded(own0[:, 7].contiguous()), padded(own0[:, 8].contiguous()),
+                    padded(own0[:, 9].contiguous())]
+            dvo = torch.zeros((cap, 4), device=dev)
+            n_own2 = n0
+            clouds = [c, moved,
+                      np.clip(moved + (T(0.2) * r) * rng.uniform(-1, 1, c.shape).astype(T), mn, mx).astype(T)]
+            overlapped = []
+            for it, cloud in enumerate(clouds):
+                gid2 = arrs[4][:n_own2].to(torch.int64)
+                arrs[0][:n_own2] = torch.as_tensor(cloud, device=dev)[gid2]
+                arrs, dvo, n_own2 = stepper.step(arrs, n_own2, dvo)
+                overlapped.append(stepper.last["overlapped"])
+                gid2 = arrs[4][:n_own2].to(torch.int64)
+                dv_g = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+                seen = torch.zeros(N, dtype=torch.int64, device=dev)
+                dv_g[gid2] = dvo[:n_own2]
+                seen[gid2] = 1
+                for t in (dv_g, seen):
+                    dist.all_reduce(t)
+                if rank == 0:
+                    assert bool((seen == 1).all()), f"ownership broken in overlapped step {mode} {it}"
+                    og.build(cloud)
+                    _, ref64, refabs = og.wcsph(cloud, cloud, vv, vv, mass, mass, pres, pres,
+                                                f.params_array(), wide=True)
+                    assert np.all(np.abs(dv_g.cpu().numpy() - ref64) <= 1e-5 * refabs + 1e-30), (mode, it)
+            assert overlapped[0] is False and overlapped[-1] is True, overlapped
         if rank == 0:
             open(os.path.join(out_dir, "ok"), "w").write("ok")
         dist.barrier()
