@@ -184,6 +184,8 @@ typedef struct pnb_slab_link pnb_slab_link;
 pnb_status pnb_slab_link_create(int64_t cap_rows, int width, pnb_slab_link **out);
 pnb_status pnb_slab_link_export(pnb_slab_link *l, void *handle_out);
 pnb_status pnb_slab_link_connect(pnb_slab_link *l, const void *handle_down, const void *handle_up);
+/* two links of the same process (tests, profiles): pointers instead of handles */
+pnb_status pnb_slab_link_connect_local(pnb_slab_link *l, pnb_slab_link *down, pnb_slab_link *up);
 pnb_status pnb_slab_link_send(pnb_slab_link *l, const pnb_slab_arrays *arrays, int64_t n, int ndims,
                               float padded_min_z, float cell_size_z, int64_t z_lo, int64_t z_hi,
                               int32_t *leave_idx, uint64_t seq, void *stream);

@@ -42,6 +42,7 @@ struct pnb_slab_link {
     long long *h_out;              // mapped pinned: what pnb_slab_link_recv reports
     long long *d_out;
     uint64_t seq_sent, seq_recv;
+    bool peer_local[2];            // connected with pnb_slab_link_connect_local (same process)
 };
 
 static size_t link_flags_bytes() { return 4 * sizeof(LinkFlag); }
@@ -57,7 +58,7 @@ extern "C" void pnb_slab_link_destroy(pnb_slab_link *l)
     if (!l) return;
     cudaDeviceSynchronize();
     for (int d = 0; d < 2; d++)
-        if (l->peer[d]) cudaIpcCloseMemHandle(l->peer[d]);
+        if (l->peer[d] && !l->peer_local[d]) cudaIpcCloseMemHandle(l->peer[d]);
     cudaFree(l->area);
     cudaFree(l->counts);
     if (l->h_out) cudaFreeHost(l->h_out);
@@ -115,6 +116,25 @@ extern "C" pnb_status pnb_slab_link_connect(pnb_slab_link *l, const void *handle
         void *p = nullptr;
         PNB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         l->peer[d] = static_cast<unsigned char *>(p);
+    }
+    return PNB_OK;
+}
+
+// Two links of the SAME process (two slabs on one device, or on two devices of one process with
+// peer access enabled): plain pointers instead of cudaIpc handles.  Used by the single-GPU tests
+// and profiles of the exchange kernels; the protocol is the same.
+extern "C" pnb_status pnb_slab_link_connect_local(pnb_slab_link *l, pnb_slab_link *down, pnb_slab_link *up)
+{
+    if (!l) { set_error("NULL argument"); return PNB_ERR_ARG; }
+    pnb_slab_link *o[2] = {down, up};
+    for (int d = 0; d < 2; d++) {
+        if (!o[d] || l->peer[d]) continue;
+        if (o[d]->cap != l->cap || o[d]->width != l->width) {
+            set_error("link: neighbours must be created with the same capacity and row width");
+            return PNB_ERR_ARG;
+        }
+        l->peer[d] = o[d]->area;
+        l->peer_local[d] = true;
     }
     return PNB_OK;
 }

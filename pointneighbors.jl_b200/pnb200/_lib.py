@@ -125,6 +125,7 @@ SIGNATURES = {
     "pnb_slab_link_create": (C.c_int, [_i64, C.c_int, C.POINTER(_vp)]),
     "pnb_slab_link_export": (C.c_int, [_vp, _vp]),
     "pnb_slab_link_connect": (C.c_int, [_vp, _vp, _vp]),
+    "pnb_slab_link_connect_local": (C.c_int, [_vp, _vp, _vp]),
     "pnb_slab_link_send": (C.c_int, [_vp, C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
                                      _vp, C.c_uint64, _vp]),
     "pnb_slab_link_recv": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), C.POINTER(_vp),

@@ -1,6 +1,10 @@
 #!/bin/bash
-# 2 GPUs: compute-sanitizer memcheck over the 2-GPU parity test (peer-memory link, strided append,
-# gather / sweep-only layer calls, both overlap modes)
-timeout 420 compute-sanitizer --tool memcheck --target-processes all --print-limit 20 \
-    python -m pytest tests/test_multigpu.py -m gpu -x -q -k two_gpu > gpurun_out/r2k_mg_memcheck.log 2>&1
-echo "rc=$?"; grep -c "ERROR SUMMARY" gpurun_out/r2k_mg_memcheck.log; grep "ERROR SUMMARY\|passed\|failed\|Error" gpurun_out/r2k_mg_memcheck.log | sort | uniq -c | head -20
+# 2 GPUs: compute-sanitizer memcheck around EACH rank of the 2-GPU parity test (peer-memory link,
+# strided append, gather / sweep-only layer calls, both overlap modes)
+o=gpurun_out
+for r in 0 1; do
+  RANK=$r WORLD_SIZE=2 MASTER_PORT=29541 timeout 500 compute-sanitizer --tool memcheck --print-limit 20 \
+      python tools/mg_worker.py > $o/r2k_mg_memcheck_rank$r.log 2>&1 &
+done
+wait
+for r in 0 1; do grep "ERROR SUMMARY\|worker finished\|Error\|Invalid" $o/r2k_mg_memcheck_rank$r.log | sort | uniq -c | head; done
