@@ -90,6 +90,7 @@ def test_link_matches_classify_and_pack(pn, steps):
                 expect.append({"up": rows[lists[0][:n_up].long()], "down": rows[lists[1][:n_down].long()],
                                "leave": np.sort(lists[2][:n_leave].cpu().numpy())})
             leave_bufs = [torch.full((2 * cap,), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+            torch.cuda.synchronize()        # the sends run on other streams than the fills above
             for k in range(world):
                 tab, n = tabs[k]
                 ex = exs[k]
