@@ -544,6 +544,19 @@ pnb_status pnb_wcsph_interact_f64(pnb_grid *g, const double *x, int64_t nx, cons
                                   const double *mass_y, const double *pressure_x,
                                   const double *pressure_y, const pnb_wcsph_params_f64 *params,
                                   double *dv, void *stream);
+/* The same closures on a MIXED-precision search (pnb_grid_create_mixed: Float64 coordinates,
+ * Float32 radius): the closure receives Float32 pos_diff / distance (nhs_grid.jl:547-555 under
+ * Julia's promotion rules), the state arrays and dv are Float32 and the closure arithmetic is the
+ * Float32 operation sequence -- sums bit-identical to the mixed oracle. */
+pnb_status pnb_nbody_mixed(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                           const int32_t *points, int64_t n_points, int index_base, const float *mass,
+                           float G, float *dv, void *stream);
+pnb_status pnb_wcsph_interact_mixed(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                                    const int32_t *points, int64_t n_points, int index_base,
+                                    const float *v_x, const float *v_y, const float *mass_x,
+                                    const float *mass_y, const float *pressure_x,
+                                    const float *pressure_y, const pnb_wcsph_params *params, float *dv,
+                                    void *stream);
 pnb_status pnb_nlist_build_f64(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
                                int sort, pnb_nlist **out, void *stream);
 pnb_status pnb_nlist_pairs_f64(const pnb_nlist *list, const pnb_grid *g, const double *x,

@@ -534,6 +534,44 @@ class MixedGrid:
                                  _ptr(pd, C.c_float), _ptr(dist, C.c_float))
         return pd[:P], dist[:P]
 
+    # fused closures (Float32 closure arithmetic on the mixed pair geometry)
+    def _points(self, points):
+        if points is None:
+            return None, 0
+        pts = np.ascontiguousarray(points, dtype=np.int64)
+        return pts, pts.shape[0]
+
+    def nbody(self, x, y, mass, G, points=None):
+        x, y = self._coords(x), self._coords(y)
+        mass = np.ascontiguousarray(mass, dtype=np.float32)
+        dv = np.zeros((x.shape[0], self.ndims), dtype=np.float32)
+        pts, npts = self._points(points)
+        rc = lib().pno_nbody_mix(C.byref(self.g), _ptr(self.cell_start, C.c_int64),
+                                 _ptr(self.cell_points, C.c_int32), _ptr(x, C.c_double),
+                                 C.c_int64(x.shape[0]), _ptr(y, C.c_double), _ptr(pts, C.c_int64),
+                                 C.c_int64(npts), _ptr(mass, C.c_float), C.c_float(G), _ptr(dv, C.c_float))
+        if rc:
+            raise OracleError(rc)
+        return dv
+
+    def wcsph(self, x, y, v_x, v_y, mass_x, mass_y, pressure_x, pressure_y, params, points=None):
+        x, y = self._coords(x), self._coords(y)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        v_x, v_y, mass_x, mass_y, pressure_x, pressure_y, params = (
+            f(v_x), f(v_y), f(mass_x), f(mass_y), f(pressure_x), f(pressure_y), f(params))
+        dv = np.zeros((x.shape[0], self.ndims + 1), dtype=np.float32)
+        pts, npts = self._points(points)
+        rc = lib().pno_wcsph_mix(C.byref(self.g), _ptr(self.cell_start, C.c_int64),
+                                 _ptr(self.cell_points, C.c_int32), _ptr(x, C.c_double),
+                                 C.c_int64(x.shape[0]), _ptr(y, C.c_double), _ptr(pts, C.c_int64),
+                                 C.c_int64(npts), _ptr(v_x, C.c_float), _ptr(v_y, C.c_float),
+                                 _ptr(mass_x, C.c_float), _ptr(mass_y, C.c_float),
+                                 _ptr(pressure_x, C.c_float), _ptr(pressure_y, C.c_float),
+                                 _ptr(params, C.c_float), _ptr(dv, C.c_float))
+        if rc:
+            raise OracleError(rc)
+        return dv
+
 
 def trivial_lists(x, y, search_radius, periodic_box=None, dtype=np.float32):
     """Brute force (TrivialNeighborhoodSearch) neighbour lists as CSR, ascending ids."""

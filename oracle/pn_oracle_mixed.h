@@ -203,3 +203,74 @@ void pno_list_pairs_mix(const pno_grid_mix *g, const double *x, int64_t nx, cons
             dist[k] = (float)sqrt((double)d2);
         }
 }
+
+/* The fused closures on a mixed-precision search.  foreach_point_neighbor hands the closure the
+ * Float32 pos_diff / distance of nhs_grid.jl:547-555 (distance = sqrt(distance2) in Float32, :555);
+ * with Float32 state arrays the closures of benchmarks/n_body.jl:38-48 and of the WCSPH benchmark
+ * (smoothed_particle_hydrodynamics.jl:45-102) then compute in Float32: exactly the Float32
+ * instantiation of pno_cl_nbody / pno_cl_wcsph above.  Pairs in the reference's visiting order.
+ * points == NULL: all nx points.  Returns 4 when a stencil leaves the grid. */
+typedef void (*pno_pair_fn_mix)(void *ctx, int64_t i, int64_t j, const float *p, float d);
+
+static int pno_foreach_mix(const pno_grid_mix *g, const int64_t *cell_start, const int32_t *cell_points,
+                           const double *x, int64_t nx, const double *y, const int64_t *points,
+                           int64_t npoints, pno_pair_fn_mix f, void *ctx)
+{
+    const int nd = g->ndims;
+    const float r = g->search_radius;
+    const float r2 = r * r;
+    int rc = 0;
+    const int64_t n_loop = points ? npoints : nx;
+    for (int64_t t = 0; t < n_loop; t++) {
+        const int64_t i = points ? points[t] : t;
+        const double *xi = x + i * nd;
+        float p[3] = {0, 0, 0};
+        int64_t cell[3];
+        pno_cell_coords_mix(g, xi, cell);
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int d = 0; d < nd; d++) { lo[d] = -1; hi[d] = 1; }
+        for (int o3 = lo[2]; o3 <= hi[2]; o3++)
+            for (int o2 = lo[1]; o2 <= hi[1]; o2++)
+                for (int o1 = lo[0]; o1 <= hi[0]; o1++) {
+                    int64_t nc[3] = {cell[0] + o1, cell[1] + o2, cell[2] + o3};
+                    pno_periodic_cell_mix(g, nc);
+                    int ok = 1;
+                    for (int d = 0; d < nd; d++)
+                        if (nc[d] < 1 || nc[d] > g->grid_size[d]) ok = 0;
+                    if (!ok) { rc = 4; continue; }
+                    int64_t c = pno_linear_mix(g, nc);
+                    for (int64_t k = cell_start[c]; k < cell_start[c + 1]; k++) {
+                        int64_t j = cell_points[k];
+                        float d2 = pno_pair_mix(g, xi, y + j * nd, p, r2);
+                        if (d2 <= r2) f(ctx, i, j, p, (float)sqrt((double)d2));
+                    }
+                }
+    }
+    return rc;
+}
+
+int pno_nbody_mix(const pno_grid_mix *g, const int64_t *cell_start, const int32_t *cell_points,
+                  const double *x, int64_t nx, const double *y, const int64_t *points, int64_t npoints,
+                  const float *mass, float G, float *dv)
+{
+    pno_nbody_ctx_f32 c = {g->ndims, mass, G, dv, NULL, NULL};
+    for (int64_t i = 0; i < nx * g->ndims; i++) dv[i] = 0;     /* n_body.jl:36 */
+    return pno_foreach_mix(g, cell_start, cell_points, x, nx, y, points, npoints, pno_cl_nbody_f32, &c);
+}
+
+int pno_wcsph_mix(const pno_grid_mix *g, const int64_t *cell_start, const int32_t *cell_points,
+                  const double *x, int64_t nx, const double *y, const int64_t *points, int64_t npoints,
+                  const float *v_x, const float *v_y, const float *mass_x, const float *mass_y,
+                  const float *pressure_x, const float *pressure_y,
+                  const float *params /*h,c,alpha,beta,eps,delta,norm*/, float *dv)
+{
+    pno_wcsph_ctx_f32 c;
+    c.nd = g->ndims;
+    c.v_x = v_x; c.v_y = v_y; c.mass_x = mass_x; c.mass_y = mass_y;
+    c.pressure_x = pressure_x; c.pressure_y = pressure_y;
+    c.h = params[0]; c.sound_speed = params[1]; c.alpha = params[2]; c.beta = params[3];
+    c.epsilon = params[4]; c.delta = params[5]; c.kernel_norm = params[6];
+    c.dv = dv; c.dv64 = NULL; c.dvabs = NULL;
+    for (int64_t i = 0; i < nx * (g->ndims + 1); i++) dv[i] = 0;
+    return pno_foreach_mix(g, cell_start, cell_points, x, nx, y, points, npoints, pno_cl_wcsph_f32, &c);
+}

@@ -154,33 +154,58 @@ k_sweep_points64(GridP64 g, const uint32_t *__restrict__ cell_start,
 // operation an explicit IEEE double operation in the oracle's order (pno_cl_nbody / pno_cl_wcsph
 // instantiated for double) -> sums bit-identical to the Float64 oracle.  Per-point state is read
 // by id straight from the caller's arrays.
-struct Wcsph64P {
-    double h, sound_speed, alpha, beta, epsilon, delta, kernel_norm;
+template <class T>
+struct WcsphTP {
+    T h, sound_speed, alpha, beta, epsilon, delta, kernel_norm;
+};
+using Wcsph64P = WcsphTP<double>;
+// explicit IEEE operations of the element type the CLOSURE computes in: double for a Float64
+// search; float for a mixed-precision search (Float64 coordinates, Float32 radius: pos_diff and
+// distance arrive as Float32, so the closures of the benchmarks run in Float32 on Float32 state)
+struct OpsF64 {
+    using R = double;
+    static __device__ __forceinline__ R mul(R a, R b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ R add(R a, R b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ R sub(R a, R b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ R div(R a, R b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ R sqrt(R a) { return __dsqrt_rn(a); }
+    static __device__ __forceinline__ R sqrt_eps() { return 1.4901161193847656e-8; }
+};
+struct OpsF32 {
+    using R = float;
+    static __device__ __forceinline__ R mul(R a, R b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ R add(R a, R b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ R sub(R a, R b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ R div(R a, R b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ R sqrt(R a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ R sqrt_eps() { return 3.4526698300124393e-4f; }
 };
 //   KIND 0: n-body   (benchmarks/n_body.jl:38-48)            state: mass[n], out dv[nx x nd]
 //   KIND 1: WCSPH    (smoothed_particle_hydrodynamics.jl:45-102)  state: v (nd+1), mass, pressure
-template <int ND, int KIND>
+template <int ND, int KIND, class O>
 __global__ void __launch_bounds__(128)
-k_sweep_closure64(GridP64 g, const uint32_t *__restrict__ cell_start,
+k_sweep_closure_t(GridP64 g, const uint32_t *__restrict__ cell_start,
                   const Rec64 *__restrict__ sorted, const double *__restrict__ x, int64_t n_loop,
-                  const int32_t *__restrict__ points, int base, const double *__restrict__ v_x,
-                  const double *__restrict__ v_y, const double *__restrict__ mass_y,
-                  const double *__restrict__ p_x, const double *__restrict__ p_y, double G,
-                  Wcsph64P prm, double *__restrict__ dv, int *__restrict__ err)
+                  const int32_t *__restrict__ points, int base, const typename O::R *__restrict__ v_x,
+                  const typename O::R *__restrict__ v_y, const typename O::R *__restrict__ mass_y,
+                  const typename O::R *__restrict__ p_x, const typename O::R *__restrict__ p_y,
+                  typename O::R G, WcsphTP<typename O::R> prm, typename O::R *__restrict__ dv,
+                  int *__restrict__ err)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_loop) return;
     const int64_t i = points ? (int64_t)points[t] - base : t;
     constexpr int NS = ND + 1;
-    const double sqrt_eps = 1.4901161193847656e-8;
+    using R = typename O::R;
+    const R sqrt_eps = O::sqrt_eps();
     double xi[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int d = 0; d < ND; d++) xi[d] = x[i * ND + d];
     int cc[3] = {1, 1, 1};
 #pragma unroll
     for (int d = 0; d < ND; d++) cc[d] = cell_coord64(xi[d], g.minc[d], g.cs[d], g.periodic, g.nc[d]);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    double va[4] = {0.0, 0.0, 0.0, 0.0}, p_a = 0.0;
+    R acc[4] = {R(0.0), R(0.0), R(0.0), R(0.0)};
+    R va[4] = {R(0.0), R(0.0), R(0.0), R(0.0)}, p_a = R(0.0);
     if (KIND == 1) {
 #pragma unroll
         for (int k = 0; k < NS; k++) va[k] = v_x[i * NS + k];
@@ -204,76 +229,78 @@ k_sweep_closure64(GridP64 g, const uint32_t *__restrict__ cell_start,
                 const uint32_t b0 = cell_start[lin], b1 = cell_start[lin + 1];
                 for (uint32_t kk = b0; kk < b1; kk++) {
                     const Rec64 yj = sorted[kk];
-                    double p[3];
-                    const double d2 = pair_d2_64<ND>(g, xi, yj, p, true);
-                    if (!(d2 <= g.r2)) continue;
-                    const double d = __dsqrt_rn(d2);
+                    double pd[3];
+                    const double d2d = pair_d2_64<ND>(g, xi, yj, pd, true);
+                    if (!(d2d <= g.r2)) continue;
+                    // (a mixed-precision search hands over Float32 values, widened: the casts are exact)
+                    const R p[3] = {(R)pd[0], (R)pd[1], (R)pd[2]};
+                    const R d = O::sqrt((R)d2d);
                     const int64_t j = yj.id;
                     if (KIND == 0) {
                         if (d < sqrt_eps) continue;
-                        const double tt = __dmul_rn(-G, mass_y[j]);
-                        const double d3 = __dmul_rn(__dmul_rn(d, d), d);
+                        const R tt = O::mul(-G, mass_y[j]);
+                        const R d3 = O::mul(O::mul(d, d), d);
 #pragma unroll
                         for (int k = 0; k < ND; k++)
-                            acc[k] = __dadd_rn(acc[k], __ddiv_rn(__dmul_rn(tt, p[k]), d3));
+                            acc[k] = O::add(acc[k], O::div(O::mul(tt, p[k]), d3));
                     } else {
-                        double vb[4];
+                        R vb[4];
 #pragma unroll
                         for (int k = 0; k < NS; k++) vb[k] = v_y[j * NS + k];
-                        const double rho_a = va[ND], rho_b = vb[ND];
-                        const double rho_mean = __dmul_rn(0.5, __dadd_rn(rho_a, rho_b));
-                        const double m_b = mass_y[j], p_b = p_y[j];
+                        const R rho_a = va[ND], rho_b = vb[ND];
+                        const R rho_mean = O::mul(R(0.5), O::add(rho_a, rho_b));
+                        const R m_b = mass_y[j], p_b = p_y[j];
                         const bool far = !(d < sqrt_eps);
-                        double grad[3] = {0.0, 0.0, 0.0};
+                        R grad[3] = {R(0.0), R(0.0), R(0.0)};
                         if (far) {
-                            const double q = __ddiv_rn(d, prm.h);
-                            double w = 0.0;
-                            if (q < 2.0) {
-                                const double t1 = __dsub_rn(1.0, __dmul_rn(q, 0.5));
-                                w = __dmul_rn(__dmul_rn(-5.0, q), __dmul_rn(__dmul_rn(t1, t1), t1));
+                            const R q = O::div(d, prm.h);
+                            R w = R(0.0);
+                            if (q < R(2.0)) {
+                                const R t1 = O::sub(R(1.0), O::mul(q, R(0.5)));
+                                w = O::mul(O::mul(R(-5.0), q), O::mul(O::mul(t1, t1), t1));
                             }
-                            const double dw = __dmul_rn(__ddiv_rn(prm.kernel_norm, prm.h), w);
-                            const double sg = __ddiv_rn(dw, d);
+                            const R dw = O::mul(O::div(prm.kernel_norm, prm.h), w);
+                            const R sg = O::div(dw, d);
 #pragma unroll
-                            for (int k = 0; k < ND; k++) grad[k] = __dmul_rn(sg, p[k]);
+                            for (int k = 0; k < ND; k++) grad[k] = O::mul(sg, p[k]);
                         }
-                        const double pf = __ddiv_rn(__dmul_rn(-m_b, __dadd_rn(p_a, p_b)), __dmul_rn(rho_a, rho_b));
-                        double vdiff[3] = {0.0, 0.0, 0.0};
+                        const R pf = O::div(O::mul(-m_b, O::add(p_a, p_b)), O::mul(rho_a, rho_b));
+                        R vdiff[3] = {R(0.0), R(0.0), R(0.0)};
 #pragma unroll
-                        for (int k = 0; k < ND; k++) vdiff[k] = __dsub_rn(va[k], vb[k]);
-                        double vr = __dmul_rn(vdiff[0], p[0]);
+                        for (int k = 0; k < ND; k++) vdiff[k] = O::sub(va[k], vb[k]);
+                        R vr = O::mul(vdiff[0], p[0]);
 #pragma unroll
-                        for (int k = 1; k < ND; k++) vr = __dadd_rn(vr, __dmul_rn(vdiff[k], p[k]));
-                        double visc = 0.0;
-                        if (vr < 0.0) {
-                            const double mu = __ddiv_rn(__dmul_rn(prm.h, vr),
-                                                        __dadd_rn(__dmul_rn(d, d), __dmul_rn(prm.epsilon, __dmul_rn(prm.h, prm.h))));
-                            const double pi_ab = __ddiv_rn(
-                                __dsub_rn(__dmul_rn(__dmul_rn(prm.alpha, prm.sound_speed), mu),
-                                          __dmul_rn(prm.beta, __dmul_rn(mu, mu))), rho_mean);
-                            visc = __dmul_rn(m_b, pi_ab);
+                        for (int k = 1; k < ND; k++) vr = O::add(vr, O::mul(vdiff[k], p[k]));
+                        R visc = R(0.0);
+                        if (vr < R(0.0)) {
+                            const R mu = O::div(O::mul(prm.h, vr),
+                                                        O::add(O::mul(d, d), O::mul(prm.epsilon, O::mul(prm.h, prm.h))));
+                            const R pi_ab = O::div(
+                                O::sub(O::mul(O::mul(prm.alpha, prm.sound_speed), mu),
+                                          O::mul(prm.beta, O::mul(mu, mu))), rho_mean);
+                            visc = O::mul(m_b, pi_ab);
                         }
 #pragma unroll
                         for (int k = 0; k < ND; k++)
-                            acc[k] = __dadd_rn(acc[k], __dadd_rn(__dmul_rn(pf, grad[k]), __dmul_rn(visc, grad[k])));
-                        double vg = __dmul_rn(vdiff[0], grad[0]);
+                            acc[k] = O::add(acc[k], O::add(O::mul(pf, grad[k]), O::mul(visc, grad[k])));
+                        R vg = O::mul(vdiff[0], grad[0]);
 #pragma unroll
-                        for (int k = 1; k < ND; k++) vg = __dadd_rn(vg, __dmul_rn(vdiff[k], grad[k]));
-                        double drho = __dmul_rn(__dmul_rn(__ddiv_rn(rho_a, rho_b), m_b), vg);
+                        for (int k = 1; k < ND; k++) vg = O::add(vg, O::mul(vdiff[k], grad[k]));
+                        R drho = O::mul(O::mul(O::div(rho_a, rho_b), m_b), vg);
                         if (far) {
-                            const double vol_b = __ddiv_rn(m_b, rho_b);
-                            const double two_drho = __dmul_rn(2.0, __dsub_rn(rho_a, rho_b));
-                            const double dd = __dmul_rn(d, d);
-                            double pg = 0.0;
+                            const R vol_b = O::div(m_b, rho_b);
+                            const R two_drho = O::mul(R(2.0), O::sub(rho_a, rho_b));
+                            const R dd = O::mul(d, d);
+                            R pg = R(0.0);
 #pragma unroll
                             for (int k = 0; k < ND; k++) {
-                                const double psi = __ddiv_rn(__dmul_rn(two_drho, p[k]), dd);
-                                pg = (k == 0) ? __dmul_rn(psi, grad[k]) : __dadd_rn(pg, __dmul_rn(psi, grad[k]));
+                                const R psi = O::div(O::mul(two_drho, p[k]), dd);
+                                pg = (k == 0) ? O::mul(psi, grad[k]) : O::add(pg, O::mul(psi, grad[k]));
                             }
-                            drho = __dadd_rn(drho, __dmul_rn(__dmul_rn(__dmul_rn(prm.delta, prm.h), prm.sound_speed),
-                                                             __dmul_rn(pg, vol_b)));
+                            drho = O::add(drho, O::mul(O::mul(O::mul(prm.delta, prm.h), prm.sound_speed),
+                                                             O::mul(pg, vol_b)));
                         }
-                        acc[ND] = __dadd_rn(acc[ND], drho);
+                        acc[ND] = O::add(acc[ND], drho);
                     }
                 }
             }

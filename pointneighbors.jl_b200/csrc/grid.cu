@@ -2821,9 +2821,9 @@ extern "C" pnb_status pnb_nbody_f64(pnb_grid *g, const double *x, int64_t nx, co
         const Wcsph64P none{};
         ProfScope ps(PH_SWEEP_POINTS, s);
         switch (nd) {
-            case 1: k_sweep_closure64<1, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
-            case 2: k_sweep_closure64<2, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
-            default: k_sweep_closure64<3, 0><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            case 1: k_sweep_closure_t<1, 0, OpsF64><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            case 2: k_sweep_closure_t<2, 0, OpsF64><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            default: k_sweep_closure_t<3, 0, OpsF64><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
         }
         PNB_LAUNCHED();
     }
@@ -2851,9 +2851,82 @@ extern "C" pnb_status pnb_wcsph_interact_f64(pnb_grid *g, const double *x, int64
                            params->epsilon, params->delta, params->kernel_norm};
         ProfScope ps(PH_SWEEP_POINTS, s);
         switch (nd) {
-            case 1: k_sweep_closure64<1, 1><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
-            case 2: k_sweep_closure64<2, 1><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
-            default: k_sweep_closure64<3, 1><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+            case 1: k_sweep_closure_t<1, 1, OpsF64><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+            case 2: k_sweep_closure_t<2, 1, OpsF64><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+            default: k_sweep_closure_t<3, 1, OpsF64><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0, prm, dv, g->d_err); break;
+        }
+        PNB_LAUNCHED();
+    }
+    return check_err_word(g, s);
+}
+
+// The fused closures on a MIXED-precision search (Float64 coordinates, Float32 radius,
+// tut_gpu_usage.jl:45-50): the closure receives Float32 pos_diff / distance (nhs_grid.jl:547-555
+// under Julia's promotion rules), so with Float32 state arrays the benchmark closures compute in
+// Float32 -- the Float32 instantiation of the same kernel (oracle: pno_nbody_mix / pno_wcsph_mix).
+static pnb_status closure_mixed_precheck(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                                         cudaStream_t s)
+{
+    if (!g || !g->f64 || !g->p64.mixed) {
+        set_error("not a mixed-precision grid handle (pnb_grid_create_mixed)");
+        return PNB_ERR_ARG;
+    }
+    if (!g->built) {
+        set_error("the neighborhood search has not been initialized (call initialize! first)");
+        return PNB_ERR_STATE;
+    }
+    if (nx > 0 && !x) { set_error("x is NULL"); return PNB_ERR_ARG; }
+    return check_built_y(g, y, n, s);
+}
+
+extern "C" pnb_status pnb_nbody_mixed(pnb_grid *g, const double *x, int64_t nx, const double *y, int64_t n,
+                                      const int32_t *points, int64_t n_points, int index_base,
+                                      const float *mass, float G, float *dv, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    pnb_status st = closure_mixed_precheck(g, x, nx, y, n, s);
+    if (st != PNB_OK) return st;
+    const int nd = g->p64.ndims;
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * nd, s));
+    const int64_t n_loop = points ? n_points : nx;
+    if (!g->template_search && g->n_built > 0 && n_loop > 0) {
+        const unsigned blocks = (unsigned)div_up(n_loop, 128);
+        const WcsphTP<float> none{};
+        ProfScope ps(PH_SWEEP_POINTS, s);
+        switch (nd) {
+            case 1: k_sweep_closure_t<1, 0, OpsF32><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            case 2: k_sweep_closure_t<2, 0, OpsF32><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+            default: k_sweep_closure_t<3, 0, OpsF32><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, nullptr, nullptr, mass, nullptr, nullptr, G, none, dv, g->d_err); break;
+        }
+        PNB_LAUNCHED();
+    }
+    return check_err_word(g, s);
+}
+
+extern "C" pnb_status pnb_wcsph_interact_mixed(pnb_grid *g, const double *x, int64_t nx, const double *y,
+                                               int64_t n, const int32_t *points, int64_t n_points,
+                                               int index_base, const float *v_x, const float *v_y,
+                                               const float *mass_x, const float *mass_y,
+                                               const float *pressure_x, const float *pressure_y,
+                                               const pnb_wcsph_params *params, float *dv, void *stream)
+{
+    (void)mass_x;
+    cudaStream_t s = (cudaStream_t)stream;
+    pnb_status st = closure_mixed_precheck(g, x, nx, y, n, s);
+    if (st != PNB_OK) return st;
+    if (!params) { set_error("params is NULL"); return PNB_ERR_ARG; }
+    const int nd = g->p64.ndims;
+    if (nx > 0) PNB_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)nx * (nd + 1), s));
+    const int64_t n_loop = points ? n_points : nx;
+    if (!g->template_search && g->n_built > 0 && n_loop > 0) {
+        const unsigned blocks = (unsigned)div_up(n_loop, 128);
+        const WcsphTP<float> prm{params->smoothing_length, params->sound_speed, params->alpha, params->beta,
+                                 params->epsilon, params->delta, params->kernel_norm};
+        ProfScope ps(PH_SWEEP_POINTS, s);
+        switch (nd) {
+            case 1: k_sweep_closure_t<1, 1, OpsF32><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0f, prm, dv, g->d_err); break;
+            case 2: k_sweep_closure_t<2, 1, OpsF32><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0f, prm, dv, g->d_err); break;
+            default: k_sweep_closure_t<3, 1, OpsF32><<<blocks, 128, 0, s>>>(g->p64, g->cell_start, g->sorted64, x, n_loop, points, index_base, v_x, v_y, mass_y, pressure_x, pressure_y, 0.0f, prm, dv, g->d_err); break;
         }
         PNB_LAUNCHED();
     }

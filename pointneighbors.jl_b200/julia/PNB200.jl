@@ -385,6 +385,37 @@ function foreach_point_neighbor(f::WCSPHInteract64, x::B200Array{Float64, 2}, y:
     return nothing
 end
 
+# Mixed precision (Float64 coordinates, Float32 search radius, tut_gpu_usage.jl:45-50): the closure
+# receives Float32 pos_diff / distance, so the Float32 closures apply to Float64 coordinates; the
+# library rejects a handle that is not a mixed-precision search.
+function foreach_point_neighbor(f::NBodyGravity, x::B200Array{Float64, 2}, y::B200Array{Float64, 2},
+                                nhs::B200GridNeighborhoodSearch;
+                                parallelization_backend = default_backend(x),
+                                points = axes(x, 2))
+    pv, np = points_arg(points, size(x, 2))
+    GC.@preserve pv check(ccall((:pnb_nbody_mixed, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint,
+                 Ptr{Cvoid}, Cfloat, Ptr{Cvoid}, Ptr{Cvoid}),
+                nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2),
+                pv === C_NULL ? C_NULL : pv.ptr, np, 1, f.mass.ptr, f.G, f.dv.ptr, C_NULL))
+    return nothing
+end
+function foreach_point_neighbor(f::WCSPHInteract, x::B200Array{Float64, 2}, y::B200Array{Float64, 2},
+                                nhs::B200GridNeighborhoodSearch;
+                                parallelization_backend = default_backend(x),
+                                points = axes(x, 2))
+    pv, np = points_arg(points, size(x, 2))
+    prm = Ref(f.params)
+    GC.@preserve pv check(ccall((:pnb_wcsph_interact_mixed, libpnb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint,
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ref{WcsphParams}, Ptr{Cvoid}, Ptr{Cvoid}),
+                nhs.handle, x.ptr, size(x, 2), y.ptr, size(y, 2),
+                pv === C_NULL ? C_NULL : pv.ptr, np, 1, f.v_x.ptr, f.v_y.ptr, f.mass_x.ptr,
+                f.mass_y.ptr, f.pressure_x.ptr, f.pressure_y.ptr, prm, f.dv.ptr, C_NULL))
+    return nothing
+end
+
 # The WCSPH step from HOST arrays, pipelined inside the library (pnb_hoststep_*): what a host-side
 # caller does per step -- copy coordinates and state to the device, update!, interact!, copy dv
 # back -- with the copies of neighbouring steps overlapping the kernels.  Host arrays should be

@@ -91,6 +91,9 @@ SIGNATURES = {
     "pnb_nbody_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _f64, _vp, _vp]),
     "pnb_wcsph_interact_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _vp,
                                          _vp, _vp, _vp, C.POINTER(WcsphParams64), _vp, _vp]),
+    "pnb_nbody_mixed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _f32, _vp, _vp]),
+    "pnb_wcsph_interact_mixed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, C.POINTER(WcsphParams), _vp, _vp]),
     "pnb_nlist_build_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), _vp]),
     "pnb_nlist_pairs_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnb_grid_create_hashed_f32": (C.c_int, [C.c_int, _f32, _i64, _pf, _pf, C.POINTER(_vp)]),

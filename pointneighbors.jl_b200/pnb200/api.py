@@ -881,6 +881,25 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
             check(L.pnb_count_neighbors_f64(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(),
                                             y.shape[0], _ptr(pts), 0 if pts is None else pts.numel(),
                                             0, f.n_neighbors.data_ptr(), _stream()))
+        elif isinstance(f, (NBodyGravity, WCSPHInteract)) and getattr(nhs.cell_list, "mixed", False):
+            # mixed precision: Float64 coordinates, Float32 pos_diff / distance, Float32 state
+            import torch
+            arrs = [f.dv, f.mass] if isinstance(f, NBodyGravity) else \
+                [f.dv, f.v_x, f.v_y, f.mass_x, f.mass_y, f.pressure_x, f.pressure_y]
+            if any(a.dtype != torch.float32 for a in arrs):
+                raise TypeError("a mixed-precision search hands Float32 pos_diff / distance to the closure: "
+                                "its state arrays and dv must be float32")
+            n_pts = 0 if pts is None else pts.numel()
+            if isinstance(f, NBodyGravity):
+                check(L.pnb_nbody_mixed(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
+                                        _ptr(pts), n_pts, 0, f.mass.data_ptr(), np.float32(f.G),
+                                        f.dv.data_ptr(), _stream()))
+            else:
+                check(L.pnb_wcsph_interact_mixed(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(),
+                                                 y.shape[0], _ptr(pts), n_pts, 0, f.v_x.data_ptr(),
+                                                 f.v_y.data_ptr(), f.mass_x.data_ptr(), f.mass_y.data_ptr(),
+                                                 f.pressure_x.data_ptr(), f.pressure_y.data_ptr(),
+                                                 C.byref(f.params), f.dv.data_ptr(), _stream()))
         elif isinstance(f, NBodyGravity) and not getattr(nhs.cell_list, "mixed", False):
             check(L.pnb_nbody_f64(nhs._grid(), x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0],
                                   _ptr(pts), 0 if pts is None else pts.numel(), 0, f.mass.data_ptr(),
@@ -898,9 +917,9 @@ def foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_searc
             lists = _NeighborLists.build(nhs, x, y, sort=False)
             lists.call_host(f, x, y, nhs, points, radius_test=True)
         else:
-            raise TypeError("Float64 searches have the fused n-body / WCSPH closures (all arrays "
-                            "float64); the TLSPH closures and mixed-precision searches use Float32 / "
-                            "neighbour lists")
+            raise TypeError("Float64 searches have the fused n-body / WCSPH closures (all arrays float64; "
+                            "float32 state on a mixed-precision search); the TLSPH closures use Float32 "
+                            "searches / neighbour lists")
         return None
     pts = _index_tensor(points, x.shape[0], "points")
     npts = 0 if pts is None else pts.numel()

@@ -114,3 +114,48 @@ def test_mixed_from_padded_corners(pn, oracle):
         assert np.array_equal(a.cpu().numpy(), og.point_cells(y))
     finally:
         L.pnb_grid_destroy(h)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_mixed_fused_closures(pn, oracle, nd, periodic):
+    """n-body and WCSPH closures on a mixed-precision search: Float32 pos_diff / distance reach the
+    closure (nhs_grid.jl:547-555), Float32 state, Float32 closure arithmetic -- sums bit-identical
+    to the mixed oracle (np.array_equal), with a `points` subset and two point sets, beta != 0."""
+    rng = np.random.default_rng(70 + nd)
+    n, T = 2500, np.float32
+    shift = 1000.0
+    y = rng.random((n, nd)) * 2 - 1 + shift
+    xq = rng.random((301, nd)) * 2 - 1 + shift
+    r = T(0.16 if nd == 3 else 0.07)
+    mn, mx = np.full(nd, shift - 1.0), np.full(nd, shift + 1.0)
+    box = (mn.astype(T), mx.astype(T)) if periodic else None
+    nhs = make_mixed(pn, nd, r, mn, mx, box=box, n_points=n)
+    og = oracle.MixedGrid(nd, r, mn, mx, periodic_box=box)
+    ty, tx = dev(y), dev(xq)
+    pn.initialize_(nhs, tx, ty)
+    og.build(y)
+    mass = (T(0.5) + rng.random(n).astype(T)).astype(T)
+    # ---- n-body: two point sets, then a subset of the points --------------------------------
+    dv = torch.full((len(xq), nd), 7.0, dtype=torch.float32, device="cuda")
+    pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), T(1.5)), tx, ty, nhs)
+    assert np.array_equal(dv.cpu().numpy(), og.nbody(xq, y, mass, T(1.5)))
+    pts = rng.choice(len(xq), 77, replace=False)
+    dv.fill_(3.0)
+    pn.foreach_point_neighbor(pn.NBodyGravity(dv, dev(mass), T(1.5)), tx, ty, nhs, points=pts)
+    assert np.array_equal(dv.cpu().numpy(), og.nbody(xq, y, mass, T(1.5), points=pts))
+    # ---- WCSPH, x === y -------------------------------------------------------------------------
+    pn.initialize_(nhs, ty, ty)
+    v = np.concatenate([rng.normal(0, 0.1, (n, nd)), 1000.0 + rng.random((n, 1))], axis=1).astype(T)
+    pres = (T(100.0) * (v[:, nd] - T(1000.0))).astype(T)
+    dvw = torch.zeros((n, nd + 1), dtype=torch.float32, device="cuda")
+    f = pn.WCSPHInteract(dvw, dev(v), dev(v), dev(mass), dev(mass), dev(pres), dev(pres),
+                         smoothing_length=T(r / T(2)), sound_speed=T(10.0), alpha=T(0.02), beta=T(0.3),
+                         delta=T(0.1), ndims_=nd)
+    pn.foreach_point_neighbor(f, ty, ty, nhs)
+    ref = og.wcsph(y, y, v, v, mass, mass, pres, pres, f.params_array())
+    assert np.array_equal(dvw.cpu().numpy(), ref)
+    assert np.abs(ref).max() > 0
+    # Float64 state on a mixed search is a type error, not a silent conversion
+    with pytest.raises(TypeError):
+        pn.foreach_point_neighbor(pn.NBodyGravity(dv.double(), dev(mass).double(), 1.5), tx, ty, nhs)
