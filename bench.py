@@ -458,6 +458,29 @@ def sub_configs(dev, hbm_peak, fp32_peak):
     return out
 
 
+def config5_one_gpu(steps=5, timeout_s=240):
+    """`bench.py --slabs --slab-quick` in a child process: 504^3 = 128 M particles through the slab
+    code path on one GPU (what N = 2, 4, 8 are compared with).  Never raises."""
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--slabs", "--slab-quick", "--steps",
+                              str(steps), "--warmup", "3"], capture_output=True, text=True,
+                             timeout=timeout_s, env=env)
+        rows = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        if not rows:
+            return {"error": (out.stderr or out.stdout)[-400:]}
+        d = json.loads(rows[-1])
+        return {"workload": d["config"]["workload"], "metric": d["metric"], "value": d["value"],
+                "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"],
+                "particles": d["config"]["particles_total"], "gpu_launches": d["gpu_launches"],
+                "what": "strong-scaling base line of `bench.py --gpus N` for N > 1 (same code path, one slab)"}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
 def gpu_arm(args):
     import torch
     import pnb200 as pn
@@ -735,6 +758,11 @@ def gpu_arm(args):
             line["configs"] = sub_configs(dev, hbm_peak, fp32_peak)
         except Exception as exc:      # the headline must survive a failing side measurement
             line["configs"] = {"error": repr(exc)}
+    if not args.no_sub_configs and n == 254:
+        # BASELINE config 5 on this one GPU: the strong-scaling base line of `bench.py --gpus N > 1`
+        # (a child process: the slab path sets up torch.distributed with one rank)
+        torch.cuda.empty_cache()
+        line["configs"]["5_one_gpu"] = config5_one_gpu()
     if not args.no_cpu_baseline:
         cb = run_cpu_arm(n, 2, 0, budget_s=25.0)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"],
@@ -759,6 +787,7 @@ def main():
     ap.add_argument("--slab-lattice", type=int, default=504,
                     help="lattice of the slab-decomposed cloud (504 = BASELINE config 5)")
     ap.add_argument("--no-overlap", action="store_true", help="slab path: exchange not overlapped (A/B)")
+    ap.add_argument("--slab-quick", action="store_true", help="slab path: headline only, no A/B runs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -846,9 +846,10 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     launches = int(_lib.lib().pnb_launch_count()) - launches0
     prof = _lib.profile(enable=False)
     stats = dict(stepper.last)
+    quick = bool(getattr(args, "slab_quick", False))      # headline only (sub-line of the N = 1 bench)
     # phases of the overlapped step (CUDA events on the main stream, a few extra steps)
     phase_acc = {}
-    for s in range(4):
+    for s in range(0 if quick else 4):
         k = (s + 1) % 2
         bufs[k], dvs[k], n_cur[k] = stepper.step(bufs[k], n_cur[k], dvs[k], overlap=overlap, profile=True)
         for name, v_ in stepper.last.get("phase_ms", {}).items():
@@ -858,7 +859,7 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     a0.record()
-    for s in range(k_ab):
+    for s in range(0 if quick else k_ab):
         step(s, ovl=False)
     a1.record()
     torch.cuda.synchronize()
@@ -867,12 +868,13 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     # ... and with the other way of hiding the exchange
     mode_main = stepper.MODE
     stepper.MODE = "split" if mode_main == "gather" else "gather"
-    step(0, ovl=True)
-    step(1, ovl=True)
+    if not quick:
+        step(0, ovl=True)
+        step(1, ovl=True)
     torch.cuda.synchronize()
     dist.barrier()
     a0.record()
-    for s in range(k_ab):
+    for s in range(0 if quick else k_ab):
         step(s, ovl=True)
     a1.record()
     torch.cuda.synchronize()
@@ -881,11 +883,11 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
     dist.barrier()
     t0 = time.perf_counter()
     e2e_pairs = 0
-    for s in range(k_ab):
+    for s in range(1 if quick else k_ab):
         step(s, ovl=overlap, e2e=True)
         e2e_pairs += pairs[(s + 1) % 2]
     torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / k_ab
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / (1 if quick else k_ab)
     h2d = int(sum(t.numel() * 4 for t in host[0]))
     d2h = int(n_cur[0] * 16)
     t = torch.tensor([ms, float(my_pairs), float(N), float(stats.get("bytes_sent", 0)),
@@ -954,7 +956,11 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
             "config": {"workload": f"WCSPH step 3D, slab-decomposed (BASELINE config 5): {n}^3 = {int(tsum[2])} "
                                    f"particles, {gs[0]}x{gs[1]}x{gs[2]} cells, over {world} GPU(s) "
                                    f"({(gs[2] - 2) // world} cell layers per GPU), per step: migrant + ghost "
-                                   "exchange (NCCL send/recv), update!, interact! of the owned layers",
+                                   "exchange with the neighbouring slabs, update!, interact! of the owned layers",
+                       "exchange": ("none (one slab)" if world == 1 else
+                                    "NVLink peer memory: one kernel classifies, packs and stores the rows into the "
+                                    "neighbour's buffer (csrc/link.cu)" if stepper.EXCHANGE == "p2p"
+                                    else "NCCL send/recv (counts, then rows)"),
                        "particles_total": int(tsum[2]), "search_radius": float(r),
                        "velocities": "zero (reference benchmark)",
                        "ghost_points_per_rank_max": int(tmax[4]),
@@ -978,7 +984,7 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
             "roofline": roofline,
             "gpu_launches": launches,
             "clocks": clocks,
-            "e2e": {"value": float(tsum[7]) / k_ab / (float(tmax[6]) * 1e-3), "unit": unit,
+            "e2e": {"value": float(tsum[7]) / (1 if quick else k_ab) / (float(tmax[6]) * 1e-3), "unit": unit,
                     "h2d_bytes_per_step": int(tsum[8]), "d2h_bytes_per_step": int(tsum[9]),
                     "ms_per_step": float(tmax[6]), "steps": k_ab,
                     "mode": "every rank copies the coordinates, state and pressure of its owned rows from "
