@@ -636,27 +636,37 @@ def gpu_arm(args):
     hdv = [torch.empty((N, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     hcoords = [hA, hB]
     stepper = pn.HostStepper(nhs, N)
-    e2e_steps = max(4, min(args.steps, 10))
+    # like TrixiParticles (compute_pressure! before interact!, smoothed_particle_hydrodynamics.jl:99)
+    # the pressure is derived on the DEVICE from the density row of v: the host inputs of a step are
+    # the coordinates and v
+    stepper.set_state_equation(sound_speed=10.0, reference_density=1000.0)
+    e2e_steps = max(4, min(args.steps, 50))
 
     def run_e2e(k):
         done = 0
         for s in range(k):
-            stepper.submit(hcoords[(s + 1) % 2], hv, hp, hdv[s % 2], closure, mass_host=hm if s == 0 else None)
+            stepper.submit(hcoords[(s + 1) % 2], hv, None, hdv[s % 2], closure, mass_host=hm if s == 0 else None)
             done += pairs[(s + 1) % 2]
         stepper.wait()
         return done
 
     run_e2e(3)
     torch.cuda.synchronize()
+    ht0 = stepper.host_times()
     t0 = time.perf_counter()
     e2e_pairs = run_e2e(e2e_steps)
     e2e_ms = 1e3 * (time.perf_counter() - t0)      # wall clock around submit ... wait
+    e2e_host = stepper.host_times(since=ht0)
     # the device result of the last step must be what the resident path computes
     e2e_same = None
     try:
         yl = coords[e2e_steps % 2]
         pn.update_(nhs, yl, yl)
-        pn.foreach_point_neighbor(closure, yl, yl, nhs)
+        p_dev = torch.empty_like(pressure)
+        pn.compute_pressure_(p_dev, v, sound_speed=10.0, reference_density=1000.0)
+        closure_p = pn.WCSPHInteract(dv, v, v, mass, mass, p_dev, p_dev, smoothing_length=h,
+                                     sound_speed=T(10.0), alpha=T(0.02), beta=T(0.0), delta=T(0.1))
+        pn.foreach_point_neighbor(closure_p, yl, yl, nhs)
         ref_dv = dv.cpu().double()
         got_dv = hdv[(e2e_steps - 1) % 2].double()
         # same kernels, but the order of the records inside a cell (atomic arrival order of the
@@ -667,11 +677,11 @@ def gpu_arm(args):
     # one step alone (latency): submit + wait
     t0 = time.perf_counter()
     for s in range(3):
-        stepper.submit(hcoords[s % 2], hv, hp, hdv[0], closure)
+        stepper.submit(hcoords[s % 2], hv, None, hdv[0], closure)
         stepper.wait()
     e2e_serial_ms = 1e3 * (time.perf_counter() - t0) / 3
     del stepper
-    h2d = int(hA.numel() * 4 + hv.numel() * 4 + hp.numel() * 4)
+    h2d = int(hA.numel() * 4 + hv.numel() * 4)
     d2h = int(hdv[0].numel() * 4)
 
     # ---- roofline -----------------------------------------------------------------------------
@@ -722,10 +732,13 @@ def gpu_arm(args):
                 "api": "pnb200.HostStepper.submit/wait = pnb_hoststep_wcsph_submit / pnb_hoststep_wait "
                        "(include/pnb200.h): host pointers in, host pointer out",
                 "mode": "pipelined inside the library: 3 streams, double-buffered device arrays, every "
-                        "step copies its inputs from pinned host memory and its dv back (wall clock "
-                        "around the submits and the final wait)",
+                        "step copies its inputs (coordinates, v) from pinned host memory and its dv back; "
+                        "the pressure is computed on the device from the density row of v "
+                        "(compute_pressure!, as TrixiParticles does before interact!); wall clock around "
+                        "the submits and the final wait",
                 "serial_ms_per_step": e2e_serial_ms,
                 "serial_value": P_avg / (e2e_serial_ms * 1e-3),
+                "host_ms_per_submit": e2e_host,
                 "matches_resident_path": e2e_same},
         "roofline": {"bound": "hbm", "kernel": "k_sweep_flat<3,false,WcsphClT<false>,false>", "achieved": ach,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,

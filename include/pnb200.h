@@ -406,6 +406,14 @@ pnb_status pnb_hoststep_create(pnb_grid *g, int64_t n, pnb_hoststep **out);
 pnb_status pnb_hoststep_wcsph_submit(pnb_hoststep *h, const float *y_host, const float *v_host,
                                      const float *mass_host, const float *pressure_host,
                                      const pnb_wcsph_params *params, float *dv_host);
+/* StateEquationCole of the system: afterwards pressure_host may be NULL in a submit and the
+ * pressure is computed on the device from the density row of v (compute_pressure!,
+ * benchmarks/smoothed_particle_hydrodynamics.jl:64-69, 99), saving its host-to-device copy. */
+pnb_status pnb_hoststep_set_state_equation(pnb_hoststep *h, float sound_speed, float reference_density,
+                                           float exponent, float background_pressure);
+/* host seconds spent inside the submits so far: {H2D enqueue, wait for the previous step, update!
+ * enqueue, interact! enqueue, D2H enqueue}; steps = number of submits (diagnostics of the pipeline) */
+pnb_status pnb_hoststep_host_times(const pnb_hoststep *h, double *out5, int64_t *steps);
 pnb_status pnb_hoststep_wait(pnb_hoststep *h);
 void pnb_hoststep_destroy(pnb_hoststep *h);
 

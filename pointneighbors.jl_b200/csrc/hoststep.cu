@@ -16,6 +16,7 @@
 // stream-ordered build makes the library rebuild the cell list, repeat the sweep and the D2H),
 // then enqueues the kernels and the D2H of step s.  Host buffers should be pinned
 // (pnb_malloc_host) -- pageable memory works but serialises the copies.
+#include <chrono>
 #include <cstring>
 
 #include "grid.cuh"
@@ -32,6 +33,9 @@ struct pnb_hoststep {
     bool pending[2];         // kernels of buffer b enqueued, not settled yet
     pnb_wcsph_params prm[2];
     float *dv_host[2];
+    double host_s[5];        // host seconds spent in submit: H2D enqueue / settle / update! enqueue / interact! enqueue / D2H enqueue
+    bool have_eos;           // pressure computed on the device (compute_pressure!) instead of copied
+    float eos_c, eos_rho0, eos_exp, eos_bg;
 };
 
 using namespace pnb;
@@ -96,6 +100,24 @@ extern "C" pnb_status pnb_hoststep_create(pnb_grid *g, int64_t n, pnb_hoststep *
     return PNB_OK;
 }
 
+// StateEquationCole of the system (benchmarks/smoothed_particle_hydrodynamics.jl:64-69): with it a
+// submit may pass pressure_host = NULL and the pressure is computed on the device from the density
+// row of v, like TrixiParticles.compute_pressure! (:99) does before interact! -- in the reference's
+// flow the pressure is derived device state, not a host input.
+extern "C" pnb_status pnb_hoststep_set_state_equation(pnb_hoststep *h, float sound_speed,
+                                                      float reference_density, float exponent,
+                                                      float background_pressure)
+{
+    if (!h) { set_error("handle is NULL"); return PNB_ERR_ARG; }
+    if (!(exponent > 0.0f) || !(reference_density > 0.0f)) {
+        set_error("state equation: exponent and reference_density must be positive");
+        return PNB_ERR_ARG;
+    }
+    h->have_eos = true;
+    h->eos_c = sound_speed; h->eos_rho0 = reference_density; h->eos_exp = exponent; h->eos_bg = background_pressure;
+    return PNB_OK;
+}
+
 // settle the kernels of buffer b: error word, repeat after a bucket overflow
 static pnb_status hoststep_settle(pnb_hoststep *h, int b)
 {
@@ -121,18 +143,25 @@ extern "C" pnb_status pnb_hoststep_wcsph_submit(pnb_hoststep *h, const float *y_
                                                 const float *pressure_host,
                                                 const pnb_wcsph_params *params, float *dv_host)
 {
-    if (!h || !y_host || !v_host || !pressure_host || !params || !dv_host) {
+    if (!h || !y_host || !v_host || !params || !dv_host) {
         set_error("pnb_hoststep_wcsph_submit: NULL argument");
+        return PNB_ERR_ARG;
+    }
+    if (!pressure_host && !h->have_eos) {
+        set_error("pressure_host is NULL and no state equation was set (pnb_hoststep_set_state_equation)");
         return PNB_ERR_ARG;
     }
     if (!mass_host && !h->have_mass) { set_error("mass_host is NULL and no mass was given before"); return PNB_ERR_ARG; }
     const int b = (int)(h->steps & 1);
     const size_t nn = (size_t)h->n;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     // ---- inputs of this step (buffer b is free once the kernels of step s - 2 are done) ----
     HS_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[b], 0));
     HS_CUDA(cudaMemcpyAsync(h->y[b], y_host, sizeof(float) * nn * h->nd, cudaMemcpyHostToDevice, h->s_in));
     HS_CUDA(cudaMemcpyAsync(h->v[b], v_host, sizeof(float) * nn * (h->nd + 1), cudaMemcpyHostToDevice, h->s_in));
-    HS_CUDA(cudaMemcpyAsync(h->p[b], pressure_host, sizeof(float) * nn, cudaMemcpyHostToDevice, h->s_in));
+    if (pressure_host)
+        HS_CUDA(cudaMemcpyAsync(h->p[b], pressure_host, sizeof(float) * nn, cudaMemcpyHostToDevice, h->s_in));
     if (mass_host) {
         // the mass array is shared by both buffers: the kernels of step s - 1 may still read it
         HS_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[b ^ 1], 0));
@@ -140,14 +169,26 @@ extern "C" pnb_status pnb_hoststep_wcsph_submit(pnb_hoststep *h, const float *y_
         h->have_mass = true;
     }
     HS_CUDA(cudaEventRecord(h->ev_in[b], h->s_in));
+    double t1 = now();
+    h->host_s[0] += t1 - t0;
     // ---- settle the previous step (its kernels overlap the copies just enqueued) ------------
     pnb_status st = hoststep_settle(h, b ^ 1);
     if (st != PNB_OK) return st;
+    t0 = now();
+    h->host_s[1] += t0 - t1;
     // ---- kernels of this step -----------------------------------------------------------------
     HS_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_in[b], 0));
     HS_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_out[b], 0));    // dv[b] of step s - 2 has left
+    if (!pressure_host) {
+        st = pnb_wcsph_compute_pressure_f32(h->nd, h->n, h->v[b], h->eos_c, h->eos_rho0, h->eos_exp, h->eos_bg,
+                                            h->p[b], h->s_cmp);
+        if (st != PNB_OK) return st;
+    }
     st = pnb_grid_build_async_f32(h->g, h->y[b], h->n, h->s_cmp);
     if (st != PNB_OK) return st;
+    t1 = now();
+    h->host_s[2] += t1 - t0;
+    t0 = t1;
     st = pnb_wcsph_interact_async_f32(h->g, h->y[b], h->n, h->v[b], h->mass, h->p[b], params, h->dv[b],
                                       h->s_cmp);
     if (st != PNB_OK) return st;
@@ -155,12 +196,26 @@ extern "C" pnb_status pnb_hoststep_wcsph_submit(pnb_hoststep *h, const float *y_
     h->pending[b] = true;
     h->prm[b] = *params;
     h->dv_host[b] = dv_host;
+    t1 = now();
+    h->host_s[3] += t1 - t0;
     // ---- result ------------------------------------------------------------------------------
     HS_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_cmp[b], 0));
     HS_CUDA(cudaMemcpyAsync(dv_host, h->dv[b], sizeof(float) * nn * (h->nd + 1), cudaMemcpyDeviceToHost,
                             h->s_out));
     HS_CUDA(cudaEventRecord(h->ev_out[b], h->s_out));
+    h->host_s[4] += now() - t1;
     h->steps++;
+    return PNB_OK;
+}
+
+// host seconds spent inside pnb_hoststep_wcsph_submit since the creation, by part: enqueueing the
+// H2D copies / waiting for the previous step (settle) / enqueueing update! / enqueueing interact! /
+// enqueueing the D2H copy
+extern "C" pnb_status pnb_hoststep_host_times(const pnb_hoststep *h, double *out5, int64_t *steps)
+{
+    if (!h || !out5) { set_error("NULL argument"); return PNB_ERR_ARG; }
+    for (int k = 0; k < 5; k++) out5[k] = h->host_s[k];
+    if (steps) *steps = h->steps;
     return PNB_OK;
 }
 

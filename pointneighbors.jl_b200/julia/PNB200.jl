@@ -433,14 +433,26 @@ mutable struct HostStepper
         return s
     end
 end
-function submit!(s::HostStepper, y::Matrix{Float32}, v::Matrix{Float32}, pressure::Vector{Float32},
-                 dv::Matrix{Float32}, params::WcsphParams; mass::Union{Nothing, Vector{Float32}} = nothing)
+# pressure === nothing: computed on the device from the density row of v (compute_pressure!);
+# needs set_state_equation! first
+function submit!(s::HostStepper, y::Matrix{Float32}, v::Matrix{Float32},
+                 pressure::Union{Nothing, Vector{Float32}}, dv::Matrix{Float32}, params::WcsphParams;
+                 mass::Union{Nothing, Vector{Float32}} = nothing)
     push!(s.keep, (y, v, pressure, dv, mass)); length(s.keep) > 3 && popfirst!(s.keep)
     prm = Ref(params)
     check(ccall((:pnb_hoststep_wcsph_submit, libpnb200), Cint,
                 (Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ref{WcsphParams},
                  Ptr{Cfloat}),
-                s.handle, y, v, isnothing(mass) ? C_NULL : mass, pressure, prm, dv))
+                s.handle, y, v, isnothing(mass) ? C_NULL : mass,
+                isnothing(pressure) ? C_NULL : pressure, prm, dv))
+    return s
+end
+# StateEquationCole of the system (benchmarks/smoothed_particle_hydrodynamics.jl:64-69)
+function set_state_equation!(s::HostStepper; sound_speed, reference_density, exponent = 1,
+                             background_pressure = 0)
+    check(ccall((:pnb_hoststep_set_state_equation, libpnb200), Cint,
+                (Ptr{Cvoid}, Cfloat, Cfloat, Cfloat, Cfloat),
+                s.handle, sound_speed, reference_density, exponent, background_pressure))
     return s
 end
 Base.wait(s::HostStepper) = (check(ccall((:pnb_hoststep_wait, libpnb200), Cint, (Ptr{Cvoid},), s.handle)); s)

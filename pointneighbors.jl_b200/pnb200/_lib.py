@@ -112,6 +112,8 @@ SIGNATURES = {
     "pnb_hoststep_create": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
     "pnb_hoststep_wcsph_submit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(WcsphParams), _vp]),
     "pnb_hoststep_wait": (C.c_int, [_vp]),
+    "pnb_hoststep_set_state_equation": (C.c_int, [_vp, _f32, _f32, _f32, _f32]),
+    "pnb_hoststep_host_times": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pnb_hoststep_destroy": (None, [_vp]),
     "pnb_grid_append_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "pnb_wcsph_interact_layers_async_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp,

@@ -660,7 +660,7 @@ class HostStepper:
 
         stepper = HostStepper(nhs, n_points)
         stepper.submit(y_host, v_host, pressure_host, dv_host, params, mass_host=mass_host)
-        ...
+        ...                       # pressure_host=None after set_state_equation(...): computed on the device
         stepper.wait()            # every dv_host passed so far is complete
 
     Host arrays: contiguous float32 numpy arrays or CPU torch tensors (pin them for overlap)."""
@@ -687,6 +687,14 @@ class HostStepper:
             raise TypeError(f"{what}: contiguous float32 array with {n_elems} elements expected")
         return a.ctypes.data
 
+    def set_state_equation(self, *, sound_speed, reference_density, exponent=1.0, background_pressure=0.0):
+        """StateEquationCole of the system: `submit(..., pressure_host=None, ...)` then computes the
+        pressure on the device (compute_pressure!) instead of copying it from the host."""
+        check(_lib.lib().pnb_hoststep_set_state_equation(
+            self._h, np.float32(sound_speed), np.float32(reference_density), np.float32(exponent),
+            np.float32(background_pressure)))
+        return self
+
     def submit(self, y_host, v_host, pressure_host, dv_host, params, mass_host=None):
         nd = self.nhs._ndims
         n = self.n
@@ -695,11 +703,26 @@ class HostStepper:
         check(_lib.lib().pnb_hoststep_wcsph_submit(
             self._h, self._hptr(y_host, n * nd, "y_host"), self._hptr(v_host, n * (nd + 1), "v_host"),
             None if mass_host is None else self._hptr(mass_host, n, "mass_host"),
-            self._hptr(pressure_host, n, "pressure_host"), C.byref(prm),
+            None if pressure_host is None else self._hptr(pressure_host, n, "pressure_host"), C.byref(prm),
             self._hptr(dv_host, n * (nd + 1), "dv_host")))
 
     def wait(self):
         check(_lib.lib().pnb_hoststep_wait(self._h))
+
+    def host_times(self, since=None):
+        """Host milliseconds spent inside the submits {enqueueing the H2D copies, waiting for the
+        previous step, enqueueing update!, enqueueing interact!, enqueueing the D2H copy} and the number of submits,
+        since the creation -- or, with since = an earlier result, per submit since then."""
+        out, steps = (C.c_double * 5)(), C.c_int64()
+        check(_lib.lib().pnb_hoststep_host_times(self._h, out, C.byref(steps)))
+        names = ("h2d_enqueue_ms", "settle_wait_ms", "update_enqueue_ms", "interact_enqueue_ms",
+                 "d2h_enqueue_ms")
+        tot = dict(zip(names, (1e3 * v for v in out)))
+        tot["submits"] = int(steps.value)
+        if since is None:
+            return tot
+        k = max(tot["submits"] - since["submits"], 1)
+        return {nm: (tot[nm] - since[nm]) / k for nm in names}
 
     def __del__(self):
         h = getattr(self, "_h", None)

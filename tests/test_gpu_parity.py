@@ -1314,3 +1314,46 @@ def test_stream_ordered_update(pn, oracle):
     pn.update_(nhs, x3, x3, points_moving=(True, True), blocking=False)
     with pytest.raises(pn.PointNeighborsError, match="outside the domain bounds"):
         pn.check_(nhs)
+
+
+def test_host_stepper(pn, oracle):
+    """pnb200.HostStepper (pnb_hoststep_*): the WCSPH step from HOST buffers, pipelined inside the
+    library.  Every submitted step's dv equals the oracle's (1e-5 of sum |term|), with the pressure
+    copied from the host and with the pressure computed on the device from the state equation
+    (compute_pressure!, oracle: pno_wcsph_compute_pressure); a point outside the grid is reported
+    by the call that settles its step."""
+    c0, r, mn, mx = pn.benchmark_cloud((18, 20, 16), seed=5)
+    n = len(c0)
+    nhs = make_grid(pn, 3, r, mn, mx, n_points=n)
+    x0 = dev(c0)
+    pn.initialize_(nhs, x0, x0)
+    og = oracle.Grid(3, r, mn, mx)
+    rng = np.random.default_rng(9)
+    v, mass, pressure, kw = _wcsph_inputs(pn, c0, r, 3)
+    f = pn.WCSPHInteract(None, None, None, None, None, None, None, **kw)
+    stepper = pn.HostStepper(nhs, n)
+    clouds, outs = [], []
+    for s in range(5):
+        c = np.clip(c0 + np.float32(0.1) * r * rng.standard_normal(c0.shape).astype(np.float32), mn, mx)
+        clouds.append(np.ascontiguousarray(c, np.float32))
+        outs.append(np.full((n, 4), np.nan, np.float32))
+    with pytest.raises(pn.ArgumentError, match="state equation"):
+        stepper.submit(clouds[0], v, None, outs[0], f, mass_host=mass)
+    for s in range(3):                       # pressure from the host
+        stepper.submit(clouds[s], v, pressure, outs[s], f, mass_host=mass if s == 0 else None)
+    stepper.set_state_equation(sound_speed=10.0, reference_density=1000.0)
+    for s in range(3, 5):                    # pressure computed on the device
+        stepper.submit(clouds[s], v, None, outs[s], f)
+    stepper.wait()
+    p_eos = oracle.wcsph_compute_pressure(v, 10.0, 1000.0)
+    for s in range(5):
+        og.build(clouds[s])
+        p = pressure if s < 3 else p_eos
+        _, ref64, refabs = og.wcsph(clouds[s], clouds[s], v, v, mass, mass, p, p, f.params_array(), wide=True)
+        assert np.all(np.abs(outs[s] - ref64) <= 1e-5 * refabs + 1e-30), s
+    # a point outside the grid: reported when its step is settled
+    bad = clouds[0].copy()
+    bad[3] = mx + np.float32(4.0) * r
+    stepper.submit(bad, v, pressure, outs[0], f)
+    with pytest.raises(pn.PointNeighborsError, match="outside the domain bounds"):
+        stepper.wait()
