@@ -360,6 +360,10 @@ class SlabNeighborhoodSearch:
 # ---------------------------------------------------------------------------------------------
 # row exchange over NVLink peer memory (csrc/link.cu)
 # ---------------------------------------------------------------------------------------------
+class LinkUnavailable(RuntimeError):
+    """The peer-memory link could not be set up on some rank (raised on every rank)."""
+
+
 class SlabLink:
     """Receive area of this rank + the mapped areas of rank - 1 / rank + 1 (cudaIpc).  The handles
     travel once through torch.distributed (all_gather of 64 bytes); afterwards a step's exchange is
@@ -375,9 +379,18 @@ class SlabLink:
         c = torch.tensor([self.cap], dtype=torch.int64, device=device)
         dist.all_reduce(c, op=dist.ReduceOp.MAX, group=exchange.group)
         self.cap = int(c.item())
-        check(L.pnb_slab_link_create(self.cap, self.width, C.byref(self.handle)))
+        # every collective below is executed by every rank whatever happens locally; a rank that
+        # cannot create, export or map a receive area (cudaIpc unavailable: no peer access, a
+        # container without shared IPC namespace) makes ALL ranks raise LinkUnavailable together
+        err = None
         blob = (C.c_ubyte * 64)()
-        check(L.pnb_slab_link_export(self.handle, blob))
+        try:
+            if os.environ.get("PNB_SLAB_LINK_FAIL_RANK", "") == str(exchange.rank):     # test hook
+                raise RuntimeError("PNB_SLAB_LINK_FAIL_RANK")
+            check(L.pnb_slab_link_create(self.cap, self.width, C.byref(self.handle)))
+            check(L.pnb_slab_link_export(self.handle, blob))
+        except Exception as exc:        # noqa: BLE001 -- reported below, on every rank
+            err = exc
         mine = torch.tensor(list(blob), dtype=torch.uint8, device=device)
         every = [torch.zeros_like(mine) for _ in range(exchange.world)]
         dist.all_gather(every, mine, group=exchange.group)
@@ -388,8 +401,16 @@ class SlabLink:
                 return None
             return (C.c_ubyte * 64)(*every[k].cpu().tolist())
 
-        down, up = raw(r - 1), raw(r + 1)
-        check(L.pnb_slab_link_connect(self.handle, down, up))
+        if err is None:
+            try:
+                check(L.pnb_slab_link_connect(self.handle, raw(r - 1), raw(r + 1)))
+            except Exception as exc:    # noqa: BLE001
+                err = exc
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int64, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=exchange.group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise LinkUnavailable(str(err) if err is not None else "a neighbouring rank could not map the link")
         self.seq = 0
         self.leave_idx = torch.empty(2 * self.cap, dtype=torch.int32, device=device)
         dist.barrier(group=exchange.group)
@@ -445,6 +466,7 @@ class OverlappedWCSPHStep:
         self.counters = None
         self.cnt_host = None
         self.link = None
+        self.link_error = None
         self.last = {}
 
     def _table(self, arrs):
@@ -510,7 +532,17 @@ class OverlappedWCSPHStep:
             #      on the side stream (csrc/link.cu), enqueued before anything else of the step ------
             if self.link is None:
                 layers = max(ex.z_hi - ex.z_lo + 1, 1)
-                self.link = SlabLink(ex, max(self.LINK_LAYERS * n // layers, 1 << 16), W, dev)
+                try:
+                    self.link = SlabLink(ex, max(self.LINK_LAYERS * n // layers, 1 << 16), W, dev)
+                except LinkUnavailable as exc:
+                    # no peer mapping on this machine: the same rows travel through NCCL instead
+                    # (every rank takes this branch together); said loudly, and in bench.py's line
+                    import warnings
+                    warnings.warn(f"pnb200: peer-memory link unavailable ({exc}); exchanging through NCCL")
+                    self.EXCHANGE = "nccl"
+                    self.link_error = str(exc)
+                    use_link = False
+        if use_link:
             link = self.link
             link.seq += 1
             tab = self._table(arrays)
@@ -960,7 +992,9 @@ def bench_multi_gpu(args, rank, world, dev, metric, unit):
                        "exchange": ("none (one slab)" if world == 1 else
                                     "NVLink peer memory: one kernel classifies, packs and stores the rows into the "
                                     "neighbour's buffer (csrc/link.cu)" if stepper.EXCHANGE == "p2p"
-                                    else "NCCL send/recv (counts, then rows)"),
+                                    else "NCCL send/recv (counts, then rows)"
+                                    + (f" -- peer-memory link unavailable: {stepper.link_error}"
+                                       if stepper.link_error else "")),
                        "particles_total": int(tsum[2]), "search_radius": float(r),
                        "velocities": "zero (reference benchmark)",
                        "ghost_points_per_rank_max": int(tmax[4]),

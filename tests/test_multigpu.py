@@ -139,6 +139,17 @@ def test_two_gpu_slabs_match_oracle(tmp_path):
     assert (tmp_path / "ok").exists()
 
 
+def test_two_gpu_link_unavailable_falls_back_to_nccl(tmp_path, monkeypatch):
+    """A rank that cannot set up the peer-memory link makes ALL ranks exchange through NCCL (a
+    warning, no hang, same results)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    monkeypatch.setenv("PNB_SLAB_LINK_FAIL_RANK", "1")
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
 def test_four_gpu_slabs_match_oracle(tmp_path):
     """Interior ranks exchange with two neighbours (both directions of pnb_slab_pack/unpack)."""
     if torch.cuda.device_count() < 4:
