@@ -1,5 +1,6 @@
 """Multi-GPU slab decomposition of the grid search: one process per GPU, one ghost cell layer
-exchanged per step over torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
+exchanged per step -- by kernels that store into the neighbouring GPU's memory (csrc/link.cu, the
+overlapped step below) or over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 
 There is no counterpart in the reference (single device).  Design:
 
@@ -425,21 +426,27 @@ class SlabLink:
 # the overlapped WCSPH step of one rank (CUDA only)
 # ---------------------------------------------------------------------------------------------
 class OverlappedWCSPHStep:
-    """update! + WCSPH interact! of one slab with the ghost exchange hidden behind the sweep of the
-    interior cell layers:
+    """update! + WCSPH interact! of one slab with the migrant + ghost exchange off the critical path
+    (DESIGN.md 6).  Default (MODE "gather", EXCHANGE "p2p"):
 
-        pack the boundary rows (pnb_slab_pack_f32)
-        side stream : NCCL send/recv with both neighbours (counts, then rows)
-        main stream : stream-ordered update! of the OWNED points, gather + sweep of the interior
-                      layers [z_lo + 2, z_hi - 2]        <- runs while the rows travel
-        main stream : wait for the rows, append them to the arrays (pnb_slab_append_f32) and to
-                      the cell list (pnb_grid_append_f32), gather + sweep of the boundary layers
-        check, then compaction (pnb_slab_compact_f32): leavers out, migrants in
+        main : pnb_slab_link_send -- one kernel classifies the owned points, packs the rows of the
+               boundary layer / the leavers and stores them into the neighbours' memory (NVLink)
+        main : stream-ordered update! of the OWNED points, payload gather of the interior layers
+                                                          <- the neighbours' rows arrive meanwhile
+        side : pnb_slab_link_recv (waits for both neighbours' flags; the host waits for this only)
+        main : append the rows to the arrays (pnb_slab_append_strided_f32) and to the cell list
+               (pnb_grid_append_f32), payload gather of the boundary layers, ONE sweep of all
+               owned layers
+        host : waits for an event behind the append (not for the sweep), checks the error word,
+               enqueues the compaction (pnb_slab_compact_f32): leavers out, migrants in
 
-    Only the owned layers are swept (the ghosts are candidates, never query points).  The first
-    step of a search (no bucket capacity known yet) and steps whose update! overflowed a bucket or
-    received a migrant deeper than one layer inside the slab run the same sequence without the
-    overlap.  Results: dv[:n_own_new] belongs to arrays[k][:n_own_new]."""
+    MODE "split" hides the exchange behind a separate sweep of the interior layers instead (two
+    sweep launches); EXCHANGE "nccl" sends counts, then rows, through torch.distributed.  Only the
+    owned layers are swept (the ghosts are candidates, never query points).  The first step of a
+    search (no bucket capacity known yet) and steps whose update! overflowed a bucket or received a
+    migrant deeper than DEPTH layers inside the slab run the same sequence without the overlap.
+    Results: dv[:n_own_new] belongs to arrays[k][:n_own_new]; the sweep may still be running when
+    step() returns (stream-ordered: use the arrays on the current stream, or synchronise)."""
 
     DEPTH = 2          # boundary layers per side that wait for the exchange
     RESERVE_CTAS = 2   # SMs the interior sweep leaves to the NCCL kernels (MODE "split")
