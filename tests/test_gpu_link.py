@@ -151,3 +151,49 @@ def test_link_errors(pn):
         assert list(cnts) == [0, 0, 0, 0, 0]
     finally:
         L.pnb_slab_link_destroy(h)
+
+
+def test_link_capacity_exceeded(pn):
+    """A message larger than the link capacity: nothing is written behind the buffer (the rows that
+    do not fit are dropped) and BOTH sides get PNB_ERR_LIST_FULL from the receive call."""
+    from pnb200 import _lib
+    from pnb200.slabs import SlabExchange
+    L = _lib.lib()
+    T = np.float32
+    rng = np.random.default_rng(2)
+    r = T(0.1)
+    mn, mx = np.zeros(3, T), np.ones(3, T)
+    exs = [SlabExchange(3, r, mn, mx, k, 2) for k in range(2)]
+    pts = rng.random((20000, 3)).astype(T)
+    cap = 64                                      # far fewer rows than a boundary layer holds
+    links = []
+    for _ in range(2):
+        h = C.c_void_p()
+        _lib.check(L.pnb_slab_link_create(cap, 3, C.byref(h)))
+        links.append(h)
+    _lib.check(L.pnb_slab_link_connect_local(links[0], None, links[1]))
+    _lib.check(L.pnb_slab_link_connect_local(links[1], links[0], None))
+    try:
+        keep = []
+        for k in range(2):
+            t = torch.as_tensor(pts, device="cuda")
+            own = t[exs[k].owned_mask(t)].contiguous()
+            keep.append(own)
+            tab = _lib.SlabArrays()
+            tab.ptr[0], tab.width[0], tab.n_arrays = own.data_ptr(), 3, 1
+            leave = torch.empty(2 * cap, dtype=torch.int32, device="cuda")
+            keep.append(leave)
+            torch.cuda.synchronize()
+            _lib.check(L.pnb_slab_link_send(links[k], C.byref(tab), own.shape[0], 3, T(exs[k].padded_min[-1]), r,
+                                            exs[k].z_lo, exs[k].z_hi, leave.data_ptr(), 1, None))
+        for k in range(2):
+            p0, p1 = C.c_void_p(), C.c_void_p()
+            cnts = (C.c_int64 * 5)()
+            st = L.pnb_slab_link_recv(links[k], 1, C.byref(p0), C.byref(p1), cnts, None)
+            assert st == _lib.PNB_ERR_LIST_FULL, st
+            assert b"capacity" in L.pnb_last_error()
+            assert max(cnts[0], cnts[1]) > cap and max(cnts[2], cnts[3]) > cap
+    finally:
+        torch.cuda.synchronize()
+        for h in links:
+            L.pnb_slab_link_destroy(h)
