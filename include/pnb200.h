@@ -179,7 +179,7 @@ pnb_status pnb_slab_compact_f32(const pnb_slab_arrays *arrays, int64_t n_own, in
  *     stream; rows_down / rows_up point into this rank's receive area (valid until step seq + 2 is
  *     received; rows are pnb_slab_link_row_stride() floats apart, the width rounded up to 4), counts = {n_from_down, n_from_up, n_sent_down, n_sent_up, n_leave}.
  *     PNB_ERR_LIST_FULL if a message exceeded cap_rows, PNB_ERR_STATE if a neighbour did not
- *     answer within 20 s. */
+ *     answer within the time limit (pnb_slab_link_set_timeout, default 120 s). */
 typedef struct pnb_slab_link pnb_slab_link;
 pnb_status pnb_slab_link_create(int64_t cap_rows, int width, pnb_slab_link **out);
 pnb_status pnb_slab_link_export(pnb_slab_link *l, void *handle_out);
@@ -191,6 +191,7 @@ pnb_status pnb_slab_link_send(pnb_slab_link *l, const pnb_slab_arrays *arrays, i
                               int32_t *leave_idx, uint64_t seq, void *stream);
 pnb_status pnb_slab_link_recv(pnb_slab_link *l, uint64_t seq, const float **rows_down,
                               const float **rows_up, int64_t *counts, void *stream);
+pnb_status pnb_slab_link_set_timeout(pnb_slab_link *l, double seconds);   /* default 120 */
 int pnb_slab_link_row_stride(const pnb_slab_link *l);
 void pnb_slab_link_destroy(pnb_slab_link *l);
 

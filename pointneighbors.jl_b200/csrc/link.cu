@@ -43,6 +43,7 @@ struct pnb_slab_link {
     long long *d_out;
     uint64_t seq_sent, seq_recv;
     bool peer_local[2];            // connected with pnb_slab_link_connect_local (same process)
+    long long timeout_ns;          // how long a receive waits for a neighbour (default 120 s)
 };
 
 static size_t link_flags_bytes() { return 4 * sizeof(LinkFlag); }
@@ -76,6 +77,7 @@ extern "C" pnb_status pnb_slab_link_create(int64_t cap_rows, int width, pnb_slab
     l->cap = cap_rows;
     l->width = width;
     l->stride = (width + 3) & ~3;
+    l->timeout_ns = 120LL * 1000 * 1000 * 1000;
     l->area_bytes = link_flags_bytes() + 4 * link_buf_bytes(l);
     cudaError_t e;
     if ((e = cudaMalloc(&l->area, l->area_bytes)) != cudaSuccess ||
@@ -89,6 +91,15 @@ extern "C" pnb_status pnb_slab_link_create(int64_t cap_rows, int width, pnb_slab
     }
     PNB_CUDA(cudaDeviceSynchronize());
     *out = l;
+    return PNB_OK;
+}
+
+// how long pnb_slab_link_recv lets the GPU wait for a neighbour before it gives up with
+// PNB_ERR_STATE instead of hanging (default 120 s)
+extern "C" pnb_status pnb_slab_link_set_timeout(pnb_slab_link *l, double seconds)
+{
+    if (!l || !(seconds > 0.0)) { set_error("link: positive timeout expected"); return PNB_ERR_ARG; }
+    l->timeout_ns = (long long)(seconds * 1e9);
     return PNB_OK;
 }
 
@@ -296,6 +307,7 @@ extern "C" pnb_status pnb_slab_link_send(pnb_slab_link *l, const pnb_slab_arrays
     int W = 0;
     for (int a = 0; a < arrays->n_arrays; a++) W += arrays->width[a];
     if (W != l->width) { set_error("link: row width %d, created for %d", W, l->width); return PNB_ERR_ARG; }
+    if (n < 0 || n > 0x7ffffff0LL) { set_error("link: 0 <= n < 2^31 points expected"); return PNB_ERR_ARG; }
     if (seq != l->seq_sent + 1) { set_error("link: step %llu sent after step %llu", (unsigned long long)seq, (unsigned long long)l->seq_sent); return PNB_ERR_STATE; }
     cudaStream_t s = (cudaStream_t)stream;
     const int par = (int)(seq & 1);
@@ -331,13 +343,17 @@ extern "C" pnb_status pnb_slab_link_recv(pnb_slab_link *l, uint64_t seq, const f
     const int par = (int)(seq & 1);
     k_link_wait<<<1, 1, 0, s>>>(l->peer[0] ? link_flag(l->area, 0, par) : nullptr,
                                 l->peer[1] ? link_flag(l->area, 1, par) : nullptr, (unsigned long long)seq,
-                                l->counts, l->d_out, 20LL * 1000 * 1000 * 1000);
+                                l->counts, l->d_out, l->timeout_ns);
     PNB_LAUNCHED();
     PNB_CUDA(cudaStreamSynchronize(s));
     l->seq_recv = seq;
     volatile long long *h = l->h_out;
     for (int k = 0; k < 5; k++) counts[k] = h[k];
-    if (h[5] != 0) { set_error("link: a neighbouring rank did not send step %llu within 20 s", (unsigned long long)seq); return PNB_ERR_STATE; }
+    if (h[5] != 0) {
+        set_error("link: a neighbouring rank did not send step %llu within %.0f s (pnb_slab_link_set_timeout)",
+                  (unsigned long long)seq, 1e-9 * (double)l->timeout_ns);
+        return PNB_ERR_STATE;
+    }
     if (counts[0] > l->cap || counts[1] > l->cap || counts[2] > l->cap || counts[3] > l->cap) {
         set_error("link: %lld / %lld rows received, %lld / %lld sent, capacity %lld rows: create the link "
                   "with a larger capacity", (long long)counts[0], (long long)counts[1], (long long)counts[2],

@@ -125,6 +125,7 @@ SIGNATURES = {
     "pnb_slab_append_strided_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, C.c_int, _f32, _f32, _i64, _i64,
                                               _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pnb_slab_link_row_stride": (C.c_int, [_vp]),
+    "pnb_slab_link_set_timeout": (C.c_int, [_vp, C.c_double]),
     "pnb_slab_compact_f32": (C.c_int, [C.POINTER(SlabArrays), _i64, _i64, _vp, _i64, _i64, _vp, _vp,
                                        _vp, _vp]),
     "pnb_slab_link_create": (C.c_int, [_i64, C.c_int, C.POINTER(_vp)]),

@@ -144,6 +144,8 @@ def test_link_errors(pn):
         assert L.pnb_slab_link_send(h, C.byref(tab), 100, 3, np.float32(0), np.float32(0.1), 2, 5,
                                     leave.data_ptr(), 2, None) != 0
         assert b"step" in L.pnb_last_error()
+        assert L.pnb_slab_link_set_timeout(h, C.c_double(-1.0)) != 0
+        _lib.check(L.pnb_slab_link_set_timeout(h, C.c_double(5.0)))
         # no neighbours: nothing is sent, nothing leaves
         _lib.check(L.pnb_slab_link_send(h, C.byref(tab), 100, 3, np.float32(0), np.float32(0.1), 2, 5,
                                         leave.data_ptr(), 1, None))
@@ -193,6 +195,41 @@ def test_link_capacity_exceeded(pn):
             assert st == _lib.PNB_ERR_LIST_FULL, st
             assert b"capacity" in L.pnb_last_error()
             assert max(cnts[0], cnts[1]) > cap and max(cnts[2], cnts[3]) > cap
+    finally:
+        torch.cuda.synchronize()
+        for h in links:
+            L.pnb_slab_link_destroy(h)
+
+
+def test_link_neighbour_timeout(pn):
+    """A neighbour that never publishes its step: the waiting kernel gives up after the time limit
+    and the receive call returns PNB_ERR_STATE -- the GPU is not left spinning."""
+    import time
+    from pnb200 import _lib
+    L = _lib.lib()
+    links = []
+    for _ in range(2):
+        h = C.c_void_p()
+        _lib.check(L.pnb_slab_link_create(1 << 10, 3, C.byref(h)))
+        links.append(h)
+    _lib.check(L.pnb_slab_link_connect_local(links[0], None, links[1]))
+    _lib.check(L.pnb_slab_link_connect_local(links[1], links[0], None))
+    try:
+        _lib.check(L.pnb_slab_link_set_timeout(links[0], C.c_double(0.3)))
+        y = torch.rand(500, 3, device="cuda")
+        tab = _lib.SlabArrays()
+        tab.ptr[0], tab.width[0], tab.n_arrays = y.data_ptr(), 3, 1
+        leave = torch.empty(2 << 10, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        _lib.check(L.pnb_slab_link_send(links[0], C.byref(tab), 500, 3, np.float32(0), np.float32(0.1), 2, 5,
+                                        leave.data_ptr(), 1, None))
+        p0, p1 = C.c_void_p(), C.c_void_p()
+        cnts = (C.c_int64 * 5)()
+        t0 = time.perf_counter()
+        st = L.pnb_slab_link_recv(links[0], 1, C.byref(p0), C.byref(p1), cnts, None)
+        dt = time.perf_counter() - t0
+        assert st == _lib.PNB_ERR_STATE and b"did not send step 1" in L.pnb_last_error()
+        assert 0.25 < dt < 5.0, dt
     finally:
         torch.cuda.synchronize()
         for h in links:
