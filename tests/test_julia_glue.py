@@ -119,3 +119,55 @@ def test_glue_covers_the_hot_path_entry_points():
                 "pnb_nlist_export_dvov", "pnb_tlsph_deformation_grad_f32", "pnb_malloc",
                 "pnb_memcpy_h2d", "pnb_memcpy_d2h", "pnb_last_error"):
         assert sym in called
+
+
+def _c_struct_fields(name):
+    """[(ctype, field), ...] of `typedef struct name { ... } name;` in the header"""
+    h = open(HDR).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    m = re.search(r"typedef\s+struct\s+" + name + r"\s*\{(.*?)\}\s*" + name + r"\s*;", h, flags=re.S)
+    assert m, name
+    out = []
+    for stmt in m.group(1).split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        ctype, names = stmt.split(None, 1)
+        out += [(ctype, n.strip()) for n in names.split(",")]
+    return out
+
+
+def _julia_struct_fields(name):
+    src = open(JL).read()
+    m = re.search(r"\bstruct\s+" + name + r"\b[^\n]*\n(.*?)\nend", src, flags=re.S)
+    assert m, name
+    out = []
+    for line in m.group(1).splitlines():
+        line = re.sub(r"#.*", "", line).strip()
+        if line:
+            f, t = [x.strip() for x in line.split("::")]
+            out.append((t, f))
+    return out
+
+
+def test_parameter_structs_have_the_same_layout():
+    """The by-reference parameter blocks: field order and scalar types of the C struct, the Julia
+    struct and the ctypes Structure of the Python mirror agree (a silent mismatch would shift
+    every physical parameter)."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "pointneighbors.jl_b200"))
+    from pnb200 import _lib
+    jl_of = {"float": "Cfloat", "double": "Cdouble", "int32_t": "Int32", "int": "Cint"}
+    ct_of = {"float": C.c_float, "double": C.c_double, "int32_t": C.c_int32, "int": C.c_int}
+    for cname, jname, pyname in (("pnb_wcsph_params", "WcsphParams", "WcsphParams"),
+                                 ("pnb_wcsph_params_f64", "WcsphParams64", "WcsphParams64"),
+                                 ("pnb_tlsph_params", "TlsphParams", "TlsphParams")):
+        cf = _c_struct_fields(cname)
+        jf = _julia_struct_fields(jname)
+        assert [f for _, f in cf] == [f for _, f in jf], (cname, cf, jf)
+        alias = {"Float32": "Cfloat", "Float64": "Cdouble", "Int32": "Int32", "Cint": "Cint"}
+        assert [jl_of[t] for t, _ in cf] == [alias.get(t, t) for t, _ in jf], (cname, cf, jf)
+        py = getattr(_lib, pyname)._fields_
+        assert [f for _, f in cf] == [f for f, _ in py], (cname, cf, py)
+        assert [ct_of[t] for t, _ in cf] == [t for _, t in py], (cname, cf, py)
