@@ -379,3 +379,33 @@ def test_tlsph_oracle_definitions():
     # compute_pressure!: Cole with exponent 1 is linear in the density
     v = np.concatenate([np.zeros((5, 3)), 1000 + np.arange(5)[:, None]], axis=1)
     assert np.allclose(po.wcsph_compute_pressure(v, 10.0, 1000.0, dtype=np.float64), 100.0 * np.arange(5))
+
+
+def test_ctypes_signatures_match_the_header(pn):
+    """Every entry of pnb200/_lib.py's SIGNATURES has the arity of its C declaration, pointers
+    where C has pointers, and scalars of the C width -- a stale binding (a parameter added in the
+    header only) would otherwise shift every following argument silently."""
+    import test_julia_glue as tj
+    decls = tj.header_decls()
+    scalar = {"int": (C.c_int,), "float": (C.c_float,), "double": (C.c_double,),
+              "int64_t": (C.c_int64, C.c_longlong, C.c_long), "int32_t": (C.c_int32, C.c_int),
+              "uint64_t": (C.c_uint64, C.c_ulonglong, C.c_ulong), "uint32_t": (C.c_uint32, C.c_uint)}
+    checked = 0
+    for name, (restype, argtypes) in pn._lib.SIGNATURES.items():
+        cret, cparams = decls[name]
+        assert len(argtypes) == len(cparams), f"{name}: {len(argtypes)} ctypes arguments, {len(cparams)} in C"
+        if cret == "void":
+            assert restype is None, name
+        elif cret in ("pnb_status", "int"):
+            assert restype is C.c_int, name
+        for k, (at, cp) in enumerate(zip(argtypes, cparams)):
+            is_ptr_c = "*" in cp
+            is_ptr_py = at is C.c_void_p or at is C.c_char_p or hasattr(at, "_type_") and \
+                isinstance(getattr(at, "_type_"), type)
+            if is_ptr_c:
+                assert is_ptr_py, f"{name} argument {k + 1}: C `{cp}` is a pointer, ctypes has {at}"
+            else:
+                base = cp.replace("const ", "").split()[0]
+                assert at in scalar[base], f"{name} argument {k + 1}: C `{cp}` vs ctypes {at}"
+            checked += 1
+    assert checked > 400
