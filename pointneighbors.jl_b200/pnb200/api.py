@@ -30,6 +30,7 @@ from ._lib import (ArgumentError, BoundsError, PointNeighborsError, TlsphParams,
 
 __all__ = [
     "foreach_neighbor", "foreach_neighbor_unsafe", "mapreduce_neighbor", "mapreduce_neighbor_unsafe",
+    "foreach_point_neighbor_unsafe", "initialize_grid_", "update_grid_", "default_backend", "B200Backend",
     "ArgumentError", "PointNeighborsError", "BoundsError",
     "ParallelUpdate", "SerialUpdate", "ParallelIncrementalUpdate", "SemiParallelUpdate",
     "SerialIncrementalUpdate", "DynamicVectorOfVectors",
@@ -1004,6 +1005,44 @@ def foreach_neighbor(f, system_coords, neighbor_coords, neighborhood_search, poi
 
 
 foreach_neighbor_unsafe = foreach_neighbor   # the bounds checks are host-side and cost nothing here
+
+
+def foreach_point_neighbor_unsafe(f, system_coords, neighbor_coords, neighborhood_search, **kw):
+    """foreach_point_neighbor_unsafe (src/neighborhood_search.jl:204-234): the reference skips the
+    bounds checks INSIDE its kernel; the explicit check of `points` before the loop stays (:226).
+    The device kernels here never index out of bounds on a search initialized with these arrays
+    (stencil cells outside the grid are reported, not read), so both names run the same code."""
+    return foreach_point_neighbor(f, system_coords, neighbor_coords, neighborhood_search, **kw)
+
+
+def initialize_grid_(neighborhood_search, y, *, parallelization_backend=None, eachindex_y=None):
+    """initialize_grid!(nhs, y; eachindex_y)  (src/nhs_grid.jl:227-281): the cell-list part of
+    initialize! (which only forwards to it, :220-225)."""
+    return initialize_(neighborhood_search, y, y, eachindex_y=eachindex_y)
+
+
+def update_grid_(neighborhood_search, y, *, parallelization_backend=None, eachindex_y=None):
+    """update_grid!(nhs, y; eachindex_y) of ParallelUpdate / SerialUpdate = a full rebuild
+    (src/nhs_grid.jl:470-477)."""
+    return update_(neighborhood_search, y, y, points_moving=(True, True), eachindex_y=eachindex_y)
+
+
+class B200Backend:
+    """What `default_backend(x)` returns for a CUDA tensor (src/util.jl:81-83 returns the
+    KernelAbstractions backend of a GPU array): a marker, there is one device code path."""
+
+    def __repr__(self):
+        return "B200Backend()"
+
+
+def default_backend(x):
+    """default_backend(x) (src/util.jl:81-83).  Host arrays have no backend here: the CPU thread
+    backends of the reference are out of scope and the library has no CPU path."""
+    torch = _torch()
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        return B200Backend()
+    raise ArgumentError("pnb200 has a device code path only: pass CUDA tensors (the reference's CPU "
+                        "thread backends are out of scope)")
 
 
 def mapreduce_neighbor(f, op, system_coords, neighbor_coords, neighborhood_search, point, *, init,

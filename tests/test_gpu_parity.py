@@ -1357,3 +1357,32 @@ def test_host_stepper(pn, oracle):
     stepper.submit(bad, v, pressure, outs[0], f)
     with pytest.raises(pn.PointNeighborsError, match="outside the domain bounds"):
         stepper.wait()
+
+
+def test_grid_level_calls_and_unsafe_variant(pn, oracle):
+    """initialize_grid! / update_grid! (src/nhs_grid.jl:227-281, 470-477) and
+    foreach_point_neighbor_unsafe (src/neighborhood_search.jl:204-234) of the host mirror: same
+    cell list and counts as initialize! / update! / foreach_point_neighbor and as the oracle."""
+    c, r, mn, mx = pn.benchmark_cloud((12, 10, 9), seed=4)
+    nhs = make_grid(pn, 3, r, mn, mx, n_points=len(c))
+    x = dev(c)
+    og = oracle.Grid(3, r, mn, mx)
+    assert repr(pn.default_backend(x)) == "B200Backend()"
+    pn.initialize_grid_(nhs, x)
+    og.build(c)
+    cs, cp = nhs.export_csr()
+    assert (cs.cpu().numpy() == og.cell_start).all() and (cp.cpu().numpy() == og.cell_points).all()
+    cnt = torch.zeros(len(c), dtype=torch.int64, device="cuda")
+    pn.foreach_point_neighbor_unsafe(pn.CountNeighbors(cnt), x, x, nhs)
+    assert (cnt.cpu().numpy() == og.count_neighbors(c, c)).all()
+    c2 = np.clip(c + np.float32(0.2) * r * np.random.default_rng(1).standard_normal(c.shape).astype(np.float32),
+                 mn, mx).astype(np.float32)
+    x2 = dev(c2)
+    pn.update_grid_(nhs, x2)
+    og.build(c2)
+    pn.foreach_point_neighbor_unsafe(pn.CountNeighbors(cnt), x2, x2, nhs, points=range(5, 50))
+    ref = og.count_neighbors(c2, c2)
+    got = cnt.cpu().numpy()
+    assert (got[5:50] == ref[5:50]).all() and got[:5].sum() == 0 and got[50:].sum() == 0
+    with pytest.raises(pn.BoundsError):
+        pn.foreach_point_neighbor_unsafe(pn.CountNeighbors(cnt), x2, x2, nhs, points=[len(c2)])

@@ -409,3 +409,21 @@ def test_ctypes_signatures_match_the_header(pn):
                 assert at in scalar[base], f"{name} argument {k + 1}: C `{cp}` vs ctypes {at}"
             checked += 1
     assert checked > 400
+
+
+def test_api_surface_mirrors_the_reference_exports(pn):
+    """Every name src/PointNeighbors.jl exports that is in scope (SURVEY.md sections 2 / 8) exists in
+    the host mirror (`!` -> trailing underscore); what is out of scope is absent, not stubbed."""
+    in_scope = ["foreach_point_neighbor", "foreach_point_neighbor_unsafe", "foreach_neighbor",
+                "foreach_neighbor_unsafe", "mapreduce_neighbor", "mapreduce_neighbor_unsafe",
+                "GridNeighborhoodSearch", "PrecomputedNeighborhoodSearch", "FullGridCellList",
+                "SpatialHashingCellList", "DynamicVectorOfVectors", "ParallelUpdate", "SemiParallelUpdate",
+                "SerialIncrementalUpdate", "SerialUpdate", "ParallelIncrementalUpdate", "requires_update",
+                "initialize_", "update_", "initialize_grid_", "update_grid_", "default_backend",
+                "PeriodicBox", "copy_neighborhood_search"]
+    for name in in_scope:
+        assert hasattr(pn, name), name
+    for name in ("TrivialNeighborhoodSearch", "DictionaryCellList", "PolyesterBackend", "SerialBackend"):
+        assert not hasattr(pn, name), name          # CPU-only parts of the reference
+    with pytest.raises(pn.ArgumentError):
+        pn.default_backend(np.zeros((3, 2), np.float32))
