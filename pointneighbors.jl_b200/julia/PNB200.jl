@@ -223,6 +223,19 @@ function update!(nhs::B200GridNeighborhoodSearch{NDIMS, T}, x::B200Array{T, 2},
     return initialize!(nhs, x, y; eachindex_y)
 end
 
+# initialize_grid! / update_grid!(nhs, y; eachindex_y)      src/nhs_grid.jl:227-281, 470-477
+# (the cell-list part of initialize! / update!; ParallelUpdate's update_grid! is a full rebuild)
+initialize_grid!(nhs::B200GridNeighborhoodSearch, y::B200Array; parallelization_backend = default_backend(y),
+                 eachindex_y = axes(y, 2)) = initialize!(nhs, y, y; eachindex_y)
+update_grid!(nhs::B200GridNeighborhoodSearch, y::B200Array; parallelization_backend = default_backend(y),
+             eachindex_y = axes(y, 2)) = initialize!(nhs, y, y; eachindex_y)
+
+# foreach_point_neighbor_unsafe      src/neighborhood_search.jl:204-234
+# (the reference skips the bounds checks inside its kernel; the device kernels here never index
+#  out of bounds on an initialized search, so both names run the same code)
+foreach_point_neighbor_unsafe(f, x::B200Array, y::B200Array, nhs; kwargs...) =
+    foreach_point_neighbor(f, x, y, nhs; kwargs...)
+
 # synchronise and raise what a blocking update! would have raised
 function check!(nhs::B200GridNeighborhoodSearch)
     check(ccall((:pnb_grid_check, libpnb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), nhs.handle, C_NULL))
