@@ -712,6 +712,9 @@ def gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling_note": "N = 1 is the headline configuration (BASELINE config 3, 254^3); --gpus N > 1 runs "
+                        "BASELINE config 5 (504^3) in STRONG scaling, whose one-GPU base line is "
+                        "configs['5_one_gpu'] of this line",
         "config": cfg,
         "workload_stats": {"cells": C_cells, "pairs_per_step": P_avg, "candidate_tests_per_step": K_avg,
                            "pairs_oracle_check": oracle_check, "git": git_head()},
